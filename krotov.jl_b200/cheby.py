@@ -1,0 +1,158 @@
+"""Host-side Chebyshev propagator settings: spectral envelope, control-range bookkeeping, coefficients.
+
+This is the part of QuantumPropagators' ``init_prop`` / ``reinit_prop!`` (called by the reference at
+``src/optimize.jl:251,306,324`` with Krotov's ``transform_control_ranges`` hook, ``:238-244``) that
+stays on the host: it runs once per sweep, never per time step, and its product -- per generator
+``E_min``, ``Delta`` and the coefficient vector -- is handed to the device through
+``krotov_set_cheby``.  Semantics restated from the published algorithm.
+"""
+from __future__ import annotations
+
+import numpy as np
+from scipy.special import jv
+
+__all__ = ["cheby_coeffs", "specrange", "transform_control_ranges", "ChebyDirection"]
+
+
+def cheby_coeffs(Delta, dt, limit=1e-12):
+    """Expansion coefficients of exp(-i H dt) in Chebyshev polynomials for spectral radius ``Delta``:
+    ``a_0 = J_0(alpha)``, ``a_n = 2 J_n(alpha)``, ``alpha = |Delta dt| / 2``, truncated at the first
+    ``|a_n| <= limit`` beyond ``n > alpha``."""
+    alpha = abs(0.5 * Delta * dt)
+    out = [float(jv(0, alpha))]
+    n = 1
+    while abs(out[-1]) > limit or n <= alpha:
+        out.append(2.0 * float(jv(n, alpha)))
+        n += 1
+    return np.asarray(out, np.float64)
+
+
+def specrange(G, method="auto"):
+    """``(E_min, E_max)`` of an operator.  ``diag``: exact eigenvalues (dense).  ``auto`` uses
+    ``diag`` up to dimension 512 and a Lanczos/Arnoldi estimate (scipy ``eigs``, widened by 5 %)
+    beyond; pass ``prop_E_min`` / ``prop_E_max`` to bypass it."""
+    G = np.asarray(G)
+    d = G.shape[0]
+    if method == "auto":
+        method = "diag" if d <= 512 else "arnoldi"
+    if method == "diag":
+        ev = np.linalg.eigvals(G)
+        return float(ev.real.min()), float(ev.real.max())
+    if method == "arnoldi":
+        from scipy.sparse.linalg import eigs
+
+        v0 = np.ones(d, np.complex128) / np.sqrt(d)
+        hi = eigs(G, k=1, which="LR", v0=v0, return_eigenvectors=False, tol=1e-4)[0].real
+        lo = eigs(G, k=1, which="SR", v0=v0, return_eigenvectors=False, tol=1e-4)[0].real
+        pad = 0.05 * (hi - lo)
+        return float(lo - pad), float(hi + pad)
+    raise ValueError(f"unknown specrange method {method!r}")
+
+
+def transform_control_ranges(c, eps_min, eps_max, check):
+    """Krotov's range hook (``src/optimize.jl:238-244``): a propagator's spectral envelope is
+    re-derived when twice the current amplitude range leaves the stored range, and then stored for
+    five times the current range."""
+    f = 2 if check else 5
+    return (min(eps_min, f * eps_min), max(eps_max, f * eps_max))
+
+
+class ChebyDirection:
+    """Settings of all propagators of one direction (they see the same pulses, so their control
+    ranges move in lock-step; the spectral envelope is per generator).
+
+    ``H0[g]``, ``Hc[g][l]`` are the terms of the generator the direction propagates with: the plain
+    generator forward, the ADJOINT generator backward (``src/workspace.jl:69,150-160``)."""
+
+    def __init__(self, H0, Hc, tlist, backward, pulses, *, limit=1e-12, specrange_buffer=0.01,
+                 specrange_method="auto", E_min=None, E_max=None):
+        self.H0, self.Hc = H0, Hc
+        self.tlist = np.asarray(tlist, np.float64)
+        self.backward = bool(backward)
+        self.limit = float(limit)
+        self.buffer = float(specrange_buffer)
+        self.method = specrange_method
+        self.manual = None if (E_min is None or E_max is None) else (float(E_min), float(E_max))
+        self.control_ranges = [(float(np.min(p)), float(np.max(p))) for p in pulses]
+        self.n_updates = 0
+        self._derive()
+
+    # -- spectral envelope (cheby_get_spectral_envelope + specrange_buffer) ----------------
+    def _evaluate(self, g, vals):
+        G = np.array(self.H0[g], np.complex128)
+        for l, Hl in enumerate(self.Hc[g]):
+            if Hl is not None:
+                G = G + vals[l] * Hl
+        return G
+
+    def _derive(self):
+        n_gen = len(self.H0)
+        self.E_min = np.empty(n_gen)
+        self.Delta = np.empty(n_gen)
+        lo = [r[0] for r in self.control_ranges]
+        hi = [r[1] for r in self.control_ranges]
+        for g in range(n_gen):
+            if self.manual is not None:
+                e_min, e_max = self.manual
+            else:
+                e_min, e_max = specrange(self._evaluate(g, hi), self.method)
+                e_min2, e_max2 = specrange(self._evaluate(g, lo), self.method)
+                e_min, e_max = min(e_min, e_min2), max(e_max, e_max2)
+            Delta = e_max - e_min
+            delta = self.buffer * Delta
+            self.E_min[g] = e_min - delta / 2
+            self.Delta[g] = Delta + delta
+        self._tabulate()
+
+    def _tabulate(self):
+        """dt classes and per-class coefficients, walking the grid in propagation order with the
+        propagator's rule: coefficients are re-derived only when the step differs from the one they
+        were derived for.  A class is a (exact step, step the coefficients belong to) pair: the
+        final phase e^{-i beta dt} uses the exact step."""
+        t = self.tlist
+        N_T = len(t) - 1
+        sign = -1.0 if self.backward else 1.0
+        cur = sign * (t[1] - t[0])
+        order = range(N_T - 1, -1, -1) if self.backward else range(N_T)
+        classes, key_to_class = [], {}
+        self.dt_class_of_step = np.zeros(N_T, np.int32)
+        for n in order:
+            dt = sign * (t[n + 1] - t[n])
+            if abs(dt - cur) > 1e-12 * max(1.0, abs(cur)):
+                cur = dt
+            key = (dt, cur)
+            if key not in key_to_class:
+                key_to_class[key] = len(classes)
+                classes.append(key)
+            self.dt_class_of_step[n] = key_to_class[key]
+        self.dt_of_class = np.array([k[0] for k in classes], np.float64)
+        self.coeffs = []
+        for g in range(len(self.H0)):
+            cache = {}
+            row = []
+            for (_, rep) in classes:
+                if rep not in cache:
+                    cache[rep] = cheby_coeffs(self.Delta[g], rep, self.limit)
+                row.append(cache[rep])
+            self.coeffs.append(row)
+
+    # -- reinit_prop! ------------------------------------------------------------------------
+    def reinit(self, pulses, transform=transform_control_ranges):
+        """Range check of ``reinit_prop!``; returns True when the envelope (hence the device tables)
+        changed."""
+        need = False
+        for l, p in enumerate(pulses):
+            lo, hi = float(np.min(p)), float(np.max(p))
+            c_lo, c_hi = transform(l, lo, hi, True)
+            o_lo, o_hi = self.control_ranges[l]
+            if c_lo < o_lo or c_hi > o_hi:
+                need = True
+        if need:
+            self.control_ranges = [transform(l, float(np.min(p)), float(np.max(p)), False)
+                                   for l, p in enumerate(pulses)]
+            self._derive()
+            self.n_updates += 1
+        return need
+
+    def push(self, engine, direction):
+        engine.set_cheby(direction, self.dt_class_of_step, self.dt_of_class, self.E_min, self.Delta, self.coeffs)

@@ -1,0 +1,29 @@
+// Dense-generator engine (FP64 DMMA complex GEMM per Chebyshev term) -- interface.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <complex>
+#include <string>
+#include <vector>
+
+#include "../../include/krotov_cuda.h"
+
+namespace kr {
+struct DenseEngine;
+DenseEngine *dense_create(int d, int N, int L, int N_T, int n_gen, const std::vector<std::complex<double>> &Hdense,
+                          const std::vector<int> &gen_of_traj, const double *psi0, const double *target, int store_fw,
+                          cudaStream_t stream, std::string &err);
+void dense_destroy(DenseEngine *e);
+void dense_info(DenseEngine *e, krotov_info *out);
+bool dense_set_cheby(DenseEngine *e, int direction, int ndtc, const std::vector<int> &dtc_of_step,
+                     const std::vector<double> &E_min, const std::vector<double> &Delta, const std::vector<int> &m,
+                     const std::vector<double> &coef, int m_max, const std::vector<std::complex<double>> &phase,
+                     std::string &err);
+bool dense_forward(DenseEngine *e, const double *d_eps, double2 *d_tau, long long &launches, std::string &err);
+bool dense_iterate(DenseEngine *e, const double *d_eps_old, double *d_eps_new, const double *d_alpha,
+                   const double *d_dt, double *d_ga, const double2 *d_chi_coef, double2 *d_tau, long long &launches,
+                   std::string &err);
+bool dense_set_chi(DenseEngine *e, const double *chi_host, std::string &err);
+bool dense_get_states(DenseEngine *e, double *states_host, std::string &err);
+bool dense_get_storage(DenseEngine *e, int which, int k, int n0, int n1, double *out_host, std::string &err);
+}  // namespace kr

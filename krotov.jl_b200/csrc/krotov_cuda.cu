@@ -1,0 +1,837 @@
+// libkrotov_cuda: C ABI (include/krotov_cuda.h) + host-side preparation for the sm_100a kernels.
+//
+// Host work done here (all of it outside the per-time-step path):
+//   * union sparsity pattern of all generator terms, slot assignment (per-diagonal when possible)
+//   * per-direction row tables P_t = 2c (H_t - beta delta_t0) rebuilt whenever the Chebyshev
+//     polynomial changes (krotov_set_cheby)
+//   * launch configuration of the persistent kernel, exchange-array reset, CUDA-event timing
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../../include/krotov_cuda.h"
+#include "dense_kernel.cuh"
+#include "warp_kernel.cuh"
+
+using cplx = std::complex<double>;
+
+namespace {
+
+thread_local std::string g_create_error = "";
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+
+struct ChebyTables {  // one direction
+    bool set = false;
+    int ndtc = 0, mmax = 0, m_max_used = 0;
+    std::vector<double> E_min, Delta;
+    DevBuf coef, m, phase, dtc;
+    std::vector<int> dtc_of_step;
+    std::vector<int> m_host;
+    std::vector<double> coef_host;
+    std::vector<cplx> phase_host;
+};
+
+}  // namespace
+
+struct krotov_handle_s {
+    int d = 0, N = 0, L = 0, N_T = 0, n_gen = 0, functional = 0, N_global = 0, store_fw = 0, device = 0;
+    int path = 0;
+    std::vector<double> tlist, dt;
+    std::vector<int> gen_of_traj;
+    std::vector<double> weight;
+    bool has_target = false;
+    // generator, dense host copy per (g, term): row-major d*d
+    std::vector<cplx> Hdense;  // [n_gen][1+L][d][d]
+    // ---- warp path
+    int W = 0;   // off-diagonal slots actually needed
+    int Wt = 0;  // template width serving it
+    int nnz_union = 0;
+    bool preg = false;
+    std::vector<int> cols;  // [Wt][32]
+    int wpc = 1, tpw = 1, nCTA = 1;
+    DevBuf d_cols, d_Pf, d_Pb, d_inv_s, d_gen, d_dt, d_alpha, d_eps_old, d_eps_new, d_ga, d_X, d_Phi, d_psi0,
+        d_target, d_chiT, d_chicoef, d_psif, d_tau, d_R, d_err, d_weight;
+    DevBuf d_mbox[2];
+    ChebyTables cheb[2];
+    bool chiT_valid = false, chicoef_valid = false, swept = false;
+    // comm
+    int rank = 0, world = 1;
+    double *peer_mbox[2][kr::kMaxRanks] = {};
+    bool peer_opened[kr::kMaxRanks] = {};
+    long long iter_count = 0;
+    // dense path
+    kr::DenseEngine *dense = nullptr;
+    // misc
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 0;
+    long long launches_total = 0, launches_last = 0;
+    double ms_last = 0.0, ms_last_bw = 0.0;
+    std::string err;
+};
+
+namespace {
+
+#define KR_CUDA(h, call)                                                                             \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) {                                                                     \
+            (h)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+            return KROTOV_ERR_CUDA;                                                                  \
+        }                                                                                            \
+    } while (0)
+
+int fail(krotov_handle h, int code, const std::string &msg) {
+    if (h)
+        h->err = msg;
+    else
+        g_create_error = msg;
+    return code;
+}
+
+int dev_alloc(krotov_handle h, DevBuf &b, size_t bytes) {
+    b.release();
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(&b.p, bytes);
+    if (e != cudaSuccess) {
+        h->err = std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e);
+        return e == cudaErrorMemoryAllocation ? KROTOV_ERR_NOMEM : KROTOV_ERR_CUDA;
+    }
+    b.bytes = bytes;
+    return KROTOV_OK;
+}
+
+template <typename T>
+int upload(krotov_handle h, DevBuf &b, const std::vector<T> &v) {
+    int rc = dev_alloc(h, b, v.size() * sizeof(T));
+    if (rc) return rc;
+    if (!v.empty()) KR_CUDA(h, cudaMemcpy(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return KROTOV_OK;
+}
+
+// ---- kernel table ------------------------------------------------------------------------
+using WarpKernel = void (*)(const kr::WarpParams);
+struct KernelKey {
+    int W, LT;
+    bool operator<(const KernelKey &o) const { return W < o.W || (W == o.W && LT < o.LT); }
+};
+
+#define KR_INST(W, LT, MT) {{W, LT}, (WarpKernel)kr::krotov_warp_kernel<W, LT, MT>}
+const std::map<KernelKey, WarpKernel> &kernel_table() {
+    static const std::map<KernelKey, WarpKernel> tab = {
+        // runtime-L variants (rows reloaded per use), up to 15 trajectory warps per CTA
+        KR_INST(1, 0, 512), KR_INST(2, 0, 512), KR_INST(3, 0, 512), KR_INST(4, 0, 512), KR_INST(5, 0, 512),
+        KR_INST(6, 0, 512), KR_INST(7, 0, 512), KR_INST(8, 0, 512), KR_INST(10, 0, 512), KR_INST(12, 0, 512),
+        KR_INST(16, 0, 512), KR_INST(20, 0, 512), KR_INST(24, 0, 512), KR_INST(31, 0, 512),
+        // register-resident term rows (PREG): (1+L)(W+1) <= 36 double2
+        KR_INST(1, 1, 256), KR_INST(2, 1, 256), KR_INST(3, 1, 256), KR_INST(4, 1, 256), KR_INST(5, 1, 256),
+        KR_INST(6, 1, 256), KR_INST(7, 1, 256), KR_INST(8, 1, 256), KR_INST(10, 1, 256), KR_INST(12, 1, 256),
+        
+        KR_INST(1, 2, 256), KR_INST(2, 2, 256), KR_INST(3, 2, 256), KR_INST(4, 2, 256), KR_INST(5, 2, 256),
+        KR_INST(6, 2, 256), KR_INST(7, 2, 256), KR_INST(8, 2, 256), KR_INST(10, 2, 256),
+        KR_INST(2, 3, 256), KR_INST(4, 3, 256), KR_INST(6, 3, 256),
+    };
+    return tab;
+}
+
+const int kWidths[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 16, 20, 24, 31};
+
+int pick_width(int W) {
+    for (int w : kWidths)
+        if (w >= W) return w;
+    return -1;
+}
+
+cplx Hval(const krotov_handle h, int g, int t, int i, int j) {
+    return h->Hdense[(((size_t)g * (1 + h->L) + t) * h->d + i) * h->d + j];
+}
+
+// ---- pattern + slot assignment -------------------------------------------------------------
+int build_pattern(krotov_handle h) {
+    const int d = h->d;
+    std::vector<char> pat((size_t)d * d, 0);
+    for (int g = 0; g < h->n_gen; ++g)
+        for (int t = 0; t <= h->L; ++t)
+            for (int i = 0; i < d; ++i)
+                for (int j = 0; j < d; ++j)
+                    if (Hval(h, g, t, i, j) != cplx(0.0, 0.0)) pat[(size_t)i * d + j] = 1;
+    // adjoint pattern must be covered too (backward sweep uses H^dagger): symmetrise
+    for (int i = 0; i < d; ++i)
+        for (int j = 0; j < d; ++j)
+            if (pat[(size_t)i * d + j]) pat[(size_t)j * d + i] = 1;
+    int nnz = 0, wmax = 0;
+    std::set<int> diags;
+    for (int i = 0; i < d; ++i) {
+        int w = 0;
+        for (int j = 0; j < d; ++j)
+            if (pat[(size_t)i * d + j]) {
+                ++nnz;
+                if (i != j) {
+                    ++w;
+                    diags.insert(j - i);
+                }
+            }
+        wmax = std::max(wmax, w);
+        if (!pat[(size_t)i * d + i]) ++nnz;  // diagonal is always kept
+    }
+    h->nnz_union = nnz;
+    const bool use_dia = (int)diags.size() <= std::max(wmax, 1) + 1 && pick_width((int)diags.size()) > 0 &&
+                         pick_width((int)diags.size()) <= pick_width(std::max(wmax, 1));
+    h->W = std::max(1, use_dia ? (int)diags.size() : wmax);
+    h->Wt = pick_width(h->W);
+    if (h->Wt < 0) return fail(h, KROTOV_ERR_UNSUPPORTED, "row too wide for the warp path");
+    h->cols.assign((size_t)h->Wt * 32, 0);
+    for (int s = 0; s < h->Wt; ++s)
+        for (int i = 0; i < 32; ++i) h->cols[(size_t)s * 32 + i] = i;  // padding: own column, value 0
+    if (use_dia) {
+        int s = 0;
+        for (int off : diags) {
+            for (int i = 0; i < d; ++i) {
+                int j = i + off;
+                if (j >= 0 && j < d && pat[(size_t)i * d + j]) h->cols[(size_t)s * 32 + i] = j;
+            }
+            ++s;
+        }
+    } else {
+        for (int i = 0; i < d; ++i) {
+            int s = 0;
+            for (int j = 0; j < d; ++j)
+                if (i != j && pat[(size_t)i * d + j]) h->cols[(size_t)(s++) * 32 + i] = j;
+        }
+    }
+    return KROTOV_OK;
+}
+
+// rows P_t for one direction: [g][1+L][Wt+1][32]
+void build_rows(krotov_handle h, int dir, std::vector<cplx> &out) {
+    const int d = h->d, L = h->L, Wt = h->Wt;
+    const ChebyTables &ct = h->cheb[dir];
+    out.assign((size_t)h->n_gen * (1 + L) * (Wt + 1) * 32, cplx(0, 0));
+    for (int g = 0; g < h->n_gen; ++g) {
+        const double s = 4.0 / ct.Delta[g];
+        const double beta = ct.Delta[g] / 2 + ct.E_min[g];
+        const cplx f = (dir == KROTOV_FORWARD) ? cplx(0.0, -s) : cplx(0.0, s);  // 2c = -/+ 4i/Delta
+        for (int t = 0; t <= L; ++t) {
+            cplx *row = &out[((size_t)g * (1 + L) + t) * (Wt + 1) * 32];
+            for (int i = 0; i < d; ++i) {
+                for (int sl = 0; sl < Wt; ++sl) {
+                    const int j = h->cols[(size_t)sl * 32 + i];
+                    if (j == i) continue;
+                    const cplx v = (dir == KROTOV_FORWARD) ? Hval(h, g, t, i, j) : std::conj(Hval(h, g, t, j, i));
+                    row[(size_t)sl * 32 + i] = f * v;
+                }
+                cplx dv = (dir == KROTOV_FORWARD) ? Hval(h, g, t, i, i) : std::conj(Hval(h, g, t, i, i));
+                if (t == 0) dv -= beta;
+                row[(size_t)Wt * 32 + i] = f * dv;
+            }
+        }
+    }
+}
+
+__global__ void chi_coef_kernel(int functional, int N, int N_global, const double2 *tau, const double *w,
+                                double2 *coef) {
+    // one warp; fixed summation order
+    const int lane = threadIdx.x;
+    const double Ng = (double)N_global;
+    if (functional == KROTOV_CHI_SM) {
+        double sr = 0.0, si = 0.0;
+        for (int k = lane; k < N; k += 32) {
+            sr += w[k] * tau[k].x;
+            si += w[k] * tau[k].y;
+        }
+        sr = kr::warp_sum_xor(sr);
+        si = kr::warp_sum_xor(si);
+        for (int k = lane; k < N; k += 32) {
+            const double f = w[k] / (Ng * Ng);
+            coef[k] = make_double2(f * sr, f * si);
+        }
+    } else if (functional == KROTOV_CHI_SS) {
+        for (int k = lane; k < N; k += 32) {
+            const double f = w[k] / Ng;
+            coef[k] = make_double2(f * tau[k].x, f * tau[k].y);
+        }
+    } else {
+        for (int k = lane; k < N; k += 32) coef[k] = make_double2(w[k] / (2.0 * Ng), 0.0);
+    }
+}
+
+int choose_launch(krotov_handle h) {
+    // One trajectory per warp while they fit on the chip (<= sm_count CTAs, co-resident for the
+    // in-kernel grid exchange); register-resident term rows (PREG) when an instance exists and the
+    // CTA stays <= 7 trajectory warps; otherwise rows are re-read per use and a warp may own several
+    // trajectories.  KROTOV_WPC overrides the warps-per-CTA heuristic (experiments).
+    const int N = h->N, sm = h->sm_count;
+    const int cap_preg = 7, cap = 15;
+    const bool preg_possible = kernel_table().count(KernelKey{h->Wt, h->L}) > 0;
+    int wpc = (N <= 8) ? N : std::max(std::min(N, 4), (N + sm - 1) / sm);
+    if (const char *env = getenv("KROTOV_WPC")) wpc = std::max(1, atoi(env));
+    h->tpw = 1;
+    if (preg_possible && wpc <= cap_preg && (N + wpc - 1) / wpc <= sm && !getenv("KROTOV_NO_PREG")) {
+        h->preg = true;
+    } else {
+        h->preg = false;
+        wpc = std::min(wpc, cap);
+        if ((N + wpc - 1) / wpc > sm) {
+            wpc = cap;
+            h->tpw = (N + sm * wpc - 1) / (sm * wpc);
+        }
+    }
+    h->wpc = wpc;
+    h->nCTA = (N + wpc * h->tpw - 1) / (wpc * h->tpw);
+    return KROTOV_OK;
+}
+
+size_t warp_smem_bytes(const krotov_handle h) {
+    return (size_t)h->wpc * 2 * 32 * 16 + (size_t)h->wpc * h->tpw * 32 * 16 + (size_t)h->L * h->wpc * 32 * 8 +
+           kr::kMaxCtrl * 8;
+}
+
+int launch_warp(krotov_handle h, int mode) {
+    kr::WarpParams p;
+    memset(&p, 0, sizeof(p));
+    p.d = h->d; p.N = h->N; p.L = h->L; p.N_T = h->N_T; p.n_gen = h->n_gen;
+    p.wpc = h->wpc; p.tpw = h->tpw; p.nCTA = h->nCTA; p.mode = mode; p.store_fw = h->store_fw;
+    p.ndtc_f = h->cheb[0].ndtc; p.ndtc_b = h->cheb[1].set ? h->cheb[1].ndtc : 1; p.mmax_f = h->cheb[0].mmax; p.mmax_b = h->cheb[1].set ? h->cheb[1].mmax : 1;
+    p.gen_of_traj = (const int *)h->d_gen.p;
+    p.cols = (const int *)h->d_cols.p;
+    p.Pf = (const double2 *)h->d_Pf.p; p.Pb = (const double2 *)h->d_Pb.p;
+    p.inv_s_f = (const double *)h->d_inv_s.p;
+    p.coef_f = (const double *)h->cheb[0].coef.p; p.m_f = (const int *)h->cheb[0].m.p;
+    p.phase_f = (const double2 *)h->cheb[0].phase.p;
+    p.coef_b = (const double *)h->cheb[1].coef.p; p.m_b = (const int *)h->cheb[1].m.p;
+    p.phase_b = (const double2 *)h->cheb[1].phase.p;
+    p.dtc_f = (const int *)h->cheb[0].dtc.p; p.dtc_b = (const int *)h->cheb[1].dtc.p; p.dt = (const double *)h->d_dt.p;
+    p.alpha = (const double *)h->d_alpha.p;
+    p.eps_old = (const double *)h->d_eps_old.p; p.eps_new = (double *)h->d_eps_new.p;
+    p.g_a_int = (double *)h->d_ga.p;
+    p.X = (double2 *)h->d_X.p; p.Phi = (double2 *)h->d_Phi.p;
+    p.psi0 = (const double2 *)h->d_psi0.p;
+    p.target = h->has_target ? (const double2 *)h->d_target.p : nullptr;
+    p.chiT = h->chiT_valid ? (const double2 *)h->d_chiT.p : nullptr;
+    p.chi_coef = (const double2 *)h->d_chicoef.p;
+    p.psi_final = (double2 *)h->d_psif.p; p.tau = (double2 *)h->d_tau.p;
+    p.R = (double *)h->d_R.p;
+    p.rank = h->rank; p.world = h->world;
+    const int par = (int)(h->iter_count & 1);
+    for (int r = 0; r < h->world && r < kr::kMaxRanks; ++r) p.mbox[r] = h->peer_mbox[par][r];
+    p.err_flag = (int *)h->d_err.p;
+    p.timeout_cycles = 20000000000ll;  // ~10 s
+    if (const char *e = getenv("KROTOV_TIMEOUT_CYCLES")) p.timeout_cycles = atoll(e);
+
+    KernelKey key{h->Wt, h->preg ? h->L : 0};
+    auto it = kernel_table().find(key);
+    if (it == kernel_table().end()) return fail(h, KROTOV_ERR_UNSUPPORTED, "no kernel instance for this (W, L)");
+    WarpKernel fn = it->second;
+    const size_t smem = warp_smem_bytes(h);
+    KR_CUDA(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(h->nCTA), block((h->wpc + 1) * 32);
+    void *args[] = {(void *)&p};
+    if (h->nCTA > 1 && mode == 1) {
+        KR_CUDA(h, cudaLaunchCooperativeKernel((const void *)fn, grid, block, args, smem, h->stream));
+    } else {
+        KR_CUDA(h, cudaLaunchKernel((const void *)fn, grid, block, args, smem, h->stream));
+    }
+    h->launches_last += 1;
+    return KROTOV_OK;
+}
+
+int check_err_flag(krotov_handle h) {
+    int flag = 0;
+    KR_CUDA(h, cudaMemcpy(&flag, h->d_err.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) {
+        cudaMemset(h->d_err.p, 0, sizeof(int));
+        return fail(h, KROTOV_ERR_TIMEOUT, "in-kernel exchange timed out waiting for a partial sum");
+    }
+    return KROTOV_OK;
+}
+
+}  // namespace
+
+// ============================================================================== C ABI
+extern "C" {
+
+int krotov_abi_version(void) { return KROTOV_ABI_VERSION; }
+
+const char *krotov_last_error(krotov_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int krotov_destroy(krotov_handle h) {
+    if (!h) return KROTOV_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (int r = 0; r < kr::kMaxRanks; ++r)
+        if (h->peer_opened[r])
+            for (int par = 0; par < 2; ++par)
+                if (h->peer_mbox[par][r]) cudaIpcCloseMemHandle(h->peer_mbox[par][r]);
+    DevBuf *bufs[] = {&h->d_cols, &h->d_Pf, &h->d_Pb, &h->d_inv_s, &h->d_gen, &h->d_dt, &h->d_alpha,
+                      &h->d_eps_old, &h->d_eps_new, &h->d_ga, &h->d_X, &h->d_Phi, &h->d_psi0, &h->d_target,
+                      &h->d_chiT, &h->d_chicoef, &h->d_psif, &h->d_tau, &h->d_R, &h->d_err, &h->d_weight,
+                      &h->d_mbox[0], &h->d_mbox[1]};
+    for (DevBuf *b : bufs) b->release();
+    for (int dir = 0; dir < 2; ++dir) {
+        h->cheb[dir].coef.release();
+        h->cheb[dir].m.release();
+        h->cheb[dir].phase.release();
+        h->cheb[dir].dtc.release();
+    }
+    if (h->dense) {
+        kr::dense_destroy(h->dense);
+        h->dense = nullptr;
+    }
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return KROTOV_OK;
+}
+
+int krotov_create(const krotov_problem *pb, krotov_handle *out) {
+    if (!pb || !out) return fail(nullptr, KROTOV_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (pb->struct_size != (int32_t)sizeof(krotov_problem))
+        return fail(nullptr, KROTOV_ERR_ARG, "krotov_problem.struct_size mismatch (ABI version?)");
+    if (pb->d < 1 || pb->n_traj < 1 || pb->n_steps < 1 || pb->n_gen < 1)
+        return fail(nullptr, KROTOV_ERR_ARG, "d, n_traj, n_steps, n_gen must be >= 1");
+    if (pb->n_ctrl < 1) return fail(nullptr, KROTOV_ERR_ARG, "no controls in trajectories: cannot optimize");
+    if (pb->n_ctrl > kr::kMaxCtrl) return fail(nullptr, KROTOV_ERR_UNSUPPORTED, "more than 8 controls");
+    if (!pb->tlist || !pb->gen_of_traj || !pb->gen_values || !pb->psi0 || !pb->update_shape || !pb->lambda_a)
+        return fail(nullptr, KROTOV_ERR_ARG, "null array in krotov_problem");
+    if (pb->gen_format == KROTOV_GEN_CSR && (!pb->csr_rowptr || !pb->csr_colind))
+        return fail(nullptr, KROTOV_ERR_ARG, "CSR pattern missing");
+    if (pb->functional != KROTOV_CHI_HOST && !pb->target)
+        return fail(nullptr, KROTOV_ERR_ARG, "built-in functional needs target states");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(nullptr, KROTOV_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(ce));
+    if (pb->device < 0 || pb->device >= ndev) return fail(nullptr, KROTOV_ERR_ARG, "bad device ordinal");
+
+    krotov_handle h = new krotov_handle_s();
+    auto bail = [&](int rc) {
+        g_create_error = h->err;
+        krotov_destroy(h);
+        return rc;
+    };
+    h->d = pb->d; h->N = pb->n_traj; h->L = pb->n_ctrl; h->N_T = pb->n_steps; h->n_gen = pb->n_gen;
+    h->functional = pb->functional;
+    h->N_global = pb->n_traj_global > 0 ? pb->n_traj_global : pb->n_traj;
+    h->store_fw = pb->store_fw; h->device = pb->device;
+    const int d = h->d, N = h->N, L = h->L, N_T = h->N_T;
+    if (cudaSetDevice(h->device) != cudaSuccess) return bail(fail(h, KROTOV_ERR_CUDA, "cudaSetDevice failed"));
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, h->device);
+    h->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) return bail(fail(h, KROTOV_ERR_UNSUPPORTED, "libkrotov_cuda is built for sm_100a only"));
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess)
+        return bail(fail(h, KROTOV_ERR_CUDA, "stream/event creation failed"));
+
+    h->tlist.assign(pb->tlist, pb->tlist + N_T + 1);
+    h->dt.resize(N_T);
+    for (int n = 0; n < N_T; ++n) {
+        h->dt[n] = h->tlist[n + 1] - h->tlist[n];
+        if (!(h->dt[n] > 0)) return bail(fail(h, KROTOV_ERR_ARG, "tlist must be strictly increasing"));
+    }
+    h->gen_of_traj.assign(pb->gen_of_traj, pb->gen_of_traj + N);
+    for (int k = 0; k < N; ++k)
+        if (h->gen_of_traj[k] < 0 || h->gen_of_traj[k] >= h->n_gen)
+            return bail(fail(h, KROTOV_ERR_ARG, "gen_of_traj out of range"));
+    h->weight.assign(N, 1.0);
+    if (pb->weight) h->weight.assign(pb->weight, pb->weight + N);
+    h->has_target = pb->target != nullptr;
+
+    // dense host copy of every term (row-major)
+    h->Hdense.assign((size_t)h->n_gen * (1 + L) * d * d, cplx(0, 0));
+    const cplx *vals = reinterpret_cast<const cplx *>(pb->gen_values);
+    for (int g = 0; g < h->n_gen; ++g)
+        for (int t = 0; t <= L; ++t) {
+            if (pb->term_present && !pb->term_present[(size_t)g * (1 + L) + t]) continue;
+            cplx *dst = &h->Hdense[((size_t)g * (1 + L) + t) * d * d];
+            if (pb->gen_format == KROTOV_GEN_DENSE_COLMAJOR) {
+                const cplx *src = vals + ((size_t)g * (1 + L) + t) * d * d;
+                for (int j = 0; j < d; ++j)
+                    for (int i = 0; i < d; ++i) dst[(size_t)i * d + j] = src[(size_t)j * d + i];
+            } else if (pb->gen_format == KROTOV_GEN_CSR) {
+                const cplx *src = vals + ((size_t)g * (1 + L) + t) * pb->nnz;
+                for (int i = 0; i < d; ++i)
+                    for (int q = pb->csr_rowptr[i]; q < pb->csr_rowptr[i + 1]; ++q) {
+                        int j = pb->csr_colind[q];
+                        if (j < 0 || j >= d) return bail(fail(h, KROTOV_ERR_ARG, "CSR column out of range"));
+                        dst[(size_t)i * d + j] += src[q];
+                    }
+            } else {
+                return bail(fail(h, KROTOV_ERR_ARG, "unknown gen_format"));
+            }
+        }
+
+    int path = pb->force_path;
+    if (path == 0) path = (d <= 32) ? KROTOV_PATH_WARP : KROTOV_PATH_DENSE;
+    if (path == KROTOV_PATH_WARP && d > 32)
+        return bail(fail(h, KROTOV_ERR_UNSUPPORTED, "warp path needs d <= 32"));
+    h->path = path;
+
+    int rc;
+    // ---- buffers common to both paths
+    std::vector<double> alpha((size_t)L * N_T);
+    for (int l = 0; l < L; ++l) {
+        if (!(pb->lambda_a[l] != 0.0)) return bail(fail(h, KROTOV_ERR_ARG, "lambda_a must be non-zero"));
+        for (int n = 0; n < N_T; ++n) alpha[(size_t)l * N_T + n] = pb->update_shape[(size_t)l * N_T + n] / pb->lambda_a[l];
+    }
+    if ((rc = upload(h, h->d_alpha, alpha))) return bail(rc);
+    if ((rc = upload(h, h->d_dt, h->dt))) return bail(rc);
+    if ((rc = upload(h, h->d_gen, h->gen_of_traj))) return bail(rc);
+    if ((rc = upload(h, h->d_weight, h->weight))) return bail(rc);
+    if ((rc = dev_alloc(h, h->d_eps_old, (size_t)L * N_T * 8))) return bail(rc);
+    if ((rc = dev_alloc(h, h->d_eps_new, (size_t)L * N_T * 8))) return bail(rc);
+    if ((rc = dev_alloc(h, h->d_ga, kr::kMaxCtrl * 8))) return bail(rc);
+    if ((rc = dev_alloc(h, h->d_tau, (size_t)N * 16))) return bail(rc);
+    if ((rc = dev_alloc(h, h->d_chicoef, (size_t)N * 16))) return bail(rc);
+    if ((rc = dev_alloc(h, h->d_err, 16))) return bail(rc);
+    cudaMemset(h->d_err.p, 0, 16);
+    cudaMemset(h->d_tau.p, 0, (size_t)N * 16);
+
+    if (path == KROTOV_PATH_WARP) {
+        if ((rc = build_pattern(h))) return bail(rc);
+        if ((rc = upload(h, h->d_cols, h->cols))) return bail(rc);
+        choose_launch(h);
+        // padded state arrays [N][32]
+        auto pad_states = [&](const double *src, std::vector<cplx> &dst) {
+            dst.assign((size_t)N * 32, cplx(0, 0));
+            const cplx *s = reinterpret_cast<const cplx *>(src);
+            for (int k = 0; k < N; ++k)
+                for (int i = 0; i < d; ++i) dst[(size_t)k * 32 + i] = s[(size_t)k * d + i];
+        };
+        std::vector<cplx> tmp;
+        pad_states(pb->psi0, tmp);
+        if ((rc = upload(h, h->d_psi0, tmp))) return bail(rc);
+        if (h->has_target) {
+            pad_states(pb->target, tmp);
+            if ((rc = upload(h, h->d_target, tmp))) return bail(rc);
+        }
+        const size_t slab = (size_t)N * (N_T + 1) * 32 * 16;
+        if ((rc = dev_alloc(h, h->d_X, slab))) return bail(rc);
+        if (h->store_fw && (rc = dev_alloc(h, h->d_Phi, slab))) return bail(rc);
+        if ((rc = dev_alloc(h, h->d_chiT, (size_t)N * 32 * 16))) return bail(rc);
+        if ((rc = dev_alloc(h, h->d_psif, (size_t)N * 32 * 16))) return bail(rc);
+        cudaMemset(h->d_psif.p, 0, (size_t)N * 32 * 16);
+        if ((rc = dev_alloc(h, h->d_R, (size_t)N_T * h->nCTA * L * 8))) return bail(rc);
+        for (int par = 0; par < 2; ++par) {
+            if ((rc = dev_alloc(h, h->d_mbox[par], (size_t)N_T * kr::kMaxRanks * L * 8))) return bail(rc);
+            cudaMemset(h->d_mbox[par].p, 0xFF, h->d_mbox[par].bytes);
+            h->peer_mbox[par][0] = (double *)h->d_mbox[par].p;
+        }
+    } else {
+        h->dense = kr::dense_create(h->d, h->N, h->L, h->N_T, h->n_gen, h->Hdense, h->gen_of_traj, pb->psi0,
+                                    pb->target, h->store_fw, h->stream, h->err);
+        if (!h->dense) return bail(KROTOV_ERR_UNSUPPORTED);
+    }
+    if (cudaDeviceSynchronize() != cudaSuccess) return bail(fail(h, KROTOV_ERR_CUDA, "device sync after create failed"));
+    *out = h;
+    return KROTOV_OK;
+}
+
+int krotov_get_info(krotov_handle h, krotov_info *out) {
+    if (!h || !out) return KROTOV_ERR_ARG;
+    memset(out, 0, sizeof(*out));
+    out->struct_size = sizeof(krotov_info);
+    out->path = h->path;
+    out->ell_width = h->Wt;
+    out->nnz_union = h->nnz_union;
+    out->grid_blocks = h->nCTA;
+    out->block_threads = (h->wpc + 1) * 32;
+    out->m_fw = h->cheb[0].m_max_used;
+    out->m_bw = h->cheb[1].m_max_used;
+    out->sm_count = h->sm_count;
+    out->launches_total = h->launches_total;
+    out->launches_last = h->launches_last;
+    out->ms_last = h->ms_last;
+    out->ms_last_backward = h->ms_last_bw;
+    out->hbm_bytes_state = (int64_t)h->d_X.bytes;
+    if (h->dense) kr::dense_info(h->dense, out);
+    return KROTOV_OK;
+}
+
+int krotov_set_cheby(krotov_handle h, int direction, int n_dt_class, const int32_t *dt_class_of_step,
+                     const double *dt_of_class, const double *E_min, const double *Delta, const int32_t *m,
+                     const double *coeffs, int m_max) {
+    if (!h) return KROTOV_ERR_ARG;
+    if (direction != KROTOV_FORWARD && direction != KROTOV_BACKWARD) return fail(h, KROTOV_ERR_ARG, "bad direction");
+    if (n_dt_class < 1 || !dt_class_of_step || !dt_of_class || !E_min || !Delta || !m || !coeffs || m_max < 1)
+        return fail(h, KROTOV_ERR_ARG, "bad argument to krotov_set_cheby");
+    cudaSetDevice(h->device);
+    ChebyTables &ct = h->cheb[direction];
+    for (int n = 0; n < h->N_T; ++n)
+        if (dt_class_of_step[n] < 0 || dt_class_of_step[n] >= n_dt_class)
+            return fail(h, KROTOV_ERR_ARG, "dt_class_of_step out of range");
+    for (int c = 0; c < n_dt_class; ++c) {
+        if (direction == KROTOV_FORWARD && !(dt_of_class[c] > 0)) return fail(h, KROTOV_ERR_ARG, "forward dt must be > 0");
+        if (direction == KROTOV_BACKWARD && !(dt_of_class[c] < 0)) return fail(h, KROTOV_ERR_ARG, "backward dt must be < 0");
+    }
+    ct.ndtc = n_dt_class;
+    ct.mmax = m_max;
+    ct.E_min.assign(E_min, E_min + h->n_gen);
+    ct.Delta.assign(Delta, Delta + h->n_gen);
+    ct.m_host.assign(m, m + (size_t)h->n_gen * n_dt_class);
+    ct.coef_host.assign(coeffs, coeffs + (size_t)h->n_gen * n_dt_class * m_max);
+    ct.m_max_used = 0;
+    for (int g = 0; g < h->n_gen; ++g) {
+        if (!(Delta[g] > 0)) return fail(h, KROTOV_ERR_ARG, "Delta must be > 0");
+        for (int c = 0; c < n_dt_class; ++c) {
+            int mm = ct.m_host[(size_t)g * n_dt_class + c];
+            if (mm < 1 || mm > m_max) return fail(h, KROTOV_ERR_ARG, "m out of range");
+            ct.m_max_used = std::max(ct.m_max_used, mm);
+        }
+    }
+    ct.phase_host.resize((size_t)h->n_gen * n_dt_class);
+    for (int g = 0; g < h->n_gen; ++g) {
+        const double beta = Delta[g] / 2 + E_min[g];
+        for (int c = 0; c < n_dt_class; ++c)
+            ct.phase_host[(size_t)g * n_dt_class + c] = std::exp(cplx(0.0, -beta * dt_of_class[c]));
+    }
+    ct.dtc_of_step.assign(dt_class_of_step, dt_class_of_step + h->N_T);
+    int rc;
+    if ((rc = upload(h, ct.dtc, ct.dtc_of_step))) return rc;
+    if ((rc = upload(h, ct.coef, ct.coef_host))) return rc;
+    if ((rc = upload(h, ct.m, ct.m_host))) return rc;
+    if ((rc = upload(h, ct.phase, ct.phase_host))) return rc;
+    ct.set = true;
+    if (h->path == KROTOV_PATH_WARP) {
+        std::vector<cplx> rows;
+        build_rows(h, direction, rows);
+        if ((rc = upload(h, direction == KROTOV_FORWARD ? h->d_Pf : h->d_Pb, rows))) return rc;
+        if (direction == KROTOV_FORWARD) {
+            std::vector<double> inv_s(h->n_gen);
+            for (int g = 0; g < h->n_gen; ++g) inv_s[g] = Delta[g] / 4.0;
+            if ((rc = upload(h, h->d_inv_s, inv_s))) return rc;
+        }
+    } else {
+        std::string e;
+        if (!kr::dense_set_cheby(h->dense, direction, n_dt_class, ct.dtc_of_step, ct.E_min, ct.Delta, ct.m_host,
+                                 ct.coef_host, m_max, ct.phase_host, e))
+            return fail(h, KROTOV_ERR_CUDA, e);
+    }
+    return KROTOV_OK;
+}
+
+static int begin_timed(krotov_handle h) {
+    h->launches_last = 0;
+    KR_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    return KROTOV_OK;
+}
+static int end_timed(krotov_handle h) {
+    KR_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    KR_CUDA(h, cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    KR_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->ms_last = ms;
+    h->launches_total += h->launches_last;
+    KR_CUDA(h, cudaGetLastError());
+    return KROTOV_OK;
+}
+
+int krotov_forward(krotov_handle h, const double *pulses) {
+    if (!h || !pulses) return KROTOV_ERR_ARG;
+    if (!h->cheb[0].set) return fail(h, KROTOV_ERR_STATE, "krotov_set_cheby(FORWARD) must be called before krotov_forward");
+    cudaSetDevice(h->device);
+    KR_CUDA(h, cudaMemcpyAsync(h->d_eps_old.p, pulses, (size_t)h->L * h->N_T * 8, cudaMemcpyHostToDevice, h->stream));
+    int rc;
+    if ((rc = begin_timed(h))) return rc;
+    if (h->path == KROTOV_PATH_WARP) {
+        if ((rc = launch_warp(h, 0))) return rc;
+    } else {
+        std::string e;
+        if (!kr::dense_forward(h->dense, (const double *)h->d_eps_old.p, (double2 *)h->d_tau.p, h->launches_last, e))
+            return fail(h, KROTOV_ERR_CUDA, e);
+    }
+    if ((rc = end_timed(h))) return rc;
+    h->swept = true;
+    h->chiT_valid = false;
+    h->chicoef_valid = false;
+    return KROTOV_OK;
+}
+
+int krotov_set_chi(krotov_handle h, const double *chi) {
+    if (!h || !chi) return KROTOV_ERR_ARG;
+    cudaSetDevice(h->device);
+    const int N = h->N, d = h->d;
+    if (h->path == KROTOV_PATH_WARP) {
+        std::vector<cplx> tmp((size_t)N * 32, cplx(0, 0));
+        const cplx *s = reinterpret_cast<const cplx *>(chi);
+        for (int k = 0; k < N; ++k)
+            for (int i = 0; i < d; ++i) tmp[(size_t)k * 32 + i] = s[(size_t)k * d + i];
+        KR_CUDA(h, cudaMemcpy(h->d_chiT.p, tmp.data(), tmp.size() * 16, cudaMemcpyHostToDevice));
+    } else {
+        std::string e;
+        if (!kr::dense_set_chi(h->dense, chi, e)) return fail(h, KROTOV_ERR_CUDA, e);
+    }
+    h->chiT_valid = true;
+    return KROTOV_OK;
+}
+
+int krotov_set_chi_coeffs(krotov_handle h, const double *coef) {
+    if (!h || !coef) return KROTOV_ERR_ARG;
+    if (!h->has_target) return fail(h, KROTOV_ERR_STATE, "krotov_set_chi_coeffs needs target states");
+    cudaSetDevice(h->device);
+    KR_CUDA(h, cudaMemcpy(h->d_chicoef.p, coef, (size_t)h->N * 16, cudaMemcpyHostToDevice));
+    h->chicoef_valid = true;
+    h->chiT_valid = false;
+    return KROTOV_OK;
+}
+
+int krotov_iterate(krotov_handle h, const double *guess_pulses, double *new_pulses, double *g_a_int) {
+    if (!h || !guess_pulses || !new_pulses || !g_a_int) return KROTOV_ERR_ARG;
+    if (!h->cheb[0].set || !h->cheb[1].set)
+        return fail(h, KROTOV_ERR_STATE, "krotov_set_cheby must be called for both directions before krotov_iterate");
+    cudaSetDevice(h->device);
+    const bool need_device_coef = !h->chiT_valid && !h->chicoef_valid;
+    if (need_device_coef) {
+        if (h->functional == KROTOV_CHI_HOST)
+            return fail(h, KROTOV_ERR_STATE, "functional is KROTOV_CHI_HOST: call krotov_set_chi before krotov_iterate");
+        if (!h->swept) return fail(h, KROTOV_ERR_STATE, "krotov_forward must run before the first krotov_iterate");
+        if (h->world > 1 && h->functional == KROTOV_CHI_SM)
+            return fail(h, KROTOV_ERR_STATE, "multi-rank J_T_sm needs krotov_set_chi_coeffs (global sum of tau)");
+    }
+    const size_t pbytes = (size_t)h->L * h->N_T * 8;
+    KR_CUDA(h, cudaMemcpyAsync(h->d_eps_old.p, guess_pulses, pbytes, cudaMemcpyHostToDevice, h->stream));
+    int rc;
+    if ((rc = begin_timed(h))) return rc;
+    if (need_device_coef) {
+        chi_coef_kernel<<<1, 32, 0, h->stream>>>(h->functional, h->N, h->N_global, (const double2 *)h->d_tau.p,
+                                                 (const double *)h->d_weight.p, (double2 *)h->d_chicoef.p);
+        h->launches_last += 1;
+    }
+    if (h->path == KROTOV_PATH_WARP) {
+        if (h->nCTA > 1) KR_CUDA(h, cudaMemsetAsync(h->d_R.p, 0xFF, h->d_R.bytes, h->stream));
+        if (h->world > 1) {
+            // the mailbox of the NEXT iteration's parity is cleared now (peers are at most one iteration ahead)
+            const int nxt = (int)((h->iter_count + 1) & 1);
+            KR_CUDA(h, cudaMemsetAsync(h->d_mbox[nxt].p, 0xFF, h->d_mbox[nxt].bytes, h->stream));
+        }
+        if ((rc = launch_warp(h, 1))) return rc;
+    } else {
+        std::string e;
+        double ms_bw = 0.0;
+        if (!kr::dense_iterate(h->dense, (const double *)h->d_eps_old.p, (double *)h->d_eps_new.p,
+                               (const double *)h->d_alpha.p, (const double *)h->d_dt.p, (double *)h->d_ga.p,
+                               h->chiT_valid ? nullptr : (const double2 *)h->d_chicoef.p, (double2 *)h->d_tau.p,
+                               h->launches_last, e))
+            return fail(h, KROTOV_ERR_CUDA, e);
+        h->ms_last_bw = ms_bw;
+    }
+    if ((rc = end_timed(h))) return rc;
+    h->iter_count += 1;
+    if ((rc = check_err_flag(h))) return rc;
+    KR_CUDA(h, cudaMemcpy(new_pulses, h->d_eps_new.p, pbytes, cudaMemcpyDeviceToHost));
+    KR_CUDA(h, cudaMemcpy(g_a_int, h->d_ga.p, (size_t)h->L * 8, cudaMemcpyDeviceToHost));
+    h->chiT_valid = false;
+    h->chicoef_valid = false;
+    h->swept = true;
+    return KROTOV_OK;
+}
+
+int krotov_get_states(krotov_handle h, double *states) {
+    if (!h || !states) return KROTOV_ERR_ARG;
+    cudaSetDevice(h->device);
+    const int N = h->N, d = h->d;
+    if (h->path == KROTOV_PATH_WARP) {
+        std::vector<cplx> tmp((size_t)N * 32);
+        KR_CUDA(h, cudaMemcpy(tmp.data(), h->d_psif.p, tmp.size() * 16, cudaMemcpyDeviceToHost));
+        cplx *o = reinterpret_cast<cplx *>(states);
+        for (int k = 0; k < N; ++k)
+            for (int i = 0; i < d; ++i) o[(size_t)k * d + i] = tmp[(size_t)k * 32 + i];
+    } else {
+        std::string e;
+        if (!kr::dense_get_states(h->dense, states, e)) return fail(h, KROTOV_ERR_CUDA, e);
+    }
+    return KROTOV_OK;
+}
+
+int krotov_get_tau(krotov_handle h, double *tau) {
+    if (!h || !tau) return KROTOV_ERR_ARG;
+    cudaSetDevice(h->device);
+    KR_CUDA(h, cudaMemcpy(tau, h->d_tau.p, (size_t)h->N * 16, cudaMemcpyDeviceToHost));
+    return KROTOV_OK;
+}
+
+int krotov_get_storage(krotov_handle h, int which, int k, int n0, int n1, double *out) {
+    if (!h || !out) return KROTOV_ERR_ARG;
+    if (k < 0 || k >= h->N || n0 < 0 || n1 > h->N_T + 1 || n0 >= n1) return fail(h, KROTOV_ERR_ARG, "bad storage range");
+    if (which == KROTOV_FORWARD && !h->store_fw) return fail(h, KROTOV_ERR_STATE, "forward storage was not requested (store_fw)");
+    cudaSetDevice(h->device);
+    const int d = h->d;
+    if (h->path == KROTOV_PATH_WARP) {
+        const DevBuf &b = which == KROTOV_FORWARD ? h->d_Phi : h->d_X;
+        std::vector<cplx> tmp((size_t)(n1 - n0) * 32);
+        const char *src = (const char *)b.p + ((size_t)k * (h->N_T + 1) + n0) * 32 * 16;
+        KR_CUDA(h, cudaMemcpy(tmp.data(), src, tmp.size() * 16, cudaMemcpyDeviceToHost));
+        cplx *o = reinterpret_cast<cplx *>(out);
+        for (int n = 0; n < n1 - n0; ++n)
+            for (int i = 0; i < d; ++i) o[(size_t)n * d + i] = tmp[(size_t)n * 32 + i];
+    } else {
+        std::string e;
+        if (!kr::dense_get_storage(h->dense, which, k, n0, n1, out, e)) return fail(h, KROTOV_ERR_CUDA, e);
+    }
+    return KROTOV_OK;
+}
+
+// ---- multi-GPU mailbox exchange over CUDA IPC -------------------------------------------------
+struct CommDesc {
+    cudaIpcMemHandle_t mh[2];
+};
+static_assert(sizeof(CommDesc) <= KROTOV_COMM_DESC_BYTES, "descriptor too large");
+
+int krotov_comm_export(krotov_handle h, void *desc) {
+    if (!h || !desc) return KROTOV_ERR_ARG;
+    if (h->path != KROTOV_PATH_WARP) return fail(h, KROTOV_ERR_UNSUPPORTED, "in-kernel exchange exists on the warp path only");
+    cudaSetDevice(h->device);
+    CommDesc cd;
+    memset(&cd, 0, sizeof(cd));
+    for (int par = 0; par < 2; ++par) KR_CUDA(h, cudaIpcGetMemHandle(&cd.mh[par], h->d_mbox[par].p));
+    memset(desc, 0, KROTOV_COMM_DESC_BYTES);
+    memcpy(desc, &cd, sizeof(cd));
+    return KROTOV_OK;
+}
+
+int krotov_comm_connect(krotov_handle h, int rank, int world, const void *descs) {
+    if (!h || !descs) return KROTOV_ERR_ARG;
+    if (world < 1 || world > kr::kMaxRanks || rank < 0 || rank >= world) return fail(h, KROTOV_ERR_ARG, "bad rank/world");
+    if (h->path != KROTOV_PATH_WARP) return fail(h, KROTOV_ERR_UNSUPPORTED, "in-kernel exchange exists on the warp path only");
+    cudaSetDevice(h->device);
+    h->rank = rank;
+    h->world = world;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) {
+            for (int par = 0; par < 2; ++par) h->peer_mbox[par][r] = (double *)h->d_mbox[par].p;
+            continue;
+        }
+        CommDesc cd;
+        memcpy(&cd, (const char *)descs + (size_t)r * KROTOV_COMM_DESC_BYTES, sizeof(cd));
+        for (int par = 0; par < 2; ++par) {
+            void *ptr = nullptr;
+            KR_CUDA(h, cudaIpcOpenMemHandle(&ptr, cd.mh[par], cudaIpcMemLazyEnablePeerAccess));
+            h->peer_mbox[par][r] = (double *)ptr;
+        }
+        h->peer_opened[r] = true;
+    }
+    h->iter_count = 0;
+    return KROTOV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,451 @@
+// Persistent warp-per-trajectory Krotov kernel for small Hilbert spaces (d <= 32), sm_100a.
+//
+// One launch = one whole Krotov iteration (src/optimize.jl:279-371 of the reference):
+//   backward sweep   chi_k(t_n) = exp(+i H_k^dagger dt) chi_k(t_{n+1})   stored for every n in HBM
+//   forward sweep    per time step: overlaps Im<chi_k|mu_l|psi_k> -> grid-wide fixed-order sum
+//                    -> pulse update -> Chebyshev step of every psi_k with the new pulse value
+// with NO host round trip and NO kernel boundary between time steps.
+//
+// Mapping.  One warp owns one trajectory (or `tpw` of them), lane i owns component i of the
+// state and row i of the generator.  The generator is kept as "G = 2c (H - beta)" rows in
+// registers: W off-diagonal slots + the diagonal, rebuilt once per time step from the per-term
+// rows P_t = 2c (H_t - beta delta_t0):  G = P_0 + sum_l eps_l[n] P_l.  The Chebyshev recursion
+//   v_1 = G v_0 / 2,   v_j = G v_{j-1} + v_{j-2},   psi' = e^{-i beta dt} sum_j a_j v_j
+// keeps v_{j-1}, v_{j-2} and the running sum in registers; only v_{j-1} is exchanged between
+// lanes, through a 2-deep ping-pong buffer in shared memory (one __syncwarp per term).  Slots
+// are assigned per matrix diagonal when the pattern allows it, so that every LDS.128 gather of
+// a warp touches consecutive 16-byte words (bank-conflict free).
+//
+// Grid-wide reduction per time step (the serial dependency of Krotov's method): every CTA has a
+// dedicated communication warp.  Trajectory warps leave their per-lane partial overlaps in
+// shared memory and arrive on named barrier A; the comm warp reduces them in a fixed order,
+// publishes the CTA partial into the step-indexed exchange array R[n][cta][l] (pre-filled with
+// a NaN sentinel, so the 8-byte value is its own "ready" flag -- no fence, no atomics), polls
+// the slots of all CTAs, sums them in CTA order (bitwise reproducible, identical in every CTA),
+// applies the update and releases the trajectory warps through named barrier B.  With several
+// ranks, CTA 0 additionally pushes the rank's sum into every peer's mailbox over NVLink (P2P
+// stores) and every CTA sums the `world` mailbox slots in rank order.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace kr {
+
+constexpr int kMaxRanks = 8;
+constexpr int kMaxCtrl = 8;
+constexpr unsigned long long kSentinel = 0xFFFFFFFFFFFFFFFFull;
+
+struct WarpParams {
+    int d, N, L, N_T, n_gen;
+    int wpc;   // trajectory warps per CTA (the CTA has wpc+1 warps)
+    int tpw;   // trajectories per warp
+    int nCTA;
+    int mode;  // 0 = plain forward sweep under eps_old, 1 = full iteration
+    int store_fw;
+    int ndtc_f, ndtc_b, mmax_f, mmax_b;
+    const int *gen_of_traj;
+    const int *cols;           // [W][32] column (= smem index) of slot s for row `lane`
+    const double2 *Pf, *Pb;    // [g][1+L][W+1][32], slot W = diagonal
+    const double *inv_s_f;     // [g]  1/s_g = Delta_g/4 of the forward polynomial
+    const double *coef_f, *coef_b;    // [g][ndtc][mmax]
+    const int *m_f, *m_b;             // [g][ndtc]
+    const double2 *phase_f, *phase_b; // [g][ndtc]  e^{-i beta dt}
+    const int *dtc_f, *dtc_b;  // [N_T] dt class of every interval, per direction
+    const double *dt;          // [N_T]
+    const double *alpha;       // [L][N_T]  S_l[n] / lambda_l
+    const double *eps_old;     // [L][N_T]
+    double *eps_new;           // [L][N_T]
+    double *g_a_int;           // [L]
+    double2 *X;                // [N][N_T+1][32]  chi trajectory, trajectory-major
+    double2 *Phi;              // [N][N_T+1][32]  optional forward storage
+    const double2 *psi0;       // [N][32]
+    const double2 *target;     // [N][32]
+    const double2 *chiT;       // [N][32] host-supplied boundary or nullptr
+    const double2 *chi_coef;   // [N]
+    double2 *psi_final;        // [N][32]
+    double2 *tau;              // [N]
+    double *R;                 // [N_T][nCTA][L] exchange, sentinel-filled
+    int rank, world;
+    double *mbox[kMaxRanks];   // mailbox of every rank (this iteration's parity): [N_T][world][L]
+    int *err_flag;
+    long long timeout_cycles;
+};
+
+__device__ __forceinline__ void st_relaxed_f64(double *p, double v) {
+    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const double *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// acc += G_row . v   (complex), two independent FMA chains per component
+template <int W>
+__device__ __forceinline__ void row_dot(const double2 (&g)[W + 1], const int (&col)[W], const double2 *__restrict__ vs,
+                                        const double2 own, double &ar, double &ai) {
+    double ar1 = 0.0, ai1 = 0.0;
+    ar = fma(g[W].x, own.x, ar);
+    ar1 = fma(-g[W].y, own.y, ar1);
+    ai = fma(g[W].x, own.y, ai);
+    ai1 = fma(g[W].y, own.x, ai1);
+#pragma unroll
+    for (int s = 0; s < W; ++s) {
+        const double2 x = vs[col[s]];
+        ar = fma(g[s].x, x.x, ar);
+        ar1 = fma(-g[s].y, x.y, ar1);
+        ai = fma(g[s].x, x.y, ai);
+        ai1 = fma(g[s].y, x.x, ai1);
+    }
+    ar += ar1;
+    ai += ai1;
+}
+
+template <int W>
+__device__ __forceinline__ void load_row(const double2 *__restrict__ base, double2 (&out)[W + 1], int lane) {
+#pragma unroll
+    for (int s = 0; s <= W; ++s) out[s] = base[s * 32 + lane];
+}
+
+// One Chebyshev step.  v0buf holds psi for all lanes (written + synced by the caller).
+template <int W>
+__device__ __forceinline__ double2 cheby_step(const double2 psi, const double2 (&g)[W + 1], const int (&col)[W],
+                                              const double2 *v0buf, double2 *bufA, double2 *bufB,
+                                              const double *__restrict__ a, const int m, const double2 phase,
+                                              const int lane) {
+    double2 vm2 = psi;
+    const double a0 = a[0];
+    double outr = a0 * psi.x, outi = a0 * psi.y;
+    double ar = 0.0, ai = 0.0;
+    row_dot<W>(g, col, v0buf, psi, ar, ai);
+    double2 vm1 = make_double2(0.5 * ar, 0.5 * ai);
+    if (m > 1) {
+        const double a1 = a[1];
+        outr = fma(a1, vm1.x, outr);
+        outi = fma(a1, vm1.y, outi);
+    }
+    bufB[lane] = vm1;
+    __syncwarp();
+    double2 *cur = bufB, *nxt = bufA;
+    for (int j = 2; j < m; ++j) {
+        const double aj = a[j];
+        ar = vm2.x;
+        ai = vm2.y;
+        row_dot<W>(g, col, cur, vm1, ar, ai);
+        outr = fma(aj, ar, outr);
+        outi = fma(aj, ai, outi);
+        vm2 = vm1;
+        vm1 = make_double2(ar, ai);
+        nxt[lane] = vm1;
+        __syncwarp();
+        double2 *t = cur;
+        cur = nxt;
+        nxt = t;
+    }
+    return make_double2(phase.x * outr - phase.y * outi, phase.x * outi + phase.y * outr);
+}
+
+__device__ __forceinline__ double warp_sum_xor(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Wait for `cnt` doubles spaced `stride` apart starting at `base + lane*stride` ... to become
+// non-sentinel; returns their sum in index order for this lane's subset {lane, lane+32, ...}.
+__device__ __forceinline__ double poll_sum(const double *base, int cnt, int stride, int lane, int *err_flag,
+                                           long long timeout) {
+    double s = 0.0;
+    const long long t0 = clock64();
+    for (int c = lane; c < cnt; c += 32) {
+        unsigned long long u = ld_relaxed_u64(base + (size_t)c * stride);
+        int spins = 0;
+        while (u == kSentinel) {
+            if ((++spins & 1023) == 0) {
+                if (clock64() - t0 > timeout || *(volatile int *)err_flag) {
+                    atomicExch(err_flag, 1);
+                    return 0.0;
+                }
+            }
+            u = ld_relaxed_u64(base + (size_t)c * stride);
+        }
+        s += __longlong_as_double((long long)u);
+    }
+    return s;
+}
+
+template <int W, int LT /*0 = runtime L, rows reloaded from L1/L2 per use*/, int MAXTHREADS>
+__global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid_constant__ WarpParams p) {
+    constexpr bool PREG = (LT > 0);
+    constexpr int NT = PREG ? (1 + LT) : 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int L = PREG ? LT : p.L;
+    const int wpc = p.wpc, tpw = p.tpw;
+    // smem carve-up
+    double2 *vbuf = reinterpret_cast<double2 *>(smem_raw);        // [wpc][2][32]
+    double2 *psis = vbuf + (size_t)wpc * 2 * 32;                  // [wpc][tpw][32]
+    double *red = reinterpret_cast<double *>(psis + (size_t)wpc * tpw * 32);  // [L][wpc*32]
+    double *eps_s = red + (size_t)L * wpc * 32;                   // [kMaxCtrl]
+    const int nthr_all = (wpc + 1) * 32;
+    const int N_T = p.N_T;
+    const bool is_comm = (warp == wpc);
+
+    if (is_comm) {
+        // ---------------------------------------------------------------- communication warp
+        if (p.mode != 1) return;
+        double ga = 0.0;  // lane l accumulates g_a_int[l]  (CTA 0 writes it)
+        for (int n = 0; n < N_T; ++n) {
+            double a_ln = 0.0, e_old = 0.0, dtn = 0.0;
+            if (lane < L) {
+                a_ln = p.alpha[(size_t)lane * N_T + n];
+                e_old = p.eps_old[(size_t)lane * N_T + n];
+                dtn = p.dt[n];
+            }
+            bar_sync(1, nthr_all);  // barrier A: partials are in `red`
+            double mine = 0.0;      // lane l ends up holding du[l]
+            for (int l = 0; l < L; ++l) {
+                double s = 0.0;
+                for (int q = 0; q < wpc; ++q) s += red[(size_t)l * wpc * 32 + q * 32 + lane];
+                s = warp_sum_xor(s);
+                if (p.nCTA > 1) {
+                    double *slot = p.R + ((size_t)n * p.nCTA) * L + l;
+                    if (lane == 0) st_relaxed_f64(slot + (size_t)blockIdx.x * L, s);
+                    s = poll_sum(slot, p.nCTA, L, lane, p.err_flag, p.timeout_cycles);
+                    s = warp_sum_xor(s);
+                }
+                if (p.world > 1) {
+                    if (blockIdx.x == 0 && lane < p.world)
+                        st_relaxed_f64(p.mbox[lane] + ((size_t)n * p.world + p.rank) * L + l, s);
+                    s = poll_sum(p.mbox[p.rank] + ((size_t)n * p.world) * L + l, p.world, L, lane, p.err_flag,
+                                 p.timeout_cycles);
+                    s = warp_sum_xor(s);
+                }
+                if (lane == l) mine = s;
+            }
+            if (lane < L) {
+                const double d_eps = __dmul_rn(a_ln, mine);      // src/optimize.jl:355
+                const double e_new = __dadd_rn(e_old, d_eps);    // :356
+                eps_s[lane] = e_new;
+                if (blockIdx.x == 0) {
+                    p.eps_new[(size_t)lane * N_T + n] = e_new;
+                    ga = __dadd_rn(ga, __dmul_rn(__dmul_rn(a_ln, __dmul_rn(fabs(mine), fabs(mine))), dtn));  // :357
+                }
+            }
+            bar_arrive(2, nthr_all);  // barrier B: eps_s is valid
+        }
+        if (blockIdx.x == 0 && lane < L) p.g_a_int[lane] = ga;
+        return;
+    }
+
+    // -------------------------------------------------------------------- trajectory warps
+    const int gw = blockIdx.x * wpc + warp;       // global trajectory-warp index
+    const int kbase = gw * tpw;                   // first trajectory of this warp
+    double2 *bufA = vbuf + (size_t)warp * 64;
+    double2 *bufB = bufA + 32;
+    double2 *mypsi = psis + (size_t)warp * tpw * 32;
+
+    int col[W];
+#pragma unroll
+    for (int s = 0; s < W; ++s) col[s] = p.cols[s * 32 + lane];
+
+    const size_t rowstride = (size_t)(W + 1) * 32;   // one term
+    double2 P[NT][W + 1];                            // PREG: per-term rows of this lane's trajectory
+    double2 g[W + 1];
+
+    // ================================================================ backward sweep
+    if (p.mode == 1) {
+        for (int t = 0; t < tpw; ++t) {
+            const int k = kbase + t;
+            if (k >= p.N) break;
+            const int gi = p.gen_of_traj[k];
+            const double2 *Pg = p.Pb + (size_t)gi * (1 + L) * rowstride;
+            if (PREG) {
+#pragma unroll
+                for (int q = 0; q < NT; ++q) load_row<W>(Pg + q * rowstride, P[q], lane);
+            }
+            double2 chi;
+            if (p.chiT != nullptr) {
+                chi = p.chiT[(size_t)k * 32 + lane];
+            } else {
+                const double2 c = p.chi_coef[k];
+                const double2 tg = p.target[(size_t)k * 32 + lane];
+                chi = make_double2(c.x * tg.x - c.y * tg.y, c.x * tg.y + c.y * tg.x);
+            }
+            double2 *Xk = p.X + (size_t)k * (N_T + 1) * 32;
+            Xk[(size_t)N_T * 32 + lane] = chi;
+            mypsi[t * 32 + lane] = chi;
+            __syncwarp();
+            for (int n = N_T - 1; n >= 0; --n) {
+                const int dtc = p.dtc_b[n];
+                const int ci = gi * p.ndtc_b + dtc;
+                if (PREG) {
+#pragma unroll
+                    for (int s = 0; s <= W; ++s) g[s] = P[0][s];
+#pragma unroll
+                    for (int l = 0; l < NT - 1; ++l) {
+                        const double e = p.eps_old[(size_t)l * N_T + n];
+#pragma unroll
+                        for (int s = 0; s <= W; ++s) {
+                            g[s].x = fma(e, P[l + 1][s].x, g[s].x);
+                            g[s].y = fma(e, P[l + 1][s].y, g[s].y);
+                        }
+                    }
+                } else {
+                    load_row<W>(Pg, g, lane);
+                    for (int l = 0; l < L; ++l) {
+                        const double e = p.eps_old[(size_t)l * N_T + n];
+                        const double2 *Pl = Pg + (size_t)(l + 1) * rowstride;
+#pragma unroll
+                        for (int s = 0; s <= W; ++s) {
+                            const double2 v = Pl[s * 32 + lane];
+                            g[s].x = fma(e, v.x, g[s].x);
+                            g[s].y = fma(e, v.y, g[s].y);
+                        }
+                    }
+                }
+                chi = cheby_step<W>(chi, g, col, mypsi + t * 32, bufA, bufB, p.coef_b + (size_t)ci * p.mmax_b,
+                                    p.m_b[ci], p.phase_b[ci], lane);
+                mypsi[t * 32 + lane] = chi;
+                __syncwarp();
+                Xk[(size_t)n * 32 + lane] = chi;
+            }
+        }
+    }
+
+    // ================================================================ forward sweep
+    double2 psi_reg = make_double2(0.0, 0.0);
+    for (int t = 0; t < tpw; ++t) {
+        const int k = kbase + t;
+        double2 v = make_double2(0.0, 0.0);
+        if (k < p.N) {
+            v = p.psi0[(size_t)k * 32 + lane];
+            if (p.store_fw) p.Phi[(size_t)k * (N_T + 1) * 32 + lane] = v;
+        }
+        mypsi[t * 32 + lane] = v;
+        if (t == 0) psi_reg = v;
+    }
+    __syncwarp();
+    const int k0 = kbase;
+    const int g0 = (k0 < p.N) ? p.gen_of_traj[k0] : 0;
+    if (PREG && k0 < p.N) {
+        const double2 *Pg = p.Pf + (size_t)g0 * (1 + L) * rowstride;
+#pragma unroll
+        for (int q = 0; q < NT; ++q) load_row<W>(Pg + q * rowstride, P[q], lane);
+    }
+    double2 chi_next = make_double2(0.0, 0.0);
+    if (p.mode == 1 && k0 < p.N) chi_next = p.X[(size_t)k0 * (N_T + 1) * 32 + lane];
+
+    for (int n = 0; n < N_T; ++n) {
+        double eps[PREG ? (LT > 0 ? LT : 1) : kMaxCtrl];
+        if (p.mode == 1) {
+            // ---- overlaps  Im <chi_k| mu_l |psi_k>   (src/optimize.jl:339-349)
+            double part[PREG ? (LT > 0 ? LT : 1) : kMaxCtrl];
+#pragma unroll
+            for (int l = 0; l < (PREG ? LT : kMaxCtrl); ++l) part[l] = 0.0;
+            for (int t = 0; t < tpw; ++t) {
+                const int k = kbase + t;
+                if (k >= p.N) break;
+                const int gi = (t == 0) ? g0 : p.gen_of_traj[k];
+                const double inv_s = p.inv_s_f[gi];
+                const double2 psi = (tpw == 1) ? psi_reg : mypsi[t * 32 + lane];
+                const double2 chi = (t == 0) ? chi_next : p.X[((size_t)k * (N_T + 1) + n) * 32 + lane];
+                if (PREG) {
+#pragma unroll
+                    for (int l = 0; l < NT - 1; ++l) {
+                        double wr = 0.0, wi = 0.0;
+                        row_dot<W>(P[l + 1], col, mypsi + t * 32, psi, wr, wi);
+                        part[l] = fma(inv_s, fma(chi.x, wr, chi.y * wi), part[l]);
+                    }
+                } else {
+                    const double2 *Pg = p.Pf + (size_t)gi * (1 + L) * rowstride;
+                    for (int l = 0; l < L; ++l) {
+                        load_row<W>(Pg + (size_t)(l + 1) * rowstride, g, lane);
+                        double wr = 0.0, wi = 0.0;
+                        row_dot<W>(g, col, mypsi + t * 32, psi, wr, wi);
+                        part[l] = fma(inv_s, fma(chi.x, wr, chi.y * wi), part[l]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int l = 0; l < (PREG ? LT : kMaxCtrl); ++l)
+                if (l < L) red[(size_t)l * wpc * 32 + warp * 32 + lane] = part[l];
+            bar_arrive(1, nthr_all);  // barrier A
+            if (n + 1 < N_T && k0 < p.N) chi_next = p.X[((size_t)k0 * (N_T + 1) + n + 1) * 32 + lane];
+            bar_sync(2, nthr_all);    // barrier B: updated pulse value is in eps_s
+#pragma unroll
+            for (int l = 0; l < (PREG ? LT : kMaxCtrl); ++l)
+                if (l < L) eps[l] = eps_s[l];
+        } else {
+#pragma unroll
+            for (int l = 0; l < (PREG ? LT : kMaxCtrl); ++l)
+                if (l < L) eps[l] = p.eps_old[(size_t)l * N_T + n];
+        }
+        // ---- forward step with the (updated) pulse value  (src/optimize.jl:360-368)
+        const int dtc = p.dtc_f[n];
+        for (int t = 0; t < tpw; ++t) {
+            const int k = kbase + t;
+            if (k >= p.N) break;
+            const int gi = (t == 0) ? g0 : p.gen_of_traj[k];
+            const int ci = gi * p.ndtc_f + dtc;
+            if (PREG) {
+#pragma unroll
+                for (int s = 0; s <= W; ++s) g[s] = P[0][s];
+#pragma unroll
+                for (int l = 0; l < NT - 1; ++l) {
+#pragma unroll
+                    for (int s = 0; s <= W; ++s) {
+                        g[s].x = fma(eps[l], P[l + 1][s].x, g[s].x);
+                        g[s].y = fma(eps[l], P[l + 1][s].y, g[s].y);
+                    }
+                }
+            } else {
+                const double2 *Pg = p.Pf + (size_t)gi * (1 + L) * rowstride;
+                load_row<W>(Pg, g, lane);
+                for (int l = 0; l < L; ++l) {
+                    const double2 *Pl = Pg + (size_t)(l + 1) * rowstride;
+#pragma unroll
+                    for (int s = 0; s <= W; ++s) {
+                        const double2 v = Pl[s * 32 + lane];
+                        g[s].x = fma(eps[l], v.x, g[s].x);
+                        g[s].y = fma(eps[l], v.y, g[s].y);
+                    }
+                }
+            }
+            double2 psi = (tpw == 1) ? psi_reg : mypsi[t * 32 + lane];
+            psi = cheby_step<W>(psi, g, col, mypsi + t * 32, bufA, bufB, p.coef_f + (size_t)ci * p.mmax_f,
+                                p.m_f[ci], p.phase_f[ci], lane);
+            mypsi[t * 32 + lane] = psi;
+            if (t == 0) psi_reg = psi;
+            __syncwarp();
+            if (p.store_fw) {
+                // mode 1 writes slot n like the reference (sic, src/optimize.jl:367); the plain
+                // forward sweep writes slot n+1 (src/optimize.jl:263)
+                const int slot = (p.mode == 1) ? n : n + 1;
+                p.Phi[((size_t)k * (N_T + 1) + slot) * 32 + lane] = psi;
+            }
+        }
+    }
+
+    // ---- final states and tau_k = <tgt_k|psi_k(T)>  (src/optimize.jl:378-381)
+    for (int t = 0; t < tpw; ++t) {
+        const int k = kbase + t;
+        if (k >= p.N) break;
+        const double2 psi = mypsi[t * 32 + lane];
+        p.psi_final[(size_t)k * 32 + lane] = psi;
+        double tr = 0.0, ti = 0.0;
+        if (p.target != nullptr) {
+            const double2 tg = p.target[(size_t)k * 32 + lane];
+            tr = tg.x * psi.x + tg.y * psi.y;
+            ti = tg.x * psi.y - tg.y * psi.x;
+        }
+        tr = warp_sum_xor(tr);
+        ti = warp_sum_xor(ti);
+        if (lane == 0) p.tau[k] = make_double2(tr, ti);
+    }
+}
+
+}  // namespace kr

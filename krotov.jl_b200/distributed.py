@@ -1,0 +1,74 @@
+"""Multi-GPU plumbing: one process per GPU, trajectories sharded across ranks.
+
+The data path has exactly one cross-GPU dependency per time step -- the L-vector of overlap sums
+(``src/optimize.jl:340-349``) -- and it is exchanged INSIDE the persistent kernel through peer-mapped
+mailboxes over NVLink (``krotov_comm_export`` / ``krotov_comm_connect``).  ``torch.distributed`` is
+used only for plumbing: gathering the IPC descriptors once, and gathering tau / states per iteration
+(N complex numbers).  With the ``gloo`` backend the same host logic runs on CPU in the tests."""
+from __future__ import annotations
+
+import numpy as np
+
+__all__ = ["shard_bounds", "Comm"]
+
+
+def shard_bounds(gen_of_traj, rank, world):
+    """Contiguous block [lo, hi) of trajectories for ``rank``.  Blocks are cut at generator boundaries
+    when the trajectories are grouped by generator (ensemble samples stay on one GPU, so each
+    generator is stored once); otherwise at equal counts."""
+    gen_of_traj = np.asarray(gen_of_traj)
+    N = len(gen_of_traj)
+    if world <= 1:
+        return 0, N
+    # boundaries where the generator index changes
+    cuts = [0] + [k for k in range(1, N) if gen_of_traj[k] != gen_of_traj[k - 1]] + [N]
+    grouped = len(set(gen_of_traj.tolist())) == len(cuts) - 1  # each generator is one contiguous run
+    if grouped and len(cuts) - 1 >= world:
+        # choose the cut closest to the ideal equal split
+        ideal = [round(r * N / world) for r in range(world + 1)]
+        bounds = [min(cuts, key=lambda c: abs(c - x)) for x in ideal]
+        bounds[0], bounds[-1] = 0, N
+        for r in range(1, world + 1):  # keep strictly increasing
+            if bounds[r] <= bounds[r - 1]:
+                bigger = [c for c in cuts if c > bounds[r - 1]]
+                bounds[r] = bigger[0] if bigger else N
+        bounds[-1] = N
+    else:
+        bounds = [(r * N) // world for r in range(world + 1)]
+    return int(bounds[rank]), int(bounds[rank + 1])
+
+
+class Comm:
+    """Thin wrapper over an initialised ``torch.distributed`` process group."""
+
+    def __init__(self, device=None):
+        import torch.distributed as dist
+
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self.dist = dist
+        self.rank = dist.get_rank()
+        self.world = dist.get_world_size()
+        self.backend = dist.get_backend()
+        self.device = self.rank if device is None else device
+
+    def all_gather_object(self, obj):
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
+    def connect(self, engine):
+        """Exchange the mailbox IPC descriptors and map the peers' mailboxes."""
+        descs = self.all_gather_object(engine.comm_export())
+        engine.comm_connect(self.rank, self.world, descs)
+        self.dist.barrier()
+
+    def all_gather_rows(self, local, n_total):
+        """Concatenate per-rank blocks of rows (tau or states) in rank order."""
+        parts = self.all_gather_object(np.ascontiguousarray(local))
+        out = np.concatenate(parts, axis=0)
+        assert out.shape[0] == n_total
+        return out
+
+    def barrier(self):
+        self.dist.barrier()

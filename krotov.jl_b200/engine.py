@@ -1,0 +1,148 @@
+"""`KrotovCuda`: thin object wrapper over one ``krotov_handle`` (one GPU, one shard of trajectories).
+
+Everything numeric happens in ``libkrotov_cuda``; this class only marshals NumPy arrays to
+the C ABI.  It is what the Julia shim's ``ccall`` layer would be."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as B
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class KrotovCuda:
+    def __init__(self, *, tlist, H0, Hc, gen_of_traj, psi0, target=None, weight=None, update_shape, lambda_a,
+                 functional=B.CHI_HOST, n_traj_global=0, store_fw=False, device=0, force_path=0):
+        """H0: (n_gen, d, d) complex, Hc: (n_gen, L, d, d) complex with ``None`` entries allowed
+        (as zeros + term_present=0); psi0/target: (N, d); update_shape: (L, N_T); lambda_a: (L,)."""
+        lib = B.lib()
+        self._lib = lib
+        self._h = C.c_void_p()
+        tlist = np.ascontiguousarray(tlist, np.float64)
+        psi0 = np.ascontiguousarray(psi0, np.complex128)
+        N, d = psi0.shape
+        n_gen = len(H0)
+        L = len(Hc[0])
+        N_T = len(tlist) - 1
+        vals = np.zeros((n_gen, 1 + L, d, d), np.complex128)
+        present = np.ones((n_gen, 1 + L), np.uint8)
+        for g in range(n_gen):
+            vals[g, 0] = np.asarray(H0[g]).T  # column-major on the wire (Julia Matrix layout)
+            for l in range(L):
+                if Hc[g][l] is None:
+                    present[g, 1 + l] = 0
+                else:
+                    vals[g, 1 + l] = np.asarray(Hc[g][l]).T
+        self.N, self.d, self.L, self.N_T, self.n_gen = N, d, L, N_T, n_gen
+        gen = np.ascontiguousarray(gen_of_traj, np.int32)
+        S = np.ascontiguousarray(update_shape, np.float64).reshape(L, N_T)
+        lam = np.ascontiguousarray(lambda_a, np.float64).reshape(L)
+        tgt = None if target is None else np.ascontiguousarray(target, np.complex128).reshape(N, d)
+        w = None if weight is None else np.ascontiguousarray(weight, np.float64).reshape(N)
+        p = B.Problem()
+        p.struct_size = C.sizeof(B.Problem)
+        p.d, p.n_traj, p.n_ctrl, p.n_steps, p.n_gen = d, N, L, N_T, n_gen
+        p.gen_format, p.nnz = B.GEN_DENSE_COLMAJOR, 0
+        p.tlist, p.gen_of_traj = _ptr(tlist), _ptr(gen)
+        p.gen_values, p.term_present = _ptr(vals), _ptr(present)
+        p.psi0, p.target, p.weight = _ptr(psi0), _ptr(tgt), _ptr(w)
+        p.update_shape, p.lambda_a = _ptr(S), _ptr(lam)
+        p.functional, p.n_traj_global = int(functional), int(n_traj_global)
+        p.store_fw, p.device, p.force_path = int(bool(store_fw)), int(device), int(force_path)
+        rc = lib.krotov_create(C.byref(p), C.byref(self._h))
+        if rc != B.KROTOV_OK:
+            msg = lib.krotov_last_error(None).decode()
+            self._h = C.c_void_p()
+            raise B.KrotovCudaError(rc, msg)
+
+    # -- plumbing -------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != B.KROTOV_OK:
+            raise B.KrotovCudaError(rc, self._lib.krotov_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.krotov_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        i = B.Info()
+        self._check(self._lib.krotov_get_info(self._h, C.byref(i)))
+        return {k: getattr(i, k) for k, _ in B.Info._fields_ if not k.startswith("reserved")}
+
+    # -- propagator settings --------------------------------------------------------------
+    def set_cheby(self, direction, dt_class_of_step, dt_of_class, E_min, Delta, coeffs):
+        """coeffs: list over generators of list over dt classes of 1-D coefficient arrays."""
+        n_gen, ndtc = self.n_gen, len(dt_of_class)
+        m = np.array([[len(coeffs[g][c]) for c in range(ndtc)] for g in range(n_gen)], np.int32)
+        m_max = int(m.max())
+        tab = np.zeros((n_gen, ndtc, m_max), np.float64)
+        for g in range(n_gen):
+            for c in range(ndtc):
+                tab[g, c, : m[g, c]] = coeffs[g][c]
+        dtc = np.ascontiguousarray(dt_class_of_step, np.int32)
+        dts = np.ascontiguousarray(dt_of_class, np.float64)
+        Emin = np.ascontiguousarray(E_min, np.float64).reshape(n_gen)
+        Dl = np.ascontiguousarray(Delta, np.float64).reshape(n_gen)
+        self._check(self._lib.krotov_set_cheby(self._h, int(direction), ndtc, _ptr(dtc), _ptr(dts), _ptr(Emin),
+                                               _ptr(Dl), _ptr(m), _ptr(tab), m_max))
+
+    # -- hot path -------------------------------------------------------------------------
+    def forward(self, pulses):
+        p = np.ascontiguousarray(pulses, np.float64).reshape(self.L, self.N_T)
+        self._check(self._lib.krotov_forward(self._h, _ptr(p)))
+
+    def set_chi(self, chi):
+        c = np.ascontiguousarray(chi, np.complex128).reshape(self.N, self.d)
+        self._check(self._lib.krotov_set_chi(self._h, _ptr(c)))
+
+    def set_chi_coeffs(self, coef):
+        c = np.ascontiguousarray(coef, np.complex128).reshape(self.N)
+        self._check(self._lib.krotov_set_chi_coeffs(self._h, _ptr(c)))
+
+    def iterate(self, guess_pulses, out_pulses=None):
+        g = np.ascontiguousarray(guess_pulses, np.float64).reshape(self.L, self.N_T)
+        out = np.empty((self.L, self.N_T), np.float64) if out_pulses is None else out_pulses
+        ga = np.empty(self.L, np.float64)
+        self._check(self._lib.krotov_iterate(self._h, _ptr(g), _ptr(out), _ptr(ga)))
+        return out, ga
+
+    # -- results --------------------------------------------------------------------------
+    def states(self):
+        out = np.empty((self.N, self.d), np.complex128)
+        self._check(self._lib.krotov_get_states(self._h, _ptr(out)))
+        return out
+
+    def tau(self):
+        out = np.empty(self.N, np.complex128)
+        self._check(self._lib.krotov_get_tau(self._h, _ptr(out)))
+        return out
+
+    def storage(self, which, k, n0=0, n1=None):
+        n1 = self.N_T + 1 if n1 is None else n1
+        out = np.empty((n1 - n0, self.d), np.complex128)
+        self._check(self._lib.krotov_get_storage(self._h, int(which), int(k), int(n0), int(n1), _ptr(out)))
+        return out
+
+    # -- multi-GPU ------------------------------------------------------------------------
+    def comm_export(self):
+        buf = (C.c_ubyte * B.COMM_DESC_BYTES)()
+        self._check(self._lib.krotov_comm_export(self._h, buf))
+        return bytes(buf)
+
+    def comm_connect(self, rank, world, descs):
+        blob = b"".join(descs)
+        assert len(blob) == world * B.COMM_DESC_BYTES
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._check(self._lib.krotov_comm_connect(self._h, int(rank), int(world), buf))

@@ -1,0 +1,71 @@
+"""Generators: ``hamiltonian(H0, (H1, eps1), ...)`` as in QuantumControl (used by the reference's tests,
+``test/test_tls_optimization.jl:16-28``)."""
+from __future__ import annotations
+
+import numpy as np
+
+__all__ = ["Generator", "hamiltonian"]
+
+
+def _as_matrix(op):
+    if hasattr(op, "toarray"):  # scipy.sparse
+        op = op.toarray()
+    m = np.asarray(op, dtype=np.complex128)
+    if m.ndim != 2 or m.shape[0] != m.shape[1]:
+        raise ValueError("operators must be square matrices")
+    return m
+
+
+class Generator:
+    """``G(t) = sum(drift ops) + sum_i amplitudes[i](t) * control_ops[i]`` with linear controls."""
+
+    def __init__(self, drift_ops, control_ops, amplitudes):
+        self.drift_ops = [_as_matrix(o) for o in drift_ops]
+        self.control_ops = [_as_matrix(o) for o in control_ops]
+        self.amplitudes = list(amplitudes)
+        if len(self.control_ops) != len(self.amplitudes):
+            raise ValueError("one amplitude per control operator")
+
+    @property
+    def ops(self):
+        return self.drift_ops + self.control_ops
+
+    @property
+    def dim(self):
+        return self.ops[0].shape[0]
+
+    def drift(self):
+        d = self.dim
+        out = np.zeros((d, d), np.complex128)
+        for o in self.drift_ops:
+            out = out + o
+        return out
+
+    def adjoint(self):
+        return Generator([o.conj().T for o in self.drift_ops], [o.conj().T for o in self.control_ops], self.amplitudes)
+
+    def __repr__(self):
+        return f"Generator(dim={self.dim}, drift terms={len(self.drift_ops)}, controls={len(self.amplitudes)})"
+
+
+def hamiltonian(*terms):
+    """``hamiltonian(H0, (H1, eps1), (H2, eps2))``: bare operators are drift terms, ``(op, control)``
+    pairs are control terms.  Without any control term the plain (summed) matrix is returned, as in
+    ``test/test_empty_optimization.jl:16-29``."""
+    drift, cops, amps = [], [], []
+    for term in terms:
+        if isinstance(term, (tuple, list)) and len(term) == 2 and not np.isscalar(term[0]) and (
+                callable(term[1]) or np.ndim(term[1]) == 1) and np.ndim(term[0]) == 2:
+            cops.append(term[0])
+            amps.append(term[1])
+        else:
+            drift.append(term)
+    if not cops:
+        out = _as_matrix(drift[0])
+        for o in drift[1:]:
+            out = out + _as_matrix(o)
+        return out
+    if not drift:
+        d = _as_matrix(cops[0]).shape[0]
+        drift = [np.zeros((d, d), np.complex128)]
+    return Generator(drift, cops, amps)

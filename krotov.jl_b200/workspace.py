@@ -1,0 +1,350 @@
+"""``KrotovWrk``: the workspace of ``src/workspace.jl:30-200`` with the device as owner of the heavy
+fields.  Field names follow the reference so that callbacks written for it keep working:
+``trajectories, adjoint_trajectories, kwargs, controls, pulses0, pulses1, g_a_int, update_shapes,
+lambda_vals, J_T_takes_tau, chi_takes_tau, result, control_derivs, fw_prop_kwargs, bw_prop_kwargs,
+fw_storage, fw_storage2, bw_storage, fw_propagators, bw_propagators, use_threads``.
+
+What lives where: pulses, S_l, lambda_l, g_a_int and the result are host NumPy arrays (the host copy
+of the pulses is authoritative between iterations -- callbacks may edit it); states, the chi
+trajectory (``bw_storage``) and the optional forward storage live in HBM behind a ``KrotovCuda``
+handle and are fetched lazily when a callback touches them.
+"""
+from __future__ import annotations
+
+import datetime as _dt
+import inspect
+import logging
+import warnings
+
+import numpy as np
+
+from . import _lib as B
+from .cheby import ChebyDirection
+from .controls import discretize_on_midpoints, get_control_derivs, get_controls
+from .engine import KrotovCuda
+from .errors import ArgumentError, ErrorException
+from .functionals import make_chi
+from .generators import Generator
+from .result import KrotovResult, convert_result
+
+log = logging.getLogger("krotov_jl_b200")
+
+__all__ = ["KrotovWrk", "IdDict"]
+
+
+class IdDict:
+    """Mapping keyed by object identity (controls may be unhashable arrays)."""
+
+    def __init__(self, pairs=()):
+        self._items = [(k, v) for k, v in (pairs.items() if hasattr(pairs, "items") else pairs)]
+
+    def __contains__(self, key):
+        return any(k is key for k, _ in self._items)
+
+    def __getitem__(self, key):
+        for k, v in self._items:
+            if k is key:
+                return v
+        raise KeyError(key)
+
+    def __setitem__(self, key, value):
+        for i, (k, _) in enumerate(self._items):
+            if k is key:
+                self._items[i] = (key, value)
+                return
+        self._items.append((key, value))
+
+    def keys(self):
+        return [k for k, _ in self._items]
+
+    def items(self):
+        return list(self._items)
+
+    def __len__(self):
+        return len(self._items)
+
+
+def _lookup(options, control):
+    if isinstance(options, IdDict):
+        return options[control]
+    for k, v in options.items():
+        if k is control:
+            return v
+    raise KeyError
+
+
+def _has(options, control):
+    try:
+        _lookup(options, control)
+        return True
+    except KeyError:
+        return False
+
+
+def _takes_tau(fn):
+    try:
+        return "tau" in inspect.signature(fn).parameters
+    except (TypeError, ValueError):
+        return False
+
+
+_CHEBY_NAMES = {"cheby", "Cheby", ":Cheby", ":cheby"}
+
+
+def _is_cheby(method):
+    if method is None:
+        return False
+    if isinstance(method, str):
+        return method in _CHEBY_NAMES
+    return getattr(method, "__name__", "").split(".")[-1] in _CHEBY_NAMES
+
+
+def _prop_kwargs(traj, kwargs, prefixes):
+    """``init_prop_trajectory``'s harvesting rule: problem kwargs first, trajectory properties
+    override; later prefixes override earlier ones (``src/workspace.jl:133,148``)."""
+    out = {}
+    for source in (kwargs, getattr(traj, "kwargs", {})):
+        for prefix in prefixes:
+            for key, val in source.items():
+                if key.startswith(prefix):
+                    out[key[len(prefix):]] = val
+    return out
+
+
+class _LazyStates:
+    """List-like view of Psi_k(T) on the device; fetched once per sweep on first access."""
+
+    def __init__(self, wrk):
+        self._wrk = wrk
+        self._cache = None
+
+    def invalidate(self):
+        self._cache = None
+
+    def _get(self):
+        if self._cache is None:
+            self._cache = self._wrk._fetch_states()
+        return self._cache
+
+    def __len__(self):
+        return self._wrk.N
+
+    def __getitem__(self, k):
+        return self._get()[k]
+
+    def __iter__(self):
+        return iter(self._get())
+
+    def __setitem__(self, k, v):  # `res.states[k] = propagator.state` (src/optimize.jl:379) is a no-op alias
+        pass
+
+
+class _PropagatorView:
+    """What callbacks see as ``wrk.fw_propagators[k]`` / ``wrk.bw_propagators[k]``."""
+
+    def __init__(self, wrk, k, backward):
+        self._wrk, self._k, self.backward = wrk, k, backward
+        self.parameters = None
+
+    @property
+    def state(self):
+        if self.backward:
+            return self._wrk.bw_storage[self._k][:, 0]
+        return self._wrk.result.states[self._k]
+
+    @property
+    def tlist(self):
+        return self._wrk.result.tlist
+
+
+class _Storage:
+    """``storage[k]`` -> (d, N_T+1) array, column n = time-grid point n, fetched from HBM on demand."""
+
+    def __init__(self, wrk, which):
+        self._wrk, self._which = wrk, which
+
+    def __len__(self):
+        return self._wrk.N
+
+    def __getitem__(self, k):
+        wrk = self._wrk
+        if self._which == B.FORWARD and not wrk.store_fw:
+            raise ErrorException("forward storage is off; pass `store_fw_states=True` to `optimize`")
+        lo, hi = wrk._shard
+        if not (lo <= k < hi):
+            raise ErrorException(f"trajectory {k} lives on another rank (this rank holds {lo}:{hi})")
+        return wrk.engine.storage(self._which, k - lo).T.copy()
+
+
+class KrotovWrk:
+    def __init__(self, problem, *, verbose=False, comm=None):
+        kwargs_in = problem.kwargs
+        self.use_threads = bool(kwargs_in.get("use_threads", False))  # accepted, ignored: the GPU batches
+        self.trajectories = list(problem.trajectories)
+        N = len(self.trajectories)
+        self.adjoint_trajectories = [t.adjoint() for t in self.trajectories]
+        self.controls = get_controls(self.trajectories)
+        if len(self.controls) == 0:
+            raise ErrorException("no controls in trajectories: cannot optimize")
+        self.control_derivs = [get_control_derivs(t.generator, self.controls) for t in self.trajectories]
+        tlist = np.asarray(problem.tlist, np.float64)
+        kwargs = dict(kwargs_in)  # shallow copy; ok to modify
+        default_shape = kwargs_in.get("update_shape", lambda t: 1.0)
+        default_lambda = float(kwargs_in.get("lambda_a", 1.0))
+        default_options = IdDict(
+            [(c, {"lambda_a": default_lambda, "update_shape": default_shape}) for c in self.controls])
+        if "pulse_options" in kwargs:
+            if "update_shape" in kwargs:
+                warnings.warn("`update_shape` is ignored due to given `pulse_options`")
+            if "lambda_a" in kwargs:
+                warnings.warn(f"`lambda_a={kwargs['lambda_a']}` is ignored due to given `pulse_options`")
+        elif "update_shape" not in kwargs and "lambda_a" not in kwargs:
+            warnings.warn("Using default pulse_options: (:lambda_a => 1.0, :update_shape => (t -> 1.0))")
+        pulse_options = kwargs.get("pulse_options", default_options)
+        for c in self.controls:
+            if not _has(pulse_options, c):
+                raise ErrorException("pulse_options must be defined for all controls")
+
+        def opt(c, name):
+            o = _lookup(pulse_options, c)
+            return o[name] if name in o else o[":" + name]
+
+        self.update_shapes = [discretize_on_midpoints(opt(c, "update_shape"), tlist) for c in self.controls]
+        self.lambda_vals = np.array([float(opt(c, "lambda_a")) for c in self.controls], np.float64)
+        if "continue_from" in kwargs:
+            log.info("Continuing previous optimization")
+            result = convert_result(kwargs["continue_from"])
+            result.iter_stop = int(kwargs.get("iter_stop", 5000))
+            result.converged = False
+            result.start_local_time = _dt.datetime.now()
+            result.message = "in progress"
+            pulses0 = [discretize_on_midpoints(c, tlist) for c in result.optimized_controls]
+        else:
+            result = KrotovResult.from_problem(problem)
+            pulses0 = [discretize_on_midpoints(c, tlist) for c in self.controls]
+        self.result = result
+        self.pulses0 = pulses0
+        self.pulses1 = [p.copy() for p in pulses0]
+        self.g_a_int = np.zeros(len(pulses0))
+        kwargs["piecewise"] = True  # only piecewise propagators
+        self.fw_prop_kwargs = [_prop_kwargs(t, kwargs, ["prop_", "fw_prop_"]) for t in self.trajectories]
+        self.bw_prop_kwargs = [_prop_kwargs(t, kwargs, ["prop_", "bw_prop_"]) for t in self.adjoint_trajectories]
+        for k in range(N):
+            self.bw_prop_kwargs[k]["backward"] = True
+        for pk in self.fw_prop_kwargs + self.bw_prop_kwargs:
+            if "method" not in pk:
+                raise ArgumentError("The propagation method must be specified (`prop_method=Cheby`)")
+            if not _is_cheby(pk["method"]):
+                raise ArgumentError(
+                    f"prop_method={pk['method']!r}: libkrotov_cuda serves the `Cheby` propagator only "
+                    "(there is no CPU fallback for other methods)")
+            if "callback" in pk:
+                raise ArgumentError("per-step propagation callbacks cannot run inside the device sweep")
+        if "J_T" not in kwargs:
+            raise ArgumentError("`optimize` for `method=Krotov` must be passed the functional `J_T`.")
+        J_T = kwargs["J_T"]
+        self.J_T_takes_tau = _takes_tau(J_T)
+        if "chi" not in kwargs:
+            kwargs["chi"] = make_chi(J_T, self.trajectories)
+        self.chi_takes_tau = _takes_tau(kwargs["chi"])
+        self.kwargs = kwargs
+        self.N = N
+        self.verbose = verbose
+        self.store_fw = bool(kwargs.get("store_fw_states", False))
+        self.fw_storage2 = None  # never read or written by the reference (src/workspace.jl:129-130)
+        self._build_device_side(tlist, comm)
+        self.fw_storage = _Storage(self, B.FORWARD)
+        self.bw_storage = _Storage(self, B.BACKWARD)
+        self.fw_propagators = [_PropagatorView(self, k, False) for k in range(N)]
+        self.bw_propagators = [_PropagatorView(self, k, True) for k in range(N)]
+        self._states = _LazyStates(self)
+        if not isinstance(self.result.states, _LazyStates):
+            self.result.states = self._states
+
+    # -------------------------------------------------------------------------------------
+    def _build_device_side(self, tlist, comm):
+        trajs = self.trajectories
+        N, L = self.N, len(self.controls)
+        d = trajs[0].initial_state.shape[0]
+        # distinct generators by identity: ensemble members sharing a Hamiltonian share its storage
+        gen_ids, gens, gen_of_traj = {}, [], np.zeros(N, np.int32)
+        for k, t in enumerate(trajs):
+            key = id(t.generator)
+            if key not in gen_ids:
+                gen_ids[key] = len(gens)
+                gens.append((t.generator, self.control_derivs[k]))
+            gen_of_traj[k] = gen_ids[key]
+        H0, Hc = [], []
+        for gen, derivs in gens:
+            if isinstance(gen, Generator):
+                H0.append(gen.drift())
+            else:
+                H0.append(np.asarray(gen, np.complex128))
+            Hc.append([None if mu is None else np.asarray(mu, np.complex128) for mu in derivs])
+        psi0 = np.array([t.initial_state for t in trajs], np.complex128).reshape(N, d)
+        has_all_targets = all(t.target_state is not None for t in trajs)
+        has_any_target = any(t.target_state is not None for t in trajs)
+        target = None
+        if has_any_target:
+            target = np.zeros((N, d), np.complex128)
+            for k, t in enumerate(trajs):
+                if t.target_state is not None:
+                    target[k] = t.target_state
+        weight = np.array([t.weight for t in trajs], np.float64)
+        builtin = getattr(self.kwargs["chi"], "krotov_builtin", None)
+        functional = {"sm": B.CHI_SM, "ss": B.CHI_SS, "re": B.CHI_RE}.get(builtin, B.CHI_HOST)
+        if functional != B.CHI_HOST and not has_all_targets:
+            functional = B.CHI_HOST
+        self.functional = functional
+        # ---- sharding over ranks (contiguous blocks of trajectories, aligned to generators when possible)
+        self.comm = comm
+        rank, world = (comm.rank, comm.world) if comm is not None else (0, 1)
+        from .distributed import shard_bounds
+
+        lo, hi = shard_bounds(gen_of_traj, rank, world)
+        self._shard = (lo, hi)
+        local_gens = sorted(set(int(g) for g in gen_of_traj[lo:hi]))
+        remap = {g: i for i, g in enumerate(local_gens)}
+        self._H0 = [H0[g] for g in local_gens]
+        self._Hc = [Hc[g] for g in local_gens]
+        S = np.array(self.update_shapes, np.float64).reshape(L, -1)
+        pk = self.fw_prop_kwargs[0]
+        device = int(self.kwargs.get("device", comm.device if comm is not None else 0))
+        self.engine = KrotovCuda(
+            tlist=tlist, H0=self._H0, Hc=self._Hc,
+            gen_of_traj=np.array([remap[int(g)] for g in gen_of_traj[lo:hi]], np.int32),
+            psi0=psi0[lo:hi], target=None if target is None else target[lo:hi], weight=weight[lo:hi],
+            update_shape=S, lambda_a=self.lambda_vals, functional=functional, n_traj_global=N,
+            store_fw=self.store_fw, device=device, force_path=int(self.kwargs.get("force_path", 0)))
+        if comm is not None and world > 1:
+            comm.connect(self.engine)
+        # ---- Chebyshev settings of both directions (init_prop: un-widened ranges of the guess pulses)
+        def settings(pk, backward):
+            H0s = [h.conj().T for h in self._H0] if backward else self._H0
+            Hcs = [[None if h is None else h.conj().T for h in row] for row in self._Hc] if backward else self._Hc
+            return ChebyDirection(
+                H0s, Hcs, tlist, backward, self.pulses0,
+                limit=pk.get("cheby_coeffs_limit", 1e-12), specrange_buffer=pk.get("specrange_buffer", 0.01),
+                specrange_method=pk.get("specrange_method", "auto"), E_min=pk.get("E_min"), E_max=pk.get("E_max"))
+
+        self.fw_settings = settings(self.fw_prop_kwargs[0], False)
+        self.bw_settings = settings(self.bw_prop_kwargs[0], True)
+        self.fw_settings.push(self.engine, B.FORWARD)
+        self.bw_settings.push(self.engine, B.BACKWARD)
+        self._weight = weight
+        self._target = target
+
+    def _fetch_states(self):
+        local = self.engine.states()
+        if self.comm is not None and self.comm.world > 1:
+            return self.comm.all_gather_rows(local, self.N)
+        return local
+
+    def _fetch_tau(self):
+        local = self.engine.tau()
+        if self.comm is not None and self.comm.world > 1:
+            return self.comm.all_gather_rows(local, self.N)
+        return local
+
+    def close(self):
+        self.engine.close()
