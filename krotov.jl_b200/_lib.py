@@ -24,7 +24,7 @@ COMM_DESC_BYTES = 128
 EXPORTS = [
     "krotov_abi_version", "krotov_create", "krotov_destroy", "krotov_last_error", "krotov_get_info",
     "krotov_set_cheby", "krotov_forward", "krotov_set_chi", "krotov_set_chi_coeffs", "krotov_iterate",
-    "krotov_get_states", "krotov_get_tau", "krotov_get_storage", "krotov_comm_export", "krotov_comm_connect",
+    "krotov_get_states", "krotov_get_tau", "krotov_get_storage", "krotov_get_profile", "krotov_comm_export", "krotov_comm_connect",
 ]
 
 
@@ -86,6 +86,7 @@ def lib():
     L.krotov_get_states.argtypes = [vp, vp]
     L.krotov_get_tau.argtypes = [vp, vp]
     L.krotov_get_storage.argtypes = [vp, i32, i32, i32, i32, vp]
+    L.krotov_get_profile.argtypes = [vp, vp]
     L.krotov_comm_export.argtypes = [vp, vp]
     L.krotov_comm_connect.argtypes = [vp, i32, i32, vp]
     for name in EXPORTS:

@@ -66,9 +66,10 @@ struct krotov_handle_s {
     int nnz_union = 0;
     bool preg = false;
     std::vector<int> cols;  // [Wt][32]
+    std::vector<char> slot_valid;  // [Wt][32] slot holds a real matrix entry (i, cols[s][i])
     int wpc = 1, tpw = 1, nCTA = 1;
     DevBuf d_cols, d_Pf, d_Pb, d_inv_s, d_gen, d_dt, d_alpha, d_eps_old, d_eps_new, d_ga, d_X, d_Phi, d_psi0,
-        d_target, d_chiT, d_chicoef, d_psif, d_tau, d_R, d_err, d_weight;
+        d_target, d_chiT, d_chicoef, d_psif, d_tau, d_R, d_err, d_weight, d_prof;
     DevBuf d_mbox[2];
     ChebyTables cheb[2];
     bool chiT_valid = false, chicoef_valid = false, swept = false;
@@ -199,14 +200,19 @@ int build_pattern(krotov_handle h) {
     h->Wt = pick_width(h->W);
     if (h->Wt < 0) return fail(h, KROTOV_ERR_UNSUPPORTED, "row too wide for the warp path");
     h->cols.assign((size_t)h->Wt * 32, 0);
+    h->slot_valid.assign((size_t)h->Wt * 32, 0);
     for (int s = 0; s < h->Wt; ++s)
         for (int i = 0; i < 32; ++i) h->cols[(size_t)s * 32 + i] = i;  // padding: own column, value 0
     if (use_dia) {
+        // one slot per matrix diagonal; EVERY lane reads x[(i + off) mod 32] so that a warp's LDS.128
+        // gather always touches 32 consecutive 16-byte words (bank-conflict free); entries that are not
+        // in the pattern (or wrapped around) carry the value 0
         int s = 0;
         for (int off : diags) {
-            for (int i = 0; i < d; ++i) {
-                int j = i + off;
-                if (j >= 0 && j < d && pat[(size_t)i * d + j]) h->cols[(size_t)s * 32 + i] = j;
+            for (int i = 0; i < 32; ++i) {
+                const int j = i + off;
+                h->cols[(size_t)s * 32 + i] = (j + 64) & 31;
+                if (i < d && j >= 0 && j < d && pat[(size_t)i * d + j]) h->slot_valid[(size_t)s * 32 + i] = 1;
             }
             ++s;
         }
@@ -214,7 +220,11 @@ int build_pattern(krotov_handle h) {
         for (int i = 0; i < d; ++i) {
             int s = 0;
             for (int j = 0; j < d; ++j)
-                if (i != j && pat[(size_t)i * d + j]) h->cols[(size_t)(s++) * 32 + i] = j;
+                if (i != j && pat[(size_t)i * d + j]) {
+                    h->cols[(size_t)s * 32 + i] = j;
+                    h->slot_valid[(size_t)s * 32 + i] = 1;
+                    ++s;
+                }
         }
     }
     return KROTOV_OK;
@@ -233,8 +243,8 @@ void build_rows(krotov_handle h, int dir, std::vector<cplx> &out) {
             cplx *row = &out[((size_t)g * (1 + L) + t) * (Wt + 1) * 32];
             for (int i = 0; i < d; ++i) {
                 for (int sl = 0; sl < Wt; ++sl) {
+                    if (!h->slot_valid[(size_t)sl * 32 + i]) continue;
                     const int j = h->cols[(size_t)sl * 32 + i];
-                    if (j == i) continue;
                     const cplx v = (dir == KROTOV_FORWARD) ? Hval(h, g, t, i, j) : std::conj(Hval(h, g, t, j, i));
                     row[(size_t)sl * 32 + i] = f * v;
                 }
@@ -301,7 +311,7 @@ int choose_launch(krotov_handle h) {
 
 size_t warp_smem_bytes(const krotov_handle h) {
     return (size_t)h->wpc * 2 * 32 * 16 + (size_t)h->wpc * h->tpw * 32 * 16 + (size_t)h->L * h->wpc * 32 * 8 +
-           kr::kMaxCtrl * 8;
+           kr::kMaxCtrl * 8 + (size_t)kr::kMaxCtrl * 160 * 8;
 }
 
 int launch_warp(krotov_handle h, int mode) {
@@ -329,10 +339,12 @@ int launch_warp(krotov_handle h, int mode) {
     p.chi_coef = (const double2 *)h->d_chicoef.p;
     p.psi_final = (double2 *)h->d_psif.p; p.tau = (double2 *)h->d_tau.p;
     p.R = (double *)h->d_R.p;
+    p.E = (double *)h->d_R.p + (size_t)h->N_T * h->nCTA * h->L;
     p.rank = h->rank; p.world = h->world;
     const int par = (int)(h->iter_count & 1);
     for (int r = 0; r < h->world && r < kr::kMaxRanks; ++r) p.mbox[r] = h->peer_mbox[par][r];
     p.err_flag = (int *)h->d_err.p;
+    p.prof = (long long *)h->d_prof.p;
     p.timeout_cycles = 20000000000ll;  // ~10 s
     if (const char *e = getenv("KROTOV_TIMEOUT_CYCLES")) p.timeout_cycles = atoll(e);
 
@@ -382,7 +394,7 @@ int krotov_destroy(krotov_handle h) {
                 if (h->peer_mbox[par][r]) cudaIpcCloseMemHandle(h->peer_mbox[par][r]);
     DevBuf *bufs[] = {&h->d_cols, &h->d_Pf, &h->d_Pb, &h->d_inv_s, &h->d_gen, &h->d_dt, &h->d_alpha,
                       &h->d_eps_old, &h->d_eps_new, &h->d_ga, &h->d_X, &h->d_Phi, &h->d_psi0, &h->d_target,
-                      &h->d_chiT, &h->d_chicoef, &h->d_psif, &h->d_tau, &h->d_R, &h->d_err, &h->d_weight,
+                      &h->d_chiT, &h->d_chicoef, &h->d_psif, &h->d_tau, &h->d_R, &h->d_err, &h->d_weight, &h->d_prof,
                       &h->d_mbox[0], &h->d_mbox[1]};
     for (DevBuf *b : bufs) b->release();
     for (int dir = 0; dir < 2; ++dir) {
@@ -531,7 +543,11 @@ int krotov_create(const krotov_problem *pb, krotov_handle *out) {
         if ((rc = dev_alloc(h, h->d_chiT, (size_t)N * 32 * 16))) return bail(rc);
         if ((rc = dev_alloc(h, h->d_psif, (size_t)N * 32 * 16))) return bail(rc);
         cudaMemset(h->d_psif.p, 0, (size_t)N * 32 * 16);
-        if ((rc = dev_alloc(h, h->d_R, (size_t)N_T * h->nCTA * L * 8))) return bail(rc);
+        if ((rc = dev_alloc(h, h->d_R, ((size_t)N_T * h->nCTA * L + (size_t)N_T * L) * 8))) return bail(rc);
+        if (getenv("KROTOV_PROF")) {
+            if ((rc = dev_alloc(h, h->d_prof, (size_t)h->nCTA * 8 * 8))) return bail(rc);
+            cudaMemset(h->d_prof.p, 0, h->d_prof.bytes);
+        }
         for (int par = 0; par < 2; ++par) {
             if ((rc = dev_alloc(h, h->d_mbox[par], (size_t)N_T * kr::kMaxRanks * L * 8))) return bail(rc);
             cudaMemset(h->d_mbox[par].p, 0xFF, h->d_mbox[par].bytes);
@@ -718,7 +734,7 @@ int krotov_iterate(krotov_handle h, const double *guess_pulses, double *new_puls
         h->launches_last += 1;
     }
     if (h->path == KROTOV_PATH_WARP) {
-        if (h->nCTA > 1) KR_CUDA(h, cudaMemsetAsync(h->d_R.p, 0xFF, h->d_R.bytes, h->stream));
+        if (h->nCTA > 1 || h->world > 1) KR_CUDA(h, cudaMemsetAsync(h->d_R.p, 0xFF, h->d_R.bytes, h->stream));
         if (h->world > 1) {
             // the mailbox of the NEXT iteration's parity is cleared now (peers are at most one iteration ahead)
             const int nxt = (int)((h->iter_count + 1) & 1);
@@ -788,6 +804,18 @@ int krotov_get_storage(krotov_handle h, int which, int k, int n0, int n1, double
         std::string e;
         if (!kr::dense_get_storage(h->dense, which, k, n0, n1, out, e)) return fail(h, KROTOV_ERR_CUDA, e);
     }
+    return KROTOV_OK;
+}
+
+int krotov_get_profile(krotov_handle h, int64_t *out) {
+    if (!h || !out) return KROTOV_ERR_ARG;
+    for (int i = 0; i < 8; ++i) out[i] = 0;
+    if (!h->d_prof.p) return fail(h, KROTOV_ERR_STATE, "profiling counters are off (set KROTOV_PROF=1 before krotov_create)");
+    cudaSetDevice(h->device);
+    std::vector<long long> tmp((size_t)h->nCTA * 8);
+    KR_CUDA(h, cudaMemcpy(tmp.data(), h->d_prof.p, tmp.size() * 8, cudaMemcpyDeviceToHost));
+    for (int c = 0; c < h->nCTA; ++c)
+        for (int i = 0; i < 8; ++i) out[i] = std::max<int64_t>(out[i], tmp[(size_t)c * 8 + i]);
     return KROTOV_OK;
 }
 

@@ -21,10 +21,13 @@
 // shared memory and arrive on named barrier A; the comm warp reduces them in a fixed order,
 // publishes the CTA partial into the step-indexed exchange array R[n][cta][l] (pre-filled with
 // a NaN sentinel, so the 8-byte value is its own "ready" flag -- no fence, no atomics), polls
-// the slots of all CTAs, sums them in CTA order (bitwise reproducible, identical in every CTA),
-// applies the update and releases the trajectory warps through named barrier B.  With several
-// ranks, CTA 0 additionally pushes the rank's sum into every peer's mailbox over NVLink (P2P
-// stores) and every CTA sums the `world` mailbox slots in rank order.
+// the slots of all CTAs, sums them in a fixed order (bitwise reproducible),
+// applies the update and releases the trajectory warps through named barrier B.  The gather is done
+// by ONE reducer (the comm warp of CTA 0), which then broadcasts the L sums through E[n][l]; the other
+// CTAs spin on that single line.  (An all-gather in which every CTA polled every slot made 147 CTAs
+// hammer the same ~20 L2 lines and cost 7 us per step.)  With several ranks the reducer additionally
+// pushes the rank's sum into every peer's mailbox over NVLink (P2P stores) and sums the `world`
+// mailbox slots in rank order before broadcasting.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -64,11 +67,13 @@ struct WarpParams {
     const double2 *chi_coef;   // [N]
     double2 *psi_final;        // [N][32]
     double2 *tau;              // [N]
-    double *R;                 // [N_T][nCTA][L] exchange, sentinel-filled
+    double *R;                 // [N_T][L][nCTA] CTA partial sums, sentinel-filled before every iteration
+    double *E;                 // [N_T][L] grid-wide sums broadcast by the reducer (CTA 0), sentinel-filled
     int rank, world;
     double *mbox[kMaxRanks];   // mailbox of every rank (this iteration's parity): [N_T][world][L]
     int *err_flag;
     long long timeout_cycles;
+    long long *prof;           // optional [nCTA][8] cycle counters (KROTOV_PROF=1), see krotov_get_profile
 };
 
 __device__ __forceinline__ void st_relaxed_f64(double *p, double v) {
@@ -82,7 +87,9 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const double *p) {
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-// acc += G_row . v   (complex), two independent FMA chains per component
+// acc += G_row . v   (complex).  Two independent FMA chains per component: with 4 chains in flight a
+// warp already issues one DFMA every 2 cycles (the FP64 pipe rate measured on B200, tools/microbench.cu;
+// dependent latency 8 cycles), so more chains only add the instructions that join them.
 template <int W>
 __device__ __forceinline__ void row_dot(const double2 (&g)[W + 1], const int (&col)[W], const double2 *__restrict__ vs,
                                         const double2 own, double &ar, double &ai) {
@@ -153,27 +160,92 @@ __device__ __forceinline__ double warp_sum_xor(double v) {
     return v;
 }
 
-// Wait for `cnt` doubles spaced `stride` apart starting at `base + lane*stride` ... to become
-// non-sentinel; returns their sum in index order for this lane's subset {lane, lane+32, ...}.
-__device__ __forceinline__ double poll_sum(const double *base, int cnt, int stride, int lane, int *err_flag,
-                                           long long timeout) {
-    double s = 0.0;
+__device__ __forceinline__ void st_relaxed_gpu_f64(double *p, double v) {
+    asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+template <bool SYS>
+__device__ __forceinline__ unsigned long long ld_poll_u64(const double *p) {
+    unsigned long long v;
+    if (SYS)
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    else
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+constexpr int kGatherMax = 40;  // ceil(kMaxCtrl * 148 / 32) = 37 values per lane at most
+
+// Reducer side.  Gather `L*cnt` doubles laid out [l][c] at `base` (all loads of a round are in flight
+// before any is examined; the round is repeated until no slot holds the sentinel), park them in shared
+// memory and sum every control's `cnt` values in a FIXED order: the 32 lanes are split into groups of
+// `G = 32 / pow2ceil(L)` lanes, group l sums control l -- lane j of the group adds c = j, j+G, j+2G, ...
+// in order, then an xor butterfly inside the group.  Returns du[l] in tot[l] on every lane.
+template <bool SYS>
+__device__ __forceinline__ void reducer_gather(const double *base, const int cnt, const int L, const int lane,
+                                               double *gbuf, double (&tot)[kMaxCtrl], int *err_flag,
+                                               const long long timeout) {
+    const int total = L * cnt;
+    const int nper = (total + 31) >> 5;  // values per lane
     const long long t0 = clock64();
-    for (int c = lane; c < cnt; c += 32) {
-        unsigned long long u = ld_relaxed_u64(base + (size_t)c * stride);
-        int spins = 0;
-        while (u == kSentinel) {
-            if ((++spins & 1023) == 0) {
-                if (clock64() - t0 > timeout || *(volatile int *)err_flag) {
-                    atomicExch(err_flag, 1);
-                    return 0.0;
-                }
+    int spins = 0;
+    for (;;) {
+        bool pending = false;
+        for (int jb = 0; jb < nper; jb += 12) {  // 12 loads in flight per lane per batch (384 slots)
+            unsigned long long u[12];
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+                const int idx = lane + 32 * (jb + j);
+                u[j] = ld_poll_u64<SYS>(base + (idx < total ? idx : 0));
             }
-            u = ld_relaxed_u64(base + (size_t)c * stride);
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+                const int idx = lane + 32 * (jb + j);
+                pending |= (u[j] == kSentinel);
+                if (idx < total) gbuf[idx] = __longlong_as_double((long long)u[j]);
+            }
         }
-        s += __longlong_as_double((long long)u);
+        if (!__any_sync(0xffffffffu, pending)) break;
+        if ((++spins & 63) == 0) {
+            if (clock64() - t0 > timeout || *(volatile int *)err_flag) {
+                atomicExch(err_flag, 1);
+                break;
+            }
+        }
     }
-    return s;
+    __syncwarp();
+    int p2 = 1;
+    while (p2 < L) p2 <<= 1;
+    const int G = 32 / p2;          // lanes per control
+    const int myl = lane / G;       // control this lane works for
+    const int j0 = lane - myl * G;
+    double sacc = 0.0;
+    if (myl < L)
+        for (int c = j0; c < cnt; c += G) sacc += gbuf[myl * cnt + c];
+    for (int o = G >> 1; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+#pragma unroll
+    for (int l = 0; l < kMaxCtrl; ++l) tot[l] = __shfl_sync(0xffffffffu, sacc, (l < L ? l : 0) * G);
+    __syncwarp();
+}
+
+// Everyone else: spin on the L broadcast words E[n][0..L-1] written by the reducer.
+__device__ __forceinline__ void poll_broadcast(const double *E, const int L, const int lane, double (&tot)[kMaxCtrl],
+                                               int *err_flag, const long long timeout) {
+    const long long t0 = clock64();
+    int spins = 0;
+    unsigned long long u;
+    for (;;) {
+        u = ld_poll_u64<false>(E + (lane < L ? lane : 0));
+        if (__all_sync(0xffffffffu, u != kSentinel)) break;
+        if ((++spins & 63) == 0) {
+            if (clock64() - t0 > timeout || *(volatile int *)err_flag) {
+                atomicExch(err_flag, 1);
+                break;
+            }
+        }
+    }
+    const double v = __longlong_as_double((long long)u);
+#pragma unroll
+    for (int l = 0; l < kMaxCtrl; ++l) tot[l] = __shfl_sync(0xffffffffu, v, l < L ? l : 0);
 }
 
 template <int W, int LT /*0 = runtime L, rows reloaded from L1/L2 per use*/, int MAXTHREADS>
@@ -190,6 +262,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
     double2 *psis = vbuf + (size_t)wpc * 2 * 32;                  // [wpc][tpw][32]
     double *red = reinterpret_cast<double *>(psis + (size_t)wpc * tpw * 32);  // [L][wpc*32]
     double *eps_s = red + (size_t)L * wpc * 32;                   // [kMaxCtrl]
+    double *gbuf = eps_s + kMaxCtrl;                              // [kMaxCtrl * 160] reducer scratch (CTA 0)
     const int nthr_all = (wpc + 1) * 32;
     const int N_T = p.N_T;
     const bool is_comm = (warp == wpc);
@@ -198,6 +271,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
         // ---------------------------------------------------------------- communication warp
         if (p.mode != 1) return;
         double ga = 0.0;  // lane l accumulates g_a_int[l]  (CTA 0 writes it)
+        long long c_wait_a = 0, c_reduce = 0, c_gather = 0;
         for (int n = 0; n < N_T; ++n) {
             double a_ln = 0.0, e_old = 0.0, dtn = 0.0;
             if (lane < L) {
@@ -205,27 +279,64 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
                 e_old = p.eps_old[(size_t)lane * N_T + n];
                 dtn = p.dt[n];
             }
+            const long long c0 = clock64();
             bar_sync(1, nthr_all);  // barrier A: partials are in `red`
-            double mine = 0.0;      // lane l ends up holding du[l]
-            for (int l = 0; l < L; ++l) {
-                double s = 0.0;
-                for (int q = 0; q < wpc; ++q) s += red[(size_t)l * wpc * 32 + q * 32 + lane];
-                s = warp_sum_xor(s);
-                if (p.nCTA > 1) {
-                    double *slot = p.R + ((size_t)n * p.nCTA) * L + l;
-                    if (lane == 0) st_relaxed_f64(slot + (size_t)blockIdx.x * L, s);
-                    s = poll_sum(slot, p.nCTA, L, lane, p.err_flag, p.timeout_cycles);
-                    s = warp_sum_xor(s);
-                }
-                if (p.world > 1) {
-                    if (blockIdx.x == 0 && lane < p.world)
-                        st_relaxed_f64(p.mbox[lane] + ((size_t)n * p.world + p.rank) * L + l, s);
-                    s = poll_sum(p.mbox[p.rank] + ((size_t)n * p.world) * L + l, p.world, L, lane, p.err_flag,
-                                 p.timeout_cycles);
-                    s = warp_sum_xor(s);
-                }
-                if (lane == l) mine = s;
+            const long long c1 = clock64();
+            double tot[kMaxCtrl];
+#pragma unroll
+            for (int l = 0; l < kMaxCtrl; ++l) {
+                double sacc = 0.0;
+                if (l < L)
+                    for (int q = 0; q < wpc; ++q) sacc += red[(size_t)l * wpc * 32 + q * 32 + lane];
+                tot[l] = sacc;
             }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int l = 0; l < kMaxCtrl; ++l)
+                    if (l < L) tot[l] += __shfl_xor_sync(0xffffffffu, tot[l], o);
+            }
+            const long long c2 = clock64();
+            if (p.nCTA > 1 || p.world > 1) {
+                // R[n][l][cta]: CTA partials;  E[n][l]: the grid-wide (and rank-wide) sums, written by the reducer
+                double *Rn = p.R + (size_t)n * L * p.nCTA;
+                double *En = p.E + (size_t)n * L;
+                if (blockIdx.x != 0) {
+#pragma unroll
+                    for (int l = 0; l < kMaxCtrl; ++l)
+                        if (l < L && lane == l) st_relaxed_gpu_f64(Rn + (size_t)l * p.nCTA + blockIdx.x, tot[l]);
+                    poll_broadcast(En, L, lane, tot, p.err_flag, p.timeout_cycles);
+                } else {
+                    if (p.nCTA > 1) {
+#pragma unroll
+                        for (int l = 0; l < kMaxCtrl; ++l)
+                            if (l < L && lane == l) st_relaxed_gpu_f64(Rn + (size_t)l * p.nCTA, tot[l]);
+                        reducer_gather<false>(Rn, p.nCTA, L, lane, gbuf, tot, p.err_flag, p.timeout_cycles);
+                    }
+                    if (p.world > 1) {
+                        const size_t off = (size_t)n * L * p.world;  // mailbox layout [n][l][rank]
+#pragma unroll
+                        for (int l = 0; l < kMaxCtrl; ++l)
+                            if (l < L && lane < p.world)
+                                st_relaxed_f64(p.mbox[lane] + off + (size_t)l * p.world + p.rank, tot[l]);
+                        reducer_gather<true>(p.mbox[p.rank] + off, p.world, L, lane, gbuf, tot, p.err_flag,
+                                             p.timeout_cycles);
+                    }
+                    if (p.nCTA > 1) {
+#pragma unroll
+                        for (int l = 0; l < kMaxCtrl; ++l)
+                            if (l < L && lane == l) st_relaxed_gpu_f64(En + l, tot[l]);
+                    }
+                }
+            }
+            const long long c3 = clock64();
+            c_wait_a += c1 - c0;
+            c_reduce += c2 - c1;
+            c_gather += c3 - c2;
+            double mine = 0.0;  // lane l holds du[l]
+#pragma unroll
+            for (int l = 0; l < kMaxCtrl; ++l)
+                if (lane == l) mine = tot[l];
             if (lane < L) {
                 const double d_eps = __dmul_rn(a_ln, mine);      // src/optimize.jl:355
                 const double e_new = __dadd_rn(e_old, d_eps);    // :356
@@ -238,6 +349,11 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
             bar_arrive(2, nthr_all);  // barrier B: eps_s is valid
         }
         if (blockIdx.x == 0 && lane < L) p.g_a_int[lane] = ga;
+        if (p.prof != nullptr && lane == 0) {
+            p.prof[blockIdx.x * 8 + 3] = c_wait_a;
+            p.prof[blockIdx.x * 8 + 4] = c_reduce;
+            p.prof[blockIdx.x * 8 + 5] = c_gather;
+        }
         return;
     }
 
@@ -256,6 +372,8 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
     double2 P[NT][W + 1];                            // PREG: per-term rows of this lane's trajectory
     double2 g[W + 1];
 
+    const long long t_begin = clock64();
+    long long t_wait_b = 0;
     // ================================================================ backward sweep
     if (p.mode == 1) {
         for (int t = 0; t < tpw; ++t) {
@@ -316,6 +434,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
         }
     }
 
+    const long long t_bw_end = clock64();
     // ================================================================ forward sweep
     double2 psi_reg = make_double2(0.0, 0.0);
     for (int t = 0; t < tpw; ++t) {
@@ -375,7 +494,9 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
                 if (l < L) red[(size_t)l * wpc * 32 + warp * 32 + lane] = part[l];
             bar_arrive(1, nthr_all);  // barrier A
             if (n + 1 < N_T && k0 < p.N) chi_next = p.X[((size_t)k0 * (N_T + 1) + n + 1) * 32 + lane];
+            const long long w0 = clock64();
             bar_sync(2, nthr_all);    // barrier B: updated pulse value is in eps_s
+            t_wait_b += clock64() - w0;
 #pragma unroll
             for (int l = 0; l < (PREG ? LT : kMaxCtrl); ++l)
                 if (l < L) eps[l] = eps_s[l];
@@ -430,6 +551,12 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
         }
     }
 
+    if (p.prof != nullptr && warp == 0 && lane == 0) {
+        const long long t_end = clock64();
+        p.prof[blockIdx.x * 8 + 0] = t_bw_end - t_begin;
+        p.prof[blockIdx.x * 8 + 1] = t_end - t_bw_end;
+        p.prof[blockIdx.x * 8 + 2] = t_wait_b;
+    }
     // ---- final states and tau_k = <tgt_k|psi_k(T)>  (src/optimize.jl:378-381)
     for (int t = 0; t < tpw; ++t) {
         const int k = kbase + t;

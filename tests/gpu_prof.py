@@ -1,0 +1,16 @@
+"""Ad-hoc: in-kernel cycle counters of one iteration for several ensemble sizes (KROTOV_PROF=1)."""
+import os, sys
+os.environ["KROTOV_PROF"] = "1"
+sys.path.insert(0, "tests")
+from util import *  # noqa
+for ns in [1, 8, 64, 256]:
+    w = W.c4_ensemble(n_samples=ns)
+    out = {}
+    def cb(wrk, it, a, b):
+        if it >= 1:
+            out["prof"] = wrk.engine.profile(); out["info"] = wrk.engine.info()
+    K.optimize(to_problem(w, iter_stop=3, callback=cb), method=K.Krotov)
+    pr, info = out["prof"], out["info"]
+    ghz = 1.965
+    print(f"samples={ns:4d} grid={info['grid_blocks']}x{info['block_threads']} ms={info['ms_last']:.2f} | " +
+          " ".join(f"{k}={v/ghz/1e3/w.N_T:.3f}us/step" for k, v in pr.items()))
