@@ -177,12 +177,13 @@ int krotov_get_tau(krotov_handle h, double *tau /* cplx[N] */);
  * store_fw).  out: cplx[n1-n0][d].  Backs wrk.fw_storage / wrk.bw_storage for callbacks. */
 int krotov_get_storage(krotov_handle h, int which, int k, int n0, int n1, double *out);
 
-/* Diagnostic cycle counters of the last krotov_iterate on the WARP path (max over CTAs), available
+/* Diagnostic cycle counters of the last krotov_iterate on the WARP path (of CTA `cta`, or the max over
+ * all CTAs for cta = -1), available
  * when the environment variable KROTOV_PROF=1 was set at krotov_create:
  *   out[0] backward sweep, out[1] forward sweep, out[2] trajectory warp 0 waiting for the updated pulse,
  *   out[3] comm warp waiting for its CTA's partials, out[4] CTA-local reduction, out[5] grid/peer gather.
  * SM clock cycles; out has 8 entries. */
-int krotov_get_profile(krotov_handle h, int64_t *out);
+int krotov_get_profile(krotov_handle h, int cta, int64_t *out);
 
 /* ---- multi-GPU (one process per GPU; trajectories sharded across ranks) ----------------
  * The only per-step cross-GPU dependency is the L-vector of overlap sums

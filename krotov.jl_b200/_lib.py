@@ -86,7 +86,7 @@ def lib():
     L.krotov_get_states.argtypes = [vp, vp]
     L.krotov_get_tau.argtypes = [vp, vp]
     L.krotov_get_storage.argtypes = [vp, i32, i32, i32, i32, vp]
-    L.krotov_get_profile.argtypes = [vp, vp]
+    L.krotov_get_profile.argtypes = [vp, i32, vp]
     L.krotov_comm_export.argtypes = [vp, vp]
     L.krotov_comm_connect.argtypes = [vp, i32, i32, vp]
     for name in EXPORTS:

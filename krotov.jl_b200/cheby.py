@@ -87,21 +87,28 @@ class ChebyDirection:
 
     def _derive(self):
         n_gen = len(self.H0)
-        self.E_min = np.empty(n_gen)
-        self.Delta = np.empty(n_gen)
         lo = [r[0] for r in self.control_ranges]
         hi = [r[1] for r in self.control_ranges]
-        for g in range(n_gen):
-            if self.manual is not None:
-                e_min, e_max = self.manual
-            else:
-                e_min, e_max = specrange(self._evaluate(g, hi), self.method)
-                e_min2, e_max2 = specrange(self._evaluate(g, lo), self.method)
-                e_min, e_max = min(e_min, e_min2), max(e_max, e_max2)
-            Delta = e_max - e_min
-            delta = self.buffer * Delta
-            self.E_min[g] = e_min - delta / 2
-            self.Delta[g] = Delta + delta
+        if self.manual is not None:
+            e_min = np.full(n_gen, self.manual[0])
+            e_max = np.full(n_gen, self.manual[1])
+        elif self.method in ("auto", "diag") and self.H0[0].shape[0] <= 512:
+            # all generators in two batched LAPACK calls (numpy loops over the stack in C and calls the same
+            # zgeev per matrix, so every number is what `specrange` returns for the single matrix)
+            ev_hi = np.linalg.eigvals(np.stack([self._evaluate(g, hi) for g in range(n_gen)])).real
+            ev_lo = np.linalg.eigvals(np.stack([self._evaluate(g, lo) for g in range(n_gen)])).real
+            e_min = np.minimum(ev_hi.min(axis=1), ev_lo.min(axis=1))
+            e_max = np.maximum(ev_hi.max(axis=1), ev_lo.max(axis=1))
+        else:
+            e_min, e_max = np.empty(n_gen), np.empty(n_gen)
+            for g in range(n_gen):
+                a0, b0 = specrange(self._evaluate(g, hi), self.method)
+                a1, b1 = specrange(self._evaluate(g, lo), self.method)
+                e_min[g], e_max[g] = min(a0, a1), max(b0, b1)
+        Delta = e_max - e_min
+        delta = self.buffer * Delta
+        self.E_min = e_min - delta / 2
+        self.Delta = Delta + delta
         self._tabulate()
 
     def _tabulate(self):

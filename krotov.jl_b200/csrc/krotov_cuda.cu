@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <complex>
 #include <cstdio>
@@ -27,6 +28,20 @@ using cplx = std::complex<double>;
 namespace {
 
 thread_local std::string g_create_error = "";
+
+// KROTOV_TRACE=1 prints host-side timings of the non-hot-path entry points to stderr
+struct Trace {
+    const char *what;
+    std::chrono::steady_clock::time_point t0;
+    bool on;
+    explicit Trace(const char *w) : what(w), t0(std::chrono::steady_clock::now()), on(getenv("KROTOV_TRACE") != nullptr) {}
+    void lap(const char *label) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[krotov trace] %s: %s %.3f ms\n", what, label, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 struct DevBuf {
     void *p = nullptr;
@@ -591,6 +606,7 @@ int krotov_set_cheby(krotov_handle h, int direction, int n_dt_class, const int32
     if (direction != KROTOV_FORWARD && direction != KROTOV_BACKWARD) return fail(h, KROTOV_ERR_ARG, "bad direction");
     if (n_dt_class < 1 || !dt_class_of_step || !dt_of_class || !E_min || !Delta || !m || !coeffs || m_max < 1)
         return fail(h, KROTOV_ERR_ARG, "bad argument to krotov_set_cheby");
+    Trace tr("set_cheby");
     cudaSetDevice(h->device);
     ChebyTables &ct = h->cheb[direction];
     for (int n = 0; n < h->N_T; ++n)
@@ -628,15 +644,18 @@ int krotov_set_cheby(krotov_handle h, int direction, int n_dt_class, const int32
     if ((rc = upload(h, ct.m, ct.m_host))) return rc;
     if ((rc = upload(h, ct.phase, ct.phase_host))) return rc;
     ct.set = true;
+    tr.lap("tables uploaded");
     if (h->path == KROTOV_PATH_WARP) {
         std::vector<cplx> rows;
         build_rows(h, direction, rows);
+        tr.lap("rows built");
         if ((rc = upload(h, direction == KROTOV_FORWARD ? h->d_Pf : h->d_Pb, rows))) return rc;
         if (direction == KROTOV_FORWARD) {
             std::vector<double> inv_s(h->n_gen);
             for (int g = 0; g < h->n_gen; ++g) inv_s[g] = Delta[g] / 4.0;
             if ((rc = upload(h, h->d_inv_s, inv_s))) return rc;
         }
+        tr.lap("rows uploaded");
     } else {
         std::string e;
         if (!kr::dense_set_cheby(h->dense, direction, n_dt_class, ct.dtc_of_step, ct.E_min, ct.Delta, ct.m_host,
@@ -807,15 +826,17 @@ int krotov_get_storage(krotov_handle h, int which, int k, int n0, int n1, double
     return KROTOV_OK;
 }
 
-int krotov_get_profile(krotov_handle h, int64_t *out) {
+int krotov_get_profile(krotov_handle h, int cta, int64_t *out) {
     if (!h || !out) return KROTOV_ERR_ARG;
     for (int i = 0; i < 8; ++i) out[i] = 0;
     if (!h->d_prof.p) return fail(h, KROTOV_ERR_STATE, "profiling counters are off (set KROTOV_PROF=1 before krotov_create)");
     cudaSetDevice(h->device);
     std::vector<long long> tmp((size_t)h->nCTA * 8);
     KR_CUDA(h, cudaMemcpy(tmp.data(), h->d_prof.p, tmp.size() * 8, cudaMemcpyDeviceToHost));
+    if (cta >= h->nCTA) return fail(h, KROTOV_ERR_ARG, "cta out of range");
     for (int c = 0; c < h->nCTA; ++c)
-        for (int i = 0; i < 8; ++i) out[i] = std::max<int64_t>(out[i], tmp[(size_t)c * 8 + i]);
+        if (cta < 0 || c == cta)
+            for (int i = 0; i < 8; ++i) out[i] = std::max<int64_t>(out[i], tmp[(size_t)c * 8 + i]);
     return KROTOV_OK;
 }
 

@@ -154,6 +154,24 @@ __device__ __forceinline__ double2 cheby_step(const double2 psi, const double2 (
     return make_double2(phase.x * outr - phase.y * outi, phase.x * outi + phase.y * outr);
 }
 
+// Per-step propagator metadata (coefficient count, final phase, coefficient row).  It is fetched ONE STEP
+// AHEAD: the dependent chain dt-class -> (m, phase, row) is three L1/L2 round trips that would otherwise
+// sit at the head of every time step.
+struct StepMeta {
+    int m;
+    double2 phase;
+    const double *a;
+};
+__device__ __forceinline__ StepMeta load_meta(const int *dtc, const int *m_tab, const double2 *ph_tab,
+                                              const double *coef, int ndtc, int mmax, int gi, int n) {
+    const int ci = gi * ndtc + dtc[n];
+    StepMeta s;
+    s.m = m_tab[ci];
+    s.phase = ph_tab[ci];
+    s.a = coef + (size_t)ci * mmax;
+    return s;
+}
+
 __device__ __forceinline__ double warp_sum_xor(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -227,7 +245,9 @@ __device__ __forceinline__ void reducer_gather(const double *base, const int cnt
     __syncwarp();
 }
 
-// Everyone else: spin on the L broadcast words E[n][0..L-1] written by the reducer.
+// Everyone else: spin on the L broadcast words E[n][0..L-1] written by the reducer.  (Keeping several
+// staggered poll loads in flight was measured and does not help: the wait is dominated by the two L2
+// signalling hops, 690 cycles same-die / 1075 cross-die each, tools/pingpong.cu.)
 __device__ __forceinline__ void poll_broadcast(const double *E, const int L, const int lane, double (&tot)[kMaxCtrl],
                                                int *err_flag, const long long timeout) {
     const long long t0 = clock64();
@@ -397,15 +417,22 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
             Xk[(size_t)N_T * 32 + lane] = chi;
             mypsi[t * 32 + lane] = chi;
             __syncwarp();
+            StepMeta meta = load_meta(p.dtc_b, p.m_b, p.phase_b, p.coef_b, p.ndtc_b, p.mmax_b, gi, N_T - 1);
+            double e_cur[kMaxCtrl];
+#pragma unroll
+            for (int l = 0; l < kMaxCtrl; ++l) e_cur[l] = (l < L) ? p.eps_old[(size_t)l * N_T + N_T - 1] : 0.0;
             for (int n = N_T - 1; n >= 0; --n) {
-                const int dtc = p.dtc_b[n];
-                const int ci = gi * p.ndtc_b + dtc;
+                const int nn = n > 0 ? n - 1 : 0;  // prefetch the next step's metadata and pulse values
+                const StepMeta meta_next = load_meta(p.dtc_b, p.m_b, p.phase_b, p.coef_b, p.ndtc_b, p.mmax_b, gi, nn);
+                double e_next[kMaxCtrl];
+#pragma unroll
+                for (int l = 0; l < kMaxCtrl; ++l) e_next[l] = (l < L) ? p.eps_old[(size_t)l * N_T + nn] : 0.0;
                 if (PREG) {
 #pragma unroll
                     for (int s = 0; s <= W; ++s) g[s] = P[0][s];
 #pragma unroll
                     for (int l = 0; l < NT - 1; ++l) {
-                        const double e = p.eps_old[(size_t)l * N_T + n];
+                        const double e = e_cur[l];
 #pragma unroll
                         for (int s = 0; s <= W; ++s) {
                             g[s].x = fma(e, P[l + 1][s].x, g[s].x);
@@ -415,7 +442,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
                 } else {
                     load_row<W>(Pg, g, lane);
                     for (int l = 0; l < L; ++l) {
-                        const double e = p.eps_old[(size_t)l * N_T + n];
+                        const double e = p.eps_old[(size_t)l * N_T + n];  // (runtime index: reload, L1 hit)
                         const double2 *Pl = Pg + (size_t)(l + 1) * rowstride;
 #pragma unroll
                         for (int s = 0; s <= W; ++s) {
@@ -425,8 +452,10 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
                         }
                     }
                 }
-                chi = cheby_step<W>(chi, g, col, mypsi + t * 32, bufA, bufB, p.coef_b + (size_t)ci * p.mmax_b,
-                                    p.m_b[ci], p.phase_b[ci], lane);
+                chi = cheby_step<W>(chi, g, col, mypsi + t * 32, bufA, bufB, meta.a, meta.m, meta.phase, lane);
+                meta = meta_next;
+#pragma unroll
+                for (int l = 0; l < kMaxCtrl; ++l) e_cur[l] = e_next[l];
                 mypsi[t * 32 + lane] = chi;
                 __syncwarp();
                 Xk[(size_t)n * 32 + lane] = chi;
@@ -455,6 +484,8 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
 #pragma unroll
         for (int q = 0; q < NT; ++q) load_row<W>(Pg + q * rowstride, P[q], lane);
     }
+    const double inv_s0 = (k0 < p.N) ? p.inv_s_f[g0] : 0.0;
+    StepMeta fmeta = load_meta(p.dtc_f, p.m_f, p.phase_f, p.coef_f, p.ndtc_f, p.mmax_f, g0, 0);
     double2 chi_next = make_double2(0.0, 0.0);
     if (p.mode == 1 && k0 < p.N) chi_next = p.X[(size_t)k0 * (N_T + 1) * 32 + lane];
 
@@ -469,7 +500,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
                 const int k = kbase + t;
                 if (k >= p.N) break;
                 const int gi = (t == 0) ? g0 : p.gen_of_traj[k];
-                const double inv_s = p.inv_s_f[gi];
+                const double inv_s = (t == 0) ? inv_s0 : p.inv_s_f[gi];
                 const double2 psi = (tpw == 1) ? psi_reg : mypsi[t * 32 + lane];
                 const double2 chi = (t == 0) ? chi_next : p.X[((size_t)k * (N_T + 1) + n) * 32 + lane];
                 if (PREG) {
@@ -506,12 +537,13 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
                 if (l < L) eps[l] = p.eps_old[(size_t)l * N_T + n];
         }
         // ---- forward step with the (updated) pulse value  (src/optimize.jl:360-368)
-        const int dtc = p.dtc_f[n];
+        const StepMeta fmeta_next =
+            load_meta(p.dtc_f, p.m_f, p.phase_f, p.coef_f, p.ndtc_f, p.mmax_f, g0, n + 1 < N_T ? n + 1 : n);
         for (int t = 0; t < tpw; ++t) {
             const int k = kbase + t;
             if (k >= p.N) break;
             const int gi = (t == 0) ? g0 : p.gen_of_traj[k];
-            const int ci = gi * p.ndtc_f + dtc;
+            const StepMeta sm = (t == 0) ? fmeta : load_meta(p.dtc_f, p.m_f, p.phase_f, p.coef_f, p.ndtc_f, p.mmax_f, gi, n);
             if (PREG) {
 #pragma unroll
                 for (int s = 0; s <= W; ++s) g[s] = P[0][s];
@@ -537,8 +569,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
                 }
             }
             double2 psi = (tpw == 1) ? psi_reg : mypsi[t * 32 + lane];
-            psi = cheby_step<W>(psi, g, col, mypsi + t * 32, bufA, bufB, p.coef_f + (size_t)ci * p.mmax_f,
-                                p.m_f[ci], p.phase_f[ci], lane);
+            psi = cheby_step<W>(psi, g, col, mypsi + t * 32, bufA, bufB, sm.a, sm.m, sm.phase, lane);
             mypsi[t * 32 + lane] = psi;
             if (t == 0) psi_reg = psi;
             __syncwarp();
@@ -549,6 +580,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
                 p.Phi[((size_t)k * (N_T + 1) + slot) * 32 + lane] = psi;
             }
         }
+        fmeta = fmeta_next;
     }
 
     if (p.prof != nullptr && warp == 0 && lane == 0) {

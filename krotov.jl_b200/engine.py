@@ -135,9 +135,9 @@ class KrotovCuda:
         self._check(self._lib.krotov_get_storage(self._h, int(which), int(k), int(n0), int(n1), _ptr(out)))
         return out
 
-    def profile(self):
+    def profile(self, cta=-1):
         out = np.zeros(8, np.int64)
-        self._check(self._lib.krotov_get_profile(self._h, _ptr(out)))
+        self._check(self._lib.krotov_get_profile(self._h, int(cta), _ptr(out)))
         names = ["backward", "forward", "wait_pulse", "comm_wait_partials", "comm_reduce", "comm_gather"]
         return dict(zip(names, out.tolist()))
 

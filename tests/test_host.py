@@ -1,0 +1,228 @@
+"""Host-side logic of the product, without a GPU: the reference's API semantics, error behaviour,
+the C-ABI export surface, sharding, and a world_size=2 gloo run of the plumbing."""
+import ctypes
+import io
+import os
+import re
+import sys
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+
+import krotov_jl_b200 as K
+import workloads as W
+from util import to_problem
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- C ABI surface -----------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "krotov_cuda.h")).read()
+    declared = set(re.findall(r"^(?:int|const char \*)\s*(krotov_\w+)\(", hdr, flags=re.M))
+    assert len(declared) >= 15
+    lib = ctypes.CDLL(K._lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/krotov_cuda.h but not exported"
+    assert declared == set(K._lib.EXPORTS)
+    assert lib.krotov_abi_version() == 1
+
+
+def test_problem_struct_layout_matches_header():
+    # krotov_create rejects a struct of the wrong size: proves the ctypes mirror and the header agree
+    lib = K._lib.lib()
+    p = K._lib.Problem()
+    p.struct_size = ctypes.sizeof(K._lib.Problem) - 4
+    h = ctypes.c_void_p()
+    assert lib.krotov_create(ctypes.byref(p), ctypes.byref(h)) == 1
+    assert b"struct_size" in lib.krotov_last_error(None)
+
+
+def test_create_without_gpu_fails_loudly():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    w = W.c1_tls()
+    with pytest.raises(K.KrotovCudaError) as ei:
+        K.optimize(to_problem(w, iter_stop=1), method=K.Krotov)
+    assert "KROTOV_ERR_CUDA" in str(ei.value)  # no silent CPU fallback
+
+
+# ---- reference error behaviour -------------------------------------------------------------------
+def test_no_controls_error_message():
+    """test/test_empty_optimization.jl:31-32."""
+    rng = np.random.default_rng(1)
+    H = rng.standard_normal((10, 10))
+    H = H + H.T
+    traj = [K.Trajectory(np.ones(10) / np.sqrt(10), K.hamiltonian(H), target_state=np.eye(10)[0])]
+    assert len(K.get_controls(traj)) == 0
+    problem = K.ControlProblem(traj, np.arange(1001.0), pulse_options={})
+    with pytest.raises(K.ErrorException, match="no controls in trajectories: cannot optimize"):
+        K.optimize(problem, method=K.Krotov)
+
+
+def test_argument_errors():
+    w = W.c1_tls()
+    with pytest.raises(K.ArgumentError, match="must be passed the functional `J_T`"):
+        K.optimize(to_problem(w, J_T=None, iter_stop=1).__class__(to_problem(w).trajectories, w.tlist,
+                                                                   prop_method=K.Cheby, lambda_a=1.0), method=K.Krotov)
+    with pytest.raises(K.ArgumentError, match="superseded by the `callback` argument"):
+        K.optimize(to_problem(w, update_hook=lambda *a: None), method=K.Krotov)
+    with pytest.raises(K.ArgumentError, match="Cheby"):
+        K.optimize(to_problem(w, prop_method="ExpProp"), method=K.Krotov)
+    with pytest.raises(K.ArgumentError, match="propagation method must be specified"):
+        p = to_problem(w)
+        del p.kwargs["prop_method"]
+        K.optimize(p, method=K.Krotov)
+    with pytest.raises(K.ErrorException, match="pulse_options must be defined for all controls"):
+        K.optimize(to_problem(w, pulse_options=K.IdDict()), method=K.Krotov)
+    with pytest.raises(K.ArgumentError, match="store_iter_info"):
+        K.optimize(to_problem(w, print_iters=True, store_iter_info=["nope"]), method=K.Krotov)
+
+
+# ---- controls / shapes ---------------------------------------------------------------------------
+def test_discretize_semantics():
+    t = np.linspace(0, 5, 501)
+    eps = lambda x: 0.2 * K.flattop(x, T=5, t_rise=0.3, func="blackman")  # noqa: E731
+    mid = K.discretize_on_midpoints(eps, t)
+    assert len(mid) == 500 and mid[0] == 0.0 and mid[-1] == 0.0
+    assert mid[10] == eps(t[10] + 0.5 * (t[11] - t[10]))
+    v = np.arange(500.0)
+    c = K.discretize_on_midpoints(v, t)
+    assert c is not v and np.array_equal(c, v)  # must copy (test_pulse_optimization.jl:42)
+    g = K.discretize(v, t)
+    assert len(g) == 501 and g[0] == v[0] and g[-1] == v[-1] and g[7] == 0.5 * (v[6] + v[7])
+    back = K.discretize_on_midpoints(g, t)
+    assert len(back) == 500 and back[0] == g[0] and back[5] == 0.5 * (g[5] + g[6])
+    # same numbers as the oracle's independent restatement
+    from oracle import krotov_oracle as O
+
+    ref = O.discretize_on_midpoints(lambda x: 0.2 * O.flattop(x, T=5, t_rise=0.3), t)
+    assert np.abs(mid - ref).max() < 1e-15  # (the two Blackman formulas round differently in the last bit)
+
+
+def test_get_controls_by_identity_and_derivs():
+    f = lambda t: 1.0  # noqa: E731
+    g = lambda t: 1.0  # noqa: E731
+    sx = np.array([[0, 1], [1, 0]], complex)
+    sz = np.diag([1.0, -1.0]).astype(complex)
+    H1 = K.hamiltonian(sz, (sx, f))
+    H2 = K.hamiltonian(sz, (sx, f), (sz, g))
+    trajs = [K.Trajectory([1, 0], H1), K.Trajectory([1, 0], H2)]
+    ctr = K.get_controls(trajs)
+    assert len(ctr) == 2 and ctr[0] is f and ctr[1] is g
+    d1 = K.get_control_derivs(H1, ctr)
+    assert np.array_equal(d1[0], sx) and d1[1] is None  # `nothing` for a control the generator lacks
+    assert isinstance(K.hamiltonian(sz), np.ndarray)  # no controls -> bare matrix
+
+
+def test_cheby_settings_match_oracle_bits():
+    from oracle import krotov_oracle as O
+
+    w = W.c3_two_transmon(n_grid=101)
+    p = W.to_oracle(w)
+    pulses = [p.pulses[0].copy(), p.pulses[1].copy()]
+    for backward in (False, True):
+        H0 = [h.conj().T for h in p.H0] if backward else p.H0
+        Hc = [[h.conj().T for h in row] for row in p.Hc] if backward else p.Hc
+        mine = K.cheby.ChebyDirection(H0, Hc, p.tlist, backward, pulses)
+        ref = O.ChebyPropagator(H0[0], Hc[0], p.tlist, pulses, backward)
+        assert mine.E_min[0] == ref.E_min and mine.Delta[0] == ref.Delta
+        assert np.array_equal(mine.coeffs[0][0], ref.coeffs)
+        assert mine.reinit(pulses) is True  # first reinit widens to 5x
+        ref.reinit_prop(p.psi0[0], O.transform_control_ranges)
+        assert mine.Delta[0] == ref.Delta and np.array_equal(mine.coeffs[0][0], ref.coeffs)
+        assert mine.reinit(pulses) is False
+        assert mine.reinit([3.0 * pulses[0], pulses[1]]) is True  # 2 x 3 > 5: leaves the stored range
+        assert len(mine.dt_of_class) >= 1 and (np.sign(mine.dt_of_class) == (-1 if backward else 1)).all()
+    assert K.transform_control_ranges(None, -1.0, 2.0, True) == (-2.0, 4.0)
+
+
+def test_result_layout():
+    names = [f.name for f in K.KrotovResult.__dataclass_fields__.values()]
+    assert names == ["tlist", "iter_start", "iter_stop", "iter", "secs", "tau_vals", "J_T", "J_T_prev",
+                     "guess_controls", "optimized_controls", "states", "start_local_time", "end_local_time",
+                     "records", "converged", "message"]  # src/result.jl:34-51
+    r = K.KrotovResult.from_problem(to_problem(W.c1_tls(), iter_start=10, iter_stop=12))
+    assert (r.iter_start, r.iter_stop, r.iter, r.message, r.converged) == (10, 12, 10, "in progress", False)
+    assert len(r.guess_controls[0]) == 501 and r.optimized_controls[0] is not r.guess_controls[0]
+    assert repr(r) == "KrotovResult<in progress>" and "Number of trajectories: 1" in str(r)
+
+
+def test_iteration_table_format():
+    """Header string and column formats of src/optimize.jl:448-492 (pinned by test_iterations.jl:71-74)."""
+
+    class R:
+        J_T, J_T_prev, secs = 0.9514, 0.0, 0.21
+
+    class Wk:
+        result, g_a_int, kwargs = R(), np.array([0.0]), {"iter_stop": 5}
+
+    pr = K.make_krotov_print_iters(store_iter_info=["iter.", "J_T"])
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        rec0 = pr(Wk(), 0)
+        Wk.result.J_T, Wk.result.J_T_prev, Wk.g_a_int = 0.7236, 0.9514, np.array([0.0671])
+        rec1 = pr(Wk(), 1)
+    lines = buf.getvalue().splitlines()
+    assert lines[0] == " iter.        J_T   ∫gₐ(t)dt          J       ΔJ_T         ΔJ    secs"
+    assert lines[1] == "     0   9.51e-01   0.00e+00   9.51e-01        n/a        n/a     0.2"
+    assert lines[2] == "     1   7.24e-01   6.71e-02   7.91e-01  -2.28e-01  -1.61e-01     0.2"
+    assert rec0 == (0, 0.9514) and rec1 == (1, 0.7236)
+
+
+def test_sharding():
+    from krotov_jl_b200.distributed import shard_bounds
+
+    gen = np.repeat(np.arange(256), 4)
+    for world in (1, 2, 4, 8):
+        b = [shard_bounds(gen, r, world) for r in range(world)]
+        assert b[0][0] == 0 and b[-1][1] == 1024
+        assert all(b[r][1] == b[r + 1][0] for r in range(world - 1))
+        assert all((hi - lo) == 1024 // world and lo % 4 == 0 for lo, hi in b)  # whole samples per GPU
+    assert shard_bounds(np.zeros(10, int), 1, 3) == (3, 6)
+    gen = np.repeat(np.arange(3), [5, 1, 6])  # uneven groups: cut at generator boundaries
+    b = [shard_bounds(gen, r, 2) for r in range(2)]
+    assert b == [(0, 6), (6, 12)]
+
+
+def _gloo_worker(rank, world, port, out):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from krotov_jl_b200.distributed import Comm, shard_bounds
+
+        comm = Comm(device=0)
+        gen = np.repeat(np.arange(8), 4)
+        lo, hi = shard_bounds(gen, rank, world)
+        local_tau = (np.arange(lo, hi) + 1j * rank).astype(complex)
+        tau = comm.all_gather_rows(local_tau, len(gen))
+        descs = comm.all_gather_object(bytes([rank]) * 128)
+        # J_T_sm chi coefficients from the gathered tau: identical on all ranks
+        coef = (1.0 / len(gen) ** 2) * np.sum(tau)
+        out.put((rank, lo, hi, tau.real.tolist(), [d[0] for d in descs], complex(coef)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_plumbing():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [(r[1], r[2]) for r in res] == [(0, 16), (16, 32)]
+    assert res[0][3] == res[1][3] == list(map(float, range(32)))
+    assert res[0][4] == res[1][4] == [0, 1]
+    assert res[0][5] == res[1][5]

@@ -1,0 +1,310 @@
+"""Parity of the CUDA path against the oracle, through the public API (which calls the C ABI).
+
+Tolerances are BASELINE.json's: per-iteration J_T within 1e-10 relative, optimised pulses within 1e-9
+max-abs.  J_T carries an absolute floor of 2e-15: J_T_sm = 1 - |F|^2 is a difference of O(1) numbers, so
+2e-16 of rounding in F is 4e-16 in J_T however small J_T is; at
+J_T ~ 1e-5 that alone is 4e-11 relative."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import krotov_jl_b200 as K
+import workloads as W
+from util import run_product, to_problem
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+RTOL_JT, ATOL_JT, ATOL_PULSE = 1e-10, 2e-15, 1e-9
+
+
+def gold(name):
+    with open(os.path.join(GOLD, name + ".json")) as fh:
+        return json.load(fh)
+
+
+def assert_parity(got, ref_JT, ref_pulses, ref_ga=None, rtol=RTOL_JT, atol=ATOL_JT):
+    ref_JT = np.asarray(ref_JT)
+    dj = np.abs(np.asarray(got["J_T"]) - ref_JT)
+    assert np.all(dj <= rtol * np.abs(ref_JT) + atol), (list(got["J_T"]), list(ref_JT), list(dj / np.abs(ref_JT)))
+    assert np.abs(got["pulses"] - np.asarray(ref_pulses)).max() <= ATOL_PULSE
+    if ref_ga is not None:
+        assert np.abs(np.asarray(got["g_a_int"]) - np.asarray(ref_ga)).max() <= 1e-11
+
+
+# ---- BASELINE configs against live oracle and golden vectors ----------------------------------------
+def test_c1_tls_parity_and_reference_inequalities():
+    """configs[0]: test/test_tls_optimization.jl:47-70 with the Chebyshev propagator on both sides."""
+    from oracle import krotov_oracle as O
+
+    w = W.c1_tls()
+    got = run_product(w, 5)
+    ref = O.optimize_krotov(W.to_oracle(w), 5)
+    assert_parity(got, ref["J_T"], ref["pulses"], ref["g_a_int"])
+    res = got["result"]
+    assert res.J_T < 1e-3  # test_tls_optimization.jl:66
+    assert 1.0 < np.abs(res.optimized_controls[0]).max() < 1.2  # :67
+    assert len(res.optimized_controls[0]) == 501 and res.converged
+    assert res.message == "Reached maximum number of iterations"
+    g = gold("c1_tls_cheby")
+    assert_parity(got, g["J_T"], g["pulses"], g["g_a_int"])
+
+
+def test_c2_single_transmon_parity():
+    from oracle import krotov_oracle as O
+
+    w = W.c2_transmon_x()
+    got = run_product(w, 4)
+    ref = O.optimize_krotov(W.to_oracle(w), 4)
+    assert_parity(got, ref["J_T"], ref["pulses"], ref["g_a_int"])
+    assert got["info"]["grid_blocks"] == 1  # tiny Hilbert space: a single persistent CTA
+
+
+def test_c3_two_transmon_golden():
+    """configs[2] at full size (d=25, 4 trajectories, L=2, 2000 steps) against the committed golden vector."""
+    g = gold("c3_two_transmon")
+    got = run_product(W.c3_two_transmon(), 2)
+    assert_parity(got, g["J_T"], g["pulses"], g["g_a_int"])
+    assert got["m_fw"][0] == g["m_fw"]
+    tau = got["tau"][-1]
+    assert np.abs(tau - (np.array(g["tau_re"]) + 1j * np.array(g["tau_im"]))).max() < 1e-11
+
+
+def test_c4_subset_multi_cta_golden_and_c_oracle():
+    """Cut-down configs[3] (8 samples, 200 steps): exercises the grid-wide exchange (8 CTAs)."""
+    from oracle import c_oracle as C
+
+    w = W.c4_ensemble(n_samples=8, n_grid=201)
+    got = run_product(w, 2)
+    g = gold("c4_8samples_g201")
+    assert_parity(got, g["J_T"], g["pulses"], g["g_a_int"])
+    assert got["info"]["grid_blocks"] > 1
+    ref = C.optimize_krotov_c(W.to_oracle(w), 2)  # second, independent restatement (own Bessel / eigen code)
+    assert_parity(got, ref["J_T"], ref["pulses"], rtol=1e-10, atol=5e-13)
+
+
+def test_c4_64_samples_vs_c_oracle():
+    from oracle import c_oracle as C
+
+    w = W.c4_ensemble(n_samples=64, n_grid=401)
+    got = run_product(w, 2)
+    ref = C.optimize_krotov_c(W.to_oracle(w), 2)
+    assert_parity(got, ref["J_T"], ref["pulses"], rtol=1e-10, atol=5e-13)
+    assert got["info"]["grid_blocks"] == 64
+
+
+# ---- shapes of problems the reference's tests use ---------------------------------------------------
+@pytest.mark.parametrize("d,n_traj,L,functional", [(10, 2, 2, "ss"), (10, 2, 1, "re"), (32, 5, 3, "sm"), (7, 3, 4, "ss")])
+def test_dense_dummy_problems(d, n_traj, L, functional):
+    """Dense random Hermitian generators in the spirit of dummy_control_problem (test_iterations.jl:16-24,
+    density = 1.0), all three built-in functionals, up to the widest row the warp path takes (d = 32)."""
+    from oracle import krotov_oracle as O
+
+    w = W.dummy_dense(d=d, n_traj=n_traj, n_controls=L, functional=functional, seed=d + L)
+    got = run_product(w, 3)
+    ref = O.optimize_krotov(W.to_oracle(w), 3)
+    assert_parity(got, ref["J_T"], ref["pulses"], ref["g_a_int"])
+
+
+def test_missing_control_derivative_and_two_generators():
+    """A generator that does not depend on one control (`nothing`, src/optimize.jl:344) next to one that does."""
+    from oracle import krotov_oracle as O
+
+    w = W.dummy_dense(d=6, n_traj=4, n_controls=2, seed=3)
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((6, 6)) + 1j * rng.standard_normal((6, 6))
+    w.H0 = [w.H0[0], 0.5 * (A + A.conj().T) / 3]
+    w.Hc = [w.Hc[0], [w.Hc[0][0], None]]
+    w.gen_of_traj = np.array([0, 1, 0, 1])
+    got = run_product(w, 3)
+    ref = O.optimize_krotov(W.to_oracle(w), 3)
+    assert_parity(got, ref["J_T"], ref["pulses"], ref["g_a_int"])
+
+
+def test_user_chi_host_path_equals_builtin():
+    w = W.c2_transmon_x()
+    a = run_product(w, 3)
+
+    def my_chi(states, trajectories, tau=None):  # same maths as chi_sm, but opaque to the library
+        n = len(trajectories)
+        s = sum(t.weight * x for t, x in zip(trajectories, tau))
+        return [(t.weight / n**2) * s * t.target_state for t in trajectories]
+
+    b = run_product(w, 3, chi=my_chi)
+    assert np.abs(np.array(a["J_T"]) - np.array(b["J_T"])).max() < 1e-14
+    assert np.abs(a["pulses"] - b["pulses"]).max() < 1e-13
+
+
+# ---- kernel variants must agree ------------------------------------------------------------------------
+def test_register_rows_vs_reloaded_rows(monkeypatch):
+    w = W.c4_ensemble(n_samples=4, n_grid=101)
+    a = run_product(w, 2)
+    monkeypatch.setenv("KROTOV_NO_PREG", "1")
+    b = run_product(w, 2)
+    assert np.abs(np.array(a["J_T"]) - np.array(b["J_T"])).max() < 1e-13
+    assert np.abs(a["pulses"] - b["pulses"]).max() < 1e-12
+
+
+def test_many_trajectories_per_warp():
+    """More trajectories than resident warps: a warp owns several (tpw > 1)."""
+    from oracle import c_oracle as C
+
+    w = W.dummy_dense(d=3, n_traj=2400, n_controls=1, n_grid=21, seed=11)
+    got = run_product(w, 1)
+    ref = C.optimize_krotov_c(W.to_oracle(w), 1)
+    assert_parity(got, ref["J_T"], ref["pulses"], rtol=1e-10, atol=5e-13)
+
+
+def test_bitwise_reproducible():
+    w = W.c4_ensemble(n_samples=16, n_grid=101)
+    a = run_product(w, 2)
+    b = run_product(w, 2)
+    assert np.array_equal(a["pulses"], b["pulses"]) and a["J_T"] == b["J_T"]
+
+
+# ---- driver semantics of the reference's tests -------------------------------------------------------
+def test_iter_start_stop_records():
+    """test/test_iterations.jl:13-35."""
+    w = W.dummy_dense(d=10, n_traj=2, n_controls=2)
+    res = K.optimize(to_problem(w, iter_start=10, store_iter_info=["iter.", "J_T"], print_iters=True), method=K.Krotov,
+                     iter_stop=12)
+    assert res.converged and res.iter_start == 10 and res.iter_stop == 12
+    assert [r[0] for r in res.records] == [0, 11, 12]
+
+
+def test_callbacks_order_records_and_pulse_mutation(capsys):
+    """test/test_iterations.jl:38-145."""
+    w = W.dummy_dense(d=10, n_traj=2, n_controls=2)
+    cb1 = lambda _, it, *a: print(f"This is callback 1 for iter {it}")  # noqa: E731
+
+    def cb2(_, it, *a):
+        print(f"This is callback 2 for iter {it}")
+        return ("cb2", it)
+
+    K.optimize(to_problem(w, callback=cb1, print_iters=True), method=K.Krotov, iter_stop=1)
+    out = capsys.readouterr().out
+    assert ("This is callback 1 for iter 0\n iter.        J_T   ∫gₐ(t)dt          J       ΔJ_T         ΔJ    secs"
+            in out)
+    assert "This is callback 1 for iter 1\n     1" in out
+    res = K.optimize(to_problem(w, callback=cb1), method=K.Krotov, iter_stop=1, callback=(cb1, cb2), print_iters=False)
+    out = capsys.readouterr().out
+    assert out == ("This is callback 1 for iter 0\nThis is callback 2 for iter 0\n"
+                   "This is callback 1 for iter 1\nThis is callback 2 for iter 1\n")
+    assert res.records == [("cb2", 0), ("cb2", 1)]
+    res = K.optimize(to_problem(w), method=K.Krotov, iter_stop=1, callback=(cb1, cb2), print_iters=True,
+                     store_iter_info=["J_T"])
+    capsys.readouterr()
+    assert len(res.records) == 2 and len(res.records[0]) == 3 and isinstance(res.records[0][2], float)
+
+    def reduce_pulse(wrk, it, eps_new, eps_old):
+        r0, r1 = np.linalg.norm(eps_old[0]), np.linalg.norm(eps_new[0])
+        eps_new[0] *= 0.8  # in place: must become the next guess
+        return (r0, r1, np.linalg.norm(eps_new[0]))
+
+    res = K.optimize(to_problem(w), method=K.Krotov, iter_stop=3, callback=reduce_pulse, print_iters=True,
+                     store_iter_info=["iter.", "J_T"])
+    capsys.readouterr()
+    assert res.converged
+    for i in range(1, len(res.records)):
+        r0, r1, r2, it, jt = res.records[i]
+        assert abs(r2 - 0.8 * r1) < 1e-12 * r1
+        if i >= 2:
+            assert abs(r0 - res.records[i - 1][2]) < 1e-12 * r0
+
+
+def test_pulses_as_controls_are_not_mutated():
+    """test/test_pulse_optimization.jl (issue #28): controls given as midpoint vectors stay untouched."""
+    w = W.dummy_dense(d=8, n_traj=1, n_controls=1, n_grid=31)
+    from workloads import midpoint_samples
+
+    guess = midpoint_samples(w.controls[0], w.tlist)
+    keep = guess.copy()
+    gen = K.hamiltonian(w.H0[0], (w.Hc[0][0], guess))
+    problem = K.ControlProblem([K.Trajectory(w.psi0[0], gen, target_state=w.target[0])], w.tlist, prop_method=K.Cheby,
+                               J_T=K.J_T_re, iter_stop=2, lambda_a=0.05, print_iters=False)
+    res = K.optimize(problem, method=K.Krotov)
+    assert len(res.optimized_controls[0]) == len(w.tlist)
+    assert K.get_controls(problem.trajectories)[0] is guess and np.array_equal(guess, keep)
+    assert np.linalg.norm(guess - K.discretize_on_midpoints(res.optimized_controls[0], w.tlist)) > 1e-3
+
+
+def test_continue_from_and_check_convergence():
+    w = W.c1_tls()
+    r2 = K.optimize(to_problem(w, iter_stop=2), method=K.Krotov)
+    j2 = r2.J_T  # `continue_from` continues the SAME result object in place, like the reference
+    r5 = K.optimize(to_problem(w, iter_stop=5, store_iter_info=["J_T"], print_iters=True, continue_from=r2),
+                    method=K.Krotov)
+    full = K.optimize(to_problem(w, iter_stop=5), method=K.Krotov)
+    assert abs(r5.records[0][0] - j2) < 1e-14 and len(r5.records) == 4 and r5.iter == 5 and r5 is r2
+    # continuing re-discretises through optimized_controls (on tlist), so the path differs slightly from a
+    # straight run -- exactly like the reference (src/workspace.jl:118-120)
+    assert abs(r5.J_T - full.J_T) < 1e-3
+
+    def conv(res):
+        if res.J_T < 0.2:
+            res.converged, res.message = True, "J_T < 0.2"
+
+    r = K.optimize(to_problem(w, iter_stop=50, check_convergence=conv), method=K.Krotov)
+    assert r.message == "J_T < 0.2" and r.iter == 2
+
+
+def test_exception_in_callback_is_captured():
+    w = W.c1_tls()
+
+    def boom(wrk, it, *a):
+        if it == 2:
+            raise RuntimeError("stop here")
+
+    r = K.optimize(to_problem(w, iter_stop=5, callback=boom), method=K.Krotov)
+    assert r.message == "Exception: stop here" and r.iter == 2
+    with pytest.raises(RuntimeError):
+        K.optimize(to_problem(w, iter_stop=5, callback=boom, rethrow_exceptions=True), method=K.Krotov)
+
+
+def test_storages_are_reachable_from_callbacks():
+    w = W.c2_transmon_x(n_grid=51)
+    seen = {}
+
+    def cb(wrk, it, *a):
+        if it == 1:
+            seen["X"] = wrk.bw_storage[1]
+            seen["Phi"] = wrk.fw_storage[0]
+            seen["psi"] = np.array(wrk.fw_propagators[0].state)
+            seen["tau"] = wrk.result.tau_vals.copy()
+
+    K.optimize(to_problem(w, iter_stop=1, callback=cb, store_fw_states=True), method=K.Krotov)
+    X, Phi = seen["X"], seen["Phi"]
+    assert X.shape == (3, 51) and Phi.shape == (3, 51)
+    # chi(T) of the first iteration is the J_T_sm boundary condition built from the guess sweep
+    assert abs(np.linalg.norm(X[:, -1]) - np.linalg.norm(X[:, 0])) < 1e-12  # unitary backward sweep
+    assert np.abs(Phi[:, 49] - seen["psi"]).max() < 1e-15  # slot n holds the state after step n (sic, :367)
+    assert abs(np.vdot(w.target[0], seen["psi"]) - seen["tau"][0]) < 1e-14
+
+
+# ---- BASELINE sizes: size-independent properties --------------------------------------------------------
+def test_c4_full_size_properties():
+    """configs[3] at full size (1024 trajectories, 2000 steps): unitarity, Krotov monotonicity, positivity of
+    the running cost, agreement of tau with the returned states, identical result on a second run."""
+    w = W.c4_ensemble()
+    got = run_product(w, 2)
+    res = got["result"]
+    states = np.array(res.states)
+    assert states.shape == (1024, 25)
+    assert np.abs(np.linalg.norm(states, axis=1) - 1.0).max() < 1e-11
+    tau = np.einsum("kd,kd->k", w.target.conj(), states)
+    assert np.abs(tau - got["tau"][-1]).max() < 1e-13
+    J = got["J_T"]
+    for i in (1, 2):
+        ga = float(np.sum(got["g_a_int"][i - 1]))
+        assert ga > 0 and J[i] - J[i - 1] + ga < 0  # Delta J = Delta J_T + int g_a < 0
+    assert abs(J[-1] - (1 - abs(tau.sum() / 1024) ** 2)) < 1e-13
+    assert got["info"]["grid_blocks"] >= 128
+    # independence of the ensemble members: the first 8 samples alone, forward-propagated under the optimised
+    # pulses (iter_stop = 0 runs only the initial sweep), must end in the same states
+    sub = W.c4_ensemble(n_samples=8)
+    sub.controls = [np.array(got["pulses"][0]), np.array(got["pulses"][1])]
+    r = K.optimize(to_problem(sub, iter_stop=0), method=K.Krotov)
+    assert r.iter == 0 and r.converged
+    assert np.abs(np.array(r.states) - states[:32]).max() < 1e-10
