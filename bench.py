@@ -49,45 +49,50 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """SM clock and throttle reasons DURING the timed region, sampled through NVML in a thread
+    (an `nvidia-smi -lms` child process was measured to perturb the launches it is supposed to watch)."""
 
-    def __init__(self, index=0):
-        self.samples, self.reasons, self.proc, self.index = [], set(), None, index
-        self.max_mhz = None
+    def __init__(self, index=0, period=0.05):
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.thread = None
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            self.proc = None
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
             return
-        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
 
-    def _read(self):
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.proc.stdout:
-            parts = [x.strip() for x in line.split(",")]
+    def _run(self):
+        nv = self.nv
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop.is_set():
             try:
-                self.samples.append(float(parts[0]))
-                self.max_mhz = float(parts[1])
-                for nm, val in zip(names, parts[2:6]):
-                    if val.lower().startswith("active"):
-                        self.reasons.add(nm)
-            except (ValueError, IndexError):
-                pass
-
-    def stop(self):
-        if self.proc is not None:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
             except Exception:
                 pass
+            self._stop.wait(self.period)
+
+    def stop(self):
+        self._stop.set()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
         s = sorted(self.samples)
         med = s[len(s) // 2] if s else None
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
@@ -194,6 +199,7 @@ def main():
     sampler = ClockSampler(local_rank)
 
     def cb(wrk, it, eps_new, eps_old):
+        marks.setdefault("wall", []).append(time.perf_counter())
         if it >= 1:
             info = wrk.engine.info()
             dev_ms.append(info["ms_last"])
@@ -253,7 +259,8 @@ def main():
                        "l2": "chi trajectory (%.0f MB per GPU) is larger than L2; no flush needed" % (info["hbm_bytes_state"] / 1e6),
                        "grid": [info["grid_blocks"], info["block_threads"]], "J_T_last": marks["J_T"]},
             "e2e": {"value": e2e, "unit": UNIT, "iterations_per_s": steps / wall_s,
-                    "h2d_bytes_per_step": L * N_T * 8, "d2h_bytes_per_step": L * N_T * 8 + L * 8 + n_loc * 16},
+                    "h2d_bytes_per_step": L * N_T * 8, "d2h_bytes_per_step": L * N_T * 8 + L * 8 + n_loc * 16,
+                    "ms_per_step_each": [round(1e3 * (b - a), 2) for a, b in zip(marks["wall"][warmup:warmup + steps], marks["wall"][warmup + 1:warmup + steps + 1])]},
             "gpu_launches": int(sum(launches[warmup:warmup + steps])),
             "clocks": marks["clocks"],
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",

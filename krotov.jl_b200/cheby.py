@@ -36,6 +36,9 @@ def specrange(G, method="auto"):
     if method == "auto":
         method = "diag" if d <= 512 else "arnoldi"
     if method == "diag":
+        if np.array_equal(G, G.conj().T):  # Hermitian: symmetric solver (what Julia's `eigvals` picks)
+            ev = np.linalg.eigvalsh(G)
+            return float(ev[0]), float(ev[-1])
         ev = np.linalg.eigvals(G)
         return float(ev.real.min()), float(ev.real.max())
     if method == "arnoldi":
@@ -95,8 +98,15 @@ class ChebyDirection:
         elif self.method in ("auto", "diag") and self.H0[0].shape[0] <= 512:
             # all generators in two batched LAPACK calls (numpy loops over the stack in C and calls the same
             # zgeev per matrix, so every number is what `specrange` returns for the single matrix)
-            ev_hi = np.linalg.eigvals(np.stack([self._evaluate(g, hi) for g in range(n_gen)])).real
-            ev_lo = np.linalg.eigvals(np.stack([self._evaluate(g, lo) for g in range(n_gen)])).real
+            # (the Hermitian solver when every evaluated generator is Hermitian, like `specrange`)
+            G_hi = np.stack([self._evaluate(g, hi) for g in range(n_gen)])
+            G_lo = np.stack([self._evaluate(g, lo) for g in range(n_gen)])
+            herm = np.array_equal(G_hi, G_hi.conj().transpose(0, 2, 1)) and np.array_equal(
+                G_lo, G_lo.conj().transpose(0, 2, 1))
+            if herm:
+                ev_hi, ev_lo = np.linalg.eigvalsh(G_hi), np.linalg.eigvalsh(G_lo)
+            else:
+                ev_hi, ev_lo = np.linalg.eigvals(G_hi).real, np.linalg.eigvals(G_lo).real
             e_min = np.minimum(ev_hi.min(axis=1), ev_lo.min(axis=1))
             e_max = np.maximum(ev_hi.max(axis=1), ev_lo.max(axis=1))
         else:

@@ -38,7 +38,9 @@ def discretize_on_midpoints(control, tlist):
 
     The first / last value sit on the first / last grid point, the others on interval
     midpoints.  A vector that already has ``len(tlist)-1`` values is COPIED, never aliased
-    (``test/test_pulse_optimization.jl:42``)."""
+    (``test/test_pulse_optimization.jl:42``).  A vector ON the grid is mapped back by the exact inverse of
+    :func:`discretize`, so that continuing from ``result.optimized_controls`` restarts from the very
+    same pulse (``test/test_tls_optimization.jl:126,160`` demand the same J_T to 1e-14)."""
     t = _as_grid(tlist)
     if callable(control):
         mid = np.empty(t.size - 1)
@@ -51,7 +53,8 @@ def discretize_on_midpoints(control, tlist):
     if v.size == t.size:
         out = np.empty(t.size - 1)
         out[0], out[-1] = v[0], v[-1]
-        out[1:-1] = 0.5 * (v[1:-2] + v[2:-1])
+        for i in range(1, t.size - 2):  # exact inverse of `discretize`: v[i] = (out[i-1] + out[i]) / 2
+            out[i] = 2.0 * v[i] - out[i - 1]
         return out
     raise ValueError("control array must have len(tlist) or len(tlist)-1 values")
 

@@ -127,7 +127,7 @@ def discretize_on_midpoints(control, tlist):
         vals[0] = arr[0]
         vals[-1] = arr[-1]
         for i in range(1, nt - 2):
-            vals[i] = 0.5 * (arr[i] + arr[i + 1])
+            vals[i] = 2.0 * arr[i] - vals[i - 1]
         return vals
     raise ValueError("control array length must be len(tlist) or len(tlist)-1")
 
@@ -218,7 +218,11 @@ def cheby_coeffs(Delta, dt, limit=1e-12):
 
 
 def specrange_diag(G):
-    """(E_min, E_max) by exact diagonalisation (``specrange_method=:diag``)."""
+    """(E_min, E_max) by exact diagonalisation (``specrange_method=:diag``).  Julia's ``eigvals`` of a
+    dense matrix dispatches to the Hermitian solver when ``ishermitian(G)``; same here."""
+    if np.array_equal(G, G.conj().T):
+        ev = np.linalg.eigvalsh(G)
+        return float(ev[0]), float(ev[-1])
     ev = np.linalg.eigvals(G)
     return float(ev.real.min()), float(ev.real.max())
 

@@ -95,7 +95,7 @@ def test_discretize_semantics():
     g = K.discretize(v, t)
     assert len(g) == 501 and g[0] == v[0] and g[-1] == v[-1] and g[7] == 0.5 * (v[6] + v[7])
     back = K.discretize_on_midpoints(g, t)
-    assert len(back) == 500 and back[0] == g[0] and back[5] == 0.5 * (g[5] + g[6])
+    assert len(back) == 500 and np.abs(back - v).max() < 1e-9  # exact inverse of `discretize`
     # same numbers as the oracle's independent restatement
     from oracle import krotov_oracle as O
 
