@@ -1,21 +1,678 @@
-// placeholder until the DMMA engine lands: the dense path reports "unsupported" loudly
+// Dense-generator engine: the batched Chebyshev propagator as FP64 tensor-core complex GEMMs (sm_100a).
+//
+// For Hilbert spaces too large for the warp-per-trajectory kernel the trajectories that share a generator
+// are propagated TOGETHER: the state block Psi is a (d x N) complex matrix and every Chebyshev term
+//     V_j = G V_{j-1} + V_{j-2},      G = 2c (H_0 - beta + sum_l eps_l[n] H_l)   (d x d, dense)
+// is one complex GEMM with a fused epilogue (recursion, running sum  OUT += a_j V_j, and on the last term the
+// phase e^{-i beta dt}, the store of chi(t_n) into the HBM trajectory and nothing else).  The GEMM runs on the
+// FP64 tensor pipe: `mma.sync.m8n8k4.f64` (DMMA; tcgen05 has no FP64 kind).  Complex arithmetic is the 4M form
+//     C_r += G_r X_r + (-G_i) X_i,    C_i += G_r X_i + G_i X_r
+// on interleaved (re, im) operands: one 16-byte shared-memory load feeds the real and the imaginary fragment.
+//
+// Kernel shape: CTA tile 32 rows x up to 64 trajectories; 4 consumer warps (one 8-row DMMA tile each, all
+// column tiles: 32 accumulator registers pairs) + 1 producer warp that streams K-chunks of 32 through a
+// 4-stage shared-memory ring with bulk async copies (`cp.async.bulk` -> SASS UBLKCP) completing on mbarriers.
+// Rows are padded in shared memory (A: 36, X: 66 sixteen-byte words per row) so that the DMMA fragment loads
+// of every quarter-warp hit 8 different bank groups.
+//
+// Time-serial forward sweep without host round trips: per time step the host only ENQUEUES kernels
+//   overlap GEMMs (H_l Psi, epilogue reduces Im<chi|H_l|psi> per CTA) -> update kernel (fixed-order sum,
+//   pulse update written to device memory) -> build-G kernel (reads the new pulse value from device memory)
+//   -> m-1 GEMMs;
+// the pulse value never visits the host.
 #include "dense_kernel.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
 namespace kr {
-struct DenseEngine { int dummy; };
-DenseEngine *dense_create(int, int, int, int, int, const std::vector<std::complex<double>> &, const std::vector<int> &,
-                          const double *, const double *, int, cudaStream_t, std::string &err) {
-    err = "dense path (d > 32) not built yet";
-    return nullptr;
+
+using cplx = std::complex<double>;
+
+namespace {
+
+constexpr int BM = 32;       // rows per CTA
+constexpr int BK = 32;       // complex k per stage
+constexpr int STAGES = 4;
+constexpr int A_STRIDE = 36;  // 16-byte words per A row in smem (32 + 4 pad)
+constexpr int X_STRIDE = 66;  // 16-byte words per X row in smem (64 + 2 pad)
+constexpr int A_STAGE_WORDS = BM * A_STRIDE;
+constexpr int X_STAGE_WORDS = BK * X_STRIDE;
+constexpr int STAGE_WORDS = A_STAGE_WORDS + X_STAGE_WORDS;
+constexpr int GEMM_THREADS = 160;
+constexpr int kMaxL = 8;
+
+#define DK_CHECK(call)                                                                 \
+    do {                                                                               \
+        cudaError_t e_ = (call);                                                       \
+        if (e_ != cudaSuccess) {                                                       \
+            err = std::string(#call) + ": " + cudaGetErrorString(e_);                  \
+            return false;                                                              \
+        }                                                                              \
+    } while (0)
+
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-void dense_destroy(DenseEngine *e) { delete e; }
-void dense_info(DenseEngine *, krotov_info *) {}
-bool dense_set_cheby(DenseEngine *, int, int, const std::vector<int> &, const std::vector<double> &,
-                     const std::vector<double> &, const std::vector<int> &, const std::vector<double> &, int,
-                     const std::vector<std::complex<double>> &, std::string &) { return false; }
-bool dense_forward(DenseEngine *, const double *, double2 *, long long &, std::string &) { return false; }
-bool dense_iterate(DenseEngine *, const double *, double *, const double *, const double *, double *, const double2 *,
-                   double2 *, long long &, std::string &) { return false; }
-bool dense_set_chi(DenseEngine *, const double *, std::string &) { return false; }
-bool dense_get_states(DenseEngine *, double *, std::string &) { return false; }
-bool dense_get_storage(DenseEngine *, int, int, int, int, double *, std::string &) { return false; }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void dmma(double &c0, double &c1, const double a, const double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+struct GemmParams {
+    const double2 *A;   // [dp][dp] row-major
+    const double2 *B;   // [dp][ld] row-major state block, columns col0 .. col0 + 8*NT
+    int dp, ld, col0;
+    int epi;            // 0 = Chebyshev term, 1 = overlap partial sums
+    // ---- epi 0
+    const double2 *Vold;  // V_{j-2}  (j == 1: unused)
+    double2 *Vnew;        // V_j
+    double2 *OUT;         // running sum
+    int j, last;
+    double a0, aj;
+    double2 phase;
+    double2 *PSI;         // last term: phase * OUT
+    double2 *store;       // last term: optional second copy (storage slot), same layout
+    // ---- epi 1
+    const double2 *CHI;
+    double *partial;      // [gridDim.x]
+};
+
+template <int NT>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) dense_gemm_kernel(const __grid_constant__ GemmParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double2 *ring = reinterpret_cast<double2 *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(ring + (size_t)STAGES * STAGE_WORDS);
+    uint64_t *empty = full + STAGES;
+    double *wsum = reinterpret_cast<double *>(empty + STAGES);  // [4] per-warp partials (epi 1)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row0 = blockIdx.x * BM;
+    const int nk = p.dp / BK;
+    constexpr uint32_t X_ROW_BYTES = NT * 8 * 16;
+    constexpr uint32_t STAGE_BYTES = BM * BK * 16 + BK * X_ROW_BYTES;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == 4) {
+        // ------------------------------------------------------------ producer: bulk copies, one row per lane
+        for (int kc = 0; kc < nk; ++kc) {
+            const int s = kc % STAGES;
+            if (kc >= STAGES) mbar_wait(&empty[s], ((kc / STAGES) - 1) & 1);
+            double2 *As = ring + (size_t)s * STAGE_WORDS;
+            double2 *Xs = As + A_STAGE_WORDS;
+            if (lane == 0) mbar_expect_tx(&full[s], STAGE_BYTES);
+            __syncwarp();
+            bulk_g2s(As + lane * A_STRIDE, p.A + (size_t)(row0 + lane) * p.dp + (size_t)kc * BK, BK * 16, &full[s]);
+            bulk_g2s(Xs + lane * X_STRIDE, p.B + (size_t)(kc * BK + lane) * p.ld + p.col0, X_ROW_BYTES, &full[s]);
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------- consumers: DMMA
+    double cr[NT][2], ci[NT][2];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) cr[t][0] = cr[t][1] = ci[t][0] = ci[t][1] = 0.0;
+    const int fr = lane >> 2, fk = lane & 3;  // fragment row / k (A), fragment col / k (B)
+    for (int kc = 0; kc < nk; ++kc) {
+        const int s = kc % STAGES;
+        mbar_wait(&full[s], (kc / STAGES) & 1);
+        const double2 *As = ring + (size_t)s * STAGE_WORDS + (warp * 8 + fr) * A_STRIDE + fk;
+        const double2 *Xs = ring + (size_t)s * STAGE_WORDS + A_STAGE_WORDS + fk * X_STRIDE + fr;
+#pragma unroll
+        for (int ks = 0; ks < BK / 4; ++ks) {
+            const double2 a = As[ks * 4];
+            const double nai = -a.y;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                const double2 x = Xs[(ks * 4) * X_STRIDE + t * 8];
+                dmma(cr[t][0], cr[t][1], a.x, x.x);
+                dmma(cr[t][0], cr[t][1], nai, x.y);
+                dmma(ci[t][0], ci[t][1], a.x, x.y);
+                dmma(ci[t][0], ci[t][1], a.y, x.x);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+
+    // ---------------------------------------------------------------- epilogue
+    const int row = row0 + warp * 8 + fr;
+    if (p.epi == 0) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const size_t idx = (size_t)row * p.ld + p.col0 + t * 8 + 2 * fk;
+            double2 v0, v1, o0, o1;
+            if (p.j == 1) {
+                const double2 b0 = p.B[idx], b1 = p.B[idx + 1];  // V_0
+                v0 = make_double2(0.5 * cr[t][0], 0.5 * ci[t][0]);
+                v1 = make_double2(0.5 * cr[t][1], 0.5 * ci[t][1]);
+                o0 = make_double2(fma(p.aj, v0.x, p.a0 * b0.x), fma(p.aj, v0.y, p.a0 * b0.y));
+                o1 = make_double2(fma(p.aj, v1.x, p.a0 * b1.x), fma(p.aj, v1.y, p.a0 * b1.y));
+            } else {
+                const double2 w0 = p.Vold[idx], w1 = p.Vold[idx + 1];
+                const double2 q0 = p.OUT[idx], q1 = p.OUT[idx + 1];
+                v0 = make_double2(cr[t][0] + w0.x, ci[t][0] + w0.y);
+                v1 = make_double2(cr[t][1] + w1.x, ci[t][1] + w1.y);
+                o0 = make_double2(fma(p.aj, v0.x, q0.x), fma(p.aj, v0.y, q0.y));
+                o1 = make_double2(fma(p.aj, v1.x, q1.x), fma(p.aj, v1.y, q1.y));
+            }
+            if (p.last) {
+                const double2 r0 = make_double2(p.phase.x * o0.x - p.phase.y * o0.y, p.phase.x * o0.y + p.phase.y * o0.x);
+                const double2 r1 = make_double2(p.phase.x * o1.x - p.phase.y * o1.y, p.phase.x * o1.y + p.phase.y * o1.x);
+                p.PSI[idx] = r0;
+                p.PSI[idx + 1] = r1;
+                if (p.store) {
+                    p.store[idx] = r0;
+                    p.store[idx + 1] = r1;
+                }
+            } else {
+                p.Vnew[idx] = v0;
+                p.Vnew[idx + 1] = v1;
+                p.OUT[idx] = o0;
+                p.OUT[idx + 1] = o1;
+            }
+        }
+    } else {
+        // Im <chi | w> = chi_r w_i - chi_i w_r, summed over the CTA tile in a fixed order
+        double acc = 0.0;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const size_t idx = (size_t)row * p.ld + p.col0 + t * 8 + 2 * fk;
+            const double2 c0 = p.CHI[idx], c1 = p.CHI[idx + 1];
+            acc += c0.x * ci[t][0] - c0.y * cr[t][0];
+            acc += c1.x * ci[t][1] - c1.y * cr[t][1];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) wsum[warp] = acc;
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 consumer warps only
+        if (warp == 0 && lane == 0) p.partial[blockIdx.x] = (wsum[0] + wsum[1]) + (wsum[2] + wsum[3]);
+    }
+}
+
+// G = f (H_0 - beta + sum_l eps_l[n] H_l)   elementwise; eps is read from DEVICE memory (no host round trip)
+__global__ void build_G_kernel(double2 *G, const double2 *H, int dp, int L, double2 f, double beta, const double *eps,
+                               int N_T, int n) {
+    const size_t total = (size_t)dp * dp;
+    double e[kMaxL];
+    for (int l = 0; l < L; ++l) e[l] = eps[(size_t)l * N_T + n];
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        double2 h = H[i];
+        const size_t r = i / dp, c = i - r * dp;
+        if (r == c) h.x -= beta;
+        for (int l = 0; l < L; ++l) {
+            const double2 hl = H[(size_t)(l + 1) * total + i];
+            h.x = fma(e[l], hl.x, h.x);
+            h.y = fma(e[l], hl.y, h.y);
+        }
+        G[i] = make_double2(f.x * h.x - f.y * h.y, f.x * h.y + f.y * h.x);
+    }
+}
+
+// fixed-order sum of the CTA partials of every control, pulse update (src/optimize.jl:351-358)
+__global__ void update_kernel(const double *partial, int n_partial, int L, const double *alpha, const double *eps_old,
+                              double *eps_new, double *ga, const double *dt, int N_T, int n) {
+    const int l = blockIdx.x, lane = threadIdx.x;
+    double s = 0.0;
+    for (int c = lane; c < n_partial; c += 32) s += partial[(size_t)l * n_partial + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        const double a = alpha[(size_t)l * N_T + n];
+        eps_new[(size_t)l * N_T + n] = __dadd_rn(eps_old[(size_t)l * N_T + n], __dmul_rn(a, s));
+        const double prev = (n == 0) ? 0.0 : ga[l];
+        ga[l] = __dadd_rn(prev, __dmul_rn(__dmul_rn(a, __dmul_rn(fabs(s), fabs(s))), dt[n]));
+    }
+}
+
+// tau_k = <tgt_k | psi_k>: one warp per column
+__global__ void tau_kernel(const double2 *PSI, const double2 *TGT, int d, int ld, const int *col_of_traj, int N,
+                           double2 *tau) {
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (k >= N) return;
+    const int c = col_of_traj[k];
+    double tr = 0.0, ti = 0.0;
+    for (int i = lane; i < d; i += 32) {
+        const double2 t = TGT[(size_t)i * ld + c], x = PSI[(size_t)i * ld + c];
+        tr += t.x * x.x + t.y * x.y;
+        ti += t.x * x.y - t.y * x.x;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        tr += __shfl_xor_sync(0xffffffffu, tr, o);
+        ti += __shfl_xor_sync(0xffffffffu, ti, o);
+    }
+    if (lane == 0) tau[k] = make_double2(tr, ti);
+}
+
+// chi(T)[i][col] = coef[k] * tgt[i][col]
+__global__ void chi_from_coef_kernel(double2 *CHI, const double2 *TGT, const double2 *coef, const int *traj_of_col,
+                                     int dp, int ld) {
+    const size_t total = (size_t)dp * ld;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % ld);
+        const int k = traj_of_col[c];
+        double2 out = make_double2(0.0, 0.0);
+        if (k >= 0) {
+            const double2 a = coef[k], t = TGT[i];
+            out = make_double2(a.x * t.x - a.y * t.y, a.x * t.y + a.y * t.x);
+        }
+        CHI[i] = out;
+    }
+}
+
+__global__ void scale_kernel(double2 *dst, const double2 *src, double2 f, size_t total) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const double2 s = src[i];
+        dst[i] = make_double2(f.x * s.x - f.y * s.y, f.x * s.y + f.y * s.x);
+    }
+}
+
+struct Block {  // one GEMM column block
+    int g, col0, nt;
+};
+
+struct Cheb {
+    bool set = false;
+    int ndtc = 0, mmax = 0;
+    std::vector<int> dtc_of_step, m;
+    std::vector<double> E_min, Delta, coef;
+    std::vector<cplx> phase;
+};
+
+}  // namespace
+
+struct DenseEngine {
+    int d = 0, dp = 0, N = 0, L = 0, N_T = 0, n_gen = 0, store_fw = 0, ld = 0;
+    bool hermitian = true;
+    cudaStream_t stream = nullptr;
+    std::vector<int> col_of_traj, traj_of_col;
+    std::vector<Block> blocks;
+    int n_partial = 0;
+    // device
+    double2 *Hf = nullptr, *Hb = nullptr, *G = nullptr;
+    double2 *V[3] = {nullptr, nullptr, nullptr}, *OUT = nullptr, *PSI = nullptr, *PSI0 = nullptr, *TGT = nullptr,
+            *CHI = nullptr, *X = nullptr, *PHI = nullptr;
+    double *partial = nullptr;
+    int *d_col_of_traj = nullptr, *d_traj_of_col = nullptr;
+    bool chi_from_host = false;
+    Cheb ch[2];
+    size_t slab = 0;  // elements per time slot
+    long long launches = 0;
+    int sm_count = 148;
+};
+
+namespace {
+
+template <typename T>
+bool dalloc(T *&p, size_t n, std::string &err) {
+    cudaError_t e = cudaMalloc((void **)&p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e != cudaSuccess) {
+        err = std::string("cudaMalloc of ") + std::to_string(n * sizeof(T)) + " bytes: " + cudaGetErrorString(e);
+        return false;
+    }
+    return true;
+}
+
+size_t gemm_smem_bytes() { return (size_t)STAGES * STAGE_WORDS * 16 + 2 * STAGES * 8 + 64; }
+
+bool launch_gemm(DenseEngine *e, const Block &b, GemmParams p, std::string &err) {
+    p.dp = e->dp;
+    p.ld = e->ld;
+    p.col0 = b.col0;
+    dim3 grid(e->dp / BM), block(GEMM_THREADS);
+    const size_t smem = gemm_smem_bytes();
+    static bool attr_set = false;
+    if (!attr_set) {
+        DK_CHECK(cudaFuncSetAttribute(dense_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DK_CHECK(cudaFuncSetAttribute(dense_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DK_CHECK(cudaFuncSetAttribute(dense_gemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DK_CHECK(cudaFuncSetAttribute(dense_gemm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    switch (b.nt) {
+        case 1: dense_gemm_kernel<1><<<grid, block, smem, e->stream>>>(p); break;
+        case 2: dense_gemm_kernel<2><<<grid, block, smem, e->stream>>>(p); break;
+        case 4: dense_gemm_kernel<4><<<grid, block, smem, e->stream>>>(p); break;
+        default: dense_gemm_kernel<8><<<grid, block, smem, e->stream>>>(p); break;
+    }
+    e->launches++;
+    DK_CHECK(cudaGetLastError());
+    return true;
+}
+
+// One propagation step of every column block: PSI <- exp(-/+ i H dt) PSI.   `store` = storage slot or nullptr.
+bool step(DenseEngine *e, int dir, int n, const double *d_eps, double2 *store, std::string &err) {
+    const Cheb &c = e->ch[dir];
+    const int dtc = c.dtc_of_step[n];
+    const size_t mat = (size_t)e->dp * e->dp;
+    const double2 *H = (dir == KROTOV_FORWARD || e->hermitian) ? e->Hf : e->Hb;
+    for (int g = 0; g < e->n_gen; ++g) {
+        const double s = 4.0 / c.Delta[g], beta = c.Delta[g] / 2 + c.E_min[g];
+        const double2 f = (dir == KROTOV_FORWARD) ? make_double2(0.0, -s) : make_double2(0.0, s);
+        build_G_kernel<<<e->sm_count * 4, 256, 0, e->stream>>>(e->G + (size_t)g * mat, H + (size_t)g * (1 + e->L) * mat,
+                                                             e->dp, e->L, f, beta, d_eps, e->N_T, n);
+        e->launches++;
+    }
+    for (const Block &b : e->blocks) {
+        const int ci = b.g * c.ndtc + dtc;
+        const int m = c.m[ci];
+        const double *a = &c.coef[(size_t)ci * c.mmax];
+        const cplx ph = c.phase[ci];
+        if (m < 2) {
+            err = "Chebyshev expansion with fewer than 2 coefficients is not supported on the dense path";
+            return false;
+        }
+        // V[0] aliases PSI for j = 1;  ring of three work blocks afterwards
+        const double2 *vprev = e->PSI;  // V_{j-1}
+        const double2 *vprev2 = nullptr;
+        for (int j = 1; j < m; ++j) {
+            GemmParams p;
+            memset(&p, 0, sizeof(p));
+            p.A = e->G + (size_t)b.g * mat;
+            p.B = vprev;
+            p.epi = 0;
+            p.Vold = vprev2;
+            p.Vnew = e->V[j % 3];
+            p.OUT = e->OUT;
+            p.j = j;
+            p.last = (j == m - 1);
+            p.a0 = a[0];
+            p.aj = a[j];
+            p.phase = make_double2(ph.real(), ph.imag());
+            // the last term must not overwrite PSI while other CTAs still read it as V_0 (only when m == 2)
+            p.PSI = (m == 2) ? e->V[2] : e->PSI;
+            p.store = store;
+            if (!launch_gemm(e, b, p, err)) return false;
+            vprev2 = vprev;
+            vprev = e->V[j % 3];
+        }
+        if (m == 2) {
+            err = "m == 2 on the dense path is not supported";
+            return false;
+        }
+    }
+    return true;
+}
+
+}  // namespace
+
+DenseEngine *dense_create(int d, int N, int L, int N_T, int n_gen, const std::vector<cplx> &Hdense,
+                          const std::vector<int> &gen_of_traj, const double *psi0, const double *target, int store_fw,
+                          cudaStream_t stream, std::string &err) {
+    if (L > kMaxL) {
+        err = "too many controls";
+        return nullptr;
+    }
+    DenseEngine *e = new DenseEngine();
+    e->d = d; e->N = N; e->L = L; e->N_T = N_T; e->n_gen = n_gen; e->store_fw = store_fw; e->stream = stream;
+    e->dp = (d + BM - 1) / BM * BM;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, dev);
+    // columns: trajectories grouped by generator, groups cut into blocks of <= 64 columns (8 DMMA column tiles)
+    e->col_of_traj.assign(N, -1);
+    int col = 0;
+    for (int g = 0; g < n_gen; ++g) {
+        std::vector<int> ks;
+        for (int k = 0; k < N; ++k)
+            if (gen_of_traj[k] == g) ks.push_back(k);
+        size_t pos = 0;
+        while (pos < ks.size()) {
+            const int rem = (int)std::min<size_t>(64, ks.size() - pos);
+            int nt = (rem + 7) / 8;
+            nt = nt <= 1 ? 1 : nt <= 2 ? 2 : nt <= 4 ? 4 : 8;
+            e->blocks.push_back({g, col, nt});
+            for (int i = 0; i < rem; ++i) e->col_of_traj[ks[pos + i]] = col + i;
+            col += nt * 8;
+            pos += rem;
+        }
+    }
+    e->ld = col;
+    e->traj_of_col.assign(e->ld, -1);
+    for (int k = 0; k < N; ++k) e->traj_of_col[e->col_of_traj[k]] = k;
+    e->slab = (size_t)e->dp * e->ld;
+    e->n_partial = (int)e->blocks.size() * (e->dp / BM);
+    const size_t mat = (size_t)e->dp * e->dp;
+
+    // Hermitian generators: the adjoint terms are the terms themselves
+    e->hermitian = true;
+    for (int q = 0; q < n_gen * (1 + L) && e->hermitian; ++q) {
+        const cplx *M = &Hdense[(size_t)q * d * d];
+        for (int i = 0; i < d && e->hermitian; ++i)
+            for (int j = i; j < d; ++j)
+                if (M[(size_t)i * d + j] != std::conj(M[(size_t)j * d + i])) {
+                    e->hermitian = false;
+                    break;
+                }
+    }
+    size_t need = (size_t)n_gen * (1 + L) * mat * (e->hermitian ? 1 : 2) + (size_t)n_gen * mat;
+    need += e->slab * (8 + (size_t)(N_T + 1) * (store_fw ? 2 : 1));
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    if (need * 16 > free_b) {
+        err = "dense path needs " + std::to_string(need * 16 >> 20) + " MiB of device memory, " +
+              std::to_string(free_b >> 20) + " MiB free";
+        delete e;
+        return nullptr;
+    }
+    bool ok = dalloc(e->Hf, (size_t)n_gen * (1 + L) * mat, err) && dalloc(e->G, (size_t)n_gen * mat, err) &&
+              dalloc(e->V[0], e->slab, err) && dalloc(e->V[1], e->slab, err) && dalloc(e->V[2], e->slab, err) &&
+              dalloc(e->OUT, e->slab, err) && dalloc(e->PSI, e->slab, err) && dalloc(e->PSI0, e->slab, err) &&
+              dalloc(e->TGT, e->slab, err) && dalloc(e->CHI, e->slab, err) &&
+              dalloc(e->X, e->slab * (size_t)(N_T + 1), err) && dalloc(e->partial, (size_t)L * e->n_partial, err) &&
+              dalloc(e->d_col_of_traj, (size_t)N, err) && dalloc(e->d_traj_of_col, (size_t)e->ld, err);
+    if (ok && !e->hermitian) ok = dalloc(e->Hb, (size_t)n_gen * (1 + L) * mat, err);
+    if (ok && store_fw) ok = dalloc(e->PHI, e->slab * (size_t)(N_T + 1), err);
+    if (!ok) {
+        dense_destroy(e);
+        return nullptr;
+    }
+    // upload padded generator terms (and adjoints), states, targets
+    std::vector<cplx> buf(mat);
+    for (int q = 0; q < n_gen * (1 + L); ++q) {
+        const cplx *M = &Hdense[(size_t)q * d * d];
+        std::fill(buf.begin(), buf.end(), cplx(0, 0));
+        for (int i = 0; i < d; ++i) memcpy(&buf[(size_t)i * e->dp], &M[(size_t)i * d], sizeof(cplx) * d);
+        cudaMemcpy(e->Hf + (size_t)q * mat, buf.data(), mat * 16, cudaMemcpyHostToDevice);
+        if (!e->hermitian) {
+            std::fill(buf.begin(), buf.end(), cplx(0, 0));
+            for (int i = 0; i < d; ++i)
+                for (int j = 0; j < d; ++j) buf[(size_t)i * e->dp + j] = std::conj(M[(size_t)j * d + i]);
+            cudaMemcpy(e->Hb + (size_t)q * mat, buf.data(), mat * 16, cudaMemcpyHostToDevice);
+        }
+    }
+    auto to_block = [&](const double *src, double2 *dst) {
+        std::vector<cplx> blk(e->slab, cplx(0, 0));
+        if (src) {
+            const cplx *s = reinterpret_cast<const cplx *>(src);
+            for (int k = 0; k < N; ++k)
+                for (int i = 0; i < d; ++i) blk[(size_t)i * e->ld + e->col_of_traj[k]] = s[(size_t)k * d + i];
+        }
+        cudaMemcpy(dst, blk.data(), e->slab * 16, cudaMemcpyHostToDevice);
+    };
+    to_block(psi0, e->PSI0);
+    to_block(target, e->TGT);
+    cudaMemset(e->CHI, 0, e->slab * 16);
+    cudaMemset(e->PSI, 0, e->slab * 16);
+    cudaMemcpy(e->d_col_of_traj, e->col_of_traj.data(), (size_t)N * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(e->d_traj_of_col, e->traj_of_col.data(), (size_t)e->ld * 4, cudaMemcpyHostToDevice);
+    if (cudaGetLastError() != cudaSuccess) {
+        err = "dense_create: upload failed";
+        dense_destroy(e);
+        return nullptr;
+    }
+    return e;
+}
+
+void dense_destroy(DenseEngine *e) {
+    if (!e) return;
+    void *ptrs[] = {e->Hf, e->Hb, e->G, e->V[0], e->V[1], e->V[2], e->OUT, e->PSI, e->PSI0, e->TGT, e->CHI, e->X,
+                    e->PHI, e->partial, e->d_col_of_traj, e->d_traj_of_col};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    delete e;
+}
+
+void dense_info(DenseEngine *e, krotov_info *out) {
+    out->grid_blocks = e->dp / BM;
+    out->block_threads = GEMM_THREADS;
+    out->nnz_union = e->d * e->d;
+    out->ell_width = 0;
+    out->hbm_bytes_state = (int64_t)(e->slab * (size_t)(e->N_T + 1) * 16);
+    for (int dir = 0; dir < 2; ++dir) {
+        int mm = 0;
+        for (int v : e->ch[dir].m) mm = std::max(mm, v);
+        (dir == 0 ? out->m_fw : out->m_bw) = mm;
+    }
+}
+
+bool dense_set_cheby(DenseEngine *e, int direction, int ndtc, const std::vector<int> &dtc_of_step,
+                     const std::vector<double> &E_min, const std::vector<double> &Delta, const std::vector<int> &m,
+                     const std::vector<double> &coef, int m_max, const std::vector<cplx> &phase, std::string &err) {
+    Cheb &c = e->ch[direction];
+    c.ndtc = ndtc; c.mmax = m_max; c.dtc_of_step = dtc_of_step; c.E_min = E_min; c.Delta = Delta; c.m = m;
+    c.coef = coef; c.phase = phase; c.set = true;
+    for (int v : m)
+        if (v < 3) {
+            err = "dense path needs at least 3 Chebyshev coefficients per step (Delta * dt too small)";
+            return false;
+        }
+    return true;
+}
+
+static bool finish_sweep(DenseEngine *e, double2 *d_tau, std::string &err) {
+    tau_kernel<<<(e->N + 3) / 4, 128, 0, e->stream>>>(e->PSI, e->TGT, e->d, e->ld, e->d_col_of_traj, e->N, d_tau);
+    e->launches++;
+    DK_CHECK(cudaGetLastError());
+    return true;
+}
+
+bool dense_forward(DenseEngine *e, const double *d_eps, double2 *d_tau, long long &launches, std::string &err) {
+    e->launches = 0;
+    DK_CHECK(cudaMemcpyAsync(e->PSI, e->PSI0, e->slab * 16, cudaMemcpyDeviceToDevice, e->stream));
+    if (e->store_fw) DK_CHECK(cudaMemcpyAsync(e->PHI, e->PSI0, e->slab * 16, cudaMemcpyDeviceToDevice, e->stream));
+    for (int n = 0; n < e->N_T; ++n)
+        if (!step(e, KROTOV_FORWARD, n, d_eps, e->store_fw ? e->PHI + e->slab * (size_t)(n + 1) : nullptr, err))
+            return false;
+    if (!finish_sweep(e, d_tau, err)) return false;
+    launches += e->launches;
+    return true;
+}
+
+bool dense_iterate(DenseEngine *e, const double *d_eps_old, double *d_eps_new, const double *d_alpha,
+                   const double *d_dt, double *d_ga, const double2 *d_chi_coef, double2 *d_tau, long long &launches,
+                   std::string &err) {
+    e->launches = 0;
+    const int N_T = e->N_T;
+    // ---- chi(T)
+    if (d_chi_coef != nullptr) {
+        chi_from_coef_kernel<<<e->sm_count * 2, 256, 0, e->stream>>>(e->CHI, e->TGT, d_chi_coef, e->d_traj_of_col,
+                                                                     e->dp, e->ld);
+        e->launches++;
+    }
+    // ---- backward sweep: chi(t_n) for all n into X
+    DK_CHECK(cudaMemcpyAsync(e->PSI, e->CHI, e->slab * 16, cudaMemcpyDeviceToDevice, e->stream));
+    DK_CHECK(cudaMemcpyAsync(e->X + e->slab * (size_t)N_T, e->CHI, e->slab * 16, cudaMemcpyDeviceToDevice, e->stream));
+    for (int n = N_T - 1; n >= 0; --n)
+        if (!step(e, KROTOV_BACKWARD, n, d_eps_old, e->X + e->slab * (size_t)n, err)) return false;
+    // ---- forward sweep with sequential update
+    DK_CHECK(cudaMemcpyAsync(e->PSI, e->PSI0, e->slab * 16, cudaMemcpyDeviceToDevice, e->stream));
+    const size_t mat = (size_t)e->dp * e->dp;
+    const int ctas = e->dp / BM;
+    for (int n = 0; n < N_T; ++n) {
+        for (int l = 0; l < e->L; ++l) {
+            for (size_t bi = 0; bi < e->blocks.size(); ++bi) {
+                const Block &b = e->blocks[bi];
+                GemmParams p;
+                memset(&p, 0, sizeof(p));
+                p.A = e->Hf + ((size_t)b.g * (1 + e->L) + 1 + l) * mat;  // mu_l = H_l (src/optimize.jl:275-276)
+                p.B = e->PSI;
+                p.epi = 1;
+                p.CHI = e->X + e->slab * (size_t)n;
+                p.partial = e->partial + (size_t)l * e->n_partial + bi * ctas;
+                if (!launch_gemm(e, b, p, err)) return false;
+            }
+        }
+        update_kernel<<<e->L, 32, 0, e->stream>>>(e->partial, e->n_partial, e->L, d_alpha, d_eps_old, d_eps_new, d_ga,
+                                                 d_dt, N_T, n);
+        e->launches++;
+        if (!step(e, KROTOV_FORWARD, n, d_eps_new, e->store_fw ? e->PHI + e->slab * (size_t)n : nullptr, err))
+            return false;
+    }
+    if (!finish_sweep(e, d_tau, err)) return false;
+    e->chi_from_host = false;
+    launches += e->launches;
+    return true;
+}
+
+bool dense_set_chi(DenseEngine *e, const double *chi_host, std::string &err) {
+    std::vector<cplx> blk(e->slab, cplx(0, 0));
+    const cplx *s = reinterpret_cast<const cplx *>(chi_host);
+    for (int k = 0; k < e->N; ++k)
+        for (int i = 0; i < e->d; ++i) blk[(size_t)i * e->ld + e->col_of_traj[k]] = s[(size_t)k * e->d + i];
+    DK_CHECK(cudaMemcpy(e->CHI, blk.data(), e->slab * 16, cudaMemcpyHostToDevice));
+    e->chi_from_host = true;
+    return true;
+}
+
+bool dense_get_states(DenseEngine *e, double *states_host, std::string &err) {
+    std::vector<cplx> blk(e->slab);
+    DK_CHECK(cudaMemcpy(blk.data(), e->PSI, e->slab * 16, cudaMemcpyDeviceToHost));
+    cplx *o = reinterpret_cast<cplx *>(states_host);
+    for (int k = 0; k < e->N; ++k)
+        for (int i = 0; i < e->d; ++i) o[(size_t)k * e->d + i] = blk[(size_t)i * e->ld + e->col_of_traj[k]];
+    return true;
+}
+
+bool dense_get_storage(DenseEngine *e, int which, int k, int n0, int n1, double *out_host, std::string &err) {
+    const double2 *S = which == KROTOV_FORWARD ? e->PHI : e->X;
+    const int c = e->col_of_traj[k];
+    cplx *o = reinterpret_cast<cplx *>(out_host);
+    std::vector<cplx> colbuf(e->d);
+    for (int n = n0; n < n1; ++n) {
+        // column c of slot n: strided gather (one 2-D copy per slot)
+        DK_CHECK(cudaMemcpy2D(colbuf.data(), 16, S + e->slab * (size_t)n + c, (size_t)e->ld * 16, 16, e->d,
+                              cudaMemcpyDeviceToHost));
+        memcpy(o + (size_t)(n - n0) * e->d, colbuf.data(), (size_t)e->d * 16);
+    }
+    return true;
+}
+
 }  // namespace kr
