@@ -51,17 +51,20 @@ class Comm:
         self.world = dist.get_world_size()
         self.backend = dist.get_backend()
         self.device = self.rank if device is None else device
+        # host-side object collectives (IPC descriptors, tau, states) go through a gloo group: they are small
+        # CPU buffers, and NCCL would stage them through device memory
+        self.cpu_group = dist.new_group(backend="gloo") if self.backend != "gloo" else None
 
     def all_gather_object(self, obj):
         out = [None] * self.world
-        self.dist.all_gather_object(out, obj)
+        self.dist.all_gather_object(out, obj, group=self.cpu_group)
         return out
 
     def connect(self, engine):
         """Exchange the mailbox IPC descriptors and map the peers' mailboxes."""
         descs = self.all_gather_object(engine.comm_export())
         engine.comm_connect(self.rank, self.world, descs)
-        self.dist.barrier()
+        self.barrier()
 
     def all_gather_rows(self, local, n_total):
         """Concatenate per-rank blocks of rows (tau or states) in rank order."""
@@ -71,4 +74,4 @@ class Comm:
         return out
 
     def barrier(self):
-        self.dist.barrier()
+        self.dist.barrier(group=self.cpu_group)
