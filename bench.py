@@ -251,6 +251,11 @@ def main():
         ach_gbs = alg_bytes / (ms_launch * 1e-3) / 1e9
         nnz = info["nnz_union"]
         flops = 2.0 * n_loc * N_T * (m - 1) * 8 * nnz + n_loc * N_T * L * 8 * (nnz + d)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if world == 1 and args.samples == 256 and args.n_grid == 2001 and os.path.exists(tpath):
+            with open(tpath) as fh:  # measured once under ncu for exactly this launch shape
+                traffic = json.load(fh).get("krotov_warp_kernel<6,2,256> on C4 (1024 trajectories, N_T=2000)")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": dev_total_ms / steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
@@ -267,14 +272,17 @@ def main():
             "gpu_launches": int(sum(launches[warmup:warmup + steps])),
             "clocks": marks["clocks"],
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": ach_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                         "frac": ach_gbs / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
                          "kernel": "krotov_warp_kernel", "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "the fused kernel keeps all Chebyshev vectors on chip, so HBM traffic is only the chi "
                                  "trajectory; the binding resources are the FP64 pipe and the shared-memory crossbar "
                                  "(see roofline_fp64 and DESIGN.md)"},
             "roofline_fp64": {"achieved_tflops": flops / (ms_launch * 1e-3) / 1e12, "flops_per_launch": flops,
-                              "nominal_peak_tflops": 37.0,
-                              "frac_of_nominal": flops / (ms_launch * 1e-3) / 1e12 / 37.0},
+                              "peak_tflops": 34.2, "peak_source": "self-measured DFMA peak on this pool's B200 "
+                              "(tools/microbench.cu, profiles/r1_microbench_fp64.txt; DMMA: 37.1)",
+                              "frac": flops / (ms_launch * 1e-3) / 1e12 / 34.2,
+                              "bound": "latency (dependent STS->LDS->DFMA chain per Chebyshev term at 1.75 warps per SM "
+                                       "sub-partition, plus one grid-wide exchange per time step)"},
         }
         if world == 1 and not args.no_cpu_baseline:
             try:

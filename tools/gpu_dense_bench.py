@@ -1,6 +1,6 @@
 """Ad-hoc: throughput of the dense (DMMA) path on a C5-shaped problem with a short time grid."""
 import sys, time
-sys.path.insert(0, "tests")
+sys.path.insert(0, "tests"); sys.path.insert(0, ".")
 from util import *  # noqa
 import argparse
 ap = argparse.ArgumentParser(); ap.add_argument("--d", type=int, default=4096); ap.add_argument("--n", type=int, default=64)

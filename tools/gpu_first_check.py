@@ -1,6 +1,6 @@
 """Ad-hoc first GPU check (not a pytest file): parity of the CUDA path against the oracle on C1-C3 and a cut-down C4."""
 import sys, time
-sys.path.insert(0, "tests")
+sys.path.insert(0, "tests"); sys.path.insert(0, ".")
 from util import *  # noqa
 from oracle import krotov_oracle as O, c_oracle as C
 

@@ -1,6 +1,6 @@
 """Ad-hoc: cProfile of the host side of optimize() on C4 (where do the e2e milliseconds go?)."""
 import cProfile, pstats, sys, time
-sys.path.insert(0, "tests")
+sys.path.insert(0, "tests"); sys.path.insert(0, ".")
 from util import *  # noqa
 w = W.c4_ensemble()
 t = time.time(); problem = to_problem(w, iter_stop=8); print("build problem", time.time() - t)

@@ -1,7 +1,7 @@
 """Ad-hoc: in-kernel cycle counters of one iteration for several ensemble sizes (KROTOV_PROF=1)."""
 import os, sys
 os.environ["KROTOV_PROF"] = "1"
-sys.path.insert(0, "tests")
+sys.path.insert(0, "tests"); sys.path.insert(0, ".")
 from util import *  # noqa
 for ns in [1, 8, 64, 256]:
     w = W.c4_ensemble(n_samples=ns)

@@ -1,6 +1,6 @@
 import os, sys, time
 os.environ["KROTOV_TRACE"] = "1"
-sys.path.insert(0, "tests")
+sys.path.insert(0, "tests"); sys.path.insert(0, ".")
 from util import *  # noqa
 w = W.c4_ensemble()
 def cb(wrk, it, *a):
