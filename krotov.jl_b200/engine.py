@@ -17,7 +17,7 @@ def _ptr(a):
 
 class KrotovCuda:
     def __init__(self, *, tlist, H0, Hc, gen_of_traj, psi0, target=None, weight=None, update_shape, lambda_a,
-                 functional=B.CHI_HOST, n_traj_global=0, store_fw=False, device=0, force_path=0):
+                 functional=B.CHI_HOST, n_traj_global=0, store_fw=False, device=0, force_path=0, csr=False):
         """H0: (n_gen, d, d) complex, Hc: (n_gen, L, d, d) complex with ``None`` entries allowed
         (as zeros + term_present=0); psi0/target: (N, d); update_shape: (L, N_T); lambda_a: (L,)."""
         lib = B.lib()
@@ -39,6 +39,22 @@ class KrotovCuda:
                 else:
                     vals[g, 1 + l] = np.asarray(Hc[g][l]).T
         self.N, self.d, self.L, self.N_T, self.n_gen = N, d, L, N_T, n_gen
+        rowptr = colind = None
+        nnz = 0
+        if csr:
+            # KROTOV_GEN_CSR: one shared (union) pattern, values [n_gen][1+L][nnz]
+            pat = np.zeros((d, d), bool)
+            for g in range(n_gen):
+                for t in range(1 + L):
+                    pat |= vals[g, t].T != 0
+            rows, cols = np.nonzero(pat)
+            rowptr = np.zeros(d + 1, np.int32)
+            np.add.at(rowptr, rows + 1, 1)
+            rowptr = np.cumsum(rowptr).astype(np.int32)
+            colind = cols.astype(np.int32)
+            nnz = len(colind)
+            vals = np.ascontiguousarray(np.stack([[vals[g, t].T[rows, cols] for t in range(1 + L)]
+                                                  for g in range(n_gen)]), np.complex128)
         gen = np.ascontiguousarray(gen_of_traj, np.int32)
         S = np.ascontiguousarray(update_shape, np.float64).reshape(L, N_T)
         lam = np.ascontiguousarray(lambda_a, np.float64).reshape(L)
@@ -47,7 +63,8 @@ class KrotovCuda:
         p = B.Problem()
         p.struct_size = C.sizeof(B.Problem)
         p.d, p.n_traj, p.n_ctrl, p.n_steps, p.n_gen = d, N, L, N_T, n_gen
-        p.gen_format, p.nnz = B.GEN_DENSE_COLMAJOR, 0
+        p.gen_format, p.nnz = (B.GEN_CSR, nnz) if csr else (B.GEN_DENSE_COLMAJOR, 0)
+        p.csr_rowptr, p.csr_colind = _ptr(rowptr), _ptr(colind)
         p.tlist, p.gen_of_traj = _ptr(tlist), _ptr(gen)
         p.gen_values, p.term_present = _ptr(vals), _ptr(present)
         p.psi0, p.target, p.weight = _ptr(psi0), _ptr(tgt), _ptr(w)

@@ -315,7 +315,8 @@ class KrotovWrk:
             gen_of_traj=np.array([remap[int(g)] for g in gen_of_traj[lo:hi]], np.int32),
             psi0=psi0[lo:hi], target=None if target is None else target[lo:hi], weight=weight[lo:hi],
             update_shape=S, lambda_a=self.lambda_vals, functional=functional, n_traj_global=N,
-            store_fw=self.store_fw, device=device, force_path=int(self.kwargs.get("force_path", 0)))
+            store_fw=self.store_fw, device=device, force_path=int(self.kwargs.get("force_path", 0)),
+            csr=bool(self.kwargs.get("csr_generators", False)))
         if comm is not None and world > 1:
             comm.connect(self.engine)
         # ---- Chebyshev settings of both directions (init_prop: un-widened ranges of the guess pulses)

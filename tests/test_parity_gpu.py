@@ -356,3 +356,36 @@ def test_dense_path_two_generators_and_storage():
     K.optimize(to_problem(w, iter_stop=1, callback=cb), method=K.Krotov)
     assert seen["X"].shape == (48, 31) and abs(np.linalg.norm(seen["X"][:, 0]) - np.linalg.norm(seen["X"][:, -1])) < 1e-12
     assert abs(np.linalg.norm(seen["psi"]) - 1.0) < 1e-12
+
+
+def test_csr_generator_input_equals_dense_input():
+    """Both wire formats of the C ABI (KROTOV_GEN_DENSE_COLMAJOR / KROTOV_GEN_CSR) give the same bits."""
+    w = W.c4_ensemble(n_samples=4, n_grid=101)
+    a = run_product(w, 2)
+    b = run_product(w, 2, csr_generators=True)
+    assert np.array_equal(a["pulses"], b["pulses"]) and a["J_T"] == b["J_T"]
+
+
+def test_c5_shape_reduced_vs_c_oracle():
+    """configs[4] cut down (d=256 dense GUE generator, 16 trajectories, 12 steps, explicit spectral range):
+    the DMMA path against the C oracle."""
+    from oracle import c_oracle as C
+
+    w = W.c5_dense(d=256, n_traj=16, n_grid=13)
+    got = run_product(w, 2)
+    assert got["info"]["path"] == 2
+    ref = C.optimize_krotov_c(W.to_oracle(w), 2)
+    assert_parity(got, ref["J_T"], ref["pulses"], rtol=1e-10, atol=5e-13)
+
+
+def test_c5_full_width_properties():
+    """configs[4] at full width (d=4096, 64 trajectories), short grid: unitarity and monotonic convergence."""
+    w = W.c5_dense(d=4096, n_traj=64, n_grid=5)
+    got = run_product(w, 2)
+    states = np.array(got["result"].states)
+    assert np.abs(np.linalg.norm(states, axis=1) - 1.0).max() < 1e-12
+    J = got["J_T"]
+    for i in (1, 2):
+        assert J[i] - J[i - 1] + float(np.sum(got["g_a_int"][i - 1])) < 0
+    tau = np.einsum("kd,kd->k", w.target.conj(), states)
+    assert np.abs(tau - got["tau"][-1]).max() < 1e-13
