@@ -245,14 +245,36 @@ __global__ void build_G_kernel(double2 *G, const double2 *H, int dp, int L, doub
     }
 }
 
-// fixed-order sum of the CTA partials of every control, pulse update (src/optimize.jl:351-358)
+// fixed-order sum of the CTA partials of every control, rank exchange, pulse update (src/optimize.jl:351-358).
+// With several ranks the rank sum is pushed into every peer's mailbox (system-scope stores over NVLink) and
+// the `world` slots are summed in rank order -- the same protocol as the warp path's reducer.
 __global__ void update_kernel(const double *partial, int n_partial, int L, const double *alpha, const double *eps_old,
-                              double *eps_new, double *ga, const double *dt, int N_T, int n) {
+                              double *eps_new, double *ga, const double *dt, int N_T, int n, DenseComm cm) {
     const int l = blockIdx.x, lane = threadIdx.x;
     double s = 0.0;
     for (int c = lane; c < n_partial; c += 32) s += partial[(size_t)l * n_partial + c];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (cm.world > 1) {
+        const size_t off = ((size_t)n * L + l) * cm.world;
+        if (lane < cm.world)
+            asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(cm.mbox[lane] + off + cm.rank), "d"(s) : "memory");
+        const double *mine = cm.mbox[cm.rank] + off + (lane < cm.world ? lane : 0);
+        unsigned long long u;
+        const long long t0 = clock64();
+        int spins = 0;
+        for (;;) {
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(u) : "l"(mine) : "memory");
+            if (__all_sync(0xffffffffu, u != 0xFFFFFFFFFFFFFFFFull)) break;
+            if ((++spins & 63) == 0 && (clock64() - t0 > cm.timeout_cycles || *(volatile int *)cm.err_flag)) {
+                atomicExch(cm.err_flag, 1);
+                break;
+            }
+        }
+        const double v = __longlong_as_double((long long)u);
+        s = 0.0;
+        for (int r = 0; r < cm.world; ++r) s += __shfl_sync(0xffffffffu, v, r);
+    }
     if (lane == 0) {
         const double a = alpha[(size_t)l * N_T + n];
         eps_new[(size_t)l * N_T + n] = __dadd_rn(eps_old[(size_t)l * N_T + n], __dmul_rn(a, s));
@@ -336,6 +358,7 @@ struct DenseEngine {
     size_t slab = 0;  // elements per time slot
     long long launches = 0;
     int sm_count = 148;
+    DenseComm comm;
 };
 
 namespace {
@@ -541,6 +564,8 @@ DenseEngine *dense_create(int d, int N, int L, int N_T, int n_gen, const std::ve
     return e;
 }
 
+void dense_set_comm(DenseEngine *e, const DenseComm &c) { e->comm = c; }
+
 void dense_destroy(DenseEngine *e) {
     if (!e) return;
     void *ptrs[] = {e->Hf, e->Hb, e->G, e->V[0], e->V[1], e->V[2], e->OUT, e->PSI, e->PSI0, e->TGT, e->CHI, e->X,
@@ -631,7 +656,7 @@ bool dense_iterate(DenseEngine *e, const double *d_eps_old, double *d_eps_new, c
             }
         }
         update_kernel<<<e->L, 32, 0, e->stream>>>(e->partial, e->n_partial, e->L, d_alpha, d_eps_old, d_eps_new, d_ga,
-                                                 d_dt, N_T, n);
+                                                 d_dt, N_T, n, e->comm);
         e->launches++;
         if (!step(e, KROTOV_FORWARD, n, d_eps_new, e->store_fw ? e->PHI + e->slab * (size_t)n : nullptr, err))
             return false;

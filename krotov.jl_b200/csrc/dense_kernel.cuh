@@ -10,6 +10,13 @@
 
 namespace kr {
 struct DenseEngine;
+struct DenseComm {  // per-iteration view of the rank mailboxes (see krotov_comm_connect)
+    int rank = 0, world = 1;
+    double *mbox[8] = {};
+    int *err_flag = nullptr;
+    long long timeout_cycles = 0;
+};
+void dense_set_comm(DenseEngine *e, const DenseComm &c);
 DenseEngine *dense_create(int d, int N, int L, int N_T, int n_gen, const std::vector<std::complex<double>> &Hdense,
                           const std::vector<int> &gen_of_traj, const double *psi0, const double *target, int store_fw,
                           cudaStream_t stream, std::string &err);

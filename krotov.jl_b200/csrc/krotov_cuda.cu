@@ -533,6 +533,12 @@ int krotov_create(const krotov_problem *pb, krotov_handle *out) {
     if ((rc = dev_alloc(h, h->d_err, 16))) return bail(rc);
     cudaMemset(h->d_err.p, 0, 16);
     cudaMemset(h->d_tau.p, 0, (size_t)N * 16);
+    // peer mailboxes for the per-time-step exchange between ranks: [N_T][L][rank], one per iteration parity
+    for (int par = 0; par < 2; ++par) {
+        if ((rc = dev_alloc(h, h->d_mbox[par], (size_t)N_T * kr::kMaxRanks * L * 8))) return bail(rc);
+        cudaMemset(h->d_mbox[par].p, 0xFF, h->d_mbox[par].bytes);
+        h->peer_mbox[par][0] = (double *)h->d_mbox[par].p;
+    }
 
     if (path == KROTOV_PATH_WARP) {
         if ((rc = build_pattern(h))) return bail(rc);
@@ -562,11 +568,6 @@ int krotov_create(const krotov_problem *pb, krotov_handle *out) {
         if (getenv("KROTOV_PROF")) {
             if ((rc = dev_alloc(h, h->d_prof, (size_t)h->nCTA * 8 * 8))) return bail(rc);
             cudaMemset(h->d_prof.p, 0, h->d_prof.bytes);
-        }
-        for (int par = 0; par < 2; ++par) {
-            if ((rc = dev_alloc(h, h->d_mbox[par], (size_t)N_T * kr::kMaxRanks * L * 8))) return bail(rc);
-            cudaMemset(h->d_mbox[par].p, 0xFF, h->d_mbox[par].bytes);
-            h->peer_mbox[par][0] = (double *)h->d_mbox[par].p;
         }
     } else {
         h->dense = kr::dense_create(h->d, h->N, h->L, h->N_T, h->n_gen, h->Hdense, h->gen_of_traj, pb->psi0,
@@ -752,17 +753,24 @@ int krotov_iterate(krotov_handle h, const double *guess_pulses, double *new_puls
                                                  (const double *)h->d_weight.p, (double2 *)h->d_chicoef.p);
         h->launches_last += 1;
     }
+    if (h->world > 1) {
+        // the mailbox of the NEXT iteration's parity is cleared now (peers are at most one iteration ahead)
+        const int nxt = (int)((h->iter_count + 1) & 1);
+        KR_CUDA(h, cudaMemsetAsync(h->d_mbox[nxt].p, 0xFF, h->d_mbox[nxt].bytes, h->stream));
+    }
     if (h->path == KROTOV_PATH_WARP) {
         if (h->nCTA > 1 || h->world > 1) KR_CUDA(h, cudaMemsetAsync(h->d_R.p, 0xFF, h->d_R.bytes, h->stream));
-        if (h->world > 1) {
-            // the mailbox of the NEXT iteration's parity is cleared now (peers are at most one iteration ahead)
-            const int nxt = (int)((h->iter_count + 1) & 1);
-            KR_CUDA(h, cudaMemsetAsync(h->d_mbox[nxt].p, 0xFF, h->d_mbox[nxt].bytes, h->stream));
-        }
         if ((rc = launch_warp(h, 1))) return rc;
     } else {
         std::string e;
         double ms_bw = 0.0;
+        kr::DenseComm dc;
+        dc.rank = h->rank;
+        dc.world = h->world;
+        dc.err_flag = (int *)h->d_err.p;
+        dc.timeout_cycles = 20000000000ll;
+        for (int r = 0; r < kr::kMaxRanks; ++r) dc.mbox[r] = h->peer_mbox[(int)(h->iter_count & 1)][r];
+        kr::dense_set_comm(h->dense, dc);
         if (!kr::dense_iterate(h->dense, (const double *)h->d_eps_old.p, (double *)h->d_eps_new.p,
                                (const double *)h->d_alpha.p, (const double *)h->d_dt.p, (double *)h->d_ga.p,
                                h->chiT_valid ? nullptr : (const double2 *)h->d_chicoef.p, (double2 *)h->d_tau.p,
@@ -848,7 +856,6 @@ static_assert(sizeof(CommDesc) <= KROTOV_COMM_DESC_BYTES, "descriptor too large"
 
 int krotov_comm_export(krotov_handle h, void *desc) {
     if (!h || !desc) return KROTOV_ERR_ARG;
-    if (h->path != KROTOV_PATH_WARP) return fail(h, KROTOV_ERR_UNSUPPORTED, "in-kernel exchange exists on the warp path only");
     cudaSetDevice(h->device);
     CommDesc cd;
     memset(&cd, 0, sizeof(cd));
@@ -861,7 +868,6 @@ int krotov_comm_export(krotov_handle h, void *desc) {
 int krotov_comm_connect(krotov_handle h, int rank, int world, const void *descs) {
     if (!h || !descs) return KROTOV_ERR_ARG;
     if (world < 1 || world > kr::kMaxRanks || rank < 0 || rank >= world) return fail(h, KROTOV_ERR_ARG, "bad rank/world");
-    if (h->path != KROTOV_PATH_WARP) return fail(h, KROTOV_ERR_UNSUPPORTED, "in-kernel exchange exists on the warp path only");
     cudaSetDevice(h->device);
     h->rank = rank;
     h->world = world;

@@ -10,7 +10,13 @@ import workloads as W
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, n_samples, n_grid, iters, q):
+def _make(kind, n_samples, n_grid):
+    if kind == "c4":
+        return W.c4_ensemble(n_samples=n_samples, n_grid=n_grid)
+    return W.dummy_dense(d=64, n_traj=n_samples, n_controls=2, n_grid=n_grid, functional=kind, seed=5)
+
+
+def _worker(rank, world, port, kind, n_samples, n_grid, iters, q):
     import sys
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -28,7 +34,7 @@ def _worker(rank, world, port, n_samples, n_grid, iters, q):
         from util import to_problem
 
         comm = Comm(device=rank)
-        w = W.c4_ensemble(n_samples=n_samples, n_grid=n_grid)
+        w = _make(kind, n_samples, n_grid)
         hist = {"J_T": [], "shard": None}
 
         def cb(wrk, it, eps_new, eps_old):
@@ -43,8 +49,9 @@ def _worker(rank, world, port, n_samples, n_grid, iters, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_samples,n_grid", [(8, 201), (64, 101)])
-def test_two_ranks_match_single_gpu(n_samples, n_grid):
+@pytest.mark.parametrize("kind,n_samples,n_grid", [("c4", 8, 201), ("c4", 64, 101), ("sm", 20, 21), ("ss", 9, 21)])
+def test_two_ranks_match_single_gpu(kind, n_samples, n_grid):
+    """kind c4: warp path (in-kernel reducer exchange); kinds sm/ss: dense DMMA path (exchange in update_kernel)."""
     import torch
 
     if torch.cuda.device_count() < 2:
@@ -53,11 +60,11 @@ def test_two_ranks_match_single_gpu(n_samples, n_grid):
     from util import run_product
 
     iters = 2
-    single = run_product(W.c4_ensemble(n_samples=n_samples, n_grid=n_grid), iters)
+    single = run_product(_make(kind, n_samples, n_grid), iters)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29700 + os.getpid() % 1000
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_samples, n_grid, iters, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, kind, n_samples, n_grid, iters, q)) for r in range(2)]
     for p in procs:
         p.start()
     out = sorted([q.get(timeout=300) for _ in procs], key=lambda t: t[0])
@@ -66,7 +73,8 @@ def test_two_ranks_match_single_gpu(n_samples, n_grid):
         assert p.exitcode == 0
     (r0, J0, P0, s0, m0, st0, ga0), (r1, J1, P1, s1, m1, st1, ga1) = out
     assert m0 == m1 == "Reached maximum number of iterations"
-    assert s0 == (0, 2 * n_samples) and s1 == (2 * n_samples, 4 * n_samples)
+    n_traj = 4 * n_samples if kind == "c4" else n_samples
+    assert s0 == (0, n_traj // 2) and s1 == (n_traj // 2, n_traj)
     # replicas must hold bit-identical pulses (every rank applies the same rank-ordered sum)
     assert np.array_equal(P0, P1) and J0 == J1 and np.array_equal(ga0, ga1)
     # and agree with the single-GPU run up to the summation order of the overlap sums
