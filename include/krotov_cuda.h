@@ -181,7 +181,8 @@ int krotov_get_storage(krotov_handle h, int which, int k, int n0, int n1, double
  * all CTAs for cta = -1), available
  * when the environment variable KROTOV_PROF=1 was set at krotov_create:
  *   out[0] backward sweep, out[1] forward sweep, out[2] trajectory warp 0 waiting for the updated pulse,
- *   out[3] comm warp waiting for its CTA's partials, out[4] CTA-local reduction, out[5] grid/peer gather.
+ *   out[3] comm warp waiting for its CTA's partials, out[4] CTA-local reduction, out[5] grid/peer gather,
+ *   out[6] overlap computation of trajectory warp 0, out[7] its whole forward steps (sum over steps).
  * SM clock cycles; out has 8 entries. */
 int krotov_get_profile(krotov_handle h, int cta, int64_t *out);
 

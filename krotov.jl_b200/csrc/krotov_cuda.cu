@@ -80,6 +80,7 @@ struct krotov_handle_s {
     int Wt = 0;  // template width serving it
     int nnz_union = 0;
     bool preg = false;
+    bool mu_hermitian = false;
     std::vector<int> cols;  // [Wt][32]
     std::vector<char> slot_valid;  // [Wt][32] slot holds a real matrix entry (i, cols[s][i])
     int wpc = 1, tpw = 1, nCTA = 1;
@@ -326,7 +327,7 @@ int choose_launch(krotov_handle h) {
 
 size_t warp_smem_bytes(const krotov_handle h) {
     return (size_t)h->wpc * 2 * 32 * 16 + (size_t)h->wpc * h->tpw * 32 * 16 + (size_t)h->L * h->wpc * 32 * 8 +
-           kr::kMaxCtrl * 8 + (size_t)kr::kMaxCtrl * 160 * 8;
+           kr::kMaxCtrl * 8 + (size_t)kr::kMaxCtrl * 160 * 8 + (size_t)h->wpc * 32 * 16;
 }
 
 int launch_warp(krotov_handle h, int mode) {
@@ -334,6 +335,7 @@ int launch_warp(krotov_handle h, int mode) {
     memset(&p, 0, sizeof(p));
     p.d = h->d; p.N = h->N; p.L = h->L; p.N_T = h->N_T; p.n_gen = h->n_gen;
     p.wpc = h->wpc; p.tpw = h->tpw; p.nCTA = h->nCTA; p.mode = mode; p.store_fw = h->store_fw;
+    p.mu_hermitian = (h->mu_hermitian && !getenv("KROTOV_NO_FAST")) ? 1 : 0;
     p.ndtc_f = h->cheb[0].ndtc; p.ndtc_b = h->cheb[1].set ? h->cheb[1].ndtc : 1; p.mmax_f = h->cheb[0].mmax; p.mmax_b = h->cheb[1].set ? h->cheb[1].mmax : 1;
     p.gen_of_traj = (const int *)h->d_gen.p;
     p.cols = (const int *)h->d_cols.p;
@@ -540,6 +542,16 @@ int krotov_create(const krotov_problem *pb, krotov_handle *out) {
         h->peer_mbox[par][0] = (double *)h->d_mbox[par].p;
     }
 
+    // are all control terms Hermitian?  (mu_l^dagger = mu_l lets the kernel form mu_l chi ahead of time)
+    h->mu_hermitian = true;
+    for (int g = 0; g < h->n_gen && h->mu_hermitian; ++g)
+        for (int t = 1; t <= L && h->mu_hermitian; ++t)
+            for (int i = 0; i < d && h->mu_hermitian; ++i)
+                for (int j = i; j < d; ++j)
+                    if (Hval(h, g, t, i, j) != std::conj(Hval(h, g, t, j, i))) {
+                        h->mu_hermitian = false;
+                        break;
+                    }
     if (path == KROTOV_PATH_WARP) {
         if ((rc = build_pattern(h))) return bail(rc);
         if ((rc = upload(h, h->d_cols, h->cols))) return bail(rc);

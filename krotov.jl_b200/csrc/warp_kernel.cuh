@@ -44,6 +44,7 @@ struct WarpParams {
     int tpw;   // trajectories per warp
     int nCTA;
     int mode;  // 0 = plain forward sweep under eps_old, 1 = full iteration
+    int mu_hermitian;  // every control term of every generator is Hermitian (enables the idle-window precompute)
     int store_fw;
     int ndtc_f, ndtc_b, mmax_f, mmax_b;
     const int *gen_of_traj;
@@ -172,6 +173,40 @@ __device__ __forceinline__ StepMeta load_meta(const int *dtc, const int *m_tab, 
     return s;
 }
 
+// Same recursion, but the first term v_1 = G v_0 / 2 was assembled by the caller from products that do not
+// depend on the pulse value (computed while the warp waited for the grid-wide sum).
+template <int W>
+__device__ __forceinline__ double2 cheby_step_from_v1(const double2 psi, const double2 v1, const double2 (&g)[W + 1],
+                                                      const int (&col)[W], double2 *bufA, double2 *bufB,
+                                                      const double *__restrict__ a, const int m, const double2 phase,
+                                                      const int lane) {
+    double2 vm2 = psi, vm1 = v1;
+    double outr = a[0] * psi.x, outi = a[0] * psi.y;
+    if (m > 1) {
+        const double a1 = a[1];
+        outr = fma(a1, vm1.x, outr);
+        outi = fma(a1, vm1.y, outi);
+    }
+    bufB[lane] = vm1;
+    __syncwarp();
+    double2 *cur = bufB, *nxt = bufA;
+    for (int j = 2; j < m; ++j) {
+        const double aj = a[j];
+        double ar = vm2.x, ai = vm2.y;
+        row_dot<W>(g, col, cur, vm1, ar, ai);
+        outr = fma(aj, ar, outr);
+        outi = fma(aj, ai, outi);
+        vm2 = vm1;
+        vm1 = make_double2(ar, ai);
+        nxt[lane] = vm1;
+        __syncwarp();
+        double2 *t = cur;
+        cur = nxt;
+        nxt = t;
+    }
+    return make_double2(phase.x * outr - phase.y * outi, phase.x * outi + phase.y * outr);
+}
+
 __device__ __forceinline__ double warp_sum_xor(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -283,6 +318,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
     double *red = reinterpret_cast<double *>(psis + (size_t)wpc * tpw * 32);  // [L][wpc*32]
     double *eps_s = red + (size_t)L * wpc * 32;                   // [kMaxCtrl]
     double *gbuf = eps_s + kMaxCtrl;                              // [kMaxCtrl * 160] reducer scratch (CTA 0)
+    double2 *chibufs = reinterpret_cast<double2 *>(gbuf + kMaxCtrl * 160);  // [wpc][32] chi(t_{n+1}) for the precompute
     const int nthr_all = (wpc + 1) * 32;
     const int N_T = p.N_T;
     const bool is_comm = (warp == wpc);
@@ -393,7 +429,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
     double2 g[W + 1];
 
     const long long t_begin = clock64();
-    long long t_wait_b = 0;
+    long long t_wait_b = 0, t_overlap = 0, t_step = 0;
     // ================================================================ backward sweep
     if (p.mode == 1) {
         for (int t = 0; t < tpw; ++t) {
@@ -488,14 +524,42 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
     StepMeta fmeta = load_meta(p.dtc_f, p.m_f, p.phase_f, p.coef_f, p.ndtc_f, p.mmax_f, g0, 0);
     double2 chi_next = make_double2(0.0, 0.0);
     if (p.mode == 1 && k0 < p.N) chi_next = p.X[(size_t)k0 * (N_T + 1) * 32 + lane];
+    // FAST: register-resident rows, one trajectory per warp, Hermitian control terms.  Then
+    //   Im<chi|mu_l|psi> = -(1/s) Re <P_l chi|psi>   (P_l = -i s mu_l is anti-Hermitian)
+    // so xi_l = P_l chi(t_n) can be formed BEFORE psi(t_n) exists, and the overlap on the critical path is a
+    // plain dot product; and the products w_t = P_t psi(t_n) that make up the first Chebyshev term
+    // v_1 = (w_0 + sum_l eps_l w_l) / 2 are formed while the warp waits for eps.
+    const bool FAST = PREG && tpw == 1 && p.mode == 1 && p.mu_hermitian != 0;
+    double2 *chibuf = chibufs + (size_t)warp * 32;
+    double2 xi[PREG ? (LT > 0 ? LT : 1) : 1];
+    double2 wv[PREG ? NT : 1];
+    if (PREG && FAST) {
+        chibuf[lane] = chi_next;
+        __syncwarp();
+#pragma unroll
+        for (int l = 0; l < NT - 1; ++l) {
+            double wr = 0.0, wi = 0.0;
+            row_dot<W>(P[l + 1], col, chibuf, chi_next, wr, wi);
+            xi[l] = make_double2(wr, wi);
+        }
+        __syncwarp();
+    }
 
     for (int n = 0; n < N_T; ++n) {
         double eps[PREG ? (LT > 0 ? LT : 1) : kMaxCtrl];
+        const long long ts0 = clock64();
         if (p.mode == 1) {
             // ---- overlaps  Im <chi_k| mu_l |psi_k>   (src/optimize.jl:339-349)
             double part[PREG ? (LT > 0 ? LT : 1) : kMaxCtrl];
 #pragma unroll
             for (int l = 0; l < (PREG ? LT : kMaxCtrl); ++l) part[l] = 0.0;
+            if (PREG && FAST) {
+                if (k0 < p.N) {
+#pragma unroll
+                    for (int l = 0; l < NT - 1; ++l)
+                        part[l] = -inv_s0 * fma(xi[l].x, psi_reg.x, xi[l].y * psi_reg.y);
+                }
+            } else
             for (int t = 0; t < tpw; ++t) {
                 const int k = kbase + t;
                 if (k >= p.N) break;
@@ -524,13 +588,35 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
             for (int l = 0; l < (PREG ? LT : kMaxCtrl); ++l)
                 if (l < L) red[(size_t)l * wpc * 32 + warp * 32 + lane] = part[l];
             bar_arrive(1, nthr_all);  // barrier A
-            if (n + 1 < N_T && k0 < p.N) chi_next = p.X[((size_t)k0 * (N_T + 1) + n + 1) * 32 + lane];
             const long long w0 = clock64();
+            t_overlap += w0 - ts0;
+            if (n + 1 < N_T && k0 < p.N) chi_next = p.X[((size_t)k0 * (N_T + 1) + n + 1) * 32 + lane];
+            if (PREG && FAST && k0 < p.N) {
+                // ---- idle window: everything for this and the next step that does not depend on eps_n
+#pragma unroll
+                for (int q = 0; q < NT; ++q) {
+                    double wr = 0.0, wi = 0.0;
+                    row_dot<W>(P[q], col, mypsi, psi_reg, wr, wi);
+                    wv[q] = make_double2(wr, wi);
+                }
+                chibuf[lane] = chi_next;
+                __syncwarp();
+#pragma unroll
+                for (int l = 0; l < NT - 1; ++l) {
+                    double wr = 0.0, wi = 0.0;
+                    row_dot<W>(P[l + 1], col, chibuf, chi_next, wr, wi);
+                    xi[l] = make_double2(wr, wi);
+                }
+                __syncwarp();
+            }
             bar_sync(2, nthr_all);    // barrier B: updated pulse value is in eps_s
-            t_wait_b += clock64() - w0;
 #pragma unroll
             for (int l = 0; l < (PREG ? LT : kMaxCtrl); ++l)
                 if (l < L) eps[l] = eps_s[l];
+            if (p.prof != nullptr) {  // the barrier is deferred-blocking: time the wait at the first consumer
+                asm volatile("" ::"d"(eps[0]) : "memory");
+                t_wait_b += clock64() - w0;
+            }
         } else {
 #pragma unroll
             for (int l = 0; l < (PREG ? LT : kMaxCtrl); ++l)
@@ -569,7 +655,18 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
                 }
             }
             double2 psi = (tpw == 1) ? psi_reg : mypsi[t * 32 + lane];
-            psi = cheby_step<W>(psi, g, col, mypsi + t * 32, bufA, bufB, sm.a, sm.m, sm.phase, lane);
+            if (PREG && FAST) {
+                double v1r = wv[0].x, v1i = wv[0].y;
+#pragma unroll
+                for (int l = 0; l < NT - 1; ++l) {
+                    v1r = fma(eps[l], wv[l + 1].x, v1r);
+                    v1i = fma(eps[l], wv[l + 1].y, v1i);
+                }
+                psi = cheby_step_from_v1<W>(psi, make_double2(0.5 * v1r, 0.5 * v1i), g, col, bufA, bufB, sm.a, sm.m,
+                                            sm.phase, lane);
+            } else {
+                psi = cheby_step<W>(psi, g, col, mypsi + t * 32, bufA, bufB, sm.a, sm.m, sm.phase, lane);
+            }
             mypsi[t * 32 + lane] = psi;
             if (t == 0) psi_reg = psi;
             __syncwarp();
@@ -581,6 +678,10 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
             }
         }
         fmeta = fmeta_next;
+        if (p.prof != nullptr) {
+            asm volatile("" ::"d"(psi_reg.x) : "memory");
+            t_step += clock64() - ts0;
+        }
     }
 
     if (p.prof != nullptr && warp == 0 && lane == 0) {
@@ -588,6 +689,8 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
         p.prof[blockIdx.x * 8 + 0] = t_bw_end - t_begin;
         p.prof[blockIdx.x * 8 + 1] = t_end - t_bw_end;
         p.prof[blockIdx.x * 8 + 2] = t_wait_b;
+        p.prof[blockIdx.x * 8 + 6] = t_overlap;
+        p.prof[blockIdx.x * 8 + 7] = t_step;
     }
     // ---- final states and tau_k = <tgt_k|psi_k(T)>  (src/optimize.jl:378-381)
     for (int t = 0; t < tpw; ++t) {

@@ -155,7 +155,7 @@ class KrotovCuda:
     def profile(self, cta=-1):
         out = np.zeros(8, np.int64)
         self._check(self._lib.krotov_get_profile(self._h, int(cta), _ptr(out)))
-        names = ["backward", "forward", "wait_pulse", "comm_wait_partials", "comm_reduce", "comm_gather"]
+        names = ["backward", "forward", "wait_pulse", "comm_wait_partials", "comm_reduce", "comm_gather", "overlap", "fw_step_total"]
         return dict(zip(names, out.tolist()))
 
     # -- multi-GPU ------------------------------------------------------------------------

@@ -18,6 +18,6 @@ for ns in [1, 8, 64, 256]:
           " ".join(f"{k}={v/ghz/1e3/w.N_T:.3f}us/step" for k, v in pr.items()))
     al = out["all"]
     f = lambda v: v / ghz / 1e3 / w.N_T
-    for key in ["backward", "forward", "comm_reduce", "comm_gather"]:
+    for key in ["backward", "forward", "overlap", "wait_pulse", "fw_step_total", "comm_gather"]:
         vals = np.array([f(a[key]) for a in al])
         print(f"      {key:12s} cta0={vals[0]:.3f} others: min={vals[1:].min() if len(vals)>1 else 0:.3f} mean={vals[1:].mean() if len(vals)>1 else 0:.3f} max={vals[1:].max() if len(vals)>1 else 0:.3f}")
