@@ -389,3 +389,62 @@ def test_c5_full_width_properties():
         assert J[i] - J[i - 1] + float(np.sum(got["g_a_int"][i - 1])) < 0
     tau = np.einsum("kd,kd->k", w.target.conj(), states)
     assert np.abs(tau - got["tau"][-1]).max() < 1e-13
+
+
+# ---- options of the reference API that change the numbers --------------------------------------------------
+def test_nonuniform_time_grid_weights_and_pulse_options():
+    """Non-uniform tlist (several dt classes with their own Chebyshev coefficients), trajectory weights, and a
+    per-control `pulse_options` dict with different lambda_a / update_shape (src/workspace.jl:77-106)."""
+    from oracle import krotov_oracle as O
+
+    w = W.dummy_dense(d=9, n_traj=3, n_controls=2, n_grid=41, seed=21)
+    t = np.concatenate([np.linspace(0, 2, 21)[:-1], np.linspace(2, 5, 21)])  # dt = 0.1 then 0.15
+    w.tlist = t
+    weights = np.array([1.0, 0.5, 2.0])
+    lam = [2.0, 0.7]
+    shapes = [lambda x: W.flattop(x, T=5.0, t_rise=0.5), lambda x: 1.0]
+    p = W.to_oracle(w)
+    p.weight = weights
+    p.lam = np.array(lam)
+    p.S = np.array([W.midpoint_samples(s, t) for s in shapes])
+    ref = O.optimize_krotov(p, 3)
+    assert len(set(np.round(np.diff(t), 12))) == 2
+
+    hist = dict(J_T=[], g=[])
+
+    def cb(wrk, it, eps_new, eps_old):
+        hist["J_T"].append(wrk.result.J_T)
+        hist["pulses"] = np.array([np.array(e) for e in eps_new])
+        if it > 0:
+            hist["g"].append(np.array(wrk.g_a_int))
+
+    problem = to_problem(w, iter_stop=3, callback=cb)
+    for traj, wt in zip(problem.trajectories, weights):
+        traj.weight = float(wt)
+    ctr = K.get_controls(problem.trajectories)
+    del problem.kwargs["lambda_a"], problem.kwargs["update_shape"]
+    problem.kwargs["pulse_options"] = K.IdDict([(ctr[0], {"lambda_a": lam[0], "update_shape": shapes[0]}),
+                                                (ctr[1], {"lambda_a": lam[1], "update_shape": shapes[1]})])
+    K.optimize(problem, method=K.Krotov)
+    got = dict(J_T=hist["J_T"], pulses=hist["pulses"], g_a_int=hist["g"])
+    assert_parity(got, ref["J_T"], ref["pulses"], ref["g_a_int"])
+
+
+def test_trajectory_without_target_uses_host_chi():
+    """A trajectory with target_state = nothing: tau is 0 for it (src/optimize.jl:381) and chi comes from the user."""
+    w = W.dummy_dense(d=8, n_traj=2, n_controls=1, n_grid=31, seed=4)
+    problem = to_problem(w, iter_stop=2)
+    problem.trajectories[1].target_state = None
+    tgt0 = problem.trajectories[0].target_state
+
+    def J_T(states, trajectories, tau=None):
+        return 1.0 - abs(tau[0]) ** 2 + 0.0 * abs(tau[1])
+
+    def chi(states, trajectories, tau=None):
+        return [tau[0] * tgt0, np.zeros(8, complex)]
+
+    taus_seen = []
+    problem.kwargs.update(J_T=J_T, chi=chi, callback=lambda wrk, it, *a: taus_seen.append(wrk.result.tau_vals.copy()))
+    res = K.optimize(problem, method=K.Krotov)
+    assert all(t[1] == 0 for t in taus_seen)
+    assert res.J_T <= 1.0 - abs(taus_seen[0][0]) ** 2 + 1e-12  # did not get worse
