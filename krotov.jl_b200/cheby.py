@@ -27,6 +27,24 @@ def cheby_coeffs(Delta, dt, limit=1e-12):
     return np.asarray(out, np.float64)
 
 
+def cheby_coeffs_many(Deltas, dt, limit=1e-12):
+    """`cheby_coeffs` for many spectral radii at once (one vectorised Bessel call); every number is what
+    the scalar function returns (same ufunc, evaluated elementwise)."""
+    Deltas = np.asarray(Deltas, np.float64)
+    alpha = np.abs(0.5 * Deltas * dt)
+    nmax = int(np.max(alpha)) + 64
+    while True:
+        n = np.arange(nmax)
+        a = jv(n[None, :], alpha[:, None])
+        a[:, 1:] *= 2.0
+        # length m = first n >= 1 with |a_{n-1}| <= limit and n > alpha
+        stop = (np.abs(a[:, :-1]) <= limit) & (n[None, 1:] > alpha[:, None])
+        if stop.any(axis=1).all():
+            m = stop.argmax(axis=1) + 1
+            return [a[g, : m[g]].copy() for g in range(len(Deltas))]
+        nmax *= 2
+
+
 def specrange(G, method="auto"):
     """``(E_min, E_max)`` of an operator.  ``diag``: exact eigenvalues (dense).  ``auto`` uses
     ``diag`` up to dimension 512 and a Lanczos/Arnoldi estimate (scipy ``eigs``, widened by 5 %)
@@ -50,6 +68,20 @@ def specrange(G, method="auto"):
         pad = 0.05 * (hi - lo)
         return float(lo - pad), float(hi + pad)
     raise ValueError(f"unknown specrange method {method!r}")
+
+
+def _batched(solver, stack, workers=8):
+    """Apply a LAPACK-backed solver to a stack of matrices in a few threads (numpy releases the GIL inside
+    the gufunc loop); per-matrix results are independent of the chunking."""
+    n = stack.shape[0]
+    if n < 4 * workers:
+        return solver(stack)
+    from concurrent.futures import ThreadPoolExecutor
+
+    bounds = [(i * n) // workers for i in range(workers + 1)]
+    with ThreadPoolExecutor(workers) as ex:
+        parts = list(ex.map(lambda ab: solver(stack[ab[0]:ab[1]]), zip(bounds[:-1], bounds[1:])))
+    return np.concatenate(parts, axis=0)
 
 
 def transform_control_ranges(c, eps_min, eps_max, check):
@@ -78,6 +110,10 @@ class ChebyDirection:
         self.manual = None if (E_min is None or E_max is None) else (float(E_min), float(E_max))
         self.control_ranges = [(float(np.min(p)), float(np.max(p))) for p in pulses]
         self.n_updates = 0
+        self._H0s = np.stack([np.asarray(h, np.complex128) for h in H0])
+        d = self._H0s.shape[1]
+        self._Hcs = [np.stack([np.zeros((d, d), np.complex128) if row[l] is None else np.asarray(row[l], np.complex128)
+                               for row in Hc]) for l in range(len(pulses))]
         self._derive()
 
     # -- spectral envelope (cheby_get_spectral_envelope + specrange_buffer) ----------------
@@ -99,14 +135,14 @@ class ChebyDirection:
             # all generators in two batched LAPACK calls (numpy loops over the stack in C and calls the same
             # zgeev per matrix, so every number is what `specrange` returns for the single matrix)
             # (the Hermitian solver when every evaluated generator is Hermitian, like `specrange`)
-            G_hi = np.stack([self._evaluate(g, hi) for g in range(n_gen)])
-            G_lo = np.stack([self._evaluate(g, lo) for g in range(n_gen)])
+            G_hi, G_lo = self._H0s.copy(), self._H0s.copy()  # same elementwise sums as `_evaluate`, for all g at once
+            for l in range(len(hi)):
+                G_hi = G_hi + hi[l] * self._Hcs[l]
+                G_lo = G_lo + lo[l] * self._Hcs[l]
             herm = np.array_equal(G_hi, G_hi.conj().transpose(0, 2, 1)) and np.array_equal(
                 G_lo, G_lo.conj().transpose(0, 2, 1))
-            if herm:
-                ev_hi, ev_lo = np.linalg.eigvalsh(G_hi), np.linalg.eigvalsh(G_lo)
-            else:
-                ev_hi, ev_lo = np.linalg.eigvals(G_hi).real, np.linalg.eigvals(G_lo).real
+            solver = np.linalg.eigvalsh if herm else (lambda a: np.linalg.eigvals(a).real)
+            ev_hi, ev_lo = _batched(solver, G_hi), _batched(solver, G_lo)
             e_min = np.minimum(ev_hi.min(axis=1), ev_lo.min(axis=1))
             e_max = np.maximum(ev_hi.max(axis=1), ev_lo.max(axis=1))
         else:
@@ -143,15 +179,12 @@ class ChebyDirection:
                 classes.append(key)
             self.dt_class_of_step[n] = key_to_class[key]
         self.dt_of_class = np.array([k[0] for k in classes], np.float64)
-        self.coeffs = []
-        for g in range(len(self.H0)):
-            cache = {}
-            row = []
-            for (_, rep) in classes:
-                if rep not in cache:
-                    cache[rep] = cheby_coeffs(self.Delta[g], rep, self.limit)
-                row.append(cache[rep])
-            self.coeffs.append(row)
+        reps = []
+        for (_, rep) in classes:
+            if rep not in reps:
+                reps.append(rep)
+        per_rep = {rep: cheby_coeffs_many(self.Delta, rep, self.limit) for rep in reps}
+        self.coeffs = [[per_rep[rep][g] for (_, rep) in classes] for g in range(len(self.H0))]
 
     # -- reinit_prop! ------------------------------------------------------------------------
     def reinit(self, pulses, transform=transform_control_ranges):

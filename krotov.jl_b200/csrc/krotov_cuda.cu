@@ -125,8 +125,9 @@ int fail(krotov_handle h, int code, const std::string &msg) {
 }
 
 int dev_alloc(krotov_handle h, DevBuf &b, size_t bytes) {
-    b.release();
     if (bytes == 0) bytes = 16;
+    if (b.p != nullptr && b.bytes >= bytes) return KROTOV_OK;  // reuse: cudaFree/cudaMalloc cost up to 100 ms
+    b.release();
     cudaError_t e = cudaMalloc(&b.p, bytes);
     if (e != cudaSuccess) {
         h->err = std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e);

@@ -448,3 +448,23 @@ def test_trajectory_without_target_uses_host_chi():
     res = K.optimize(problem, method=K.Krotov)
     assert all(t[1] == 0 for t in taus_seen)
     assert res.J_T <= 1.0 - abs(taus_seen[0][0]) ** 2 + 1e-12  # did not get worse
+
+
+# ---- edge cases ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d,n_traj,L,n_grid", [(1, 1, 1, 3), (2, 1, 3, 2), (5, 33, 1, 4), (32, 1, 1, 6), (31, 2, 8, 5)])
+def test_edge_shapes(d, n_traj, L, n_grid):
+    """Minimal time grids (N_T = 1, 2), a 1x1 'Hilbert space', the widest row (d = 32), the maximum number of
+    controls (8), more trajectories than one warp's worth of CTAs."""
+    from oracle import krotov_oracle as O
+
+    w = W.dummy_dense(d=d, n_traj=n_traj, n_controls=L, n_grid=n_grid, seed=100 + d)
+    w.update_shape = lambda t: 1.0  # the flattop shape vanishes on such short grids
+    got = run_product(w, 2)
+    ref = O.optimize_krotov(W.to_oracle(w), 2)
+    assert_parity(got, ref["J_T"], ref["pulses"], ref["g_a_int"])
+
+
+def test_nine_controls_rejected():
+    w = W.dummy_dense(d=4, n_traj=1, n_controls=9, n_grid=5)
+    with pytest.raises(K.KrotovCudaError, match="more than 8 controls"):
+        K.optimize(to_problem(w, iter_stop=1), method=K.Krotov)
