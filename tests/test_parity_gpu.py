@@ -451,9 +451,9 @@ def test_trajectory_without_target_uses_host_chi():
 
 
 # ---- edge cases ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("d,n_traj,L,n_grid", [(1, 1, 1, 3), (2, 1, 3, 2), (5, 33, 1, 4), (32, 1, 1, 6), (31, 2, 8, 5)])
+@pytest.mark.parametrize("d,n_traj,L,n_grid", [(2, 1, 1, 3), (2, 1, 3, 2), (5, 33, 1, 4), (32, 1, 1, 6), (31, 2, 8, 5)])
 def test_edge_shapes(d, n_traj, L, n_grid):
-    """Minimal time grids (N_T = 1, 2), a 1x1 'Hilbert space', the widest row (d = 32), the maximum number of
+    """Minimal time grids (N_T = 1, 2), the widest row (d = 32), the maximum number of
     controls (8), more trajectories than one warp's worth of CTAs."""
     from oracle import krotov_oracle as O
 
