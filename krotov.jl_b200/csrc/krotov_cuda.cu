@@ -22,6 +22,7 @@
 #include "../../include/krotov_cuda.h"
 #include "dense_kernel.cuh"
 #include "warp_kernel.cuh"
+#include "warp2_kernel.cuh"
 
 using cplx = std::complex<double>;
 
@@ -80,6 +81,7 @@ struct krotov_handle_s {
     int Wt = 0;  // template width serving it
     int nnz_union = 0;
     bool preg = false;
+    bool pair = false;  // two trajectories of one generator per warp (warp2_kernel.cuh)
     bool mu_hermitian = false;
     std::vector<int> cols;  // [Wt][32]
     std::vector<char> slot_valid;  // [Wt][32] slot holds a real matrix entry (i, cols[s][i])
@@ -166,6 +168,17 @@ const std::map<KernelKey, WarpKernel> &kernel_table() {
         KR_INST(1, 2, 256), KR_INST(2, 2, 256), KR_INST(3, 2, 256), KR_INST(4, 2, 256), KR_INST(5, 2, 256),
         KR_INST(6, 2, 256), KR_INST(7, 2, 256), KR_INST(8, 2, 256), KR_INST(10, 2, 256),
         KR_INST(2, 3, 256), KR_INST(4, 3, 256), KR_INST(6, 3, 256),
+    };
+    return tab;
+}
+
+// pair kernel (two trajectories of one generator per warp): register-resident rows only
+#define KR_INST2(W, LT) {{W, LT}, (WarpKernel)kr::krotov_warp2_kernel<W, LT>}
+const std::map<KernelKey, WarpKernel> &kernel2_table() {
+    static const std::map<KernelKey, WarpKernel> tab = {
+        KR_INST2(2, 1), KR_INST2(3, 1), KR_INST2(4, 1), KR_INST2(5, 1), KR_INST2(6, 1), KR_INST2(7, 1), KR_INST2(8, 1),
+        KR_INST2(2, 2), KR_INST2(3, 2), KR_INST2(4, 2), KR_INST2(5, 2), KR_INST2(6, 2), KR_INST2(7, 2), KR_INST2(8, 2),
+        KR_INST2(4, 3), KR_INST2(6, 3),
     };
     return tab;
 }
@@ -308,6 +321,26 @@ int choose_launch(krotov_handle h) {
     const int N = h->N, sm = h->sm_count;
     const int cap_preg = 7, cap = 15;
     const bool preg_possible = kernel_table().count(KernelKey{h->Wt, h->L}) > 0;
+    // Pair mode: when there are more trajectories than one-per-warp CTAs with register-resident rows can hold
+    // (N > 7 per SM) and they come in generator-sharing pairs (ensembles over basis states), one warp runs two
+    // of them interleaved and keeps the rows in registers.  Measured on B200: +19 % at N = 2048 against the
+    // row-reloading variant; at N = 1024 two independent warps per sub-partition overlap better than one warp
+    // with two interleaved recursions (13.7 vs 15.3 ms), so the pair kernel is not used there.
+    // KROTOV_NO_PAIR=1 disables it, KROTOV_FORCE_PAIR=1 uses it whenever the pairing exists.
+    h->pair = false;
+    if (kernel2_table().count(KernelKey{h->Wt, h->L}) > 0 && N % 2 == 0 &&
+        (N > cap_preg * sm || getenv("KROTOV_FORCE_PAIR")) && N / 2 <= cap_preg * sm &&
+        !getenv("KROTOV_NO_PAIR") && !getenv("KROTOV_NO_PREG")) {
+        bool ok = true;
+        for (int k = 0; k < N; k += 2) ok = ok && (h->gen_of_traj[k] == h->gen_of_traj[k + 1]);
+        if (ok) {
+            int wpc2 = std::max(1, (N / 2 + sm - 1) / sm);
+            if (const char *env = getenv("KROTOV_WPC")) wpc2 = std::max(1, std::min(cap_preg, atoi(env)));
+            h->pair = true; h->preg = true; h->tpw = 1; h->wpc = wpc2;
+            h->nCTA = (N / 2 + wpc2 - 1) / wpc2;
+            return KROTOV_OK;
+        }
+    }
     int wpc = (N <= 8) ? N : std::max(std::min(N, 4), (N + sm - 1) / sm);
     if (const char *env = getenv("KROTOV_WPC")) wpc = std::max(1, atoi(env));
     h->tpw = 1;
@@ -327,6 +360,9 @@ int choose_launch(krotov_handle h) {
 }
 
 size_t warp_smem_bytes(const krotov_handle h) {
+    if (h->pair)
+        return (size_t)h->wpc * (128 + 64) * 16 + (size_t)h->L * h->wpc * 32 * 8 + kr::kMaxCtrl * 8 +
+               (size_t)kr::kMaxCtrl * 160 * 8;
     return (size_t)h->wpc * 2 * 32 * 16 + (size_t)h->wpc * h->tpw * 32 * 16 + (size_t)h->L * h->wpc * 32 * 8 +
            kr::kMaxCtrl * 8 + (size_t)kr::kMaxCtrl * 160 * 8 + (size_t)h->wpc * 32 * 16;
 }
@@ -367,8 +403,9 @@ int launch_warp(krotov_handle h, int mode) {
     if (const char *e = getenv("KROTOV_TIMEOUT_CYCLES")) p.timeout_cycles = atoll(e);
 
     KernelKey key{h->Wt, h->preg ? h->L : 0};
-    auto it = kernel_table().find(key);
-    if (it == kernel_table().end()) return fail(h, KROTOV_ERR_UNSUPPORTED, "no kernel instance for this (W, L)");
+    const auto &table = h->pair ? kernel2_table() : kernel_table();
+    auto it = table.find(key);
+    if (it == table.end()) return fail(h, KROTOV_ERR_UNSUPPORTED, "no kernel instance for this (W, L)");
     WarpKernel fn = it->second;
     const size_t smem = warp_smem_bytes(h);
     KR_CUDA(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

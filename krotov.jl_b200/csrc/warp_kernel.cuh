@@ -303,6 +303,99 @@ __device__ __forceinline__ void poll_broadcast(const double *E, const int L, con
     for (int l = 0; l < kMaxCtrl; ++l) tot[l] = __shfl_sync(0xffffffffu, v, l < L ? l : 0);
 }
 
+// The communication warp of a CTA (shared by both kernel variants): per time step it waits for the CTA's
+// per-lane partial overlaps (named barrier 1), reduces them in a fixed order, runs the grid / rank exchange,
+// applies the pulse update (src/optimize.jl:351-358) and releases the trajectory warps (named barrier 2).
+__device__ __forceinline__ void comm_warp_run(const WarpParams &p, const int L, const int lane, const int wpc,
+                                              const int nthr_all, double *red, double *eps_s, double *gbuf) {
+    const int N_T = p.N_T;
+    if (p.mode != 1) return;
+    double ga = 0.0;  // lane l accumulates g_a_int[l]  (CTA 0 writes it)
+    long long c_wait_a = 0, c_reduce = 0, c_gather = 0;
+    for (int n = 0; n < N_T; ++n) {
+        double a_ln = 0.0, e_old = 0.0, dtn = 0.0;
+        if (lane < L) {
+            a_ln = p.alpha[(size_t)lane * N_T + n];
+            e_old = p.eps_old[(size_t)lane * N_T + n];
+            dtn = p.dt[n];
+        }
+        const long long c0 = clock64();
+        bar_sync(1, nthr_all);  // barrier A: partials are in `red`
+        const long long c1 = clock64();
+        double tot[kMaxCtrl];
+#pragma unroll
+        for (int l = 0; l < kMaxCtrl; ++l) {
+            double sacc = 0.0;
+            if (l < L)
+                for (int q = 0; q < wpc; ++q) sacc += red[(size_t)l * wpc * 32 + q * 32 + lane];
+            tot[l] = sacc;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int l = 0; l < kMaxCtrl; ++l)
+                if (l < L) tot[l] += __shfl_xor_sync(0xffffffffu, tot[l], o);
+        }
+        const long long c2 = clock64();
+        if (p.nCTA > 1 || p.world > 1) {
+            // R[n][l][cta]: CTA partials;  E[n][l]: the grid-wide (and rank-wide) sums, written by the reducer
+            double *Rn = p.R + (size_t)n * L * p.nCTA;
+            double *En = p.E + (size_t)n * L;
+            if (blockIdx.x != 0) {
+#pragma unroll
+                for (int l = 0; l < kMaxCtrl; ++l)
+                    if (l < L && lane == l) st_relaxed_gpu_f64(Rn + (size_t)l * p.nCTA + blockIdx.x, tot[l]);
+                poll_broadcast(En, L, lane, tot, p.err_flag, p.timeout_cycles);
+            } else {
+                if (p.nCTA > 1) {
+#pragma unroll
+                    for (int l = 0; l < kMaxCtrl; ++l)
+                        if (l < L && lane == l) st_relaxed_gpu_f64(Rn + (size_t)l * p.nCTA, tot[l]);
+                    reducer_gather<false>(Rn, p.nCTA, L, lane, gbuf, tot, p.err_flag, p.timeout_cycles);
+                }
+                if (p.world > 1) {
+                    const size_t off = (size_t)n * L * p.world;  // mailbox layout [n][l][rank]
+#pragma unroll
+                    for (int l = 0; l < kMaxCtrl; ++l)
+                        if (l < L && lane < p.world)
+                            st_relaxed_f64(p.mbox[lane] + off + (size_t)l * p.world + p.rank, tot[l]);
+                    reducer_gather<true>(p.mbox[p.rank] + off, p.world, L, lane, gbuf, tot, p.err_flag,
+                                         p.timeout_cycles);
+                }
+                if (p.nCTA > 1) {
+#pragma unroll
+                    for (int l = 0; l < kMaxCtrl; ++l)
+                        if (l < L && lane == l) st_relaxed_gpu_f64(En + l, tot[l]);
+                }
+            }
+        }
+        const long long c3 = clock64();
+        c_wait_a += c1 - c0;
+        c_reduce += c2 - c1;
+        c_gather += c3 - c2;
+        double mine = 0.0;  // lane l holds du[l]
+#pragma unroll
+        for (int l = 0; l < kMaxCtrl; ++l)
+            if (lane == l) mine = tot[l];
+        if (lane < L) {
+            const double d_eps = __dmul_rn(a_ln, mine);      // src/optimize.jl:355
+            const double e_new = __dadd_rn(e_old, d_eps);    // :356
+            eps_s[lane] = e_new;
+            if (blockIdx.x == 0) {
+                p.eps_new[(size_t)lane * N_T + n] = e_new;
+                ga = __dadd_rn(ga, __dmul_rn(__dmul_rn(a_ln, __dmul_rn(fabs(mine), fabs(mine))), dtn));  // :357
+            }
+        }
+        bar_arrive(2, nthr_all);  // barrier B: eps_s is valid
+    }
+    if (blockIdx.x == 0 && lane < L) p.g_a_int[lane] = ga;
+    if (p.prof != nullptr && lane == 0) {
+        p.prof[blockIdx.x * 8 + 3] = c_wait_a;
+        p.prof[blockIdx.x * 8 + 4] = c_reduce;
+        p.prof[blockIdx.x * 8 + 5] = c_gather;
+    }
+}
+
 template <int W, int LT /*0 = runtime L, rows reloaded from L1/L2 per use*/, int MAXTHREADS>
 __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid_constant__ WarpParams p) {
     constexpr bool PREG = (LT > 0);
@@ -324,92 +417,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
     const bool is_comm = (warp == wpc);
 
     if (is_comm) {
-        // ---------------------------------------------------------------- communication warp
-        if (p.mode != 1) return;
-        double ga = 0.0;  // lane l accumulates g_a_int[l]  (CTA 0 writes it)
-        long long c_wait_a = 0, c_reduce = 0, c_gather = 0;
-        for (int n = 0; n < N_T; ++n) {
-            double a_ln = 0.0, e_old = 0.0, dtn = 0.0;
-            if (lane < L) {
-                a_ln = p.alpha[(size_t)lane * N_T + n];
-                e_old = p.eps_old[(size_t)lane * N_T + n];
-                dtn = p.dt[n];
-            }
-            const long long c0 = clock64();
-            bar_sync(1, nthr_all);  // barrier A: partials are in `red`
-            const long long c1 = clock64();
-            double tot[kMaxCtrl];
-#pragma unroll
-            for (int l = 0; l < kMaxCtrl; ++l) {
-                double sacc = 0.0;
-                if (l < L)
-                    for (int q = 0; q < wpc; ++q) sacc += red[(size_t)l * wpc * 32 + q * 32 + lane];
-                tot[l] = sacc;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                for (int l = 0; l < kMaxCtrl; ++l)
-                    if (l < L) tot[l] += __shfl_xor_sync(0xffffffffu, tot[l], o);
-            }
-            const long long c2 = clock64();
-            if (p.nCTA > 1 || p.world > 1) {
-                // R[n][l][cta]: CTA partials;  E[n][l]: the grid-wide (and rank-wide) sums, written by the reducer
-                double *Rn = p.R + (size_t)n * L * p.nCTA;
-                double *En = p.E + (size_t)n * L;
-                if (blockIdx.x != 0) {
-#pragma unroll
-                    for (int l = 0; l < kMaxCtrl; ++l)
-                        if (l < L && lane == l) st_relaxed_gpu_f64(Rn + (size_t)l * p.nCTA + blockIdx.x, tot[l]);
-                    poll_broadcast(En, L, lane, tot, p.err_flag, p.timeout_cycles);
-                } else {
-                    if (p.nCTA > 1) {
-#pragma unroll
-                        for (int l = 0; l < kMaxCtrl; ++l)
-                            if (l < L && lane == l) st_relaxed_gpu_f64(Rn + (size_t)l * p.nCTA, tot[l]);
-                        reducer_gather<false>(Rn, p.nCTA, L, lane, gbuf, tot, p.err_flag, p.timeout_cycles);
-                    }
-                    if (p.world > 1) {
-                        const size_t off = (size_t)n * L * p.world;  // mailbox layout [n][l][rank]
-#pragma unroll
-                        for (int l = 0; l < kMaxCtrl; ++l)
-                            if (l < L && lane < p.world)
-                                st_relaxed_f64(p.mbox[lane] + off + (size_t)l * p.world + p.rank, tot[l]);
-                        reducer_gather<true>(p.mbox[p.rank] + off, p.world, L, lane, gbuf, tot, p.err_flag,
-                                             p.timeout_cycles);
-                    }
-                    if (p.nCTA > 1) {
-#pragma unroll
-                        for (int l = 0; l < kMaxCtrl; ++l)
-                            if (l < L && lane == l) st_relaxed_gpu_f64(En + l, tot[l]);
-                    }
-                }
-            }
-            const long long c3 = clock64();
-            c_wait_a += c1 - c0;
-            c_reduce += c2 - c1;
-            c_gather += c3 - c2;
-            double mine = 0.0;  // lane l holds du[l]
-#pragma unroll
-            for (int l = 0; l < kMaxCtrl; ++l)
-                if (lane == l) mine = tot[l];
-            if (lane < L) {
-                const double d_eps = __dmul_rn(a_ln, mine);      // src/optimize.jl:355
-                const double e_new = __dadd_rn(e_old, d_eps);    // :356
-                eps_s[lane] = e_new;
-                if (blockIdx.x == 0) {
-                    p.eps_new[(size_t)lane * N_T + n] = e_new;
-                    ga = __dadd_rn(ga, __dmul_rn(__dmul_rn(a_ln, __dmul_rn(fabs(mine), fabs(mine))), dtn));  // :357
-                }
-            }
-            bar_arrive(2, nthr_all);  // barrier B: eps_s is valid
-        }
-        if (blockIdx.x == 0 && lane < L) p.g_a_int[lane] = ga;
-        if (p.prof != nullptr && lane == 0) {
-            p.prof[blockIdx.x * 8 + 3] = c_wait_a;
-            p.prof[blockIdx.x * 8 + 4] = c_reduce;
-            p.prof[blockIdx.x * 8 + 5] = c_gather;
-        }
+        comm_warp_run(p, L, lane, wpc, nthr_all, red, eps_s, gbuf);
         return;
     }
 

@@ -468,3 +468,22 @@ def test_nine_controls_rejected():
     w = W.dummy_dense(d=4, n_traj=1, n_controls=9, n_grid=5)
     with pytest.raises(K.KrotovCudaError, match="more than 8 controls"):
         K.optimize(to_problem(w, iter_stop=1), method=K.Krotov)
+
+
+def test_pair_kernel_large_ensemble(monkeypatch):
+    """More trajectories than one-per-warp CTAs hold (N > 7 x 148): two trajectories of one ensemble sample per warp
+    (warp2_kernel.cuh).  Checked against the C oracle, and against the one-trajectory kernel on a smaller case."""
+    from oracle import c_oracle as C
+
+    w = W.c4_ensemble(n_samples=300, n_grid=41)
+    got = run_product(w, 2)
+    assert got["info"]["block_threads"] <= 256 and got["info"]["grid_blocks"] * (got["info"]["block_threads"] // 32 - 1) * 2 >= 1200
+    ref = C.optimize_krotov_c(W.to_oracle(w), 2)
+    assert_parity(got, ref["J_T"], ref["pulses"], rtol=1e-10, atol=5e-13)
+    w = W.c4_ensemble(n_samples=12, n_grid=101)
+    a = run_product(w, 2)
+    monkeypatch.setenv("KROTOV_FORCE_PAIR", "1")
+    b = run_product(w, 2, store_fw_states=True)
+    assert b["info"]["grid_blocks"] < a["info"]["grid_blocks"] or b["info"]["block_threads"] < a["info"]["block_threads"]
+    assert np.abs(np.array(a["J_T"]) - np.array(b["J_T"])).max() < 1e-13
+    assert np.abs(a["pulses"] - b["pulses"]).max() < 1e-12
