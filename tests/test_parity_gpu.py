@@ -487,3 +487,21 @@ def test_pair_kernel_large_ensemble(monkeypatch):
     assert b["info"]["grid_blocks"] < a["info"]["grid_blocks"] or b["info"]["block_threads"] < a["info"]["block_threads"]
     assert np.abs(np.array(a["J_T"]) - np.array(b["J_T"])).max() < 1e-13
     assert np.abs(a["pulses"] - b["pulses"]).max() < 1e-12
+
+
+@pytest.mark.parametrize("d,force_path", [(12, 0), (40, 0)])
+def test_non_hermitian_generator_uses_adjoint_backward(d, force_path):
+    """A weakly non-Hermitian generator (decay -i Gamma/2 on the drift, a non-Hermitian control operator): the
+    backward sweep must propagate with the ADJOINT generator (src/workspace.jl:69,150-160) and the overlap uses the
+    plain mu_l.  Hermitian test problems cannot tell H from its adjoint; this one can."""
+    from oracle import krotov_oracle as O
+
+    w = W.dummy_dense(d=d, n_traj=3, n_controls=2, n_grid=31, seed=77)
+    rng = np.random.default_rng(3)
+    w.H0 = [w.H0[0] - 0.02j * np.diag(rng.uniform(0, 1, d))]
+    B = (rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d))) / np.sqrt(d)
+    w.Hc = [[w.Hc[0][0], w.Hc[0][1] + 0.05 * B]]
+    got = run_product(w, 2)
+    ref = O.optimize_krotov(W.to_oracle(w), 2)
+    assert np.isfinite(ref["J_T"]).all()
+    assert_parity(got, ref["J_T"], ref["pulses"], ref["g_a_int"])
