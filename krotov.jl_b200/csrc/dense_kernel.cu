@@ -326,6 +326,113 @@ __global__ void scale_kernel(double2 *dst, const double2 *src, double2 f, size_t
     }
 }
 
+// ============================================================================ sparse generators, d > 32
+// The same block propagator for SPARSE generators (spin chains, coupled-oscillator networks ...): the Chebyshev
+// term is an SpMM over the state block.  ELL storage with one shared pattern: slot 0 of every row is the
+// diagonal, `cols[row][s]` / values `[row][s]`; padded slots point at the own row with value 0.  One warp owns 4
+// rows x 32 trajectories: the generator entry is a warp-uniform (broadcast) load, the gathered state row is one
+// coalesced 512-byte read served by L1/L2 (the state blocks of all terms fit the 126 MB L2), so the kernel is
+// bound by L2 -> SM bandwidth, not by FP64.  Same fused epilogues as the dense GEMM.
+constexpr int SP_ROWS_PER_WARP = 4;
+constexpr int SP_WARPS = 8;
+constexpr int SP_ROWS = SP_ROWS_PER_WARP * SP_WARPS;
+
+struct SpmmParams {
+    const int *cols;      // [dp][W]
+    const double2 *Gv;    // [dp][W]
+    int W, ncols;         // ELL width; columns of this block (multiple of 8)
+    GemmParams e;         // B, dp, ld, col0 and the epilogue fields
+};
+
+__device__ __forceinline__ void cheby_epilogue_1(const GemmParams &p, const size_t idx, const double cr, const double ci) {
+    double2 v, o;
+    if (p.j == 1) {
+        const double2 b0 = p.B[idx];
+        v = make_double2(0.5 * cr, 0.5 * ci);
+        o = make_double2(fma(p.aj, v.x, p.a0 * b0.x), fma(p.aj, v.y, p.a0 * b0.y));
+    } else {
+        const double2 w0 = p.Vold[idx], q0 = p.OUT[idx];
+        v = make_double2(cr + w0.x, ci + w0.y);
+        o = make_double2(fma(p.aj, v.x, q0.x), fma(p.aj, v.y, q0.y));
+    }
+    if (p.last) {
+        const double2 r = make_double2(p.phase.x * o.x - p.phase.y * o.y, p.phase.x * o.y + p.phase.y * o.x);
+        p.PSI[idx] = r;
+        if (p.store) p.store[idx] = r;
+    } else {
+        p.Vnew[idx] = v;
+        p.OUT[idx] = o;
+    }
+}
+
+__global__ void __launch_bounds__(SP_WARPS * 32) spmm_kernel(const __grid_constant__ SpmmParams p) {
+    __shared__ double wsum[SP_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.y * 32 + lane;
+    const bool cvalid = c < p.ncols;
+    const int row0 = blockIdx.x * SP_ROWS + warp * SP_ROWS_PER_WARP;
+    const GemmParams &e = p.e;
+    double cr[SP_ROWS_PER_WARP], ci[SP_ROWS_PER_WARP], cr1[SP_ROWS_PER_WARP], ci1[SP_ROWS_PER_WARP];
+#pragma unroll
+    for (int q = 0; q < SP_ROWS_PER_WARP; ++q) cr[q] = ci[q] = cr1[q] = ci1[q] = 0.0;
+    const size_t cbase = (size_t)e.col0 + (cvalid ? c : 0);
+    for (int s = 0; s < p.W; ++s) {
+#pragma unroll
+        for (int q = 0; q < SP_ROWS_PER_WARP; ++q) {
+            const size_t slot = (size_t)(row0 + q) * p.W + s;
+            const int j = p.cols[slot];          // warp-uniform
+            const double2 g = p.Gv[slot];        // warp-uniform
+            const double2 x = e.B[(size_t)j * e.ld + cbase];
+            cr[q] = fma(g.x, x.x, cr[q]);
+            cr1[q] = fma(-g.y, x.y, cr1[q]);
+            ci[q] = fma(g.x, x.y, ci[q]);
+            ci1[q] = fma(g.y, x.x, ci1[q]);
+        }
+    }
+    if (e.epi == 0) {
+        if (cvalid) {
+#pragma unroll
+            for (int q = 0; q < SP_ROWS_PER_WARP; ++q)
+                cheby_epilogue_1(e, (size_t)(row0 + q) * e.ld + cbase, cr[q] + cr1[q], ci[q] + ci1[q]);
+        }
+    } else {
+        double acc = 0.0;
+        if (cvalid) {
+#pragma unroll
+            for (int q = 0; q < SP_ROWS_PER_WARP; ++q) {
+                const double2 ch = e.CHI[(size_t)(row0 + q) * e.ld + cbase];
+                acc += ch.x * (ci[q] + ci1[q]) - ch.y * (cr[q] + cr1[q]);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) wsum[warp] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < SP_WARPS; ++w) t += wsum[w];
+            e.partial[blockIdx.y * gridDim.x + blockIdx.x] = t;
+        }
+    }
+}
+
+// ELL values of G = f (P_0 - beta on the diagonal slot + sum_l eps_l[n] P_l); eps read from device memory
+__global__ void build_G_sparse_kernel(double2 *Gv, const double2 *Pv, size_t nslots, int W, int L, double2 f,
+                                      double beta, const double *eps, int N_T, int n) {
+    double ev[kMaxL];
+    for (int l = 0; l < L; ++l) ev[l] = eps[(size_t)l * N_T + n];
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nslots; i += (size_t)gridDim.x * blockDim.x) {
+        double2 h = Pv[i];
+        if (i % W == 0) h.x -= beta;  // slot 0 is the diagonal
+        for (int l = 0; l < L; ++l) {
+            const double2 hl = Pv[(size_t)(l + 1) * nslots + i];
+            h.x = fma(ev[l], hl.x, h.x);
+            h.y = fma(ev[l], hl.y, h.y);
+        }
+        Gv[i] = make_double2(f.x * h.x - f.y * h.y, f.x * h.y + f.y * h.x);
+    }
+}
+
 struct Block {  // one GEMM column block
     int g, col0, nt;
 };
@@ -359,6 +466,13 @@ struct DenseEngine {
     long long launches = 0;
     int sm_count = 148;
     DenseComm comm;
+    // sparse mode (ELL): shared pattern, values per generator and term for both directions
+    bool sparse = false;
+    int W = 0;
+    int *ell_cols = nullptr;
+    double2 *Pvf = nullptr, *Pvb = nullptr, *Gv = nullptr;  // [g][1+L][dp*W], [g][dp*W]
+    std::vector<int> sp_part_off;  // offset of every column block's CTA partials
+    int nnz_union = 0;
 };
 
 namespace {
@@ -400,15 +514,43 @@ bool launch_gemm(DenseEngine *e, const Block &b, GemmParams p, std::string &err)
     return true;
 }
 
+bool launch_spmm(DenseEngine *e, const Block &b, const double2 *Gv, GemmParams p, int n_partial_off, std::string &err) {
+    SpmmParams sp;
+    memset(&sp, 0, sizeof(sp));
+    p.dp = e->dp;
+    p.ld = e->ld;
+    p.col0 = b.col0;
+    if (p.partial) p.partial += n_partial_off;
+    sp.e = p;
+    sp.cols = e->ell_cols;
+    sp.Gv = Gv;
+    sp.W = e->W;
+    sp.ncols = b.nt * 8;
+    dim3 grid(e->dp / SP_ROWS, (sp.ncols + 31) / 32), block(SP_WARPS * 32);
+    spmm_kernel<<<grid, block, 0, e->stream>>>(sp);
+    e->launches++;
+    DK_CHECK(cudaGetLastError());
+    return true;
+}
+
 // One propagation step of every column block: PSI <- exp(-/+ i H dt) PSI.   `store` = storage slot or nullptr.
 bool step(DenseEngine *e, int dir, int n, const double *d_eps, double2 *store, std::string &err) {
     const Cheb &c = e->ch[dir];
     const int dtc = c.dtc_of_step[n];
     const size_t mat = (size_t)e->dp * e->dp;
     const double2 *H = (dir == KROTOV_FORWARD || e->hermitian) ? e->Hf : e->Hb;
+    const size_t nslots = (size_t)e->dp * e->W;
     for (int g = 0; g < e->n_gen; ++g) {
         const double s = 4.0 / c.Delta[g], beta = c.Delta[g] / 2 + c.E_min[g];
         const double2 f = (dir == KROTOV_FORWARD) ? make_double2(0.0, -s) : make_double2(0.0, s);
+        if (e->sparse) {
+            const double2 *Pv = (dir == KROTOV_FORWARD || e->hermitian) ? e->Pvf : e->Pvb;
+            build_G_sparse_kernel<<<std::max(1, (int)std::min<size_t>(e->sm_count * 4, (nslots + 255) / 256)), 256, 0,
+                                    e->stream>>>(e->Gv + (size_t)g * nslots, Pv + (size_t)g * (1 + e->L) * nslots, nslots,
+                                                 e->W, e->L, f, beta, d_eps, e->N_T, n);
+            e->launches++;
+            continue;
+        }
         build_G_kernel<<<e->sm_count * 4, 256, 0, e->stream>>>(e->G + (size_t)g * mat, H + (size_t)g * (1 + e->L) * mat,
                                                              e->dp, e->L, f, beta, d_eps, e->N_T, n);
         e->launches++;
@@ -442,7 +584,11 @@ bool step(DenseEngine *e, int dir, int n, const double *d_eps, double2 *store, s
             // the last term must not overwrite PSI while other CTAs still read it as V_0 (only when m == 2)
             p.PSI = (m == 2) ? e->V[2] : e->PSI;
             p.store = store;
-            if (!launch_gemm(e, b, p, err)) return false;
+            if (e->sparse) {
+                if (!launch_spmm(e, b, e->Gv + (size_t)b.g * nslots, p, 0, err)) return false;
+            } else if (!launch_gemm(e, b, p, err)) {
+                return false;
+            }
             vprev2 = vprev;
             vprev = e->V[j % 3];
         }
@@ -458,7 +604,7 @@ bool step(DenseEngine *e, int dir, int n, const double *d_eps, double2 *store, s
 
 DenseEngine *dense_create(int d, int N, int L, int N_T, int n_gen, const std::vector<cplx> &Hdense,
                           const std::vector<int> &gen_of_traj, const double *psi0, const double *target, int store_fw,
-                          cudaStream_t stream, std::string &err) {
+                          cudaStream_t stream, std::string &err, const SparseDesc *sp) {
     if (L > kMaxL) {
         err = "too many controls";
         return nullptr;
@@ -492,11 +638,22 @@ DenseEngine *dense_create(int d, int N, int L, int N_T, int n_gen, const std::ve
     for (int k = 0; k < N; ++k) e->traj_of_col[e->col_of_traj[k]] = k;
     e->slab = (size_t)e->dp * e->ld;
     e->n_partial = (int)e->blocks.size() * (e->dp / BM);
-    const size_t mat = (size_t)e->dp * e->dp;
+    e->sparse = (sp != nullptr);
+    if (e->sparse) {
+        e->W = sp->W;
+        e->nnz_union = sp->nnz_union;
+        e->n_partial = 0;
+        for (const Block &b : e->blocks) {
+            e->sp_part_off.push_back(e->n_partial);
+            e->n_partial += (e->dp / SP_ROWS) * ((b.nt * 8 + 31) / 32);
+        }
+    }
+    const size_t mat = e->sparse ? 0 : (size_t)e->dp * e->dp;
+    const size_t nslots = e->sparse ? (size_t)e->dp * e->W : 0;
 
     // Hermitian generators: the adjoint terms are the terms themselves
-    e->hermitian = true;
-    for (int q = 0; q < n_gen * (1 + L) && e->hermitian; ++q) {
+    e->hermitian = e->sparse ? sp->hermitian : true;
+    for (int q = 0; !e->sparse && q < n_gen * (1 + L) && e->hermitian; ++q) {
         const cplx *M = &Hdense[(size_t)q * d * d];
         for (int i = 0; i < d && e->hermitian; ++i)
             for (int j = i; j < d; ++j)
@@ -505,7 +662,7 @@ DenseEngine *dense_create(int d, int N, int L, int N_T, int n_gen, const std::ve
                     break;
                 }
     }
-    size_t need = (size_t)n_gen * (1 + L) * mat * (e->hermitian ? 1 : 2) + (size_t)n_gen * mat;
+    size_t need = (size_t)n_gen * (1 + L) * (mat + nslots) * (e->hermitian ? 1 : 2) + (size_t)n_gen * (mat + nslots);
     need += e->slab * (8 + (size_t)(N_T + 1) * (store_fw ? 2 : 1));
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
@@ -521,15 +678,37 @@ DenseEngine *dense_create(int d, int N, int L, int N_T, int n_gen, const std::ve
               dalloc(e->TGT, e->slab, err) && dalloc(e->CHI, e->slab, err) &&
               dalloc(e->X, e->slab * (size_t)(N_T + 1), err) && dalloc(e->partial, (size_t)L * e->n_partial, err) &&
               dalloc(e->d_col_of_traj, (size_t)N, err) && dalloc(e->d_traj_of_col, (size_t)e->ld, err);
-    if (ok && !e->hermitian) ok = dalloc(e->Hb, (size_t)n_gen * (1 + L) * mat, err);
+    if (ok && !e->hermitian && !e->sparse) ok = dalloc(e->Hb, (size_t)n_gen * (1 + L) * mat, err);
     if (ok && store_fw) ok = dalloc(e->PHI, e->slab * (size_t)(N_T + 1), err);
+    if (ok && e->sparse)
+        ok = dalloc(e->ell_cols, nslots, err) && dalloc(e->Pvf, (size_t)n_gen * (1 + L) * nslots, err) &&
+             dalloc(e->Gv, (size_t)n_gen * nslots, err) &&
+             (e->hermitian || dalloc(e->Pvb, (size_t)n_gen * (1 + L) * nslots, err));
     if (!ok) {
         dense_destroy(e);
         return nullptr;
     }
+    if (e->sparse) {
+        // ELL arrays padded to dp rows: padding rows / slots point at their own row with value 0
+        std::vector<int> cols(nslots);
+        for (size_t i = 0; i < (size_t)e->dp; ++i)
+            for (int sl = 0; sl < e->W; ++sl)
+                cols[i * e->W + sl] = (i < (size_t)d) ? (*sp->cols)[i * e->W + sl] : (int)i;
+        cudaMemcpy(e->ell_cols, cols.data(), nslots * 4, cudaMemcpyHostToDevice);
+        std::vector<cplx> vbuf(nslots);
+        for (int dir = 0; dir < (e->hermitian ? 1 : 2); ++dir) {
+            const std::vector<cplx> &src = dir == 0 ? *sp->vals_f : *sp->vals_b;
+            double2 *dst = dir == 0 ? e->Pvf : e->Pvb;
+            for (int q = 0; q < n_gen * (1 + L); ++q) {
+                std::fill(vbuf.begin(), vbuf.end(), cplx(0, 0));
+                memcpy(vbuf.data(), &src[(size_t)q * d * e->W], sizeof(cplx) * (size_t)d * e->W);
+                cudaMemcpy(dst + (size_t)q * nslots, vbuf.data(), nslots * 16, cudaMemcpyHostToDevice);
+            }
+        }
+    }
     // upload padded generator terms (and adjoints), states, targets
     std::vector<cplx> buf(mat);
-    for (int q = 0; q < n_gen * (1 + L); ++q) {
+    for (int q = 0; !e->sparse && q < n_gen * (1 + L); ++q) {
         const cplx *M = &Hdense[(size_t)q * d * d];
         std::fill(buf.begin(), buf.end(), cplx(0, 0));
         for (int i = 0; i < d; ++i) memcpy(&buf[(size_t)i * e->dp], &M[(size_t)i * d], sizeof(cplx) * d);
@@ -569,17 +748,17 @@ void dense_set_comm(DenseEngine *e, const DenseComm &c) { e->comm = c; }
 void dense_destroy(DenseEngine *e) {
     if (!e) return;
     void *ptrs[] = {e->Hf, e->Hb, e->G, e->V[0], e->V[1], e->V[2], e->OUT, e->PSI, e->PSI0, e->TGT, e->CHI, e->X,
-                    e->PHI, e->partial, e->d_col_of_traj, e->d_traj_of_col};
+                    e->PHI, e->partial, e->d_col_of_traj, e->d_traj_of_col, e->ell_cols, e->Pvf, e->Pvb, e->Gv};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     delete e;
 }
 
 void dense_info(DenseEngine *e, krotov_info *out) {
-    out->grid_blocks = e->dp / BM;
-    out->block_threads = GEMM_THREADS;
-    out->nnz_union = e->d * e->d;
-    out->ell_width = 0;
+    out->grid_blocks = e->sparse ? e->dp / SP_ROWS : e->dp / BM;
+    out->block_threads = e->sparse ? SP_WARPS * 32 : GEMM_THREADS;
+    out->nnz_union = e->sparse ? e->nnz_union : e->d * e->d;
+    out->ell_width = e->sparse ? e->W : 0;
     out->hbm_bytes_state = (int64_t)(e->slab * (size_t)(e->N_T + 1) * 16);
     for (int dir = 0; dir < 2; ++dir) {
         int mm = 0;
@@ -651,6 +830,12 @@ bool dense_iterate(DenseEngine *e, const double *d_eps_old, double *d_eps_new, c
                 p.B = e->PSI;
                 p.epi = 1;
                 p.CHI = e->X + e->slab * (size_t)n;
+                if (e->sparse) {
+                    p.partial = e->partial + (size_t)l * e->n_partial;
+                    const double2 *mu = e->Pvf + ((size_t)b.g * (1 + e->L) + 1 + l) * ((size_t)e->dp * e->W);
+                    if (!launch_spmm(e, b, mu, p, e->sp_part_off[bi], err)) return false;
+                    continue;
+                }
                 p.partial = e->partial + (size_t)l * e->n_partial + bi * ctas;
                 if (!launch_gemm(e, b, p, err)) return false;
             }

@@ -17,9 +17,17 @@ struct DenseComm {  // per-iteration view of the rank mailboxes (see krotov_comm
     long long timeout_cycles = 0;
 };
 void dense_set_comm(DenseEngine *e, const DenseComm &c);
+// Sparse generators (d > 32): ELL description with one shared pattern, slot 0 = diagonal.
+struct SparseDesc {
+    int W = 0, nnz_union = 0;
+    bool hermitian = true;
+    const std::vector<int> *cols = nullptr;                     // [d][W]
+    const std::vector<std::complex<double>> *vals_f = nullptr;  // [n_gen][1+L][d][W]
+    const std::vector<std::complex<double>> *vals_b = nullptr;  // adjoint terms (unused when hermitian)
+};
 DenseEngine *dense_create(int d, int N, int L, int N_T, int n_gen, const std::vector<std::complex<double>> &Hdense,
                           const std::vector<int> &gen_of_traj, const double *psi0, const double *target, int store_fw,
-                          cudaStream_t stream, std::string &err);
+                          cudaStream_t stream, std::string &err, const SparseDesc *sp = nullptr);
 void dense_destroy(DenseEngine *e);
 void dense_info(DenseEngine *e, krotov_info *out);
 bool dense_set_cheby(DenseEngine *e, int direction, int ndtc, const std::vector<int> &dtc_of_step,

@@ -54,6 +54,13 @@ struct DevBuf {
     }
 };
 
+struct HostSparse {  // ELL description of a sparse generator family (d > 32), slot 0 = diagonal
+    int W = 0, nnz_union = 0;
+    bool hermitian = true;
+    std::vector<int> cols;
+    std::vector<cplx> vals_f, vals_b;
+};
+
 struct ChebyTables {  // one direction
     bool set = false;
     int ndtc = 0, mmax = 0, m_max_used = 0;
@@ -524,35 +531,96 @@ int krotov_create(const krotov_problem *pb, krotov_handle *out) {
     if (pb->weight) h->weight.assign(pb->weight, pb->weight + N);
     h->has_target = pb->target != nullptr;
 
-    // dense host copy of every term (row-major)
-    h->Hdense.assign((size_t)h->n_gen * (1 + L) * d * d, cplx(0, 0));
+    // ---- generator ingestion.  `for_each_entry` walks the non-zeros of term (g, t) in either wire format.
     const cplx *vals = reinterpret_cast<const cplx *>(pb->gen_values);
-    for (int g = 0; g < h->n_gen; ++g)
-        for (int t = 0; t <= L; ++t) {
-            if (pb->term_present && !pb->term_present[(size_t)g * (1 + L) + t]) continue;
-            cplx *dst = &h->Hdense[((size_t)g * (1 + L) + t) * d * d];
-            if (pb->gen_format == KROTOV_GEN_DENSE_COLMAJOR) {
-                const cplx *src = vals + ((size_t)g * (1 + L) + t) * d * d;
-                for (int j = 0; j < d; ++j)
-                    for (int i = 0; i < d; ++i) dst[(size_t)i * d + j] = src[(size_t)j * d + i];
-            } else if (pb->gen_format == KROTOV_GEN_CSR) {
-                const cplx *src = vals + ((size_t)g * (1 + L) + t) * pb->nnz;
+    if (pb->gen_format != KROTOV_GEN_DENSE_COLMAJOR && pb->gen_format != KROTOV_GEN_CSR)
+        return bail(fail(h, KROTOV_ERR_ARG, "unknown gen_format"));
+    if (pb->gen_format == KROTOV_GEN_CSR)
+        for (int q = 0; q < pb->csr_rowptr[d]; ++q)
+            if (pb->csr_colind[q] < 0 || pb->csr_colind[q] >= d)
+                return bail(fail(h, KROTOV_ERR_ARG, "CSR column out of range"));
+    auto for_each_entry = [&](int g, int t, auto &&fn) {
+        if (pb->term_present && !pb->term_present[(size_t)g * (1 + L) + t]) return;
+        if (pb->gen_format == KROTOV_GEN_DENSE_COLMAJOR) {
+            const cplx *src = vals + ((size_t)g * (1 + L) + t) * d * d;
+            for (int j = 0; j < d; ++j)
                 for (int i = 0; i < d; ++i)
-                    for (int q = pb->csr_rowptr[i]; q < pb->csr_rowptr[i + 1]; ++q) {
-                        int j = pb->csr_colind[q];
-                        if (j < 0 || j >= d) return bail(fail(h, KROTOV_ERR_ARG, "CSR column out of range"));
-                        dst[(size_t)i * d + j] += src[q];
-                    }
-            } else {
-                return bail(fail(h, KROTOV_ERR_ARG, "unknown gen_format"));
-            }
+                    if (src[(size_t)j * d + i] != cplx(0.0, 0.0)) fn(i, j, src[(size_t)j * d + i]);
+        } else {
+            const cplx *src = vals + ((size_t)g * (1 + L) + t) * pb->nnz;
+            for (int i = 0; i < d; ++i)
+                for (int q = pb->csr_rowptr[i]; q < pb->csr_rowptr[i + 1]; ++q) fn(i, pb->csr_colind[q], src[q]);
         }
+    };
 
     int path = pb->force_path;
-    if (path == 0) path = (d <= 32) ? KROTOV_PATH_WARP : KROTOV_PATH_DENSE;
     if (path == KROTOV_PATH_WARP && d > 32)
         return bail(fail(h, KROTOV_ERR_UNSUPPORTED, "warp path needs d <= 32"));
+    if (path != 0 && path != KROTOV_PATH_WARP && path != KROTOV_PATH_DENSE && path != KROTOV_PATH_SPARSE)
+        return bail(fail(h, KROTOV_ERR_ARG, "bad force_path"));
+    if (path != KROTOV_PATH_WARP && d <= 32 && path == 0) path = KROTOV_PATH_WARP;
+
+    // d > 32: union sparsity pattern (symmetrised: the backward sweep needs the adjoint; diagonal always present)
+    HostSparse hs;
+    if (path == 0 || path == KROTOV_PATH_SPARSE) {
+        std::vector<std::vector<int>> pat(d);
+        for (int i = 0; i < d; ++i) pat[i].push_back(i);
+        for (int g = 0; g < h->n_gen; ++g)
+            for (int t = 0; t <= L; ++t)
+                for_each_entry(g, t, [&](int i, int j, cplx) {
+                    if (i != j) {
+                        pat[i].push_back(j);
+                        pat[j].push_back(i);
+                    }
+                });
+        size_t nnz = 0;
+        int W = 1;
+        for (int i = 0; i < d; ++i) {
+            std::sort(pat[i].begin() + 1, pat[i].end());
+            pat[i].erase(std::unique(pat[i].begin() + 1, pat[i].end()), pat[i].end());
+            nnz += pat[i].size();
+            W = std::max(W, (int)pat[i].size());
+        }
+        // sparse path when the generator is sparse enough for ELL rows to pay off against DMMA tiles
+        const bool sparse_ok = (double)nnz <= 0.25 * (double)d * d && W <= 512;
+        if (path == 0) path = sparse_ok ? KROTOV_PATH_SPARSE : KROTOV_PATH_DENSE;
+        if (path == KROTOV_PATH_SPARSE) {
+            hs.W = W;
+            hs.nnz_union = (int)std::min<size_t>(nnz, 0x7fffffff);
+            hs.cols.assign((size_t)d * W, 0);
+            for (int i = 0; i < d; ++i)
+                for (int sl = 0; sl < W; ++sl) hs.cols[(size_t)i * W + sl] = sl < (int)pat[i].size() ? pat[i][sl] : i;
+            auto slot_of = [&](int i, int j) -> int {
+                if (i == j) return 0;
+                auto it = std::lower_bound(pat[i].begin() + 1, pat[i].end(), j);
+                return (int)(it - pat[i].begin());
+            };
+            const size_t per_term = (size_t)d * W;
+            hs.vals_f.assign((size_t)h->n_gen * (1 + L) * per_term, cplx(0, 0));
+            hs.vals_b.assign(hs.vals_f.size(), cplx(0, 0));
+            for (int g = 0; g < h->n_gen; ++g)
+                for (int t = 0; t <= L; ++t) {
+                    const size_t base = ((size_t)g * (1 + L) + t) * per_term;
+                    for_each_entry(g, t, [&](int i, int j, cplx v) {
+                        hs.vals_f[base + (size_t)i * W + slot_of(i, j)] += v;
+                        hs.vals_b[base + (size_t)j * W + slot_of(j, i)] += std::conj(v);
+                    });
+                }
+            hs.hermitian = (hs.vals_f == hs.vals_b);
+            if (hs.hermitian) std::vector<cplx>().swap(hs.vals_b);
+        }
+    }
     h->path = path;
+
+    if (path != KROTOV_PATH_SPARSE) {
+        // dense host copy of every term (row-major)
+        h->Hdense.assign((size_t)h->n_gen * (1 + L) * d * d, cplx(0, 0));
+        for (int g = 0; g < h->n_gen; ++g)
+            for (int t = 0; t <= L; ++t) {
+                cplx *dst = &h->Hdense[((size_t)g * (1 + L) + t) * d * d];
+                for_each_entry(g, t, [&](int i, int j, cplx v) { dst[(size_t)i * d + j] += v; });
+            }
+    }
 
     int rc;
     // ---- buffers common to both paths
@@ -581,8 +649,8 @@ int krotov_create(const krotov_problem *pb, krotov_handle *out) {
     }
 
     // are all control terms Hermitian?  (mu_l^dagger = mu_l lets the kernel form mu_l chi ahead of time)
-    h->mu_hermitian = true;
-    for (int g = 0; g < h->n_gen && h->mu_hermitian; ++g)
+    h->mu_hermitian = (path == KROTOV_PATH_WARP);
+    for (int g = 0; path == KROTOV_PATH_WARP && g < h->n_gen && h->mu_hermitian; ++g)
         for (int t = 1; t <= L && h->mu_hermitian; ++t)
             for (int i = 0; i < d && h->mu_hermitian; ++i)
                 for (int j = i; j < d; ++j)
@@ -620,9 +688,16 @@ int krotov_create(const krotov_problem *pb, krotov_handle *out) {
             cudaMemset(h->d_prof.p, 0, h->d_prof.bytes);
         }
     } else {
+        kr::SparseDesc sd;
+        if (path == KROTOV_PATH_SPARSE) {
+            sd.W = hs.W; sd.nnz_union = hs.nnz_union; sd.hermitian = hs.hermitian;
+            sd.cols = &hs.cols; sd.vals_f = &hs.vals_f; sd.vals_b = &hs.vals_b;
+        }
         h->dense = kr::dense_create(h->d, h->N, h->L, h->N_T, h->n_gen, h->Hdense, h->gen_of_traj, pb->psi0,
-                                    pb->target, h->store_fw, h->stream, h->err);
+                                    pb->target, h->store_fw, h->stream, h->err,
+                                    path == KROTOV_PATH_SPARSE ? &sd : nullptr);
         if (!h->dense) return bail(KROTOV_ERR_UNSUPPORTED);
+        std::vector<cplx>().swap(h->Hdense);  // the device holds the generators now
     }
     if (cudaDeviceSynchronize() != cudaSuccess) return bail(fail(h, KROTOV_ERR_CUDA, "device sync after create failed"));
     *out = h;

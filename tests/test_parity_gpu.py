@@ -505,3 +505,38 @@ def test_non_hermitian_generator_uses_adjoint_backward(d, force_path):
     ref = O.optimize_krotov(W.to_oracle(w), 2)
     assert np.isfinite(ref["J_T"]).all()
     assert_parity(got, ref["J_T"], ref["pulses"], ref["g_a_int"])
+
+
+# ---- sparse generators on larger Hilbert spaces: ELL SpMM path --------------------------------------------------
+@pytest.mark.parametrize("n_spins,n_traj,functional", [(6, 8, "ss"), (7, 40, "sm"), (8, 5, "re")])
+def test_sparse_path_spin_chain_vs_oracle(n_spins, n_traj, functional):
+    from oracle import c_oracle as C
+
+    w = W.spin_chain(n_spins=n_spins, n_traj=n_traj, functional=functional)
+    got = run_product(w, 2)
+    assert got["info"]["path"] == 3 and got["info"]["ell_width"] <= 2 * n_spins  # diag + (n-1) exchange + n flips
+    ref = C.optimize_krotov_c(W.to_oracle(w), 2)
+    assert_parity(got, ref["J_T"], ref["pulses"], rtol=1e-10, atol=5e-13)
+
+
+def test_sparse_path_equals_dense_path_and_csr_input():
+    w = W.spin_chain(n_spins=6, n_traj=12)
+    a = run_product(w, 2)
+    b = run_product(w, 2, force_path=2)
+    c = run_product(w, 2, csr_generators=True)
+    assert (a["info"]["path"], b["info"]["path"], c["info"]["path"]) == (3, 2, 3)
+    assert np.abs(np.array(a["J_T"]) - np.array(b["J_T"])).max() < 1e-13
+    assert np.abs(a["pulses"] - b["pulses"]).max() < 1e-12
+    assert np.array_equal(a["pulses"], c["pulses"])
+
+
+def test_sparse_path_non_hermitian():
+    from oracle import krotov_oracle as O
+
+    w = W.spin_chain(n_spins=6, n_traj=4, n_grid=21)
+    rng = np.random.default_rng(8)
+    w.H0 = [w.H0[0] - 0.02j * np.diag(rng.uniform(0, 1, 64))]
+    got = run_product(w, 2)
+    assert got["info"]["path"] == 3
+    ref = O.optimize_krotov(W.to_oracle(w), 2)
+    assert_parity(got, ref["J_T"], ref["pulses"], ref["g_a_int"])

@@ -317,3 +317,47 @@ def to_oracle(w: Workload):
         functional=w.functional,
         specrange=w.specrange,
     )
+
+
+# ---- spin chain: sparse generator on a large Hilbert space ---------------------------------------------------
+def spin_chain(n_spins=6, n_traj=8, n_grid=41, T=4.0, seed=12, functional="ss"):
+    """XXZ chain with open ends in a longitudinal field, driven by global sigma_x and sigma_y fields:
+    d = 2^n_spins, about n_spins + 1 non-zeros per row (sparse; complex entries through sigma_y)."""
+    sx = np.array([[0, 1], [1, 0]], complex)
+    sy = np.array([[0, -1j], [1j, 0]], complex)
+    sz = np.array([[1, 0], [0, -1]], complex)
+    I2 = np.eye(2, dtype=complex)
+
+    def op(single, site):
+        out = np.array([[1.0 + 0j]])
+        for s in range(n_spins):
+            out = np.kron(out, single if s == site else I2)
+        return out
+
+    d = 2 ** n_spins
+    H0 = np.zeros((d, d), complex)
+    for i in range(n_spins - 1):
+        H0 += 0.25 * (op(sx, i) @ op(sx, i + 1) + op(sy, i) @ op(sy, i + 1)) + 0.15 * op(sz, i) @ op(sz, i + 1)
+    for i in range(n_spins):
+        H0 += 0.1 * (1 + 0.3 * i) * op(sz, i)
+    Hx = sum(op(sx, i) for i in range(n_spins)) * 0.5
+    Hy = sum(op(sy, i) for i in range(n_spins)) * 0.5
+    rng = np.random.default_rng(seed)
+    psi0 = np.zeros((n_traj, d), complex)
+    for k in range(n_traj):
+        psi0[k, k % d] = 1.0
+    tg = rng.standard_normal((n_traj, d)) + 1j * rng.standard_normal((n_traj, d))
+    tg /= np.linalg.norm(tg, axis=1, keepdims=True)
+    return Workload(
+        name=f"spin-chain-{n_spins}",
+        tlist=np.linspace(0, T, n_grid),
+        H0=[H0],
+        Hc=[[Hx, Hy]],
+        gen_of_traj=np.zeros(n_traj, int),
+        psi0=psi0,
+        target=tg,
+        controls=[lambda t: 0.4 * flattop(t, T=T, t_rise=0.4), lambda t: 0.1 * flattop(t, T=T, t_rise=0.4) * math.sin(2 * t)],
+        update_shape=lambda t: flattop(t, T=T, t_rise=0.4),
+        lambda_a=1.0,
+        functional=functional,
+    )
