@@ -49,10 +49,14 @@ def specrange(G, method="auto"):
     """``(E_min, E_max)`` of an operator.  ``diag``: exact eigenvalues (dense).  ``auto`` uses
     ``diag`` up to dimension 512 and a Lanczos/Arnoldi estimate (scipy ``eigs``, widened by 5 %)
     beyond; pass ``prop_E_min`` / ``prop_E_max`` to bypass it."""
-    G = np.asarray(G)
+    sparse = hasattr(G, "tocsr")
     d = G.shape[0]
     if method == "auto":
         method = "diag" if d <= 512 else "arnoldi"
+    if sparse and method == "diag":
+        G = G.toarray()
+    elif not sparse:
+        G = np.asarray(G)
     if method == "diag":
         if np.array_equal(G, G.conj().T):  # Hermitian: symmetric solver (what Julia's `eigvals` picks)
             ev = np.linalg.eigvalsh(G)
@@ -60,11 +64,17 @@ def specrange(G, method="auto"):
         ev = np.linalg.eigvals(G)
         return float(ev.real.min()), float(ev.real.max())
     if method == "arnoldi":
-        from scipy.sparse.linalg import eigs
+        from scipy.sparse.linalg import eigs, eigsh
 
-        v0 = np.ones(d, np.complex128) / np.sqrt(d)
-        hi = eigs(G, k=1, which="LR", v0=v0, return_eigenvectors=False, tol=1e-4)[0].real
-        lo = eigs(G, k=1, which="SR", v0=v0, return_eigenvectors=False, tol=1e-4)[0].real
+        v0 = (np.arange(1, d + 1) % 7 + 1.0).astype(np.complex128)  # fixed, non-symmetric start vector
+        v0 /= np.linalg.norm(v0)
+        herm = (abs(G - G.conj().T).max() == 0) if sparse else np.array_equal(G, G.conj().T)
+        if herm:
+            hi = eigsh(G, k=1, which="LA", v0=v0, return_eigenvectors=False, tol=1e-5)[0].real
+            lo = eigsh(G, k=1, which="SA", v0=v0, return_eigenvectors=False, tol=1e-5)[0].real
+        else:
+            hi = eigs(G, k=1, which="LR", v0=v0, return_eigenvectors=False, tol=1e-5)[0].real
+            lo = eigs(G, k=1, which="SR", v0=v0, return_eigenvectors=False, tol=1e-5)[0].real
         pad = 0.05 * (hi - lo)
         return float(lo - pad), float(hi + pad)
     raise ValueError(f"unknown specrange method {method!r}")
@@ -110,15 +120,17 @@ class ChebyDirection:
         self.manual = None if (E_min is None or E_max is None) else (float(E_min), float(E_max))
         self.control_ranges = [(float(np.min(p)), float(np.max(p))) for p in pulses]
         self.n_updates = 0
-        self._H0s = np.stack([np.asarray(h, np.complex128) for h in H0])
-        d = self._H0s.shape[1]
-        self._Hcs = [np.stack([np.zeros((d, d), np.complex128) if row[l] is None else np.asarray(row[l], np.complex128)
-                               for row in Hc]) for l in range(len(pulses))]
+        self._any_sparse = any(hasattr(m, "tocsr") for m in list(H0) + [x for row in Hc for x in row if x is not None])
+        if not self._any_sparse and H0[0].shape[0] <= 512:
+            self._H0s = np.stack([np.asarray(h, np.complex128) for h in H0])
+            d = self._H0s.shape[1]
+            self._Hcs = [np.stack([np.zeros((d, d), np.complex128) if row[l] is None else
+                                   np.asarray(row[l], np.complex128) for row in Hc]) for l in range(len(pulses))]
         self._derive()
 
     # -- spectral envelope (cheby_get_spectral_envelope + specrange_buffer) ----------------
     def _evaluate(self, g, vals):
-        G = np.array(self.H0[g], np.complex128)
+        G = self.H0[g].copy() if hasattr(self.H0[g], "tocsr") else np.array(self.H0[g], np.complex128)
         for l, Hl in enumerate(self.Hc[g]):
             if Hl is not None:
                 G = G + vals[l] * Hl
@@ -131,7 +143,7 @@ class ChebyDirection:
         if self.manual is not None:
             e_min = np.full(n_gen, self.manual[0])
             e_max = np.full(n_gen, self.manual[1])
-        elif self.method in ("auto", "diag") and self.H0[0].shape[0] <= 512:
+        elif self.method in ("auto", "diag") and self.H0[0].shape[0] <= 512 and not self._any_sparse:
             # all generators in two batched LAPACK calls (numpy loops over the stack in C and calls the same
             # zgeev per matrix, so every number is what `specrange` returns for the single matrix)
             # (the Hermitian solver when every evaluated generator is Hermitian, like `specrange`)

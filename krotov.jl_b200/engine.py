@@ -29,32 +29,51 @@ class KrotovCuda:
         n_gen = len(H0)
         L = len(Hc[0])
         N_T = len(tlist) - 1
-        vals = np.zeros((n_gen, 1 + L, d, d), np.complex128)
         present = np.ones((n_gen, 1 + L), np.uint8)
         for g in range(n_gen):
-            vals[g, 0] = np.asarray(H0[g]).T  # column-major on the wire (Julia Matrix layout)
             for l in range(L):
                 if Hc[g][l] is None:
                     present[g, 1 + l] = 0
-                else:
-                    vals[g, 1 + l] = np.asarray(Hc[g][l]).T
+        any_sparse = any(hasattr(m, "tocsr") for m in list(H0) + [x for row in Hc for x in row if x is not None])
         self.N, self.d, self.L, self.N_T, self.n_gen = N, d, L, N_T, n_gen
         rowptr = colind = None
         nnz = 0
-        if csr:
-            # KROTOV_GEN_CSR: one shared (union) pattern, values [n_gen][1+L][nnz]
-            pat = np.zeros((d, d), bool)
-            for g in range(n_gen):
-                for t in range(1 + L):
-                    pat |= vals[g, t].T != 0
-            rows, cols = np.nonzero(pat)
-            rowptr = np.zeros(d + 1, np.int32)
+        if any_sparse or csr:
+            # KROTOV_GEN_CSR: one shared (union) pattern, values [n_gen][1+L][nnz]; nothing is densified
+            import scipy.sparse as sp
+
+            terms = [[sp.csr_matrix(H0[g], dtype=np.complex128)] +
+                     [None if Hc[g][l] is None else sp.csr_matrix(Hc[g][l], dtype=np.complex128) for l in range(L)]
+                     for g in range(n_gen)]
+            keys = []
+            for row in terms:
+                for m in row:
+                    if m is not None:
+                        c = m.tocoo()
+                        nz = c.data != 0
+                        keys.append(c.row[nz].astype(np.int64) * d + c.col[nz])
+            union = np.unique(np.concatenate(keys)) if keys else np.zeros(0, np.int64)
+            rows, cols = union // d, union % d
+            rowptr = np.zeros(d + 1, np.int64)
             np.add.at(rowptr, rows + 1, 1)
             rowptr = np.cumsum(rowptr).astype(np.int32)
             colind = cols.astype(np.int32)
             nnz = len(colind)
-            vals = np.ascontiguousarray(np.stack([[vals[g, t].T[rows, cols] for t in range(1 + L)]
-                                                  for g in range(n_gen)]), np.complex128)
+            vals = np.zeros((n_gen, 1 + L, nnz), np.complex128)
+            for g, row in enumerate(terms):
+                for t, m in enumerate(row):
+                    if m is not None:
+                        c = m.tocoo()
+                        pos = np.searchsorted(union, c.row.astype(np.int64) * d + c.col)
+                        ok = c.data != 0
+                        np.add.at(vals[g, t], pos[ok], c.data[ok])
+        else:
+            vals = np.zeros((n_gen, 1 + L, d, d), np.complex128)
+            for g in range(n_gen):
+                vals[g, 0] = np.asarray(H0[g]).T  # column-major on the wire (Julia Matrix layout)
+                for l in range(L):
+                    if Hc[g][l] is not None:
+                        vals[g, 1 + l] = np.asarray(Hc[g][l]).T
         gen = np.ascontiguousarray(gen_of_traj, np.int32)
         S = np.ascontiguousarray(update_shape, np.float64).reshape(L, N_T)
         lam = np.ascontiguousarray(lambda_a, np.float64).reshape(L)
@@ -63,7 +82,7 @@ class KrotovCuda:
         p = B.Problem()
         p.struct_size = C.sizeof(B.Problem)
         p.d, p.n_traj, p.n_ctrl, p.n_steps, p.n_gen = d, N, L, N_T, n_gen
-        p.gen_format, p.nnz = (B.GEN_CSR, nnz) if csr else (B.GEN_DENSE_COLMAJOR, 0)
+        p.gen_format, p.nnz = (B.GEN_CSR, nnz) if rowptr is not None else (B.GEN_DENSE_COLMAJOR, 0)
         p.csr_rowptr, p.csr_colind = _ptr(rowptr), _ptr(colind)
         p.tlist, p.gen_of_traj = _ptr(tlist), _ptr(gen)
         p.gen_values, p.term_present = _ptr(vals), _ptr(present)

@@ -7,9 +7,16 @@ import numpy as np
 __all__ = ["Generator", "hamiltonian"]
 
 
+def _is_sparse(op):
+    return hasattr(op, "tocsr") and hasattr(op, "nnz")
+
+
 def _as_matrix(op):
-    if hasattr(op, "toarray"):  # scipy.sparse
-        op = op.toarray()
+    if _is_sparse(op):  # scipy.sparse operators stay sparse: large spin chains are never densified
+        m = op.tocsr().astype(np.complex128)
+        if m.shape[0] != m.shape[1]:
+            raise ValueError("operators must be square matrices")
+        return m
     m = np.asarray(op, dtype=np.complex128)
     if m.ndim != 2 or m.shape[0] != m.shape[1]:
         raise ValueError("operators must be square matrices")
@@ -35,14 +42,14 @@ class Generator:
         return self.ops[0].shape[0]
 
     def drift(self):
-        d = self.dim
-        out = np.zeros((d, d), np.complex128)
-        for o in self.drift_ops:
+        out = self.drift_ops[0]
+        for o in self.drift_ops[1:]:
             out = out + o
-        return out
+        return out.copy()
 
     def adjoint(self):
-        return Generator([o.conj().T for o in self.drift_ops], [o.conj().T for o in self.control_ops], self.amplitudes)
+        adj = lambda o: o.conj().T.tocsr() if _is_sparse(o) else o.conj().T  # noqa: E731
+        return Generator([adj(o) for o in self.drift_ops], [adj(o) for o in self.control_ops], self.amplitudes)
 
     def __repr__(self):
         return f"Generator(dim={self.dim}, drift terms={len(self.drift_ops)}, controls={len(self.amplitudes)})"
@@ -55,7 +62,7 @@ def hamiltonian(*terms):
     drift, cops, amps = [], [], []
     for term in terms:
         if isinstance(term, (tuple, list)) and len(term) == 2 and not np.isscalar(term[0]) and (
-                callable(term[1]) or np.ndim(term[1]) == 1) and np.ndim(term[0]) == 2:
+                callable(term[1]) or np.ndim(term[1]) == 1) and (_is_sparse(term[0]) or np.ndim(term[0]) == 2):
             cops.append(term[0])
             amps.append(term[1])
         else:
@@ -66,6 +73,6 @@ def hamiltonian(*terms):
             out = out + _as_matrix(o)
         return out
     if not drift:
-        d = _as_matrix(cops[0]).shape[0]
-        drift = [np.zeros((d, d), np.complex128)]
+        first = _as_matrix(cops[0])
+        drift = [first * 0.0 if _is_sparse(first) else np.zeros(first.shape, np.complex128)]
     return Generator(drift, cops, amps)

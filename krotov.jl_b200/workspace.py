@@ -276,11 +276,9 @@ class KrotovWrk:
             gen_of_traj[k] = gen_ids[key]
         H0, Hc = [], []
         for gen, derivs in gens:
-            if isinstance(gen, Generator):
-                H0.append(gen.drift())
-            else:
-                H0.append(np.asarray(gen, np.complex128))
-            Hc.append([None if mu is None else np.asarray(mu, np.complex128) for mu in derivs])
+            keep = lambda m: m if hasattr(m, "tocsr") else np.asarray(m, np.complex128)  # noqa: E731
+            H0.append(keep(gen.drift()) if isinstance(gen, Generator) else keep(gen))
+            Hc.append([None if mu is None else keep(mu) for mu in derivs])
         psi0 = np.array([t.initial_state for t in trajs], np.complex128).reshape(N, d)
         has_all_targets = all(t.target_state is not None for t in trajs)
         has_any_target = any(t.target_state is not None for t in trajs)
@@ -321,8 +319,9 @@ class KrotovWrk:
             comm.connect(self.engine)
         # ---- Chebyshev settings of both directions (init_prop: un-widened ranges of the guess pulses)
         def settings(pk, backward):
-            H0s = [h.conj().T for h in self._H0] if backward else self._H0
-            Hcs = [[None if h is None else h.conj().T for h in row] for row in self._Hc] if backward else self._Hc
+            adj = lambda m: m.conj().T.tocsr() if hasattr(m, "tocsr") else m.conj().T  # noqa: E731
+            H0s = [adj(h) for h in self._H0] if backward else self._H0
+            Hcs = [[None if h is None else adj(h) for h in row] for row in self._Hc] if backward else self._Hc
             return ChebyDirection(
                 H0s, Hcs, tlist, backward, self.pulses0,
                 limit=pk.get("cheby_coeffs_limit", 1e-12), specrange_buffer=pk.get("specrange_buffer", 0.01),
