@@ -61,7 +61,7 @@ enum krotov_functional { /* built-in chi = -dJ_T/d<psi| (QuantumControl.Function
 };
 
 enum krotov_path { /* which kernel family serves the handle (krotov_info.path) */
-    KROTOV_PATH_WARP = 1, /* d <= 32: one warp per trajectory, whole iteration in one persistent launch */
+    KROTOV_PATH_WARP = 1, /* d <= 32 (or d <= 128 with narrow rows): 1/2/4 warps per trajectory, whole iteration in one persistent launch */
     KROTOV_PATH_DENSE = 2, /* larger d, dense generators: FP64 DMMA complex GEMM per Chebyshev term             */
     KROTOV_PATH_SPARSE = 3 /* larger d, sparse generators: ELL SpMM over the state block per Chebyshev term      */
 };

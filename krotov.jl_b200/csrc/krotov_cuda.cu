@@ -90,7 +90,8 @@ struct krotov_handle_s {
     bool preg = false;
     bool pair = false;  // two trajectories of one generator per warp (warp2_kernel.cuh)
     bool mu_hermitian = false;
-    std::vector<int> cols;  // [Wt][32]
+    int lpt = 32;  // threads (= padded rows) per trajectory on the warp path: 32, 64 or 128
+    std::vector<int> cols;  // [Wt][lpt]
     std::vector<char> slot_valid;  // [Wt][32] slot holds a real matrix entry (i, cols[s][i])
     int wpc = 1, tpw = 1, nCTA = 1;
     DevBuf d_cols, d_Pf, d_Pb, d_inv_s, d_gen, d_dt, d_alpha, d_eps_old, d_eps_new, d_ga, d_X, d_Phi, d_psi0,
@@ -157,11 +158,14 @@ int upload(krotov_handle h, DevBuf &b, const std::vector<T> &v) {
 // ---- kernel table ------------------------------------------------------------------------
 using WarpKernel = void (*)(const kr::WarpParams);
 struct KernelKey {
-    int W, LT;
-    bool operator<(const KernelKey &o) const { return W < o.W || (W == o.W && LT < o.LT); }
+    int W, LT, LPT = 32;
+    bool operator<(const KernelKey &o) const {
+        return W != o.W ? W < o.W : (LT != o.LT ? LT < o.LT : LPT < o.LPT);
+    }
 };
 
-#define KR_INST(W, LT, MT) {{W, LT}, (WarpKernel)kr::krotov_warp_kernel<W, LT, MT>}
+#define KR_INST(W, LT, MT) {{W, LT, 32}, (WarpKernel)kr::krotov_warp_kernel<W, LT, MT>}
+#define KR_INSTW(W, LT, MT, LPT) {{W, LT, LPT}, (WarpKernel)kr::krotov_warp_kernel<W, LT, MT, LPT>}
 const std::map<KernelKey, WarpKernel> &kernel_table() {
     static const std::map<KernelKey, WarpKernel> tab = {
         // runtime-L variants (rows reloaded per use), up to 15 trajectory warps per CTA
@@ -175,12 +179,21 @@ const std::map<KernelKey, WarpKernel> &kernel_table() {
         KR_INST(1, 2, 256), KR_INST(2, 2, 256), KR_INST(3, 2, 256), KR_INST(4, 2, 256), KR_INST(5, 2, 256),
         KR_INST(6, 2, 256), KR_INST(7, 2, 256), KR_INST(8, 2, 256), KR_INST(10, 2, 256),
         KR_INST(2, 3, 256), KR_INST(4, 3, 256), KR_INST(6, 3, 256),
+        // wider groups: 64 or 128 threads (rows) per trajectory for 32 < d <= 128 with narrow rows
+        KR_INSTW(4, 0, 512, 64), KR_INSTW(6, 0, 512, 64), KR_INSTW(8, 0, 512, 64), KR_INSTW(10, 0, 512, 64),
+        KR_INSTW(12, 0, 512, 64), KR_INSTW(16, 0, 512, 64), KR_INSTW(20, 0, 512, 64), KR_INSTW(24, 0, 512, 64),
+        KR_INSTW(4, 1, 256, 64), KR_INSTW(6, 1, 256, 64), KR_INSTW(8, 1, 256, 64), KR_INSTW(10, 1, 256, 64),
+        KR_INSTW(4, 2, 256, 64), KR_INSTW(6, 2, 256, 64), KR_INSTW(8, 2, 256, 64),
+        KR_INSTW(4, 0, 512, 128), KR_INSTW(6, 0, 512, 128), KR_INSTW(8, 0, 512, 128), KR_INSTW(12, 0, 512, 128),
+        KR_INSTW(16, 0, 512, 128), KR_INSTW(24, 0, 512, 128),
+        KR_INSTW(4, 1, 256, 128), KR_INSTW(6, 1, 256, 128), KR_INSTW(8, 1, 256, 128), KR_INSTW(4, 2, 256, 128),
+        KR_INSTW(6, 2, 256, 128), KR_INSTW(8, 2, 256, 128),
     };
     return tab;
 }
 
 // pair kernel (two trajectories of one generator per warp): register-resident rows only
-#define KR_INST2(W, LT) {{W, LT}, (WarpKernel)kr::krotov_warp2_kernel<W, LT>}
+#define KR_INST2(W, LT) {{W, LT, 32}, (WarpKernel)kr::krotov_warp2_kernel<W, LT>}
 const std::map<KernelKey, WarpKernel> &kernel2_table() {
     static const std::map<KernelKey, WarpKernel> tab = {
         KR_INST2(2, 1), KR_INST2(3, 1), KR_INST2(4, 1), KR_INST2(5, 1), KR_INST2(6, 1), KR_INST2(7, 1), KR_INST2(8, 1),
@@ -191,8 +204,20 @@ const std::map<KernelKey, WarpKernel> &kernel2_table() {
 }
 
 const int kWidths[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 16, 20, 24, 31};
+const int kWidthsWide64[] = {4, 6, 8, 10, 12, 16, 20, 24};
+const int kWidthsWide128[] = {4, 6, 8, 12, 16, 24};
 
-int pick_width(int W) {
+int pick_width(int W, int lpt = 32) {
+    if (lpt == 64) {
+        for (int w : kWidthsWide64)
+            if (w >= W) return w;
+        return -1;
+    }
+    if (lpt == 128) {
+        for (int w : kWidthsWide128)
+            if (w >= W) return w;
+        return -1;
+    }
     for (int w : kWidths)
         if (w >= W) return w;
     return -1;
@@ -204,7 +229,7 @@ cplx Hval(const krotov_handle h, int g, int t, int i, int j) {
 
 // ---- pattern + slot assignment -------------------------------------------------------------
 int build_pattern(krotov_handle h) {
-    const int d = h->d;
+    const int d = h->d, lpt = h->lpt;
     std::vector<char> pat((size_t)d * d, 0);
     for (int g = 0; g < h->n_gen; ++g)
         for (int t = 0; t <= h->L; ++t)
@@ -231,25 +256,26 @@ int build_pattern(krotov_handle h) {
         if (!pat[(size_t)i * d + i]) ++nnz;  // diagonal is always kept
     }
     h->nnz_union = nnz;
-    const bool use_dia = (int)diags.size() <= std::max(wmax, 1) + 1 && pick_width((int)diags.size()) > 0 &&
-                         pick_width((int)diags.size()) <= pick_width(std::max(wmax, 1));
+    const bool use_dia = (int)diags.size() <= std::max(wmax, 1) + 1 && pick_width((int)diags.size(), lpt) > 0 &&
+                         (pick_width(std::max(wmax, 1), lpt) < 0 ||
+                          pick_width((int)diags.size(), lpt) <= pick_width(std::max(wmax, 1), lpt));
     h->W = std::max(1, use_dia ? (int)diags.size() : wmax);
-    h->Wt = pick_width(h->W);
+    h->Wt = pick_width(h->W, lpt);
     if (h->Wt < 0) return fail(h, KROTOV_ERR_UNSUPPORTED, "row too wide for the warp path");
-    h->cols.assign((size_t)h->Wt * 32, 0);
-    h->slot_valid.assign((size_t)h->Wt * 32, 0);
+    h->cols.assign((size_t)h->Wt * h->lpt, 0);
+    h->slot_valid.assign((size_t)h->Wt * h->lpt, 0);
     for (int s = 0; s < h->Wt; ++s)
-        for (int i = 0; i < 32; ++i) h->cols[(size_t)s * 32 + i] = i;  // padding: own column, value 0
+        for (int i = 0; i < lpt; ++i) h->cols[(size_t)s * lpt + i] = i;  // padding: own column, value 0
     if (use_dia) {
         // one slot per matrix diagonal; EVERY lane reads x[(i + off) mod 32] so that a warp's LDS.128
         // gather always touches 32 consecutive 16-byte words (bank-conflict free); entries that are not
         // in the pattern (or wrapped around) carry the value 0
         int s = 0;
         for (int off : diags) {
-            for (int i = 0; i < 32; ++i) {
+            for (int i = 0; i < lpt; ++i) {
                 const int j = i + off;
-                h->cols[(size_t)s * 32 + i] = (j + 64) & 31;
-                if (i < d && j >= 0 && j < d && pat[(size_t)i * d + j]) h->slot_valid[(size_t)s * 32 + i] = 1;
+                h->cols[(size_t)s * lpt + i] = ((j % lpt) + lpt) % lpt;
+                if (i < d && j >= 0 && j < d && pat[(size_t)i * d + j]) h->slot_valid[(size_t)s * lpt + i] = 1;
             }
             ++s;
         }
@@ -258,8 +284,8 @@ int build_pattern(krotov_handle h) {
             int s = 0;
             for (int j = 0; j < d; ++j)
                 if (i != j && pat[(size_t)i * d + j]) {
-                    h->cols[(size_t)s * 32 + i] = j;
-                    h->slot_valid[(size_t)s * 32 + i] = 1;
+                    h->cols[(size_t)s * lpt + i] = j;
+                    h->slot_valid[(size_t)s * lpt + i] = 1;
                     ++s;
                 }
         }
@@ -271,23 +297,23 @@ int build_pattern(krotov_handle h) {
 void build_rows(krotov_handle h, int dir, std::vector<cplx> &out) {
     const int d = h->d, L = h->L, Wt = h->Wt;
     const ChebyTables &ct = h->cheb[dir];
-    out.assign((size_t)h->n_gen * (1 + L) * (Wt + 1) * 32, cplx(0, 0));
+    out.assign((size_t)h->n_gen * (1 + L) * (Wt + 1) * h->lpt, cplx(0, 0));
     for (int g = 0; g < h->n_gen; ++g) {
         const double s = 4.0 / ct.Delta[g];
         const double beta = ct.Delta[g] / 2 + ct.E_min[g];
         const cplx f = (dir == KROTOV_FORWARD) ? cplx(0.0, -s) : cplx(0.0, s);  // 2c = -/+ 4i/Delta
         for (int t = 0; t <= L; ++t) {
-            cplx *row = &out[((size_t)g * (1 + L) + t) * (Wt + 1) * 32];
+            cplx *row = &out[((size_t)g * (1 + L) + t) * (Wt + 1) * h->lpt];
             for (int i = 0; i < d; ++i) {
                 for (int sl = 0; sl < Wt; ++sl) {
-                    if (!h->slot_valid[(size_t)sl * 32 + i]) continue;
-                    const int j = h->cols[(size_t)sl * 32 + i];
+                    if (!h->slot_valid[(size_t)sl * h->lpt + i]) continue;
+                    const int j = h->cols[(size_t)sl * h->lpt + i];
                     const cplx v = (dir == KROTOV_FORWARD) ? Hval(h, g, t, i, j) : std::conj(Hval(h, g, t, j, i));
-                    row[(size_t)sl * 32 + i] = f * v;
+                    row[(size_t)sl * h->lpt + i] = f * v;
                 }
                 cplx dv = (dir == KROTOV_FORWARD) ? Hval(h, g, t, i, i) : std::conj(Hval(h, g, t, i, i));
                 if (t == 0) dv -= beta;
-                row[(size_t)Wt * 32 + i] = f * dv;
+                row[(size_t)Wt * h->lpt + i] = f * dv;
             }
         }
     }
@@ -326,8 +352,9 @@ int choose_launch(krotov_handle h) {
     // CTA stays <= 7 trajectory warps; otherwise rows are re-read per use and a warp may own several
     // trajectories.  KROTOV_WPC overrides the warps-per-CTA heuristic (experiments).
     const int N = h->N, sm = h->sm_count;
-    const int cap_preg = 7, cap = 15;
-    const bool preg_possible = kernel_table().count(KernelKey{h->Wt, h->L}) > 0;
+    const int lpt = h->lpt;
+    const int cap_preg = (256 - 32) / lpt, cap = std::min(13, (512 - 32) / lpt);  // groups per CTA (named barriers 3..15)
+    const bool preg_possible = kernel_table().count(KernelKey{h->Wt, h->L, lpt}) > 0;
     // Pair mode: when there are more trajectories than one-per-warp CTAs with register-resident rows can hold
     // (N > 7 per SM) and they come in generator-sharing pairs (ensembles over basis states), one warp runs two
     // of them interleaved and keeps the rows in registers.  Measured on B200: +19 % at N = 2048 against the
@@ -335,7 +362,7 @@ int choose_launch(krotov_handle h) {
     // with two interleaved recursions (13.7 vs 15.3 ms), so the pair kernel is not used there.
     // KROTOV_NO_PAIR=1 disables it, KROTOV_FORCE_PAIR=1 uses it whenever the pairing exists.
     h->pair = false;
-    if (kernel2_table().count(KernelKey{h->Wt, h->L}) > 0 && N % 2 == 0 &&
+    if (lpt == 32 && kernel2_table().count(KernelKey{h->Wt, h->L, 32}) > 0 && N % 2 == 0 &&
         (N > cap_preg * sm || getenv("KROTOV_FORCE_PAIR")) && N / 2 <= cap_preg * sm &&
         !getenv("KROTOV_NO_PAIR") && !getenv("KROTOV_NO_PREG")) {
         bool ok = true;
@@ -348,7 +375,7 @@ int choose_launch(krotov_handle h) {
             return KROTOV_OK;
         }
     }
-    int wpc = (N <= 8) ? N : std::max(std::min(N, 4), (N + sm - 1) / sm);
+    int wpc = (N <= 8 && N <= cap_preg) ? N : std::max(std::min(std::min(N, 4), cap_preg), (N + sm - 1) / sm);
     if (const char *env = getenv("KROTOV_WPC")) wpc = std::max(1, atoi(env));
     h->tpw = 1;
     if (preg_possible && wpc <= cap_preg && (N + wpc - 1) / wpc <= sm && !getenv("KROTOV_NO_PREG")) {
@@ -370,8 +397,8 @@ size_t warp_smem_bytes(const krotov_handle h) {
     if (h->pair)
         return (size_t)h->wpc * (128 + 64) * 16 + (size_t)h->L * h->wpc * 32 * 8 + kr::kMaxCtrl * 8 +
                (size_t)kr::kMaxCtrl * 160 * 8;
-    return (size_t)h->wpc * 2 * 32 * 16 + (size_t)h->wpc * h->tpw * 32 * 16 + (size_t)h->L * h->wpc * 32 * 8 +
-           kr::kMaxCtrl * 8 + (size_t)kr::kMaxCtrl * 160 * 8 + (size_t)h->wpc * 32 * 16;
+    return (size_t)h->wpc * 2 * h->lpt * 16 + (size_t)h->wpc * h->tpw * h->lpt * 16 + (size_t)h->L * h->wpc * h->lpt * 8 +
+           kr::kMaxCtrl * 8 + (size_t)kr::kMaxCtrl * 160 * 8 + (size_t)h->wpc * h->lpt * 16;
 }
 
 int launch_warp(krotov_handle h, int mode) {
@@ -409,14 +436,14 @@ int launch_warp(krotov_handle h, int mode) {
     p.timeout_cycles = 20000000000ll;  // ~10 s
     if (const char *e = getenv("KROTOV_TIMEOUT_CYCLES")) p.timeout_cycles = atoll(e);
 
-    KernelKey key{h->Wt, h->preg ? h->L : 0};
+    KernelKey key{h->Wt, h->preg ? h->L : 0, h->pair ? 32 : h->lpt};
     const auto &table = h->pair ? kernel2_table() : kernel_table();
     auto it = table.find(key);
     if (it == table.end()) return fail(h, KROTOV_ERR_UNSUPPORTED, "no kernel instance for this (W, L)");
     WarpKernel fn = it->second;
     const size_t smem = warp_smem_bytes(h);
     KR_CUDA(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(h->nCTA), block((h->wpc + 1) * 32);
+    dim3 grid(h->nCTA), block(h->wpc * h->lpt + 32);
     void *args[] = {(void *)&p};
     if (h->nCTA > 1 && mode == 1) {
         KR_CUDA(h, cudaLaunchCooperativeKernel((const void *)fn, grid, block, args, smem, h->stream));
@@ -554,11 +581,34 @@ int krotov_create(const krotov_problem *pb, krotov_handle *out) {
     };
 
     int path = pb->force_path;
-    if (path == KROTOV_PATH_WARP && d > 32)
-        return bail(fail(h, KROTOV_ERR_UNSUPPORTED, "warp path needs d <= 32"));
+    if (path == KROTOV_PATH_WARP && d > 128)
+        return bail(fail(h, KROTOV_ERR_UNSUPPORTED, "warp path needs d <= 128"));
     if (path != 0 && path != KROTOV_PATH_WARP && path != KROTOV_PATH_DENSE && path != KROTOV_PATH_SPARSE)
         return bail(fail(h, KROTOV_ERR_ARG, "bad force_path"));
-    if (path != KROTOV_PATH_WARP && d <= 32 && path == 0) path = KROTOV_PATH_WARP;
+    auto fill_dense = [&]() {  // dense host copy of every term (row-major)
+        h->Hdense.assign((size_t)h->n_gen * (1 + L) * d * d, cplx(0, 0));
+        for (int g = 0; g < h->n_gen; ++g)
+            for (int t = 0; t <= L; ++t) {
+                cplx *dst = &h->Hdense[((size_t)g * (1 + L) + t) * d * d];
+                for_each_entry(g, t, [&](int i, int j, cplx v) { dst[(size_t)i * d + j] += v; });
+            }
+    };
+    // persistent one-launch kernel: one row per thread, 32 / 64 / 128 threads per trajectory; needs narrow rows
+    // beyond d = 32 (the generator row lives in registers)
+    h->lpt = d <= 32 ? 32 : (d <= 64 ? 64 : 128);
+    bool pattern_built = false;
+    if ((path == 0 || path == KROTOV_PATH_WARP) && d <= 128) {
+        fill_dense();
+        const int prc = build_pattern(h);
+        if (prc == KROTOV_OK) {
+            path = KROTOV_PATH_WARP;
+            pattern_built = true;
+        } else if (path == KROTOV_PATH_WARP) {
+            return bail(prc);
+        } else {
+            h->err.clear();
+        }
+    }
 
     // d > 32: union sparsity pattern (symmetrised: the backward sweep needs the adjoint; diagonal always present)
     HostSparse hs;
@@ -612,15 +662,7 @@ int krotov_create(const krotov_problem *pb, krotov_handle *out) {
     }
     h->path = path;
 
-    if (path != KROTOV_PATH_SPARSE) {
-        // dense host copy of every term (row-major)
-        h->Hdense.assign((size_t)h->n_gen * (1 + L) * d * d, cplx(0, 0));
-        for (int g = 0; g < h->n_gen; ++g)
-            for (int t = 0; t <= L; ++t) {
-                cplx *dst = &h->Hdense[((size_t)g * (1 + L) + t) * d * d];
-                for_each_entry(g, t, [&](int i, int j, cplx v) { dst[(size_t)i * d + j] += v; });
-            }
-    }
+    if (path != KROTOV_PATH_SPARSE && h->Hdense.empty()) fill_dense();
 
     int rc;
     // ---- buffers common to both paths
@@ -659,15 +701,15 @@ int krotov_create(const krotov_problem *pb, krotov_handle *out) {
                         break;
                     }
     if (path == KROTOV_PATH_WARP) {
-        if ((rc = build_pattern(h))) return bail(rc);
+        if (!pattern_built && (rc = build_pattern(h))) return bail(rc);
         if ((rc = upload(h, h->d_cols, h->cols))) return bail(rc);
         choose_launch(h);
         // padded state arrays [N][32]
         auto pad_states = [&](const double *src, std::vector<cplx> &dst) {
-            dst.assign((size_t)N * 32, cplx(0, 0));
+            dst.assign((size_t)N * h->lpt, cplx(0, 0));
             const cplx *s = reinterpret_cast<const cplx *>(src);
             for (int k = 0; k < N; ++k)
-                for (int i = 0; i < d; ++i) dst[(size_t)k * 32 + i] = s[(size_t)k * d + i];
+                for (int i = 0; i < d; ++i) dst[(size_t)k * h->lpt + i] = s[(size_t)k * d + i];
         };
         std::vector<cplx> tmp;
         pad_states(pb->psi0, tmp);
@@ -676,12 +718,12 @@ int krotov_create(const krotov_problem *pb, krotov_handle *out) {
             pad_states(pb->target, tmp);
             if ((rc = upload(h, h->d_target, tmp))) return bail(rc);
         }
-        const size_t slab = (size_t)N * (N_T + 1) * 32 * 16;
+        const size_t slab = (size_t)N * (N_T + 1) * h->lpt * 16;
         if ((rc = dev_alloc(h, h->d_X, slab))) return bail(rc);
         if (h->store_fw && (rc = dev_alloc(h, h->d_Phi, slab))) return bail(rc);
-        if ((rc = dev_alloc(h, h->d_chiT, (size_t)N * 32 * 16))) return bail(rc);
-        if ((rc = dev_alloc(h, h->d_psif, (size_t)N * 32 * 16))) return bail(rc);
-        cudaMemset(h->d_psif.p, 0, (size_t)N * 32 * 16);
+        if ((rc = dev_alloc(h, h->d_chiT, (size_t)N * h->lpt * 16))) return bail(rc);
+        if ((rc = dev_alloc(h, h->d_psif, (size_t)N * h->lpt * 16))) return bail(rc);
+        cudaMemset(h->d_psif.p, 0, (size_t)N * h->lpt * 16);
         if ((rc = dev_alloc(h, h->d_R, ((size_t)N_T * h->nCTA * L + (size_t)N_T * L) * 8))) return bail(rc);
         if (getenv("KROTOV_PROF")) {
             if ((rc = dev_alloc(h, h->d_prof, (size_t)h->nCTA * 8 * 8))) return bail(rc);
@@ -712,7 +754,7 @@ int krotov_get_info(krotov_handle h, krotov_info *out) {
     out->ell_width = h->Wt;
     out->nnz_union = h->nnz_union;
     out->grid_blocks = h->nCTA;
-    out->block_threads = (h->wpc + 1) * 32;
+    out->block_threads = h->wpc * h->lpt + 32;
     out->m_fw = h->cheb[0].m_max_used;
     out->m_bw = h->cheb[1].m_max_used;
     out->sm_count = h->sm_count;
@@ -833,10 +875,10 @@ int krotov_set_chi(krotov_handle h, const double *chi) {
     cudaSetDevice(h->device);
     const int N = h->N, d = h->d;
     if (h->path == KROTOV_PATH_WARP) {
-        std::vector<cplx> tmp((size_t)N * 32, cplx(0, 0));
+        std::vector<cplx> tmp((size_t)N * h->lpt, cplx(0, 0));
         const cplx *s = reinterpret_cast<const cplx *>(chi);
         for (int k = 0; k < N; ++k)
-            for (int i = 0; i < d; ++i) tmp[(size_t)k * 32 + i] = s[(size_t)k * d + i];
+            for (int i = 0; i < d; ++i) tmp[(size_t)k * h->lpt + i] = s[(size_t)k * d + i];
         KR_CUDA(h, cudaMemcpy(h->d_chiT.p, tmp.data(), tmp.size() * 16, cudaMemcpyHostToDevice));
     } else {
         std::string e;
@@ -919,11 +961,11 @@ int krotov_get_states(krotov_handle h, double *states) {
     cudaSetDevice(h->device);
     const int N = h->N, d = h->d;
     if (h->path == KROTOV_PATH_WARP) {
-        std::vector<cplx> tmp((size_t)N * 32);
+        std::vector<cplx> tmp((size_t)N * h->lpt);
         KR_CUDA(h, cudaMemcpy(tmp.data(), h->d_psif.p, tmp.size() * 16, cudaMemcpyDeviceToHost));
         cplx *o = reinterpret_cast<cplx *>(states);
         for (int k = 0; k < N; ++k)
-            for (int i = 0; i < d; ++i) o[(size_t)k * d + i] = tmp[(size_t)k * 32 + i];
+            for (int i = 0; i < d; ++i) o[(size_t)k * d + i] = tmp[(size_t)k * h->lpt + i];
     } else {
         std::string e;
         if (!kr::dense_get_states(h->dense, states, e)) return fail(h, KROTOV_ERR_CUDA, e);
@@ -946,12 +988,12 @@ int krotov_get_storage(krotov_handle h, int which, int k, int n0, int n1, double
     const int d = h->d;
     if (h->path == KROTOV_PATH_WARP) {
         const DevBuf &b = which == KROTOV_FORWARD ? h->d_Phi : h->d_X;
-        std::vector<cplx> tmp((size_t)(n1 - n0) * 32);
-        const char *src = (const char *)b.p + ((size_t)k * (h->N_T + 1) + n0) * 32 * 16;
+        std::vector<cplx> tmp((size_t)(n1 - n0) * h->lpt);
+        const char *src = (const char *)b.p + ((size_t)k * (h->N_T + 1) + n0) * h->lpt * 16;
         KR_CUDA(h, cudaMemcpy(tmp.data(), src, tmp.size() * 16, cudaMemcpyDeviceToHost));
         cplx *o = reinterpret_cast<cplx *>(out);
         for (int n = 0; n < n1 - n0; ++n)
-            for (int i = 0; i < d; ++i) o[(size_t)n * d + i] = tmp[(size_t)n * 32 + i];
+            for (int i = 0; i < d; ++i) o[(size_t)n * d + i] = tmp[(size_t)n * h->lpt + i];
     } else {
         std::string e;
         if (!kr::dense_get_storage(h->dense, which, k, n0, n1, out, e)) return fail(h, KROTOV_ERR_CUDA, e);

@@ -111,18 +111,28 @@ __device__ __forceinline__ void row_dot(const double2 (&g)[W + 1], const int (&c
     ai += ai1;
 }
 
-template <int W>
+// A trajectory is owned by a group of LPT threads (one generator row per thread): a warp for d <= 32, two or
+// four warps for d <= 64 / 128.  Groups wider than a warp synchronise on their own named barrier.
+template <int LPT>
+__device__ __forceinline__ void grp_sync(const int bar_id) {
+    if (LPT == 32)
+        __syncwarp();
+    else
+        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(LPT) : "memory");
+}
+
+template <int W, int LPT = 32>
 __device__ __forceinline__ void load_row(const double2 *__restrict__ base, double2 (&out)[W + 1], int lane) {
 #pragma unroll
-    for (int s = 0; s <= W; ++s) out[s] = base[s * 32 + lane];
+    for (int s = 0; s <= W; ++s) out[s] = base[s * LPT + lane];
 }
 
 // One Chebyshev step.  v0buf holds psi for all lanes (written + synced by the caller).
-template <int W>
+template <int W, int LPT = 32>
 __device__ __forceinline__ double2 cheby_step(const double2 psi, const double2 (&g)[W + 1], const int (&col)[W],
                                               const double2 *v0buf, double2 *bufA, double2 *bufB,
                                               const double *__restrict__ a, const int m, const double2 phase,
-                                              const int lane) {
+                                              const int lane, const int bar_id = 0) {
     double2 vm2 = psi;
     const double a0 = a[0];
     double outr = a0 * psi.x, outi = a0 * psi.y;
@@ -135,7 +145,7 @@ __device__ __forceinline__ double2 cheby_step(const double2 psi, const double2 (
         outi = fma(a1, vm1.y, outi);
     }
     bufB[lane] = vm1;
-    __syncwarp();
+    grp_sync<LPT>(bar_id);
     double2 *cur = bufB, *nxt = bufA;
     for (int j = 2; j < m; ++j) {
         const double aj = a[j];
@@ -147,7 +157,7 @@ __device__ __forceinline__ double2 cheby_step(const double2 psi, const double2 (
         vm2 = vm1;
         vm1 = make_double2(ar, ai);
         nxt[lane] = vm1;
-        __syncwarp();
+        grp_sync<LPT>(bar_id);
         double2 *t = cur;
         cur = nxt;
         nxt = t;
@@ -175,11 +185,11 @@ __device__ __forceinline__ StepMeta load_meta(const int *dtc, const int *m_tab, 
 
 // Same recursion, but the first term v_1 = G v_0 / 2 was assembled by the caller from products that do not
 // depend on the pulse value (computed while the warp waited for the grid-wide sum).
-template <int W>
+template <int W, int LPT = 32>
 __device__ __forceinline__ double2 cheby_step_from_v1(const double2 psi, const double2 v1, const double2 (&g)[W + 1],
                                                       const int (&col)[W], double2 *bufA, double2 *bufB,
                                                       const double *__restrict__ a, const int m, const double2 phase,
-                                                      const int lane) {
+                                                      const int lane, const int bar_id = 0) {
     double2 vm2 = psi, vm1 = v1;
     double outr = a[0] * psi.x, outi = a[0] * psi.y;
     if (m > 1) {
@@ -188,7 +198,7 @@ __device__ __forceinline__ double2 cheby_step_from_v1(const double2 psi, const d
         outi = fma(a1, vm1.y, outi);
     }
     bufB[lane] = vm1;
-    __syncwarp();
+    grp_sync<LPT>(bar_id);
     double2 *cur = bufB, *nxt = bufA;
     for (int j = 2; j < m; ++j) {
         const double aj = a[j];
@@ -199,7 +209,7 @@ __device__ __forceinline__ double2 cheby_step_from_v1(const double2 psi, const d
         vm2 = vm1;
         vm1 = make_double2(ar, ai);
         nxt[lane] = vm1;
-        __syncwarp();
+        grp_sync<LPT>(bar_id);
         double2 *t = cur;
         cur = nxt;
         nxt = t;
@@ -396,43 +406,46 @@ __device__ __forceinline__ void comm_warp_run(const WarpParams &p, const int L, 
     }
 }
 
-template <int W, int LT /*0 = runtime L, rows reloaded from L1/L2 per use*/, int MAXTHREADS>
+template <int W, int LT /*0 = runtime L, rows reloaded from L1/L2 per use*/, int MAXTHREADS, int LPT = 32>
 __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid_constant__ WarpParams p) {
     constexpr bool PREG = (LT > 0);
     constexpr int NT = PREG ? (1 + LT) : 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
+    // trajectory threads: `warp` = index of the trajectory group in the CTA, `lane` = row within the group;
+    // the communication warp is the last 32 threads of the CTA
+    const bool is_comm = (int)threadIdx.x >= p.wpc * LPT;
+    const int lane = is_comm ? ((int)threadIdx.x - p.wpc * LPT) : ((int)threadIdx.x % LPT);
+    const int warp = (int)threadIdx.x / LPT;
+    const int gbar = 3 + warp;  // named barrier of this group (LPT > 32)
     const int L = PREG ? LT : p.L;
     const int wpc = p.wpc, tpw = p.tpw;
     // smem carve-up
-    double2 *vbuf = reinterpret_cast<double2 *>(smem_raw);        // [wpc][2][32]
-    double2 *psis = vbuf + (size_t)wpc * 2 * 32;                  // [wpc][tpw][32]
-    double *red = reinterpret_cast<double *>(psis + (size_t)wpc * tpw * 32);  // [L][wpc*32]
-    double *eps_s = red + (size_t)L * wpc * 32;                   // [kMaxCtrl]
+    double2 *vbuf = reinterpret_cast<double2 *>(smem_raw);        // [wpc][2][LPT]
+    double2 *psis = vbuf + (size_t)wpc * 2 * LPT;                 // [wpc][tpw][LPT]
+    double *red = reinterpret_cast<double *>(psis + (size_t)wpc * tpw * LPT);  // [L][wpc*LPT]
+    double *eps_s = red + (size_t)L * wpc * LPT;                  // [kMaxCtrl]
     double *gbuf = eps_s + kMaxCtrl;                              // [kMaxCtrl * 160] reducer scratch (CTA 0)
-    double2 *chibufs = reinterpret_cast<double2 *>(gbuf + kMaxCtrl * 160);  // [wpc][32] chi(t_{n+1}) for the precompute
-    const int nthr_all = (wpc + 1) * 32;
+    double2 *chibufs = reinterpret_cast<double2 *>(gbuf + kMaxCtrl * 160);  // [wpc][LPT] chi(t_{n+1}) for the precompute
+    const int nthr_all = wpc * LPT + 32;
     const int N_T = p.N_T;
-    const bool is_comm = (warp == wpc);
 
     if (is_comm) {
-        comm_warp_run(p, L, lane, wpc, nthr_all, red, eps_s, gbuf);
+        comm_warp_run(p, L, lane, wpc * (LPT / 32), nthr_all, red, eps_s, gbuf);
         return;
     }
 
     // -------------------------------------------------------------------- trajectory warps
     const int gw = blockIdx.x * wpc + warp;       // global trajectory-warp index
     const int kbase = gw * tpw;                   // first trajectory of this warp
-    double2 *bufA = vbuf + (size_t)warp * 64;
-    double2 *bufB = bufA + 32;
-    double2 *mypsi = psis + (size_t)warp * tpw * 32;
+    double2 *bufA = vbuf + (size_t)warp * 2 * LPT;
+    double2 *bufB = bufA + LPT;
+    double2 *mypsi = psis + (size_t)warp * tpw * LPT;
 
     int col[W];
 #pragma unroll
-    for (int s = 0; s < W; ++s) col[s] = p.cols[s * 32 + lane];
+    for (int s = 0; s < W; ++s) col[s] = p.cols[s * LPT + lane];
 
-    const size_t rowstride = (size_t)(W + 1) * 32;   // one term
+    const size_t rowstride = (size_t)(W + 1) * LPT;   // one term
     double2 P[NT][W + 1];                            // PREG: per-term rows of this lane's trajectory
     double2 g[W + 1];
 
@@ -447,20 +460,20 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
             const double2 *Pg = p.Pb + (size_t)gi * (1 + L) * rowstride;
             if (PREG) {
 #pragma unroll
-                for (int q = 0; q < NT; ++q) load_row<W>(Pg + q * rowstride, P[q], lane);
+                for (int q = 0; q < NT; ++q) load_row<W, LPT>(Pg + q * rowstride, P[q], lane);
             }
             double2 chi;
             if (p.chiT != nullptr) {
-                chi = p.chiT[(size_t)k * 32 + lane];
+                chi = p.chiT[(size_t)k * LPT + lane];
             } else {
                 const double2 c = p.chi_coef[k];
-                const double2 tg = p.target[(size_t)k * 32 + lane];
+                const double2 tg = p.target[(size_t)k * LPT + lane];
                 chi = make_double2(c.x * tg.x - c.y * tg.y, c.x * tg.y + c.y * tg.x);
             }
-            double2 *Xk = p.X + (size_t)k * (N_T + 1) * 32;
-            Xk[(size_t)N_T * 32 + lane] = chi;
-            mypsi[t * 32 + lane] = chi;
-            __syncwarp();
+            double2 *Xk = p.X + (size_t)k * (N_T + 1) * LPT;
+            Xk[(size_t)N_T * LPT + lane] = chi;
+            mypsi[t * LPT + lane] = chi;
+            grp_sync<LPT>(gbar);
             StepMeta meta = load_meta(p.dtc_b, p.m_b, p.phase_b, p.coef_b, p.ndtc_b, p.mmax_b, gi, N_T - 1);
             double e_cur[kMaxCtrl];
 #pragma unroll
@@ -484,25 +497,25 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
                         }
                     }
                 } else {
-                    load_row<W>(Pg, g, lane);
+                    load_row<W, LPT>(Pg, g, lane);
                     for (int l = 0; l < L; ++l) {
                         const double e = p.eps_old[(size_t)l * N_T + n];  // (runtime index: reload, L1 hit)
                         const double2 *Pl = Pg + (size_t)(l + 1) * rowstride;
 #pragma unroll
                         for (int s = 0; s <= W; ++s) {
-                            const double2 v = Pl[s * 32 + lane];
+                            const double2 v = Pl[s * LPT + lane];
                             g[s].x = fma(e, v.x, g[s].x);
                             g[s].y = fma(e, v.y, g[s].y);
                         }
                     }
                 }
-                chi = cheby_step<W>(chi, g, col, mypsi + t * 32, bufA, bufB, meta.a, meta.m, meta.phase, lane);
+                chi = cheby_step<W, LPT>(chi, g, col, mypsi + t * LPT, bufA, bufB, meta.a, meta.m, meta.phase, lane, gbar);
                 meta = meta_next;
 #pragma unroll
                 for (int l = 0; l < kMaxCtrl; ++l) e_cur[l] = e_next[l];
-                mypsi[t * 32 + lane] = chi;
-                __syncwarp();
-                Xk[(size_t)n * 32 + lane] = chi;
+                mypsi[t * LPT + lane] = chi;
+                grp_sync<LPT>(gbar);
+                Xk[(size_t)n * LPT + lane] = chi;
             }
         }
     }
@@ -514,43 +527,43 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
         const int k = kbase + t;
         double2 v = make_double2(0.0, 0.0);
         if (k < p.N) {
-            v = p.psi0[(size_t)k * 32 + lane];
-            if (p.store_fw) p.Phi[(size_t)k * (N_T + 1) * 32 + lane] = v;
+            v = p.psi0[(size_t)k * LPT + lane];
+            if (p.store_fw) p.Phi[(size_t)k * (N_T + 1) * LPT + lane] = v;
         }
-        mypsi[t * 32 + lane] = v;
+        mypsi[t * LPT + lane] = v;
         if (t == 0) psi_reg = v;
     }
-    __syncwarp();
+    grp_sync<LPT>(gbar);
     const int k0 = kbase;
     const int g0 = (k0 < p.N) ? p.gen_of_traj[k0] : 0;
     if (PREG && k0 < p.N) {
         const double2 *Pg = p.Pf + (size_t)g0 * (1 + L) * rowstride;
 #pragma unroll
-        for (int q = 0; q < NT; ++q) load_row<W>(Pg + q * rowstride, P[q], lane);
+        for (int q = 0; q < NT; ++q) load_row<W, LPT>(Pg + q * rowstride, P[q], lane);
     }
     const double inv_s0 = (k0 < p.N) ? p.inv_s_f[g0] : 0.0;
     StepMeta fmeta = load_meta(p.dtc_f, p.m_f, p.phase_f, p.coef_f, p.ndtc_f, p.mmax_f, g0, 0);
     double2 chi_next = make_double2(0.0, 0.0);
-    if (p.mode == 1 && k0 < p.N) chi_next = p.X[(size_t)k0 * (N_T + 1) * 32 + lane];
+    if (p.mode == 1 && k0 < p.N) chi_next = p.X[(size_t)k0 * (N_T + 1) * LPT + lane];
     // FAST: register-resident rows, one trajectory per warp, Hermitian control terms.  Then
     //   Im<chi|mu_l|psi> = -(1/s) Re <P_l chi|psi>   (P_l = -i s mu_l is anti-Hermitian)
     // so xi_l = P_l chi(t_n) can be formed BEFORE psi(t_n) exists, and the overlap on the critical path is a
     // plain dot product; and the products w_t = P_t psi(t_n) that make up the first Chebyshev term
     // v_1 = (w_0 + sum_l eps_l w_l) / 2 are formed while the warp waits for eps.
     const bool FAST = PREG && tpw == 1 && p.mode == 1 && p.mu_hermitian != 0;
-    double2 *chibuf = chibufs + (size_t)warp * 32;
+    double2 *chibuf = chibufs + (size_t)warp * LPT;
     double2 xi[PREG ? (LT > 0 ? LT : 1) : 1];
     double2 wv[PREG ? NT : 1];
     if (PREG && FAST) {
         chibuf[lane] = chi_next;
-        __syncwarp();
+        grp_sync<LPT>(gbar);
 #pragma unroll
         for (int l = 0; l < NT - 1; ++l) {
             double wr = 0.0, wi = 0.0;
             row_dot<W>(P[l + 1], col, chibuf, chi_next, wr, wi);
             xi[l] = make_double2(wr, wi);
         }
-        __syncwarp();
+        grp_sync<LPT>(gbar);
     }
 
     for (int n = 0; n < N_T; ++n) {
@@ -573,32 +586,32 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
                 if (k >= p.N) break;
                 const int gi = (t == 0) ? g0 : p.gen_of_traj[k];
                 const double inv_s = (t == 0) ? inv_s0 : p.inv_s_f[gi];
-                const double2 psi = (tpw == 1) ? psi_reg : mypsi[t * 32 + lane];
-                const double2 chi = (t == 0) ? chi_next : p.X[((size_t)k * (N_T + 1) + n) * 32 + lane];
+                const double2 psi = (tpw == 1) ? psi_reg : mypsi[t * LPT + lane];
+                const double2 chi = (t == 0) ? chi_next : p.X[((size_t)k * (N_T + 1) + n) * LPT + lane];
                 if (PREG) {
 #pragma unroll
                     for (int l = 0; l < NT - 1; ++l) {
                         double wr = 0.0, wi = 0.0;
-                        row_dot<W>(P[l + 1], col, mypsi + t * 32, psi, wr, wi);
+                        row_dot<W>(P[l + 1], col, mypsi + t * LPT, psi, wr, wi);
                         part[l] = fma(inv_s, fma(chi.x, wr, chi.y * wi), part[l]);
                     }
                 } else {
                     const double2 *Pg = p.Pf + (size_t)gi * (1 + L) * rowstride;
                     for (int l = 0; l < L; ++l) {
-                        load_row<W>(Pg + (size_t)(l + 1) * rowstride, g, lane);
+                        load_row<W, LPT>(Pg + (size_t)(l + 1) * rowstride, g, lane);
                         double wr = 0.0, wi = 0.0;
-                        row_dot<W>(g, col, mypsi + t * 32, psi, wr, wi);
+                        row_dot<W>(g, col, mypsi + t * LPT, psi, wr, wi);
                         part[l] = fma(inv_s, fma(chi.x, wr, chi.y * wi), part[l]);
                     }
                 }
             }
 #pragma unroll
             for (int l = 0; l < (PREG ? LT : kMaxCtrl); ++l)
-                if (l < L) red[(size_t)l * wpc * 32 + warp * 32 + lane] = part[l];
+                if (l < L) red[(size_t)l * wpc * LPT + warp * LPT + lane] = part[l];
             bar_arrive(1, nthr_all);  // barrier A
             const long long w0 = clock64();
             t_overlap += w0 - ts0;
-            if (n + 1 < N_T && k0 < p.N) chi_next = p.X[((size_t)k0 * (N_T + 1) + n + 1) * 32 + lane];
+            if (n + 1 < N_T && k0 < p.N) chi_next = p.X[((size_t)k0 * (N_T + 1) + n + 1) * LPT + lane];
             if (PREG && FAST && k0 < p.N) {
                 // ---- idle window: everything for this and the next step that does not depend on eps_n
 #pragma unroll
@@ -608,14 +621,14 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
                     wv[q] = make_double2(wr, wi);
                 }
                 chibuf[lane] = chi_next;
-                __syncwarp();
+                grp_sync<LPT>(gbar);
 #pragma unroll
                 for (int l = 0; l < NT - 1; ++l) {
                     double wr = 0.0, wi = 0.0;
                     row_dot<W>(P[l + 1], col, chibuf, chi_next, wr, wi);
                     xi[l] = make_double2(wr, wi);
                 }
-                __syncwarp();
+                grp_sync<LPT>(gbar);
             }
             bar_sync(2, nthr_all);    // barrier B: updated pulse value is in eps_s
 #pragma unroll
@@ -651,18 +664,18 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
                 }
             } else {
                 const double2 *Pg = p.Pf + (size_t)gi * (1 + L) * rowstride;
-                load_row<W>(Pg, g, lane);
+                load_row<W, LPT>(Pg, g, lane);
                 for (int l = 0; l < L; ++l) {
                     const double2 *Pl = Pg + (size_t)(l + 1) * rowstride;
 #pragma unroll
                     for (int s = 0; s <= W; ++s) {
-                        const double2 v = Pl[s * 32 + lane];
+                        const double2 v = Pl[s * LPT + lane];
                         g[s].x = fma(eps[l], v.x, g[s].x);
                         g[s].y = fma(eps[l], v.y, g[s].y);
                     }
                 }
             }
-            double2 psi = (tpw == 1) ? psi_reg : mypsi[t * 32 + lane];
+            double2 psi = (tpw == 1) ? psi_reg : mypsi[t * LPT + lane];
             if (PREG && FAST) {
                 double v1r = wv[0].x, v1i = wv[0].y;
 #pragma unroll
@@ -670,19 +683,19 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
                     v1r = fma(eps[l], wv[l + 1].x, v1r);
                     v1i = fma(eps[l], wv[l + 1].y, v1i);
                 }
-                psi = cheby_step_from_v1<W>(psi, make_double2(0.5 * v1r, 0.5 * v1i), g, col, bufA, bufB, sm.a, sm.m,
-                                            sm.phase, lane);
+                psi = cheby_step_from_v1<W, LPT>(psi, make_double2(0.5 * v1r, 0.5 * v1i), g, col, bufA, bufB, sm.a, sm.m,
+                                            sm.phase, lane, gbar);
             } else {
-                psi = cheby_step<W>(psi, g, col, mypsi + t * 32, bufA, bufB, sm.a, sm.m, sm.phase, lane);
+                psi = cheby_step<W, LPT>(psi, g, col, mypsi + t * LPT, bufA, bufB, sm.a, sm.m, sm.phase, lane, gbar);
             }
-            mypsi[t * 32 + lane] = psi;
+            mypsi[t * LPT + lane] = psi;
             if (t == 0) psi_reg = psi;
-            __syncwarp();
+            grp_sync<LPT>(gbar);
             if (p.store_fw) {
                 // mode 1 writes slot n like the reference (sic, src/optimize.jl:367); the plain
                 // forward sweep writes slot n+1 (src/optimize.jl:263)
                 const int slot = (p.mode == 1) ? n : n + 1;
-                p.Phi[((size_t)k * (N_T + 1) + slot) * 32 + lane] = psi;
+                p.Phi[((size_t)k * (N_T + 1) + slot) * LPT + lane] = psi;
             }
         }
         fmeta = fmeta_next;
@@ -704,16 +717,27 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
     for (int t = 0; t < tpw; ++t) {
         const int k = kbase + t;
         if (k >= p.N) break;
-        const double2 psi = mypsi[t * 32 + lane];
-        p.psi_final[(size_t)k * 32 + lane] = psi;
+        const double2 psi = mypsi[t * LPT + lane];
+        p.psi_final[(size_t)k * LPT + lane] = psi;
         double tr = 0.0, ti = 0.0;
         if (p.target != nullptr) {
-            const double2 tg = p.target[(size_t)k * 32 + lane];
+            const double2 tg = p.target[(size_t)k * LPT + lane];
             tr = tg.x * psi.x + tg.y * psi.y;
             ti = tg.x * psi.y - tg.y * psi.x;
         }
         tr = warp_sum_xor(tr);
         ti = warp_sum_xor(ti);
+        if (LPT > 32) {  // combine the group's warps through its (now free) Chebyshev buffer
+            grp_sync<LPT>(gbar);
+            if ((lane & 31) == 0) bufA[lane >> 5] = make_double2(tr, ti);
+            grp_sync<LPT>(gbar);
+            tr = 0.0;
+            ti = 0.0;
+            for (int q = 0; q < LPT / 32; ++q) {
+                tr += bufA[q].x;
+                ti += bufA[q].y;
+            }
+        }
         if (lane == 0) p.tau[k] = make_double2(tr, ti);
     }
 }

@@ -513,7 +513,8 @@ def test_sparse_path_spin_chain_vs_oracle(n_spins, n_traj, functional):
     from oracle import c_oracle as C
 
     w = W.spin_chain(n_spins=n_spins, n_traj=n_traj, functional=functional)
-    got = run_product(w, 2)
+    # (d <= 128 with rows this narrow would go to the persistent kernel by default: force the block path there)
+    got = run_product(w, 2, force_path=3 if w.d <= 128 else 0)
     assert got["info"]["path"] == 3 and got["info"]["ell_width"] <= 2 * n_spins  # diag + (n-1) exchange + n flips
     ref = C.optimize_krotov_c(W.to_oracle(w), 2)
     assert_parity(got, ref["J_T"], ref["pulses"], rtol=1e-10, atol=5e-13)
@@ -521,10 +522,12 @@ def test_sparse_path_spin_chain_vs_oracle(n_spins, n_traj, functional):
 
 def test_sparse_path_equals_dense_path_and_csr_input():
     w = W.spin_chain(n_spins=6, n_traj=12)
-    a = run_product(w, 2)
+    a = run_product(w, 2, force_path=3)
     b = run_product(w, 2, force_path=2)
-    c = run_product(w, 2, csr_generators=True)
-    assert (a["info"]["path"], b["info"]["path"], c["info"]["path"]) == (3, 2, 3)
+    c = run_product(w, 2, force_path=3, csr_generators=True)
+    p1 = run_product(w, 2)  # default for d = 64 with 11 off-diagonals per row: the persistent kernel
+    assert (a["info"]["path"], b["info"]["path"], c["info"]["path"], p1["info"]["path"]) == (3, 2, 3, 1)
+    assert np.abs(a["pulses"] - p1["pulses"]).max() < 1e-12
     assert np.abs(np.array(a["J_T"]) - np.array(b["J_T"])).max() < 1e-13
     assert np.abs(a["pulses"] - b["pulses"]).max() < 1e-12
     assert np.array_equal(a["pulses"], c["pulses"])
@@ -536,7 +539,7 @@ def test_sparse_path_non_hermitian():
     w = W.spin_chain(n_spins=6, n_traj=4, n_grid=21)
     rng = np.random.default_rng(8)
     w.H0 = [w.H0[0] - 0.02j * np.diag(rng.uniform(0, 1, 64))]
-    got = run_product(w, 2)
+    got = run_product(w, 2, force_path=3)
     assert got["info"]["path"] == 3
     ref = O.optimize_krotov(W.to_oracle(w), 2)
     assert_parity(got, ref["J_T"], ref["pulses"], ref["g_a_int"])
@@ -552,7 +555,7 @@ def test_scipy_sparse_operators_are_not_densified():
     ws = W.spin_chain(n_spins=6, n_traj=5, n_grid=21)
     ws.H0 = [sp.csr_matrix(ws.H0[0])]
     ws.Hc = [[sp.csr_matrix(m) for m in ws.Hc[0]]]
-    b = run_product(ws, 2)
+    b = run_product(ws, 2, force_path=3)
     assert b["info"]["path"] == 3
     assert np.abs(np.array(a["J_T"]) - np.array(b["J_T"])).max() < 1e-13 and np.abs(a["pulses"] - b["pulses"]).max() < 1e-12
     # d = 1024 > 512: the spectral envelope comes from Lanczos (eigsh); compare with the exact-diagonalisation run
@@ -564,3 +567,38 @@ def test_scipy_sparse_operators_are_not_densified():
     e = run_product(w10s, 1)
     assert e["info"]["path"] == 3
     assert np.abs(np.array(c["J_T"]) - np.array(e["J_T"])).max() < 1e-9  # different (but valid) Chebyshev envelopes
+
+
+# ---- 32 < d <= 128 with narrow rows: the persistent kernel with 64 / 128 threads per trajectory ----------------
+@pytest.mark.parametrize("levels,n_grid,iters", [(6, 201, 2), (8, 101, 2), (10, 61, 2), (11, 41, 1)])
+def test_wide_groups_two_transmons_more_levels(levels, n_grid, iters):
+    """Two coupled transmons with 6, 8, 10, 11 levels each: d = 36, 64, 100, 121.  Same one-launch kernel as C3,
+    with two or four warps per trajectory."""
+    from oracle import c_oracle as C
+
+    w = W.c3_two_transmon(n_grid=n_grid, levels=levels, T=40.0 * (n_grid - 1) / 200)
+    got = run_product(w, iters)
+    assert got["info"]["path"] == 1 and got["info"]["launches_last"] <= 2
+    ref = C.optimize_krotov_c(W.to_oracle(w), iters)
+    assert_parity(got, ref["J_T"], ref["pulses"], rtol=1e-10, atol=5e-13)
+
+
+def test_wide_groups_ensemble_multi_cta_and_storage():
+    w = W.c4_ensemble(n_samples=6, n_grid=81, levels=7, T=16.0)  # d = 49, 24 trajectories
+    from oracle import c_oracle as C
+
+    seen = {}
+
+    def cb(wrk, it, *a):
+        if it == 1:
+            seen["X"] = wrk.bw_storage[5]
+            seen["psi"] = np.array(wrk.result.states[5])
+
+    got = run_product(w, 2)
+    assert got["info"]["path"] == 1 and got["info"]["grid_blocks"] > 1
+    ref = C.optimize_krotov_c(W.to_oracle(w), 2)
+    assert_parity(got, ref["J_T"], ref["pulses"], rtol=1e-10, atol=5e-13)
+    b = run_product(w, 2, force_path=3)  # the same problem through the SpMM block path
+    assert b["info"]["path"] == 3 and np.abs(got["pulses"] - b["pulses"]).max() < 1e-12
+    K.optimize(to_problem(w, iter_stop=1, callback=cb), method=K.Krotov)
+    assert seen["X"].shape == (49, 81) and abs(np.linalg.norm(seen["psi"]) - 1.0) < 1e-10
