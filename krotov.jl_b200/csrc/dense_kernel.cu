@@ -319,13 +319,6 @@ __global__ void chi_from_coef_kernel(double2 *CHI, const double2 *TGT, const dou
     }
 }
 
-__global__ void scale_kernel(double2 *dst, const double2 *src, double2 f, size_t total) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const double2 s = src[i];
-        dst[i] = make_double2(f.x * s.x - f.y * s.y, f.x * s.y + f.y * s.x);
-    }
-}
-
 // ============================================================================ sparse generators, d > 32
 // The same block propagator for SPARSE generators (spin chains, coupled-oscillator networks ...): the Chebyshev
 // term is an SpMM over the state block.  ELL storage with one shared pattern: slot 0 of every row is the
@@ -376,12 +369,41 @@ __global__ void __launch_bounds__(SP_WARPS * 32) spmm_kernel(const __grid_consta
 #pragma unroll
     for (int q = 0; q < SP_ROWS_PER_WARP; ++q) cr[q] = ci[q] = cr1[q] = ci1[q] = 0.0;
     const size_t cbase = (size_t)e.col0 + (cvalid ? c : 0);
-    for (int s = 0; s < p.W; ++s) {
+    // The gathers are latency-bound (ncu: long-scoreboard stalls dominate), so 4 slots x 4 rows = 16 independent
+    // state-row loads are put in flight before the first FMA.
+    constexpr int SU = 4;
+    int s = 0;
+    for (; s + SU <= p.W; s += SU) {
+        int jj[SU][SP_ROWS_PER_WARP];
+        double2 gg[SU][SP_ROWS_PER_WARP], xx[SU][SP_ROWS_PER_WARP];
+#pragma unroll
+        for (int u = 0; u < SU; ++u)
+#pragma unroll
+            for (int q = 0; q < SP_ROWS_PER_WARP; ++q) {
+                const size_t slot = (size_t)(row0 + q) * p.W + s + u;
+                jj[u][q] = p.cols[slot];  // warp-uniform
+                gg[u][q] = p.Gv[slot];    // warp-uniform
+            }
+#pragma unroll
+        for (int u = 0; u < SU; ++u)
+#pragma unroll
+            for (int q = 0; q < SP_ROWS_PER_WARP; ++q) xx[u][q] = e.B[(size_t)jj[u][q] * e.ld + cbase];
+#pragma unroll
+        for (int u = 0; u < SU; ++u)
+#pragma unroll
+            for (int q = 0; q < SP_ROWS_PER_WARP; ++q) {
+                cr[q] = fma(gg[u][q].x, xx[u][q].x, cr[q]);
+                cr1[q] = fma(-gg[u][q].y, xx[u][q].y, cr1[q]);
+                ci[q] = fma(gg[u][q].x, xx[u][q].y, ci[q]);
+                ci1[q] = fma(gg[u][q].y, xx[u][q].x, ci1[q]);
+            }
+    }
+    for (; s < p.W; ++s) {
 #pragma unroll
         for (int q = 0; q < SP_ROWS_PER_WARP; ++q) {
             const size_t slot = (size_t)(row0 + q) * p.W + s;
-            const int j = p.cols[slot];          // warp-uniform
-            const double2 g = p.Gv[slot];        // warp-uniform
+            const int j = p.cols[slot];
+            const double2 g = p.Gv[slot];
             const double2 x = e.B[(size_t)j * e.ld + cbase];
             cr[q] = fma(g.x, x.x, cr[q]);
             cr1[q] = fma(-g.y, x.y, cr1[q]);

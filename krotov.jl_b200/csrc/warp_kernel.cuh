@@ -1,4 +1,5 @@
-// Persistent warp-per-trajectory Krotov kernel for small Hilbert spaces (d <= 32), sm_100a.
+// Persistent Krotov kernel for small Hilbert spaces, sm_100a: one warp per trajectory for d <= 32, two or four
+// warps per trajectory (template parameter LPT = 64 / 128) for d <= 128 with narrow generator rows.
 //
 // One launch = one whole Krotov iteration (src/optimize.jl:279-371 of the reference):
 //   backward sweep   chi_k(t_n) = exp(+i H_k^dagger dt) chi_k(t_{n+1})   stored for every n in HBM
@@ -6,8 +7,8 @@
 //                    -> pulse update -> Chebyshev step of every psi_k with the new pulse value
 // with NO host round trip and NO kernel boundary between time steps.
 //
-// Mapping.  One warp owns one trajectory (or `tpw` of them), lane i owns component i of the
-// state and row i of the generator.  The generator is kept as "G = 2c (H - beta)" rows in
+// Mapping.  One group of LPT threads (a warp for d <= 32) owns one trajectory (or `tpw` of them), thread i owns
+// component i of the state and row i of the generator.  The generator is kept as "G = 2c (H - beta)" rows in
 // registers: W off-diagonal slots + the diagonal, rebuilt once per time step from the per-term
 // rows P_t = 2c (H_t - beta delta_t0):  G = P_0 + sum_l eps_l[n] P_l.  The Chebyshev recursion
 //   v_1 = G v_0 / 2,   v_j = G v_{j-1} + v_{j-2},   psi' = e^{-i beta dt} sum_j a_j v_j
