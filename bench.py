@@ -275,14 +275,26 @@ def main():
                          "frac": ach_gbs / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
                          "kernel": "krotov_warp_kernel", "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "the fused kernel keeps all Chebyshev vectors on chip, so HBM traffic is only the chi "
-                                 "trajectory; the binding resources are the FP64 pipe and the shared-memory crossbar "
-                                 "(see roofline_fp64 and DESIGN.md)"},
+                                 "trajectory; the binding resource is the shared-memory crossbar (see roofline_smem "
+                                 "and DESIGN.md 4.1)"},
+            # the resource that actually binds this kernel: the shared-memory crossbar (128 B/clk/SM).  One
+            # Chebyshev term moves (W+1) warp-wide 512-byte accesses per trajectory (W LDS.128 gathers + 1 STS.128).
+            "roofline_smem": (lambda b: {"achieved": b / (ms_launch * 1e-3) / 1e9, "unit": "GB/s",
+                                         "peak": 128.0 * info["sm_count"] * (marks["clocks"]["sm_max_mhz"] or 1965.0) * 1e6 / 1e9,
+                                         "frac": b / (ms_launch * 1e-3) / (128.0 * info["sm_count"] * (marks["clocks"]["sm_max_mhz"] or 1965.0) * 1e6),
+                                         "bytes_per_launch": b,
+                                         "peak_source": "128 B/clk/SM (B300_MICROARCH.md) x SMs x max SM clock; tools/chain_bench.cu "
+                                                        "reaches 92 % of it with this kernel's inner loop (profiles/r1_chain_bench.txt)",
+                                         "note": "algorithmic: N x N_T x (m_fw + m_bw - 2) terms x (W+1) x 512 B; the backward sweep "
+                                                 "alone runs at ~80 % of this roof, the forward sweep idles ~half of every time "
+                                                 "step in the grid-wide exchange (DESIGN.md 4.1)"})(
+                float(n_loc) * N_T * (marks["m_fw"] + marks["m_bw"] - 2) * (info["ell_width"] + 1) * 512.0),
             "roofline_fp64": {"achieved_tflops": flops / (ms_launch * 1e-3) / 1e12, "flops_per_launch": flops,
                               "peak_tflops": 34.2, "peak_source": "self-measured DFMA peak on this pool's B200 "
                               "(tools/microbench.cu, profiles/r1_microbench_fp64.txt; DMMA: 37.1)",
                               "frac": flops / (ms_launch * 1e-3) / 1e12 / 34.2,
-                              "bound": "latency (dependent STS->LDS->DFMA chain per Chebyshev term at 1.75 warps per SM "
-                                       "sub-partition, plus one grid-wide exchange per time step)"},
+                              "bound": "not the FP64 pipe: shared-memory crossbar (roofline_smem) in the sweeps, exchange "
+                                       "latency between the time steps of the forward sweep"},
         }
         if world == 1 and not args.no_cpu_baseline:
             try:

@@ -23,6 +23,7 @@
 #include "dense_kernel.cuh"
 #include "warp_kernel.cuh"
 #include "warp2_kernel.cuh"
+#include "tiny_kernel.cuh"
 
 using cplx = std::complex<double>;
 
@@ -91,11 +92,12 @@ struct krotov_handle_s {
     bool pair = false;  // two trajectories of one generator per warp (warp2_kernel.cuh)
     bool mu_hermitian = false;
     int lpt = 32;  // threads (= padded rows) per trajectory on the warp path: 32, 64 or 128
+    bool tiny = false;  // d <= 4, N <= 32, L <= 2: one thread per trajectory, everything in registers (tiny_kernel.cuh)
     std::vector<int> cols;  // [Wt][lpt]
     std::vector<char> slot_valid;  // [Wt][32] slot holds a real matrix entry (i, cols[s][i])
     int wpc = 1, tpw = 1, nCTA = 1;
     DevBuf d_cols, d_Pf, d_Pb, d_inv_s, d_gen, d_dt, d_alpha, d_eps_old, d_eps_new, d_ga, d_X, d_Phi, d_psi0,
-        d_target, d_chiT, d_chicoef, d_psif, d_tau, d_R, d_err, d_weight, d_prof;
+        d_target, d_chiT, d_chicoef, d_psif, d_tau, d_R, d_err, d_weight, d_prof, d_Tf, d_Tb;
     DevBuf d_mbox[2];
     ChebyTables cheb[2];
     bool chiT_valid = false, chicoef_valid = false, swept = false;
@@ -137,6 +139,13 @@ int fail(krotov_handle h, int code, const std::string &msg) {
 int dev_alloc(krotov_handle h, DevBuf &b, size_t bytes) {
     if (bytes == 0) bytes = 16;
     if (b.p != nullptr && b.bytes >= bytes) return KROTOV_OK;  // reuse: cudaFree/cudaMalloc cost up to 100 ms
+    // small tables (Chebyshev coefficients, ...) grow by a few entries when a spectral range widens: give them
+    // headroom so that a re-derived polynomial never re-allocates in the middle of an optimisation
+    if (bytes < (1u << 20)) {
+        size_t cap = 4096;
+        while (cap < 2 * bytes) cap <<= 1;
+        bytes = cap;
+    }
     b.release();
     cudaError_t e = cudaMalloc(&b.p, bytes);
     if (e != cudaSuccess) {
@@ -319,6 +328,34 @@ void build_rows(krotov_handle h, int dir, std::vector<cplx> &out) {
     }
 }
 
+// dense prepared terms of one direction for the tiny kernel: [g][1+L][d*d] row-major, same numbers as build_rows
+void build_dense_terms(krotov_handle h, int dir, std::vector<cplx> &out) {
+    const int d = h->d, L = h->L;
+    const ChebyTables &ct = h->cheb[dir];
+    out.assign((size_t)h->n_gen * (1 + L) * d * d, cplx(0, 0));
+    for (int g = 0; g < h->n_gen; ++g) {
+        const double s = 4.0 / ct.Delta[g];
+        const double beta = ct.Delta[g] / 2 + ct.E_min[g];
+        const cplx f = (dir == KROTOV_FORWARD) ? cplx(0.0, -s) : cplx(0.0, s);
+        for (int t = 0; t <= L; ++t)
+            for (int i = 0; i < d; ++i)
+                for (int j = 0; j < d; ++j) {
+                    cplx v = (dir == KROTOV_FORWARD) ? Hval(h, g, t, i, j) : std::conj(Hval(h, g, t, j, i));
+                    if (t == 0 && i == j) v -= beta;
+                    out[(((size_t)g * (1 + L) + t) * d + i) * d + j] = f * v;
+                }
+    }
+}
+
+using TinyKernel = void (*)(const kr::TinyParams);
+TinyKernel tiny_kernel_for(int d, int L) {
+#define KR_TINY(D, LT) \
+    if (d == D && L == LT) return (TinyKernel)kr::krotov_tiny_kernel<D, LT, ((1 + LT) * D * D <= 12)>
+    KR_TINY(2, 1); KR_TINY(2, 2); KR_TINY(3, 1); KR_TINY(3, 2); KR_TINY(4, 1); KR_TINY(4, 2);
+#undef KR_TINY
+    return nullptr;
+}
+
 __global__ void chi_coef_kernel(int functional, int N, int N_global, const double2 *tau, const double *w,
                                 double2 *coef) {
     // one warp; fixed summation order
@@ -436,6 +473,23 @@ int launch_warp(krotov_handle h, int mode) {
     p.timeout_cycles = 20000000000ll;  // ~10 s
     if (const char *e = getenv("KROTOV_TIMEOUT_CYCLES")) p.timeout_cycles = atoll(e);
 
+    if (h->tiny && h->world == 1) {
+        kr::TinyParams tp;
+        tp.w = p;
+        tp.Tf = (const double2 *)h->d_Tf.p;
+        tp.Tb = (const double2 *)h->d_Tb.p;
+        const int te = (1 + h->L) * h->d * h->d;
+        const size_t term_bytes = te <= 12 ? 0 : (size_t)te * 32 * 16;
+        const size_t coef_bytes = ((size_t)p.ndtc_f * p.mmax_f + (size_t)p.ndtc_b * p.mmax_b) * 32 * 8;
+        tp.coef_in_smem = (term_bytes + coef_bytes <= 160 * 1024) ? 1 : 0;
+        const size_t smem = term_bytes + (tp.coef_in_smem ? coef_bytes : 0) + 16;
+        TinyKernel fn = tiny_kernel_for(h->d, h->L);
+        KR_CUDA(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        void *args[] = {(void *)&tp};
+        KR_CUDA(h, cudaLaunchKernel((const void *)fn, dim3(1), dim3(32), args, smem, h->stream));
+        h->launches_last += 1;
+        return KROTOV_OK;
+    }
     KernelKey key{h->Wt, h->preg ? h->L : 0, h->pair ? 32 : h->lpt};
     const auto &table = h->pair ? kernel2_table() : kernel_table();
     auto it = table.find(key);
@@ -481,7 +535,7 @@ int krotov_destroy(krotov_handle h) {
         if (h->peer_opened[r])
             for (int par = 0; par < 2; ++par)
                 if (h->peer_mbox[par][r]) cudaIpcCloseMemHandle(h->peer_mbox[par][r]);
-    DevBuf *bufs[] = {&h->d_cols, &h->d_Pf, &h->d_Pb, &h->d_inv_s, &h->d_gen, &h->d_dt, &h->d_alpha,
+    DevBuf *bufs[] = {&h->d_Tf, &h->d_Tb, &h->d_cols, &h->d_Pf, &h->d_Pb, &h->d_inv_s, &h->d_gen, &h->d_dt, &h->d_alpha,
                       &h->d_eps_old, &h->d_eps_new, &h->d_ga, &h->d_X, &h->d_Phi, &h->d_psi0, &h->d_target,
                       &h->d_chiT, &h->d_chicoef, &h->d_psif, &h->d_tau, &h->d_R, &h->d_err, &h->d_weight, &h->d_prof,
                       &h->d_mbox[0], &h->d_mbox[1]};
@@ -704,6 +758,7 @@ int krotov_create(const krotov_problem *pb, krotov_handle *out) {
         if (!pattern_built && (rc = build_pattern(h))) return bail(rc);
         if ((rc = upload(h, h->d_cols, h->cols))) return bail(rc);
         choose_launch(h);
+        h->tiny = d >= 2 && d <= 4 && N <= 32 && tiny_kernel_for(d, L) != nullptr && !getenv("KROTOV_NO_TINY");
         // padded state arrays [N][32]
         auto pad_states = [&](const double *src, std::vector<cplx> &dst) {
             dst.assign((size_t)N * h->lpt, cplx(0, 0));
@@ -755,6 +810,10 @@ int krotov_get_info(krotov_handle h, krotov_info *out) {
     out->nnz_union = h->nnz_union;
     out->grid_blocks = h->nCTA;
     out->block_threads = h->wpc * h->lpt + 32;
+    if (h->tiny && h->world == 1) {
+        out->grid_blocks = 1;
+        out->block_threads = 32;
+    }
     out->m_fw = h->cheb[0].m_max_used;
     out->m_bw = h->cheb[1].m_max_used;
     out->sm_count = h->sm_count;
@@ -822,6 +881,10 @@ int krotov_set_cheby(krotov_handle h, int direction, int n_dt_class, const int32
             std::vector<double> inv_s(h->n_gen);
             for (int g = 0; g < h->n_gen; ++g) inv_s[g] = Delta[g] / 4.0;
             if ((rc = upload(h, h->d_inv_s, inv_s))) return rc;
+        }
+        if (h->tiny) {
+            build_dense_terms(h, direction, rows);
+            if ((rc = upload(h, direction == KROTOV_FORWARD ? h->d_Tf : h->d_Tb, rows))) return rc;
         }
         tr.lap("rows uploaded");
     } else {

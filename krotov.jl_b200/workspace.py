@@ -318,14 +318,21 @@ class KrotovWrk:
         if comm is not None and world > 1:
             comm.connect(self.engine)
         # ---- Chebyshev settings of both directions (init_prop: un-widened ranges of the guess pulses)
+        adj = lambda m: m.conj().T.tocsr() if hasattr(m, "tocsr") else m.conj().T  # noqa: E731
+        same = lambda a, b: (abs(a - b).max() == 0) if hasattr(a, "tocsr") else np.array_equal(a, b)  # noqa: E731
+        terms = list(self._H0) + [h for row in self._Hc for h in row if h is not None]
+        # Hermitian generators: both directions propagate with the same matrices, so they share their
+        # spectral envelopes (see ChebyDirection)
+        shared = {} if all(same(m, adj(m)) for m in terms) else None
+
         def settings(pk, backward):
-            adj = lambda m: m.conj().T.tocsr() if hasattr(m, "tocsr") else m.conj().T  # noqa: E731
             H0s = [adj(h) for h in self._H0] if backward else self._H0
             Hcs = [[None if h is None else adj(h) for h in row] for row in self._Hc] if backward else self._Hc
             return ChebyDirection(
                 H0s, Hcs, tlist, backward, self.pulses0,
                 limit=pk.get("cheby_coeffs_limit", 1e-12), specrange_buffer=pk.get("specrange_buffer", 0.01),
-                specrange_method=pk.get("specrange_method", "auto"), E_min=pk.get("E_min"), E_max=pk.get("E_max"))
+                specrange_method=pk.get("specrange_method", "auto"), E_min=pk.get("E_min"), E_max=pk.get("E_max"),
+                envelope_cache=shared if self._shared_envelope_ok(pk) else None)
 
         self.fw_settings = settings(self.fw_prop_kwargs[0], False)
         self.bw_settings = settings(self.bw_prop_kwargs[0], True)
@@ -333,6 +340,12 @@ class KrotovWrk:
         self.bw_settings.push(self.engine, B.BACKWARD)
         self._weight = weight
         self._target = target
+
+    def _shared_envelope_ok(self, pk):
+        """The shared cache is keyed by control ranges only, so both directions must also agree on how the
+        envelope is computed."""
+        other = self.bw_prop_kwargs[0] if pk is self.fw_prop_kwargs[0] else self.fw_prop_kwargs[0]
+        return all(pk.get(k) == other.get(k) for k in ("specrange_method", "E_min", "E_max"))
 
     def _fetch_states(self):
         local = self.engine.states()

@@ -602,3 +602,63 @@ def test_wide_groups_ensemble_multi_cta_and_storage():
     assert b["info"]["path"] == 3 and np.abs(got["pulses"] - b["pulses"]).max() < 1e-12
     K.optimize(to_problem(w, iter_stop=1, callback=cb), method=K.Krotov)
     assert seen["X"].shape == (49, 81) and abs(np.linalg.norm(seen["psi"]) - 1.0) < 1e-10
+
+
+# ---- register-resident kernel for tiny Hilbert spaces (d <= 4, N <= 32, L <= 2) -------------------------------
+@pytest.mark.parametrize("d,n_traj,L,functional,n_grid", [(2, 1, 1, "sm", 41), (2, 5, 2, "ss", 7), (3, 2, 1, "re", 33),
+                                                         (3, 32, 2, "sm", 12), (4, 7, 1, "ss", 25), (4, 17, 2, "sm", 6)])
+def test_tiny_kernel_vs_oracle_and_warp_kernel(d, n_traj, L, functional, n_grid, monkeypatch):
+    """One thread per trajectory: against the oracle, and against the warp kernel on the same problem."""
+    from oracle import krotov_oracle as O
+
+    w = W.dummy_dense(d=d, n_traj=n_traj, n_controls=L, functional=functional, n_grid=n_grid, seed=7 * d + L)
+    w.update_shape = lambda t: 1.0
+    got = run_product(w, 3)
+    assert got["info"]["block_threads"] == 32 and got["info"]["grid_blocks"] == 1  # the tiny kernel ran
+    ref = O.optimize_krotov(W.to_oracle(w), 3)
+    assert_parity(got, ref["J_T"], ref["pulses"], ref["g_a_int"])
+    monkeypatch.setenv("KROTOV_NO_TINY", "1")
+    other = run_product(w, 3)
+    assert other["info"]["block_threads"] > 32
+    assert np.abs(np.array(got["J_T"]) - np.array(other["J_T"])).max() < 1e-13
+    assert np.abs(got["pulses"] - other["pulses"]).max() < 1e-12
+
+
+def test_tiny_kernel_nonuniform_grid_storage_and_host_chi(monkeypatch):
+    """dt classes, forward/backward storage read-back and a user-supplied chi through the tiny kernel."""
+    from oracle import krotov_oracle as O
+
+    w = W.dummy_dense(d=3, n_traj=2, n_controls=1, n_grid=41, seed=9, functional="sm")
+    w.tlist = np.concatenate([np.linspace(0, 2, 21)[:-1], np.linspace(2, 5, 21)])
+    ref = O.optimize_krotov(W.to_oracle(w), 2)
+    got = run_product(w, 2)
+    assert got["info"]["block_threads"] == 32
+    assert_parity(got, ref["J_T"], ref["pulses"], ref["g_a_int"])
+
+    def storages():
+        seen = {}
+
+        def cb(wrk, it, *a):
+            if it == 1:
+                seen["X"] = np.array(wrk.bw_storage[1])
+                seen["Phi"] = np.array(wrk.fw_storage[0])
+                seen["psi"] = np.array(wrk.fw_propagators[0].state)
+
+        K.optimize(to_problem(w, iter_stop=1, callback=cb, store_fw_states=True), method=K.Krotov)
+        return seen
+
+    a = storages()
+    assert np.abs(a["Phi"][:, 39] - a["psi"]).max() < 1e-15  # slot n holds the state after step n (sic, :367)
+    monkeypatch.setenv("KROTOV_NO_TINY", "1")
+    b = storages()
+    monkeypatch.delenv("KROTOV_NO_TINY")
+    assert np.abs(a["X"] - b["X"]).max() < 1e-13 and np.abs(a["Phi"] - b["Phi"]).max() < 1e-13
+
+    def my_chi(states, trajectories, tau=None):
+        n = len(trajectories)
+        s = sum(t.weight * x for t, x in zip(trajectories, tau))
+        return [(t.weight / n**2) * s * t.target_state for t in trajectories]
+
+    c = run_product(w, 2, chi=my_chi)
+    assert c["info"]["block_threads"] == 32
+    assert np.abs(np.array(got["J_T"]) - np.array(c["J_T"])).max() < 1e-14
