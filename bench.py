@@ -217,8 +217,8 @@ def main():
             marks["t1"] = time.perf_counter()
             marks["clocks"] = sampler.stop()
         marks["J_T"] = wrk.result.J_T
-        marks["m_fw"] = max(len(c[0]) for c in wrk.fw_settings.coeffs)
-        marks["m_bw"] = max(len(c[0]) for c in wrk.bw_settings.coeffs)
+        marks["m_fw"] = int(wrk.fw_settings.coeff_count.max())
+        marks["m_bw"] = int(wrk.bw_settings.coeff_count.max())
         marks["shard"] = wrk._shard
 
     problem = to_problem(w, iter_stop=warmup + steps, callback=cb, device=local_rank)

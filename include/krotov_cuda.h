@@ -196,6 +196,14 @@ int krotov_get_profile(krotov_handle h, int cta, int64_t *out);
 int krotov_comm_export(krotov_handle h, void *desc /* KROTOV_COMM_DESC_BYTES */);
 int krotov_comm_connect(krotov_handle h, int rank, int world, const void *descs /* [world][DESC_BYTES] */);
 
+/* ---- host utility -----------------------------------------------------------------------
+ * Smallest and largest eigenvalue of n_mat complex Hermitian d x d matrices (cplx[n_mat][d][d]; the Hermitian
+ * part is taken, so row- and column-major callers agree), spread over n_threads host threads (0 = all cores).
+ * Pure host code.  It is the arithmetic behind the spectral envelope that `reinit_prop!` re-derives
+ * (QuantumPropagators `specrange(...; method=:diag)`, reached from src/optimize.jl:251,306,324 through the range
+ * hook :238-244) for every ensemble member at once; a Julia caller may keep using `eigvals`. */
+int krotov_hermitian_extremes(int n_mat, int d, const double *mats, double *e_min, double *e_max, int n_threads);
+
 #ifdef __cplusplus
 }
 #endif

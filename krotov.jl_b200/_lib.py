@@ -25,6 +25,7 @@ EXPORTS = [
     "krotov_abi_version", "krotov_create", "krotov_destroy", "krotov_last_error", "krotov_get_info",
     "krotov_set_cheby", "krotov_forward", "krotov_set_chi", "krotov_set_chi_coeffs", "krotov_iterate",
     "krotov_get_states", "krotov_get_tau", "krotov_get_storage", "krotov_get_profile", "krotov_comm_export", "krotov_comm_connect",
+    "krotov_hermitian_extremes",
 ]
 
 
@@ -89,9 +90,25 @@ def lib():
     L.krotov_get_profile.argtypes = [vp, i32, vp]
     L.krotov_comm_export.argtypes = [vp, vp]
     L.krotov_comm_connect.argtypes = [vp, i32, i32, vp]
+    L.krotov_hermitian_extremes.argtypes = [i32, i32, vp, vp, vp, i32]
     for name in EXPORTS:
         if name not in ("krotov_last_error",):
             getattr(L, name).restype = i32
     L.krotov_last_error.restype = C.c_char_p
     _lib = L
     return L
+
+
+def hermitian_extremes(stack, n_threads=0):
+    """``(e_min, e_max)`` of every matrix of a stack of complex Hermitian matrices through the library's threaded
+    host solver (``krotov_hermitian_extremes``)."""
+    import numpy as np
+
+    a = np.ascontiguousarray(stack, np.complex128)
+    n, d = a.shape[0], a.shape[-1]
+    lo, hi = np.empty(n, np.float64), np.empty(n, np.float64)
+    rc = lib().krotov_hermitian_extremes(n, d, a.ctypes.data_as(C.c_void_p), lo.ctypes.data_as(C.c_void_p),
+                                         hi.ctypes.data_as(C.c_void_p), int(n_threads))
+    if rc != KROTOV_OK:
+        raise KrotovCudaError(rc, "krotov_hermitian_extremes: bad argument")
+    return lo, hi

@@ -27,12 +27,13 @@ def cheby_coeffs(Delta, dt, limit=1e-12):
     return np.asarray(out, np.float64)
 
 
-def cheby_coeffs_many(Deltas, dt, limit=1e-12):
-    """`cheby_coeffs` for many spectral radii at once (one vectorised Bessel call); every number is what
-    the scalar function returns (same ufunc, evaluated elementwise)."""
+def cheby_coeffs_table(Deltas, dt, limit=1e-12):
+    """`cheby_coeffs` for many spectral radii at once (one vectorised Bessel call) as a zero-padded table
+    ``(a[n_gen, m_max], m[n_gen])``; every number is what the scalar function returns (same ufunc, evaluated
+    elementwise)."""
     Deltas = np.asarray(Deltas, np.float64)
     alpha = np.abs(0.5 * Deltas * dt)
-    nmax = int(np.max(alpha)) + 64
+    nmax = int(np.max(alpha)) + 24  # enough for limit = 1e-12 at small alpha; doubled below when it is not
     while True:
         n = np.arange(nmax)
         a = jv(n[None, :], alpha[:, None])
@@ -41,8 +42,16 @@ def cheby_coeffs_many(Deltas, dt, limit=1e-12):
         stop = (np.abs(a[:, :-1]) <= limit) & (n[None, 1:] > alpha[:, None])
         if stop.any(axis=1).all():
             m = stop.argmax(axis=1) + 1
-            return [a[g, : m[g]].copy() for g in range(len(Deltas))]
+            a = a[:, : int(m.max())].copy()
+            a[np.arange(a.shape[1])[None, :] >= m[:, None]] = 0.0
+            return a, m.astype(np.int32)
         nmax *= 2
+
+
+def cheby_coeffs_many(Deltas, dt, limit=1e-12):
+    """List form of `cheby_coeffs_table`: one coefficient vector per spectral radius."""
+    a, m = cheby_coeffs_table(Deltas, dt, limit)
+    return [a[g, : m[g]].copy() for g in range(len(m))]
 
 
 def specrange(G, method="auto"):
@@ -78,6 +87,9 @@ def specrange(G, method="auto"):
         pad = 0.05 * (hi - lo)
         return float(lo - pad), float(hi + pad)
     raise ValueError(f"unknown specrange method {method!r}")
+
+
+_NATIVE_MIN_BATCH = 32  # matrices per envelope from which the library's threaded solver replaces NumPy's
 
 
 def _batched(solver, stack, workers=8):
@@ -132,6 +144,8 @@ class ChebyDirection:
             d = self._H0s.shape[1]
             self._Hcs = [np.stack([np.zeros((d, d), np.complex128) if row[l] is None else
                                    np.asarray(row[l], np.complex128) for row in Hc]) for l in range(len(pulses))]
+            # Hermitian terms and real amplitudes: every evaluated generator is Hermitian (checked once, not per event)
+            self._herm = all(np.array_equal(a, a.conj().transpose(0, 2, 1)) for a in [self._H0s] + self._Hcs)
         self._classify_steps()
         self._derive()
 
@@ -161,13 +175,22 @@ class ChebyDirection:
             for l in range(len(hi)):
                 G_hi = G_hi + hi[l] * self._Hcs[l]
                 G_lo = G_lo + lo[l] * self._Hcs[l]
-            herm = np.array_equal(G_hi, G_hi.conj().transpose(0, 2, 1)) and np.array_equal(
-                G_lo, G_lo.conj().transpose(0, 2, 1))
-            solver = np.linalg.eigvalsh if herm else (lambda a: np.linalg.eigvals(a).real)
-            ev = _batched(solver, np.concatenate([G_hi, G_lo]))
-            ev_hi, ev_lo = ev[:n_gen], ev[n_gen:]
-            e_min = np.minimum(ev_hi.min(axis=1), ev_lo.min(axis=1))
-            e_max = np.maximum(ev_hi.max(axis=1), ev_lo.max(axis=1))
+            herm = self._herm or (np.array_equal(G_hi, G_hi.conj().transpose(0, 2, 1)) and np.array_equal(
+                G_lo, G_lo.conj().transpose(0, 2, 1)))
+            if herm and 2 * n_gen >= _NATIVE_MIN_BATCH and G_hi.shape[-1] <= 64:
+                # ensembles: the library's threaded host solver (extreme eigenvalues only); agrees with LAPACK to
+                # a few ulp of the matrix norm, far below what the Chebyshev expansion resolves
+                from ._lib import hermitian_extremes
+
+                lo_ev, hi_ev = hermitian_extremes(np.concatenate([G_hi, G_lo]))
+                e_min = np.minimum(lo_ev[:n_gen], lo_ev[n_gen:])
+                e_max = np.maximum(hi_ev[:n_gen], hi_ev[n_gen:])
+            else:
+                solver = np.linalg.eigvalsh if herm else (lambda a: np.linalg.eigvals(a).real)
+                ev = _batched(solver, np.concatenate([G_hi, G_lo]))
+                ev_hi, ev_lo = ev[:n_gen], ev[n_gen:]
+                e_min = np.minimum(ev_hi.min(axis=1), ev_lo.min(axis=1))
+                e_max = np.maximum(ev_hi.max(axis=1), ev_lo.max(axis=1))
         else:
             e_min, e_max = np.empty(n_gen), np.empty(n_gen)
             for g in range(n_gen):
@@ -215,8 +238,21 @@ class ChebyDirection:
         for (_, rep) in classes:
             if rep not in reps:
                 reps.append(rep)
-        per_rep = {rep: cheby_coeffs_many(self.Delta, rep, self.limit) for rep in reps}
-        self.coeffs = [[per_rep[rep][g] for (_, rep) in classes] for g in range(len(self.H0))]
+        per_rep = {rep: cheby_coeffs_table(self.Delta, rep, self.limit) for rep in reps}
+        n_gen = len(self.H0)
+        m_max = max(int(a.shape[1]) for a, _ in per_rep.values())
+        self.coeff_table = np.zeros((n_gen, len(classes), m_max), np.float64)  # [g][class][j], zero-padded
+        self.coeff_count = np.zeros((n_gen, len(classes)), np.int32)
+        for c, (_, rep) in enumerate(classes):
+            a, m = per_rep[rep]
+            self.coeff_table[:, c, : a.shape[1]] = a
+            self.coeff_count[:, c] = m
+
+    @property
+    def coeffs(self):
+        """``coeffs[g][class]``: the coefficient vector of generator g for a dt class."""
+        return [[self.coeff_table[g, c, : self.coeff_count[g, c]] for c in range(self.coeff_table.shape[1])]
+                for g in range(self.coeff_table.shape[0])]
 
     # -- reinit_prop! ------------------------------------------------------------------------
     def reinit(self, pulses, transform=transform_control_ranges):
@@ -237,4 +273,5 @@ class ChebyDirection:
         return need
 
     def push(self, engine, direction):
-        engine.set_cheby(direction, self.dt_class_of_step, self.dt_of_class, self.E_min, self.Delta, self.coeffs)
+        engine.set_cheby(direction, self.dt_class_of_step, self.dt_of_class, self.E_min, self.Delta,
+                         self.coeff_count, self.coeff_table)

@@ -118,15 +118,12 @@ class KrotovCuda:
         return {k: getattr(i, k) for k, _ in B.Info._fields_ if not k.startswith("reserved")}
 
     # -- propagator settings --------------------------------------------------------------
-    def set_cheby(self, direction, dt_class_of_step, dt_of_class, E_min, Delta, coeffs):
-        """coeffs: list over generators of list over dt classes of 1-D coefficient arrays."""
+    def set_cheby(self, direction, dt_class_of_step, dt_of_class, E_min, Delta, m, tab):
+        """m: (n_gen, n_dt_class) coefficient counts; tab: (n_gen, n_dt_class, m_max) zero-padded coefficients."""
         n_gen, ndtc = self.n_gen, len(dt_of_class)
-        m = np.array([[len(coeffs[g][c]) for c in range(ndtc)] for g in range(n_gen)], np.int32)
-        m_max = int(m.max())
-        tab = np.zeros((n_gen, ndtc, m_max), np.float64)
-        for g in range(n_gen):
-            for c in range(ndtc):
-                tab[g, c, : m[g, c]] = coeffs[g][c]
+        m = np.ascontiguousarray(m, np.int32).reshape(n_gen, ndtc)
+        tab = np.ascontiguousarray(tab, np.float64).reshape(n_gen, ndtc, -1)
+        m_max = int(tab.shape[2])
         dtc = np.ascontiguousarray(dt_class_of_step, np.int32)
         dts = np.ascontiguousarray(dt_of_class, np.float64)
         Emin = np.ascontiguousarray(E_min, np.float64).reshape(n_gen)

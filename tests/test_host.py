@@ -226,3 +226,37 @@ def test_gloo_world2_plumbing():
     assert res[0][3] == res[1][3] == list(map(float, range(32)))
     assert res[0][4] == res[1][4] == [0, 1]
     assert res[0][5] == res[1][5]
+
+
+def test_hermitian_extremes_matches_lapack():
+    """krotov_hermitian_extremes (threaded Householder + Sturm multi-section) against numpy's eigvalsh: the
+    spectral envelopes of an ensemble differ from LAPACK's by a few ulp of the matrix norm at most."""
+    from krotov_jl_b200._lib import hermitian_extremes
+
+    rng = np.random.default_rng(3)
+    for d in (1, 2, 3, 7, 25, 32, 48):
+        A = rng.normal(size=(40, d, d)) + 1j * rng.normal(size=(40, d, d))
+        A = A + A.conj().transpose(0, 2, 1)
+        A[0] = np.diag(np.arange(d)).astype(complex)  # already diagonal
+        A[1] = np.eye(d)  # fully degenerate
+        A[2] = 0.0
+        if d >= 3:
+            A[3] = np.diag(np.ones(d)) + 1e-9 * (np.eye(d, k=1) + np.eye(d, k=-1))  # near-degenerate
+        ev = np.linalg.eigvalsh(A)
+        lo, hi = hermitian_extremes(A)
+        lo1, hi1 = hermitian_extremes(A, n_threads=1)
+        assert np.array_equal(lo, lo1) and np.array_equal(hi, hi1)  # independent of the thread count
+        nrm = np.abs(ev).max(axis=1)
+        assert np.all(np.abs(lo - ev[:, 0]) <= 8e-15 * nrm + 1e-300)
+        assert np.all(np.abs(hi - ev[:, -1]) <= 8e-15 * nrm + 1e-300)
+    # the ensemble path of ChebyDirection uses it and agrees with the per-matrix LAPACK path
+    w = W.c4_ensemble(n_samples=20, n_grid=21)
+    p = W.to_oracle(w)
+    pulses = [q.copy() for q in p.pulses]
+    many = K.cheby.ChebyDirection(p.H0, p.Hc, p.tlist, False, pulses)
+    for g in (0, 7, 19):
+        one = K.cheby.ChebyDirection([p.H0[g]], [p.Hc[g]], p.tlist, False, pulses)
+        assert abs(many.Delta[g] - one.Delta[0]) <= 1e-14 * one.Delta[0]
+        assert abs(many.E_min[g] - one.E_min[0]) <= 1e-14 * one.Delta[0]
+        assert len(many.coeffs[g][0]) == len(one.coeffs[0][0])
+        assert np.abs(many.coeffs[g][0] - one.coeffs[0][0]).max() < 1e-12  # alpha ~ 200 on this coarse grid
