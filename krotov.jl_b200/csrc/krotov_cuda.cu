@@ -97,7 +97,7 @@ struct krotov_handle_s {
     std::vector<char> slot_valid;  // [Wt][32] slot holds a real matrix entry (i, cols[s][i])
     int wpc = 1, tpw = 1, nCTA = 1;
     DevBuf d_cols, d_Pf, d_Pb, d_inv_s, d_gen, d_dt, d_alpha, d_eps_old, d_eps_new, d_ga, d_X, d_Phi, d_psi0,
-        d_target, d_chiT, d_chicoef, d_psif, d_tau, d_R, d_err, d_weight, d_prof, d_Tf, d_Tb;
+        d_target, d_chiT, d_chicoef, d_psif, d_tau, d_R, d_err, d_weight, d_prof, d_Tf, d_Tb, d_acc;
     DevBuf d_mbox[2];
     ChebyTables cheb[2];
     bool chiT_valid = false, chicoef_valid = false, swept = false;
@@ -465,6 +465,7 @@ int launch_warp(krotov_handle h, int mode) {
     p.psi_final = (double2 *)h->d_psif.p; p.tau = (double2 *)h->d_tau.p;
     p.R = (double *)h->d_R.p;
     p.E = (double *)h->d_R.p + (size_t)h->N_T * h->nCTA * h->L;
+    p.acc = (h->world == 1 && h->nCTA > 1 && h->nCTA < 256 && !getenv("KROTOV_NO_ATOMIC_SUM")) ? (unsigned long long *)h->d_acc.p : nullptr;
     p.rank = h->rank; p.world = h->world;
     const int par = (int)(h->iter_count & 1);
     for (int r = 0; r < h->world && r < kr::kMaxRanks; ++r) p.mbox[r] = h->peer_mbox[par][r];
@@ -535,7 +536,7 @@ int krotov_destroy(krotov_handle h) {
         if (h->peer_opened[r])
             for (int par = 0; par < 2; ++par)
                 if (h->peer_mbox[par][r]) cudaIpcCloseMemHandle(h->peer_mbox[par][r]);
-    DevBuf *bufs[] = {&h->d_Tf, &h->d_Tb, &h->d_cols, &h->d_Pf, &h->d_Pb, &h->d_inv_s, &h->d_gen, &h->d_dt, &h->d_alpha,
+    DevBuf *bufs[] = {&h->d_acc, &h->d_Tf, &h->d_Tb, &h->d_cols, &h->d_Pf, &h->d_Pb, &h->d_inv_s, &h->d_gen, &h->d_dt, &h->d_alpha,
                       &h->d_eps_old, &h->d_eps_new, &h->d_ga, &h->d_X, &h->d_Phi, &h->d_psi0, &h->d_target,
                       &h->d_chiT, &h->d_chicoef, &h->d_psif, &h->d_tau, &h->d_R, &h->d_err, &h->d_weight, &h->d_prof,
                       &h->d_mbox[0], &h->d_mbox[1]};
@@ -780,6 +781,7 @@ int krotov_create(const krotov_problem *pb, krotov_handle *out) {
         if ((rc = dev_alloc(h, h->d_psif, (size_t)N * h->lpt * 16))) return bail(rc);
         cudaMemset(h->d_psif.p, 0, (size_t)N * h->lpt * 16);
         if ((rc = dev_alloc(h, h->d_R, ((size_t)N_T * h->nCTA * L + (size_t)N_T * L) * 8))) return bail(rc);
+        if ((rc = dev_alloc(h, h->d_acc, (size_t)N_T * L * kr::kFixLimbs * 8))) return bail(rc);
         if (getenv("KROTOV_PROF")) {
             if ((rc = dev_alloc(h, h->d_prof, (size_t)h->nCTA * 8 * 8))) return bail(rc);
             cudaMemset(h->d_prof.p, 0, h->d_prof.bytes);
@@ -990,6 +992,7 @@ int krotov_iterate(krotov_handle h, const double *guess_pulses, double *new_puls
     }
     if (h->path == KROTOV_PATH_WARP) {
         if (h->nCTA > 1 || h->world > 1) KR_CUDA(h, cudaMemsetAsync(h->d_R.p, 0xFF, h->d_R.bytes, h->stream));
+        if (h->nCTA > 1 && h->world == 1) KR_CUDA(h, cudaMemsetAsync(h->d_acc.p, 0, h->d_acc.bytes, h->stream));
         if ((rc = launch_warp(h, 1))) return rc;
     } else {
         std::string e;

@@ -71,6 +71,7 @@ struct WarpParams {
     double2 *tau;              // [N]
     double *R;                 // [N_T][L][nCTA] CTA partial sums, sentinel-filled before every iteration
     double *E;                 // [N_T][L] grid-wide sums broadcast by the reducer (CTA 0), sentinel-filled
+    unsigned long long *acc;   // [N_T][L][3] fixed-point accumulators of the one-hop grid sum (zero-filled), or nullptr
     int rank, world;
     double *mbox[kMaxRanks];   // mailbox of every rank (this iteration's parity): [N_T][world][L]
     int *err_flag;
@@ -314,6 +315,108 @@ __device__ __forceinline__ void poll_broadcast(const double *E, const int L, con
     for (int l = 0; l < kMaxCtrl; ++l) tot[l] = __shfl_sync(0xffffffffu, v, l < L ? l : 0);
 }
 
+
+// ---- exact one-hop grid sum through L2 integer atomics ---------------------------------------------------------
+// Every CTA converts its partial sum to a 120-bit fixed-point number (unit 2^-88, bias 2^119), splits it into three
+// 40-bit limbs and adds limb j into word j of the step's accumulator with ONE red.add.u64 each; the same add bumps an
+// arrival count in the word's top byte (and a "does not fit" count in the byte below).  Integer addition is
+// associative, so the total is the EXACT sum of the CTA partials whatever the arrival order -- bitwise reproducible
+// like the fixed-order gather, but in one L2 hop instead of two (CTA -> reducer -> everybody): every CTA polls the
+// L*3 words (one 64-byte line for two controls) until each carries all arrivals, then rounds the sum to double once.
+// tools/atomic_allreduce.cu: 1529 cycles per round at 148 CTAs against 2356 for gather + broadcast.
+// A partial that is not finite or not below 2^31 marks the step and all CTAs redo it with the gather protocol.
+constexpr int kFixFrac = 88, kFixLimbBits = 40, kFixLimbs = 3, kFixBiasBit = 119;
+
+__device__ __forceinline__ bool fix_from_double(const double x, unsigned __int128 &biased) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(fabs(x));
+    const int ebits = (int)(bits >> 52);
+    if (ebits >= 1023 + 31) return false;  // |x| >= 2^31, Inf or NaN
+    const unsigned long long mant = (bits & 0xFFFFFFFFFFFFFull) | (ebits ? (1ull << 52) : 0ull);
+    const int shift = (ebits ? ebits : 1) - 1075 + kFixFrac;  // |x| = mant * 2^(shift - kFixFrac)
+    unsigned __int128 mag = 0;
+    if (shift >= 0)
+        mag = (unsigned __int128)mant << shift;
+    else if (shift > -64)
+        mag = mant >> (-shift);  // below 2^-88: truncated
+    const unsigned __int128 bias = (unsigned __int128)1 << kFixBiasBit;
+    biased = (x < 0.0) ? bias - mag : bias + mag;
+    return true;
+}
+
+// sum of `n` biased numbers (limb sums w0, w1, w2 without their count bytes) -> double, rounded to nearest once
+__device__ __forceinline__ double fix_to_double(const unsigned long long w0, const unsigned long long w1,
+                                                const unsigned long long w2, const int n) {
+    const unsigned long long mask = (1ull << 48) - 1;
+    unsigned __int128 sum = (unsigned __int128)(w0 & mask) + ((unsigned __int128)(w1 & mask) << kFixLimbBits) +
+                            ((unsigned __int128)(w2 & mask) << (2 * kFixLimbBits));
+    const unsigned __int128 bias = (unsigned __int128)n << kFixBiasBit;
+    const bool neg = sum < bias;
+    const unsigned __int128 mag = neg ? bias - sum : sum - bias;
+    const unsigned long long hi = (unsigned long long)(mag >> 64), lo = (unsigned long long)mag;
+    double d;
+    if (hi == 0) {
+        d = __ull2double_rn(lo);
+    } else {
+        const int sh = 64 - __clzll((long long)hi);  // 1..64 bits live in `hi`
+        unsigned long long top = (sh == 64) ? hi : ((hi << (64 - sh)) | (lo >> sh));
+        const unsigned long long lost = (sh == 64) ? lo : (lo << (64 - sh));
+        if (lost) top |= 1ull;  // sticky bit, 11 places below the rounding position
+        d = scalbn(__ull2double_rn(top), sh);
+    }
+    d = scalbn(d, -kFixFrac);
+    return neg ? -d : d;
+}
+
+__device__ __forceinline__ void red_add_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Returns true when tot[] holds the grid-wide sums; false when some CTA's partial did not fit (all CTAs see the same
+// verdict) and the step has to be redone with the gather protocol.
+__device__ __forceinline__ bool atomic_grid_sum(unsigned long long *An, const int nCTA, const int L, const int lane,
+                                                double (&tot)[kMaxCtrl], int *err_flag, const long long timeout) {
+    const int nw = L * kFixLimbs;           // words of this step; lane q < nw owns word q = (control q / 3, limb q % 3)
+    const int myl = lane / kFixLimbs, myj = lane - myl * kFixLimbs;
+    double mine = 0.0;
+#pragma unroll
+    for (int l = 0; l < kMaxCtrl; ++l)
+        if (l == myl) mine = tot[l];
+    if (lane < nw) {
+        unsigned __int128 v;
+        const bool ok = fix_from_double(mine, v);
+        unsigned long long add = 1ull << 56;  // one arrival
+        if (ok)
+            add += (unsigned long long)(v >> (myj * kFixLimbBits)) & ((1ull << kFixLimbBits) - 1);
+        else
+            add += 1ull << 48;  // one partial that does not fit
+        red_add_u64(An + lane, add);
+    }
+    const long long t0 = clock64();
+    int spins = 0;
+    unsigned long long w = 0;
+    for (;;) {
+        if (lane < nw) w = ld_poll_u64<false>(reinterpret_cast<const double *>(An + lane));
+        const bool pending = lane < nw && (int)(w >> 56) != nCTA;
+        if (!__any_sync(0xffffffffu, pending)) break;
+        if ((++spins & 63) == 0) {
+            if (clock64() - t0 > timeout || *(volatile int *)err_flag) {
+                atomicExch(err_flag, 1);
+                break;
+            }
+        }
+    }
+    const bool misfit = lane < nw && ((w >> 48) & 0xFF) != 0;
+    if (__any_sync(0xffffffffu, misfit)) return false;
+    // lane l < L rebuilds control l from its three words
+    const int src = (lane < L ? lane : 0) * kFixLimbs;
+    const unsigned long long w0 = __shfl_sync(0xffffffffu, w, src), w1 = __shfl_sync(0xffffffffu, w, src + 1),
+                             w2 = __shfl_sync(0xffffffffu, w, src + 2);
+    const double du = fix_to_double(w0, w1, w2, nCTA);
+#pragma unroll
+    for (int l = 0; l < kMaxCtrl; ++l) tot[l] = __shfl_sync(0xffffffffu, du, l < L ? l : 0);
+    return true;
+}
+
 // The communication warp of a CTA (shared by both kernel variants): per time step it waits for the CTA's
 // per-lane partial overlaps (named barrier 1), reduces them in a fixed order, runs the grid / rank exchange,
 // applies the pulse update (src/optimize.jl:351-358) and releases the trajectory warps (named barrier 2).
@@ -348,7 +451,10 @@ __device__ __forceinline__ void comm_warp_run(const WarpParams &p, const int L, 
                 if (l < L) tot[l] += __shfl_xor_sync(0xffffffffu, tot[l], o);
         }
         const long long c2 = clock64();
-        if (p.nCTA > 1 || p.world > 1) {
+        bool summed = false;
+        if (p.acc != nullptr && p.nCTA > 1 && p.world == 1)
+            summed = atomic_grid_sum(p.acc + (size_t)n * L * kFixLimbs, p.nCTA, L, lane, tot, p.err_flag, p.timeout_cycles);
+        if (!summed && (p.nCTA > 1 || p.world > 1)) {
             // R[n][l][cta]: CTA partials;  E[n][l]: the grid-wide (and rank-wide) sums, written by the reducer
             double *Rn = p.R + (size_t)n * L * p.nCTA;
             double *En = p.E + (size_t)n * L;
