@@ -116,7 +116,9 @@ typedef struct {
     double ms_last;          /* device time of the last forward/iterate call (CUDA events on the launch stream) */
     double ms_last_backward; /* DENSE path: share of ms_last spent in the backward sweep, else 0 */
     int64_t hbm_bytes_state; /* bytes of the chi trajectory in HBM                   */
-    int64_t reserved[6];
+    int64_t fallback_steps;  /* WARP path: time steps of the last krotov_iterate whose grid sum left the fixed-point
+                                range of the one-hop all-reduce and was redone with the gather protocol */
+    int64_t reserved[5];
 } krotov_info;
 
 /* ---- lifetime ------------------------------------------------------------------------ */

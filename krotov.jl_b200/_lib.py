@@ -54,7 +54,8 @@ class Info(C.Structure):
         ("grid_blocks", C.c_int32), ("block_threads", C.c_int32), ("m_fw", C.c_int32), ("m_bw", C.c_int32),
         ("sm_count", C.c_int32), ("reserved_i", C.c_int32),
         ("launches_total", C.c_int64), ("launches_last", C.c_int64), ("ms_last", C.c_double),
-        ("ms_last_backward", C.c_double), ("hbm_bytes_state", C.c_int64), ("reserved", C.c_int64 * 6),
+        ("ms_last_backward", C.c_double), ("hbm_bytes_state", C.c_int64), ("fallback_steps", C.c_int64),
+        ("reserved", C.c_int64 * 5),
     ]
 
 

@@ -112,7 +112,7 @@ struct krotov_handle_s {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sm_count = 0;
-    long long launches_total = 0, launches_last = 0;
+    long long launches_total = 0, launches_last = 0, fallback_steps = 0;
     double ms_last = 0.0, ms_last_bw = 0.0;
     std::string err;
 };
@@ -510,8 +510,11 @@ int launch_warp(krotov_handle h, int mode) {
 }
 
 int check_err_flag(krotov_handle h) {
-    int flag = 0;
-    KR_CUDA(h, cudaMemcpy(&flag, h->d_err.p, sizeof(int), cudaMemcpyDeviceToHost));
+    int flags[2] = {0, 0};  // [0] exchange timed out, [1] time steps redone with the gather protocol
+    KR_CUDA(h, cudaMemcpy(flags, h->d_err.p, sizeof(flags), cudaMemcpyDeviceToHost));
+    const int flag = flags[0];
+    h->fallback_steps = flags[1];
+    if (flags[1]) cudaMemset((int *)h->d_err.p + 1, 0, sizeof(int));
     if (flag) {
         cudaMemset(h->d_err.p, 0, sizeof(int));
         return fail(h, KROTOV_ERR_TIMEOUT, "in-kernel exchange timed out waiting for a partial sum");
@@ -824,6 +827,7 @@ int krotov_get_info(krotov_handle h, krotov_info *out) {
     out->ms_last = h->ms_last;
     out->ms_last_backward = h->ms_last_bw;
     out->hbm_bytes_state = (int64_t)h->d_X.bytes;
+    out->fallback_steps = h->fallback_steps;
     if (h->dense) kr::dense_info(h->dense, out);
     return KROTOV_OK;
 }

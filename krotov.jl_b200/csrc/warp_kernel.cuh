@@ -452,8 +452,10 @@ __device__ __forceinline__ void comm_warp_run(const WarpParams &p, const int L, 
         }
         const long long c2 = clock64();
         bool summed = false;
-        if (p.acc != nullptr && p.nCTA > 1 && p.world == 1)
+        if (p.acc != nullptr && p.nCTA > 1 && p.world == 1) {
             summed = atomic_grid_sum(p.acc + (size_t)n * L * kFixLimbs, p.nCTA, L, lane, tot, p.err_flag, p.timeout_cycles);
+            if (!summed && blockIdx.x == 0 && lane == 0) atomicAdd(p.err_flag + 1, 1);  // krotov_info.fallback_steps
+        }
         if (!summed && (p.nCTA > 1 || p.world > 1)) {
             // R[n][l][cta]: CTA partials;  E[n][l]: the grid-wide (and rank-wide) sums, written by the reducer
             double *Rn = p.R + (size_t)n * L * p.nCTA;

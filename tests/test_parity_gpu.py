@@ -662,3 +662,43 @@ def test_tiny_kernel_nonuniform_grid_storage_and_host_chi(monkeypatch):
     c = run_product(w, 2, chi=my_chi)
     assert c["info"]["block_threads"] == 32
     assert np.abs(np.array(got["J_T"]) - np.array(c["J_T"])).max() < 1e-14
+
+
+# ---- exact one-hop grid sum (L2 integer atomics) vs the gather + broadcast protocol -----------------------------
+def test_atomic_grid_sum_equals_gather_protocol(monkeypatch):
+    """Multi-CTA ensemble: the fixed-point all-reduce (exact sum of the CTA partials, rounded once) against the
+    fixed-order floating-point gather; and run-to-run bitwise reproducibility of the atomic path."""
+    w = W.c4_ensemble(n_samples=12, n_grid=101)
+    a = run_product(w, 3)
+    a2 = run_product(w, 3)
+    assert a["info"]["grid_blocks"] > 1
+    assert np.array_equal(a["pulses"], a2["pulses"]) and a["J_T"] == a2["J_T"]  # integer sums: order-independent
+    monkeypatch.setenv("KROTOV_NO_ATOMIC_SUM", "1")
+    b = run_product(w, 3)
+    assert np.abs(np.array(a["J_T"]) - np.array(b["J_T"])).max() < 1e-13
+    assert np.abs(a["pulses"] - b["pulses"]).max() < 1e-13
+
+
+def test_atomic_grid_sum_falls_back_when_a_partial_does_not_fit(monkeypatch):
+    """Overlap sums beyond the fixed-point range (|partial| >= 2^31, here through a user chi scaled by 1e13 and a
+    matching lambda_a) make every CTA redo the step with the gather protocol: bitwise the same as never using atomics."""
+    w = W.c4_ensemble(n_samples=6, n_grid=41)
+    scale = 1e13
+
+    def big_chi(states, trajectories, tau=None):
+        n = len(trajectories)
+        s = sum(t.weight * x for t, x in zip(trajectories, tau))
+        return [scale * (t.weight / n**2) * s * t.target_state for t in trajectories]
+
+    lam = scale * w.lambda_a
+    a = run_product(w, 2, chi=big_chi, lambda_a=lam)
+    assert a["info"]["grid_blocks"] > 1
+    assert a["info"]["fallback_steps"] > w.N_T // 2  # most steps left the range (a few zero crossings may fit)
+    monkeypatch.setenv("KROTOV_NO_ATOMIC_SUM", "1")
+    b = run_product(w, 2, chi=big_chi, lambda_a=lam)
+    assert b["info"]["fallback_steps"] == 0
+    assert np.abs(a["pulses"] - b["pulses"]).max() < 1e-13 and np.abs(np.array(a["J_T"]) - np.array(b["J_T"])).max() < 1e-13
+    monkeypatch.delenv("KROTOV_NO_ATOMIC_SUM")
+    ref = run_product(w, 2)  # the same optimisation in natural units
+    assert ref["info"]["fallback_steps"] == 0
+    assert np.abs(np.array(a["J_T"]) - np.array(ref["J_T"])).max() < 1e-12

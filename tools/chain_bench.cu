@@ -7,6 +7,7 @@
 // VAR 2: exchange through SHFL (rotation patterns only) instead of shared memory
 // VAR 3: as 0 with the loop over terms fully unrolled for m = 17 (compile-time trip count)
 // VAR 4: two independent recursions interleaved in one warp (shared rows)
+// VAR 5: as 0, but the gathers of the next term are issued right after the store, before the bookkeeping
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
@@ -163,6 +164,42 @@ __global__ void __launch_bounds__(512, 1) chain(double *out, long long *cyc, int
                 vm1 = make_double2(ar, ai);
             }
             psi = make_double2(phase.x * outr - phase.y * outi, phase.x * outi + phase.y * outr);
+        } else if (VAR == 5) {
+            bufC[lane] = psi;
+            __syncwarp();
+            double2 x[W];
+#pragma unroll
+            for (int s = 0; s < W; ++s) x[s] = bufC[col[s]];
+            double2 vm2 = psi;
+            double outr = coef[0] * psi.x, outi = coef[0] * psi.y;
+            double ar = 0.0, ai = 0.0;
+            row_dot_v<4>(g, x, psi, ar, ai);
+            double2 vm1 = make_double2(0.5 * ar, 0.5 * ai);
+            bufB[lane] = vm1;
+            __syncwarp();
+#pragma unroll
+            for (int s = 0; s < W; ++s) x[s] = bufB[col[s]];
+            outr = fma(coef[1], vm1.x, outr);
+            outi = fma(coef[1], vm1.y, outi);
+            double2 *cur = bufB, *nxt = bufA;
+            for (int j = 2; j < m; ++j) {
+                const double aj = coef[j];
+                ar = vm2.x;
+                ai = vm2.y;
+                row_dot_v<4>(g, x, vm1, ar, ai);
+                nxt[lane] = make_double2(ar, ai);
+                __syncwarp();
+#pragma unroll
+                for (int s = 0; s < W; ++s) x[s] = nxt[col[s]];
+                outr = fma(aj, ar, outr);
+                outi = fma(aj, ai, outi);
+                vm2 = vm1;
+                vm1 = make_double2(ar, ai);
+                double2 *t = cur;
+                cur = nxt;
+                nxt = t;
+            }
+            psi = make_double2(phase.x * outr - phase.y * outi, phase.x * outi + phase.y * outr);
         } else if (VAR == 4) {
             // two recursions, one instruction stream
             double2 vm2a = psi, vm2b = psi2, vm1a = psi, vm1b = psi2;
@@ -237,7 +274,7 @@ void run(const char *name, int wpc, double *out, long long *cyc, const double *c
     mean /= blocks * wpc;
     const double terms = (double)steps * (m - 1);
     printf("%-44s wpc=%2d: %7.1f cycles/term (max %7.1f), %6.1f per trajectory-term per SMSP, %.3f ms\n", name, wpc,
-           mean / terms, mx / terms, mean / terms / trajs_per_warp / (wpc / 4.0) , ms);
+           mean / terms, mx / terms, mean / terms / trajs_per_warp / (wpc < 4 ? 1.0 : wpc / 4.0) , ms);
 }
 
 int main() {
@@ -249,12 +286,13 @@ int main() {
     double hc[64];
     for (int i = 0; i < 64; ++i) hc[i] = 1.0 / (1 + i * i);
     cudaMemcpy(coef, hc, sizeof(hc), cudaMemcpyHostToDevice);
-    for (int wpc : {4, 8, 12}) {
+    for (int wpc : {1, 4, 8, 12}) {
         run<0>("0 shipped cheby_step (LDS.128, 4 chains)", wpc, out, cyc, coef);
         run<1>("1 8 FMA chains", wpc, out, cyc, coef);
         run<2>("2 SHFL exchange", wpc, out, cyc, coef);
         run<3>("3 unrolled m=17", wpc, out, cyc, coef);
         run<4>("4 two recursions per warp", wpc, out, cyc, coef, 2);
+        run<5>("5 gathers issued right after the store", wpc, out, cyc, coef);
     }
     return 0;
 }
