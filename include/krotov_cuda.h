@@ -205,6 +205,11 @@ int krotov_comm_connect(krotov_handle h, int rank, int world, const void *descs 
  * (QuantumPropagators `specrange(...; method=:diag)`, reached from src/optimize.jl:251,306,324 through the range
  * hook :238-244) for every ensemble member at once; a Julia caller may keep using `eigvals`. */
 int krotov_hermitian_extremes(int n_mat, int d, const double *mats, double *e_min, double *e_max, int n_threads);
+/* The spectral envelope of every generator of an ensemble in one call: for generator g the smallest and largest
+ * eigenvalue over the `n_corner` amplitude corners of  H0[g] + sum_l amps[corner][l] * Hc[l][g]  (Hermitian part).
+ * H0: cplx[n_gen][d][d], Hc: cplx[n_ctrl][n_gen][d][d], amps: [n_corner][n_ctrl], e_min/e_max: [n_gen]. */
+int krotov_envelope_extremes(int n_gen, int d, int n_ctrl, const double *H0, const double *Hc, int n_corner,
+                             const double *amps, double *e_min, double *e_max, int n_threads);
 
 #ifdef __cplusplus
 }

@@ -25,7 +25,7 @@ EXPORTS = [
     "krotov_abi_version", "krotov_create", "krotov_destroy", "krotov_last_error", "krotov_get_info",
     "krotov_set_cheby", "krotov_forward", "krotov_set_chi", "krotov_set_chi_coeffs", "krotov_iterate",
     "krotov_get_states", "krotov_get_tau", "krotov_get_storage", "krotov_get_profile", "krotov_comm_export", "krotov_comm_connect",
-    "krotov_hermitian_extremes",
+    "krotov_hermitian_extremes", "krotov_envelope_extremes",
 ]
 
 
@@ -92,6 +92,7 @@ def lib():
     L.krotov_comm_export.argtypes = [vp, vp]
     L.krotov_comm_connect.argtypes = [vp, i32, i32, vp]
     L.krotov_hermitian_extremes.argtypes = [i32, i32, vp, vp, vp, i32]
+    L.krotov_envelope_extremes.argtypes = [i32, i32, i32, vp, vp, i32, vp, vp, vp, i32]
     for name in EXPORTS:
         if name not in ("krotov_last_error",):
             getattr(L, name).restype = i32
@@ -112,4 +113,23 @@ def hermitian_extremes(stack, n_threads=0):
                                          hi.ctypes.data_as(C.c_void_p), int(n_threads))
     if rc != KROTOV_OK:
         raise KrotovCudaError(rc, "krotov_hermitian_extremes: bad argument")
+    return lo, hi
+
+
+def envelope_extremes(H0s, Hcs, corners, n_threads=0):
+    """``(e_min, e_max)`` per generator over the amplitude corners: ``H0s`` (n_gen, d, d), ``Hcs`` (L, n_gen, d, d),
+    ``corners`` (n_corner, L) -- ``krotov_envelope_extremes``."""
+    import numpy as np
+
+    H0s = np.ascontiguousarray(H0s, np.complex128)
+    Hcs = np.ascontiguousarray(Hcs, np.complex128)
+    amps = np.ascontiguousarray(corners, np.float64)
+    n_gen, d = H0s.shape[0], H0s.shape[-1]
+    n_ctrl = Hcs.shape[0] if Hcs.size else 0
+    lo, hi = np.empty(n_gen, np.float64), np.empty(n_gen, np.float64)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    rc = lib().krotov_envelope_extremes(n_gen, d, n_ctrl, p(H0s), p(Hcs), amps.shape[0], p(amps), p(lo), p(hi),
+                                        int(n_threads))
+    if rc != KROTOV_OK:
+        raise KrotovCudaError(rc, "krotov_envelope_extremes: bad argument")
     return lo, hi

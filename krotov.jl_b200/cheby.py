@@ -146,6 +146,7 @@ class ChebyDirection:
                                    np.asarray(row[l], np.complex128) for row in Hc]) for l in range(len(pulses))]
             # Hermitian terms and real amplitudes: every evaluated generator is Hermitian (checked once, not per event)
             self._herm = all(np.array_equal(a, a.conj().transpose(0, 2, 1)) for a in [self._H0s] + self._Hcs)
+            self._Hcs_stack = np.stack(self._Hcs) if self._Hcs else np.zeros((0,) + self._H0s.shape, np.complex128)
         self._classify_steps()
         self._derive()
 
@@ -171,21 +172,20 @@ class ChebyDirection:
             # all generators in two batched LAPACK calls (numpy loops over the stack in C and calls the same
             # zgeev per matrix, so every number is what `specrange` returns for the single matrix)
             # (the Hermitian solver when every evaluated generator is Hermitian, like `specrange`)
-            G_hi, G_lo = self._H0s.copy(), self._H0s.copy()  # same elementwise sums as `_evaluate`, for all g at once
-            for l in range(len(hi)):
-                G_hi = G_hi + hi[l] * self._Hcs[l]
-                G_lo = G_lo + lo[l] * self._Hcs[l]
-            herm = self._herm or (np.array_equal(G_hi, G_hi.conj().transpose(0, 2, 1)) and np.array_equal(
-                G_lo, G_lo.conj().transpose(0, 2, 1)))
-            if herm and 2 * n_gen >= _NATIVE_MIN_BATCH and G_hi.shape[-1] <= 64:
-                # ensembles: the library's threaded host solver (extreme eigenvalues only); agrees with LAPACK to
-                # a few ulp of the matrix norm, far below what the Chebyshev expansion resolves
-                from ._lib import hermitian_extremes
+            if self._herm and 2 * n_gen >= _NATIVE_MIN_BATCH and self._H0s.shape[-1] <= 64:
+                # ensembles: the library's threaded host solver (forms the corner generators and finds their extreme
+                # eigenvalues only); agrees with LAPACK to a few ulp of the matrix norm, far below what the
+                # Chebyshev expansion resolves
+                from ._lib import envelope_extremes
 
-                lo_ev, hi_ev = hermitian_extremes(np.concatenate([G_hi, G_lo]))
-                e_min = np.minimum(lo_ev[:n_gen], lo_ev[n_gen:])
-                e_max = np.maximum(hi_ev[:n_gen], hi_ev[n_gen:])
+                e_min, e_max = envelope_extremes(self._H0s, self._Hcs_stack, np.array([hi, lo], np.float64))
             else:
+                G_hi, G_lo = self._H0s.copy(), self._H0s.copy()  # same elementwise sums as `_evaluate`, for all g at once
+                for l in range(len(hi)):
+                    G_hi = G_hi + hi[l] * self._Hcs[l]
+                    G_lo = G_lo + lo[l] * self._Hcs[l]
+                herm = self._herm or (np.array_equal(G_hi, G_hi.conj().transpose(0, 2, 1)) and np.array_equal(
+                    G_lo, G_lo.conj().transpose(0, 2, 1)))
                 solver = np.linalg.eigvalsh if herm else (lambda a: np.linalg.eigvals(a).real)
                 ev = _batched(solver, np.concatenate([G_hi, G_lo]))
                 ev_hi, ev_lo = ev[:n_gen], ev[n_gen:]

@@ -19,6 +19,8 @@
 #include <string>
 #include <vector>
 
+#include <thread>
+
 #include "../../include/krotov_cuda.h"
 #include "dense_kernel.cuh"
 #include "warp_kernel.cuh"
@@ -302,29 +304,43 @@ int build_pattern(krotov_handle h) {
     return KROTOV_OK;
 }
 
-// rows P_t for one direction: [g][1+L][Wt+1][32]
+// rows P_t for one direction: [g][1+L][Wt+1][32].  The factor 2c = -/+ 4i/Delta is purely imaginary, so the product
+// is written out (std::complex multiplication goes through __muldc3); generators are spread over a few threads.
 void build_rows(krotov_handle h, int dir, std::vector<cplx> &out) {
-    const int d = h->d, L = h->L, Wt = h->Wt;
+    const int d = h->d, L = h->L, Wt = h->Wt, lpt = h->lpt;
     const ChebyTables &ct = h->cheb[dir];
-    out.assign((size_t)h->n_gen * (1 + L) * (Wt + 1) * h->lpt, cplx(0, 0));
-    for (int g = 0; g < h->n_gen; ++g) {
-        const double s = 4.0 / ct.Delta[g];
-        const double beta = ct.Delta[g] / 2 + ct.E_min[g];
-        const cplx f = (dir == KROTOV_FORWARD) ? cplx(0.0, -s) : cplx(0.0, s);  // 2c = -/+ 4i/Delta
-        for (int t = 0; t <= L; ++t) {
-            cplx *row = &out[((size_t)g * (1 + L) + t) * (Wt + 1) * h->lpt];
-            for (int i = 0; i < d; ++i) {
-                for (int sl = 0; sl < Wt; ++sl) {
-                    if (!h->slot_valid[(size_t)sl * h->lpt + i]) continue;
-                    const int j = h->cols[(size_t)sl * h->lpt + i];
-                    const cplx v = (dir == KROTOV_FORWARD) ? Hval(h, g, t, i, j) : std::conj(Hval(h, g, t, j, i));
-                    row[(size_t)sl * h->lpt + i] = f * v;
+    out.assign((size_t)h->n_gen * (1 + L) * (Wt + 1) * lpt, cplx(0, 0));
+    const bool fw = (dir == KROTOV_FORWARD);
+    auto work = [&](int g0, int g1) {
+        for (int g = g0; g < g1; ++g) {
+            const double s = 4.0 / ct.Delta[g];
+            const double beta = ct.Delta[g] / 2 + ct.E_min[g];
+            const double fy = fw ? -s : s;  // f = (0, fy);  f * (a + i b) = -fy b + i fy a
+            for (int t = 0; t <= L; ++t) {
+                cplx *row = &out[((size_t)g * (1 + L) + t) * (Wt + 1) * lpt];
+                const cplx *H = &h->Hdense[(((size_t)g * (1 + L) + t) * d) * d];
+                for (int sl = 0; sl < Wt; ++sl)
+                    for (int i = 0; i < d; ++i) {
+                        if (!h->slot_valid[(size_t)sl * lpt + i]) continue;
+                        const int j = h->cols[(size_t)sl * lpt + i];
+                        const cplx v = fw ? H[(size_t)i * d + j] : std::conj(H[(size_t)j * d + i]);
+                        row[(size_t)sl * lpt + i] = cplx(-fy * v.imag(), fy * v.real());
+                    }
+                for (int i = 0; i < d; ++i) {
+                    const cplx hv = H[(size_t)i * d + i];
+                    const double re = hv.real() - (t == 0 ? beta : 0.0), im = fw ? hv.imag() : -hv.imag();
+                    row[(size_t)Wt * lpt + i] = cplx(-fy * im, fy * re);
                 }
-                cplx dv = (dir == KROTOV_FORWARD) ? Hval(h, g, t, i, i) : std::conj(Hval(h, g, t, i, i));
-                if (t == 0) dv -= beta;
-                row[(size_t)Wt * h->lpt + i] = f * dv;
             }
         }
+    };
+    const int nt = (h->n_gen >= 64) ? 4 : 1;
+    if (nt == 1) {
+        work(0, h->n_gen);
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nt; ++t) pool.emplace_back(work, (h->n_gen * t) / nt, (h->n_gen * (t + 1)) / nt);
+        for (auto &th : pool) th.join();
     }
 }
 

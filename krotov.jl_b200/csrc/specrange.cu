@@ -156,13 +156,74 @@ void extreme_eigenvalues(int n, const double *dg, const double *e2, double &emin
 
 }  // namespace
 
+// One worker: extremes of matrix (ar + i ai), destroying it.
+static void extremes_of(int d, std::vector<double> &ar, std::vector<double> &ai, std::vector<double> &vr,
+                        std::vector<double> &vi, std::vector<double> &pr, std::vector<double> &pi,
+                        std::vector<double> &dg, std::vector<double> &e2, double &lo, double &hi) {
+    if (d == 1) {
+        lo = hi = ar[0];
+        return;
+    }
+    tridiagonalise(d, ar.data(), ai.data(), dg.data(), e2.data(), vr.data(), vi.data(), pr.data(), pi.data());
+    extreme_eigenvalues(d, dg.data(), e2.data(), lo, hi);
+}
+
+template <typename F>
+static void run_threads(int n_items, int n_threads, F &&work) {
+    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    nt = std::max(1, std::min(nt, std::min(n_items, 64)));
+    if (nt == 1) {
+        work(0, 1);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nt; ++t) pool.emplace_back(work, t, nt);
+    for (auto &th : pool) th.join();
+}
+
+extern "C" int krotov_envelope_extremes(int n_gen, int d, int n_ctrl, const double *H0, const double *Hc, int n_corner,
+                                        const double *amps, double *e_min, double *e_max, int n_threads) {
+    if (n_gen < 0 || d < 1 || n_ctrl < 0 || n_corner < 1 || !H0 || (n_ctrl > 0 && (!Hc || !amps)) || !e_min || !e_max)
+        return KROTOV_ERR_ARG;
+    if (n_gen == 0) return KROTOV_OK;
+    const size_t dd = (size_t)d * d;
+    run_threads(n_gen, n_threads, [&](int t, int nt) {
+        std::vector<double> ar(dd), ai(dd), vr(d), vi(d), pr(d), pi(d), dg(d), e2(d);
+        for (int g = t; g < n_gen; g += nt) {
+            const cplx *h0 = reinterpret_cast<const cplx *>(H0) + (size_t)g * dd;
+            double lo_all = 0.0, hi_all = 0.0;
+            for (int c = 0; c < n_corner; ++c) {
+                // G = H0 + sum_l amps[c][l] Hc[l], Hermitian part
+                for (int i = 0; i < d; ++i)
+                    for (int j = 0; j < d; ++j) {
+                        double xr = h0[(size_t)i * d + j].real() + h0[(size_t)j * d + i].real();
+                        double xi = h0[(size_t)i * d + j].imag() - h0[(size_t)j * d + i].imag();
+                        for (int l = 0; l < n_ctrl; ++l) {
+                            const cplx *hc = reinterpret_cast<const cplx *>(Hc) + ((size_t)l * n_gen + g) * dd;
+                            const double a = amps[(size_t)c * n_ctrl + l];
+                            xr += a * (hc[(size_t)i * d + j].real() + hc[(size_t)j * d + i].real());
+                            xi += a * (hc[(size_t)i * d + j].imag() - hc[(size_t)j * d + i].imag());
+                        }
+                        ar[(size_t)i * d + j] = 0.5 * xr;
+                        ai[(size_t)i * d + j] = 0.5 * xi;
+                    }
+                double lo, hi;
+                extremes_of(d, ar, ai, vr, vi, pr, pi, dg, e2, lo, hi);
+                lo_all = c == 0 ? lo : std::min(lo_all, lo);
+                hi_all = c == 0 ? hi : std::max(hi_all, hi);
+            }
+            e_min[g] = lo_all;
+            e_max[g] = hi_all;
+        }
+    });
+    return KROTOV_OK;
+}
+
 extern "C" int krotov_hermitian_extremes(int n_mat, int d, const double *mats, double *e_min, double *e_max,
                                          int n_threads) {
     if (n_mat < 0 || d < 1 || !mats || !e_min || !e_max) return KROTOV_ERR_ARG;
     if (n_mat == 0) return KROTOV_OK;
-    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
-    nt = std::max(1, std::min(nt, std::min(n_mat, 64)));
-    auto work = [&](int t) {
+    run_threads(n_mat, n_threads, [&](int t, int nt) {
         std::vector<double> ar((size_t)d * d), ai((size_t)d * d), vr(d), vi(d), pr(d), pi(d), dg(d), e2(d);
         for (int q = t; q < n_mat; q += nt) {
             const cplx *src = reinterpret_cast<const cplx *>(mats) + (size_t)q * d * d;
@@ -173,20 +234,8 @@ extern "C" int krotov_hermitian_extremes(int n_mat, int d, const double *mats, d
                     ar[(size_t)i * d + j] = 0.5 * (x.real() + y.real());
                     ai[(size_t)i * d + j] = 0.5 * (x.imag() - y.imag());
                 }
-            if (d == 1) {
-                e_min[q] = e_max[q] = ar[0];
-                continue;
-            }
-            tridiagonalise(d, ar.data(), ai.data(), dg.data(), e2.data(), vr.data(), vi.data(), pr.data(), pi.data());
-            extreme_eigenvalues(d, dg.data(), e2.data(), e_min[q], e_max[q]);
+            extremes_of(d, ar, ai, vr, vi, pr, pi, dg, e2, e_min[q], e_max[q]);
         }
-    };
-    if (nt == 1) {
-        work(0);
-    } else {
-        std::vector<std::thread> pool;
-        for (int t = 0; t < nt; ++t) pool.emplace_back(work, t);
-        for (auto &th : pool) th.join();
-    }
+    });
     return KROTOV_OK;
 }
