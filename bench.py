@@ -166,6 +166,11 @@ def main():
         run_reference(args)
         return
 
+    # stdout carries exactly ONE JSON line: anything a library prints there (NCCL's version banner, ...) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
 
     import krotov_jl_b200 as K
@@ -302,7 +307,8 @@ def main():
                 line["cpu_baseline"] = cpu_baseline_sample(w, min(args.samples, 128), 2)
             except Exception as exc:  # the baseline is a report, never a reason to lose the GPU number
                 line["cpu_baseline"] = {"error": str(exc)}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         import torch.distributed as dist
 

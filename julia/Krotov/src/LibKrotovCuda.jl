@@ -63,4 +63,16 @@ get_storage!(h, which, k, n0, n1, out::Matrix{ComplexF64}) =
     check(h, ccall((:krotov_get_storage, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Ptr{ComplexF64}),
                    h.ptr, which, k, n0, n1, out))
 
+# Optional host utility: the spectral envelope of every generator of an ensemble in one threaded call
+# (H0: [d, d, n_gen], Hc: [d, d, n_gen, L], amps: [L, n_corner]); `eigvals` works unchanged.
+function envelope_extremes(H0::Array{ComplexF64,3}, Hc::Array{ComplexF64,4}, amps::Matrix{Float64}; threads = 0)
+    d, n_gen, L = size(H0, 1), size(H0, 3), size(Hc, 4)
+    e_min, e_max = Vector{Float64}(undef, n_gen), Vector{Float64}(undef, n_gen)
+    rc = ccall((:krotov_envelope_extremes, lib), Cint,
+        (Cint, Cint, Cint, Ptr{ComplexF64}, Ptr{ComplexF64}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint),
+        n_gen, d, L, H0, Hc, size(amps, 2), amps, e_min, e_max, threads)
+    rc == 0 || error("libkrotov_cuda: krotov_envelope_extremes: bad argument")
+    e_min, e_max
+end
+
 end # module
