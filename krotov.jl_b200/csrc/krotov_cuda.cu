@@ -481,7 +481,7 @@ int launch_warp(krotov_handle h, int mode) {
     p.psi_final = (double2 *)h->d_psif.p; p.tau = (double2 *)h->d_tau.p;
     p.R = (double *)h->d_R.p;
     p.E = (double *)h->d_R.p + (size_t)h->N_T * h->nCTA * h->L;
-    p.acc = (h->world == 1 && h->nCTA > 1 && h->nCTA < 256 && !getenv("KROTOV_NO_ATOMIC_SUM")) ? (unsigned long long *)h->d_acc.p : nullptr;
+    p.acc = (h->nCTA > 1 && h->nCTA < 256 && !getenv("KROTOV_NO_ATOMIC_SUM")) ? (unsigned long long *)h->d_acc.p : nullptr;
     p.rank = h->rank; p.world = h->world;
     const int par = (int)(h->iter_count & 1);
     for (int r = 0; r < h->world && r < kr::kMaxRanks; ++r) p.mbox[r] = h->peer_mbox[par][r];
@@ -1012,7 +1012,7 @@ int krotov_iterate(krotov_handle h, const double *guess_pulses, double *new_puls
     }
     if (h->path == KROTOV_PATH_WARP) {
         if (h->nCTA > 1 || h->world > 1) KR_CUDA(h, cudaMemsetAsync(h->d_R.p, 0xFF, h->d_R.bytes, h->stream));
-        if (h->nCTA > 1 && h->world == 1) KR_CUDA(h, cudaMemsetAsync(h->d_acc.p, 0, h->d_acc.bytes, h->stream));
+        if (h->nCTA > 1) KR_CUDA(h, cudaMemsetAsync(h->d_acc.p, 0, h->d_acc.bytes, h->stream));
         if ((rc = launch_warp(h, 1))) return rc;
     } else {
         std::string e;

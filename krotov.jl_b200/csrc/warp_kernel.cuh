@@ -374,7 +374,8 @@ __device__ __forceinline__ void red_add_u64(unsigned long long *p, unsigned long
 // Returns true when tot[] holds the grid-wide sums; false when some CTA's partial did not fit (all CTAs see the same
 // verdict) and the step has to be redone with the gather protocol.
 __device__ __forceinline__ bool atomic_grid_sum(unsigned long long *An, const int nCTA, const int L, const int lane,
-                                                double (&tot)[kMaxCtrl], int *err_flag, const long long timeout) {
+                                                double (&tot)[kMaxCtrl], int *err_flag, const long long timeout,
+                                                const bool wait = true) {
     const int nw = L * kFixLimbs;           // words of this step; lane q < nw owns word q = (control q / 3, limb q % 3)
     const int myl = lane / kFixLimbs, myj = lane - myl * kFixLimbs;
     double mine = 0.0;
@@ -391,6 +392,7 @@ __device__ __forceinline__ bool atomic_grid_sum(unsigned long long *An, const in
             add += 1ull << 48;  // one partial that does not fit
         red_add_u64(An + lane, add);
     }
+    if (!wait) return true;  // contributor only (several ranks: the reducer alone needs the rank's sum)
     const long long t0 = clock64();
     int spins = 0;
     unsigned long long w = 0;
@@ -452,12 +454,41 @@ __device__ __forceinline__ void comm_warp_run(const WarpParams &p, const int L, 
         }
         const long long c2 = clock64();
         bool summed = false;
-        if (p.acc != nullptr && p.nCTA > 1 && p.world == 1) {
+        if (p.world > 1) {
+            // ---- several ranks.  Every CTA adds its partial into the rank's fixed-point accumulator (and leaves it in
+            // R for the fallback); the reducer (CTA 0) alone waits for the exact rank sum, pushes it into the mailbox
+            // of EVERY rank over NVLink, and every CTA of every rank polls its own rank's mailbox and adds the
+            // `world` rank sums in rank order: identical bits everywhere, no broadcast hop behind the NVLink hop.
+            double *Rn = p.R + (size_t)n * L * p.nCTA;
+            const bool use_acc = p.acc != nullptr && p.nCTA > 1;
+            if (p.nCTA > 1) {
+#pragma unroll
+                for (int l = 0; l < kMaxCtrl; ++l)
+                    if (l < L && lane == l) st_relaxed_gpu_f64(Rn + (size_t)l * p.nCTA + blockIdx.x, tot[l]);
+            }
+            bool have_rank_sum = p.nCTA == 1;
+            if (use_acc)
+                have_rank_sum = atomic_grid_sum(p.acc + (size_t)n * L * kFixLimbs, p.nCTA, L, lane, tot, p.err_flag,
+                                                p.timeout_cycles, blockIdx.x == 0);
+            const size_t off = (size_t)n * L * p.world;  // mailbox layout [n][l][rank]
+            if (blockIdx.x == 0) {
+                if (!have_rank_sum) {
+                    if (use_acc && lane == 0) atomicAdd(p.err_flag + 1, 1);  // krotov_info.fallback_steps
+                    reducer_gather<false>(Rn, p.nCTA, L, lane, gbuf, tot, p.err_flag, p.timeout_cycles);
+                }
+#pragma unroll
+                for (int l = 0; l < kMaxCtrl; ++l)
+                    if (l < L && lane < p.world) st_relaxed_f64(p.mbox[lane] + off + (size_t)l * p.world + p.rank, tot[l]);
+            }
+            reducer_gather<true>(p.mbox[p.rank] + off, p.world, L, lane, gbuf, tot, p.err_flag, p.timeout_cycles);
+            summed = true;
+        } else if (p.acc != nullptr && p.nCTA > 1) {
             summed = atomic_grid_sum(p.acc + (size_t)n * L * kFixLimbs, p.nCTA, L, lane, tot, p.err_flag, p.timeout_cycles);
             if (!summed && blockIdx.x == 0 && lane == 0) atomicAdd(p.err_flag + 1, 1);  // krotov_info.fallback_steps
         }
-        if (!summed && (p.nCTA > 1 || p.world > 1)) {
-            // R[n][l][cta]: CTA partials;  E[n][l]: the grid-wide (and rank-wide) sums, written by the reducer
+        if (!summed && p.nCTA > 1) {
+            // ---- gather + broadcast (one rank; also the fallback of the one-hop sum).  R[n][l][cta]: CTA partials;
+            // E[n][l]: the grid-wide sums, written by the reducer
             double *Rn = p.R + (size_t)n * L * p.nCTA;
             double *En = p.E + (size_t)n * L;
             if (blockIdx.x != 0) {
@@ -466,26 +497,13 @@ __device__ __forceinline__ void comm_warp_run(const WarpParams &p, const int L, 
                     if (l < L && lane == l) st_relaxed_gpu_f64(Rn + (size_t)l * p.nCTA + blockIdx.x, tot[l]);
                 poll_broadcast(En, L, lane, tot, p.err_flag, p.timeout_cycles);
             } else {
-                if (p.nCTA > 1) {
 #pragma unroll
-                    for (int l = 0; l < kMaxCtrl; ++l)
-                        if (l < L && lane == l) st_relaxed_gpu_f64(Rn + (size_t)l * p.nCTA, tot[l]);
-                    reducer_gather<false>(Rn, p.nCTA, L, lane, gbuf, tot, p.err_flag, p.timeout_cycles);
-                }
-                if (p.world > 1) {
-                    const size_t off = (size_t)n * L * p.world;  // mailbox layout [n][l][rank]
+                for (int l = 0; l < kMaxCtrl; ++l)
+                    if (l < L && lane == l) st_relaxed_gpu_f64(Rn + (size_t)l * p.nCTA, tot[l]);
+                reducer_gather<false>(Rn, p.nCTA, L, lane, gbuf, tot, p.err_flag, p.timeout_cycles);
 #pragma unroll
-                    for (int l = 0; l < kMaxCtrl; ++l)
-                        if (l < L && lane < p.world)
-                            st_relaxed_f64(p.mbox[lane] + off + (size_t)l * p.world + p.rank, tot[l]);
-                    reducer_gather<true>(p.mbox[p.rank] + off, p.world, L, lane, gbuf, tot, p.err_flag,
-                                         p.timeout_cycles);
-                }
-                if (p.nCTA > 1) {
-#pragma unroll
-                    for (int l = 0; l < kMaxCtrl; ++l)
-                        if (l < L && lane == l) st_relaxed_gpu_f64(En + l, tot[l]);
-                }
+                for (int l = 0; l < kMaxCtrl; ++l)
+                    if (l < L && lane == l) st_relaxed_gpu_f64(En + l, tot[l]);
             }
         }
         const long long c3 = clock64();
