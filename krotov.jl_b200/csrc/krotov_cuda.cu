@@ -483,6 +483,11 @@ int launch_warp(krotov_handle h, int mode) {
     p.E = (double *)h->d_R.p + (size_t)h->N_T * h->nCTA * h->L;
     p.acc = (h->nCTA > 1 && h->nCTA < 256 && !getenv("KROTOV_NO_ATOMIC_SUM")) ? (unsigned long long *)h->d_acc.p : nullptr;
     p.rank = h->rank; p.world = h->world;
+    // Who polls the rank's mailbox: every CTA (no broadcast hop) while pollers x writers stay few, else the reducer
+    // alone, which then broadcasts through E.  Measured on C4 (ms per iteration, all-poll / reducer-poll): 2 GPUs x
+    // 128 CTAs 14.0 / 14.6, 2 x 147 16.4 / 16.9, 8 x 32 14.9 / 17.2, 8 x 147 23.3 / 18.7.
+    p.mbox_all = (h->nCTA * h->world <= 400) ? 1 : 0;
+    if (const char *e = getenv("KROTOV_MBOX_ALL")) p.mbox_all = atoi(e);
     const int par = (int)(h->iter_count & 1);
     for (int r = 0; r < h->world && r < kr::kMaxRanks; ++r) p.mbox[r] = h->peer_mbox[par][r];
     p.err_flag = (int *)h->d_err.p;

@@ -72,6 +72,7 @@ struct WarpParams {
     double *R;                 // [N_T][L][nCTA] CTA partial sums, sentinel-filled before every iteration
     double *E;                 // [N_T][L] grid-wide sums broadcast by the reducer (CTA 0), sentinel-filled
     unsigned long long *acc;   // [N_T][L][3] fixed-point accumulators of the one-hop grid sum (zero-filled), or nullptr
+    int mbox_all;              // several ranks: 1 = every CTA polls the rank's mailbox, 0 = the reducer polls it and broadcasts through E
     int rank, world;
     double *mbox[kMaxRanks];   // mailbox of every rank (this iteration's parity): [N_T][world][L]
     int *err_flag;
@@ -480,7 +481,19 @@ __device__ __forceinline__ void comm_warp_run(const WarpParams &p, const int L, 
                 for (int l = 0; l < kMaxCtrl; ++l)
                     if (l < L && lane < p.world) st_relaxed_f64(p.mbox[lane] + off + (size_t)l * p.world + p.rank, tot[l]);
             }
-            reducer_gather<true>(p.mbox[p.rank] + off, p.world, L, lane, gbuf, tot, p.err_flag, p.timeout_cycles);
+            if (p.mbox_all || p.nCTA == 1) {
+                reducer_gather<true>(p.mbox[p.rank] + off, p.world, L, lane, gbuf, tot, p.err_flag, p.timeout_cycles);
+            } else {
+                double *En = p.E + (size_t)n * L;
+                if (blockIdx.x == 0) {
+                    reducer_gather<true>(p.mbox[p.rank] + off, p.world, L, lane, gbuf, tot, p.err_flag, p.timeout_cycles);
+#pragma unroll
+                    for (int l = 0; l < kMaxCtrl; ++l)
+                        if (l < L && lane == l) st_relaxed_gpu_f64(En + l, tot[l]);
+                } else {
+                    poll_broadcast(En, L, lane, tot, p.err_flag, p.timeout_cycles);
+                }
+            }
             summed = true;
         } else if (p.acc != nullptr && p.nCTA > 1) {
             summed = atomic_grid_sum(p.acc + (size_t)n * L * kFixLimbs, p.nCTA, L, lane, tot, p.err_flag, p.timeout_cycles);
