@@ -95,6 +95,7 @@ struct krotov_handle_s {
     bool mu_hermitian = false;
     int lpt = 32;  // threads (= padded rows) per trajectory on the warp path: 32, 64 or 128
     bool tiny = false;  // d <= 4, N <= 32, L <= 2: one thread per trajectory, everything in registers (tiny_kernel.cuh)
+    bool tiny_imag[2] = {false, false};  // every prepared term of the direction is purely imaginary (real Hamiltonian)
     std::vector<int> cols;  // [Wt][lpt]
     std::vector<char> slot_valid;  // [Wt][32] slot holds a real matrix entry (i, cols[s][i])
     int wpc = 1, tpw = 1, nCTA = 1;
@@ -364,9 +365,11 @@ void build_dense_terms(krotov_handle h, int dir, std::vector<cplx> &out) {
 }
 
 using TinyKernel = void (*)(const kr::TinyParams);
-TinyKernel tiny_kernel_for(int d, int L) {
-#define KR_TINY(D, LT) \
-    if (d == D && L == LT) return (TinyKernel)kr::krotov_tiny_kernel<D, LT, ((1 + LT) * D * D <= 12)>
+TinyKernel tiny_kernel_for(int d, int L, bool gimag = false) {
+#define KR_TINY(D, LT)                                                                                              \
+    if (d == D && L == LT)                                                                                          \
+        return gimag ? (TinyKernel)kr::krotov_tiny_kernel<D, LT, ((1 + LT) * D * D <= 12), true>                     \
+                     : (TinyKernel)kr::krotov_tiny_kernel<D, LT, ((1 + LT) * D * D <= 12), false>
     KR_TINY(2, 1); KR_TINY(2, 2); KR_TINY(3, 1); KR_TINY(3, 2); KR_TINY(4, 1); KR_TINY(4, 2);
 #undef KR_TINY
     return nullptr;
@@ -505,7 +508,7 @@ int launch_warp(krotov_handle h, int mode) {
         const size_t coef_bytes = ((size_t)p.ndtc_f * p.mmax_f + (size_t)p.ndtc_b * p.mmax_b) * 32 * 8;
         tp.coef_in_smem = (term_bytes + coef_bytes <= 160 * 1024) ? 1 : 0;
         const size_t smem = term_bytes + (tp.coef_in_smem ? coef_bytes : 0) + 16;
-        TinyKernel fn = tiny_kernel_for(h->d, h->L);
+        TinyKernel fn = tiny_kernel_for(h->d, h->L, h->tiny_imag[0] && h->tiny_imag[1]);
         KR_CUDA(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         void *args[] = {(void *)&tp};
         KR_CUDA(h, cudaLaunchKernel((const void *)fn, dim3(1), dim3(32), args, smem, h->stream));
@@ -911,6 +914,9 @@ int krotov_set_cheby(krotov_handle h, int direction, int n_dt_class, const int32
         }
         if (h->tiny) {
             build_dense_terms(h, direction, rows);
+            bool imag = !getenv("KROTOV_NO_TINY_IMAG");
+            for (const cplx &v : rows) imag = imag && (v.real() == 0.0);
+            h->tiny_imag[direction] = imag;
             if ((rc = upload(h, direction == KROTOV_FORWARD ? h->d_Tf : h->d_Tb, rows))) return rc;
         }
         tr.lap("rows uploaded");

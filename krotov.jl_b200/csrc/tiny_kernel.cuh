@@ -21,26 +21,39 @@ struct TinyParams {
 };
 
 
-// y = M v + add   (complex; four independent FMA chains per row)
-template <int D>
+// y = M v + add   (complex; four independent FMA chains per row).  GIMAG: every entry of M is purely imaginary --
+// the generator 2c (H - beta) of a REAL Hamiltonian (two-level systems, Duffing oscillators in the rotating frame
+// with real drives ...) -- so half of the products vanish identically and are not issued: the kernel is bound by
+// FP64 issue slots (a warp instruction costs 2 cycles however few lanes are live), this halves them.
+template <int D, bool GIMAG>
 __device__ __forceinline__ void tiny_matvec(double2 (&y)[D], const double2 (&M)[D][D], const double2 (&v)[D],
                                             const double2 (&add)[D]) {
 #pragma unroll
     for (int i = 0; i < D; ++i) {
-        double ar = add[i].x, ai = add[i].y, br = 0.0, bi = 0.0;
+        if (GIMAG) {  // (i g) (vr + i vi) = -g vi + i g vr: two chains seeded with `add`, no joining add
+            double br = add[i].x, bi = add[i].y;
 #pragma unroll
-        for (int j = 0; j < D; ++j) {
-            ar = fma(M[i][j].x, v[j].x, ar);
-            br = fma(-M[i][j].y, v[j].y, br);
-            ai = fma(M[i][j].x, v[j].y, ai);
-            bi = fma(M[i][j].y, v[j].x, bi);
+            for (int j = 0; j < D; ++j) {
+                br = fma(-M[i][j].y, v[j].y, br);
+                bi = fma(M[i][j].y, v[j].x, bi);
+            }
+            y[i] = make_double2(br, bi);
+        } else {
+            double ar = add[i].x, ai = add[i].y, br = 0.0, bi = 0.0;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                ar = fma(M[i][j].x, v[j].x, ar);
+                ai = fma(M[i][j].x, v[j].y, ai);
+                br = fma(-M[i][j].y, v[j].y, br);
+                bi = fma(M[i][j].y, v[j].x, bi);
+            }
+            y[i] = make_double2(ar + br, ai + bi);
         }
-        y[i] = make_double2(ar + br, ai + bi);
     }
 }
 
 // One Chebyshev step (same recursion and operation order as cheby_step of the warp kernel).
-template <int D>
+template <int D, bool GIMAG>
 __device__ __forceinline__ void tiny_cheby(double2 (&psi)[D], const double2 (&G)[D][D], const double *a, const int astride,
                                            const int m, const double2 phase) {
     double2 v0[D], v1[D], v2[D], out[D], zero[D];
@@ -51,7 +64,7 @@ __device__ __forceinline__ void tiny_cheby(double2 (&psi)[D], const double2 (&G)
         zero[i] = make_double2(0.0, 0.0);
         out[i] = make_double2(a0 * psi[i].x, a0 * psi[i].y);
     }
-    tiny_matvec<D>(v1, G, v0, zero);
+    tiny_matvec<D, GIMAG>(v1, G, v0, zero);
     const double a1 = m > 1 ? a[astride] : 0.0;
 #pragma unroll
     for (int i = 0; i < D; ++i) {
@@ -61,7 +74,7 @@ __device__ __forceinline__ void tiny_cheby(double2 (&psi)[D], const double2 (&G)
     }
     for (int j = 2; j < m; ++j) {
         const double aj = a[(size_t)j * astride];
-        tiny_matvec<D>(v2, G, v1, v0);
+        tiny_matvec<D, GIMAG>(v2, G, v1, v0);
 #pragma unroll
         for (int i = 0; i < D; ++i) {
             out[i].x = fma(aj, v2[i].x, out[i].x);
@@ -94,6 +107,7 @@ struct TinyTerms {
         __syncwarp();
     }
     __device__ __forceinline__ double2 get(const int e) const { return TREG ? r[e] : s[e * 32]; }
+    template <bool GIMAG>
     __device__ __forceinline__ void build(double2 (&G)[D][D], const double (&eps)[LT]) const {
 #pragma unroll
         for (int i = 0; i < D; ++i)
@@ -103,7 +117,7 @@ struct TinyTerms {
 #pragma unroll
                 for (int l = 0; l < LT; ++l) {
                     const double2 t = get((l + 1) * D * D + i * D + j);
-                    g.x = fma(eps[l], t.x, g.x);
+                    if (!GIMAG) g.x = fma(eps[l], t.x, g.x);
                     g.y = fma(eps[l], t.y, g.y);
                 }
                 G[i][j] = g;
@@ -135,7 +149,7 @@ __device__ __forceinline__ TinyMeta tiny_meta(const int *dtc, const int *m_tab, 
     return s;
 }
 
-template <int D, int LT, bool TREG>
+template <int D, int LT, bool TREG, bool GIMAG>
 __global__ void __launch_bounds__(32, 1) krotov_tiny_kernel(const __grid_constant__ TinyParams tp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const WarpParams &p = tp.w;
@@ -196,8 +210,8 @@ __global__ void __launch_bounds__(32, 1) krotov_tiny_kernel(const __grid_constan
             double e_next[LT];
 #pragma unroll
             for (int l = 0; l < LT; ++l) e_next[l] = p.eps_old[(size_t)l * N_T + nn];
-            T.build(G, e_cur);
-            tiny_cheby<D>(chi, G, meta.a, meta.astride, meta.m, meta.phase);
+            T.template build<GIMAG>(G, e_cur);
+            tiny_cheby<D, GIMAG>(chi, G, meta.a, meta.astride, meta.m, meta.phase);
             if (live) {
 #pragma unroll
                 for (int i = 0; i < D; ++i) Xk[(size_t)n * 32 + i] = chi[i];
@@ -269,9 +283,11 @@ __global__ void __launch_bounds__(32, 1) krotov_tiny_kernel(const __grid_constan
 #pragma unroll
                         for (int j = 0; j < D; ++j) {
                             const double2 t = T.get((l + 1) * D * D + i * D + j);
-                            wr = fma(t.x, psi[j].x, wr);
+                            if (!GIMAG) {
+                                wr = fma(t.x, psi[j].x, wr);
+                                wi = fma(t.x, psi[j].y, wi);
+                            }
                             wr1 = fma(-t.y, psi[j].y, wr1);
-                            wi = fma(t.x, psi[j].y, wi);
                             wi1 = fma(t.y, psi[j].x, wi1);
                         }
                         part = fma(chi[i].x, wr + wr1, fma(chi[i].y, wi + wi1, part));
@@ -291,8 +307,8 @@ __global__ void __launch_bounds__(32, 1) krotov_tiny_kernel(const __grid_constan
                 for (int l = 0; l < LT; ++l) eps[l] = eo_cur[l];
             }
             // ---- forward step with the (updated) pulse value  (:360-368)
-            T.build(G, eps);
-            tiny_cheby<D>(psi, G, meta.a, meta.astride, meta.m, meta.phase);
+            T.template build<GIMAG>(G, eps);
+            tiny_cheby<D, GIMAG>(psi, G, meta.a, meta.astride, meta.m, meta.phase);
             if (live && p.store_fw) {
                 const int slot = (p.mode == 1) ? n : n + 1;  // sic, src/optimize.jl:367 vs :263
 #pragma unroll

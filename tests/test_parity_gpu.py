@@ -702,3 +702,16 @@ def test_atomic_grid_sum_falls_back_when_a_partial_does_not_fit(monkeypatch):
     ref = run_product(w, 2)  # the same optimisation in natural units
     assert ref["info"]["fallback_steps"] == 0
     assert np.abs(np.array(a["J_T"]) - np.array(ref["J_T"])).max() < 1e-12
+
+
+def test_tiny_kernel_real_hamiltonian_specialisation(monkeypatch):
+    """Real Hamiltonians (C1, C2) give purely imaginary prepared generators: the tiny kernel then issues half the
+    products.  Same numbers as the general instance (the dropped products are exact zeros)."""
+    for w, iters in ((W.c1_tls(), 3), (W.c2_transmon_x(), 3)):
+        a = run_product(w, iters)
+        monkeypatch.setenv("KROTOV_NO_TINY_IMAG", "1")
+        b = run_product(w, iters)
+        monkeypatch.delenv("KROTOV_NO_TINY_IMAG")
+        assert a["info"]["block_threads"] == 32 and b["info"]["block_threads"] == 32
+        assert np.abs(np.array(a["J_T"]) - np.array(b["J_T"])).max() < 1e-14
+        assert np.abs(a["pulses"] - b["pulses"]).max() < 1e-13
