@@ -26,6 +26,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace kr {
@@ -104,8 +105,32 @@ struct GemmParams {
     double2 *store;       // last term: optional second copy (storage slot), same layout
     // ---- epi 1
     const double2 *CHI;
-    double *partial;      // [gridDim.x]
+    double *partial;      // [dp / BM] one entry per row block
+    // ---- stream-K (grid = SM count > row blocks): partial tiles and their ready flags
+    int streamk;
+    double2 *ws;          // [dp / BM][kSkParts][BM * 64]
+    unsigned *flags;      // [dp / BM][kSkParts][4] = epoch of the launch that wrote the partial
+    unsigned epoch;
 };
+
+constexpr int kSkParts = 8;  // most CTAs that can share one row block
+
+__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// CTA c of a stream-K launch owns the chunks [total * c / G, total * (c + 1) / G) of the linearised (row block, k chunk)
+// space; this is the CTA that owns chunk x.
+__device__ __forceinline__ int sk_cta_of(long long x, long long total, int G) {
+    int c = (int)((x * G) / total);
+    while (c + 1 < G && total * (c + 1) / G <= x) ++c;
+    while (c > 0 && total * c / G > x) --c;
+    return c;
+}
 
 template <int NT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) dense_gemm_kernel(const __grid_constant__ GemmParams p) {
@@ -115,10 +140,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dense_gemm_kernel(const __gri
     uint64_t *empty = full + STAGES;
     double *wsum = reinterpret_cast<double *>(empty + STAGES);  // [4] per-warp partials (epi 1)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row0 = blockIdx.x * BM;
     const int nk = p.dp / BK;
     constexpr uint32_t X_ROW_BYTES = NT * 8 * 16;
     constexpr uint32_t STAGE_BYTES = BM * BK * 16 + BK * X_ROW_BYTES;
+    // Work of this CTA: a contiguous range of (row block, k chunk) pairs.  Classic launch: one whole row block.
+    // Stream-K launch (as many CTAs as SMs, more than row blocks): total / G chunks each, so a row block is shared by
+    // the CTAs whose ranges meet inside it.  The CTA that holds a row block's LAST chunk owns it: it adds the partial
+    // tiles of the others (fixed order: ascending k) and runs the epilogue.  A CTA works on its trailing partial
+    // segment FIRST and on the segment it owns last, so nobody ever waits on a CTA that is itself waiting.
+    const long long total = (long long)(p.dp / BM) * nk;
+    const int G = gridDim.x;
+    const long long lo = p.streamk ? total * blockIdx.x / G : (long long)blockIdx.x * nk;
+    const long long hi = p.streamk ? total * (blockIdx.x + 1) / G : lo + nk;
+    const int rb_first = (int)(lo / nk), rb_last = (int)((hi - 1) / nk);
+    const int nseg = rb_last - rb_first + 1;
+    const bool tail_first = (hi % nk) != 0 && nseg > 1;  // trailing segment does not finish its row block
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -129,100 +165,162 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dense_gemm_kernel(const __gri
     }
     __syncthreads();
 
+    // segment q of this CTA in processing order
+    auto segment = [&](int q, int &rb, int &k0, int &k1) {
+        int idx = q;
+        if (tail_first) idx = (q == 0) ? nseg - 1 : q - 1;
+        rb = rb_first + idx;
+        k0 = (rb == rb_first) ? (int)(lo - (long long)rb_first * nk) : 0;
+        k1 = (rb == rb_last) ? (int)(hi - (long long)rb_last * nk) : nk;
+    };
+
     if (warp == 4) {
         // ------------------------------------------------------------ producer: bulk copies, one row per lane
-        for (int kc = 0; kc < nk; ++kc) {
-            const int s = kc % STAGES;
-            if (kc >= STAGES) mbar_wait(&empty[s], ((kc / STAGES) - 1) & 1);
-            double2 *As = ring + (size_t)s * STAGE_WORDS;
-            double2 *Xs = As + A_STAGE_WORDS;
-            if (lane == 0) mbar_expect_tx(&full[s], STAGE_BYTES);
-            __syncwarp();
-            bulk_g2s(As + lane * A_STRIDE, p.A + (size_t)(row0 + lane) * p.dp + (size_t)kc * BK, BK * 16, &full[s]);
-            bulk_g2s(Xs + lane * X_STRIDE, p.B + (size_t)(kc * BK + lane) * p.ld + p.col0, X_ROW_BYTES, &full[s]);
+        int it = 0;
+        for (int q = 0; q < nseg; ++q) {
+            int rb, k0, k1;
+            segment(q, rb, k0, k1);
+            const int row0 = rb * BM;
+            for (int kc = k0; kc < k1; ++kc, ++it) {
+                const int s = it % STAGES;
+                if (it >= STAGES) mbar_wait(&empty[s], ((it / STAGES) - 1) & 1);
+                double2 *As = ring + (size_t)s * STAGE_WORDS;
+                double2 *Xs = As + A_STAGE_WORDS;
+                if (lane == 0) mbar_expect_tx(&full[s], STAGE_BYTES);
+                __syncwarp();
+                bulk_g2s(As + lane * A_STRIDE, p.A + (size_t)(row0 + lane) * p.dp + (size_t)kc * BK, BK * 16, &full[s]);
+                bulk_g2s(Xs + lane * X_STRIDE, p.B + (size_t)(kc * BK + lane) * p.ld + p.col0, X_ROW_BYTES, &full[s]);
+            }
         }
         return;
     }
 
     // ---------------------------------------------------------------- consumers: DMMA
-    double cr[NT][2], ci[NT][2];
-#pragma unroll
-    for (int t = 0; t < NT; ++t) cr[t][0] = cr[t][1] = ci[t][0] = ci[t][1] = 0.0;
     const int fr = lane >> 2, fk = lane & 3;  // fragment row / k (A), fragment col / k (B)
-    for (int kc = 0; kc < nk; ++kc) {
-        const int s = kc % STAGES;
-        mbar_wait(&full[s], (kc / STAGES) & 1);
-        const double2 *As = ring + (size_t)s * STAGE_WORDS + (warp * 8 + fr) * A_STRIDE + fk;
-        const double2 *Xs = ring + (size_t)s * STAGE_WORDS + A_STAGE_WORDS + fk * X_STRIDE + fr;
+    int it = 0;
+    for (int q = 0; q < nseg; ++q) {
+        int rb, k0, k1;
+        segment(q, rb, k0, k1);
+        const int row0 = rb * BM;
+        double cr[NT][2], ci[NT][2];
 #pragma unroll
-        for (int ks = 0; ks < BK / 4; ++ks) {
-            const double2 a = As[ks * 4];
-            const double nai = -a.y;
+        for (int t = 0; t < NT; ++t) cr[t][0] = cr[t][1] = ci[t][0] = ci[t][1] = 0.0;
+        for (int kc = k0; kc < k1; ++kc, ++it) {
+            const int s = it % STAGES;
+            mbar_wait(&full[s], (it / STAGES) & 1);
+            const double2 *As = ring + (size_t)s * STAGE_WORDS + (warp * 8 + fr) * A_STRIDE + fk;
+            const double2 *Xs = ring + (size_t)s * STAGE_WORDS + A_STAGE_WORDS + fk * X_STRIDE + fr;
+#pragma unroll
+            for (int ks = 0; ks < BK / 4; ++ks) {
+                const double2 a = As[ks * 4];
+                const double nai = -a.y;
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    const double2 x = Xs[(ks * 4) * X_STRIDE + t * 8];
+                    dmma(cr[t][0], cr[t][1], a.x, x.x);
+                    dmma(cr[t][0], cr[t][1], nai, x.y);
+                    dmma(ci[t][0], ci[t][1], a.x, x.y);
+                    dmma(ci[t][0], ci[t][1], a.y, x.x);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+
+        if (p.streamk && (k0 > 0 || k1 < nk)) {
+            const int first_cta = sk_cta_of((long long)rb * nk, total, G);
+            const int slot = (int)blockIdx.x - first_cta;  // position among the CTAs sharing this row block
+            if (k1 < nk) {
+                // ---- contributor: park the partial tile, raise the flag of this warp's 8 rows
+                double2 *wt = p.ws + ((size_t)rb * kSkParts + slot) * (BM * 64) + (size_t)(warp * 8 + fr) * (NT * 8) + 2 * fk;
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    wt[t * 8] = make_double2(cr[t][0], ci[t][0]);
+                    wt[t * 8 + 1] = make_double2(cr[t][1], ci[t][1]);
+                }
+                __syncwarp();
+                if (lane == 0) st_release_u32(p.flags + ((size_t)rb * kSkParts + slot) * 4 + warp, p.epoch);
+                continue;
+            }
+            // ---- owner: add the partial tiles of the CTAs before this one, ascending k
+            double sr[NT][2], si[NT][2];
+#pragma unroll
+            for (int t = 0; t < NT; ++t) sr[t][0] = sr[t][1] = si[t][0] = si[t][1] = 0.0;
+            for (int sl = 0; sl < slot; ++sl) {
+                const unsigned *fl = p.flags + ((size_t)rb * kSkParts + sl) * 4 + warp;
+                if (lane == 0)
+                    while (ld_acquire_u32(fl) != p.epoch) {
+                    }
+                __syncwarp();
+                const double2 *wt = p.ws + ((size_t)rb * kSkParts + sl) * (BM * 64) + (size_t)(warp * 8 + fr) * (NT * 8) + 2 * fk;
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    const double2 u0 = __ldcg(wt + t * 8), u1 = __ldcg(wt + t * 8 + 1);
+                    sr[t][0] += u0.x; si[t][0] += u0.y;
+                    sr[t][1] += u1.x; si[t][1] += u1.y;
+                }
+            }
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
-                const double2 x = Xs[(ks * 4) * X_STRIDE + t * 8];
-                dmma(cr[t][0], cr[t][1], a.x, x.x);
-                dmma(cr[t][0], cr[t][1], nai, x.y);
-                dmma(ci[t][0], ci[t][1], a.x, x.y);
-                dmma(ci[t][0], ci[t][1], a.y, x.x);
+                cr[t][0] = sr[t][0] + cr[t][0]; ci[t][0] = si[t][0] + ci[t][0];
+                cr[t][1] = sr[t][1] + cr[t][1]; ci[t][1] = si[t][1] + ci[t][1];
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
-    }
 
-    // ---------------------------------------------------------------- epilogue
-    const int row = row0 + warp * 8 + fr;
-    if (p.epi == 0) {
+        // ---------------------------------------------------------------- epilogue of a finished row block
+        const int row = row0 + warp * 8 + fr;
+        if (p.epi == 0) {
 #pragma unroll
-        for (int t = 0; t < NT; ++t) {
-            const size_t idx = (size_t)row * p.ld + p.col0 + t * 8 + 2 * fk;
-            double2 v0, v1, o0, o1;
-            if (p.j == 1) {
-                const double2 b0 = p.B[idx], b1 = p.B[idx + 1];  // V_0
-                v0 = make_double2(0.5 * cr[t][0], 0.5 * ci[t][0]);
-                v1 = make_double2(0.5 * cr[t][1], 0.5 * ci[t][1]);
-                o0 = make_double2(fma(p.aj, v0.x, p.a0 * b0.x), fma(p.aj, v0.y, p.a0 * b0.y));
-                o1 = make_double2(fma(p.aj, v1.x, p.a0 * b1.x), fma(p.aj, v1.y, p.a0 * b1.y));
-            } else {
-                const double2 w0 = p.Vold[idx], w1 = p.Vold[idx + 1];
-                const double2 q0 = p.OUT[idx], q1 = p.OUT[idx + 1];
-                v0 = make_double2(cr[t][0] + w0.x, ci[t][0] + w0.y);
-                v1 = make_double2(cr[t][1] + w1.x, ci[t][1] + w1.y);
-                o0 = make_double2(fma(p.aj, v0.x, q0.x), fma(p.aj, v0.y, q0.y));
-                o1 = make_double2(fma(p.aj, v1.x, q1.x), fma(p.aj, v1.y, q1.y));
-            }
-            if (p.last) {
-                const double2 r0 = make_double2(p.phase.x * o0.x - p.phase.y * o0.y, p.phase.x * o0.y + p.phase.y * o0.x);
-                const double2 r1 = make_double2(p.phase.x * o1.x - p.phase.y * o1.y, p.phase.x * o1.y + p.phase.y * o1.x);
-                p.PSI[idx] = r0;
-                p.PSI[idx + 1] = r1;
-                if (p.store) {
-                    p.store[idx] = r0;
-                    p.store[idx + 1] = r1;
+            for (int t = 0; t < NT; ++t) {
+                const size_t idx = (size_t)row * p.ld + p.col0 + t * 8 + 2 * fk;
+                double2 v0, v1, o0, o1;
+                if (p.j == 1) {
+                    const double2 b0 = p.B[idx], b1 = p.B[idx + 1];  // V_0
+                    v0 = make_double2(0.5 * cr[t][0], 0.5 * ci[t][0]);
+                    v1 = make_double2(0.5 * cr[t][1], 0.5 * ci[t][1]);
+                    o0 = make_double2(fma(p.aj, v0.x, p.a0 * b0.x), fma(p.aj, v0.y, p.a0 * b0.y));
+                    o1 = make_double2(fma(p.aj, v1.x, p.a0 * b1.x), fma(p.aj, v1.y, p.a0 * b1.y));
+                } else {
+                    const double2 w0 = p.Vold[idx], w1 = p.Vold[idx + 1];
+                    const double2 q0 = p.OUT[idx], q1 = p.OUT[idx + 1];
+                    v0 = make_double2(cr[t][0] + w0.x, ci[t][0] + w0.y);
+                    v1 = make_double2(cr[t][1] + w1.x, ci[t][1] + w1.y);
+                    o0 = make_double2(fma(p.aj, v0.x, q0.x), fma(p.aj, v0.y, q0.y));
+                    o1 = make_double2(fma(p.aj, v1.x, q1.x), fma(p.aj, v1.y, q1.y));
                 }
-            } else {
-                p.Vnew[idx] = v0;
-                p.Vnew[idx + 1] = v1;
-                p.OUT[idx] = o0;
-                p.OUT[idx + 1] = o1;
+                if (p.last) {
+                    const double2 r0 = make_double2(p.phase.x * o0.x - p.phase.y * o0.y, p.phase.x * o0.y + p.phase.y * o0.x);
+                    const double2 r1 = make_double2(p.phase.x * o1.x - p.phase.y * o1.y, p.phase.x * o1.y + p.phase.y * o1.x);
+                    p.PSI[idx] = r0;
+                    p.PSI[idx + 1] = r1;
+                    if (p.store) {
+                        p.store[idx] = r0;
+                        p.store[idx + 1] = r1;
+                    }
+                } else {
+                    p.Vnew[idx] = v0;
+                    p.Vnew[idx + 1] = v1;
+                    p.OUT[idx] = o0;
+                    p.OUT[idx + 1] = o1;
+                }
             }
-        }
-    } else {
-        // Im <chi | w> = chi_r w_i - chi_i w_r, summed over the CTA tile in a fixed order
-        double acc = 0.0;
+        } else {
+            // Im <chi | w> = chi_r w_i - chi_i w_r, summed over the row block's tile in a fixed order
+            double acc = 0.0;
 #pragma unroll
-        for (int t = 0; t < NT; ++t) {
-            const size_t idx = (size_t)row * p.ld + p.col0 + t * 8 + 2 * fk;
-            const double2 c0 = p.CHI[idx], c1 = p.CHI[idx + 1];
-            acc += c0.x * ci[t][0] - c0.y * cr[t][0];
-            acc += c1.x * ci[t][1] - c1.y * cr[t][1];
-        }
+            for (int t = 0; t < NT; ++t) {
+                const size_t idx = (size_t)row * p.ld + p.col0 + t * 8 + 2 * fk;
+                const double2 c0 = p.CHI[idx], c1 = p.CHI[idx + 1];
+                acc += c0.x * ci[t][0] - c0.y * cr[t][0];
+                acc += c1.x * ci[t][1] - c1.y * cr[t][1];
+            }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) wsum[warp] = acc;
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 consumer warps only
-        if (warp == 0 && lane == 0) p.partial[blockIdx.x] = (wsum[0] + wsum[1]) + (wsum[2] + wsum[3]);
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // wsum of the previous segment has been read
+            if (lane == 0) wsum[warp] = acc;
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 consumer warps only
+            if (warp == 0 && lane == 0) p.partial[rb] = (wsum[0] + wsum[1]) + (wsum[2] + wsum[3]);
+        }
     }
 }
 
@@ -495,6 +593,11 @@ struct DenseEngine {
     double2 *Pvf = nullptr, *Pvb = nullptr, *Gv = nullptr;  // [g][1+L][dp*W], [g][dp*W]
     std::vector<int> sp_part_off;  // offset of every column block's CTA partials
     int nnz_union = 0;
+    // stream-K GEMM (fewer row blocks than SMs): partial tiles, ready flags, launch epoch
+    bool streamk = false;
+    double2 *sk_ws = nullptr;
+    unsigned *sk_flags = nullptr;
+    unsigned sk_epoch = 0;
 };
 
 namespace {
@@ -515,7 +618,11 @@ bool launch_gemm(DenseEngine *e, const Block &b, GemmParams p, std::string &err)
     p.dp = e->dp;
     p.ld = e->ld;
     p.col0 = b.col0;
-    dim3 grid(e->dp / BM), block(GEMM_THREADS);
+    p.streamk = e->streamk ? 1 : 0;
+    p.ws = e->sk_ws;
+    p.flags = e->sk_flags;
+    p.epoch = ++e->sk_epoch;
+    dim3 grid(e->streamk ? e->sm_count : e->dp / BM), block(GEMM_THREADS);
     const size_t smem = gemm_smem_bytes();
     static bool attr_set = false;
     if (!attr_set) {
@@ -702,6 +809,16 @@ DenseEngine *dense_create(int d, int N, int L, int N_T, int n_gen, const std::ve
               dalloc(e->d_col_of_traj, (size_t)N, err) && dalloc(e->d_traj_of_col, (size_t)e->ld, err);
     if (ok && !e->hermitian && !e->sparse) ok = dalloc(e->Hb, (size_t)n_gen * (1 + L) * mat, err);
     if (ok && store_fw) ok = dalloc(e->PHI, e->slab * (size_t)(N_T + 1), err);
+    // Stream-K for the DMMA GEMM when the row blocks would leave SMs idle (C5: 128 row blocks on 148 SMs) and K is
+    // long enough to split: as many CTAs as SMs, each total/G chunks of the (row block, k) space.
+    {
+        const int R = e->dp / BM, nk = e->dp / BK, G = e->sm_count;
+        e->streamk = !e->sparse && R >= 32 && R < G && nk >= 32 && (G + R - 1) / R + 1 <= kSkParts && !getenv("KROTOV_NO_STREAMK");
+        if (ok && e->streamk) {
+            ok = dalloc(e->sk_ws, (size_t)R * kSkParts * BM * 64, err) && dalloc(e->sk_flags, (size_t)R * kSkParts * 4, err);
+            if (ok) cudaMemset(e->sk_flags, 0, (size_t)R * kSkParts * 4 * sizeof(unsigned));
+        }
+    }
     if (ok && e->sparse)
         ok = dalloc(e->ell_cols, nslots, err) && dalloc(e->Pvf, (size_t)n_gen * (1 + L) * nslots, err) &&
              dalloc(e->Gv, (size_t)n_gen * nslots, err) &&
@@ -770,7 +887,8 @@ void dense_set_comm(DenseEngine *e, const DenseComm &c) { e->comm = c; }
 void dense_destroy(DenseEngine *e) {
     if (!e) return;
     void *ptrs[] = {e->Hf, e->Hb, e->G, e->V[0], e->V[1], e->V[2], e->OUT, e->PSI, e->PSI0, e->TGT, e->CHI, e->X,
-                    e->PHI, e->partial, e->d_col_of_traj, e->d_traj_of_col, e->ell_cols, e->Pvf, e->Pvb, e->Gv};
+                    e->PHI, e->partial, e->d_col_of_traj, e->d_traj_of_col, e->ell_cols, e->Pvf, e->Pvb, e->Gv,
+                    e->sk_ws, e->sk_flags};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     delete e;

@@ -715,3 +715,23 @@ def test_tiny_kernel_real_hamiltonian_specialisation(monkeypatch):
         assert a["info"]["block_threads"] == 32 and b["info"]["block_threads"] == 32
         assert np.abs(np.array(a["J_T"]) - np.array(b["J_T"])).max() < 1e-14
         assert np.abs(a["pulses"] - b["pulses"]).max() < 1e-13
+
+
+# ---- stream-K DMMA GEMM (fewer row blocks than SMs) ----------------------------------------------------------
+def test_streamk_gemm_vs_c_oracle_and_classic_tiling(monkeypatch):
+    """d = 1056 (33 row blocks of 32 on 148 SMs: the GEMM is split along K across CTAs, partial tiles summed by the
+    row block's owner in ascending k): against the C oracle, and against the one-CTA-per-row-block launch.  Two
+    column blocks (72 trajectories) and both epilogues (Chebyshev term, overlap sums) go through it."""
+    from oracle import c_oracle as C
+
+    w = W.c5_dense(d=1056, n_traj=72, n_grid=4)
+    got = run_product(w, 2)
+    assert got["info"]["path"] == 2
+    ref = C.optimize_krotov_c(W.to_oracle(w), 2)
+    assert_parity(got, ref["J_T"], ref["pulses"], rtol=1e-10, atol=5e-13)
+    got2 = run_product(w, 2)
+    assert np.array_equal(got["pulses"], got2["pulses"]) and got["J_T"] == got2["J_T"]  # fixed summation order
+    monkeypatch.setenv("KROTOV_NO_STREAMK", "1")
+    other = run_product(w, 2)
+    assert np.abs(np.array(got["J_T"]) - np.array(other["J_T"])).max() < 1e-13
+    assert np.abs(got["pulses"] - other["pulses"]).max() < 1e-13
