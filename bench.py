@@ -98,6 +98,20 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
 
 
+def smem_roofline(n_traj, n_steps, terms_per_step, width, sm_count, sm_mhz, ms_launch):
+    """The resource that actually binds the warp kernel: the shared-memory crossbar (128 B/clk/SM).  One Chebyshev
+    term moves (W+1) warp-wide 512-byte accesses per trajectory (W LDS.128 gathers + 1 STS.128)."""
+    moved = float(n_traj) * n_steps * terms_per_step * (width + 1) * 512.0
+    peak = 128.0 * sm_count * sm_mhz * 1e6
+    return {"achieved": moved / (ms_launch * 1e-3) / 1e9, "unit": "GB/s", "peak": peak / 1e9,
+            "frac": moved / (ms_launch * 1e-3) / peak, "bytes_per_launch": moved,
+            "peak_source": "128 B/clk/SM (B300_MICROARCH.md) x SMs x max SM clock; tools/chain_bench.cu reaches 92 % of "
+                           "it with this kernel's inner loop (profiles/r1_chain_bench.txt)",
+            "note": "algorithmic: N x N_T x (m_fw + m_bw - 2) terms x (W+1) x 512 B; the backward sweep alone runs at "
+                    "~80 % of this roof, the forward sweep waits ~40 % of every time step for the grid-wide sum "
+                    "(DESIGN.md 4.1)"}
+
+
 def cpu_baseline_sample(workload_full, samples, iters, n_threads=0):
     """Time the C restatement on a bounded sample: the first `samples` ensemble members of the workload."""
     from oracle import c_oracle
@@ -283,18 +297,8 @@ def main():
                          "note": "the fused kernel keeps all Chebyshev vectors on chip, so HBM traffic is only the chi "
                                  "trajectory; the binding resource is the shared-memory crossbar (see roofline_smem "
                                  "and DESIGN.md 4.1)"},
-            # the resource that actually binds this kernel: the shared-memory crossbar (128 B/clk/SM).  One
-            # Chebyshev term moves (W+1) warp-wide 512-byte accesses per trajectory (W LDS.128 gathers + 1 STS.128).
-            "roofline_smem": (lambda b: {"achieved": b / (ms_launch * 1e-3) / 1e9, "unit": "GB/s",
-                                         "peak": 128.0 * info["sm_count"] * (marks["clocks"]["sm_max_mhz"] or 1965.0) * 1e6 / 1e9,
-                                         "frac": b / (ms_launch * 1e-3) / (128.0 * info["sm_count"] * (marks["clocks"]["sm_max_mhz"] or 1965.0) * 1e6),
-                                         "bytes_per_launch": b,
-                                         "peak_source": "128 B/clk/SM (B300_MICROARCH.md) x SMs x max SM clock; tools/chain_bench.cu "
-                                                        "reaches 92 % of it with this kernel's inner loop (profiles/r1_chain_bench.txt)",
-                                         "note": "algorithmic: N x N_T x (m_fw + m_bw - 2) terms x (W+1) x 512 B; the backward sweep "
-                                                 "alone runs at ~80 % of this roof, the forward sweep idles ~half of every time "
-                                                 "step in the grid-wide exchange (DESIGN.md 4.1)"})(
-                float(n_loc) * N_T * (marks["m_fw"] + marks["m_bw"] - 2) * (info["ell_width"] + 1) * 512.0),
+            "roofline_smem": smem_roofline(n_loc, N_T, marks["m_fw"] + marks["m_bw"] - 2, info["ell_width"],
+                                           info["sm_count"], marks["clocks"]["sm_max_mhz"] or 1965.0, ms_launch),
             "roofline_fp64": {"achieved_tflops": flops / (ms_launch * 1e-3) / 1e12, "flops_per_launch": flops,
                               "peak_tflops": 34.2, "peak_source": "self-measured DFMA peak on this pool's B200 "
                               "(tools/microbench.cu, profiles/r1_microbench_fp64.txt; DMMA: 37.1)",
