@@ -735,3 +735,38 @@ def test_streamk_gemm_vs_c_oracle_and_classic_tiling(monkeypatch):
     other = run_product(w, 2)
     assert np.abs(np.array(got["J_T"]) - np.array(other["J_T"])).max() < 1e-13
     assert np.abs(got["pulses"] - other["pulses"]).max() < 1e-13
+
+
+# ---- seeded sweep over shapes: every kernel family against the NumPy oracle -------------------------------------
+def _sweep_cases():
+    rng = np.random.default_rng(20261018)
+    cases = []
+    for _ in range(18):
+        d = int(rng.choice([2, 3, 4, 5, 8, 13, 21, 25, 32, 33, 48, 70]))
+        n_traj = int(rng.choice([1, 2, 3, 7, 16, 40]))
+        L = int(rng.integers(1, 4))
+        n_grid = int(rng.integers(3, 40))
+        functional = str(rng.choice(["sm", "ss", "re"]))
+        hermitian = bool(rng.random() < 0.8)
+        cases.append((d, n_traj, L, n_grid, functional, hermitian, int(rng.integers(1, 10**6))))
+    return cases
+
+
+@pytest.mark.parametrize("d,n_traj,L,n_grid,functional,hermitian,seed", _sweep_cases())
+def test_seeded_shape_sweep_vs_oracle(d, n_traj, L, n_grid, functional, hermitian, seed):
+    """Random dense problems over Hilbert-space sizes 2..70, 1..40 trajectories, 1..3 controls, all functionals,
+    Hermitian and non-Hermitian generators: tiny, warp and block (DMMA) kernels, one or several CTAs, the one-hop
+    grid sum -- each against the NumPy oracle at BASELINE's tolerances."""
+    from oracle import krotov_oracle as O
+
+    w = W.dummy_dense(d=d, n_traj=n_traj, n_controls=L, n_grid=n_grid, functional=functional, seed=seed)
+    if not hermitian:  # weakly non-Hermitian: decay on the drift, a non-Hermitian admixture to the first control
+        rng = np.random.default_rng(seed + 1)
+        w.H0 = [w.H0[0] - 0.02j * np.diag(rng.uniform(0, 1, d))]
+        B = (rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d))) / np.sqrt(d)
+        w.Hc = [[w.Hc[0][0] + 0.05 * B] + list(w.Hc[0][1:])]
+    w.update_shape = lambda t: 1.0
+    got = run_product(w, 2)
+    ref = O.optimize_krotov(W.to_oracle(w), 2)
+    assert np.isfinite(ref["J_T"]).all()
+    assert_parity(got, ref["J_T"], ref["pulses"], ref["g_a_int"])
