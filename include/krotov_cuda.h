@@ -118,7 +118,8 @@ typedef struct {
     int64_t hbm_bytes_state; /* bytes of the chi trajectory in HBM                   */
     int64_t fallback_steps;  /* WARP path: time steps of the last krotov_iterate whose grid sum left the fixed-point
                                 range of the one-hop all-reduce and was redone with the gather protocol */
-    int64_t reserved[5];
+    int64_t graph_replays;   /* block paths: iterations served by replaying the captured CUDA graph since creation */
+    int64_t reserved[4];
 } krotov_info;
 
 /* ---- lifetime ------------------------------------------------------------------------ */

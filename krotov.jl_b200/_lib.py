@@ -55,7 +55,7 @@ class Info(C.Structure):
         ("sm_count", C.c_int32), ("reserved_i", C.c_int32),
         ("launches_total", C.c_int64), ("launches_last", C.c_int64), ("ms_last", C.c_double),
         ("ms_last_backward", C.c_double), ("hbm_bytes_state", C.c_int64), ("fallback_steps", C.c_int64),
-        ("reserved", C.c_int64 * 5),
+        ("graph_replays", C.c_int64), ("reserved", C.c_int64 * 4),
     ]
 
 

@@ -109,8 +109,7 @@ struct GemmParams {
     // ---- stream-K (grid = SM count > row blocks): partial tiles and their ready flags
     int streamk;
     double2 *ws;          // [dp / BM][kSkParts][BM * 64]
-    unsigned *flags;      // [dp / BM][kSkParts][4] = epoch of the launch that wrote the partial
-    unsigned epoch;
+    unsigned *flags;      // [dp / BM][kSkParts][4]: 1 = partial tile parked; the owner resets it to 0 after reading
 };
 
 constexpr int kSkParts = 8;  // most CTAs that can share one row block
@@ -239,7 +238,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dense_gemm_kernel(const __gri
                     wt[t * 8 + 1] = make_double2(cr[t][1], ci[t][1]);
                 }
                 __syncwarp();
-                if (lane == 0) st_release_u32(p.flags + ((size_t)rb * kSkParts + slot) * 4 + warp, p.epoch);
+                if (lane == 0) st_release_u32(p.flags + ((size_t)rb * kSkParts + slot) * 4 + warp, 1u);
                 continue;
             }
             // ---- owner: add the partial tiles of the CTAs before this one, ascending k
@@ -247,9 +246,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dense_gemm_kernel(const __gri
 #pragma unroll
             for (int t = 0; t < NT; ++t) sr[t][0] = sr[t][1] = si[t][0] = si[t][1] = 0.0;
             for (int sl = 0; sl < slot; ++sl) {
-                const unsigned *fl = p.flags + ((size_t)rb * kSkParts + sl) * 4 + warp;
+                unsigned *fl = p.flags + ((size_t)rb * kSkParts + sl) * 4 + warp;
                 if (lane == 0)
-                    while (ld_acquire_u32(fl) != p.epoch) {
+                    while (ld_acquire_u32(fl) != 1u) {
                     }
                 __syncwarp();
                 const double2 *wt = p.ws + ((size_t)rb * kSkParts + sl) * (BM * 64) + (size_t)(warp * 8 + fr) * (NT * 8) + 2 * fk;
@@ -259,6 +258,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dense_gemm_kernel(const __gri
                     sr[t][0] += u0.x; si[t][0] += u0.y;
                     sr[t][1] += u1.x; si[t][1] += u1.y;
                 }
+                __syncwarp();
+                if (lane == 0) *fl = 0u;  // consumed: the next launch (stream-ordered, or a graph replay) starts clean
             }
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
@@ -597,7 +598,19 @@ struct DenseEngine {
     bool streamk = false;
     double2 *sk_ws = nullptr;
     unsigned *sk_flags = nullptr;
-    unsigned sk_epoch = 0;
+    // whole-iteration CUDA graph (launch-bound problems): captured the second time an identical iteration is asked for
+    unsigned long long cheb_version = 0;
+    struct GraphKey {
+        unsigned long long cheb_version = ~0ull;
+        const void *ptr[8] = {};
+        bool operator==(const GraphKey &o) const {
+            return cheb_version == o.cheb_version && memcmp(ptr, o.ptr, sizeof(ptr)) == 0;
+        }
+    } graph_key, last_key;
+    cudaGraphExec_t graph_exec = nullptr;
+    long long graph_launches = 0, last_launches = 0;
+    int stable_iterations = 0;
+    long long graph_replays = 0;
 };
 
 namespace {
@@ -621,7 +634,6 @@ bool launch_gemm(DenseEngine *e, const Block &b, GemmParams p, std::string &err)
     p.streamk = e->streamk ? 1 : 0;
     p.ws = e->sk_ws;
     p.flags = e->sk_flags;
-    p.epoch = ++e->sk_epoch;
     dim3 grid(e->streamk ? e->sm_count : e->dp / BM), block(GEMM_THREADS);
     const size_t smem = gemm_smem_bytes();
     static bool attr_set = false;
@@ -891,11 +903,13 @@ void dense_destroy(DenseEngine *e) {
                     e->sk_ws, e->sk_flags};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
     delete e;
 }
 
 void dense_info(DenseEngine *e, krotov_info *out) {
-    out->grid_blocks = e->sparse ? e->dp / SP_ROWS : e->dp / BM;
+    out->grid_blocks = e->sparse ? e->dp / SP_ROWS : (e->streamk ? e->sm_count : e->dp / BM);
+    out->graph_replays = e->graph_replays;
     out->block_threads = e->sparse ? SP_WARPS * 32 : GEMM_THREADS;
     out->nnz_union = e->sparse ? e->nnz_union : e->d * e->d;
     out->ell_width = e->sparse ? e->W : 0;
@@ -911,8 +925,11 @@ bool dense_set_cheby(DenseEngine *e, int direction, int ndtc, const std::vector<
                      const std::vector<double> &E_min, const std::vector<double> &Delta, const std::vector<int> &m,
                      const std::vector<double> &coef, int m_max, const std::vector<cplx> &phase, std::string &err) {
     Cheb &c = e->ch[direction];
+    const bool same = c.set && c.ndtc == ndtc && c.mmax == m_max && c.dtc_of_step == dtc_of_step && c.E_min == E_min &&
+                      c.Delta == Delta && c.m == m && c.coef == coef && c.phase == phase;
     c.ndtc = ndtc; c.mmax = m_max; c.dtc_of_step = dtc_of_step; c.E_min = E_min; c.Delta = Delta; c.m = m;
     c.coef = coef; c.phase = phase; c.set = true;
+    if (!same) e->cheb_version++;  // coefficients travel by value in the launch parameters: a captured iteration is stale now
     for (int v : m)
         if (v < 3) {
             err = "dense path needs at least 3 Chebyshev coefficients per step (Delta * dt too small)";
@@ -940,10 +957,80 @@ bool dense_forward(DenseEngine *e, const double *d_eps, double2 *d_tau, long lon
     return true;
 }
 
+namespace {
+bool iterate_body(DenseEngine *e, const double *d_eps_old, double *d_eps_new, const double *d_alpha,
+                  const double *d_dt, double *d_ga, const double2 *d_chi_coef, double2 *d_tau, std::string &err);
+}
+
+// One Krotov iteration on the block path.  The iteration is a fixed stream of ~20 launches per time step and
+// direction whose parameters do not change between iterations (pulses, chi coefficients, tau live at fixed device
+// addresses) until the Chebyshev tables change, so the second time an identical iteration is asked for it is
+// captured into ONE CUDA graph and replayed from then on.  Measured (tools/gpu_graph_bench.py): dense d = 100, 20
+// trajectories, 3603 launches per iteration: 45.1 -> 36.9 ms; capture + instantiation cost ~9 us per node once, so
+// the graph is built only when two consecutive iterations were identical (tables settled) and the iteration has at
+// most kGraphMaxNodes launches (C5 has 500 000 and is compute-bound anyway).  Not with several ranks (the mailbox
+// parity alternates).
+constexpr long long kGraphMaxNodes = 60000;
+
 bool dense_iterate(DenseEngine *e, const double *d_eps_old, double *d_eps_new, const double *d_alpha,
                    const double *d_dt, double *d_ga, const double2 *d_chi_coef, double2 *d_tau, long long &launches,
                    std::string &err) {
+    DenseEngine::GraphKey key;
+    key.cheb_version = e->cheb_version;
+    const void *ptrs[8] = {d_eps_old, d_eps_new, d_alpha, d_dt, d_ga, d_chi_coef, d_tau, nullptr};
+    memcpy(key.ptr, ptrs, sizeof(ptrs));
+    const bool graph_ok = e->comm.world <= 1 && !getenv("KROTOV_NO_GRAPH");
+    if (graph_ok && e->graph_exec != nullptr && e->graph_key == key) {
+        DK_CHECK(cudaGraphLaunch(e->graph_exec, e->stream));
+        launches += e->graph_launches;
+        e->graph_replays++;
+        e->chi_from_host = false;
+        return true;
+    }
+    if (e->graph_exec != nullptr) {
+        cudaGraphExecDestroy(e->graph_exec);
+        e->graph_exec = nullptr;
+    }
+    const bool capture = graph_ok && e->last_key == key && e->stable_iterations >= 2 && e->last_launches > 0 &&
+                         e->last_launches <= kGraphMaxNodes;
+    if (capture) DK_CHECK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
     e->launches = 0;
+    const bool ok = iterate_body(e, d_eps_old, d_eps_new, d_alpha, d_dt, d_ga, d_chi_coef, d_tau, err);
+    if (capture) {
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
+        if (!ok) {
+            if (graph) cudaGraphDestroy(graph);
+            return false;
+        }
+        if (ce != cudaSuccess || graph == nullptr) {
+            err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce);
+            return false;
+        }
+        const cudaError_t ci = cudaGraphInstantiate(&e->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ci != cudaSuccess) {
+            e->graph_exec = nullptr;
+            err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ci);
+            return false;
+        }
+        e->graph_key = key;
+        e->graph_launches = e->launches;
+        DK_CHECK(cudaGraphLaunch(e->graph_exec, e->stream));
+    } else if (!ok) {
+        return false;
+    }
+    e->stable_iterations = (e->last_key == key) ? e->stable_iterations + 1 : 1;
+    e->last_key = key;
+    e->last_launches = e->launches;
+    e->chi_from_host = false;
+    launches += e->launches;
+    return true;
+}
+
+namespace {
+bool iterate_body(DenseEngine *e, const double *d_eps_old, double *d_eps_new, const double *d_alpha,
+                  const double *d_dt, double *d_ga, const double2 *d_chi_coef, double2 *d_tau, std::string &err) {
     const int N_T = e->N_T;
     // ---- chi(T)
     if (d_chi_coef != nullptr) {
@@ -986,11 +1073,9 @@ bool dense_iterate(DenseEngine *e, const double *d_eps_old, double *d_eps_new, c
         if (!step(e, KROTOV_FORWARD, n, d_eps_new, e->store_fw ? e->PHI + e->slab * (size_t)n : nullptr, err))
             return false;
     }
-    if (!finish_sweep(e, d_tau, err)) return false;
-    e->chi_from_host = false;
-    launches += e->launches;
-    return true;
+    return finish_sweep(e, d_tau, err);
 }
+}  // namespace
 
 bool dense_set_chi(DenseEngine *e, const double *chi_host, std::string &err) {
     std::vector<cplx> blk(e->slab, cplx(0, 0));

@@ -770,3 +770,17 @@ def test_seeded_shape_sweep_vs_oracle(d, n_traj, L, n_grid, functional, hermitia
     ref = O.optimize_krotov(W.to_oracle(w), 2)
     assert np.isfinite(ref["J_T"]).all()
     assert_parity(got, ref["J_T"], ref["pulses"], ref["g_a_int"])
+
+
+def test_block_path_graph_replay_equals_direct_launches(monkeypatch):
+    """The block path captures a settled iteration into one CUDA graph (third identical iteration on) and replays
+    it: same pulses and J_T, bit for bit, as launching every kernel directly."""
+    w = W.dummy_dense(d=48, n_traj=12, n_controls=2, n_grid=41, seed=12)
+    w.specrange = (-4.0, 4.0)  # fixed spectral range: the Chebyshev tables never change, so the graph is used
+    a = run_product(w, 6)
+    assert a["info"]["path"] == 2 and a["info"]["graph_replays"] >= 2
+    monkeypatch.setenv("KROTOV_NO_GRAPH", "1")
+    b = run_product(w, 6)
+    assert b["info"]["graph_replays"] == 0
+    assert np.array_equal(a["pulses"], b["pulses"]) and a["J_T"] == b["J_T"]
+    assert a["info"]["launches_last"] == b["info"]["launches_last"]
