@@ -106,6 +106,9 @@ struct GemmParams {
     // ---- epi 1
     const double2 *CHI;
     double *partial;      // [dp / BM] one entry per row block
+    // ---- operand staging: ONE bulk copy per tile when the operand is tile-contiguous in global memory
+    int a_tiled;          // A is stored tile-major [row block][k chunk][BM][A_STRIDE] (the per-step generator G)
+    int x_contig;         // ld == 8 NT + 2: the BK rows of a B tile are one contiguous piece (single column block)
     // ---- stream-K (grid = SM count > row blocks): partial tiles and their ready flags
     int streamk;
     double2 *ws;          // [dp / BM][kSkParts][BM * 64]
@@ -141,7 +144,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dense_gemm_kernel(const __gri
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nk = p.dp / BK;
     constexpr uint32_t X_ROW_BYTES = NT * 8 * 16;
-    constexpr uint32_t STAGE_BYTES = BM * BK * 16 + BK * X_ROW_BYTES;
+    // shared-memory row stride of the B tile: the global leading dimension when the tile arrives in one piece
+    const int xs = p.x_contig ? NT * 8 + 2 : X_STRIDE;
+    const uint32_t a_bytes = p.a_tiled ? BM * A_STRIDE * 16 : BM * BK * 16;
+    const uint32_t x_bytes = p.x_contig ? BK * (NT * 8 + 2) * 16 : BK * X_ROW_BYTES;
+    const uint32_t STAGE_BYTES = a_bytes + x_bytes;
     // Work of this CTA: a contiguous range of (row block, k chunk) pairs.  Classic launch: one whole row block.
     // Stream-K launch (as many CTAs as SMs, more than row blocks): total / G chunks each, so a row block is shared by
     // the CTAs whose ranges meet inside it.  The CTA that holds a row block's LAST chunk owns it: it adds the partial
@@ -187,8 +194,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dense_gemm_kernel(const __gri
                 double2 *Xs = As + A_STAGE_WORDS;
                 if (lane == 0) mbar_expect_tx(&full[s], STAGE_BYTES);
                 __syncwarp();
-                bulk_g2s(As + lane * A_STRIDE, p.A + (size_t)(row0 + lane) * p.dp + (size_t)kc * BK, BK * 16, &full[s]);
-                bulk_g2s(Xs + lane * X_STRIDE, p.B + (size_t)(kc * BK + lane) * p.ld + p.col0, X_ROW_BYTES, &full[s]);
+                // a bulk copy costs the copy engine ~50 cycles whatever its size: 64 row-sized copies per stage kept
+                // the GEMM at 1.2 TB/s of generator however few columns it had; tile-contiguous operands need two
+                if (p.a_tiled) {
+                    if (lane == 0) bulk_g2s(As, p.A + ((size_t)rb * nk + kc) * (BM * A_STRIDE), a_bytes, &full[s]);
+                } else {
+                    bulk_g2s(As + lane * A_STRIDE, p.A + (size_t)(row0 + lane) * p.dp + (size_t)kc * BK, BK * 16, &full[s]);
+                }
+                if (p.x_contig) {
+                    if (lane == 1) bulk_g2s(Xs, p.B + (size_t)(kc * BK) * p.ld, x_bytes, &full[s]);
+                } else {
+                    bulk_g2s(Xs + lane * X_STRIDE, p.B + (size_t)(kc * BK + lane) * p.ld + p.col0, X_ROW_BYTES, &full[s]);
+                }
             }
         }
         return;
@@ -208,14 +225,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dense_gemm_kernel(const __gri
             const int s = it % STAGES;
             mbar_wait(&full[s], (it / STAGES) & 1);
             const double2 *As = ring + (size_t)s * STAGE_WORDS + (warp * 8 + fr) * A_STRIDE + fk;
-            const double2 *Xs = ring + (size_t)s * STAGE_WORDS + A_STAGE_WORDS + fk * X_STRIDE + fr;
+            const double2 *Xs = ring + (size_t)s * STAGE_WORDS + A_STAGE_WORDS + fk * xs + fr;
 #pragma unroll
             for (int ks = 0; ks < BK / 4; ++ks) {
                 const double2 a = As[ks * 4];
                 const double nai = -a.y;
 #pragma unroll
                 for (int t = 0; t < NT; ++t) {
-                    const double2 x = Xs[(ks * 4) * X_STRIDE + t * 8];
+                    const double2 x = Xs[(ks * 4) * xs + t * 8];
                     dmma(cr[t][0], cr[t][1], a.x, x.x);
                     dmma(cr[t][0], cr[t][1], nai, x.y);
                     dmma(ci[t][0], ci[t][1], a.x, x.y);
@@ -340,7 +357,9 @@ __global__ void build_G_kernel(double2 *G, const double2 *H, int dp, int L, doub
             h.x = fma(e[l], hl.x, h.x);
             h.y = fma(e[l], hl.y, h.y);
         }
-        G[i] = make_double2(f.x * h.x - f.y * h.y, f.x * h.y + f.y * h.x);
+        // tile-major [row block][k chunk][BM][A_STRIDE]: exactly the shared-memory image of a GEMM stage
+        const size_t dst = ((r / BM) * (size_t)(dp / BK) + c / BK) * (BM * A_STRIDE) + (r % BM) * A_STRIDE + (c % BK);
+        G[dst] = make_double2(f.x * h.x - f.y * h.y, f.x * h.y + f.y * h.x);
     }
 }
 
@@ -594,7 +613,9 @@ struct DenseEngine {
     double2 *Pvf = nullptr, *Pvb = nullptr, *Gv = nullptr;  // [g][1+L][dp*W], [g][dp*W]
     std::vector<int> sp_part_off;  // offset of every column block's CTA partials
     int nnz_union = 0;
-    // stream-K GEMM (fewer row blocks than SMs): partial tiles, ready flags, launch epoch
+    bool x_contig = false;   // single column block stored with ld = 8 nt + 2: a B tile is one bulk copy
+    size_t gmat = 0;         // elements of one tile-major generator: (dp/BM) (dp/BK) BM A_STRIDE
+    // stream-K GEMM (fewer row blocks than SMs): partial tiles, ready flags
     bool streamk = false;
     double2 *sk_ws = nullptr;
     unsigned *sk_flags = nullptr;
@@ -632,6 +653,7 @@ bool launch_gemm(DenseEngine *e, const Block &b, GemmParams p, std::string &err)
     p.ld = e->ld;
     p.col0 = b.col0;
     p.streamk = e->streamk ? 1 : 0;
+    p.x_contig = e->x_contig ? 1 : 0;
     p.ws = e->sk_ws;
     p.flags = e->sk_flags;
     dim3 grid(e->streamk ? e->sm_count : e->dp / BM), block(GEMM_THREADS);
@@ -692,7 +714,7 @@ bool step(DenseEngine *e, int dir, int n, const double *d_eps, double2 *store, s
             e->launches++;
             continue;
         }
-        build_G_kernel<<<e->sm_count * 4, 256, 0, e->stream>>>(e->G + (size_t)g * mat, H + (size_t)g * (1 + e->L) * mat,
+        build_G_kernel<<<e->sm_count * 4, 256, 0, e->stream>>>(e->G + (size_t)g * e->gmat, H + (size_t)g * (1 + e->L) * mat,
                                                              e->dp, e->L, f, beta, d_eps, e->N_T, n);
         e->launches++;
     }
@@ -711,7 +733,8 @@ bool step(DenseEngine *e, int dir, int n, const double *d_eps, double2 *store, s
         for (int j = 1; j < m; ++j) {
             GemmParams p;
             memset(&p, 0, sizeof(p));
-            p.A = e->G + (size_t)b.g * mat;
+            p.A = e->G + (size_t)b.g * e->gmat;
+            p.a_tiled = 1;
             p.B = vprev;
             p.epi = 0;
             p.Vold = vprev2;
@@ -775,6 +798,11 @@ DenseEngine *dense_create(int d, int N, int L, int N_T, int n_gen, const std::ve
         }
     }
     e->ld = col;
+    // one column block (one generator, <= 64 trajectories): two pad columns make the global row stride equal to the
+    // conflict-free shared-memory stride, so the BK rows of a GEMM operand tile are ONE contiguous bulk copy
+    e->x_contig = sp == nullptr && e->blocks.size() == 1 && !getenv("KROTOV_NO_TILED");
+    if (e->x_contig) e->ld = col + 2;
+    e->gmat = (size_t)(e->dp / BM) * (e->dp / BK) * BM * A_STRIDE;
     e->traj_of_col.assign(e->ld, -1);
     for (int k = 0; k < N; ++k) e->traj_of_col[e->col_of_traj[k]] = k;
     e->slab = (size_t)e->dp * e->ld;
@@ -813,7 +841,7 @@ DenseEngine *dense_create(int d, int N, int L, int N_T, int n_gen, const std::ve
         delete e;
         return nullptr;
     }
-    bool ok = dalloc(e->Hf, (size_t)n_gen * (1 + L) * mat, err) && dalloc(e->G, (size_t)n_gen * mat, err) &&
+    bool ok = dalloc(e->Hf, (size_t)n_gen * (1 + L) * mat, err) && dalloc(e->G, (size_t)n_gen * e->gmat, err) &&
               dalloc(e->V[0], e->slab, err) && dalloc(e->V[1], e->slab, err) && dalloc(e->V[2], e->slab, err) &&
               dalloc(e->OUT, e->slab, err) && dalloc(e->PSI, e->slab, err) && dalloc(e->PSI0, e->slab, err) &&
               dalloc(e->TGT, e->slab, err) && dalloc(e->CHI, e->slab, err) &&
