@@ -230,13 +230,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dense_gemm_kernel(const __gri
             for (int ks = 0; ks < BK / 4; ++ks) {
                 const double2 a = As[ks * 4];
                 const double nai = -a.y;
+                // two passes over the column tiles: the two DMMAs that feed one accumulator are 2 NT - 1 instructions
+                // apart instead of back to back (the asm statements are volatile: this IS the issue order)
+                double2 x[NT];
+#pragma unroll
+                for (int t = 0; t < NT; ++t) x[t] = Xs[(ks * 4) * xs + t * 8];
 #pragma unroll
                 for (int t = 0; t < NT; ++t) {
-                    const double2 x = Xs[(ks * 4) * xs + t * 8];
-                    dmma(cr[t][0], cr[t][1], a.x, x.x);
-                    dmma(cr[t][0], cr[t][1], nai, x.y);
-                    dmma(ci[t][0], ci[t][1], a.x, x.y);
-                    dmma(ci[t][0], ci[t][1], a.y, x.x);
+                    dmma(cr[t][0], cr[t][1], a.x, x[t].x);
+                    dmma(ci[t][0], ci[t][1], a.x, x[t].y);
+                }
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    dmma(cr[t][0], cr[t][1], nai, x[t].y);
+                    dmma(ci[t][0], ci[t][1], a.y, x[t].x);
                 }
             }
             __syncwarp();
