@@ -195,7 +195,7 @@ int krotov_get_profile(krotov_handle h, int cta, int64_t *out);
  * (src/optimize.jl:340-349).  Each rank exports an IPC descriptor of its mailbox; after the
  * descriptors of all ranks have been gathered (any transport), krotov_comm_connect maps the
  * peers' mailboxes and the forward sweep exchanges partial sums in-kernel over NVLink. */
-#define KROTOV_COMM_DESC_BYTES 128
+#define KROTOV_COMM_DESC_BYTES 192
 int krotov_comm_export(krotov_handle h, void *desc /* KROTOV_COMM_DESC_BYTES */);
 int krotov_comm_connect(krotov_handle h, int rank, int world, const void *descs /* [world][DESC_BYTES] */);
 

@@ -18,7 +18,7 @@ GEN_DENSE_COLMAJOR, GEN_CSR = 0, 1
 FORWARD, BACKWARD = 0, 1
 CHI_HOST, CHI_SM, CHI_SS, CHI_RE = 0, 1, 2, 3
 PATH_WARP, PATH_DENSE, PATH_SPARSE = 1, 2, 3
-COMM_DESC_BYTES = 128
+COMM_DESC_BYTES = 192
 
 # every symbol include/krotov_cuda.h declares (tests check the .so exports all of them)
 EXPORTS = [

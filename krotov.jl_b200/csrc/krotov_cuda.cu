@@ -29,6 +29,8 @@
 
 using cplx = std::complex<double>;
 
+constexpr int kXaccMaxStride = 16;  // accumulator words of the cross-rank sum at most one 128-byte line apart
+
 namespace {
 
 thread_local std::string g_create_error = "";
@@ -107,6 +109,8 @@ struct krotov_handle_s {
     // comm
     int rank = 0, world = 1;
     double *peer_mbox[2][kr::kMaxRanks] = {};
+    size_t mail_bytes = 0, xacc_bytes = 0;  // d_mbox[par] = mailboxes (sentinel-filled) followed by the cross-rank accumulators (zero-filled)
+    int total_ctas = 0;  // CTAs of all ranks (krotov_comm_connect)
     bool peer_opened[kr::kMaxRanks] = {};
     long long iter_count = 0;
     // dense path
@@ -493,6 +497,12 @@ int launch_warp(krotov_handle h, int mode) {
     if (const char *e = getenv("KROTOV_MBOX_ALL")) p.mbox_all = atoi(e);
     const int par = (int)(h->iter_count & 1);
     for (int r = 0; r < h->world && r < kr::kMaxRanks; ++r) p.mbox[r] = h->peer_mbox[par][r];
+    // one-hop cross-rank sum (every CTA adds into every rank's accumulator): same decision on every rank
+    p.total_ctas = h->total_ctas;
+    p.xacc_stride = 1;
+    if (const char *e = getenv("KROTOV_XACC_STRIDE")) p.xacc_stride = std::max(1, std::min(kXaccMaxStride, atoi(e)));
+    if (h->world > 1 && h->xacc_bytes && h->total_ctas <= kr::kXMaxArrivals && !getenv("KROTOV_NO_XACC"))
+        for (int r = 0; r < h->world; ++r) p.xacc[r] = (unsigned long long *)((char *)h->peer_mbox[par][r] + h->mail_bytes);
     p.err_flag = (int *)h->d_err.p;
     p.prof = (long long *)h->d_prof.p;
     p.timeout_cycles = 20000000000ll;  // ~10 s
@@ -766,9 +776,13 @@ int krotov_create(const krotov_problem *pb, krotov_handle *out) {
     cudaMemset(h->d_err.p, 0, 16);
     cudaMemset(h->d_tau.p, 0, (size_t)N * 16);
     // peer mailboxes for the per-time-step exchange between ranks: [N_T][L][rank], one per iteration parity
+    // behind them (warp path): the accumulators of the one-hop cross-rank sum, word stride up to one 128-byte line
+    h->mail_bytes = (size_t)N_T * kr::kMaxRanks * L * 8;
+    h->xacc_bytes = (path == KROTOV_PATH_WARP && L * kr::kXLimbs <= 32) ? (size_t)N_T * L * kr::kXLimbs * kXaccMaxStride * 8 : 0;
     for (int par = 0; par < 2; ++par) {
-        if ((rc = dev_alloc(h, h->d_mbox[par], (size_t)N_T * kr::kMaxRanks * L * 8))) return bail(rc);
-        cudaMemset(h->d_mbox[par].p, 0xFF, h->d_mbox[par].bytes);
+        if ((rc = dev_alloc(h, h->d_mbox[par], h->mail_bytes + h->xacc_bytes))) return bail(rc);
+        cudaMemset(h->d_mbox[par].p, 0xFF, h->mail_bytes);
+        if (h->xacc_bytes) cudaMemset((char *)h->d_mbox[par].p + h->mail_bytes, 0, h->xacc_bytes);
         h->peer_mbox[par][0] = (double *)h->d_mbox[par].p;
     }
 
@@ -1019,7 +1033,8 @@ int krotov_iterate(krotov_handle h, const double *guess_pulses, double *new_puls
     if (h->world > 1) {
         // the mailbox of the NEXT iteration's parity is cleared now (peers are at most one iteration ahead)
         const int nxt = (int)((h->iter_count + 1) & 1);
-        KR_CUDA(h, cudaMemsetAsync(h->d_mbox[nxt].p, 0xFF, h->d_mbox[nxt].bytes, h->stream));
+        KR_CUDA(h, cudaMemsetAsync(h->d_mbox[nxt].p, 0xFF, h->mail_bytes, h->stream));
+        if (h->xacc_bytes) KR_CUDA(h, cudaMemsetAsync((char *)h->d_mbox[nxt].p + h->mail_bytes, 0, h->xacc_bytes, h->stream));
     }
     if (h->path == KROTOV_PATH_WARP) {
         if (h->nCTA > 1 || h->world > 1) KR_CUDA(h, cudaMemsetAsync(h->d_R.p, 0xFF, h->d_R.bytes, h->stream));
@@ -1116,7 +1131,10 @@ int krotov_get_profile(krotov_handle h, int cta, int64_t *out) {
 struct CommDesc {
     cudaIpcMemHandle_t mh[2];
 };
-static_assert(sizeof(CommDesc) <= KROTOV_COMM_DESC_BYTES, "descriptor too large");
+struct CommDescTail {  // behind the handles, in the descriptor's spare bytes
+    int nCTA;
+};
+static_assert(sizeof(CommDesc) + sizeof(CommDescTail) <= KROTOV_COMM_DESC_BYTES, "descriptor too large");
 
 int krotov_comm_export(krotov_handle h, void *desc) {
     if (!h || !desc) return KROTOV_ERR_ARG;
@@ -1126,6 +1144,8 @@ int krotov_comm_export(krotov_handle h, void *desc) {
     for (int par = 0; par < 2; ++par) KR_CUDA(h, cudaIpcGetMemHandle(&cd.mh[par], h->d_mbox[par].p));
     memset(desc, 0, KROTOV_COMM_DESC_BYTES);
     memcpy(desc, &cd, sizeof(cd));
+    CommDescTail tail{h->path == KROTOV_PATH_WARP ? h->nCTA : 0};
+    memcpy((char *)desc + sizeof(cd), &tail, sizeof(tail));
     return KROTOV_OK;
 }
 
@@ -1135,6 +1155,12 @@ int krotov_comm_connect(krotov_handle h, int rank, int world, const void *descs)
     cudaSetDevice(h->device);
     h->rank = rank;
     h->world = world;
+    h->total_ctas = 0;
+    for (int r = 0; r < world; ++r) {
+        CommDescTail tail;
+        memcpy(&tail, (const char *)descs + (size_t)r * KROTOV_COMM_DESC_BYTES + sizeof(CommDesc), sizeof(tail));
+        h->total_ctas += tail.nCTA;
+    }
     for (int r = 0; r < world; ++r) {
         if (r == rank) {
             for (int par = 0; par < 2; ++par) h->peer_mbox[par][r] = (double *)h->d_mbox[par].p;

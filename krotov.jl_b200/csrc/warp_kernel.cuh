@@ -75,6 +75,10 @@ struct WarpParams {
     int mbox_all;              // several ranks: 1 = every CTA polls the rank's mailbox, 0 = the reducer polls it and broadcasts through E
     int rank, world;
     double *mbox[kMaxRanks];   // mailbox of every rank (this iteration's parity): [N_T][world][L]
+    unsigned long long *xacc[kMaxRanks];  // several ranks, one-hop sum: fixed-point accumulators of EVERY rank (this
+                               // iteration's parity, zero-filled): word (n, l, limb) at [((n*L + l)*4 + limb) * xacc_stride]
+    int xacc_stride;           // distance between accumulator words in 8-byte units (1: one line per step, 16: one line per word)
+    int total_ctas;            // CTAs of all ranks = arrivals per accumulator word
     int *err_flag;
     long long timeout_cycles;
     long long *prof;           // optional [nCTA][8] cycle counters (KROTOV_PROF=1), see krotov_get_profile
@@ -420,6 +424,107 @@ __device__ __forceinline__ bool atomic_grid_sum(unsigned long long *An, const in
     return true;
 }
 
+// ---- the same sum across SEVERAL ranks in one NVLink hop ---------------------------------------------------------
+// Every CTA of every rank adds its fixed-point partial into the step's accumulator of EVERY rank (local L2 atomics and
+// `red.add.u64` over NVLink into the peers' memory, fire and forget) and polls only its own rank's copy until it carries
+// the arrivals of all CTAs of all ranks.  All copies receive the same set of integer adds, so every rank rounds the
+// same exact sum: bit-identical pulses on all replicas without a reducer, a rank-ordered sum or a broadcast hop
+// (CTA -> local reducer -> peers' mailboxes -> everybody becomes CTA -> everybody).  Up to 2047 arrivals: the number
+// is 117 bits wide (unit 2^-88, bias 2^116, |partial| < 2^28) in four 30-bit limbs; word = limb sum (41 bits) |
+// "does not fit" count (11 bits) | arrival count (12 bits).  A misfit makes every CTA of every rank redo the step
+// with the mailbox protocol below (same verdict everywhere, because it is read from the same sums).
+constexpr int kXLimbBits = 30, kXLimbs = 4, kXBiasBit = 116, kXMisShift = 41, kXCntShift = 52, kXMaxArrivals = 2047;
+
+__device__ __forceinline__ bool fixx_from_double(const double x, unsigned __int128 &biased) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(fabs(x));
+    const int ebits = (int)(bits >> 52);
+    if (ebits >= 1023 + (kXBiasBit - kFixFrac)) return false;  // |x| >= 2^28, Inf or NaN
+    const unsigned long long mant = (bits & 0xFFFFFFFFFFFFFull) | (ebits ? (1ull << 52) : 0ull);
+    const int shift = (ebits ? ebits : 1) - 1075 + kFixFrac;
+    unsigned __int128 mag = 0;
+    if (shift >= 0)
+        mag = (unsigned __int128)mant << shift;
+    else if (shift > -64)
+        mag = mant >> (-shift);
+    const unsigned __int128 bias = (unsigned __int128)1 << kXBiasBit;
+    biased = (x < 0.0) ? bias - mag : bias + mag;
+    return true;
+}
+
+__device__ __forceinline__ double fix_mag_to_double(const unsigned __int128 mag, const bool neg) {
+    const unsigned long long hi = (unsigned long long)(mag >> 64), lo = (unsigned long long)mag;
+    double d;
+    if (hi == 0) {
+        d = __ull2double_rn(lo);
+    } else {
+        const int sh = 64 - __clzll((long long)hi);
+        unsigned long long top = (sh == 64) ? hi : ((hi << (64 - sh)) | (lo >> sh));
+        const unsigned long long lost = (sh == 64) ? lo : (lo << (64 - sh));
+        if (lost) top |= 1ull;
+        d = scalbn(__ull2double_rn(top), sh);
+    }
+    d = scalbn(d, -kFixFrac);
+    return neg ? -d : d;
+}
+
+__device__ __forceinline__ void red_add_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ bool xrank_atomic_sum(const WarpParams &p, const int n, const int L, const int lane,
+                                                 double (&tot)[kMaxCtrl]) {
+    const int nw = L * kXLimbs;  // <= 32: lane q owns word q = (control q / 4, limb q % 4)
+    const int myl = lane / kXLimbs, myj = lane - myl * kXLimbs;
+    double mine = 0.0;
+#pragma unroll
+    for (int l = 0; l < kMaxCtrl; ++l)
+        if (l == myl) mine = tot[l];
+    const size_t off = ((size_t)n * nw + (lane < nw ? lane : 0)) * (size_t)p.xacc_stride;
+    if (lane < nw) {
+        unsigned __int128 v;
+        const bool ok = fixx_from_double(mine, v);
+        unsigned long long add = 1ull << kXCntShift;
+        if (ok)
+            add += (unsigned long long)(v >> (myj * kXLimbBits)) & ((1ull << kXLimbBits) - 1);
+        else
+            add += 1ull << kXMisShift;
+        for (int i = 1; i <= p.world; ++i) {  // peers first (the long way), own copy last
+            int r = p.rank + i;
+            if (r >= p.world) r -= p.world;
+            red_add_sys_u64(p.xacc[r] + off, add);
+        }
+    }
+    const long long t0 = clock64();
+    int spins = 0;
+    unsigned long long w = 0;
+    const double *mine_p = reinterpret_cast<const double *>(p.xacc[p.rank] + off);
+    for (;;) {
+        if (lane < nw) w = ld_poll_u64<true>(mine_p);
+        const bool pending = lane < nw && (int)(w >> kXCntShift) != p.total_ctas;
+        if (!__any_sync(0xffffffffu, pending)) break;
+        if ((++spins & 63) == 0) {
+            if (clock64() - t0 > p.timeout_cycles || *(volatile int *)p.err_flag) {
+                atomicExch(p.err_flag, 1);
+                break;
+            }
+        }
+    }
+    const bool misfit = lane < nw && ((w >> kXMisShift) & 0x7FF) != 0;
+    if (__any_sync(0xffffffffu, misfit)) return false;
+    const int src = (lane < L ? lane : 0) * kXLimbs;
+    const unsigned long long mask = (1ull << kXMisShift) - 1;
+    unsigned __int128 sum = 0;
+#pragma unroll
+    for (int j = 0; j < kXLimbs; ++j)
+        sum += (unsigned __int128)(__shfl_sync(0xffffffffu, w, src + j) & mask) << (j * kXLimbBits);
+    const unsigned __int128 bias = (unsigned __int128)p.total_ctas << kXBiasBit;
+    const bool neg = sum < bias;
+    const double du = fix_mag_to_double(neg ? bias - sum : sum - bias, neg);
+#pragma unroll
+    for (int l = 0; l < kMaxCtrl; ++l) tot[l] = __shfl_sync(0xffffffffu, du, l < L ? l : 0);
+    return true;
+}
+
 // The communication warp of a CTA (shared by both kernel variants): per time step it waits for the CTA's
 // per-lane partial overlaps (named barrier 1), reduces them in a fixed order, runs the grid / rank exchange,
 // applies the pulse update (src/optimize.jl:351-358) and releases the trajectory warps (named barrier 2).
@@ -455,7 +560,11 @@ __device__ __forceinline__ void comm_warp_run(const WarpParams &p, const int L, 
         }
         const long long c2 = clock64();
         bool summed = false;
-        if (p.world > 1) {
+        if (p.world > 1 && p.xacc[0] != nullptr) {
+            summed = xrank_atomic_sum(p, n, L, lane, tot);
+            if (!summed && blockIdx.x == 0 && lane == 0) atomicAdd(p.err_flag + 1, 1);  // krotov_info.fallback_steps
+        }
+        if (p.world > 1 && !summed) {
             // ---- several ranks.  Every CTA adds its partial into the rank's fixed-point accumulator (and leaves it in
             // R for the fallback); the reducer (CTA 0) alone waits for the exact rank sum, pushes it into the mailbox
             // of EVERY rank over NVLink, and every CTA of every rank polls its own rank's mailbox and adds the
@@ -495,7 +604,7 @@ __device__ __forceinline__ void comm_warp_run(const WarpParams &p, const int L, 
                 }
             }
             summed = true;
-        } else if (p.acc != nullptr && p.nCTA > 1) {
+        } else if (p.world == 1 && p.acc != nullptr && p.nCTA > 1) {
             summed = atomic_grid_sum(p.acc + (size_t)n * L * kFixLimbs, p.nCTA, L, lane, tot, p.err_flag, p.timeout_cycles);
             if (!summed && blockIdx.x == 0 && lane == 0) atomicAdd(p.err_flag + 1, 1);  // krotov_info.fallback_steps
         }

@@ -1,4 +1,6 @@
-"""Two ranks on two GPUs: trajectories sharded, per-step overlap sums exchanged in-kernel over NVLink mailboxes.
+"""Two ranks on two GPUs: trajectories sharded, per-step overlap sums exchanged in-kernel over NVLink -- by the
+one-hop fixed-point sum (every CTA adds into every rank's accumulator) and by the mailbox protocol (rank sums pushed
+into the peers' mailboxes; `KROTOV_NO_XACC=1`, also the dense path's protocol).
 Needs >= 2 CUDA devices (skipped on the single-GPU box); run with `gpurun --gpus 2`."""
 import os
 
@@ -16,8 +18,21 @@ def _make(kind, n_samples, n_grid):
     return W.dummy_dense(d=64, n_traj=n_samples, n_controls=2, n_grid=n_grid, functional=kind, seed=5)
 
 
-def _worker(rank, world, port, kind, n_samples, n_grid, iters, q):
+_BIG = 1e13
+
+
+def _big_chi(states, trajectories, tau=None):
+    """chi of J_T_sm scaled by 1e13 (with lambda_a scaled alike the optimisation is unchanged, but the overlap sums
+    leave the fixed-point range of the one-hop sums)."""
+    n = len(trajectories)
+    s = sum(t.weight * x for t, x in zip(trajectories, tau))
+    return [_BIG * (t.weight / n**2) * s * t.target_state for t in trajectories]
+
+
+def _worker(rank, world, port, kind, n_samples, n_grid, iters, q, env=None):
     import sys
+
+    os.environ.update(env or {})
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, root)
@@ -38,19 +53,27 @@ def _worker(rank, world, port, kind, n_samples, n_grid, iters, q):
         hist = {"J_T": [], "shard": None}
 
         def cb(wrk, it, eps_new, eps_old):
+            hist["fallback"] = hist.get("fallback", 0) + wrk.engine.info()["fallback_steps"]
             hist["J_T"].append(wrk.result.J_T)
             hist["pulses"] = np.array([np.array(e) for e in eps_new])
             hist["shard"] = wrk._shard
             hist["ga"] = np.array(wrk.g_a_int)
 
-        res = K.optimize(to_problem(w, iter_stop=iters, callback=cb, device=rank), method=K.Krotov, comm=comm)
-        q.put((rank, hist["J_T"], hist["pulses"], hist["shard"], res.message, np.array(res.states), hist["ga"]))
+        extra = {}
+        if (env or {}).get("TEST_BIG_CHI"):
+            extra = dict(chi=_big_chi, lambda_a=_BIG * w.lambda_a)
+        res = K.optimize(to_problem(w, iter_stop=iters, callback=cb, device=rank, **extra), method=K.Krotov, comm=comm)
+        q.put((rank, hist["J_T"], hist["pulses"], hist["shard"], res.message, np.array(res.states), hist["ga"],
+               hist["fallback"]))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kind,n_samples,n_grid", [("c4", 8, 201), ("c4", 64, 101), ("sm", 20, 21), ("ss", 9, 21)])
-def test_two_ranks_match_single_gpu(kind, n_samples, n_grid):
+@pytest.mark.parametrize("kind,n_samples,n_grid,env", [
+    ("c4", 8, 201, {}), ("c4", 64, 101, {}), ("c4", 64, 101, {"KROTOV_XACC_STRIDE": "16"}),
+    ("c4", 8, 201, {"KROTOV_NO_XACC": "1"}), ("c4", 64, 101, {"KROTOV_NO_XACC": "1"}),
+    ("c4", 8, 41, {"TEST_BIG_CHI": "1"}), ("sm", 20, 21, {}), ("ss", 9, 21, {})])
+def test_two_ranks_match_single_gpu(kind, n_samples, n_grid, env):
     """kind c4: warp path (in-kernel reducer exchange); kinds sm/ss: dense DMMA path (exchange in update_kernel)."""
     import torch
 
@@ -64,14 +87,14 @@ def test_two_ranks_match_single_gpu(kind, n_samples, n_grid):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29700 + os.getpid() % 1000
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, kind, n_samples, n_grid, iters, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, kind, n_samples, n_grid, iters, q, env)) for r in range(2)]
     for p in procs:
         p.start()
     out = sorted([q.get(timeout=300) for _ in procs], key=lambda t: t[0])
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (r0, J0, P0, s0, m0, st0, ga0), (r1, J1, P1, s1, m1, st1, ga1) = out
+    (r0, J0, P0, s0, m0, st0, ga0, fb0), (r1, J1, P1, s1, m1, st1, ga1, fb1) = out
     assert m0 == m1 == "Reached maximum number of iterations"
     n_traj = 4 * n_samples if kind == "c4" else n_samples
     assert s0 == (0, n_traj // 2) and s1 == (n_traj // 2, n_traj)
@@ -81,3 +104,8 @@ def test_two_ranks_match_single_gpu(kind, n_samples, n_grid):
     assert np.abs(np.array(J0) - np.array(single["J_T"])).max() < 1e-12
     assert np.abs(P0 - single["pulses"]).max() < 1e-12
     assert np.abs(st0 - np.array(single["result"].states)).max() < 1e-11
+    if env.get("TEST_BIG_CHI"):
+        # partials beyond 2^28: every CTA of both ranks redid those steps with the mailbox protocol
+        assert fb0 > n_grid // 2 and fb1 > n_grid // 2
+    elif kind == "c4":
+        assert fb0 == 0 and fb1 == 0

@@ -1,0 +1,46 @@
+"""Ad-hoc: in-kernel cycle counters of the multi-rank exchange variants (run under torchrun, KROTOV_PROF=1).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29556 tools/gpu_mg_prof.py [samples]
+"""
+import os, sys
+os.environ["KROTOV_PROF"] = "1"
+sys.path.insert(0, "tests"); sys.path.insert(0, ".")
+import torch
+import torch.distributed as dist
+from util import *  # noqa
+from krotov_jl_b200.distributed import Comm
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+comm = Comm(device=local)
+ns = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+w = W.c4_ensemble(n_samples=ns)
+ghz = 1.965
+variants = [("xacc stride 1", {"KROTOV_XACC_STRIDE": "1"}), ("xacc stride 16", {"KROTOV_XACC_STRIDE": "16"}),
+            ("mailbox", {"KROTOV_NO_XACC": "1"})]
+for name, env in variants:
+    for k in ("KROTOV_XACC_STRIDE", "KROTOV_NO_XACC"):
+        os.environ.pop(k, None)
+    os.environ.update(env)
+    out = {"ms": []}
+
+    def cb(wrk, it, a, b):
+        if it >= 1:
+            info = wrk.engine.info()
+            out["ms"].append(info["ms_last"])
+            out["info"] = info
+            out["all"] = [wrk.engine.profile(c) for c in range(info["grid_blocks"])]
+
+    K.optimize(to_problem(w, iter_stop=4, callback=cb, device=local), method=K.Krotov, comm=comm)
+    comm.barrier()
+    f = lambda v: v / ghz / 1e3 / w.N_T
+    lines = [f"[rank {rank}] {name}: grid={out['info']['grid_blocks']}x{out['info']['block_threads']} ms={['%.2f' % m for m in out['ms']]} fallback={out['info'].get('fallback_steps')}"]
+    for key in ["backward", "forward", "overlap", "wait_pulse", "fw_step_total", "comm_wait_partials", "comm_reduce", "comm_gather"]:
+        vals = np.array([f(a[key]) for a in out["all"]])
+        lines.append(f"      {key:18s} cta0={vals[0]:.3f} all: min={vals.min():.3f} mean={vals.mean():.3f} max={vals.max():.3f} us/step")
+    for r in range(world):
+        if r == rank:
+            print("\n".join(lines), flush=True)
+        comm.barrier()
+dist.destroy_process_group()
