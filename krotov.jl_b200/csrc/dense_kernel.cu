@@ -22,6 +22,8 @@
 // the pulse value never visits the host.
 #include "dense_kernel.cuh"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -580,6 +582,318 @@ __global__ void build_G_sparse_kernel(double2 *Gv, const double2 *Pv, size_t nsl
     }
 }
 
+// ============================================================================ persistent sweep, sparse generators
+// The launch-per-term stream above costs ~14 us per Chebyshev term on mid-sized problems whose SpMM takes 3-6 us
+// (profiles/r1_sparse_vs_dense.txt: 10 spins, d = 1024: 265 us per time step for 19 launches).  This kernel runs a
+// whole Krotov iteration (or the plain forward sweep) of the sparse path in ONE cooperative launch: every warp owns
+// a fixed set of (4 rows x 32 columns) items for the whole sweep, builds the generator values of its rows once per
+// time step from the pulse values into shared memory (no build_G pass, no G in global memory), and the Chebyshev
+// terms are separated by grid barriers (the only thing a term needs from other CTAs is V_{j-1}).  The per-step
+// overlap sums go through one more barrier: CTA partials, then every CTA adds them in the same fixed order, so all
+// CTAs hold the same new pulse value without a broadcast.  Same state blocks, storage and arithmetic per element as
+// spmm_kernel / build_G_sparse_kernel / update_kernel (the overlap sums differ in summation order only).
+struct SweepParams {
+    int dp, ld, W, L, N_T, n_blocks, n_items, mode, store_fw, K;  // K = items per warp (shared-memory slots)
+    int cg_sync;               // 1 = cooperative-groups grid.sync() instead of the counter barrier
+    unsigned *bar;             // barrier counter (zeroed before the launch)
+    const int *cols;           // [dp][W]
+    const double2 *Pv[2];      // per direction: [g][1+L][dp*W]
+    const int *blk;            // [n_blocks][4]: generator, first column, columns, first item
+    const double *coef[2];     // [g][ndtc][mmax]
+    const int *m[2];           // [g][ndtc]
+    const double2 *phase[2];   // [g][ndtc]
+    const int *dtc[2];         // [N_T]
+    const double *E_min[2], *Delta[2];  // [g]
+    int ndtc[2], mmax[2];
+    double2 *PSI, *V[3], *OUT, *X, *PHI;
+    const double2 *PSI0, *CHI;
+    size_t slab;
+    const double *eps_old, *alpha, *dt;
+    double *eps_new, *ga;
+    double *partial;           // [L][gridDim.x]
+};
+
+struct SweepItem {
+    int b, g, row0, ncols, c;  // column block, generator, first row, columns of the block, this lane's column
+    size_t cbase;
+    bool valid, cvalid;
+};
+
+template <int R>
+__device__ __forceinline__ SweepItem sweep_item(const SweepParams &p, const int it, const int lane) {
+    SweepItem r;
+    r.valid = it < p.n_items;
+    int b = 0;
+    if (r.valid)
+        while (b + 1 < p.n_blocks && p.blk[(b + 1) * 4 + 3] <= it) ++b;
+    r.b = b;
+    r.g = p.blk[b * 4 + 0];
+    r.ncols = p.blk[b * 4 + 2];
+    const int local = r.valid ? it - p.blk[b * 4 + 3] : 0;
+    const int rgs = p.dp / R;
+    const int cg_ = local / rgs;
+    r.row0 = (local - cg_ * rgs) * R;
+    r.c = cg_ * 32 + lane;
+    r.cvalid = r.valid && r.c < r.ncols;
+    r.cbase = (size_t)p.blk[b * 4 + 1] + (r.cvalid ? r.c : 0);
+    return r;
+}
+
+// rows of G (or of a control term) times the state block B for one item: the same loop as spmm_kernel, generator
+// values and column indices from this warp's shared-memory copy
+template <int R>
+__device__ __forceinline__ void sweep_rows_times_block(const double2 *__restrict__ gv, const int *__restrict__ cl, const int W,
+                                                       const double2 *B /* rewritten during the launch: no .nc loads */, const int ld, const size_t cbase,
+                                                       double (&outr)[R], double (&outi)[R]) {
+    double cr[R], ci[R], cr1[R], ci1[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) cr[q] = ci[q] = cr1[q] = ci1[q] = 0.0;
+    constexpr int SU = 16 / R;  // 16 state-row loads in flight per lane
+    int s = 0;
+    for (; s + SU <= W; s += SU) {
+        double2 gg[SU][R], xx[SU][R];
+#pragma unroll
+        for (int u = 0; u < SU; ++u)
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                gg[u][q] = gv[q * W + s + u];
+                xx[u][q] = B[(size_t)cl[q * W + s + u] * ld + cbase];
+            }
+#pragma unroll
+        for (int u = 0; u < SU; ++u)
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                cr[q] = fma(gg[u][q].x, xx[u][q].x, cr[q]);
+                cr1[q] = fma(-gg[u][q].y, xx[u][q].y, cr1[q]);
+                ci[q] = fma(gg[u][q].x, xx[u][q].y, ci[q]);
+                ci1[q] = fma(gg[u][q].y, xx[u][q].x, ci1[q]);
+            }
+    }
+    for (; s < W; ++s) {
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            const double2 g = gv[q * W + s];
+            const double2 x = B[(size_t)cl[q * W + s] * ld + cbase];
+            cr[q] = fma(g.x, x.x, cr[q]);
+            cr1[q] = fma(-g.y, x.y, cr1[q]);
+            ci[q] = fma(g.x, x.y, ci[q]);
+            ci1[q] = fma(g.y, x.x, ci1[q]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+        outr[q] = cr[q] + cr1[q];
+        outi[q] = ci[q] + ci1[q];
+    }
+}
+
+// Grid barrier: one monotonic counter; thread 0 of every CTA arrives (release) and spins (acquire), bar.sync on both
+// sides extends the ordering to the whole CTA (the pattern of cooperative groups' grid.sync, without its bookkeeping).
+__device__ __forceinline__ void sweep_barrier(const SweepParams &p, cooperative_groups::grid_group &grid, unsigned &target) {
+    if (p.cg_sync) {
+        grid.sync();
+        return;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.bar) : "memory");
+        while ((int)(ld_acquire_u32(p.bar) - target) < 0) {
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// One propagation step of the whole state block: m_step - 1 terms, a grid barrier behind each.
+template <int R>
+__device__ __forceinline__ void sweep_step(const SweepParams &p, cooperative_groups::grid_group &grid, const int dir,
+                                           const int n, const double (&eps)[kMaxL], double2 *store, double2 *gsm, int *csm,
+                                           const int lane, const int wg, const int total_warps, unsigned &bar_target) {
+    const int rowsz = R * p.W;
+    const size_t nslots = (size_t)p.dp * p.W;
+    const int dtc = p.dtc[dir][n];
+    int m_step = 0;
+    for (int b = 0; b < p.n_blocks; ++b) m_step = max(m_step, p.m[dir][p.blk[b * 4] * p.ndtc[dir] + dtc]);
+    // generator rows of this warp's items for this time step (same arithmetic as build_G_sparse_kernel)
+    for (int k = 0; k < p.K; ++k) {
+        const SweepItem it = sweep_item<R>(p, wg + k * total_warps, lane);
+        if (!it.valid) break;
+        const double sc = 4.0 / p.Delta[dir][it.g], beta = p.Delta[dir][it.g] / 2 + p.E_min[dir][it.g];
+        const double2 f = (dir == KROTOV_FORWARD) ? make_double2(0.0, -sc) : make_double2(0.0, sc);
+        const double2 *Pv = p.Pv[dir] + (size_t)it.g * (1 + p.L) * nslots + (size_t)it.row0 * p.W;
+        for (int i = lane; i < rowsz; i += 32) {
+            double2 h = Pv[i];
+            if (i % p.W == 0) h.x -= beta;
+            for (int l = 0; l < p.L; ++l) {
+                const double2 hl = Pv[(size_t)(l + 1) * nslots + i];
+                h.x = fma(eps[l], hl.x, h.x);
+                h.y = fma(eps[l], hl.y, h.y);
+            }
+            gsm[k * rowsz + i] = make_double2(f.x * h.x - f.y * h.y, f.x * h.y + f.y * h.x);
+        }
+    }
+    __syncwarp();
+    const double2 *vprev = p.PSI, *vprev2 = nullptr;
+    for (int j = 1; j < m_step; ++j) {
+        double2 *vnew = p.V[j % 3];
+        for (int k = 0; k < p.K; ++k) {
+            const SweepItem it = sweep_item<R>(p, wg + k * total_warps, lane);
+            if (!it.valid) break;
+            const int ci_ = it.g * p.ndtc[dir] + dtc;
+            const int m = p.m[dir][ci_];
+            if (j >= m) continue;
+            // the epilogue's operands at this lane's own elements are requested before the gathers (one L2 round trip less)
+            double2 w0[R], q0[R];
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const size_t idx = (size_t)(it.row0 + q) * p.ld + it.cbase;
+                w0[q] = (j == 1) ? vprev[idx] : vprev2[idx];
+                q0[q] = (j == 1) ? make_double2(0.0, 0.0) : p.OUT[idx];
+            }
+            double cr[R], ci[R];
+            sweep_rows_times_block<R>(gsm + k * rowsz, csm + k * rowsz, p.W, vprev, p.ld, it.cbase, cr, ci);
+            if (!it.cvalid) continue;
+            const double *a = p.coef[dir] + (size_t)ci_ * p.mmax[dir];
+            const double a0 = a[0], aj = a[j];
+            const bool last = (j == m - 1);
+            const double2 ph = p.phase[dir][ci_];
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const size_t idx = (size_t)(it.row0 + q) * p.ld + it.cbase;
+                double2 v, o;
+                if (j == 1) {
+                    v = make_double2(0.5 * cr[q], 0.5 * ci[q]);
+                    o = make_double2(fma(aj, v.x, a0 * w0[q].x), fma(aj, v.y, a0 * w0[q].y));
+                } else {
+                    v = make_double2(cr[q] + w0[q].x, ci[q] + w0[q].y);
+                    o = make_double2(fma(aj, v.x, q0[q].x), fma(aj, v.y, q0[q].y));
+                }
+                if (last) {
+                    const double2 r = make_double2(ph.x * o.x - ph.y * o.y, ph.x * o.y + ph.y * o.x);
+                    p.PSI[idx] = r;
+                    if (store) store[idx] = r;
+                } else {
+                    vnew[idx] = v;
+                    p.OUT[idx] = o;
+                }
+            }
+        }
+        sweep_barrier(p, grid, bar_target);
+        vprev2 = vprev;
+        vprev = vnew;
+    }
+}
+
+template <int R>
+__global__ void __launch_bounds__(SP_WARPS * 32) sparse_sweep_kernel(const __grid_constant__ SweepParams p) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    extern __shared__ __align__(16) unsigned char sweep_smem[];
+    __shared__ double wsum[kMaxL][SP_WARPS];
+    __shared__ double eps_sh[kMaxL];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wg = blockIdx.x * SP_WARPS + warp, total_warps = gridDim.x * SP_WARPS;
+    const int rowsz = R * p.W;
+    double2 *gsm = reinterpret_cast<double2 *>(sweep_smem) + (size_t)warp * p.K * rowsz;
+    int *csm = reinterpret_cast<int *>(reinterpret_cast<double2 *>(sweep_smem) + (size_t)SP_WARPS * p.K * rowsz) +
+               (size_t)warp * p.K * rowsz;
+    // column indices of this warp's rows never change
+    for (int k = 0; k < p.K; ++k) {
+        const SweepItem it = sweep_item<R>(p, wg + k * total_warps, lane);
+        if (!it.valid) break;
+        for (int i = lane; i < rowsz; i += 32) csm[k * rowsz + i] = p.cols[(size_t)it.row0 * p.W + i];
+    }
+    __syncwarp();
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gthreads = (size_t)gridDim.x * blockDim.x;
+    double eps[kMaxL];
+#pragma unroll
+    for (int l = 0; l < kMaxL; ++l) eps[l] = 0.0;
+    unsigned bar_target = 0;
+
+    if (p.mode == 1) {
+        // ---- backward sweep: chi(t_n) for all n into X
+        for (size_t i = gtid; i < p.slab; i += gthreads) {
+            const double2 v = p.CHI[i];
+            p.PSI[i] = v;
+            p.X[p.slab * (size_t)p.N_T + i] = v;
+        }
+        sweep_barrier(p, grid, bar_target);
+        for (int n = p.N_T - 1; n >= 0; --n) {
+            for (int l = 0; l < p.L; ++l) eps[l] = p.eps_old[(size_t)l * p.N_T + n];
+            sweep_step<R>(p, grid, KROTOV_BACKWARD, n, eps, p.X + p.slab * (size_t)n, gsm, csm, lane, wg, total_warps, bar_target);
+        }
+    }
+    // ---- forward sweep
+    for (size_t i = gtid; i < p.slab; i += gthreads) {
+        const double2 v = p.PSI0[i];
+        p.PSI[i] = v;
+        if (p.store_fw && p.mode == 0) p.PHI[i] = v;
+    }
+    sweep_barrier(p, grid, bar_target);
+    const size_t nslots = (size_t)p.dp * p.W;
+    for (int n = 0; n < p.N_T; ++n) {
+        if (p.mode == 1) {
+            // overlaps Im <chi_k(t_n)| mu_l |psi_k(t_n)> summed over this CTA's items (src/optimize.jl:339-349)
+            const double2 *CHI = p.X + p.slab * (size_t)n;
+            for (int l = 0; l < p.L; ++l) {
+                double acc = 0.0;
+                for (int k = 0; k < p.K; ++k) {
+                    const SweepItem it = sweep_item<R>(p, wg + k * total_warps, lane);
+                    if (!it.valid) break;
+                    const double2 *mu = p.Pv[0] + ((size_t)it.g * (1 + p.L) + 1 + l) * nslots + (size_t)it.row0 * p.W;
+                    double cr[R], ci[R];
+                    sweep_rows_times_block<R>(mu, csm + k * rowsz, p.W, p.PSI, p.ld, it.cbase, cr, ci);
+                    if (it.cvalid) {
+#pragma unroll
+                        for (int q = 0; q < R; ++q) {
+                            const double2 ch = CHI[(size_t)(it.row0 + q) * p.ld + it.cbase];
+                            acc += ch.x * ci[q] - ch.y * cr[q];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0) wsum[l][warp] = acc;
+            }
+            __syncthreads();
+            if ((int)threadIdx.x < p.L) {
+                double t = 0.0;
+                for (int w = 0; w < SP_WARPS; ++w) t += wsum[threadIdx.x][w];
+                p.partial[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = t;
+            }
+            sweep_barrier(p, grid, bar_target);
+            // every CTA adds the CTA partials in the same fixed order (lane-strided, then a butterfly): same bits everywhere
+            if (warp == 0) {
+                for (int l = 0; l < p.L; ++l) {
+                    double sacc = 0.0;
+                    for (int c = lane; c < (int)gridDim.x; c += 32) sacc += p.partial[(size_t)l * gridDim.x + c];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+                    if (lane == 0) {
+                        const double a = p.alpha[(size_t)l * p.N_T + n];
+                        const double e_new = __dadd_rn(p.eps_old[(size_t)l * p.N_T + n], __dmul_rn(a, sacc));  // :355-356
+                        eps_sh[l] = e_new;
+                        if (blockIdx.x == 0) {
+                            p.eps_new[(size_t)l * p.N_T + n] = e_new;
+                            const double prev = (n == 0) ? 0.0 : p.ga[l];
+                            p.ga[l] = __dadd_rn(prev, __dmul_rn(__dmul_rn(a, __dmul_rn(fabs(sacc), fabs(sacc))), p.dt[n]));  // :357
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            for (int l = 0; l < p.L; ++l) eps[l] = eps_sh[l];
+            __syncthreads();
+        } else {
+            for (int l = 0; l < p.L; ++l) eps[l] = p.eps_old[(size_t)l * p.N_T + n];
+        }
+        double2 *store = nullptr;
+        if (p.store_fw) store = p.PHI + p.slab * (size_t)(p.mode == 1 ? n : n + 1);  // slot n in an iteration (sic, :367)
+        sweep_step<R>(p, grid, KROTOV_FORWARD, n, eps, store, gsm, csm, lane, wg, total_warps, bar_target);
+    }
+}
+
 struct Block {  // one GEMM column block
     int g, col0, nt;
 };
@@ -639,6 +953,16 @@ struct DenseEngine {
     long long graph_launches = 0, last_launches = 0;
     int stable_iterations = 0;
     long long graph_replays = 0;
+    // persistent sweep (sparse path): launch shape and device copies of the small tables
+    bool sweep = false;
+    int sw_grid = 0, sw_K = 0, sw_items = 0, sw_R = 4;
+    unsigned *sw_bar = nullptr;
+    size_t sw_smem = 0;
+    int *sw_blk = nullptr, *sw_m[2] = {nullptr, nullptr}, *sw_dtc[2] = {nullptr, nullptr};
+    double *sw_partial = nullptr, *sw_coef[2] = {nullptr, nullptr}, *sw_Emin[2] = {nullptr, nullptr},
+           *sw_Delta[2] = {nullptr, nullptr};
+    double2 *sw_phase[2] = {nullptr, nullptr};
+    long long sweep_launches = 0;
 };
 
 namespace {
@@ -700,6 +1024,108 @@ bool launch_spmm(DenseEngine *e, const Block &b, const double2 *Gv, GemmParams p
     spmm_kernel<<<grid, block, 0, e->stream>>>(sp);
     e->launches++;
     DK_CHECK(cudaGetLastError());
+    return true;
+}
+
+// Launch shape of the persistent sweep: as few items per warp as the co-resident grid allows (shared memory holds the
+// generator rows and column indices of a warp's items).
+const void *sweep_kernel_for(int R) {
+    return R == 4 ? (const void *)sparse_sweep_kernel<4> : R == 2 ? (const void *)sparse_sweep_kernel<2> : (const void *)sparse_sweep_kernel<1>;
+}
+
+bool sweep_configure(DenseEngine *e) {
+    e->sweep = false;
+    if (!e->sparse) return true;
+    // rows per warp item: the terms are latency-bound until the state block is large, so small problems get more,
+    // shorter items.  Measured (tools/gpu_sparse_bench.py --variants, us per time step and direction, R = 4 / 2 / 1):
+    // 8 spins 95.6 / 57.9 / 49.5, 10 spins 130.6 / 70.7 / 69.6, 12 spins 192.8 / 158.3 / 184.1.
+    int col_groups = 0;
+    for (const Block &b : e->blocks) col_groups += (b.nt * 8 + 31) / 32;
+    const long long warps = (long long)e->sm_count * SP_WARPS;
+    int R = 1;
+    if ((long long)(e->dp / 4) * col_groups >= 4 * warps)
+        R = 4;
+    else if ((long long)(e->dp / 2) * col_groups >= warps)
+        R = 2;
+    if (const char *env = getenv("KROTOV_SWEEP_ROWS")) R = atoi(env) >= 4 ? 4 : atoi(env) >= 2 ? 2 : 1;
+    e->sw_R = R;
+    std::vector<int> blk;
+    int items = 0;
+    for (const Block &b : e->blocks) {
+        blk.insert(blk.end(), {b.g, b.col0, b.nt * 8, items});
+        items += (e->dp / R) * ((b.nt * 8 + 31) / 32);
+    }
+    e->sw_items = items;
+    const size_t rowsz = (size_t)R * e->W;
+    const void *fn = sweep_kernel_for(R);
+    for (int K = 1; K <= 16; ++K) {
+        const size_t smem = (size_t)SP_WARPS * K * rowsz * (16 + 4);
+        if (smem > 200 * 1024) break;
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) break;
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, SP_WARPS * 32, smem) != cudaSuccess || nb < 1) break;
+        const long long cap = (long long)nb * e->sm_count;
+        if (cap * SP_WARPS * K >= items) {
+            e->sw_K = K;
+            e->sw_smem = smem;
+            e->sw_grid = (int)std::min<long long>(cap, (items + SP_WARPS * K - 1) / (SP_WARPS * K));
+            e->sweep = true;
+            break;
+        }
+    }
+    cudaGetLastError();
+    if (!e->sweep) return true;
+    std::string err;
+    if (!dalloc(e->sw_blk, blk.size(), err) || !dalloc(e->sw_partial, (size_t)kMaxL * e->sw_grid, err) ||
+        !dalloc(e->sw_bar, 1, err)) {
+        e->sweep = false;
+        return false;
+    }
+    cudaMemcpy(e->sw_blk, blk.data(), blk.size() * 4, cudaMemcpyHostToDevice);
+    return true;
+}
+
+bool sweep_usable(const DenseEngine *e, int mode) {
+    return e->sweep && e->comm.world <= 1 && e->ch[0].set && (mode == 0 || e->ch[1].set) && !getenv("KROTOV_NO_SWEEP");
+}
+
+template <typename T>
+bool sweep_upload(T *&dst, const std::vector<T> &src, std::string &err) {
+    if (dst) cudaFree(dst);
+    dst = nullptr;
+    if (!dalloc(dst, src.size(), err)) return false;
+    DK_CHECK(cudaMemcpy(dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return true;
+}
+
+bool launch_sweep(DenseEngine *e, int mode, const double *d_eps_old, double *d_eps_new, const double *d_alpha,
+                  const double *d_dt, double *d_ga, std::string &err) {
+    SweepParams p;
+    memset(&p, 0, sizeof(p));
+    p.dp = e->dp; p.ld = e->ld; p.W = e->W; p.L = e->L; p.N_T = e->N_T; p.n_blocks = (int)e->blocks.size();
+    p.n_items = e->sw_items; p.mode = mode; p.store_fw = e->store_fw; p.K = e->sw_K;
+    p.cols = e->ell_cols;
+    p.Pv[0] = e->Pvf;
+    p.Pv[1] = e->hermitian ? e->Pvf : e->Pvb;
+    p.blk = e->sw_blk;
+    for (int dir = 0; dir < 2; ++dir) {
+        p.coef[dir] = e->sw_coef[dir]; p.m[dir] = e->sw_m[dir]; p.phase[dir] = e->sw_phase[dir]; p.dtc[dir] = e->sw_dtc[dir];
+        p.E_min[dir] = e->sw_Emin[dir]; p.Delta[dir] = e->sw_Delta[dir];
+        p.ndtc[dir] = e->ch[dir].ndtc; p.mmax[dir] = e->ch[dir].mmax;
+    }
+    p.PSI = e->PSI; p.V[0] = e->V[0]; p.V[1] = e->V[1]; p.V[2] = e->V[2]; p.OUT = e->OUT; p.X = e->X; p.PHI = e->PHI;
+    p.PSI0 = e->PSI0; p.CHI = e->CHI; p.slab = e->slab;
+    p.eps_old = d_eps_old; p.eps_new = d_eps_new; p.alpha = d_alpha; p.dt = d_dt; p.ga = d_ga;
+    p.partial = e->sw_partial;
+    p.cg_sync = getenv("KROTOV_SWEEP_CGSYNC") ? 1 : 0;
+    p.bar = e->sw_bar;
+    DK_CHECK(cudaMemsetAsync(e->sw_bar, 0, sizeof(unsigned), e->stream));
+    const void *fn = sweep_kernel_for(e->sw_R);
+    DK_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->sw_smem));
+    void *args[] = {(void *)&p};
+    DK_CHECK(cudaLaunchCooperativeKernel(fn, dim3(e->sw_grid), dim3(SP_WARPS * 32), args, e->sw_smem, e->stream));
+    e->launches++;
+    e->sweep_launches++;
     return true;
 }
 
@@ -892,6 +1318,11 @@ DenseEngine *dense_create(int d, int N, int L, int N_T, int n_gen, const std::ve
             }
         }
     }
+    if (e->sparse && !sweep_configure(e)) {
+        err = "dense_create: allocation for the persistent sweep failed";
+        dense_destroy(e);
+        return nullptr;
+    }
     // upload padded generator terms (and adjoints), states, targets
     std::vector<cplx> buf(mat);
     for (int q = 0; !e->sparse && q < n_gen * (1 + L); ++q) {
@@ -935,7 +1366,9 @@ void dense_destroy(DenseEngine *e) {
     if (!e) return;
     void *ptrs[] = {e->Hf, e->Hb, e->G, e->V[0], e->V[1], e->V[2], e->OUT, e->PSI, e->PSI0, e->TGT, e->CHI, e->X,
                     e->PHI, e->partial, e->d_col_of_traj, e->d_traj_of_col, e->ell_cols, e->Pvf, e->Pvb, e->Gv,
-                    e->sk_ws, e->sk_flags};
+                    e->sk_ws, e->sk_flags, e->sw_blk, e->sw_partial, e->sw_bar, e->sw_m[0], e->sw_m[1], e->sw_dtc[0], e->sw_dtc[1],
+                    e->sw_coef[0], e->sw_coef[1], e->sw_Emin[0], e->sw_Emin[1], e->sw_Delta[0], e->sw_Delta[1],
+                    e->sw_phase[0], e->sw_phase[1]};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
@@ -943,7 +1376,7 @@ void dense_destroy(DenseEngine *e) {
 }
 
 void dense_info(DenseEngine *e, krotov_info *out) {
-    out->grid_blocks = e->sparse ? e->dp / SP_ROWS : (e->streamk ? e->sm_count : e->dp / BM);
+    out->grid_blocks = e->sparse ? (e->sweep_launches ? e->sw_grid : e->dp / SP_ROWS) : (e->streamk ? e->sm_count : e->dp / BM);
     out->graph_replays = e->graph_replays;
     out->block_threads = e->sparse ? SP_WARPS * 32 : GEMM_THREADS;
     out->nnz_union = e->sparse ? e->nnz_union : e->d * e->d;
@@ -965,6 +1398,15 @@ bool dense_set_cheby(DenseEngine *e, int direction, int ndtc, const std::vector<
     c.ndtc = ndtc; c.mmax = m_max; c.dtc_of_step = dtc_of_step; c.E_min = E_min; c.Delta = Delta; c.m = m;
     c.coef = coef; c.phase = phase; c.set = true;
     if (!same) e->cheb_version++;  // coefficients travel by value in the launch parameters: a captured iteration is stale now
+    if (e->sweep && !same) {  // the persistent sweep reads the tables from device memory
+        std::vector<double2> ph(phase.size());
+        for (size_t i = 0; i < phase.size(); ++i) ph[i] = make_double2(phase[i].real(), phase[i].imag());
+        cudaStreamSynchronize(e->stream);
+        if (!sweep_upload(e->sw_coef[direction], coef, err) || !sweep_upload(e->sw_m[direction], m, err) ||
+            !sweep_upload(e->sw_phase[direction], ph, err) || !sweep_upload(e->sw_dtc[direction], dtc_of_step, err) ||
+            !sweep_upload(e->sw_Emin[direction], E_min, err) || !sweep_upload(e->sw_Delta[direction], Delta, err))
+            return false;
+    }
     for (int v : m)
         if (v < 3) {
             err = "dense path needs at least 3 Chebyshev coefficients per step (Delta * dt too small)";
@@ -983,6 +1425,11 @@ static bool finish_sweep(DenseEngine *e, double2 *d_tau, std::string &err) {
 bool dense_forward(DenseEngine *e, const double *d_eps, double2 *d_tau, long long &launches, std::string &err) {
     e->launches = 0;
     DK_CHECK(cudaMemcpyAsync(e->PSI, e->PSI0, e->slab * 16, cudaMemcpyDeviceToDevice, e->stream));
+    if (sweep_usable(e, 0)) {
+        if (!launch_sweep(e, 0, d_eps, nullptr, nullptr, nullptr, nullptr, err) || !finish_sweep(e, d_tau, err)) return false;
+        launches += e->launches;
+        return true;
+    }
     if (e->store_fw) DK_CHECK(cudaMemcpyAsync(e->PHI, e->PSI0, e->slab * 16, cudaMemcpyDeviceToDevice, e->stream));
     for (int n = 0; n < e->N_T; ++n)
         if (!step(e, KROTOV_FORWARD, n, d_eps, e->store_fw ? e->PHI + e->slab * (size_t)(n + 1) : nullptr, err))
@@ -1014,7 +1461,7 @@ bool dense_iterate(DenseEngine *e, const double *d_eps_old, double *d_eps_new, c
     key.cheb_version = e->cheb_version;
     const void *ptrs[8] = {d_eps_old, d_eps_new, d_alpha, d_dt, d_ga, d_chi_coef, d_tau, nullptr};
     memcpy(key.ptr, ptrs, sizeof(ptrs));
-    const bool graph_ok = e->comm.world <= 1 && !getenv("KROTOV_NO_GRAPH");
+    const bool graph_ok = e->comm.world <= 1 && !getenv("KROTOV_NO_GRAPH") && !sweep_usable(e, 1);  // (the sweep is 3 launches)
     if (graph_ok && e->graph_exec != nullptr && e->graph_key == key) {
         DK_CHECK(cudaGraphLaunch(e->graph_exec, e->stream));
         launches += e->graph_launches;
@@ -1073,6 +1520,8 @@ bool iterate_body(DenseEngine *e, const double *d_eps_old, double *d_eps_new, co
                                                                      e->dp, e->ld);
         e->launches++;
     }
+    if (sweep_usable(e, 1))
+        return launch_sweep(e, 1, d_eps_old, d_eps_new, d_alpha, d_dt, d_ga, err) && finish_sweep(e, d_tau, err);
     // ---- backward sweep: chi(t_n) for all n into X
     DK_CHECK(cudaMemcpyAsync(e->PSI, e->CHI, e->slab * 16, cudaMemcpyDeviceToDevice, e->stream));
     DK_CHECK(cudaMemcpyAsync(e->X + e->slab * (size_t)N_T, e->CHI, e->slab * 16, cudaMemcpyDeviceToDevice, e->stream));

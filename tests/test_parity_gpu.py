@@ -569,6 +569,48 @@ def test_scipy_sparse_operators_are_not_densified():
     assert np.abs(np.array(c["J_T"]) - np.array(e["J_T"])).max() < 1e-9  # different (but valid) Chebyshev envelopes
 
 
+# ---- persistent sweep of the sparse path (one cooperative launch per iteration) -----------------------------------
+@pytest.mark.parametrize("n_spins,n_traj,functional,ensemble", [(7, 40, "sm", 1), (8, 70, "ss", 1), (6, 9, "re", 3)])
+def test_sparse_sweep_equals_launch_per_term(n_spins, n_traj, functional, ensemble, monkeypatch):
+    """The whole-iteration kernel of the sparse path (grid barriers between Chebyshev terms, generator rows built in
+    shared memory) against the launch-per-term stream it replaces: same elementwise arithmetic, the per-step overlap
+    sums differ in summation order only.  Several column groups (40 and 70 trajectories), several column blocks
+    (an ensemble of 3 generators with different spectral radii, hence different term counts), storage slots."""
+    w = W.spin_chain(n_spins=n_spins, n_traj=n_traj, functional=functional, n_grid=31)
+    if ensemble > 1:
+        w.H0 = [w.H0[0] * (1.0 + 0.35 * g) for g in range(ensemble)]
+        w.Hc = [w.Hc[0] for _ in range(ensemble)]
+        w.gen_of_traj = np.arange(n_traj) * ensemble // n_traj
+    force = dict(force_path=3)
+
+    def run():
+        seen = {}
+
+        def cb(wrk, it, *a):
+            if it == 2:
+                seen["X"] = np.array(wrk.bw_storage[n_traj - 1])
+                seen["Phi"] = np.array(wrk.fw_storage[0])
+                seen["psi"] = np.array(wrk.fw_propagators[0].state)
+
+        out = run_product(w, 2, store_fw_states=True, **force)
+        K.optimize(to_problem(w, iter_stop=2, callback=cb, store_fw_states=True, **force), method=K.Krotov)
+        out.update(seen)
+        return out
+
+    a = run()
+    assert a["info"]["path"] == 3 and a["info"]["launches_last"] <= 4  # chi coefficients, chi(T), sweep, tau
+    assert np.abs(a["Phi"][:, w.N_T - 1] - a["psi"]).max() < 1e-15  # slot n holds the state after step n (sic, :367)
+    monkeypatch.setenv("KROTOV_NO_SWEEP", "1")
+    b = run()
+    monkeypatch.delenv("KROTOV_NO_SWEEP")
+    assert b["info"]["launches_last"] > 100
+    assert np.abs(np.array(a["J_T"]) - np.array(b["J_T"])).max() < 1e-13
+    assert np.abs(a["pulses"] - b["pulses"]).max() < 1e-13
+    assert np.abs(a["X"] - b["X"]).max() < 1e-13 and np.abs(a["Phi"] - b["Phi"]).max() < 1e-13
+    a2 = run_product(w, 2, **force)
+    assert np.array_equal(a["pulses"], a2["pulses"]) and a["J_T"] == a2["J_T"]  # fixed summation order
+
+
 # ---- 32 < d <= 128 with narrow rows: the persistent kernel with 64 / 128 threads per trajectory ----------------
 @pytest.mark.parametrize("levels,n_grid,iters", [(6, 201, 2), (8, 101, 2), (10, 61, 2), (11, 41, 1)])
 def test_wide_groups_two_transmons_more_levels(levels, n_grid, iters):
