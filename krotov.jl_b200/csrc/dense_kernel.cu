@@ -710,7 +710,8 @@ __device__ __forceinline__ void sweep_barrier(const SweepParams &p, cooperative_
 template <int R>
 __device__ __forceinline__ void sweep_step(const SweepParams &p, cooperative_groups::grid_group &grid, const int dir,
                                            const int n, const double (&eps)[kMaxL], double2 *store, double2 *gsm, int *csm,
-                                           const int lane, const int wg, const int total_warps, unsigned &bar_target) {
+                                           const int lane, const int wg, const int total_warps, unsigned &bar_target,
+                                           const SweepItem &it0) {
     const int rowsz = R * p.W;
     const size_t nslots = (size_t)p.dp * p.W;
     const int dtc = p.dtc[dir][n];
@@ -718,7 +719,7 @@ __device__ __forceinline__ void sweep_step(const SweepParams &p, cooperative_gro
     for (int b = 0; b < p.n_blocks; ++b) m_step = max(m_step, p.m[dir][p.blk[b * 4] * p.ndtc[dir] + dtc]);
     // generator rows of this warp's items for this time step (same arithmetic as build_G_sparse_kernel)
     for (int k = 0; k < p.K; ++k) {
-        const SweepItem it = sweep_item<R>(p, wg + k * total_warps, lane);
+        const SweepItem it = (k == 0) ? it0 : sweep_item<R>(p, wg + k * total_warps, lane);  // items never change
         if (!it.valid) break;
         const double sc = 4.0 / p.Delta[dir][it.g], beta = p.Delta[dir][it.g] / 2 + p.E_min[dir][it.g];
         const double2 f = (dir == KROTOV_FORWARD) ? make_double2(0.0, -sc) : make_double2(0.0, sc);
@@ -735,14 +736,20 @@ __device__ __forceinline__ void sweep_step(const SweepParams &p, cooperative_gro
         }
     }
     __syncwarp();
+    // per-step metadata of the first item (the only one unless the problem outgrows the grid)
+    const int ci0 = it0.g * p.ndtc[dir] + dtc;
+    const int m0 = p.m[dir][ci0];
+    const double2 ph0 = p.phase[dir][ci0];
+    const double *a_0 = p.coef[dir] + (size_t)ci0 * p.mmax[dir];
+    const double a00 = a_0[0];
     const double2 *vprev = p.PSI, *vprev2 = nullptr;
     for (int j = 1; j < m_step; ++j) {
         double2 *vnew = p.V[j % 3];
         for (int k = 0; k < p.K; ++k) {
-            const SweepItem it = sweep_item<R>(p, wg + k * total_warps, lane);
+            const SweepItem it = (k == 0) ? it0 : sweep_item<R>(p, wg + k * total_warps, lane);  // items never change
             if (!it.valid) break;
-            const int ci_ = it.g * p.ndtc[dir] + dtc;
-            const int m = p.m[dir][ci_];
+            const int ci_ = (k == 0) ? ci0 : it.g * p.ndtc[dir] + dtc;
+            const int m = (k == 0) ? m0 : p.m[dir][ci_];
             if (j >= m) continue;
             // the epilogue's operands at this lane's own elements are requested before the gathers (one L2 round trip less)
             double2 w0[R], q0[R];
@@ -755,10 +762,10 @@ __device__ __forceinline__ void sweep_step(const SweepParams &p, cooperative_gro
             double cr[R], ci[R];
             sweep_rows_times_block<R>(gsm + k * rowsz, csm + k * rowsz, p.W, vprev, p.ld, it.cbase, cr, ci);
             if (!it.cvalid) continue;
-            const double *a = p.coef[dir] + (size_t)ci_ * p.mmax[dir];
-            const double a0 = a[0], aj = a[j];
+            const double *a = (k == 0) ? a_0 : p.coef[dir] + (size_t)ci_ * p.mmax[dir];
+            const double a0 = (k == 0) ? a00 : a[0], aj = a[j];
             const bool last = (j == m - 1);
-            const double2 ph = p.phase[dir][ci_];
+            const double2 ph = (k == 0) ? ph0 : p.phase[dir][ci_];
 #pragma unroll
             for (int q = 0; q < R; ++q) {
                 const size_t idx = (size_t)(it.row0 + q) * p.ld + it.cbase;
@@ -787,20 +794,21 @@ __device__ __forceinline__ void sweep_step(const SweepParams &p, cooperative_gro
 }
 
 template <int R>
-__global__ void __launch_bounds__(SP_WARPS * 32) sparse_sweep_kernel(const __grid_constant__ SweepParams p) {
+__global__ void __launch_bounds__(SP_WARPS * 32, 2) sparse_sweep_kernel(const __grid_constant__ SweepParams p) {
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     extern __shared__ __align__(16) unsigned char sweep_smem[];
     __shared__ double wsum[kMaxL][SP_WARPS];
     __shared__ double eps_sh[kMaxL];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wg = blockIdx.x * SP_WARPS + warp, total_warps = gridDim.x * SP_WARPS;
+    const SweepItem it0 = sweep_item<R>(p, wg, lane);
     const int rowsz = R * p.W;
     double2 *gsm = reinterpret_cast<double2 *>(sweep_smem) + (size_t)warp * p.K * rowsz;
     int *csm = reinterpret_cast<int *>(reinterpret_cast<double2 *>(sweep_smem) + (size_t)SP_WARPS * p.K * rowsz) +
                (size_t)warp * p.K * rowsz;
     // column indices of this warp's rows never change
     for (int k = 0; k < p.K; ++k) {
-        const SweepItem it = sweep_item<R>(p, wg + k * total_warps, lane);
+        const SweepItem it = (k == 0) ? it0 : sweep_item<R>(p, wg + k * total_warps, lane);  // items never change
         if (!it.valid) break;
         for (int i = lane; i < rowsz; i += 32) csm[k * rowsz + i] = p.cols[(size_t)it.row0 * p.W + i];
     }
@@ -821,7 +829,7 @@ __global__ void __launch_bounds__(SP_WARPS * 32) sparse_sweep_kernel(const __gri
         sweep_barrier(p, grid, bar_target);
         for (int n = p.N_T - 1; n >= 0; --n) {
             for (int l = 0; l < p.L; ++l) eps[l] = p.eps_old[(size_t)l * p.N_T + n];
-            sweep_step<R>(p, grid, KROTOV_BACKWARD, n, eps, p.X + p.slab * (size_t)n, gsm, csm, lane, wg, total_warps, bar_target);
+            sweep_step<R>(p, grid, KROTOV_BACKWARD, n, eps, p.X + p.slab * (size_t)n, gsm, csm, lane, wg, total_warps, bar_target, it0);
         }
     }
     // ---- forward sweep
@@ -839,7 +847,7 @@ __global__ void __launch_bounds__(SP_WARPS * 32) sparse_sweep_kernel(const __gri
             for (int l = 0; l < p.L; ++l) {
                 double acc = 0.0;
                 for (int k = 0; k < p.K; ++k) {
-                    const SweepItem it = sweep_item<R>(p, wg + k * total_warps, lane);
+                    const SweepItem it = (k == 0) ? it0 : sweep_item<R>(p, wg + k * total_warps, lane);  // items never change
                     if (!it.valid) break;
                     const double2 *mu = p.Pv[0] + ((size_t)it.g * (1 + p.L) + 1 + l) * nslots + (size_t)it.row0 * p.W;
                     double cr[R], ci[R];
@@ -890,7 +898,7 @@ __global__ void __launch_bounds__(SP_WARPS * 32) sparse_sweep_kernel(const __gri
         }
         double2 *store = nullptr;
         if (p.store_fw) store = p.PHI + p.slab * (size_t)(p.mode == 1 ? n : n + 1);  // slot n in an iteration (sic, :367)
-        sweep_step<R>(p, grid, KROTOV_FORWARD, n, eps, store, gsm, csm, lane, wg, total_warps, bar_target);
+        sweep_step<R>(p, grid, KROTOV_FORWARD, n, eps, store, gsm, csm, lane, wg, total_warps, bar_target, it0);
     }
 }
 

@@ -4,14 +4,14 @@ sys.path.insert(0, "tests"); sys.path.insert(0, ".")
 from util import *  # noqa
 import argparse
 ap = argparse.ArgumentParser(); ap.add_argument("--spins", type=int, default=12); ap.add_argument("--n", type=int, default=64)
-ap.add_argument("--grid", type=int, default=21); ap.add_argument("--no-dense", action="store_true"); ap.add_argument("--variants", action="store_true")
+ap.add_argument("--grid", type=int, default=21); ap.add_argument("--no-dense", action="store_true"); ap.add_argument("--variants", action="store_true"); ap.add_argument("--sweep-only", action="store_true")
 a = ap.parse_args()
 t = time.time(); w = W.spin_chain(n_spins=a.spins, n_traj=a.n, n_grid=a.grid); print("workload built", round(time.time() - t, 1), "s", flush=True)
 variants = [("sweep", {}), ("sweep cg-sync", {"KROTOV_SWEEP_CGSYNC": "1"}), ("sweep R=4", {"KROTOV_SWEEP_ROWS": "4"}),
             ("sweep R=2", {"KROTOV_SWEEP_ROWS": "2"}), ("sweep R=1", {"KROTOV_SWEEP_ROWS": "1"}),
             ("launch per term", {"KROTOV_NO_SWEEP": "1"})]
 if not a.variants:
-    variants = [variants[0], variants[-1]]
+    variants = [variants[0]] if a.sweep_only else [variants[0], variants[-1]]
 runs = [(0, n, e) for n, e in variants] + ([] if a.no_dense else [(2, "dense", {})])
 for fp, name, env in runs:
     for k in ("KROTOV_NO_SWEEP", "KROTOV_SWEEP_CGSYNC", "KROTOV_SWEEP_ROWS"):
