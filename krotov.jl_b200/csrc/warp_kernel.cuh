@@ -26,9 +26,11 @@
 // applies the update and releases the trajectory warps through named barrier B.  The gather is done
 // by ONE reducer (the comm warp of CTA 0), which then broadcasts the L sums through E[n][l]; the other
 // CTAs spin on that single line.  (An all-gather in which every CTA polled every slot made 147 CTAs
-// hammer the same ~20 L2 lines and cost 7 us per step.)  With several ranks the reducer additionally
-// pushes the rank's sum into every peer's mailbox over NVLink (P2P stores) and sums the `world`
-// mailbox slots in rank order before broadcasting.
+// hammer the same ~20 L2 lines and cost 7 us per step.)  That protocol is the fallback today: on one GPU the sum is
+// an exact one-hop all-reduce through L2 integer atomics (atomic_grid_sum), and with several ranks every CTA adds its
+// fixed-point partial into EVERY rank's accumulator over NVLink (xrank_atomic_sum) -- or, beyond a few hundred CTAs,
+// the reducer pushes the rank's sum into every peer's mailbox (P2P stores) and the `world` mailbox slots are summed
+// in rank order.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
