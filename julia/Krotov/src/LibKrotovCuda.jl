@@ -63,6 +63,21 @@ get_storage!(h, which, k, n0, n1, out::Matrix{ComplexF64}) =
     check(h, ccall((:krotov_get_storage, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Ptr{ComplexF64}),
                    h.ptr, which, k, n0, n1, out))
 
+# chi(T) = coef[k] * target[k] formed on the device (built-in functionals on several ranks: the global sum of tau)
+set_chi_coeffs(h, coef::Vector{ComplexF64}) =
+    check(h, ccall((:krotov_set_chi_coeffs, lib), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}), h.ptr, coef))
+
+# Multi-GPU (one Julia process per GPU): exchange the descriptors by any transport (MPI.Allgather, Distributed ...),
+# then connect; from then on `iterate!` exchanges the per-time-step overlap sums in-kernel over NVLink.
+const COMM_DESC_BYTES = 192
+function comm_export(h)
+    desc = Vector{UInt8}(undef, COMM_DESC_BYTES)
+    check(h, ccall((:krotov_comm_export, lib), Cint, (Ptr{Cvoid}, Ptr{UInt8}), h.ptr, desc))
+    desc
+end
+comm_connect(h, rank::Integer, world::Integer, descs::Matrix{UInt8}) =   # descs: [COMM_DESC_BYTES, world]
+    check(h, ccall((:krotov_comm_connect, lib), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), h.ptr, rank, world, descs))
+
 # Optional host utility: the spectral envelope of every generator of an ensemble in one threaded call
 # (H0: [d, d, n_gen], Hc: [d, d, n_gen, L], amps: [L, n_corner]); `eigvals` works unchanged.
 function envelope_extremes(H0::Array{ComplexF64,3}, Hc::Array{ComplexF64,4}, amps::Matrix{Float64}; threads = 0)

@@ -260,3 +260,43 @@ def test_hermitian_extremes_matches_lapack():
         assert abs(many.E_min[g] - one.E_min[0]) <= 1e-14 * one.Delta[0]
         assert len(many.coeffs[g][0]) == len(one.coeffs[0][0])
         assert np.abs(many.coeffs[g][0] - one.coeffs[0][0]).max() < 1e-12  # alpha ~ 200 on this coarse grid
+
+
+def test_cross_rank_fixed_point_word_format():
+    """Bit budget of the one-hop cross-rank sum (`xrank_atomic_sum`, csrc/warp_kernel.cuh), modelled with Python
+    integers: 117-bit biased numbers (unit 2^-88, bias 2^116) in four 30-bit limbs; word = limb sum (41 bits) |
+    misfit count (11 bits) | arrival count (12 bits).  With the largest number of arrivals no field carries into
+    its neighbour, the total stays below 2^128, and the reconstruction is the exact sum rounded once."""
+    import math
+    from fractions import Fraction
+
+    FRAC, LIMB, LIMBS, BIAS, MIS, CNT, MAXARR = 88, 30, 4, 116, 41, 52, 2047
+    assert LIMB * LIMBS >= BIAS + 1 and MIS == LIMB + 11 and CNT == MIS + 11 and CNT + 12 == 64
+
+    def to_fixed(x):
+        assert abs(x) < 2.0 ** (BIAS - FRAC)
+        mag = int(Fraction(abs(x)) * 2**FRAC)  # truncation below 2^-88, like the kernel
+        return (1 << BIAS) - mag if x < 0 else (1 << BIAS) + mag
+
+    rng = np.random.default_rng(3)
+    for n in (2, 256, MAXARR):
+        xs = rng.standard_normal(n) * 10.0 ** rng.integers(-12, 8, n)
+        xs[0] = -(2.0**28) * (1 - 2.0**-53)  # extremes of the range
+        xs[1] = 2.0**28 * (1 - 2.0**-53)
+        words = [0] * LIMBS
+        for x in xs:
+            v = to_fixed(float(x))
+            assert 0 < v < (1 << (BIAS + 1))
+            for j in range(LIMBS):
+                words[j] += (1 << CNT) + ((v >> (j * LIMB)) & ((1 << LIMB) - 1))
+        for wd in words:
+            assert wd < (1 << 64) and (wd >> CNT) == n and ((wd >> MIS) & 0x7FF) == 0
+        total = sum((wd & ((1 << MIS) - 1)) << (j * LIMB) for j, wd in enumerate(words))
+        assert total < (1 << 128)
+        exact = Fraction(total - (n << BIAS), 2**FRAC)
+        truncated = sum(Fraction(int(Fraction(abs(float(x))) * 2**FRAC), 2**FRAC) * (1 if x >= 0 else -1) for x in xs)
+        assert exact == truncated
+        assert abs(float(exact) - math.fsum(float(x) for x in xs)) <= n * 2.0**-FRAC
+    # all arrivals misfit: the misfit field holds them without touching the arrival count
+    wd = MAXARR * ((1 << CNT) + (1 << MIS))
+    assert (wd >> CNT) == MAXARR and ((wd >> MIS) & 0x7FF) == MAXARR and wd < (1 << 64)
