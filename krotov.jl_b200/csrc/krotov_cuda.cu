@@ -424,7 +424,7 @@ int choose_launch(krotov_handle h) {
     h->pair = false;
     if (lpt == 32 && kernel2_table().count(KernelKey{h->Wt, h->L, 32}) > 0 && N % 2 == 0 &&
         (N > cap_preg * sm || getenv("KROTOV_FORCE_PAIR")) && N / 2 <= cap_preg * sm &&
-        !getenv("KROTOV_NO_PAIR") && !getenv("KROTOV_NO_PREG")) {
+        !getenv("KROTOV_NO_PAIR") && !getenv("KROTOV_NO_PREG") && !getenv("KROTOV_SEQ_PREG")) {
         bool ok = true;
         for (int k = 0; k < N; k += 2) ok = ok && (h->gen_of_traj[k] == h->gen_of_traj[k + 1]);
         if (ok) {
@@ -432,6 +432,25 @@ int choose_launch(krotov_handle h) {
             if (const char *env = getenv("KROTOV_WPC")) wpc2 = std::max(1, std::min(cap_preg, atoi(env)));
             h->pair = true; h->preg = true; h->tpw = 1; h->wpc = wpc2;
             h->nCTA = (N / 2 + wpc2 - 1) / wpc2;
+            return KROTOV_OK;
+        }
+    }
+    // Larger ensembles whose trajectories come in runs sharing a generator (the basis states of an ensemble sample):
+    // one warp runs `tpw` trajectories of ONE generator one after the other and keeps that generator's rows in
+    // registers, instead of re-reading rows from L2 for every trajectory and time step (21 row loads of 512 bytes
+    // per trajectory and step: ~5 TB/s of L2 traffic at N = 4096, which is what bound the row-reloading variant).
+    if (lpt == 32 && preg_possible && N > cap_preg * sm && !getenv("KROTOV_NO_PREG") && !getenv("KROTOV_NO_SEQ_PREG")) {
+        for (int tpw = 2; tpw <= 16; ++tpw) {
+            if (N % tpw != 0 || N / tpw > cap_preg * sm) continue;
+            bool ok = true;
+            for (int k = 0; k < N && ok; k += tpw)
+                for (int t = 1; t < tpw; ++t) ok = ok && (h->gen_of_traj[k + t] == h->gen_of_traj[k]);
+            if (!ok) continue;
+            const int warps = N / tpw;
+            int wpc = std::max(1, (warps + sm - 1) / sm);
+            if (const char *env = getenv("KROTOV_WPC")) wpc = std::max(1, std::min(cap_preg, atoi(env)));
+            h->preg = true; h->tpw = tpw; h->wpc = wpc;
+            h->nCTA = (warps + wpc - 1) / wpc;
             return KROTOV_OK;
         }
     }

@@ -489,6 +489,28 @@ def test_pair_kernel_large_ensemble(monkeypatch):
     assert np.abs(a["pulses"] - b["pulses"]).max() < 1e-12
 
 
+def test_sequential_register_rows_large_ensemble(monkeypatch):
+    """Ensembles beyond the pair kernel's reach (N > 2072 on one B200) whose trajectories come in runs sharing a
+    generator: one warp runs the run's trajectories one after the other with the generator rows in registers.  Here
+    at a size the pair kernel also serves (so both can be compared), against the C oracle, the pair kernel and the
+    row-reloading variant; storage slots through the multi-trajectory indexing."""
+    from oracle import c_oracle as C
+
+    w = W.c4_ensemble(n_samples=300, n_grid=41)
+    pair = run_product(w, 2)
+    monkeypatch.setenv("KROTOV_SEQ_PREG", "1")
+    seq = run_product(w, 2, store_fw_states=True)
+    assert seq["info"]["grid_blocks"] * (seq["info"]["block_threads"] // 32 - 1) * 2 >= 1200  # 600 warps, 2 trajectories each
+    ref = C.optimize_krotov_c(W.to_oracle(w), 2)
+    assert_parity(seq, ref["J_T"], ref["pulses"], rtol=1e-10, atol=5e-13)
+    assert np.abs(np.array(seq["J_T"]) - np.array(pair["J_T"])).max() < 1e-13
+    assert np.abs(seq["pulses"] - pair["pulses"]).max() < 1e-12
+    monkeypatch.setenv("KROTOV_NO_PREG", "1")
+    old = run_product(w, 2)
+    assert np.abs(np.array(seq["J_T"]) - np.array(old["J_T"])).max() < 1e-13
+    assert np.abs(seq["pulses"] - old["pulses"]).max() < 1e-12
+
+
 @pytest.mark.parametrize("d,force_path", [(12, 0), (40, 0)])
 def test_non_hermitian_generator_uses_adjoint_backward(d, force_path):
     """A weakly non-Hermitian generator (decay -i Gamma/2 on the drift, a non-Hermitian control operator): the
