@@ -633,6 +633,21 @@ def test_sparse_sweep_equals_launch_per_term(n_spins, n_traj, functional, ensemb
     assert np.array_equal(a["pulses"], a2["pulses"]) and a["J_T"] == a2["J_T"]  # fixed summation order
 
 
+def test_sparse_sweep_several_items_per_warp(monkeypatch):
+    """More (row, column-group) items than co-resident warps: a warp of the sweep kernel then owns several items
+    (here 1024 rows x 3 column groups with one row per item).  Against the launch-per-term stream."""
+    w = W.spin_chain(n_spins=10, n_traj=70, n_grid=9)
+    monkeypatch.setenv("KROTOV_SWEEP_ROWS", "1")
+    a = run_product(w, 2)
+    assert a["info"]["path"] == 3 and a["info"]["launches_last"] <= 4
+    assert a["info"]["grid_blocks"] * 8 < 1024 * 3  # fewer warps than items
+    monkeypatch.setenv("KROTOV_NO_SWEEP", "1")
+    b = run_product(w, 2)
+    assert b["info"]["launches_last"] > 100
+    assert np.abs(np.array(a["J_T"]) - np.array(b["J_T"])).max() < 1e-12
+    assert np.abs(a["pulses"] - b["pulses"]).max() < 1e-12
+
+
 # ---- 32 < d <= 128 with narrow rows: the persistent kernel with 64 / 128 threads per trajectory ----------------
 @pytest.mark.parametrize("levels,n_grid,iters", [(6, 201, 2), (8, 101, 2), (10, 61, 2), (11, 41, 1)])
 def test_wide_groups_two_transmons_more_levels(levels, n_grid, iters):
