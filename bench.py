@@ -112,10 +112,21 @@ def smem_roofline(n_traj, n_steps, terms_per_step, width, sm_count, sm_mhz, ms_l
                     "(DESIGN.md 4.1)"}
 
 
+def host_cores():
+    """Host threads the CPU arm may use: the cores this process is allowed to run on.  `torch.distributed.run`
+    exports OMP_NUM_THREADS=1 to its workers, so the OpenMP default must never be relied on -- the count is passed
+    explicitly to the C restatement (oracle/c_oracle.py `n_threads`)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline_sample(workload_full, samples, iters, n_threads=0):
     """Time the C restatement on a bounded sample: the first `samples` ensemble members of the workload."""
     from oracle import c_oracle
 
+    n_threads = n_threads or host_cores()
     w = W.c4_ensemble(n_samples=samples, n_grid=len(workload_full.tlist))
     p = W.to_oracle(w)
     out = c_oracle.optimize_krotov_c(p, iters, n_threads=n_threads)
@@ -131,9 +142,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    wfull = W.c4_ensemble(n_samples=args.samples, n_grid=args.n_grid)
     sample = min(args.samples, args.ref_samples)
-    vals = []
     from oracle import c_oracle
 
     c_oracle.build()
@@ -141,7 +150,12 @@ def run_reference(args):
     w = W.c4_ensemble(n_samples=sample, n_grid=args.n_grid)
     p = W.to_oracle(w)
     t0 = time.time()
-    out = c_oracle.optimize_krotov_c(p, args.warmup + args.steps)
+    n_threads = args.ref_threads or host_cores()
+    if n_threads == 1 and (os.cpu_count() or 1) > 1 and not args.ref_threads:
+        # a single-threaded CPU arm on a multi-core box is not the baseline BASELINE.json asks for
+        raise SystemExit(f"reference arm would run on 1 of {os.cpu_count()} cores (affinity "
+                         f"{sorted(os.sched_getaffinity(0))}); pass --ref-threads to force")
+    out = c_oracle.optimize_krotov_c(p, args.warmup + args.steps, n_threads=n_threads)
     # the C oracle reports the loop time of all iterations; per-iteration time is uniform
     secs_per_iter = out["secs"] / (args.warmup + args.steps)
     st = 2.0 * w.N * w.N_T
@@ -172,6 +186,8 @@ def main():
     ap.add_argument("--samples", type=int, default=256, help="ensemble samples (256 = BASELINE C4)")
     ap.add_argument("--n-grid", type=int, default=2001, help="time-grid points (2001 = BASELINE C4)")
     ap.add_argument("--ref-samples", type=int, default=32, help="bounded sample for the CPU arm")
+    ap.add_argument("--ref-threads", type=int, default=0, help="host threads of the CPU arm (0 = all cores this "
+                    "process may run on; never the OpenMP default, which torchrun pins to 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scaling", choices=["strong", "weak"], default="strong",
                     help="strong: the BASELINE ensemble sharded over the ranks; weak: --samples per rank")

@@ -1430,6 +1430,13 @@ static bool finish_sweep(DenseEngine *e, double2 *d_tau, std::string &err) {
     return true;
 }
 
+// Psi_k(T) := initial states, tau from them: the state of freshly initialised propagators, which is what the driver
+// reads when `skip_initial_forward_propagation` is set (src/optimize.jl:171-181, :297, :378-381)
+bool dense_seed(DenseEngine *e, double2 *d_tau, std::string &err) {
+    DK_CHECK(cudaMemcpyAsync(e->PSI, e->PSI0, e->slab * 16, cudaMemcpyDeviceToDevice, e->stream));
+    return finish_sweep(e, d_tau, err);
+}
+
 bool dense_forward(DenseEngine *e, const double *d_eps, double2 *d_tau, long long &launches, std::string &err) {
     e->launches = 0;
     DK_CHECK(cudaMemcpyAsync(e->PSI, e->PSI0, e->slab * 16, cudaMemcpyDeviceToDevice, e->stream));

@@ -34,6 +34,7 @@ bool dense_set_cheby(DenseEngine *e, int direction, int ndtc, const std::vector<
                      const std::vector<double> &E_min, const std::vector<double> &Delta, const std::vector<int> &m,
                      const std::vector<double> &coef, int m_max, const std::vector<std::complex<double>> &phase,
                      std::string &err);
+bool dense_seed(DenseEngine *e, double2 *d_tau, std::string &err);
 bool dense_forward(DenseEngine *e, const double *d_eps, double2 *d_tau, long long &launches, std::string &err);
 bool dense_iterate(DenseEngine *e, const double *d_eps_old, double *d_eps_new, const double *d_alpha,
                    const double *d_dt, double *d_ga, const double2 *d_chi_coef, double2 *d_tau, long long &launches,

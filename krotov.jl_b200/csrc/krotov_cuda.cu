@@ -26,6 +26,7 @@
 #include "warp_kernel.cuh"
 #include "warp2_kernel.cuh"
 #include "tiny_kernel.cuh"
+#include "kernel_table.h"
 
 using cplx = std::complex<double>;
 
@@ -171,51 +172,29 @@ int upload(krotov_handle h, DevBuf &b, const std::vector<T> &v) {
     return KROTOV_OK;
 }
 
-// ---- kernel table ------------------------------------------------------------------------
-using WarpKernel = void (*)(const kr::WarpParams);
-struct KernelKey {
-    int W, LT, LPT = 32;
-    bool operator<(const KernelKey &o) const {
-        return W != o.W ? W < o.W : (LT != o.LT ? LT < o.LT : LPT < o.LPT);
-    }
-};
-
-#define KR_INST(W, LT, MT) {{W, LT, 32}, (WarpKernel)kr::krotov_warp_kernel<W, LT, MT>}
-#define KR_INSTW(W, LT, MT, LPT) {{W, LT, LPT}, (WarpKernel)kr::krotov_warp_kernel<W, LT, MT, LPT>}
+// ---- kernel table (instances are compiled in warp_inst_*.cu, one translation unit per family) ------------------
+using kr::KernelKey;
+using kr::WarpKernel;
 const std::map<KernelKey, WarpKernel> &kernel_table() {
-    static const std::map<KernelKey, WarpKernel> tab = {
-        // runtime-L variants (rows reloaded per use), up to 15 trajectory warps per CTA
-        KR_INST(1, 0, 512), KR_INST(2, 0, 512), KR_INST(3, 0, 512), KR_INST(4, 0, 512), KR_INST(5, 0, 512),
-        KR_INST(6, 0, 512), KR_INST(7, 0, 512), KR_INST(8, 0, 512), KR_INST(10, 0, 512), KR_INST(12, 0, 512),
-        KR_INST(16, 0, 512), KR_INST(20, 0, 512), KR_INST(24, 0, 512), KR_INST(31, 0, 512),
-        // register-resident term rows (PREG): (1+L)(W+1) <= 36 double2
-        KR_INST(1, 1, 256), KR_INST(2, 1, 256), KR_INST(3, 1, 256), KR_INST(4, 1, 256), KR_INST(5, 1, 256),
-        KR_INST(6, 1, 256), KR_INST(7, 1, 256), KR_INST(8, 1, 256), KR_INST(10, 1, 256), KR_INST(12, 1, 256),
-        
-        KR_INST(1, 2, 256), KR_INST(2, 2, 256), KR_INST(3, 2, 256), KR_INST(4, 2, 256), KR_INST(5, 2, 256),
-        KR_INST(6, 2, 256), KR_INST(7, 2, 256), KR_INST(8, 2, 256), KR_INST(10, 2, 256),
-        KR_INST(2, 3, 256), KR_INST(4, 3, 256), KR_INST(6, 3, 256),
-        // wider groups: 64 or 128 threads (rows) per trajectory for 32 < d <= 128 with narrow rows
-        KR_INSTW(4, 0, 512, 64), KR_INSTW(6, 0, 512, 64), KR_INSTW(8, 0, 512, 64), KR_INSTW(10, 0, 512, 64),
-        KR_INSTW(12, 0, 512, 64), KR_INSTW(16, 0, 512, 64), KR_INSTW(20, 0, 512, 64), KR_INSTW(24, 0, 512, 64),
-        KR_INSTW(4, 1, 256, 64), KR_INSTW(6, 1, 256, 64), KR_INSTW(8, 1, 256, 64), KR_INSTW(10, 1, 256, 64),
-        KR_INSTW(4, 2, 256, 64), KR_INSTW(6, 2, 256, 64), KR_INSTW(8, 2, 256, 64),
-        KR_INSTW(4, 0, 512, 128), KR_INSTW(6, 0, 512, 128), KR_INSTW(8, 0, 512, 128), KR_INSTW(12, 0, 512, 128),
-        KR_INSTW(16, 0, 512, 128), KR_INSTW(24, 0, 512, 128),
-        KR_INSTW(4, 1, 256, 128), KR_INSTW(6, 1, 256, 128), KR_INSTW(8, 1, 256, 128), KR_INSTW(4, 2, 256, 128),
-        KR_INSTW(6, 2, 256, 128), KR_INSTW(8, 2, 256, 128),
-    };
+    static const std::map<KernelKey, WarpKernel> tab = [] {
+        std::map<KernelKey, WarpKernel> t;
+        kr::add_warp_instances_runtime(t);
+        kr::add_warp_instances_preg1(t);
+        kr::add_warp_instances_preg2(t);
+        kr::add_warp_instances_wide64(t);
+        kr::add_warp_instances_wide128(t);
+        return t;
+    }();
     return tab;
 }
 
 // pair kernel (two trajectories of one generator per warp): register-resident rows only
-#define KR_INST2(W, LT) {{W, LT, 32}, (WarpKernel)kr::krotov_warp2_kernel<W, LT>}
 const std::map<KernelKey, WarpKernel> &kernel2_table() {
-    static const std::map<KernelKey, WarpKernel> tab = {
-        KR_INST2(2, 1), KR_INST2(3, 1), KR_INST2(4, 1), KR_INST2(5, 1), KR_INST2(6, 1), KR_INST2(7, 1), KR_INST2(8, 1),
-        KR_INST2(2, 2), KR_INST2(3, 2), KR_INST2(4, 2), KR_INST2(5, 2), KR_INST2(6, 2), KR_INST2(7, 2), KR_INST2(8, 2),
-        KR_INST2(4, 3), KR_INST2(6, 3),
-    };
+    static const std::map<KernelKey, WarpKernel> tab = [] {
+        std::map<KernelKey, WarpKernel> t;
+        kr::add_warp2_instances(t);
+        return t;
+    }();
     return tab;
 }
 
@@ -844,7 +823,20 @@ int krotov_create(const krotov_problem *pb, krotov_handle *out) {
         if (h->store_fw && (rc = dev_alloc(h, h->d_Phi, slab))) return bail(rc);
         if ((rc = dev_alloc(h, h->d_chiT, (size_t)N * h->lpt * 16))) return bail(rc);
         if ((rc = dev_alloc(h, h->d_psif, (size_t)N * h->lpt * 16))) return bail(rc);
-        cudaMemset(h->d_psif.p, 0, (size_t)N * h->lpt * 16);
+        // Freshly initialised propagators hold the initial states: that is what `skip_initial_forward_propagation`
+        // (src/optimize.jl:171-181) leaves for the first chi(T) (:297) and update_result! (:378-381)
+        cudaMemcpy(h->d_psif.p, h->d_psi0.p, (size_t)N * h->lpt * 16, cudaMemcpyDeviceToDevice);
+        if (h->has_target) {
+            std::vector<cplx> tau0(N);
+            const cplx *s0 = reinterpret_cast<const cplx *>(pb->psi0), *tg = reinterpret_cast<const cplx *>(pb->target);
+            for (int k = 0; k < N; ++k) {
+                cplx a(0, 0);
+                for (int i = 0; i < d; ++i) a += std::conj(tg[(size_t)k * d + i]) * s0[(size_t)k * d + i];
+                tau0[k] = a;
+            }
+            cudaMemcpy(h->d_tau.p, tau0.data(), (size_t)N * 16, cudaMemcpyHostToDevice);
+        }
+        h->swept = true;
         if ((rc = dev_alloc(h, h->d_R, ((size_t)N_T * h->nCTA * L + (size_t)N_T * L) * 8))) return bail(rc);
         if ((rc = dev_alloc(h, h->d_acc, (size_t)N_T * L * kr::kFixLimbs * 8))) return bail(rc);
         if (getenv("KROTOV_PROF")) {
@@ -862,6 +854,8 @@ int krotov_create(const krotov_problem *pb, krotov_handle *out) {
                                     path == KROTOV_PATH_SPARSE ? &sd : nullptr);
         if (!h->dense) return bail(KROTOV_ERR_UNSUPPORTED);
         std::vector<cplx>().swap(h->Hdense);  // the device holds the generators now
+        if (!kr::dense_seed(h->dense, (double2 *)h->d_tau.p, h->err)) return bail(KROTOV_ERR_CUDA);
+        h->swept = true;
     }
     if (cudaDeviceSynchronize() != cudaSuccess) return bail(fail(h, KROTOV_ERR_CUDA, "device sync after create failed"));
     *out = h;

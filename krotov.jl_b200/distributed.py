@@ -33,8 +33,13 @@ def shard_bounds(gen_of_traj, rank, world):
                 bigger = [c for c in cuts if c > bounds[r - 1]]
                 bounds[r] = bigger[0] if bigger else N
         bounds[-1] = N
+        if any(bounds[r + 1] <= bounds[r] for r in range(world)):  # degenerate cut-aligned split: equal counts
+            bounds = [(r * N) // world for r in range(world + 1)]
     else:
         bounds = [(r * N) // world for r in range(world + 1)]
+    if any(bounds[r + 1] <= bounds[r] for r in range(world)):
+        # every rank evaluates the same bounds, so every rank raises: nobody is left waiting in a collective
+        raise ValueError(f"cannot shard {N} trajectories over {world} ranks: some rank would hold none")
     return int(bounds[rank]), int(bounds[rank + 1])
 
 
@@ -61,13 +66,20 @@ class Comm:
         return out
 
     def connect(self, engine):
-        """Exchange the mailbox IPC descriptors and map the peers' mailboxes."""
+        """Exchange the mailbox IPC descriptors and map the peers' mailboxes.  Ranks must sit on distinct GPUs:
+        their persistent kernels wait for one another and two of them on one device may never be co-resident."""
+        import socket
+
+        where = self.all_gather_object((socket.gethostname(), int(self.device)))
+        if self.backend != "gloo" and len(set(where)) != len(where):
+            raise RuntimeError(f"ranks share a GPU: (host, device) per rank = {where}")
         descs = self.all_gather_object(engine.comm_export())
         engine.comm_connect(self.rank, self.world, descs)
         self.barrier()
 
     def all_gather_rows(self, local, n_total):
-        """Concatenate per-rank blocks of rows (tau or states) in rank order."""
+        """Concatenate per-rank blocks of rows (tau or states) in rank order.  COLLECTIVE: every rank must call it
+        (touching `wrk.result.states` in a callback on one rank only would leave that rank waiting)."""
         parts = self.all_gather_object(np.ascontiguousarray(local))
         out = np.concatenate(parts, axis=0)
         assert out.shape[0] == n_total

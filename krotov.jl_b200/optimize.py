@@ -26,7 +26,7 @@ from .workspace import KrotovWrk
 log = logging.getLogger("krotov_jl_b200")
 
 __all__ = ["optimize", "optimize_krotov", "krotov_initial_fw_prop", "krotov_iteration", "update_result",
-           "finalize_result", "make_krotov_print_iters", "make_print_iters", "Krotov", "Cheby"]
+           "finalize_result", "detached_result", "make_krotov_print_iters", "make_print_iters", "Krotov", "Cheby"]
 
 
 class _Method:
@@ -118,6 +118,40 @@ def update_result(wrk, i):
     prev = res.end_local_time
     res.end_local_time = _dt.datetime.now()
     res.secs = (res.end_local_time - prev).total_seconds()
+
+
+def detached_result(res):
+    """Copy of a result that holds plain arrays only (no view of device memory, no engine handle): what
+    ``atexit_filename`` and user callbacks may pickle."""
+    import dataclasses
+
+    states = res.states
+    if not isinstance(states, list) or any(not isinstance(s, np.ndarray) for s in states):
+        try:
+            states = states.snapshot() if hasattr(states, "snapshot") else [np.array(s) for s in states]
+        except Exception:  # the device is gone (interpreter shutdown after a fault): keep the rest of the result
+            states = []
+    return dataclasses.replace(res, states=states, records=list(res.records),
+                               optimized_controls=[np.array(c) for c in res.optimized_controls],
+                               guess_controls=[np.array(c) for c in res.guess_controls])
+
+
+def _dump_result(res, filename):
+    import os
+    import tempfile
+
+    folder = os.path.dirname(os.path.abspath(filename))
+    fd, tmp = tempfile.mkstemp(prefix=".krotov_atexit_", dir=folder)
+    try:
+        with os.fdopen(fd, "wb") as fh:
+            pickle.dump(res, fh)
+        os.replace(tmp, filename)
+    except BaseException:
+        try:
+            os.unlink(tmp)
+        except OSError:
+            pass
+        raise
 
 
 def finalize_result(eps_opt, wrk):
@@ -224,9 +258,11 @@ def optimize_krotov(problem, comm=None):
         atexit_filename = kw.get("atexit_filename", None)
         hook = None
         if atexit_filename is not None:
-            def hook(res=wrk.result, fn=atexit_filename):
-                with open(fn, "wb") as fh:
-                    pickle.dump(res, fh)
+            # set_atexit_save_optimization (src/optimize.jl:195-205): dump the result if the process dies mid-run.
+            # The live result aliases device-backed views, so a detached copy is written (to a temporary file that
+            # is renamed into place: a crash while dumping never leaves a truncated checkpoint behind).
+            def hook(wrk=wrk, fn=atexit_filename):
+                _dump_result(detached_result(wrk.result), fn)
             atexit.register(hook)
         try:
             while not wrk.result.converged:

@@ -23,7 +23,12 @@ class Trajectory:
             setattr(self, k, v)
 
     def adjoint(self):
-        g = self.generator.adjoint() if isinstance(self.generator, Generator) else np.asarray(self.generator).conj().T
+        if isinstance(self.generator, Generator):
+            g = self.generator.adjoint()
+        elif hasattr(self.generator, "tocsr"):  # control-free scipy.sparse generator: stays sparse
+            g = self.generator.conj().T.tocsr()
+        else:
+            g = np.asarray(self.generator).conj().T
         return Trajectory(self.initial_state, g, target_state=self.target_state, weight=self.weight, **self.kwargs)
 
 

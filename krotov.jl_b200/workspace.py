@@ -111,6 +111,10 @@ def _prop_kwargs(traj, kwargs, prefixes):
     return out
 
 
+def _comparable(pk):
+    return {k: (getattr(v, "__name__", None) or repr(v)) for k, v in pk.items()}
+
+
 class _LazyStates:
     """List-like view of Psi_k(T) on the device; fetched once per sweep on first access."""
 
@@ -137,6 +141,21 @@ class _LazyStates:
 
     def __setitem__(self, k, v):  # `res.states[k] = propagator.state` (src/optimize.jl:379) is a no-op alias
         pass
+
+    def snapshot(self):
+        """Plain copies of the states WITHOUT a collective: the cached gather when there is one, a local fetch on a
+        single rank, else only what this rank can see without its peers (an exit hook must never wait for them)."""
+        if self._cache is not None:
+            return [np.array(s) for s in self._cache]
+        wrk = self._wrk
+        if wrk.comm is None or wrk.comm.world == 1:
+            return [np.array(s) for s in self._get()]
+        return [np.array(s) for s in wrk.engine.states()]  # this rank's shard only
+
+    def __reduce__(self):
+        # pickling (a callback that checkpoints `wrk.result`, the atexit hook) stores the plain state vectors, as
+        # the reference's `result.states` are; the view itself holds the engine handle and cannot be pickled
+        return (list, (self.snapshot(),))
 
 
 class _PropagatorView:
@@ -224,6 +243,10 @@ class KrotovWrk:
             pulses0 = [discretize_on_midpoints(c, tlist) for c in self.controls]
         self.result = result
         self.pulses0 = pulses0
+        # init_prop_trajectory (src/workspace.jl:136-161) sees the generator's ORIGINAL controls: their ranges seed the
+        # propagators' control ranges (differs from pulses0 only under `continue_from`)
+        self._init_pulses = pulses0 if "continue_from" not in kwargs else [
+            discretize_on_midpoints(c, tlist) for c in self.controls]
         self.pulses1 = [p.copy() for p in pulses0]
         self.g_a_int = np.zeros(len(pulses0))
         kwargs["piecewise"] = True  # only piecewise propagators
@@ -240,6 +263,13 @@ class KrotovWrk:
                     "(there is no CPU fallback for other methods)")
             if "callback" in pk:
                 raise ArgumentError("per-step propagation callbacks cannot run inside the device sweep")
+        for name, pks in (("fw", self.fw_prop_kwargs), ("bw", self.bw_prop_kwargs)):
+            # one set of propagator settings serves the whole batch: per-trajectory overrides that differ would be
+            # silently lost, so they are refused
+            for pk in pks[1:]:
+                if _comparable(pk) != _comparable(pks[0]):
+                    raise ArgumentError(f"{name}_prop_kwargs differ between trajectories; the batched device "
+                                        "propagator needs the same propagator settings for all of them")
         if "J_T" not in kwargs:
             raise ArgumentError("`optimize` for `method=Krotov` must be passed the functional `J_T`.")
         J_T = kwargs["J_T"]
@@ -329,7 +359,7 @@ class KrotovWrk:
             H0s = [adj(h) for h in self._H0] if backward else self._H0
             Hcs = [[None if h is None else adj(h) for h in row] for row in self._Hc] if backward else self._Hc
             return ChebyDirection(
-                H0s, Hcs, tlist, backward, self.pulses0,
+                H0s, Hcs, tlist, backward, self._init_pulses,
                 limit=pk.get("cheby_coeffs_limit", 1e-12), specrange_buffer=pk.get("specrange_buffer", 0.01),
                 specrange_method=pk.get("specrange_method", "auto"), E_min=pk.get("E_min"), E_max=pk.get("E_max"),
                 envelope_cache=shared if self._shared_envelope_ok(pk) else None)

@@ -131,8 +131,17 @@ static void evaluate_dense(const ctx_t *c, const csr_t *terms, int g, const doub
     }
 }
 
+static int g_oracle_diverged = 0; /* a pulse grew beyond anything a polynomial can be derived for */
+
 static int cheby_coeffs(double Delta, double dt, double limit, double **out) {
     double alpha = fabs(0.5 * Delta * dt);
+    if (!(alpha < 1e6)) { /* NaN / Inf / absurd spectral radius: a diverged optimisation, not a crash */
+        double *z = (double *)malloc(sizeof(double));
+        z[0] = NAN;
+        *out = z;
+        g_oracle_diverged = 1;
+        return 1;
+    }
     int cap = (int)(alpha * 1.5) + 64, m = 0;
     double *a = (double *)malloc(sizeof(double) * cap);
     a[m++] = jn(0, alpha);
@@ -377,6 +386,7 @@ int oracle_krotov_optimize(int d, int N, int L, int N_T, int n_gen, const double
                            int n_threads, double *out_JT, double *out_ga, double *out_tau, double *out_states,
                            int *out_m, double *out_secs) {
     if (L > 16) return -1;
+    g_oracle_diverged = 0;
 #ifdef _OPENMP
     if (n_threads > 0) omp_set_num_threads(n_threads);
 #endif
@@ -561,7 +571,7 @@ int oracle_krotov_optimize(int d, int N, int L, int N_T, int n_gen, const double
     free(fw); free(bw); free(X); free(chi); free(work); free(mu_psi); free(e0); free(e1);
     free(c.fw_terms); free(c.bw_terms); free(c.bw_rowptr); free(c.bw_col); free(c.bw_val);
     free(c.cache_key); free(c.cache_val); free(c.cache_ok);
-    return 0;
+    return g_oracle_diverged ? -2 : 0;
 }
 
 int oracle_num_threads(void) {

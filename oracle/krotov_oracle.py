@@ -60,6 +60,7 @@ __all__ = [
     "krotov_initial_fw_prop",
     "krotov_iteration",
     "optimize_krotov",
+    "optimize_krotov_blocked",
     "taus",
     "J_T_value",
     "chi_states",
@@ -585,4 +586,88 @@ def optimize_krotov(p: ProblemArrays, iter_stop=5, prop_method="cheby",
     hist["optimized_controls"] = np.array([discretize(e, p.tlist) for e in eps_i])
     hist["states"] = np.array(states)
     hist["wrk"] = wrk
+    return hist
+
+
+def optimize_krotov_blocked(p: ProblemArrays, iter_stop=5):
+    """The same algorithm as :func:`optimize_krotov` with the trajectories of one generator held as the COLUMNS of one
+    (d, B) state block, so that a propagator term is one ``op @ block`` (BLAS-3) instead of B matrix-vector products.
+    For dense generators with many trajectories (BASELINE config 5 at d = 4096, where the per-trajectory loop would
+    stream the generator from memory once per trajectory and Chebyshev term).  Every column goes through exactly the
+    arithmetic of its own :class:`ChebyPropagator` -- same polynomial, one lazy operator term at a time -- and the
+    overlap sum keeps the reference's order (``l`` outer, ``k`` inner, ``src/optimize.jl:340-349``); only BLAS's
+    summation order inside a matrix product differs from the per-trajectory oracle (checked in tests/test_oracle.py)."""
+    N, L, N_T = p.N, p.L, p.N_T
+    tlist = np.asarray(p.tlist, float)
+    w = p.weights()
+    groups = [np.nonzero(np.asarray(p.gen_of_traj) == g)[0] for g in range(len(p.H0))]
+    pulses0 = [np.array(p.pulses[l], float) for l in range(L)]
+    pulses1 = [a.copy() for a in pulses0]
+    kw = dict(limit=p.cheby_limit, specrange_buffer=p.specrange_buffer, specrange=p.specrange)
+    fw = [ChebyPropagator(p.H0[g], p.Hc[g], tlist, pulses0, False, **kw) for g in range(len(groups))]
+    bw = [ChebyPropagator(p.H0[g].conj().T, [None if h is None else h.conj().T for h in p.Hc[g]], tlist, pulses0,
+                          True, **kw) for g in range(len(groups))]
+    X = [np.zeros((N_T + 1, p.d, len(ks)), complex) for ks in groups]  # bw_storage, slot n = time-grid point n
+
+    def block(rows, ks):  # (N, d) rows -> (d, B) columns of one group
+        return np.ascontiguousarray(np.asarray(rows)[ks].T)
+
+    def final_states():
+        out = np.empty((N, p.d), complex)
+        for g, ks in enumerate(groups):
+            out[ks] = fw[g].state.T
+        return out
+
+    def sweep_forward(eps):  # krotov_initial_fw_prop! for every k (src/optimize.jl:247-265)
+        for g, ks in enumerate(groups):
+            fw[g].parameters = eps
+            fw[g].reinit_prop(block(p.psi0, ks), transform_control_ranges)
+            for _ in range(N_T):
+                fw[g].prop_step()
+
+    eps_i, eps_ip1 = pulses0, pulses1
+    sweep_forward(eps_i)
+    states = final_states()
+    tau = taus(states, p.target)
+    hist = dict(J_T=[J_T_value(p.functional, tau, w)], g_a_int=[], tau=[tau.copy()])
+    for _ in range(1, iter_stop + 1):
+        # ---- src/optimize.jl:297-317
+        chi = chi_states(p.functional, tau, w, p.target)
+        for g, ks in enumerate(groups):
+            bw[g].parameters = eps_i
+            bw[g].reinit_prop(block(chi, ks), transform_control_ranges)
+            X[g][N_T] = bw[g].state
+            for n in range(N_T - 1, -1, -1):
+                X[g][n] = bw[g].prop_step()
+        # ---- :321-370
+        for g, ks in enumerate(groups):
+            fw[g].parameters = eps_ip1
+            fw[g].reinit_prop(block(p.psi0, ks), transform_control_ranges)
+        g_a_int = np.zeros(L)
+        for n in range(N_T):
+            dt = tlist[n + 1] - tlist[n]
+            du = np.zeros(L)
+            for l in range(L):
+                contrib = np.zeros(N)
+                for g, ks in enumerate(groups):
+                    mu = p.Hc[g][l]
+                    if mu is not None:
+                        contrib[ks] = np.einsum("ik,ik->k", X[g][n].conj(), mu @ fw[g].state).imag
+                for k in range(N):  # reference order: k ascending
+                    du[l] += contrib[k]
+            for l in range(L):
+                alpha = p.S[l][n] / p.lam[l]
+                eps_ip1[l][n] = eps_i[l][n] + alpha * du[l]
+                g_a_int[l] += alpha * abs(du[l]) ** 2 * dt
+            for g in range(len(groups)):
+                fw[g].prop_step()
+        states = final_states()
+        tau = taus(states, p.target)
+        hist["J_T"].append(J_T_value(p.functional, tau, w))
+        hist["g_a_int"].append(g_a_int.copy())
+        hist["tau"].append(tau.copy())
+        eps_i, eps_ip1 = eps_ip1, eps_i
+    hist["pulses"] = np.array(eps_i)
+    hist["states"] = states
+    hist["m"] = (len(fw[0].coeffs), len(bw[0].coeffs))
     return hist

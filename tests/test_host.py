@@ -186,6 +186,35 @@ def test_sharding():
     gen = np.repeat(np.arange(3), [5, 1, 6])  # uneven groups: cut at generator boundaries
     b = [shard_bounds(gen, r, 2) for r in range(2)]
     assert b == [(0, 6), (6, 12)]
+    # degenerate cut-aligned split (runs of 1, 1, 98 over 3 ranks): falls back to equal counts, nobody gets an
+    # empty shard; more ranks than trajectories: every rank raises the same error (no rank left waiting)
+    gen = np.repeat(np.arange(3), [1, 1, 98])
+    b = [shard_bounds(gen, r, 3) for r in range(3)]
+    assert b[0][0] == 0 and b[-1][1] == 100 and all(hi > lo for lo, hi in b)
+    assert all(b[r][1] == b[r + 1][0] for r in range(2))
+    for r in range(4):
+        with pytest.raises(ValueError):
+            shard_bounds(np.zeros(3, int), r, 4)
+
+
+def test_reference_arm_uses_all_cores_even_under_torchrun_env():
+    """bench.py --impl reference must not inherit OMP_NUM_THREADS=1 from torch.distributed.run (round-1 SCALE bug)."""
+    import json
+    import subprocess
+
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                          "--warmup", "0", "--ref-samples", "2", "--n-grid", "101"], env=env, capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    cores = len(os.sched_getaffinity(0))
+    assert line["impl"] == "reference" and line["cpu_baseline"]["cores"] == cores
+    # a non-zero rank of the reference arm does no work and prints nothing
+    env["RANK"] = "1"
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], env=env,
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and out.stdout.strip() == ""
 
 
 def _gloo_worker(rank, world, port, out):

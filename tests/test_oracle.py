@@ -134,3 +134,47 @@ def test_discretize_roundtrip_and_copy():
     assert m[0] == 0.0 and m[-1] == 2.0 and abs(m[4] - 2.0 * 0.45) < 1e-15
     assert abs(O.flattop(0.15, T=5, t_rise=0.3) - O.blackman(0.15, 0, 0.6)) < 1e-16
     assert O.flattop(2.5, T=5, t_rise=0.3) == 1.0 and O.flattop(0.0, T=5, t_rise=0.3) == 0.0
+
+
+def test_oracles_against_50_digit_exact_propagator_optimisation():
+    """An oracle-independent pin of the loop of src/optimize.jl:279-371: the TLS optimisation in 50-digit arithmetic
+    with the closed-form 2x2 propagator (tests/mp_reference.py) depends on none of the recalled Chebyshev
+    conventions.  The ExpProp oracle must agree to rounding, the Chebyshev oracles to the truncation level of the
+    expansion (|a_m| <= 1e-12 per step): absolute 1e-12 in J_T -- which at J_T = 1.7e-5 is 2e-9 RELATIVE, the floor
+    SURVEY.md section 0 (fact 5) predicts for two exact methods -- and 1e-12 in the pulses."""
+    import mp_reference as M
+
+    exact = M.tls_krotov_exact(5)
+    p = W.to_oracle(W.c1_tls())
+    ex = np.array(exact["J_T"])
+    for h, tol_j, tol_p in ((O.optimize_krotov(p, 5, "expm"), 5e-14, 5e-14), (O.optimize_krotov(p, 5, "cheby"), 1e-12, 1e-12),
+                            (C.optimize_krotov_c(p, 5), 1e-12, 1e-12)):
+        assert np.abs(np.array(h["J_T"]) - ex).max() < tol_j
+        assert np.abs(np.asarray(h["pulses"])[0] - np.array(exact["pulses"])).max() < tol_p
+        assert np.abs(np.array([g[0] for g in h["g_a_int"]]) - np.array(exact["g_a_int"])).max() < 1e-12
+    assert ex[-1] < 1e-3  # test_tls_optimization.jl:66 holds for the exact optimisation too
+    # the reference's ExpProp run (what its own test uses) is reproduced to 1e-10 relative at every iteration
+    h = O.optimize_krotov(p, 5, "expm")
+    assert (np.abs(np.array(h["J_T"]) - ex) / ex).max() < 1e-9
+
+
+def test_blocked_oracle_equals_per_trajectory_oracle():
+    """optimize_krotov_blocked (trajectories of a generator as columns, BLAS-3) is the per-trajectory oracle up to
+    BLAS summation order; two generators, a missing control term, J_T_sm (needs the global tau sum)."""
+    w = W.dummy_dense(d=12, n_traj=5, n_controls=2, n_grid=21, seed=5, functional="sm")
+    w.H0 = [w.H0[0], w.H0[0] * 1.1]
+    w.Hc = [w.Hc[0], [w.Hc[0][0] * 0.9, None]]
+    w.gen_of_traj = np.array([0, 0, 1, 1, 1])
+    a = O.optimize_krotov(W.to_oracle(w), 3)
+    b = O.optimize_krotov_blocked(W.to_oracle(w), 3)
+    assert np.abs(np.array(a["J_T"]) - np.array(b["J_T"])).max() < 1e-14
+    assert np.abs(a["pulses"] - b["pulses"]).max() < 1e-14
+    assert np.abs(np.array(a["g_a_int"]) - np.array(b["g_a_int"])).max() < 1e-15
+    assert np.abs(a["states"] - b["states"]).max() < 1e-14
+
+
+def test_c_oracle_reports_divergence_instead_of_crashing():
+    w = W.c4_ensemble(n_samples=1, n_grid=201)
+    w.functional, w.lambda_a = "ss", 1e-4
+    with pytest.raises(RuntimeError):
+        C.optimize_krotov_c(W.to_oracle(w), 4, n_threads=2)

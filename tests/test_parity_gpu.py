@@ -250,6 +250,85 @@ def test_continue_from_and_check_convergence():
     assert r.message == "J_T < 0.2" and r.iter == 2
 
 
+def test_atexit_filename_and_pickling_a_result_from_a_callback(tmp_path):
+    """`atexit_filename` (src/optimize.jl:195-205, 229-231): while the optimisation runs an exit hook is registered
+    that dumps the result; it is removed on normal completion.  The dump -- and a user callback that pickles
+    `wrk.result` -- must hold plain state vectors (the live result aliases device-backed views)."""
+    import atexit
+    import pickle
+
+    w = W.c2_transmon_x(n_grid=51)
+    fn = tmp_path / "krotov_atexit.pkl"
+    seen = {}
+    registered, unregistered = [], []
+    real_register, real_unregister = atexit.register, atexit.unregister
+
+    def cb(wrk, it, eps_new, eps_old):
+        if it == 1:
+            blob = pickle.dumps(wrk.result)  # used to raise: ctypes objects containing pointers cannot be pickled
+            seen["mid"] = pickle.loads(blob)
+            registered[-1]()  # what the interpreter would run if the process died here
+            seen["dump"] = pickle.loads(fn.read_bytes())
+
+    atexit.register = lambda f, *a, **k: (registered.append(f), real_register(f, *a, **k))[1]
+    atexit.unregister = lambda f: (unregistered.append(f), real_unregister(f))[1]
+    try:
+        res = K.optimize(to_problem(w, iter_stop=2, callback=cb, atexit_filename=str(fn)), method=K.Krotov)
+    finally:
+        atexit.register, atexit.unregister = real_register, real_unregister
+    assert res.converged and len(registered) == 1 and unregistered == registered  # :229-231
+    for r in (seen["mid"], seen["dump"]):
+        assert isinstance(r, K.KrotovResult) and r.iter == 1 and isinstance(r.states, list)
+        assert np.array(r.states).shape == (2, 3) and abs(np.linalg.norm(r.states[0]) - 1) < 1e-9
+        assert r.J_T == seen["mid"].J_T and len(r.optimized_controls[0]) == 51
+    assert not [f for f in os.listdir(tmp_path) if f.startswith(".krotov_atexit_")]  # temp file was renamed
+
+
+def test_continue_from_a_foreign_result():
+    """`continue_from` with the result of ANOTHER optimiser (src/workspace.jl:107-120, test_tls_optimization.jl:
+    100-130): any object with the common fields is converted; the first record reproduces its J_T to 1e-14 and the
+    iteration counter continues."""
+    from types import SimpleNamespace
+
+    w = W.c1_tls()
+    r2 = K.optimize(to_problem(w, iter_stop=2), method=K.Krotov)
+    foreign = SimpleNamespace(tlist=r2.tlist, iter_start=0, iter_stop=2, iter=2, J_T=r2.J_T, J_T_prev=r2.J_T_prev,
+                              guess_controls=r2.guess_controls, optimized_controls=[c.copy() for c in r2.optimized_controls],
+                              states=r2.states, records=[], tau_vals=r2.tau_vals, f_calls=7, message="GRAPE says hi")
+    r5 = K.optimize(to_problem(w, iter_stop=5, store_iter_info=["iter.", "J_T"], print_iters=True, continue_from=foreign),
+                    method=K.Krotov)
+    assert isinstance(r5, K.KrotovResult) and r5 is not foreign
+    assert [rec[0] for rec in r5.records] == [0, 3, 4, 5]  # the first callback is always called with 0 (src/optimize.jl:189)
+    assert abs(r5.records[0][1] - r2.J_T) < 1e-14  # test_tls_optimization.jl:126
+    ref = run_product(w, 5)
+    assert abs(r5.J_T - ref["J_T"][5]) <= 1e-10 * ref["J_T"][5] + 2e-15
+    with pytest.raises(TypeError):
+        K.optimize(to_problem(w, iter_stop=5, continue_from=SimpleNamespace(tlist=r2.tlist)), method=K.Krotov)
+
+
+def test_skip_initial_forward_propagation():
+    """src/optimize.jl:171-181: without the initial sweep the propagators hold the initial states, so iteration 0
+    reports J_T of psi(0) and the first iteration starts from chi built on tau = <tgt|psi(0)>."""
+    from oracle import krotov_oracle as O
+
+    w = W.c2_transmon_x(n_grid=51)
+    got = run_product(w, 2, skip_initial_forward_propagation=True)
+    assert abs(got["J_T"][0] - 1.0) < 1e-15  # <1|0> = <0|1> = 0: tau = 0
+    w2 = W.dummy_dense(d=6, n_traj=3, n_controls=1, n_grid=21, seed=2, functional="ss")
+    got = run_product(w2, 2, skip_initial_forward_propagation=True)
+    p = W.to_oracle(w2)
+    tau0 = O.taus(p.psi0, p.target)
+    assert abs(got["J_T"][0] - O.J_T_value("ss", tau0, p.weights())) < 1e-14
+    # the oracle's first iteration from the same boundary condition
+    wrk = O.OracleWrk(p)
+    for k, pr in enumerate(wrk.fw_propagators):
+        pr.reinit_prop(p.psi0[k])
+    wrk.tau_vals = tau0
+    O.krotov_iteration(wrk, wrk.pulses0, wrk.pulses1)
+    O.update_result(wrk)
+    assert abs(got["J_T"][1] - wrk.J_T) <= 1e-10 * abs(wrk.J_T)
+
+
 def test_exception_in_callback_is_captured():
     w = W.c1_tls()
 
@@ -281,6 +360,63 @@ def test_storages_are_reachable_from_callbacks():
     assert abs(np.linalg.norm(X[:, -1]) - np.linalg.norm(X[:, 0])) < 1e-12  # unitary backward sweep
     assert np.abs(Phi[:, 49] - seen["psi"]).max() < 1e-15  # slot n holds the state after step n (sic, :367)
     assert abs(np.vdot(w.target[0], seen["psi"]) - seen["tau"][0]) < 1e-14
+
+
+# ---- BASELINE sizes against the oracle --------------------------------------------------------------------
+def test_c4_full_size_vs_c_oracle():
+    """configs[3] at FULL size (256 samples x 4 = 1024 trajectories, d = 25, L = 2, N_T = 2000), 3 iterations,
+    against the C restatement (OpenMP over trajectories) at BASELINE.json's tolerances.  The absolute floor is the
+    one of every C-oracle comparison here: its own Bessel / eigenvalue code moves the Chebyshev inputs by a few ulp."""
+    from oracle import c_oracle as C
+
+    w = W.c4_ensemble()
+    got = run_product(w, 3)
+    ref = C.optimize_krotov_c(W.to_oracle(w), 3, n_threads=len(os.sched_getaffinity(0)))
+    assert_parity(got, ref["J_T"], ref["pulses"], rtol=1e-10, atol=5e-13)
+    assert np.abs(np.array(got["g_a_int"]) - np.array(ref["g_a_int"])).max() <= 1e-11
+    assert np.abs(got["tau"][-1] - ref["tau"]).max() < 1e-10
+    assert np.abs(np.array(got["result"].states) - ref["states"]).max() < 1e-10
+    assert got["info"]["grid_blocks"] >= 128 and got["info"]["fallback_steps"] == 0
+
+
+def test_c4_full_size_falling_functional_vs_c_oracle():
+    """The same ensemble with J_T_re, whose gradient does not vanish with the ensemble-averaged overlap: J_T falls by
+    more than 10 % within 3 iterations (J_T_sm starts from |<tau>| ~ 0.01 and moves in the 4th digit), so the
+    per-iteration history that is compared is not a flat one."""
+    from oracle import c_oracle as C
+
+    w = W.c4_ensemble()
+    w.functional = "re"
+    got = run_product(w, 3)
+    ref = C.optimize_krotov_c(W.to_oracle(w), 3, n_threads=len(os.sched_getaffinity(0)))
+    assert ref["J_T"][3] < 0.9 * ref["J_T"][0]
+    assert all(ref["J_T"][i + 1] < ref["J_T"][i] for i in range(3))
+    assert_parity(got, ref["J_T"], ref["pulses"], rtol=1e-10, atol=5e-13)
+    assert np.abs(np.array(got["g_a_int"]) - np.array(ref["g_a_int"])).max() <= 1e-11
+    assert np.abs(np.array(got["result"].states) - ref["states"]).max() < 1e-10
+
+
+def test_c5_full_width_vs_blocked_oracle():
+    """configs[4] at full width -- d = 4096 dense generator, 64 trajectories -- over 8 time steps, one full iteration
+    (forward, backward, sequential update + forward) through the FP64 DMMA path, against the blocked NumPy oracle
+    (same algorithm, trajectories as columns: BLAS-3 instead of 64 x streaming a 268 MB matrix per Chebyshev term).
+    lambda_a is chosen small so that the pulse update is far above the tolerance it is compared at."""
+    from oracle import krotov_oracle as O
+
+    w = W.c5_dense(d=4096, n_traj=64, n_grid=9)
+    w.lambda_a = 0.01
+    got = run_product(w, 1)
+    assert got["info"]["path"] == 2
+    ref = O.optimize_krotov_blocked(W.to_oracle(w), 1)
+    assert_parity(got, ref["J_T"], ref["pulses"], rtol=1e-10, atol=5e-13)
+    guess = W.to_oracle(w).pulses
+    update = np.abs(ref["pulses"] - guess).max()
+    assert update > 1e-4  # the update is visible ...
+    assert np.abs(got["pulses"] - ref["pulses"]).max() <= 1e-9 * update + 1e-15  # ... and agrees to 1e-9 of ITSELF
+    assert np.abs(np.array(got["g_a_int"][0]) - ref["g_a_int"][0]).max() <= 1e-10 * np.abs(ref["g_a_int"][0]).max()
+    assert np.abs(got["tau"][-1] - ref["tau"][-1]).max() < 1e-13
+    assert np.abs(np.array(got["result"].states) - ref["states"]).max() < 1e-13
+    assert got["m_fw"][0] == ref["m"][0]
 
 
 # ---- BASELINE sizes: size-independent properties --------------------------------------------------------
