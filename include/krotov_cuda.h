@@ -110,7 +110,9 @@ typedef struct {
     int32_t block_threads;
     int32_t m_fw, m_bw;      /* Chebyshev coefficient counts currently loaded (max over generators) */
     int32_t sm_count;
-    int32_t reserved_i;
+    int32_t exchange;        /* cross-rank protocol of the last launch: 0 none (one rank), 1 hierarchical sum (local
+                                accumulator, then one add per rank over NVLink), 2 one-hop sum (every CTA adds into every
+                                rank's accumulator), 3 rank sums through the peers' mailboxes */
     int64_t launches_total;  /* kernels launched by this handle since creation       */
     int64_t launches_last;   /* kernels launched by the last forward/iterate call    */
     double ms_last;          /* device time of the last forward/iterate call (CUDA events on the launch stream) */
@@ -198,6 +200,15 @@ int krotov_get_profile(krotov_handle h, int cta, int64_t *out);
 #define KROTOV_COMM_DESC_BYTES 192
 int krotov_comm_export(krotov_handle h, void *desc /* KROTOV_COMM_DESC_BYTES */);
 int krotov_comm_connect(krotov_handle h, int rank, int world, const void *descs /* [world][DESC_BYTES] */);
+
+/* Several ranks emulated on ONE device, for tests and diagnostics (a single-GPU box must be able to exercise the
+ * multi-rank exchange protocols; ranks that wait for one another cannot be separate launches on one GPU).  The handles
+ * -- created on the same device, one shard each, same grid shape -- are connected in-process and one cooperative launch
+ * runs all ranks' CTAs; every rank's kernel code, accumulators and mailboxes are those of the multi-GPU path.
+ * new_pulses: [world][L][N_T] (every rank's copy, to be compared), g_a_int: [world][L].  WARP path only. */
+int krotov_group_connect(krotov_handle *handles, int world);
+int krotov_group_iterate(krotov_handle *handles, int world, const double *guess_pulses, double *new_pulses,
+                         double *g_a_int);
 
 /* ---- host utility -----------------------------------------------------------------------
  * Smallest and largest eigenvalue of n_mat complex Hermitian d x d matrices (cplx[n_mat][d][d]; the Hermitian

@@ -25,6 +25,7 @@ EXPORTS = [
     "krotov_abi_version", "krotov_create", "krotov_destroy", "krotov_last_error", "krotov_get_info",
     "krotov_set_cheby", "krotov_forward", "krotov_set_chi", "krotov_set_chi_coeffs", "krotov_iterate",
     "krotov_get_states", "krotov_get_tau", "krotov_get_storage", "krotov_get_profile", "krotov_comm_export", "krotov_comm_connect",
+    "krotov_group_connect", "krotov_group_iterate",
     "krotov_hermitian_extremes", "krotov_envelope_extremes",
 ]
 
@@ -52,7 +53,7 @@ class Info(C.Structure):
     _fields_ = [
         ("struct_size", C.c_int32), ("path", C.c_int32), ("ell_width", C.c_int32), ("nnz_union", C.c_int32),
         ("grid_blocks", C.c_int32), ("block_threads", C.c_int32), ("m_fw", C.c_int32), ("m_bw", C.c_int32),
-        ("sm_count", C.c_int32), ("reserved_i", C.c_int32),
+        ("sm_count", C.c_int32), ("exchange", C.c_int32),
         ("launches_total", C.c_int64), ("launches_last", C.c_int64), ("ms_last", C.c_double),
         ("ms_last_backward", C.c_double), ("hbm_bytes_state", C.c_int64), ("fallback_steps", C.c_int64),
         ("graph_replays", C.c_int64), ("reserved", C.c_int64 * 4),
@@ -91,6 +92,8 @@ def lib():
     L.krotov_get_profile.argtypes = [vp, i32, vp]
     L.krotov_comm_export.argtypes = [vp, vp]
     L.krotov_comm_connect.argtypes = [vp, i32, i32, vp]
+    L.krotov_group_connect.argtypes = [vp, i32]
+    L.krotov_group_iterate.argtypes = [vp, i32, vp, vp, vp]
     L.krotov_hermitian_extremes.argtypes = [i32, i32, vp, vp, vp, i32]
     L.krotov_envelope_extremes.argtypes = [i32, i32, i32, vp, vp, i32, vp, vp, vp, i32]
     for name in EXPORTS:

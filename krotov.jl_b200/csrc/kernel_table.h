@@ -21,10 +21,12 @@ void add_warp_instances_preg1(KernelMap &t);    // register-resident term rows, 
 void add_warp_instances_preg2(KernelMap &t);    // register-resident term rows, L = 2
 void add_warp_instances_wide64(KernelMap &t);   // 64 threads (rows) per trajectory, 32 < d <= 64
 void add_warp_instances_wide128(KernelMap &t);  // 128 threads per trajectory, 64 < d <= 128
+void add_warp_instances_emul(KernelMap &t);     // several ranks emulated by one launch (krotov_group_iterate)
 void add_warp2_instances(KernelMap &t);         // pair kernel: two trajectories of one generator per warp
 
 #define KR_INST(W, LT, MT) t[KernelKey{W, LT, 32}] = (WarpKernel)krotov_warp_kernel<W, LT, MT>
 #define KR_INSTW(W, LT, MT, LPT) t[KernelKey{W, LT, LPT}] = (WarpKernel)krotov_warp_kernel<W, LT, MT, LPT>
+#define KR_INSTE(W, LT, MT) t[KernelKey{W, LT, 32}] = (WarpKernel)krotov_warp_kernel<W, LT, MT, 32, true>
 #define KR_INST2(W, LT) t[KernelKey{W, LT, 32}] = (WarpKernel)krotov_warp2_kernel<W, LT>
 
 }  // namespace kr

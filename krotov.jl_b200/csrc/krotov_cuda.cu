@@ -112,6 +112,9 @@ struct krotov_handle_s {
     double *peer_mbox[2][kr::kMaxRanks] = {};
     size_t mail_bytes = 0, xacc_bytes = 0;  // d_mbox[par] = mailboxes (sentinel-filled) followed by the cross-rank accumulators (zero-filled)
     int total_ctas = 0;  // CTAs of all ranks (krotov_comm_connect)
+    int max_ctas = 0;    // largest CTA count of a rank
+    int xchg_last = 0;   // cross-rank protocol of the last launch: 0 none, 1 hier, 2 onehop, 3 mailboxes
+    DevBuf d_emul;       // krotov_group_iterate: per-rank parameter blocks of the emulated multi-rank launch
     bool peer_opened[kr::kMaxRanks] = {};
     long long iter_count = 0;
     // dense path
@@ -183,6 +186,16 @@ const std::map<KernelKey, WarpKernel> &kernel_table() {
         kr::add_warp_instances_preg2(t);
         kr::add_warp_instances_wide64(t);
         kr::add_warp_instances_wide128(t);
+        return t;
+    }();
+    return tab;
+}
+
+// the same kernel serving several emulated ranks in one launch (krotov_group_iterate)
+const std::map<KernelKey, WarpKernel> &kernel_emul_table() {
+    static const std::map<KernelKey, WarpKernel> tab = [] {
+        std::map<KernelKey, WarpKernel> t;
+        kr::add_warp_instances_emul(t);
         return t;
     }();
     return tab;
@@ -459,8 +472,7 @@ size_t warp_smem_bytes(const krotov_handle h) {
            kr::kMaxCtrl * 8 + (size_t)kr::kMaxCtrl * 160 * 8 + (size_t)h->wpc * h->lpt * 16;
 }
 
-int launch_warp(krotov_handle h, int mode) {
-    kr::WarpParams p;
+void fill_warp_params(krotov_handle h, int mode, kr::WarpParams &p) {
     memset(&p, 0, sizeof(p));
     p.d = h->d; p.N = h->N; p.L = h->L; p.N_T = h->N_T; p.n_gen = h->n_gen;
     p.wpc = h->wpc; p.tpw = h->tpw; p.nCTA = h->nCTA; p.mode = mode; p.store_fw = h->store_fw;
@@ -495,22 +507,37 @@ int launch_warp(krotov_handle h, int mode) {
     if (const char *e = getenv("KROTOV_MBOX_ALL")) p.mbox_all = atoi(e);
     const int par = (int)(h->iter_count & 1);
     for (int r = 0; r < h->world && r < kr::kMaxRanks; ++r) p.mbox[r] = h->peer_mbox[par][r];
-    // one-hop cross-rank sum (every CTA adds into every rank's accumulator): same decision on every rank
+    // The cross-rank sum of a time step -- the same decision on every rank (it only reads what all ranks know):
+    //   hier   (default)  every CTA adds into its own rank's accumulator; the add that completes a word forwards the
+    //                     rank sum with ONE add per rank over NVLink (xrank_hier_sum): `world` adds per word and rank
+    //   onehop            every CTA of every rank adds into every rank's accumulator (xrank_atomic_sum): total_ctas
+    //                     adds per word and rank, up to KROTOV_XACC_MAX (512) CTAs in total
+    //   mbox              rank sums pushed into the peers' mailboxes by the reducer CTA (also the fallback of both)
+    // KROTOV_XCHG=hier|onehop|mbox selects one (experiments, tests); KROTOV_NO_XACC=1 is the old spelling of mbox.
     p.total_ctas = h->total_ctas;
     p.xacc_stride = 1;
     if (const char *e = getenv("KROTOV_XACC_STRIDE")) p.xacc_stride = std::max(1, std::min(kXaccMaxStride, atoi(e)));
-    // (measured on C4, ms per iteration, one-hop / mailboxes: 2 GPUs x 128 CTAs 12.1 / 14.2.  Every rank receives
-    // total_ctas x 4L atomics per time step, so beyond a few hundred CTAs the mailbox protocol -- one store per rank --
-    // is kept; KROTOV_XACC_MAX moves the limit)
     int xacc_max = 512;
     if (const char *e = getenv("KROTOV_XACC_MAX")) xacc_max = std::min(atoi(e), kr::kXMaxArrivals);
-    if (h->world > 1 && h->xacc_bytes && h->total_ctas <= xacc_max && !getenv("KROTOV_NO_XACC"))
+    std::string xchg = getenv("KROTOV_XCHG") ? getenv("KROTOV_XCHG") : "hier";
+    if (getenv("KROTOV_NO_XACC")) xchg = "mbox";
+    const bool hier_ok = h->max_ctas < 256 && h->total_ctas <= kr::kXMaxArrivals && !getenv("KROTOV_NO_ATOMIC_SUM");
+    if (xchg == "hier" && !hier_ok) xchg = "onehop";
+    if (xchg == "onehop" && h->total_ctas > xacc_max) xchg = "mbox";
+    if (h->world > 1 && h->xacc_bytes && xchg != "mbox") {
         for (int r = 0; r < h->world; ++r) p.xacc[r] = (unsigned long long *)((char *)h->peer_mbox[par][r] + h->mail_bytes);
+        p.xchg_hier = (xchg == "hier") ? 1 : 0;
+    }
+    h->xchg_last = h->world > 1 ? (p.xacc[0] ? (p.xchg_hier ? 1 : 2) : 3) : 0;
     p.err_flag = (int *)h->d_err.p;
     p.prof = (long long *)h->d_prof.p;
     p.timeout_cycles = 20000000000ll;  // ~10 s
     if (const char *e = getenv("KROTOV_TIMEOUT_CYCLES")) p.timeout_cycles = atoll(e);
+}
 
+int launch_warp(krotov_handle h, int mode) {
+    kr::WarpParams p;
+    fill_warp_params(h, mode, p);
     if (h->tiny && h->world == 1) {
         kr::TinyParams tp;
         tp.w = p;
@@ -579,7 +606,7 @@ int krotov_destroy(krotov_handle h) {
     DevBuf *bufs[] = {&h->d_acc, &h->d_Tf, &h->d_Tb, &h->d_cols, &h->d_Pf, &h->d_Pb, &h->d_inv_s, &h->d_gen, &h->d_dt, &h->d_alpha,
                       &h->d_eps_old, &h->d_eps_new, &h->d_ga, &h->d_X, &h->d_Phi, &h->d_psi0, &h->d_target,
                       &h->d_chiT, &h->d_chicoef, &h->d_psif, &h->d_tau, &h->d_R, &h->d_err, &h->d_weight, &h->d_prof,
-                      &h->d_mbox[0], &h->d_mbox[1]};
+                      &h->d_mbox[0], &h->d_mbox[1], &h->d_emul};
     for (DevBuf *b : bufs) b->release();
     for (int dir = 0; dir < 2; ++dir) {
         h->cheb[dir].coef.release();
@@ -878,6 +905,7 @@ int krotov_get_info(krotov_handle h, krotov_info *out) {
     out->m_fw = h->cheb[0].m_max_used;
     out->m_bw = h->cheb[1].m_max_used;
     out->sm_count = h->sm_count;
+    out->exchange = h->xchg_last;
     out->launches_total = h->launches_total;
     out->launches_last = h->launches_last;
     out->ms_last = h->ms_last;
@@ -1026,8 +1054,9 @@ int krotov_set_chi_coeffs(krotov_handle h, const double *coef) {
     return KROTOV_OK;
 }
 
-int krotov_iterate(krotov_handle h, const double *guess_pulses, double *new_pulses, double *g_a_int) {
-    if (!h || !guess_pulses || !new_pulses || !g_a_int) return KROTOV_ERR_ARG;
+// what krotov_iterate does before its launch(es): argument / state checks, pulses to the device, chi coefficients,
+// exchange arrays reset.  Leaves the timed region open (begin_timed).
+static int iterate_prepare(krotov_handle h, const double *guess_pulses) {
     if (!h->cheb[0].set || !h->cheb[1].set)
         return fail(h, KROTOV_ERR_STATE, "krotov_set_cheby must be called for both directions before krotov_iterate");
     cudaSetDevice(h->device);
@@ -1057,6 +1086,28 @@ int krotov_iterate(krotov_handle h, const double *guess_pulses, double *new_puls
     if (h->path == KROTOV_PATH_WARP) {
         if (h->nCTA > 1 || h->world > 1) KR_CUDA(h, cudaMemsetAsync(h->d_R.p, 0xFF, h->d_R.bytes, h->stream));
         if (h->nCTA > 1) KR_CUDA(h, cudaMemsetAsync(h->d_acc.p, 0, h->d_acc.bytes, h->stream));
+    }
+    return KROTOV_OK;
+}
+
+static int iterate_finish(krotov_handle h, double *new_pulses, double *g_a_int) {
+    int rc;
+    if ((rc = end_timed(h))) return rc;
+    h->iter_count += 1;
+    if ((rc = check_err_flag(h))) return rc;
+    KR_CUDA(h, cudaMemcpy(new_pulses, h->d_eps_new.p, (size_t)h->L * h->N_T * 8, cudaMemcpyDeviceToHost));
+    KR_CUDA(h, cudaMemcpy(g_a_int, h->d_ga.p, (size_t)h->L * 8, cudaMemcpyDeviceToHost));
+    h->chiT_valid = false;
+    h->chicoef_valid = false;
+    h->swept = true;
+    return KROTOV_OK;
+}
+
+int krotov_iterate(krotov_handle h, const double *guess_pulses, double *new_pulses, double *g_a_int) {
+    if (!h || !guess_pulses || !new_pulses || !g_a_int) return KROTOV_ERR_ARG;
+    int rc;
+    if ((rc = iterate_prepare(h, guess_pulses))) return rc;
+    if (h->path == KROTOV_PATH_WARP) {
         if ((rc = launch_warp(h, 1))) return rc;
     } else {
         std::string e;
@@ -1075,14 +1126,78 @@ int krotov_iterate(krotov_handle h, const double *guess_pulses, double *new_puls
             return fail(h, KROTOV_ERR_CUDA, e);
         h->ms_last_bw = ms_bw;
     }
-    if ((rc = end_timed(h))) return rc;
-    h->iter_count += 1;
-    if ((rc = check_err_flag(h))) return rc;
-    KR_CUDA(h, cudaMemcpy(new_pulses, h->d_eps_new.p, pbytes, cudaMemcpyDeviceToHost));
-    KR_CUDA(h, cudaMemcpy(g_a_int, h->d_ga.p, (size_t)h->L * 8, cudaMemcpyDeviceToHost));
-    h->chiT_valid = false;
-    h->chicoef_valid = false;
-    h->swept = true;
+    return iterate_finish(h, new_pulses, g_a_int);
+}
+
+// ---- several ranks emulated on ONE device (diagnostics / tests) ---------------------------------------------------------
+// Ranks that wait for one another inside their persistent kernels cannot run as separate launches on one GPU (nothing
+// makes them co-resident).  A group of handles created on the same device is instead driven by ONE cooperative launch
+// whose grid is the union of the ranks' grids; every CTA picks its rank's parameter block and runs the UNCHANGED
+// multi-rank code: the cross-rank accumulators / mailboxes are then plain device pointers instead of NVLink mappings.
+int krotov_group_connect(krotov_handle *hs, int world) {
+    if (!hs || world < 1 || world > kr::kMaxRanks) return KROTOV_ERR_ARG;
+    int total = 0, mx = 0;
+    for (int r = 0; r < world; ++r) {
+        krotov_handle h = hs[r];
+        if (!h) return KROTOV_ERR_ARG;
+        if (h->path != KROTOV_PATH_WARP || h->pair || (h->tiny && world == 1))
+            return fail(h, KROTOV_ERR_UNSUPPORTED, "krotov_group_connect: warp path (one trajectory per warp) only");
+        if (h->device != hs[0]->device || h->L != hs[0]->L || h->N_T != hs[0]->N_T || h->Wt != hs[0]->Wt ||
+            h->lpt != hs[0]->lpt || h->preg != hs[0]->preg || h->wpc != hs[0]->wpc || h->tpw != hs[0]->tpw)
+            return fail(h, KROTOV_ERR_ARG, "krotov_group_connect: ranks must share device, grid shape and kernel instance");
+        total += h->nCTA;
+        mx = std::max(mx, h->nCTA);
+    }
+    if (total > hs[0]->sm_count) return fail(hs[0], KROTOV_ERR_UNSUPPORTED, "krotov_group_connect: more CTAs than SMs");
+    for (int r = 0; r < world; ++r) {
+        krotov_handle h = hs[r];
+        h->rank = r;
+        h->world = world;
+        h->total_ctas = total;
+        h->max_ctas = mx;
+        h->iter_count = 0;
+        for (int q = 0; q < world; ++q)
+            for (int par = 0; par < 2; ++par) h->peer_mbox[par][q] = (double *)hs[q]->d_mbox[par].p;
+    }
+    return KROTOV_OK;
+}
+
+int krotov_group_iterate(krotov_handle *hs, int world, const double *guess_pulses, double *new_pulses, double *g_a_int) {
+    if (!hs || world < 1 || world > kr::kMaxRanks || !guess_pulses || !new_pulses || !g_a_int) return KROTOV_ERR_ARG;
+    krotov_handle h0 = hs[0];
+    const size_t pn = (size_t)h0->L * h0->N_T;
+    int rc;
+    for (int r = 0; r < world; ++r) {
+        if (hs[r]->world != world || hs[r]->rank != r) return fail(hs[r], KROTOV_ERR_STATE, "krotov_group_connect first");
+        if ((rc = iterate_prepare(hs[r], guess_pulses))) return rc;
+    }
+    std::vector<kr::WarpParams> pv(world);
+    int base = 0;
+    for (int r = 0; r < world; ++r) {
+        fill_warp_params(hs[r], 1, pv[r]);
+        pv[r].cta_base = base;
+        base += hs[r]->nCTA;
+        KR_CUDA(hs[r], cudaStreamSynchronize(hs[r]->stream));  // the ranks' preparation ran on their own streams
+    }
+    if ((rc = upload(h0, h0->d_emul, pv))) return rc;
+    kr::WarpParams p0;
+    memset(&p0, 0, sizeof(p0));
+    p0.emul = (const kr::WarpParams *)h0->d_emul.p;
+    p0.emul_ranks = world;
+    p0.wpc = h0->wpc;
+    auto it = kernel_emul_table().find(KernelKey{h0->Wt, h0->preg ? h0->L : 0, h0->lpt});
+    if (it == kernel_emul_table().end())
+        return fail(h0, KROTOV_ERR_UNSUPPORTED, "no emulated-ranks instance of this kernel (W, L)");
+    size_t smem = 0;
+    for (int r = 0; r < world; ++r) smem = std::max(smem, warp_smem_bytes(hs[r]));
+    KR_CUDA(h0, cudaFuncSetAttribute((const void *)it->second, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(base), block(h0->wpc * h0->lpt + 32);
+    void *args[] = {(void *)&p0};
+    KR_CUDA(h0, cudaLaunchCooperativeKernel((const void *)it->second, grid, block, args, smem, h0->stream));
+    KR_CUDA(h0, cudaStreamSynchronize(h0->stream));
+    h0->launches_last += 1;
+    for (int r = 0; r < world; ++r)
+        if ((rc = iterate_finish(hs[r], new_pulses + (size_t)r * pn, g_a_int + (size_t)r * h0->L))) return rc;
     return KROTOV_OK;
 }
 
@@ -1174,10 +1289,12 @@ int krotov_comm_connect(krotov_handle h, int rank, int world, const void *descs)
     h->rank = rank;
     h->world = world;
     h->total_ctas = 0;
+    h->max_ctas = 0;
     for (int r = 0; r < world; ++r) {
         CommDescTail tail;
         memcpy(&tail, (const char *)descs + (size_t)r * KROTOV_COMM_DESC_BYTES + sizeof(CommDesc), sizeof(tail));
         h->total_ctas += tail.nCTA;
+        h->max_ctas = std::max(h->max_ctas, tail.nCTA);
     }
     for (int r = 0; r < world; ++r) {
         if (r == rank) {

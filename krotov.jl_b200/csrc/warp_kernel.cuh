@@ -80,11 +80,26 @@ struct WarpParams {
     unsigned long long *xacc[kMaxRanks];  // several ranks, one-hop sum: fixed-point accumulators of EVERY rank (this
                                // iteration's parity, zero-filled): word (n, l, limb) at [((n*L + l)*4 + limb) * xacc_stride]
     int xacc_stride;           // distance between accumulator words in 8-byte units (1: one line per step, 16: one line per word)
+    int xchg_hier;             // several ranks: 1 = hierarchical sum (rank sum in `acc`, then one add per rank into xacc)
     int total_ctas;            // CTAs of all ranks = arrivals per accumulator word
     int *err_flag;
     long long timeout_cycles;
     long long *prof;           // optional [nCTA][8] cycle counters (KROTOV_PROF=1), see krotov_get_profile
+    // several ranks emulated by ONE cooperative launch on one device (krotov_group_iterate: the multi-rank protocols
+    // on a single-GPU box; ranks as separate launches on one GPU may never be co-resident): the launch parameter then
+    // only carries `emul`, the per-rank parameter blocks in device memory, and CTA b serves the rank whose
+    // [cta_base, cta_base + nCTA) holds b
+    const WarpParams *emul;
+    int emul_ranks, cta_base;
 };
+
+template <bool EMUL>
+__device__ __forceinline__ const WarpParams &select_params(const WarpParams &p0) {
+    if (!EMUL) return p0;
+    const WarpParams *q = p0.emul;
+    for (int r = 0; r + 1 < p0.emul_ranks && (int)blockIdx.x >= q->cta_base + q->nCTA; ++r) ++q;
+    return *q;
+}
 
 __device__ __forceinline__ void st_relaxed_f64(double *p, double v) {
     asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
@@ -334,10 +349,10 @@ __device__ __forceinline__ void poll_broadcast(const double *E, const int L, con
 // A partial that is not finite or not below 2^31 marks the step and all CTAs redo it with the gather protocol.
 constexpr int kFixFrac = 88, kFixLimbBits = 40, kFixLimbs = 3, kFixBiasBit = 119;
 
-__device__ __forceinline__ bool fix_from_double(const double x, unsigned __int128 &biased) {
+__device__ __forceinline__ bool fix_from_double(const double x, unsigned __int128 &biased, const int lim_exp = 31) {
     const unsigned long long bits = (unsigned long long)__double_as_longlong(fabs(x));
     const int ebits = (int)(bits >> 52);
-    if (ebits >= 1023 + 31) return false;  // |x| >= 2^31, Inf or NaN
+    if (ebits >= 1023 + lim_exp) return false;  // |x| >= 2^lim_exp, Inf or NaN
     const unsigned long long mant = (bits & 0xFFFFFFFFFFFFFull) | (ebits ? (1ull << 52) : 0ull);
     const int shift = (ebits ? ebits : 1) - 1075 + kFixFrac;  // |x| = mant * 2^(shift - kFixFrac)
     unsigned __int128 mag = 0;
@@ -527,10 +542,94 @@ __device__ __forceinline__ bool xrank_atomic_sum(const WarpParams &p, const int 
     return true;
 }
 
+// ---- the sum across several ranks, hierarchical: local L2 atomics, then ONE add per rank and word over NVLink --------
+// xrank_atomic_sum above makes every CTA of every rank add into every rank's accumulator: `total_ctas` atomics per word
+// and time step land on one line of every rank (2048 for 8 x 32 CTAs and two controls), and the cost grows with the
+// number of ranks.  Here every CTA adds its fixed-point partial (the 120-bit format of atomic_grid_sum, |partial| < 2^28)
+// into its OWN rank's accumulator with `atom.add`, which returns the previous value: the lane whose add completes the
+// arrival count of a word holds that word's exact rank sum and forwards it -- limb sum, one arrival, a misfit mark --
+// into the same word of every rank's cross-rank accumulator with one `red.add.u64` each (peers over NVLink, fire and
+// forget).  No CTA waits for the rank sum (the mailbox protocol's reducer does), there is no polling reducer, every rank
+// receives `world` adds per word and step, and all ranks round the same exact integer sum: bit-identical pulses.
+// Cross-rank word: limb sum (52 bits: 40 + 8 for <= 255 CTAs per rank + 4 for <= 8 ranks... here <= 2047 CTAs in total)
+// | ranks with a misfit (4 bits) | rank arrivals (4 bits).
+constexpr int kHSumBits = 52, kHMisShift = 52, kHCntShift = 56, kHLimExp = 28;
+
+__device__ __forceinline__ unsigned long long atom_add_u64(unsigned long long *p, unsigned long long v) {
+    unsigned long long old;
+    asm volatile("atom.relaxed.gpu.global.add.u64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(v) : "memory");
+    return old;
+}
+
+__device__ __forceinline__ bool xrank_hier_sum(const WarpParams &p, const int n, const int L, const int lane,
+                                               double (&tot)[kMaxCtrl]) {
+    const int nw = L * kFixLimbs;  // lane q < nw owns word q = (control q / 3, limb q % 3)
+    const int myl = lane / kFixLimbs, myj = lane - myl * kFixLimbs;
+    double mine = 0.0;
+#pragma unroll
+    for (int l = 0; l < kMaxCtrl; ++l)
+        if (l == myl) mine = tot[l];
+    // cross-rank words live in the xacc area with its layout [(n * L + l) * 4 + limb] (the fourth limb slot is unused)
+    const size_t off = (((size_t)n * L + (lane < nw ? myl : 0)) * kXLimbs + (lane < nw ? myj : 0)) * (size_t)p.xacc_stride;
+    if (lane < nw) {
+        unsigned __int128 v;
+        const bool ok = fix_from_double(mine, v, kHLimExp);
+        unsigned long long add = 1ull << 56;  // one CTA arrival
+        if (ok)
+            add += (unsigned long long)(v >> (myj * kFixLimbBits)) & ((1ull << kFixLimbBits) - 1);
+        else
+            add += 1ull << 48;  // one partial that does not fit
+        unsigned long long total = add;
+        if (p.nCTA > 1) total += atom_add_u64(p.acc + (size_t)n * nw + lane, add);
+        if ((int)(total >> 56) == p.nCTA) {  // this add completed the rank's word: forward the rank sum
+            unsigned long long fwd = 1ull << kHCntShift;
+            if ((total >> 48) & 0xFF)
+                fwd += 1ull << kHMisShift;
+            else
+                fwd += total & ((1ull << 48) - 1);
+            for (int i = 1; i <= p.world; ++i) {  // peers first (the long way), own copy last
+                int r = p.rank + i;
+                if (r >= p.world) r -= p.world;
+                red_add_sys_u64(p.xacc[r] + off, fwd);
+            }
+        }
+    }
+    const long long t0 = clock64();
+    int spins = 0;
+    unsigned long long w = 0;
+    const double *mine_p = reinterpret_cast<const double *>(p.xacc[p.rank] + off);
+    for (;;) {
+        if (lane < nw) w = ld_poll_u64<true>(mine_p);
+        const bool pending = lane < nw && (int)(w >> kHCntShift) != p.world;
+        if (!__any_sync(0xffffffffu, pending)) break;
+        if ((++spins & 63) == 0) {
+            if (clock64() - t0 > p.timeout_cycles || *(volatile int *)p.err_flag) {
+                atomicExch(p.err_flag, 1);
+                break;
+            }
+        }
+    }
+    const bool misfit = lane < nw && ((w >> kHMisShift) & 0xF) != 0;
+    if (__any_sync(0xffffffffu, misfit)) return false;
+    // lane l < L rebuilds control l: the bias (2^119 per CTA = 2^39 in limb 2) comes off in the top limb, so the
+    // magnitude (< total_ctas * 2^28 * 2^88) fits the signed 128-bit sum whatever the number of CTAs
+    const int src = (lane < L ? lane : 0) * kFixLimbs;
+    const unsigned long long mask = (1ull << kHSumBits) - 1;
+    const unsigned long long w0 = __shfl_sync(0xffffffffu, w, src) & mask, w1 = __shfl_sync(0xffffffffu, w, src + 1) & mask,
+                             w2 = __shfl_sync(0xffffffffu, w, src + 2) & mask;
+    const long long top = (long long)w2 - ((long long)p.total_ctas << (kFixBiasBit - 2 * kFixLimbBits));
+    const __int128 sum = ((__int128)top << (2 * kFixLimbBits)) + ((__int128)w1 << kFixLimbBits) + (__int128)w0;
+    const bool neg = sum < 0;
+    const double du = fix_mag_to_double((unsigned __int128)(neg ? -sum : sum), neg);
+#pragma unroll
+    for (int l = 0; l < kMaxCtrl; ++l) tot[l] = __shfl_sync(0xffffffffu, du, l < L ? l : 0);
+    return true;
+}
+
 // The communication warp of a CTA (shared by both kernel variants): per time step it waits for the CTA's
 // per-lane partial overlaps (named barrier 1), reduces them in a fixed order, runs the grid / rank exchange,
 // applies the pulse update (src/optimize.jl:351-358) and releases the trajectory warps (named barrier 2).
-__device__ __forceinline__ void comm_warp_run(const WarpParams &p, const int L, const int lane, const int wpc,
+__device__ __forceinline__ void comm_warp_run(const WarpParams &p, const int cta, const int L, const int lane, const int wpc,
                                               const int nthr_all, double *red, double *eps_s, double *gbuf) {
     const int N_T = p.N_T;
     if (p.mode != 1) return;
@@ -561,10 +660,15 @@ __device__ __forceinline__ void comm_warp_run(const WarpParams &p, const int L, 
                 if (l < L) tot[l] += __shfl_xor_sync(0xffffffffu, tot[l], o);
         }
         const long long c2 = clock64();
-        bool summed = false;
+        bool summed = false, acc_used = false;
         if (p.world > 1 && p.xacc[0] != nullptr) {
-            summed = xrank_atomic_sum(p, n, L, lane, tot);
-            if (!summed && blockIdx.x == 0 && lane == 0) atomicAdd(p.err_flag + 1, 1);  // krotov_info.fallback_steps
+            if (p.xchg_hier) {
+                summed = xrank_hier_sum(p, n, L, lane, tot);
+                acc_used = true;  // the rank's accumulator words of this step are spent
+            } else {
+                summed = xrank_atomic_sum(p, n, L, lane, tot);
+            }
+            if (!summed && cta == 0 && lane == 0) atomicAdd(p.err_flag + 1, 1);  // krotov_info.fallback_steps
         }
         if (p.world > 1 && !summed) {
             // ---- several ranks.  Every CTA adds its partial into the rank's fixed-point accumulator (and leaves it in
@@ -572,18 +676,18 @@ __device__ __forceinline__ void comm_warp_run(const WarpParams &p, const int L, 
             // of EVERY rank over NVLink, and every CTA of every rank polls its own rank's mailbox and adds the
             // `world` rank sums in rank order: identical bits everywhere, no broadcast hop behind the NVLink hop.
             double *Rn = p.R + (size_t)n * L * p.nCTA;
-            const bool use_acc = p.acc != nullptr && p.nCTA > 1;
+            const bool use_acc = p.acc != nullptr && p.nCTA > 1 && !acc_used;
             if (p.nCTA > 1) {
 #pragma unroll
                 for (int l = 0; l < kMaxCtrl; ++l)
-                    if (l < L && lane == l) st_relaxed_gpu_f64(Rn + (size_t)l * p.nCTA + blockIdx.x, tot[l]);
+                    if (l < L && lane == l) st_relaxed_gpu_f64(Rn + (size_t)l * p.nCTA + cta, tot[l]);
             }
             bool have_rank_sum = p.nCTA == 1;
             if (use_acc)
                 have_rank_sum = atomic_grid_sum(p.acc + (size_t)n * L * kFixLimbs, p.nCTA, L, lane, tot, p.err_flag,
-                                                p.timeout_cycles, blockIdx.x == 0);
+                                                p.timeout_cycles, cta == 0);
             const size_t off = (size_t)n * L * p.world;  // mailbox layout [n][l][rank]
-            if (blockIdx.x == 0) {
+            if (cta == 0) {
                 if (!have_rank_sum) {
                     if (use_acc && lane == 0) atomicAdd(p.err_flag + 1, 1);  // krotov_info.fallback_steps
                     reducer_gather<false>(Rn, p.nCTA, L, lane, gbuf, tot, p.err_flag, p.timeout_cycles);
@@ -596,7 +700,7 @@ __device__ __forceinline__ void comm_warp_run(const WarpParams &p, const int L, 
                 reducer_gather<true>(p.mbox[p.rank] + off, p.world, L, lane, gbuf, tot, p.err_flag, p.timeout_cycles);
             } else {
                 double *En = p.E + (size_t)n * L;
-                if (blockIdx.x == 0) {
+                if (cta == 0) {
                     reducer_gather<true>(p.mbox[p.rank] + off, p.world, L, lane, gbuf, tot, p.err_flag, p.timeout_cycles);
 #pragma unroll
                     for (int l = 0; l < kMaxCtrl; ++l)
@@ -608,17 +712,17 @@ __device__ __forceinline__ void comm_warp_run(const WarpParams &p, const int L, 
             summed = true;
         } else if (p.world == 1 && p.acc != nullptr && p.nCTA > 1) {
             summed = atomic_grid_sum(p.acc + (size_t)n * L * kFixLimbs, p.nCTA, L, lane, tot, p.err_flag, p.timeout_cycles);
-            if (!summed && blockIdx.x == 0 && lane == 0) atomicAdd(p.err_flag + 1, 1);  // krotov_info.fallback_steps
+            if (!summed && cta == 0 && lane == 0) atomicAdd(p.err_flag + 1, 1);  // krotov_info.fallback_steps
         }
         if (!summed && p.nCTA > 1) {
             // ---- gather + broadcast (one rank; also the fallback of the one-hop sum).  R[n][l][cta]: CTA partials;
             // E[n][l]: the grid-wide sums, written by the reducer
             double *Rn = p.R + (size_t)n * L * p.nCTA;
             double *En = p.E + (size_t)n * L;
-            if (blockIdx.x != 0) {
+            if (cta != 0) {
 #pragma unroll
                 for (int l = 0; l < kMaxCtrl; ++l)
-                    if (l < L && lane == l) st_relaxed_gpu_f64(Rn + (size_t)l * p.nCTA + blockIdx.x, tot[l]);
+                    if (l < L && lane == l) st_relaxed_gpu_f64(Rn + (size_t)l * p.nCTA + cta, tot[l]);
                 poll_broadcast(En, L, lane, tot, p.err_flag, p.timeout_cycles);
             } else {
 #pragma unroll
@@ -642,23 +746,25 @@ __device__ __forceinline__ void comm_warp_run(const WarpParams &p, const int L, 
             const double d_eps = __dmul_rn(a_ln, mine);      // src/optimize.jl:355
             const double e_new = __dadd_rn(e_old, d_eps);    // :356
             eps_s[lane] = e_new;
-            if (blockIdx.x == 0) {
+            if (cta == 0) {
                 p.eps_new[(size_t)lane * N_T + n] = e_new;
                 ga = __dadd_rn(ga, __dmul_rn(__dmul_rn(a_ln, __dmul_rn(fabs(mine), fabs(mine))), dtn));  // :357
             }
         }
         bar_arrive(2, nthr_all);  // barrier B: eps_s is valid
     }
-    if (blockIdx.x == 0 && lane < L) p.g_a_int[lane] = ga;
+    if (cta == 0 && lane < L) p.g_a_int[lane] = ga;
     if (p.prof != nullptr && lane == 0) {
-        p.prof[blockIdx.x * 8 + 3] = c_wait_a;
-        p.prof[blockIdx.x * 8 + 4] = c_reduce;
-        p.prof[blockIdx.x * 8 + 5] = c_gather;
+        p.prof[cta * 8 + 3] = c_wait_a;
+        p.prof[cta * 8 + 4] = c_reduce;
+        p.prof[cta * 8 + 5] = c_gather;
     }
 }
 
-template <int W, int LT /*0 = runtime L, rows reloaded from L1/L2 per use*/, int MAXTHREADS, int LPT = 32>
-__global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid_constant__ WarpParams p) {
+template <int W, int LT /*0 = runtime L, rows reloaded from L1/L2 per use*/, int MAXTHREADS, int LPT = 32, bool EMUL = false>
+__global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid_constant__ WarpParams p0) {
+    const WarpParams &p = select_params<EMUL>(p0);
+    const int cta = EMUL ? (int)blockIdx.x - p.cta_base : (int)blockIdx.x;
     constexpr bool PREG = (LT > 0);
     constexpr int NT = PREG ? (1 + LT) : 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -681,12 +787,12 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
     const int N_T = p.N_T;
 
     if (is_comm) {
-        comm_warp_run(p, L, lane, wpc * (LPT / 32), nthr_all, red, eps_s, gbuf);
+        comm_warp_run(p, cta, L, lane, wpc * (LPT / 32), nthr_all, red, eps_s, gbuf);
         return;
     }
 
     // -------------------------------------------------------------------- trajectory warps
-    const int gw = blockIdx.x * wpc + warp;       // global trajectory-warp index
+    const int gw = cta * wpc + warp;       // global trajectory-warp index
     const int kbase = gw * tpw;                   // first trajectory of this warp
     double2 *bufA = vbuf + (size_t)warp * 2 * LPT;
     double2 *bufB = bufA + LPT;
@@ -958,11 +1064,11 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
 
     if (p.prof != nullptr && warp == 0 && lane == 0) {
         const long long t_end = clock64();
-        p.prof[blockIdx.x * 8 + 0] = t_bw_end - t_begin;
-        p.prof[blockIdx.x * 8 + 1] = t_end - t_bw_end;
-        p.prof[blockIdx.x * 8 + 2] = t_wait_b;
-        p.prof[blockIdx.x * 8 + 6] = t_overlap;
-        p.prof[blockIdx.x * 8 + 7] = t_step;
+        p.prof[cta * 8 + 0] = t_bw_end - t_begin;
+        p.prof[cta * 8 + 1] = t_end - t_bw_end;
+        p.prof[cta * 8 + 2] = t_wait_b;
+        p.prof[cta * 8 + 6] = t_overlap;
+        p.prof[cta * 8 + 7] = t_step;
     }
     // ---- final states and tau_k = <tgt_k|psi_k(T)>  (src/optimize.jl:378-381)
     for (int t = 0; t < tpw; ++t) {

@@ -185,3 +185,87 @@ class KrotovCuda:
         assert len(blob) == world * B.COMM_DESC_BYTES
         buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
         self._check(self._lib.krotov_comm_connect(self._h, int(rank), int(world), buf))
+
+
+class KrotovCudaGroup:
+    """Several ranks EMULATED on one device behind the interface of one :class:`KrotovCuda` (tests and diagnostics).
+
+    Every rank is a real handle holding its shard of the trajectories; ``krotov_group_connect`` wires their mailboxes
+    and cross-rank accumulators together in-process and ``krotov_group_iterate`` runs all ranks' CTAs in ONE
+    cooperative launch, so the multi-rank exchange protocols of the persistent kernel can be exercised (and compared
+    with a one-rank run) on a single-GPU box.  ``bounds[r] = (lo, hi)``: trajectories of rank r; ``gens[r]``: indices
+    (into the caller's generator list) of the generators rank r holds, in the rank's local order."""
+
+    def __init__(self, engines, bounds, gens):
+        self.engines, self.bounds, self.gens = list(engines), list(bounds), [np.asarray(g, int) for g in gens]
+        e0 = self.engines[0]
+        self._lib = e0._lib
+        self.N = sum(e.N for e in self.engines)
+        self.d, self.L, self.N_T = e0.d, e0.L, e0.N_T
+        self.n_gen = sum(len(g) for g in self.gens)
+        self.world = len(self.engines)
+        self.pulses_all = None  # every rank's copy of the last new pulses: (world, L, N_T)
+        arr = (C.c_void_p * self.world)(*[e._h for e in self.engines])
+        self._handles = arr
+        rc = self._lib.krotov_group_connect(arr, self.world)
+        if rc != B.KROTOV_OK:
+            raise B.KrotovCudaError(rc, "; ".join(self._lib.krotov_last_error(e._h).decode() for e in self.engines))
+
+    def close(self):
+        for e in self.engines:
+            e.close()
+
+    def info(self):
+        out = self.engines[0].info()
+        out["grid_blocks"] = sum(e.info()["grid_blocks"] for e in self.engines)
+        out["fallback_steps"] = max(e.info()["fallback_steps"] for e in self.engines)
+        out["ranks"] = self.world
+        return out
+
+    def set_cheby(self, direction, dt_class_of_step, dt_of_class, E_min, Delta, m, tab):
+        E_min, Delta = np.asarray(E_min), np.asarray(Delta)
+        m, tab = np.asarray(m), np.asarray(tab)
+        for e, g in zip(self.engines, self.gens):
+            e.set_cheby(direction, dt_class_of_step, dt_of_class, E_min[g], Delta[g], m[g], tab[g])
+
+    def forward(self, pulses):
+        for e in self.engines:  # no cross-rank dependency in a plain forward sweep
+            e.forward(pulses)
+
+    def set_chi(self, chi):
+        chi = np.asarray(chi)
+        for e, (lo, hi) in zip(self.engines, self.bounds):
+            e.set_chi(chi[lo:hi])
+
+    def set_chi_coeffs(self, coef):
+        coef = np.asarray(coef)
+        for e, (lo, hi) in zip(self.engines, self.bounds):
+            e.set_chi_coeffs(coef[lo:hi])
+
+    def iterate(self, guess_pulses, out_pulses=None):
+        g = np.ascontiguousarray(guess_pulses, np.float64).reshape(self.L, self.N_T)
+        allp = np.empty((self.world, self.L, self.N_T), np.float64)
+        ga = np.empty((self.world, self.L), np.float64)
+        rc = self._lib.krotov_group_iterate(self._handles, self.world, _ptr(g), _ptr(allp), _ptr(ga))
+        if rc != B.KROTOV_OK:
+            raise B.KrotovCudaError(rc, "; ".join(self._lib.krotov_last_error(e._h).decode() for e in self.engines))
+        self.pulses_all, self.g_a_all = allp, ga
+        if out_pulses is not None:
+            out_pulses[...] = allp[0]
+            return out_pulses, ga[0]
+        return allp[0].copy(), ga[0].copy()
+
+    def states(self):
+        return np.concatenate([e.states() for e in self.engines], axis=0)
+
+    def tau(self):
+        return np.concatenate([e.tau() for e in self.engines], axis=0)
+
+    def storage(self, which, k, n0=0, n1=None):
+        for e, (lo, hi) in zip(self.engines, self.bounds):
+            if lo <= k < hi:
+                return e.storage(which, k - lo, n0, n1)
+        raise IndexError(k)
+
+    def profile(self, cta=-1):
+        return self.engines[0].profile(cta)

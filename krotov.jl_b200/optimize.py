@@ -72,7 +72,7 @@ def krotov_iteration(wrk, eps_i, eps_ip1):
             chi = chi_fn(Psi, wrk.trajectories)
         lo, hi = wrk._shard
         wrk.engine.set_chi(np.array(chi[lo:hi], np.complex128))
-    elif wrk.comm is not None and wrk.comm.world > 1 and wrk.functional == B.CHI_SM:
+    elif wrk._n_ranks > 1 and wrk.functional == B.CHI_SM:
         # the only functional whose chi needs a sum over ALL ranks' tau: done here from the gathered tau
         tau, w, n = wrk.result.tau_vals, wrk._weight, wrk.N
         s = np.sum(w * tau)

@@ -329,22 +329,42 @@ class KrotovWrk:
         rank, world = (comm.rank, comm.world) if comm is not None else (0, 1)
         from .distributed import shard_bounds
 
-        lo, hi = shard_bounds(gen_of_traj, rank, world)
-        self._shard = (lo, hi)
-        local_gens = sorted(set(int(g) for g in gen_of_traj[lo:hi]))
-        remap = {g: i for i, g in enumerate(local_gens)}
-        self._H0 = [H0[g] for g in local_gens]
-        self._Hc = [Hc[g] for g in local_gens]
         S = np.array(self.update_shapes, np.float64).reshape(L, -1)
         pk = self.fw_prop_kwargs[0]
         device = int(self.kwargs.get("device", comm.device if comm is not None else 0))
-        self.engine = KrotovCuda(
-            tlist=tlist, H0=self._H0, Hc=self._Hc,
-            gen_of_traj=np.array([remap[int(g)] for g in gen_of_traj[lo:hi]], np.int32),
-            psi0=psi0[lo:hi], target=None if target is None else target[lo:hi], weight=weight[lo:hi],
-            update_shape=S, lambda_a=self.lambda_vals, functional=functional, n_traj_global=N,
-            store_fw=self.store_fw, device=device, force_path=int(self.kwargs.get("force_path", 0)),
-            csr=bool(self.kwargs.get("csr_generators", False)))
+
+        def make_engine(lo, hi):
+            local_gens = sorted(set(int(g) for g in gen_of_traj[lo:hi]))
+            remap = {g: i for i, g in enumerate(local_gens)}
+            eng = KrotovCuda(
+                tlist=tlist, H0=[H0[g] for g in local_gens], Hc=[Hc[g] for g in local_gens],
+                gen_of_traj=np.array([remap[int(g)] for g in gen_of_traj[lo:hi]], np.int32),
+                psi0=psi0[lo:hi], target=None if target is None else target[lo:hi], weight=weight[lo:hi],
+                update_shape=S, lambda_a=self.lambda_vals, functional=functional, n_traj_global=N,
+                store_fw=self.store_fw, device=device, force_path=int(self.kwargs.get("force_path", 0)),
+                csr=bool(self.kwargs.get("csr_generators", False)))
+            return eng, local_gens
+
+        emulate = int(self.kwargs.get("emulate_ranks", 0) or 0)
+        if emulate > 1:
+            # several ranks emulated on ONE device (tests / diagnostics): one handle per shard, one cooperative launch
+            if comm is not None and world > 1:
+                raise ArgumentError("`emulate_ranks` and a multi-rank `comm` exclude each other")
+            from .engine import KrotovCudaGroup
+
+            bounds = [shard_bounds(gen_of_traj, r, emulate) for r in range(emulate)]
+            made = [make_engine(lo, hi) for lo, hi in bounds]
+            self.engine = KrotovCudaGroup([m[0] for m in made], bounds, [m[1] for m in made])
+            self._shard = (0, N)
+            self._n_ranks = emulate
+            self._H0, self._Hc = H0, Hc
+        else:
+            lo, hi = shard_bounds(gen_of_traj, rank, world)
+            self._shard = (lo, hi)
+            self._n_ranks = world
+            self.engine, local_gens = make_engine(lo, hi)
+            self._H0 = [H0[g] for g in local_gens]
+            self._Hc = [Hc[g] for g in local_gens]
         if comm is not None and world > 1:
             comm.connect(self.engine)
         # ---- Chebyshev settings of both directions (init_prop: un-widened ranges of the guess pulses)

@@ -999,3 +999,69 @@ def test_block_path_graph_replay_equals_direct_launches(monkeypatch):
     assert b["info"]["graph_replays"] == 0
     assert np.array_equal(a["pulses"], b["pulses"]) and a["J_T"] == b["J_T"]
     assert a["info"]["launches_last"] == b["info"]["launches_last"]
+
+
+# ---- several ranks on ONE device: the multi-rank exchange protocols without a second GPU ------------------------------
+_EXCHANGE = {"hier": 1, "onehop": 2, "mbox": 3}
+
+
+@pytest.mark.parametrize("ranks,n_samples,n_grid,xchg", [
+    (2, 8, 201, "hier"), (2, 8, 201, "onehop"), (2, 8, 201, "mbox"), (2, 2, 101, "hier"), (2, 2, 101, "mbox"),
+    (4, 16, 101, "hier"), (3, 12, 101, "mbox"), (8, 32, 61, "hier"), (8, 32, 61, "onehop"), (8, 64, 41, "mbox")])
+def test_emulated_ranks_match_one_rank_and_oracle(ranks, n_samples, n_grid, xchg, monkeypatch):
+    """The ensemble sharded over `ranks` handles on one device, all ranks' CTAs in ONE cooperative launch
+    (`krotov_group_iterate`): the unchanged multi-rank kernel code with the hierarchical sum (local accumulator, one
+    add per rank into every rank's cross-rank accumulator), the one-hop sum and the mailbox protocol.  Every rank must
+    end with bit-identical pulses; the result must agree with the one-rank run and with the oracle."""
+    from oracle import c_oracle as C
+
+    w = W.c4_ensemble(n_samples=n_samples, n_grid=n_grid)
+    single = run_product(w, 2)
+    monkeypatch.setenv("KROTOV_XCHG", xchg)
+    seen = {}
+
+    def cb(wrk, it, eps_new, eps_old):
+        if it >= 1:
+            seen.setdefault("all", []).append(wrk.engine.pulses_all.copy())
+            seen.setdefault("ga", []).append(wrk.engine.g_a_all.copy())
+            seen["info"] = wrk.engine.info()
+
+    got = run_product(w, 2, emulate_ranks=ranks, callback=cb)
+    for allp, ga in zip(seen["all"], seen["ga"]):
+        assert allp.shape[0] == ranks
+        for r in range(1, ranks):  # replicas hold the same bits: same exact sum rounded once, same update
+            assert np.array_equal(allp[r], allp[0]) and np.array_equal(ga[r], ga[0])
+    assert seen["info"]["exchange"] == _EXCHANGE[xchg] and seen["info"]["ranks"] == ranks
+    assert seen["info"]["fallback_steps"] == 0
+    assert np.abs(np.array(got["J_T"]) - np.array(single["J_T"])).max() < 1e-12
+    assert np.abs(got["pulses"] - single["pulses"]).max() < 1e-12
+    assert np.abs(np.array(got["result"].states) - np.array(single["result"].states)).max() < 1e-11
+    ref = C.optimize_krotov_c(W.to_oracle(w), 2)
+    assert_parity(got, ref["J_T"], ref["pulses"], rtol=1e-10, atol=5e-13)
+
+
+@pytest.mark.parametrize("xchg", ["hier", "onehop"])
+def test_emulated_ranks_fall_back_when_a_partial_does_not_fit(xchg, monkeypatch):
+    """chi scaled by 1e13 (lambda_a alike, so the optimisation is unchanged): the overlap sums leave the fixed-point
+    range, every CTA of every rank sees the same misfit mark and redoes the step with the mailbox protocol."""
+    big = 1e13
+
+    def big_chi(states, trajectories, tau=None):
+        n = len(trajectories)
+        s = sum(t.weight * x for t, x in zip(trajectories, tau))
+        return [big * (t.weight / n**2) * s * t.target_state for t in trajectories]
+
+    w = W.c4_ensemble(n_samples=8, n_grid=41)
+    single = run_product(w, 2)
+    monkeypatch.setenv("KROTOV_XCHG", xchg)
+    fb = []
+
+    def cb(wrk, it, eps_new, eps_old):
+        if it >= 1:
+            fb.append(wrk.engine.info()["fallback_steps"])
+            assert all(np.array_equal(p, wrk.engine.pulses_all[0]) for p in wrk.engine.pulses_all)
+
+    got = run_product(w, 2, emulate_ranks=2, callback=cb, chi=big_chi, lambda_a=big * w.lambda_a)
+    assert min(fb) > 20  # most of the 40 steps carry sums beyond 2^28
+    assert np.abs(np.array(got["J_T"]) - np.array(single["J_T"])).max() < 1e-12
+    assert np.abs(got["pulses"] - single["pulses"]).max() < 1e-11

@@ -37,8 +37,11 @@ def to_problem(w, **kwargs):
 def run_product(w, iters, **kwargs):
     """Optimise through the public API, recording per-iteration J_T, g_a_int, tau."""
     hist = dict(J_T=[], g_a_int=[], tau=[])
+    extra_cb = kwargs.pop("callback", None)
 
     def record(wrk, it, eps_new, eps_old):
+        if extra_cb is not None:
+            extra_cb(wrk, it, eps_new, eps_old)
         hist["J_T"].append(wrk.result.J_T)
         hist["tau"].append(np.array(wrk.result.tau_vals))
         if it > 0:
