@@ -108,7 +108,8 @@ typedef struct {
     int32_t nnz_union;       /* nonzeros of the union pattern                        */
     int32_t grid_blocks;     /* CTAs of the persistent kernel                        */
     int32_t block_threads;
-    int32_t m_fw, m_bw;      /* Chebyshev coefficient counts currently loaded (max over generators) */
+    int32_t m_fw;            /* Chebyshev coefficient counts currently loaded (max over generators): forward, */
+    int32_t m_bw;            /* backward */
     int32_t sm_count;
     int32_t exchange;        /* cross-rank protocol of the last launch: 0 none (one rank), 1 hierarchical sum (local
                                 accumulator, then one add per rank over NVLink), 2 one-hop sum (every CTA adds into every

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkrotov_cuda.so")
+# KROTOV_CUDA_LIB points at another build of the same library (A/B experiments); the default is the in-tree build
+LIB_PATH = os.environ.get("KROTOV_CUDA_LIB") or os.path.join(_HERE, "libkrotov_cuda.so")
 
 KROTOV_OK = 0
 ERR_NAMES = {1: "KROTOV_ERR_ARG", 2: "KROTOV_ERR_CUDA", 3: "KROTOV_ERR_STATE", 4: "KROTOV_ERR_UNSUPPORTED",

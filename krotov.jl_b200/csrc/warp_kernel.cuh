@@ -626,6 +626,102 @@ __device__ __forceinline__ bool xrank_hier_sum(const WarpParams &p, const int n,
     return true;
 }
 
+// ---- exchange paths that are kept OUT OF LINE ------------------------------------------------------------------------
+// The comm warp's per-step loop used to carry every protocol inline: ~58 KB of code of which a step on one rank runs a
+// few hundred bytes, spread between jumps over the rest.  That cost the single-CTA case a full microsecond per time
+// step (instruction fetch; C3: 7.8 -> 10.1 ms per iteration as the protocols accumulated), so everything but the
+// one-rank atomic sum now lives in two functions that are called, not inlined.  `tot` travels through local memory.
+
+// Several ranks: hierarchical sum or one-hop sum, with the mailbox protocol as their fallback (and as a protocol of its
+// own).  On return tot[] holds the sums over all CTAs of all ranks, the same bits on every CTA of every rank.
+static __device__ __noinline__ void exchange_ranks(const WarpParams *pp, const int cta, const int n, const int L, const int lane,
+                                            double *tot_io, double *gbuf) {
+    const WarpParams &p = *pp;
+    double tot[kMaxCtrl];
+#pragma unroll
+    for (int l = 0; l < kMaxCtrl; ++l) tot[l] = tot_io[l];
+    bool summed = false, acc_used = false;
+    if (p.xacc[0] != nullptr) {
+        if (p.xchg_hier) {
+            summed = xrank_hier_sum(p, n, L, lane, tot);
+            acc_used = true;  // the rank's accumulator words of this step are spent
+        } else {
+            summed = xrank_atomic_sum(p, n, L, lane, tot);
+        }
+        if (!summed && cta == 0 && lane == 0) atomicAdd(p.err_flag + 1, 1);  // krotov_info.fallback_steps
+    }
+    if (!summed) {
+        // ---- mailboxes.  Every CTA adds its partial into the rank's fixed-point accumulator (and leaves it in
+        // R for the fallback); the reducer (CTA 0) alone waits for the exact rank sum, pushes it into the mailbox
+        // of EVERY rank over NVLink, and every CTA of every rank polls its own rank's mailbox and adds the
+        // `world` rank sums in rank order: identical bits everywhere, no broadcast hop behind the NVLink hop.
+        double *Rn = p.R + (size_t)n * L * p.nCTA;
+        const bool use_acc = p.acc != nullptr && p.nCTA > 1 && !acc_used;
+        if (p.nCTA > 1) {
+#pragma unroll
+            for (int l = 0; l < kMaxCtrl; ++l)
+                if (l < L && lane == l) st_relaxed_gpu_f64(Rn + (size_t)l * p.nCTA + cta, tot[l]);
+        }
+        bool have_rank_sum = p.nCTA == 1;
+        if (use_acc)
+            have_rank_sum = atomic_grid_sum(p.acc + (size_t)n * L * kFixLimbs, p.nCTA, L, lane, tot, p.err_flag,
+                                            p.timeout_cycles, cta == 0);
+        const size_t off = (size_t)n * L * p.world;  // mailbox layout [n][l][rank]
+        if (cta == 0) {
+            if (!have_rank_sum) {
+                if (use_acc && lane == 0) atomicAdd(p.err_flag + 1, 1);  // krotov_info.fallback_steps
+                reducer_gather<false>(Rn, p.nCTA, L, lane, gbuf, tot, p.err_flag, p.timeout_cycles);
+            }
+#pragma unroll
+            for (int l = 0; l < kMaxCtrl; ++l)
+                if (l < L && lane < p.world) st_relaxed_f64(p.mbox[lane] + off + (size_t)l * p.world + p.rank, tot[l]);
+        }
+        if (p.mbox_all || p.nCTA == 1) {
+            reducer_gather<true>(p.mbox[p.rank] + off, p.world, L, lane, gbuf, tot, p.err_flag, p.timeout_cycles);
+        } else {
+            double *En = p.E + (size_t)n * L;
+            if (cta == 0) {
+                reducer_gather<true>(p.mbox[p.rank] + off, p.world, L, lane, gbuf, tot, p.err_flag, p.timeout_cycles);
+#pragma unroll
+                for (int l = 0; l < kMaxCtrl; ++l)
+                    if (l < L && lane == l) st_relaxed_gpu_f64(En + l, tot[l]);
+            } else {
+                poll_broadcast(En, L, lane, tot, p.err_flag, p.timeout_cycles);
+            }
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < kMaxCtrl; ++l) tot_io[l] = tot[l];
+}
+
+// One rank, gather + broadcast: the protocol before the atomic sum existed, and its fallback when a partial does not
+// fit the fixed-point range.  R[n][l][cta]: CTA partials; E[n][l]: the grid-wide sums, written by the reducer (CTA 0).
+static __device__ __noinline__ void exchange_gather(const WarpParams *pp, const int cta, const int n, const int L, const int lane,
+                                             double *tot_io, double *gbuf) {
+    const WarpParams &p = *pp;
+    double tot[kMaxCtrl];
+#pragma unroll
+    for (int l = 0; l < kMaxCtrl; ++l) tot[l] = tot_io[l];
+    double *Rn = p.R + (size_t)n * L * p.nCTA;
+    double *En = p.E + (size_t)n * L;
+    if (cta != 0) {
+#pragma unroll
+        for (int l = 0; l < kMaxCtrl; ++l)
+            if (l < L && lane == l) st_relaxed_gpu_f64(Rn + (size_t)l * p.nCTA + cta, tot[l]);
+        poll_broadcast(En, L, lane, tot, p.err_flag, p.timeout_cycles);
+    } else {
+#pragma unroll
+        for (int l = 0; l < kMaxCtrl; ++l)
+            if (l < L && lane == l) st_relaxed_gpu_f64(Rn + (size_t)l * p.nCTA, tot[l]);
+        reducer_gather<false>(Rn, p.nCTA, L, lane, gbuf, tot, p.err_flag, p.timeout_cycles);
+#pragma unroll
+        for (int l = 0; l < kMaxCtrl; ++l)
+            if (l < L && lane == l) st_relaxed_gpu_f64(En + l, tot[l]);
+    }
+#pragma unroll
+    for (int l = 0; l < kMaxCtrl; ++l) tot_io[l] = tot[l];
+}
+
 // The communication warp of a CTA (shared by both kernel variants): per time step it waits for the CTA's
 // per-lane partial overlaps (named barrier 1), reduces them in a fixed order, runs the grid / rank exchange,
 // applies the pulse update (src/optimize.jl:351-358) and releases the trajectory warps (named barrier 2).
@@ -660,79 +756,26 @@ __device__ __forceinline__ void comm_warp_run(const WarpParams &p, const int cta
                 if (l < L) tot[l] += __shfl_xor_sync(0xffffffffu, tot[l], o);
         }
         const long long c2 = clock64();
-        bool summed = false, acc_used = false;
-        if (p.world > 1 && p.xacc[0] != nullptr) {
-            if (p.xchg_hier) {
-                summed = xrank_hier_sum(p, n, L, lane, tot);
-                acc_used = true;  // the rank's accumulator words of this step are spent
-            } else {
-                summed = xrank_atomic_sum(p, n, L, lane, tot);
-            }
-            if (!summed && cta == 0 && lane == 0) atomicAdd(p.err_flag + 1, 1);  // krotov_info.fallback_steps
-        }
-        if (p.world > 1 && !summed) {
-            // ---- several ranks.  Every CTA adds its partial into the rank's fixed-point accumulator (and leaves it in
-            // R for the fallback); the reducer (CTA 0) alone waits for the exact rank sum, pushes it into the mailbox
-            // of EVERY rank over NVLink, and every CTA of every rank polls its own rank's mailbox and adds the
-            // `world` rank sums in rank order: identical bits everywhere, no broadcast hop behind the NVLink hop.
-            double *Rn = p.R + (size_t)n * L * p.nCTA;
-            const bool use_acc = p.acc != nullptr && p.nCTA > 1 && !acc_used;
-            if (p.nCTA > 1) {
+        bool summed = p.nCTA == 1 && p.world == 1;
+        if (p.world > 1) {
+            double tl[kMaxCtrl];
 #pragma unroll
-                for (int l = 0; l < kMaxCtrl; ++l)
-                    if (l < L && lane == l) st_relaxed_gpu_f64(Rn + (size_t)l * p.nCTA + cta, tot[l]);
-            }
-            bool have_rank_sum = p.nCTA == 1;
-            if (use_acc)
-                have_rank_sum = atomic_grid_sum(p.acc + (size_t)n * L * kFixLimbs, p.nCTA, L, lane, tot, p.err_flag,
-                                                p.timeout_cycles, cta == 0);
-            const size_t off = (size_t)n * L * p.world;  // mailbox layout [n][l][rank]
-            if (cta == 0) {
-                if (!have_rank_sum) {
-                    if (use_acc && lane == 0) atomicAdd(p.err_flag + 1, 1);  // krotov_info.fallback_steps
-                    reducer_gather<false>(Rn, p.nCTA, L, lane, gbuf, tot, p.err_flag, p.timeout_cycles);
-                }
+            for (int l = 0; l < kMaxCtrl; ++l) tl[l] = tot[l];
+            exchange_ranks(&p, cta, n, L, lane, tl, gbuf);
 #pragma unroll
-                for (int l = 0; l < kMaxCtrl; ++l)
-                    if (l < L && lane < p.world) st_relaxed_f64(p.mbox[lane] + off + (size_t)l * p.world + p.rank, tot[l]);
-            }
-            if (p.mbox_all || p.nCTA == 1) {
-                reducer_gather<true>(p.mbox[p.rank] + off, p.world, L, lane, gbuf, tot, p.err_flag, p.timeout_cycles);
-            } else {
-                double *En = p.E + (size_t)n * L;
-                if (cta == 0) {
-                    reducer_gather<true>(p.mbox[p.rank] + off, p.world, L, lane, gbuf, tot, p.err_flag, p.timeout_cycles);
-#pragma unroll
-                    for (int l = 0; l < kMaxCtrl; ++l)
-                        if (l < L && lane == l) st_relaxed_gpu_f64(En + l, tot[l]);
-                } else {
-                    poll_broadcast(En, L, lane, tot, p.err_flag, p.timeout_cycles);
-                }
-            }
+            for (int l = 0; l < kMaxCtrl; ++l) tot[l] = tl[l];
             summed = true;
-        } else if (p.world == 1 && p.acc != nullptr && p.nCTA > 1) {
+        } else if (p.acc != nullptr && p.nCTA > 1) {
             summed = atomic_grid_sum(p.acc + (size_t)n * L * kFixLimbs, p.nCTA, L, lane, tot, p.err_flag, p.timeout_cycles);
             if (!summed && cta == 0 && lane == 0) atomicAdd(p.err_flag + 1, 1);  // krotov_info.fallback_steps
         }
-        if (!summed && p.nCTA > 1) {
-            // ---- gather + broadcast (one rank; also the fallback of the one-hop sum).  R[n][l][cta]: CTA partials;
-            // E[n][l]: the grid-wide sums, written by the reducer
-            double *Rn = p.R + (size_t)n * L * p.nCTA;
-            double *En = p.E + (size_t)n * L;
-            if (cta != 0) {
+        if (!summed) {
+            double tl[kMaxCtrl];
 #pragma unroll
-                for (int l = 0; l < kMaxCtrl; ++l)
-                    if (l < L && lane == l) st_relaxed_gpu_f64(Rn + (size_t)l * p.nCTA + cta, tot[l]);
-                poll_broadcast(En, L, lane, tot, p.err_flag, p.timeout_cycles);
-            } else {
+            for (int l = 0; l < kMaxCtrl; ++l) tl[l] = tot[l];
+            exchange_gather(&p, cta, n, L, lane, tl, gbuf);
 #pragma unroll
-                for (int l = 0; l < kMaxCtrl; ++l)
-                    if (l < L && lane == l) st_relaxed_gpu_f64(Rn + (size_t)l * p.nCTA, tot[l]);
-                reducer_gather<false>(Rn, p.nCTA, L, lane, gbuf, tot, p.err_flag, p.timeout_cycles);
-#pragma unroll
-                for (int l = 0; l < kMaxCtrl; ++l)
-                    if (l < L && lane == l) st_relaxed_gpu_f64(En + l, tot[l]);
-            }
+            for (int l = 0; l < kMaxCtrl; ++l) tot[l] = tl[l];
         }
         const long long c3 = clock64();
         c_wait_a += c1 - c0;

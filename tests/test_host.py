@@ -329,3 +329,77 @@ def test_cross_rank_fixed_point_word_format():
     # all arrivals misfit: the misfit field holds them without touching the arrival count
     wd = MAXARR * ((1 << CNT) + (1 << MIS))
     assert (wd >> CNT) == MAXARR and ((wd >> MIS) & 0x7FF) == MAXARR and wd < (1 << 64)
+
+
+# ---- the Julia module (julia/Krotov) cannot run here: keep its bindings in step with the header mechanically ---------------
+_C2JL = {"int32_t": "Int32", "int64_t": "Int64", "double": "Float64", "int": "Cint", "const double *": "Ptr{Float64}",
+         "double *": "Ptr{Float64}", "const int32_t *": "Ptr{Int32}", "const uint8_t *": "Ptr{UInt8}",
+         "int64_t *": "Ptr{Int64}", "krotov_handle": "Ptr{Cvoid}", "void *": "Ptr{Cvoid}", "const void *": "Ptr{Cvoid}",
+         "const krotov_problem *": "Ref{Problem}", "krotov_info *": "Ref{Info}"}
+_HANDLE_OUT = {"Ref{Ptr{Cvoid}}", "Ptr{Ptr{Cvoid}}"}
+
+
+def _c_struct_fields(hdr, name):
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    body = re.search(r"typedef struct \{([^}]*)\}\s*" + name + ";", hdr, flags=re.S).group(1)
+    out = []
+    for decl in body.split(";"):
+        decl = " ".join(decl.split())
+        if not decl:
+            continue
+        m = re.match(r"(.*?)(\w+)(\[(\d+)\])?$", decl)
+        ctype, fname, arr = m.group(1).strip(), m.group(2), m.group(4)
+        ctype = ctype.replace(" *", " *").strip()
+        jl = _C2JL[ctype if ctype.endswith("*") else ctype]
+        out.append((fname, f"NTuple{{{arr},{jl}}}" if arr else jl))
+    return out
+
+
+def _jl_struct_fields(src, name):
+    body = re.search(r"^struct " + name + r"\n(.*?)^end", src, flags=re.S | re.M).group(1)
+    return [(m.group(1), m.group(2)) for m in re.finditer(r"^\s*(\w+)::([\w{},]+)", body, flags=re.M)]
+
+
+def test_julia_bindings_match_the_header():
+    hdr = open(os.path.join(ROOT, "include", "krotov_cuda.h")).read()
+    src = open(os.path.join(ROOT, "julia", "Krotov", "src", "LibKrotovCuda.jl")).read()
+    # struct layouts, field by field
+    assert _jl_struct_fields(src, "Problem") == _c_struct_fields(hdr, "krotov_problem")
+    assert _jl_struct_fields(src, "Info") == _c_struct_fields(hdr, "krotov_info")
+    # every C entry point is bound, with the header's argument types
+    protos = {}
+    clean = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    for m in re.finditer(r"^(int|const char \*)\s*(krotov_\w+)\((.*?)\);", clean, flags=re.S | re.M):
+        args = [] if m.group(3).strip() == "void" else [" ".join(a.split()) for a in m.group(3).split(",")]
+        types = []
+        for a in args:
+            t = re.match(r"(.*?)(\w+)$", a).group(1).strip()
+            types.append(t)
+        protos[m.group(2)] = (m.group(1), types)
+    calls = {}
+    for m in re.finditer(r"ccall\(\(:(krotov_\w+), lib\),\s*(\w+),\s*\((.*?)\)\s*(?:,|\))", src, flags=re.S):
+        calls[m.group(1)] = (m.group(2), [t.strip() for t in m.group(3).split(",") if t.strip()])
+    assert set(calls) == set(protos), (sorted(set(protos) - set(calls)), sorted(set(calls) - set(protos)))
+    for name, (ret, ctypes_) in protos.items():
+        jret, jtypes = calls[name]
+        assert jret == ("Cstring" if ret.startswith("const char") else "Cint"), name
+        assert len(jtypes) == len(ctypes_), (name, jtypes, ctypes_)
+        for jt, ct in zip(jtypes, ctypes_):
+            if ct == "krotov_handle *":
+                assert jt in _HANDLE_OUT, (name, jt)
+            else:
+                assert jt == _C2JL[ct], (name, jt, ct)
+    # enum values used by the module
+    for cname, val in re.findall(r"(KROTOV_[A-Z_]+) = (\d+)", clean):
+        m = re.search(r"\b" + cname + r"\b[^\n]*", src)
+        if m and "=" in m.group(0):
+            names = [n.strip() for n in m.group(0).split("=")[0].replace("const", "").split(",")]
+            vals = re.findall(r"Cint\((\d+)\)", m.group(0))
+            if cname in names and len(vals) == len(names):
+                assert int(vals[names.index(cname)]) == int(val), cname
+    # the driver calls only bindings that exist
+    drv = open(os.path.join(ROOT, "julia", "Krotov", "src", "optimize.jl")).read() + open(
+        os.path.join(ROOT, "julia", "Krotov", "src", "workspace.jl")).read()
+    defined = set(re.findall(r"^(?:function\s+)?(\w+!?)\(", src, flags=re.M))
+    for fn in set(re.findall(r"LibKrotovCuda\.(\w+!?)\(", drv)):
+        assert fn in defined or fn in ("Problem", "Handle"), fn
