@@ -137,6 +137,79 @@ def cpu_baseline_sample(workload_full, samples, iters, n_threads=0):
                       f"{out['secs']:.2f} s; C restatement of Krotov.jl (Julia not installed), OpenMP over trajectories"}
 
 
+DMMA_PEAK_TFLOPS = 37.1  # self-measured FP64 mma.sync peak on this pool's B200 (tools/microbench.cu, profiles/r1_microbench_fp64.txt)
+DFMA_PEAK_TFLOPS = 34.2
+
+
+def extra_configs(K, to_problem, peaks):
+    """The other BASELINE configs, timed by the same run (device time from the handle, CUDA events on the launch
+    stream): C1, C2, C3 at full size on the persistent one-launch kernels, and C5 at full WIDTH (d = 4096, 64
+    trajectories) over 20 time steps, both sweeps, on the FP64 DMMA path -- every time step of C5 costs the same, so
+    the per-step figures carry to N_T = 10000.  Each entry names the roof that binds it."""
+    out = {}
+
+    def run(w, iters, warm):
+        ms, info = [], {}
+
+        def cb(wrk, it, *a):
+            if it >= 1:
+                i = wrk.engine.info()
+                ms.append(i["ms_last"])
+                info.update(i)
+
+        res = K.optimize(to_problem(w, iter_stop=warm + iters, callback=cb), method=K.Krotov)
+        if res.message.startswith("Exception"):
+            raise RuntimeError(res.message)
+        return float(np.mean(ms[warm:])), info, res
+
+    kernels = {1: "krotov_warp_kernel / krotov_tiny_kernel (one persistent launch per iteration)",
+               2: "dense_gemm_kernel<8> (FP64 DMMA, stream-K) + build_G_kernel + update_kernel",
+               3: "sparse_sweep_kernel / spmm_kernel"}
+    for name, make, iters in (("C1 TLS d=2 N=1 N_T=500", W.c1_tls, 10), ("C2 transmon X d=3 N=2 N_T=500", W.c2_transmon_x, 10),
+                              ("C3 two-transmon d=25 N=4 N_T=2000", W.c3_two_transmon, 5)):
+        try:
+            w = make()
+            ms, info, res = run(w, iters, 2)
+            out[name] = {"ms_per_iteration": ms, "iterations_per_s": 1e3 / ms,
+                         "state_timesteps_per_s": 2.0 * w.N * w.N_T / (ms * 1e-3),
+                         "us_per_time_step_both_sweeps": 1e3 * ms / w.N_T, "launches_per_iteration": info["launches_last"],
+                         "grid": [info["grid_blocks"], info["block_threads"]], "m": info["m_fw"], "J_T_last": res.J_T,
+                         "kernel": kernels[info["path"]] if info["grid_blocks"] > 1 or info["block_threads"] > 32 else
+                         "krotov_tiny_kernel (one warp, one thread per trajectory)",
+                         "bound": "latency of the serial chain (one trajectory per warp / thread; neither HBM nor FP64 "
+                                  "is loaded: %.2g GB/s, %.2g GFLOP/s)" % (
+                                      16.0 * w.d * w.N * (2 * w.N_T + 1) / (ms * 1e-3) / 1e9,
+                                      2.0 * w.N * w.N_T * (info["m_fw"] - 1) * 8 * info["nnz_union"] / (ms * 1e-3) / 1e9)}
+        except Exception as exc:  # an extra config never costs the headline
+            out[name] = {"error": str(exc)}
+    try:
+        n_grid = 21
+        w = W.c5_dense(d=4096, n_traj=64, n_grid=n_grid)
+        ms, info, res = run(w, 1, 1)
+        N_T, m, dp = w.N_T, info["m_fw"], 4096
+        gemms = N_T * (2 * (m - 1) + w.L)  # (m-1) per direction and step + the overlap GEMM of every control
+        flops = gemms * 8.0 * dp * dp * w.N
+        gen_bytes = gemms * 16.0 * dp * dp
+        out["C5 dense d=4096 N=64, N_T=%d of 10000 (every step costs the same)" % N_T] = {
+            "ms_per_iteration": ms, "ms_per_time_step_both_sweeps": ms / N_T,
+            "s_per_iteration_at_N_T_10000": ms / N_T * 10000 * 1e-3,
+            "state_timesteps_per_s": 2.0 * w.N * N_T / (ms * 1e-3), "launches_per_iteration": info["launches_last"],
+            "m": m, "kernel": kernels[info["path"]], "J_T_last": res.J_T,
+            "roofline_fp64_tensor": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": DMMA_PEAK_TFLOPS,
+                                     "unit": "TFLOP/s", "frac": flops / (ms * 1e-3) / 1e12 / DMMA_PEAK_TFLOPS,
+                                     "flops_per_iteration": flops,
+                                     "formula": "8 dp^2 N x [(m-1) x 2 + L] GEMMs per time step x N_T, over the WHOLE "
+                                                "iteration (generator builds, updates, storage and launch gaps included)",
+                                     "peak_source": "self-measured mma.sync.m8n8k4.f64 peak (tools/microbench.cu); "
+                                                    "MEASURED_PEAKS.json has no FP64 figure"},
+            "roofline_hbm_generator": {"achieved": gen_bytes / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                       "frac": gen_bytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                       "note": "16 dp^2 bytes of generator per GEMM if nothing stayed in L2"}}
+    except Exception as exc:
+        out["C5 dense d=4096 N=64"] = {"error": str(exc)}
+    return out
+
+
 def run_reference(args):
     """`--impl reference`: CPU restatement on the host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -189,6 +262,7 @@ def main():
     ap.add_argument("--ref-threads", type=int, default=0, help="host threads of the CPU arm (0 = all cores this "
                     "process may run on; never the OpenMP default, which torchrun pins to 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the C1/C2/C3/C5 block of the JSON line")
     ap.add_argument("--scaling", choices=["strong", "weak"], default="strong",
                     help="strong: the BASELINE ensemble sharded over the ranks; weak: --samples per rank")
     args = ap.parse_args()
@@ -313,7 +387,11 @@ def main():
             "gpu_launches": int(sum(launches[warmup:warmup + steps])),
             "clocks": marks["clocks"],
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": ach_gbs / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
+                         "frac": ach_gbs / peaks["hbm_gbs"], "traffic": traffic,
+                         "traffic_source": "profiles/r1_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of ONE "
+                                           "ncu --set full capture of this launch shape (round 1), NOT measured in this run; "
+                                           "1.25x the algorithmic bytes because d = 25 states sit in 32-entry records",
+                         "peak_source": peak_src,
                          "kernel": "krotov_warp_kernel", "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "the fused kernel keeps all Chebyshev vectors on chip, so HBM traffic is only the chi "
                                  "trajectory; the binding resource is the shared-memory crossbar (see roofline_smem "
@@ -327,6 +405,8 @@ def main():
                               "bound": "not the FP64 pipe: shared-memory crossbar (roofline_smem) in the sweeps, exchange "
                                        "latency between the time steps of the forward sweep"},
         }
+        if world == 1 and not args.no_extra_configs and args.samples == 256:
+            line["extra_configs"] = extra_configs(K, to_problem, peaks)
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline_sample(w, min(args.samples, 128), 2)

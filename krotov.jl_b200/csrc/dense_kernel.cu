@@ -372,11 +372,24 @@ __global__ void build_G_kernel(double2 *G, const double2 *H, int dp, int L, doub
     }
 }
 
+// coefficient of H_l in the generator for the control value e (non-linear amplitudes, src/optimize.jl:268-272)
+__device__ __forceinline__ double amp_apply(const AmpDev &am, const int l, const int N_T, const int n, const double e) {
+    double c = e;
+    if (am.poly != nullptr) {
+        const double *q = am.poly + l * (kAmpDeg + 1);
+        c = q[kAmpDeg];
+#pragma unroll
+        for (int d = kAmpDeg - 1; d >= 0; --d) c = fma(c, e, q[d]);
+    }
+    if (am.shape != nullptr) c = __dmul_rn(am.shape[(size_t)l * N_T + n], c);
+    return c;
+}
+
 // fixed-order sum of the CTA partials of every control, rank exchange, pulse update (src/optimize.jl:351-358).
 // With several ranks the rank sum is pushed into every peer's mailbox (system-scope stores over NVLink) and
 // the `world` slots are summed in rank order -- the same protocol as the warp path's reducer.
 __global__ void update_kernel(const double *partial, int n_partial, int L, const double *alpha, const double *eps_old,
-                              double *eps_new, double *ga, const double *dt, int N_T, int n, DenseComm cm) {
+                              double *eps_new, double *ga, const double *dt, int N_T, int n, DenseComm cm, AmpDev am) {
     const int l = blockIdx.x, lane = threadIdx.x;
     double s = 0.0;
     for (int c = lane; c < n_partial; c += 32) s += partial[(size_t)l * n_partial + c];
@@ -404,7 +417,10 @@ __global__ void update_kernel(const double *partial, int n_partial, int L, const
     }
     if (lane == 0) {
         const double a = alpha[(size_t)l * N_T + n];
-        eps_new[(size_t)l * N_T + n] = __dadd_rn(eps_old[(size_t)l * N_T + n], __dmul_rn(a, s));
+        if (am.dfac != nullptr) s = __dmul_rn(am.dfac[(size_t)l * N_T + n], s);  // mu_l = a_l'(eps^(i)) H_l
+        const double e_new = __dadd_rn(eps_old[(size_t)l * N_T + n], __dmul_rn(a, s));
+        eps_new[(size_t)l * N_T + n] = e_new;
+        if (am.amp_new != nullptr) am.amp_new[(size_t)l * N_T + n] = amp_apply(am, l, N_T, n, e_new);
         const double prev = (n == 0) ? 0.0 : ga[l];
         ga[l] = __dadd_rn(prev, __dmul_rn(__dmul_rn(a, __dmul_rn(fabs(s), fabs(s))), dt[n]));
     }
@@ -611,6 +627,8 @@ struct SweepParams {
     const double *eps_old, *alpha, *dt;
     double *eps_new, *ga;
     double *partial;           // [L][gridDim.x]
+    const double *amp_old;     // a(eps_old): coefficients of the generator under the known pulses (== eps_old when linear)
+    AmpDev am;
 };
 
 struct SweepItem {
@@ -828,7 +846,7 @@ __global__ void __launch_bounds__(SP_WARPS * 32, 2) sparse_sweep_kernel(const __
         }
         sweep_barrier(p, grid, bar_target);
         for (int n = p.N_T - 1; n >= 0; --n) {
-            for (int l = 0; l < p.L; ++l) eps[l] = p.eps_old[(size_t)l * p.N_T + n];
+            for (int l = 0; l < p.L; ++l) eps[l] = p.amp_old[(size_t)l * p.N_T + n];
             sweep_step<R>(p, grid, KROTOV_BACKWARD, n, eps, p.X + p.slab * (size_t)n, gsm, csm, lane, wg, total_warps, bar_target, it0);
         }
     }
@@ -880,8 +898,9 @@ __global__ void __launch_bounds__(SP_WARPS * 32, 2) sparse_sweep_kernel(const __
                     for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
                     if (lane == 0) {
                         const double a = p.alpha[(size_t)l * p.N_T + n];
+                        if (p.am.dfac != nullptr) sacc = __dmul_rn(p.am.dfac[(size_t)l * p.N_T + n], sacc);
                         const double e_new = __dadd_rn(p.eps_old[(size_t)l * p.N_T + n], __dmul_rn(a, sacc));  // :355-356
-                        eps_sh[l] = e_new;
+                        eps_sh[l] = amp_apply(p.am, l, p.N_T, n, e_new);
                         if (blockIdx.x == 0) {
                             p.eps_new[(size_t)l * p.N_T + n] = e_new;
                             const double prev = (n == 0) ? 0.0 : p.ga[l];
@@ -894,7 +913,7 @@ __global__ void __launch_bounds__(SP_WARPS * 32, 2) sparse_sweep_kernel(const __
             for (int l = 0; l < p.L; ++l) eps[l] = eps_sh[l];
             __syncthreads();
         } else {
-            for (int l = 0; l < p.L; ++l) eps[l] = p.eps_old[(size_t)l * p.N_T + n];
+            for (int l = 0; l < p.L; ++l) eps[l] = p.amp_old[(size_t)l * p.N_T + n];
         }
         double2 *store = nullptr;
         if (p.store_fw) store = p.PHI + p.slab * (size_t)(p.mode == 1 ? n : n + 1);  // slot n in an iteration (sic, :367)

@@ -146,13 +146,13 @@ __global__ void __launch_bounds__(256, 1) krotov_warp2_kernel(const __grid_const
         StepMeta meta = load_meta(p.dtc_b, p.m_b, p.phase_b, p.coef_b, p.ndtc_b, p.mmax_b, gi, N_T - 1);
         double e_cur[LT];
 #pragma unroll
-        for (int l = 0; l < LT; ++l) e_cur[l] = p.eps_old[(size_t)l * N_T + N_T - 1];
+        for (int l = 0; l < LT; ++l) e_cur[l] = p.amp_old[(size_t)l * N_T + N_T - 1];
         for (int n = N_T - 1; n >= 0; --n) {
             const int nn = n > 0 ? n - 1 : 0;
             const StepMeta meta_next = load_meta(p.dtc_b, p.m_b, p.phase_b, p.coef_b, p.ndtc_b, p.mmax_b, gi, nn);
             double e_next[LT];
 #pragma unroll
-            for (int l = 0; l < LT; ++l) e_next[l] = p.eps_old[(size_t)l * N_T + nn];
+            for (int l = 0; l < LT; ++l) e_next[l] = p.amp_old[(size_t)l * N_T + nn];
 #pragma unroll
             for (int s = 0; s <= W; ++s) g[s] = P[0][s];
 #pragma unroll
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(256, 1) krotov_warp2_kernel(const __grid_const
             }
         } else {
 #pragma unroll
-            for (int l = 0; l < LT; ++l) eps[l] = p.eps_old[(size_t)l * N_T + n];
+            for (int l = 0; l < LT; ++l) eps[l] = p.amp_old[(size_t)l * N_T + n];
         }
         const StepMeta fmeta_next =
             load_meta(p.dtc_f, p.m_f, p.phase_f, p.coef_f, p.ndtc_f, p.mmax_f, gi, n + 1 < N_T ? n + 1 : n);

@@ -39,6 +39,7 @@ namespace kr {
 
 constexpr int kMaxRanks = 8;
 constexpr int kMaxCtrl = 8;
+constexpr int kAmpMaxDeg = 4;
 constexpr unsigned long long kSentinel = 0xFFFFFFFFFFFFFFFFull;
 
 struct WarpParams {
@@ -62,6 +63,14 @@ struct WarpParams {
     const double *alpha;       // [L][N_T]  S_l[n] / lambda_l
     const double *eps_old;     // [L][N_T]
     double *eps_new;           // [L][N_T]
+    // Non-linear control amplitudes (src/optimize.jl:268-272, 337-346): term l enters the generator with the coefficient
+    // a_l(eps, n) = amp_shape[l][n] * sum_p amp_poly[l][p] eps^p.  The generator of a sweep under KNOWN pulses reads
+    // amp_old = a(eps_old) (== eps_old for linear controls); mu_l = a_l'(eps_old) H_l scales the overlap sum by amp_dfac;
+    // the forward step gets a(eps_new) from the comm warp.  All null / aliased for linear controls.
+    const double *amp_old;     // [L][N_T]
+    const double *amp_dfac;    // [L][N_T] or nullptr
+    const double *amp_poly;    // [L][kAmpMaxDeg+1] or nullptr
+    const double *amp_shape;   // [L][N_T] or nullptr
     double *g_a_int;           // [L]
     double2 *X;                // [N][N_T+1][32]  chi trajectory, trajectory-major
     double2 *Phi;              // [N][N_T+1][32]  optional forward storage
@@ -732,11 +741,13 @@ __device__ __forceinline__ void comm_warp_run(const WarpParams &p, const int cta
     double ga = 0.0;  // lane l accumulates g_a_int[l]  (CTA 0 writes it)
     long long c_wait_a = 0, c_reduce = 0, c_gather = 0;
     for (int n = 0; n < N_T; ++n) {
-        double a_ln = 0.0, e_old = 0.0, dtn = 0.0;
+        double a_ln = 0.0, e_old = 0.0, dtn = 0.0, dfac = 1.0, shp = 1.0;
         if (lane < L) {
             a_ln = p.alpha[(size_t)lane * N_T + n];
             e_old = p.eps_old[(size_t)lane * N_T + n];
             dtn = p.dt[n];
+            if (p.amp_dfac != nullptr) dfac = p.amp_dfac[(size_t)lane * N_T + n];
+            if (p.amp_shape != nullptr) shp = p.amp_shape[(size_t)lane * N_T + n];
         }
         const long long c0 = clock64();
         bar_sync(1, nthr_all);  // barrier A: partials are in `red`
@@ -786,9 +797,18 @@ __device__ __forceinline__ void comm_warp_run(const WarpParams &p, const int cta
         for (int l = 0; l < kMaxCtrl; ++l)
             if (lane == l) mine = tot[l];
         if (lane < L) {
+            if (p.amp_dfac != nullptr) mine = __dmul_rn(dfac, mine);  // mu_l = a_l'(eps^(i)_l[n]) H_l  (:337-346)
             const double d_eps = __dmul_rn(a_ln, mine);      // src/optimize.jl:355
             const double e_new = __dadd_rn(e_old, d_eps);    // :356
-            eps_s[lane] = e_new;
+            double c_new = e_new;                            // coefficient of H_l in the forward step
+            if (p.amp_poly != nullptr) {
+                const double *q = p.amp_poly + lane * (kAmpMaxDeg + 1);
+                c_new = q[kAmpMaxDeg];
+#pragma unroll
+                for (int d = kAmpMaxDeg - 1; d >= 0; --d) c_new = fma(c_new, e_new, q[d]);
+            }
+            if (p.amp_shape != nullptr) c_new = __dmul_rn(shp, c_new);
+            eps_s[lane] = c_new;
             if (cta == 0) {
                 p.eps_new[(size_t)lane * N_T + n] = e_new;
                 ga = __dadd_rn(ga, __dmul_rn(__dmul_rn(a_ln, __dmul_rn(fabs(mine), fabs(mine))), dtn));  // :357
@@ -877,13 +897,13 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
             StepMeta meta = load_meta(p.dtc_b, p.m_b, p.phase_b, p.coef_b, p.ndtc_b, p.mmax_b, gi, N_T - 1);
             double e_cur[kMaxCtrl];
 #pragma unroll
-            for (int l = 0; l < kMaxCtrl; ++l) e_cur[l] = (l < L) ? p.eps_old[(size_t)l * N_T + N_T - 1] : 0.0;
+            for (int l = 0; l < kMaxCtrl; ++l) e_cur[l] = (l < L) ? p.amp_old[(size_t)l * N_T + N_T - 1] : 0.0;
             for (int n = N_T - 1; n >= 0; --n) {
                 const int nn = n > 0 ? n - 1 : 0;  // prefetch the next step's metadata and pulse values
                 const StepMeta meta_next = load_meta(p.dtc_b, p.m_b, p.phase_b, p.coef_b, p.ndtc_b, p.mmax_b, gi, nn);
                 double e_next[kMaxCtrl];
 #pragma unroll
-                for (int l = 0; l < kMaxCtrl; ++l) e_next[l] = (l < L) ? p.eps_old[(size_t)l * N_T + nn] : 0.0;
+                for (int l = 0; l < kMaxCtrl; ++l) e_next[l] = (l < L) ? p.amp_old[(size_t)l * N_T + nn] : 0.0;
                 if (PREG) {
 #pragma unroll
                     for (int s = 0; s <= W; ++s) g[s] = P[0][s];
@@ -899,7 +919,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
                 } else {
                     load_row<W, LPT>(Pg, g, lane);
                     for (int l = 0; l < L; ++l) {
-                        const double e = p.eps_old[(size_t)l * N_T + n];  // (runtime index: reload, L1 hit)
+                        const double e = p.amp_old[(size_t)l * N_T + n];  // (runtime index: reload, L1 hit)
                         const double2 *Pl = Pg + (size_t)(l + 1) * rowstride;
 #pragma unroll
                         for (int s = 0; s <= W; ++s) {
@@ -1041,7 +1061,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
         } else {
 #pragma unroll
             for (int l = 0; l < (PREG ? LT : kMaxCtrl); ++l)
-                if (l < L) eps[l] = p.eps_old[(size_t)l * N_T + n];
+                if (l < L) eps[l] = p.amp_old[(size_t)l * N_T + n];
         }
         // ---- forward step with the (updated) pulse value  (src/optimize.jl:360-368)
         const StepMeta fmeta_next =

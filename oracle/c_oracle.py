@@ -81,6 +81,22 @@ def optimize_krotov_c(p, iters, n_threads=0):
     def P(a):
         return a.ctypes.data_as(ctypes.c_void_p)
 
+    keep = []
+    if getattr(p, "nonlinear", False):
+        poly = None
+        deg = 1
+        if p.amp_poly is not None:
+            deg = max(1, max(len(c) - 1 for c in p.amp_poly if c is not None)) if any(c is not None for c in p.amp_poly) else 1
+            poly = np.zeros((L, deg + 1))
+            for l in range(L):
+                if p.amp_poly[l] is None:
+                    poly[l, 1] = 1.0
+                else:
+                    poly[l, : len(p.amp_poly[l])] = p.amp_poly[l]
+        shape = None if p.amp_shape is None else np.ascontiguousarray(p.amp_shape, float)
+        keep = [poly, shape]
+        L_.oracle_set_amplitudes(ctypes.c_int(deg), None if poly is None else P(poly), None if shape is None else P(shape))
+
     rc = L_.oracle_krotov_optimize(
         ctypes.c_int(d), ctypes.c_int(N), ctypes.c_int(L), ctypes.c_int(N_T), ctypes.c_int(len(p.H0)),
         P(tlist), P(gen), P(rowptr), P(term_off), P(col), P(val), P(psi0), P(tgt), P(w), P(pulses), P(S), P(lam),

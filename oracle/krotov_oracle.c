@@ -64,6 +64,11 @@ typedef struct {
     int has_explicit_range;
     double ex_Emin, ex_Emax;
     double limit, buffer;
+    /* non-linear amplitudes a_l(eps, n) = shape[l][n] * sum_p poly[l][p] eps^p (src/optimize.jl:268-272); NULL = linear */
+    int amp_deg;
+    const double *amp_poly;  /* [L][amp_deg+1] */
+    const double *amp_shape; /* [L][N_T] */
+    double *amp_shape_max;   /* [L] largest |shape| (spectral envelope) */
     /* spectral-envelope cache per (direction, generator): key = control ranges */
     double *cache_key; /* 2*n_gen*(2L) */
     double *cache_val; /* 2*n_gen*2 */
@@ -120,18 +125,49 @@ static void herm_eig_range(const cplx *A, int d, double *emin, double *emax) {
     free(M);
 }
 
+static double amp_poly_value(const ctx_t *c, int l, double eps) {
+    if (!c->amp_poly) return eps;
+    const double *q = c->amp_poly + (size_t)l * (c->amp_deg + 1);
+    double v = 0.0;
+    for (int p = c->amp_deg; p >= 0; p--) v = v * eps + q[p];
+    return v;
+}
+/* coefficient of H_l on interval n for the control value eps */
+static double amp_value(const ctx_t *c, int l, int n, double eps) {
+    double v = amp_poly_value(c, l, eps);
+    return c->amp_shape ? c->amp_shape[(size_t)l * c->N_T + n] * v : v;
+}
+/* d a_l / d eps: the factor of H_l in mu_l = dH / d eps_l (evaluated at the guess pulse, src/optimize.jl:337) */
+static double amp_deriv(const ctx_t *c, int l, int n, double eps) {
+    double v = 1.0;
+    if (c->amp_poly) {
+        const double *q = c->amp_poly + (size_t)l * (c->amp_deg + 1);
+        v = 0.0;
+        for (int p = c->amp_deg; p >= 1; p--) v = v * eps + p * q[p];
+    }
+    return c->amp_shape ? c->amp_shape[(size_t)l * c->N_T + n] * v : v;
+}
+static int amp_nonlinear(const ctx_t *c) { return c->amp_poly != NULL || c->amp_shape != NULL; }
+
 static void evaluate_dense(const ctx_t *c, const csr_t *terms, int g, const double *vals, cplx *G) {
     int d = c->d;
     memset(G, 0, sizeof(cplx) * d * d);
     for (int t = 0; t <= c->L; t++) {
         const csr_t *T = &terms[g * (1 + c->L) + t];
-        double cf = (t == 0) ? 1.0 : vals[t - 1];
+        double cf = 1.0;
+        if (t > 0) { /* range corner: polynomial at the corner times the largest |shape| (unpinned convention) */
+            cf = amp_poly_value(c, t - 1, vals[t - 1]);
+            if (c->amp_shape) cf *= c->amp_shape_max[t - 1];
+        }
         for (int i = 0; i < d; i++)
             for (int q = T->rowptr[i]; q < T->rowptr[i + 1]; q++) G[i * d + T->col[q]] += cf * T->val[q];
     }
 }
 
-static int g_oracle_diverged = 0; /* a pulse grew beyond anything a polynomial can be derived for */
+static int g_oracle_diverged = 0;
+/* amplitudes of the NEXT oracle_krotov_optimize call (set by oracle_set_amplitudes, consumed by the call) */
+static int g_amp_deg = 0;
+static const double *g_amp_poly = NULL, *g_amp_shape = NULL; /* a pulse grew beyond anything a polynomial can be derived for */
 
 static int cheby_coeffs(double Delta, double dt, double limit, double **out) {
     double alpha = fabs(0.5 * Delta * dt);
@@ -302,7 +338,7 @@ static void prop_step(ctx_t *c, prop_t *p, const double *pulses, cplx *work) {
         p->m = cheby_coeffs(p->Delta, dt, c->limit, &p->coef);
     }
     double eps_n[16];
-    for (int l = 0; l < L; l++) eps_n[l] = pulses[(size_t)l * c->N_T + ni];
+    for (int l = 0; l < L; l++) eps_n[l] = amp_value(c, l, ni, pulses[(size_t)l * c->N_T + ni]);
     const csr_t *terms = p->backward ? c->bw_terms : c->fw_terms;
     cplx *v0 = work, *v1 = work + d, *v2 = work + 2 * d, *psi = work + 3 * d, *tmp = work + 4 * d;
     const double *a = p->coef;
@@ -387,6 +423,10 @@ int oracle_krotov_optimize(int d, int N, int L, int N_T, int n_gen, const double
                            int *out_m, double *out_secs) {
     if (L > 16) return -1;
     g_oracle_diverged = 0;
+    const int amp_deg = g_amp_deg;
+    const double *amp_poly = g_amp_poly, *amp_shape = g_amp_shape;
+    g_amp_poly = NULL;
+    g_amp_shape = NULL;
 #ifdef _OPENMP
     if (n_threads > 0) omp_set_num_threads(n_threads);
 #endif
@@ -399,6 +439,13 @@ int oracle_krotov_optimize(int d, int N, int L, int N_T, int n_gen, const double
     c.L = L;
     c.N_T = N_T;
     c.n_gen = n_gen;
+    c.amp_deg = amp_deg;
+    c.amp_poly = amp_poly;
+    c.amp_shape = amp_shape;
+    c.amp_shape_max = (double *)calloc(L, sizeof(double));
+    if (amp_shape)
+        for (int l = 0; l < L; l++)
+            for (int n = 0; n < N_T; n++) c.amp_shape_max[l] = fmax(c.amp_shape_max[l], fabs(amp_shape[(size_t)l * N_T + n]));
     c.tlist = tlist;
     c.gen_of_traj = gen_of_traj;
     c.limit = cheby_limit;
@@ -529,6 +576,7 @@ int oracle_krotov_optimize(int d, int N, int L, int N_T, int n_gen, const double
                         for (int q = mu->rowptr[i]; q < mu->rowptr[i + 1]; q++) r += mu->val[q] * psi[mu->col[q]];
                         s += conj(chik[i]) * r;
                     }
+                    if (amp_nonlinear(&c)) s *= amp_deriv(&c, l, n, eps_i[(size_t)l * N_T + n]);
                     du[l] += cimag(s);
                 }
             }
@@ -570,8 +618,16 @@ int oracle_krotov_optimize(int d, int N, int L, int N_T, int n_gen, const double
     }
     free(fw); free(bw); free(X); free(chi); free(work); free(mu_psi); free(e0); free(e1);
     free(c.fw_terms); free(c.bw_terms); free(c.bw_rowptr); free(c.bw_col); free(c.bw_val);
-    free(c.cache_key); free(c.cache_val); free(c.cache_ok);
+    free(c.cache_key); free(c.cache_val); free(c.cache_ok); free(c.amp_shape_max);
     return g_oracle_diverged ? -2 : 0;
+}
+
+/* Non-linear amplitudes for the next oracle_krotov_optimize call: poly [L][deg+1] (ascending powers) or NULL,
+ * shape [L][N_T] or NULL.  The arrays must stay alive until that call returns. */
+void oracle_set_amplitudes(int deg, const double *poly, const double *shape) {
+    g_amp_deg = deg;
+    g_amp_poly = poly;
+    g_amp_shape = shape;
 }
 
 int oracle_num_threads(void) {

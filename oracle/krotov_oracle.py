@@ -180,6 +180,51 @@ class ProblemArrays:
     specrange_buffer: float = 0.01
     specrange: Optional[tuple] = None  # explicit (E_min, E_max) for every generator
     meta: dict = field(default_factory=dict)
+    # Non-linear control amplitudes (src/optimize.jl:268-272, 337-346): the generator is
+    #   H0 + sum_l a_l(eps_l(t), t) H_l,   a_l(eps, n) = amp_shape[l][n] * sum_p amp_poly[l][p] eps^p .
+    # None = linear controls (a_l = eps_l).  One operator per control.
+    amp_poly: Optional[list] = None  # per control: polynomial coefficients, ascending powers (None entry = linear)
+    amp_shape: Optional[np.ndarray] = None  # (L, N_T) per-interval factor (a `ShapedAmplitude`), default 1
+
+    def amplitude(self, l, n, eps):
+        """a_l(eps, n): the coefficient of H_l on interval n for the control value eps."""
+        v = eps
+        if self.amp_poly is not None and self.amp_poly[l] is not None:
+            v = 0.0
+            for c in reversed(self.amp_poly[l]):  # Horner
+                v = v * eps + c
+        if self.amp_shape is not None:
+            v = self.amp_shape[l][n] * v
+        return v
+
+    def amplitude_deriv(self, l, n, eps):
+        """d a_l / d eps at (eps, n): the factor of H_l in mu_l = dH/d eps_l (`get_control_derivs` + `evaluate`)."""
+        v = 1.0
+        if self.amp_poly is not None and self.amp_poly[l] is not None:
+            c = self.amp_poly[l]
+            v = 0.0
+            for q in range(len(c) - 1, 0, -1):
+                v = v * eps + q * c[q]
+        if self.amp_shape is not None:
+            v = self.amp_shape[l][n] * v
+        return v
+
+    def amplitude_envelope(self, l, eps):
+        """Coefficient of H_l used for the spectral envelope at a corner `eps` of the control range: the largest
+        |shape| over the grid times the polynomial (UNPINNED convention: upstream evaluates the generator at the range
+        corners; with a time-dependent shape the safe choice is its maximum)."""
+        v = eps
+        if self.amp_poly is not None and self.amp_poly[l] is not None:
+            v = 0.0
+            for c in reversed(self.amp_poly[l]):
+                v = v * eps + c
+        if self.amp_shape is not None:
+            v = float(np.max(np.abs(self.amp_shape[l]))) * v
+        return v
+
+    @property
+    def nonlinear(self):
+        return self.amp_poly is not None or self.amp_shape is not None
 
     @property
     def N(self):
@@ -243,7 +288,7 @@ class _PWCPropagator:
     """Shared state of a piecewise-constant propagator: generator terms, time grid,
     the *aliased* pulse arrays (``parameters``), direction, current state / index."""
 
-    def __init__(self, H0, Hc, tlist, parameters, backward=False):
+    def __init__(self, H0, Hc, tlist, parameters, backward=False, problem=None):
         self.H0 = H0
         self.Hc = Hc  # list over l, entries may be None
         self.tlist = np.asarray(tlist, float)
@@ -251,6 +296,8 @@ class _PWCPropagator:
         self.backward = backward
         self.state = None
         self.n = 0  # index of the time-grid point the state sits on (0-based)
+        # non-linear amplitudes: coefficient of H_l = a_l(eps_l[n], n)  (None: linear controls)
+        self.problem = problem if (problem is not None and problem.nonlinear) else None
 
     def _ops_coeffs(self, n_interval):
         """Lazy Operator(ops, coeffs) = H0 + sum_l eps_l[n] H_l for interval n."""
@@ -259,7 +306,8 @@ class _PWCPropagator:
         for l, Hl in enumerate(self.Hc):
             if Hl is not None:
                 ops.append(Hl)
-                coeffs.append(self.parameters[l][n_interval])
+                e = self.parameters[l][n_interval]
+                coeffs.append(e if self.problem is None else self.problem.amplitude(l, n_interval, e))
         return ops, coeffs
 
     def _apply(self, ops, coeffs, v):
@@ -273,7 +321,7 @@ class _PWCPropagator:
         G = self.H0.copy()
         for l, Hl in enumerate(self.Hc):
             if Hl is not None:
-                G = G + vals[l] * Hl
+                G = G + (vals[l] if self.problem is None else self.problem.amplitude_envelope(l, vals[l])) * Hl
         return G
 
     def _reset_time(self):
@@ -298,8 +346,8 @@ class ChebyPropagator(_PWCPropagator):
     ``backward=True`` (negative time step)."""
 
     def __init__(self, H0, Hc, tlist, parameters, backward=False, limit=1e-12,
-                 specrange_buffer=0.01, specrange=None):
-        super().__init__(H0, Hc, tlist, parameters, backward)
+                 specrange_buffer=0.01, specrange=None, problem=None):
+        super().__init__(H0, Hc, tlist, parameters, backward, problem)
         self.limit = limit
         self.specrange_buffer = specrange_buffer
         self.explicit_specrange = specrange
@@ -466,12 +514,12 @@ class OracleWrk:
             H0a = H0.conj().T
             Hca = [None if h is None else h.conj().T for h in Hc]
             if prop_method == "cheby":
-                kw = dict(limit=p.cheby_limit, specrange_buffer=p.specrange_buffer, specrange=p.specrange)
+                kw = dict(limit=p.cheby_limit, specrange_buffer=p.specrange_buffer, specrange=p.specrange, problem=p)
                 self.fw_propagators.append(ChebyPropagator(H0, Hc, self.tlist, self.pulses0, False, **kw))
                 self.bw_propagators.append(ChebyPropagator(H0a, Hca, self.tlist, self.pulses0, True, **kw))
             elif prop_method == "expm":
-                self.fw_propagators.append(ExpPropagator(H0, Hc, self.tlist, self.pulses0, False))
-                self.bw_propagators.append(ExpPropagator(H0a, Hca, self.tlist, self.pulses0, True))
+                self.fw_propagators.append(ExpPropagator(H0, Hc, self.tlist, self.pulses0, False, p))
+                self.bw_propagators.append(ExpPropagator(H0a, Hca, self.tlist, self.pulses0, True, p))
             else:
                 raise ValueError(prop_method)
         self.tau_vals = np.zeros(N, complex)
@@ -532,11 +580,17 @@ def krotov_iteration(wrk: OracleWrk, eps_i, eps_ip1, chi=None):
             chi_k[k] = X[k][:, n].copy()
         du = np.zeros(L)
         for l in range(L):
+            # _eval_mu (:268-276): mu_l = dH/d eps_l evaluated at eps^(i)_n, the GUESS value (:337); for a linear control
+            # it is the static operator H_l, for a non-linear amplitude a_l'(eps^(i)_l[n], n) H_l
+            fac = p.amplitude_deriv(l, n, eps_i[l][n]) if p.nonlinear else None
             for k in range(N):
                 psi_k = wrk.fw_propagators[k].state
                 mu = wrk.control_derivs[k][l]
                 if mu is not None:
-                    du[l] += np.vdot(chi_k[k], mu @ psi_k).imag
+                    if fac is None:
+                        du[l] += np.vdot(chi_k[k], mu @ psi_k).imag
+                    else:
+                        du[l] += (fac * np.vdot(chi_k[k], mu @ psi_k)).imag
         for l in range(L):
             alpha = wrk.update_shapes[l][n] / wrk.lambda_vals[l]
             d_eps = alpha * du[l]
@@ -603,7 +657,7 @@ def optimize_krotov_blocked(p: ProblemArrays, iter_stop=5):
     groups = [np.nonzero(np.asarray(p.gen_of_traj) == g)[0] for g in range(len(p.H0))]
     pulses0 = [np.array(p.pulses[l], float) for l in range(L)]
     pulses1 = [a.copy() for a in pulses0]
-    kw = dict(limit=p.cheby_limit, specrange_buffer=p.specrange_buffer, specrange=p.specrange)
+    kw = dict(limit=p.cheby_limit, specrange_buffer=p.specrange_buffer, specrange=p.specrange, problem=p)
     fw = [ChebyPropagator(p.H0[g], p.Hc[g], tlist, pulses0, False, **kw) for g in range(len(groups))]
     bw = [ChebyPropagator(p.H0[g].conj().T, [None if h is None else h.conj().T for h in p.Hc[g]], tlist, pulses0,
                           True, **kw) for g in range(len(groups))]
@@ -652,7 +706,8 @@ def optimize_krotov_blocked(p: ProblemArrays, iter_stop=5):
                 for g, ks in enumerate(groups):
                     mu = p.Hc[g][l]
                     if mu is not None:
-                        contrib[ks] = np.einsum("ik,ik->k", X[g][n].conj(), mu @ fw[g].state).imag
+                        fac = p.amplitude_deriv(l, n, eps_i[l][n]) if p.nonlinear else 1.0
+                        contrib[ks] = (fac * np.einsum("ik,ik->k", X[g][n].conj(), mu @ fw[g].state)).imag
                 for k in range(N):  # reference order: k ascending
                     du[l] += contrib[k]
             for l in range(L):

@@ -41,13 +41,26 @@ def _step(psi, eps, dt):
     return (c * a - 1j * s * (-a / 2 + eps * b), c * b - 1j * s * (eps * a + b / 2))
 
 
-def tls_krotov_exact(iters=5, n_grid=501, dps=50, float_grid=True):
+def tls_krotov_exact(iters=5, n_grid=501, dps=50, float_grid=True, amp_poly=None, amp_shape=None, lam=1):
     """J_T history, running costs and final pulses of the TLS optimisation in `dps`-digit arithmetic.
 
     float_grid: take the time grid and the guess pulse samples from their Float64 values (what both the reference
     and the oracles start from) so that the comparison isolates the arithmetic of the loop."""
     mp.mp.dps = dps
-    T, t_rise, lam = mp.mpf(5), mp.mpf("0.3"), mp.mpf(1)
+    T, t_rise, lam = mp.mpf(5), mp.mpf("0.3"), mp.mpf(lam)
+    # non-linear amplitude: H = -sz/2 + a(eps, n) sx,  a = shape[n] * sum_p c_p eps^p;  mu = dH/d eps = a'(eps, n) sx is
+    # evaluated at the GUESS value of the interval (src/optimize.jl:337)
+    poly = None if amp_poly is None else [mp.mpf(float(c)) for c in amp_poly]
+    shape = None if amp_shape is None else [mp.mpf(float(x)) for x in amp_shape]
+
+    def amp(e, n):
+        v = e if poly is None else sum(c * e**q for q, c in enumerate(poly))
+        return v if shape is None else shape[n] * v
+
+    def damp(e, n):
+        v = mp.mpf(1) if poly is None else sum(q * c * e ** (q - 1) for q, c in enumerate(poly) if q > 0)
+        return v if shape is None else shape[n] * v
+
     if float_grid:
         import numpy as np
 
@@ -76,7 +89,7 @@ def tls_krotov_exact(iters=5, n_grid=501, dps=50, float_grid=True):
     def forward(e):
         psi = psi0
         for n in range(N_T):
-            psi = _step(psi, e[n], dts[n])
+            psi = _step(psi, amp(e[n], n), dts[n])
         return psi
 
     psi = forward(eps)
@@ -88,7 +101,7 @@ def tls_krotov_exact(iters=5, n_grid=501, dps=50, float_grid=True):
         X = [None] * (N_T + 1)
         X[N_T] = chi
         for n in range(N_T - 1, -1, -1):  # exp(+i H^dagger dt) with the GUESS pulse
-            chi = _step(chi, eps[n], -dts[n])
+            chi = _step(chi, amp(eps[n], n), -dts[n])
             X[n] = chi
         new = list(eps)
         psi = psi0
@@ -96,11 +109,11 @@ def tls_krotov_exact(iters=5, n_grid=501, dps=50, float_grid=True):
         for n in range(N_T):
             c0, c1 = X[n]
             # <chi| sx |psi> = conj(c0) psi1 + conj(c1) psi0
-            du = mp.im(mp.conj(c0) * psi[1] + mp.conj(c1) * psi[0])
+            du = damp(eps[n], n) * mp.im(mp.conj(c0) * psi[1] + mp.conj(c1) * psi[0])
             alpha = mp.mpf(1) / lam  # S = 1
             new[n] = eps[n] + alpha * du
             ga += alpha * du * du * dts[n]
-            psi = _step(psi, new[n], dts[n])
+            psi = _step(psi, amp(new[n], n), dts[n])
         eps = new
         tau = psi[1]
         J.append(1 - abs(tau) ** 2)
