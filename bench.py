@@ -376,11 +376,13 @@ def main():
                        "parallelism": f"trajectories sharded over {world} GPU(s)",
                        "l2": "chi trajectory (%.0f MB per GPU) is larger than L2; no flush needed" % (info["hbm_bytes_state"] / 1e6),
                        "grid": [info["grid_blocks"], info["block_threads"]], "J_T_last": marks["J_T"],
-                       **({"exchange": ("per time step, in-kernel over NVLink: every CTA adds its fixed-point partial into every "
-                                        "rank's accumulator (one hop)" if info["grid_blocks"] * world <= 512 and
-                                        not os.environ.get("KROTOV_NO_XACC") else
-                                        "per time step, in-kernel over NVLink: rank sums pushed into the peers' mailboxes")}
-                          if world > 1 else {})},
+                       **({"exchange": {1: "per time step, in-kernel: every CTA adds its fixed-point partial into its rank's "
+                                           "accumulator; the add that completes a word forwards the rank sum with one add per "
+                                           "rank over NVLink (hierarchical sum)",
+                                        2: "per time step, in-kernel over NVLink: every CTA adds its fixed-point partial into "
+                                           "every rank's accumulator (one hop)",
+                                        3: "per time step, in-kernel over NVLink: rank sums pushed into the peers' mailboxes"
+                                        }.get(info.get("exchange"), "?")} if world > 1 else {})},
             "e2e": {"value": e2e, "unit": UNIT, "iterations_per_s": steps / wall_s,
                     "h2d_bytes_per_step": L * N_T * 8, "d2h_bytes_per_step": L * N_T * 8 + L * 8 + n_loc * 16,
                     "ms_per_step_each": [round(1e3 * (b - a), 2) for a, b in zip(marks["wall"][warmup:warmup + steps], marks["wall"][warmup + 1:warmup + steps + 1])]},

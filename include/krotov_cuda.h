@@ -154,6 +154,17 @@ int krotov_set_cheby(krotov_handle h, int direction, int n_dt_class, const int32
                      const double *dt_of_class, const double *E_min, const double *Delta, const int32_t *m,
                      const double *coeffs, int m_max);
 
+/* Non-linear control amplitudes.  Replaces what `evaluate(generator, tlist, n; vals_dict)` and `_eval_mu`
+ * (src/optimize.jl:268-276, 337-346) do for generators whose control terms carry amplitude objects: control term l
+ * enters the generator of interval n as  a_l(eps, n) H_l  with
+ *     a_l(eps, n) = shape[l][n] * sum_{p=0..degree} poly[l][p] eps^p          (one operator per control)
+ * and the derivative  mu_l = dH/d eps_l = a_l'(eps^(i)_l[n], n) H_l  is evaluated at the GUESS pulse of the interval, as
+ * the reference does (:337).  poly: [L][degree+1], ascending powers, degree 1..4, or NULL (a = eps); shape: [L][N_T]
+ * or NULL (1) -- QuantumPropagators' ShapedAmplitude is (poly NULL, shape given).  Both NULL restores linear controls.
+ * Takes effect with the next krotov_forward / krotov_iterate.  The caller derives the spectral envelope passed to
+ * krotov_set_cheby from the amplitudes' range. */
+int krotov_set_amplitudes(krotov_handle h, int degree, const double *poly, const double *shape);
+
 /* ---- the hot path ----------------------------------------------------------------------
  * krotov_forward: forward propagation of every trajectory under `pulses` without update.
  * Replaces the loop over krotov_initial_fw_prop! (src/optimize.jl:182-184, 247-265).  Leaves

@@ -108,6 +108,14 @@ set_cheby(h, dir, dtc_of_step::Vector{Int32}, dt_of_class::Vector{Float64}, E_mi
         (Ptr{Cvoid}, Cint, Cint, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}, Cint),
         h.ptr, dir, length(dt_of_class), dtc_of_step, dt_of_class, E_min, Delta, m, coeffs, size(coeffs, 1)))
 
+# non-linear amplitudes a_l(eps, n) = shape[n, l] * sum_p poly[p+1, l] eps^p; poly: Matrix(degree+1, L) or nothing,
+# shape: Matrix(N_T, L) or nothing
+function set_amplitudes(h, poly::Union{Nothing,Matrix{Float64}}, shape::Union{Nothing,Matrix{Float64}})
+    degree = poly === nothing ? 1 : size(poly, 1) - 1
+    check(h, ccall((:krotov_set_amplitudes, lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}), h.ptr, degree,
+                   poly === nothing ? C_NULL : pointer(poly), shape === nothing ? C_NULL : pointer(shape)))
+end
+
 # pulses: Matrix{Float64}(N_T, L), column-major == [L][N_T] row-major on the wire
 forward(h, pulses::Matrix{Float64}) =
     check(h, ccall((:krotov_forward, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}), h.ptr, pulses))

@@ -24,7 +24,7 @@ COMM_DESC_BYTES = 192
 # every symbol include/krotov_cuda.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "krotov_abi_version", "krotov_create", "krotov_destroy", "krotov_last_error", "krotov_get_info",
-    "krotov_set_cheby", "krotov_forward", "krotov_set_chi", "krotov_set_chi_coeffs", "krotov_iterate",
+    "krotov_set_cheby", "krotov_set_amplitudes", "krotov_forward", "krotov_set_chi", "krotov_set_chi_coeffs", "krotov_iterate",
     "krotov_get_states", "krotov_get_tau", "krotov_get_storage", "krotov_get_profile", "krotov_comm_export", "krotov_comm_connect",
     "krotov_group_connect", "krotov_group_iterate",
     "krotov_hermitian_extremes", "krotov_envelope_extremes",
@@ -83,6 +83,7 @@ def lib():
     L.krotov_last_error.restype = C.c_char_p
     L.krotov_get_info.argtypes = [vp, C.POINTER(Info)]
     L.krotov_set_cheby.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, i32]
+    L.krotov_set_amplitudes.argtypes = [vp, i32, vp, vp]
     L.krotov_forward.argtypes = [vp, vp]
     L.krotov_set_chi.argtypes = [vp, vp]
     L.krotov_set_chi_coeffs.argtypes = [vp, vp]

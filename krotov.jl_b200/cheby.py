@@ -123,8 +123,10 @@ class ChebyDirection:
     generator forward, the ADJOINT generator backward (``src/workspace.jl:69,150-160``)."""
 
     def __init__(self, H0, Hc, tlist, backward, pulses, *, limit=1e-12, specrange_buffer=0.01,
-                 specrange_method="auto", E_min=None, E_max=None, envelope_cache=None):
+                 specrange_method="auto", E_min=None, E_max=None, envelope_cache=None, amplitude=None):
         self.H0, self.Hc = H0, Hc
+        # non-linear amplitudes: `amplitude(l, eps)` = coefficient of H_l for the control value eps (range corners)
+        self._amplitude = amplitude
         # spectral envelopes by control ranges.  The two directions of a Hermitian problem propagate with the
         # same matrices and meet the same ranges one iteration apart (the forward check sees the pulse
         # buffer the backward check saw in the previous iteration, src/optimize.jl:305-306 vs :321-325),
@@ -162,6 +164,9 @@ class ChebyDirection:
         n_gen = len(self.H0)
         lo = [r[0] for r in self.control_ranges]
         hi = [r[1] for r in self.control_ranges]
+        if self._amplitude is not None:  # the generator at the range corners carries a_l(corner), not the corner itself
+            lo = [self._amplitude(l, v) for l, v in enumerate(lo)]
+            hi = [self._amplitude(l, v) for l, v in enumerate(hi)]
         key = tuple(self.control_ranges)
         if self.manual is not None:
             e_min = np.full(n_gen, self.manual[0])

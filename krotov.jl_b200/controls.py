@@ -5,7 +5,14 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["discretize", "discretize_on_midpoints", "get_controls", "get_control_derivs"]
+__all__ = ["discretize", "discretize_on_midpoints", "get_controls", "get_control_derivs", "control_of", "get_amplitudes"]
+
+
+def control_of(amplitude):
+    """The control object behind an amplitude (the amplitude itself for a plain control function / vector)."""
+    from .generators import PolynomialAmplitude
+
+    return amplitude.control if isinstance(amplitude, PolynomialAmplitude) else amplitude
 
 
 def _as_grid(tlist):
@@ -72,6 +79,7 @@ def get_controls(obj):
             visit(x.generator)
         elif isinstance(x, Generator):
             for a in x.amplitudes:
+                a = control_of(a)
                 if id(a) not in seen:
                     seen.add(id(a))
                     out.append(a)
@@ -94,7 +102,27 @@ def get_control_derivs(generator, controls):
         mu = None
         if isinstance(generator, Generator):
             for op, a in zip(generator.control_ops, generator.amplitudes):
-                if a is c:
+                if control_of(a) is c:
                     mu = op if mu is None else mu + op
         derivs.append(mu)
     return derivs
+
+
+def get_amplitudes(generator, controls):
+    """``[amplitude object of control c or None]``: the non-linear / shaped amplitude through which each control enters
+    ``generator`` (None = the control itself multiplies its operator).  One amplitude per control and generator."""
+    from .generators import Generator, PolynomialAmplitude
+
+    out = []
+    for c in controls:
+        found = None
+        if isinstance(generator, Generator):
+            for a in generator.amplitudes:
+                if control_of(a) is c and isinstance(a, PolynomialAmplitude):
+                    if found is not None and found is not a:
+                        raise ValueError("a control enters one generator through two different amplitudes: unsupported")
+                    found = a
+                elif control_of(a) is c and found is not None:
+                    raise ValueError("a control enters one generator both directly and through an amplitude: unsupported")
+        out.append(found)
+    return out

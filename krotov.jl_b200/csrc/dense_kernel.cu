@@ -954,6 +954,7 @@ struct DenseEngine {
     long long launches = 0;
     int sm_count = 148;
     DenseComm comm;
+    AmpDev amp;
     // sparse mode (ELL): shared pattern, values per generator and term for both directions
     bool sparse = false;
     int W = 0;
@@ -1112,6 +1113,10 @@ bool sweep_configure(DenseEngine *e) {
     return true;
 }
 
+// generator coefficients of a sweep under known pulses / under the updated pulses
+inline const double *gen_coeffs_old(const DenseEngine *e, const double *d_eps) { return e->amp.amp_old ? e->amp.amp_old : d_eps; }
+inline const double *gen_coeffs_new(const DenseEngine *e, const double *d_eps_new) { return e->amp.amp_new ? e->amp.amp_new : d_eps_new; }
+
 bool sweep_usable(const DenseEngine *e, int mode) {
     return e->sweep && e->comm.world <= 1 && e->ch[0].set && (mode == 0 || e->ch[1].set) && !getenv("KROTOV_NO_SWEEP");
 }
@@ -1143,6 +1148,7 @@ bool launch_sweep(DenseEngine *e, int mode, const double *d_eps_old, double *d_e
     p.PSI = e->PSI; p.V[0] = e->V[0]; p.V[1] = e->V[1]; p.V[2] = e->V[2]; p.OUT = e->OUT; p.X = e->X; p.PHI = e->PHI;
     p.PSI0 = e->PSI0; p.CHI = e->CHI; p.slab = e->slab;
     p.eps_old = d_eps_old; p.eps_new = d_eps_new; p.alpha = d_alpha; p.dt = d_dt; p.ga = d_ga;
+    p.amp_old = gen_coeffs_old(e, d_eps_old); p.am = e->amp;
     p.partial = e->sw_partial;
     p.cg_sync = getenv("KROTOV_SWEEP_CGSYNC") ? 1 : 0;
     p.bar = e->sw_bar;
@@ -1402,6 +1408,8 @@ void dense_destroy(DenseEngine *e) {
     delete e;
 }
 
+void dense_set_amp(DenseEngine *e, const AmpDev &a) { e->amp = a; }
+
 void dense_info(DenseEngine *e, krotov_info *out) {
     out->grid_blocks = e->sparse ? (e->sweep_launches ? e->sw_grid : e->dp / SP_ROWS) : (e->streamk ? e->sm_count : e->dp / BM);
     out->graph_replays = e->graph_replays;
@@ -1466,7 +1474,7 @@ bool dense_forward(DenseEngine *e, const double *d_eps, double2 *d_tau, long lon
     }
     if (e->store_fw) DK_CHECK(cudaMemcpyAsync(e->PHI, e->PSI0, e->slab * 16, cudaMemcpyDeviceToDevice, e->stream));
     for (int n = 0; n < e->N_T; ++n)
-        if (!step(e, KROTOV_FORWARD, n, d_eps, e->store_fw ? e->PHI + e->slab * (size_t)(n + 1) : nullptr, err))
+        if (!step(e, KROTOV_FORWARD, n, gen_coeffs_old(e, d_eps), e->store_fw ? e->PHI + e->slab * (size_t)(n + 1) : nullptr, err))
             return false;
     if (!finish_sweep(e, d_tau, err)) return false;
     launches += e->launches;
@@ -1493,7 +1501,7 @@ bool dense_iterate(DenseEngine *e, const double *d_eps_old, double *d_eps_new, c
                    std::string &err) {
     DenseEngine::GraphKey key;
     key.cheb_version = e->cheb_version;
-    const void *ptrs[8] = {d_eps_old, d_eps_new, d_alpha, d_dt, d_ga, d_chi_coef, d_tau, nullptr};
+    const void *ptrs[8] = {d_eps_old, d_eps_new, d_alpha, d_dt, d_ga, d_chi_coef, d_tau, e->amp.amp_old};
     memcpy(key.ptr, ptrs, sizeof(ptrs));
     const bool graph_ok = e->comm.world <= 1 && !getenv("KROTOV_NO_GRAPH") && !sweep_usable(e, 1);  // (the sweep is 3 launches)
     if (graph_ok && e->graph_exec != nullptr && e->graph_key == key) {
@@ -1560,7 +1568,7 @@ bool iterate_body(DenseEngine *e, const double *d_eps_old, double *d_eps_new, co
     DK_CHECK(cudaMemcpyAsync(e->PSI, e->CHI, e->slab * 16, cudaMemcpyDeviceToDevice, e->stream));
     DK_CHECK(cudaMemcpyAsync(e->X + e->slab * (size_t)N_T, e->CHI, e->slab * 16, cudaMemcpyDeviceToDevice, e->stream));
     for (int n = N_T - 1; n >= 0; --n)
-        if (!step(e, KROTOV_BACKWARD, n, d_eps_old, e->X + e->slab * (size_t)n, err)) return false;
+        if (!step(e, KROTOV_BACKWARD, n, gen_coeffs_old(e, d_eps_old), e->X + e->slab * (size_t)n, err)) return false;
     // ---- forward sweep with sequential update
     DK_CHECK(cudaMemcpyAsync(e->PSI, e->PSI0, e->slab * 16, cudaMemcpyDeviceToDevice, e->stream));
     const size_t mat = (size_t)e->dp * e->dp;
@@ -1586,9 +1594,9 @@ bool iterate_body(DenseEngine *e, const double *d_eps_old, double *d_eps_new, co
             }
         }
         update_kernel<<<e->L, 32, 0, e->stream>>>(e->partial, e->n_partial, e->L, d_alpha, d_eps_old, d_eps_new, d_ga,
-                                                 d_dt, N_T, n, e->comm);
+                                                 d_dt, N_T, n, e->comm, e->amp);
         e->launches++;
-        if (!step(e, KROTOV_FORWARD, n, d_eps_new, e->store_fw ? e->PHI + e->slab * (size_t)n : nullptr, err))
+        if (!step(e, KROTOV_FORWARD, n, gen_coeffs_new(e, d_eps_new), e->store_fw ? e->PHI + e->slab * (size_t)n : nullptr, err))
             return false;
     }
     return finish_sweep(e, d_tau, err);

@@ -114,6 +114,11 @@ struct krotov_handle_s {
     int total_ctas = 0;  // CTAs of all ranks (krotov_comm_connect)
     int max_ctas = 0;    // largest CTA count of a rank
     int xchg_last = 0;   // cross-rank protocol of the last launch: 0 none, 1 hier, 2 onehop, 3 mailboxes
+    // non-linear control amplitudes (krotov_set_amplitudes)
+    bool amp_set = false;
+    std::vector<double> amp_poly;   // [L][kAmpMaxDeg+1], ascending powers (empty = a(eps) = eps)
+    std::vector<double> amp_shape;  // [L][N_T] (empty = 1)
+    DevBuf d_amp_poly, d_amp_shape, d_amp_old, d_amp_dfac, d_amp_new;
     DevBuf d_emul;       // krotov_group_iterate: per-rank parameter blocks of the emulated multi-rank launch
     bool peer_opened[kr::kMaxRanks] = {};
     long long iter_count = 0;
@@ -489,6 +494,10 @@ void fill_warp_params(krotov_handle h, int mode, kr::WarpParams &p) {
     p.dtc_f = (const int *)h->cheb[0].dtc.p; p.dtc_b = (const int *)h->cheb[1].dtc.p; p.dt = (const double *)h->d_dt.p;
     p.alpha = (const double *)h->d_alpha.p;
     p.eps_old = (const double *)h->d_eps_old.p; p.eps_new = (double *)h->d_eps_new.p;
+    p.amp_old = h->amp_set ? (const double *)h->d_amp_old.p : p.eps_old;
+    p.amp_dfac = h->amp_set ? (const double *)h->d_amp_dfac.p : nullptr;
+    p.amp_poly = (h->amp_set && !h->amp_poly.empty()) ? (const double *)h->d_amp_poly.p : nullptr;
+    p.amp_shape = (h->amp_set && !h->amp_shape.empty()) ? (const double *)h->d_amp_shape.p : nullptr;
     p.g_a_int = (double *)h->d_ga.p;
     p.X = (double2 *)h->d_X.p; p.Phi = (double2 *)h->d_Phi.p;
     p.psi0 = (const double2 *)h->d_psi0.p;
@@ -538,7 +547,7 @@ void fill_warp_params(krotov_handle h, int mode, kr::WarpParams &p) {
 int launch_warp(krotov_handle h, int mode) {
     kr::WarpParams p;
     fill_warp_params(h, mode, p);
-    if (h->tiny && h->world == 1) {
+    if (h->tiny && h->world == 1 && !h->amp_set) {
         kr::TinyParams tp;
         tp.w = p;
         tp.Tf = (const double2 *)h->d_Tf.p;
@@ -606,7 +615,8 @@ int krotov_destroy(krotov_handle h) {
     DevBuf *bufs[] = {&h->d_acc, &h->d_Tf, &h->d_Tb, &h->d_cols, &h->d_Pf, &h->d_Pb, &h->d_inv_s, &h->d_gen, &h->d_dt, &h->d_alpha,
                       &h->d_eps_old, &h->d_eps_new, &h->d_ga, &h->d_X, &h->d_Phi, &h->d_psi0, &h->d_target,
                       &h->d_chiT, &h->d_chicoef, &h->d_psif, &h->d_tau, &h->d_R, &h->d_err, &h->d_weight, &h->d_prof,
-                      &h->d_mbox[0], &h->d_mbox[1], &h->d_emul};
+                      &h->d_mbox[0], &h->d_mbox[1], &h->d_emul,
+                      &h->d_amp_poly, &h->d_amp_shape, &h->d_amp_old, &h->d_amp_dfac, &h->d_amp_new};
     for (DevBuf *b : bufs) b->release();
     for (int dir = 0; dir < 2; ++dir) {
         h->cheb[dir].coef.release();
@@ -898,7 +908,7 @@ int krotov_get_info(krotov_handle h, krotov_info *out) {
     out->nnz_union = h->nnz_union;
     out->grid_blocks = h->nCTA;
     out->block_threads = h->wpc * h->lpt + 32;
-    if (h->tiny && h->world == 1) {
+    if (h->tiny && h->world == 1 && !h->amp_set) {
         out->grid_blocks = 1;
         out->block_threads = 32;
     }
@@ -989,6 +999,36 @@ int krotov_set_cheby(krotov_handle h, int direction, int n_dt_class, const int32
     return KROTOV_OK;
 }
 
+// a_l(eps_old) and a_l'(eps_old) for the pulses of the coming sweep: O(L N_T) host work, uploaded on the launch stream
+static int prepare_amplitudes(krotov_handle h, const double *pulses) {
+    if (!h->amp_set) return KROTOV_OK;
+    const int L = h->L, N_T = h->N_T, D = kr::kAmpMaxDeg;
+    std::vector<double> a((size_t)L * N_T), da((size_t)L * N_T);
+    for (int l = 0; l < L; ++l)
+        for (int n = 0; n < N_T; ++n) {
+            const double e = pulses[(size_t)l * N_T + n];
+            double v = e, dv = 1.0;
+            if (!h->amp_poly.empty()) {
+                const double *q = &h->amp_poly[(size_t)l * (D + 1)];
+                v = q[D];
+                for (int p = D - 1; p >= 0; --p) v = std::fma(v, e, q[p]);  // same Horner form as the kernels
+                dv = 0.0;
+                for (int p = D; p >= 1; --p) dv = dv * e + p * q[p];
+            }
+            if (!h->amp_shape.empty()) {
+                const double sh = h->amp_shape[(size_t)l * N_T + n];
+                v = sh * v;
+                dv = sh * dv;
+            }
+            a[(size_t)l * N_T + n] = v;
+            da[(size_t)l * N_T + n] = dv;
+        }
+    int rc;
+    if ((rc = upload(h, h->d_amp_old, a))) return rc;
+    if ((rc = upload(h, h->d_amp_dfac, da))) return rc;
+    return KROTOV_OK;
+}
+
 static int begin_timed(krotov_handle h) {
     h->launches_last = 0;
     KR_CUDA(h, cudaEventRecord(h->ev0, h->stream));
@@ -1011,6 +1051,7 @@ int krotov_forward(krotov_handle h, const double *pulses) {
     cudaSetDevice(h->device);
     KR_CUDA(h, cudaMemcpyAsync(h->d_eps_old.p, pulses, (size_t)h->L * h->N_T * 8, cudaMemcpyHostToDevice, h->stream));
     int rc;
+    if ((rc = prepare_amplitudes(h, pulses))) return rc;
     if ((rc = begin_timed(h))) return rc;
     if (h->path == KROTOV_PATH_WARP) {
         if ((rc = launch_warp(h, 0))) return rc;
@@ -1071,6 +1112,7 @@ static int iterate_prepare(krotov_handle h, const double *guess_pulses) {
     const size_t pbytes = (size_t)h->L * h->N_T * 8;
     KR_CUDA(h, cudaMemcpyAsync(h->d_eps_old.p, guess_pulses, pbytes, cudaMemcpyHostToDevice, h->stream));
     int rc;
+    if ((rc = prepare_amplitudes(h, guess_pulses))) return rc;
     if ((rc = begin_timed(h))) return rc;
     if (need_device_coef) {
         chi_coef_kernel<<<1, 32, 0, h->stream>>>(h->functional, h->N, h->N_global, (const double2 *)h->d_tau.p,
@@ -1198,6 +1240,47 @@ int krotov_group_iterate(krotov_handle *hs, int world, const double *guess_pulse
     h0->launches_last += 1;
     for (int r = 0; r < world; ++r)
         if ((rc = iterate_finish(hs[r], new_pulses + (size_t)r * pn, g_a_int + (size_t)r * h0->L))) return rc;
+    return KROTOV_OK;
+}
+
+int krotov_set_amplitudes(krotov_handle h, int degree, const double *poly, const double *shape) {
+    if (!h) return KROTOV_ERR_ARG;
+    if (poly && (degree < 1 || degree > kr::kAmpMaxDeg))
+        return fail(h, KROTOV_ERR_UNSUPPORTED, "amplitude polynomials of degree 1..4 only");
+    cudaSetDevice(h->device);
+    const int L = h->L, N_T = h->N_T, D = kr::kAmpMaxDeg;
+    h->amp_poly.clear();
+    h->amp_shape.clear();
+    if (poly) {
+        h->amp_poly.assign((size_t)L * (D + 1), 0.0);
+        for (int l = 0; l < L; ++l)
+            for (int p = 0; p <= degree; ++p) {
+                const double v = poly[(size_t)l * (degree + 1) + p];
+                if (!std::isfinite(v)) return fail(h, KROTOV_ERR_ARG, "amplitude polynomial coefficient is not finite");
+                h->amp_poly[(size_t)l * (D + 1) + p] = v;
+            }
+    }
+    if (shape) h->amp_shape.assign(shape, shape + (size_t)L * N_T);
+    h->amp_set = poly != nullptr || shape != nullptr;
+    int rc;
+    if (!h->amp_poly.empty() && (rc = upload(h, h->d_amp_poly, h->amp_poly))) return rc;
+    if (!h->amp_shape.empty() && (rc = upload(h, h->d_amp_shape, h->amp_shape))) return rc;
+    if (h->amp_set) {
+        if ((rc = dev_alloc(h, h->d_amp_old, (size_t)L * N_T * 8))) return rc;
+        if ((rc = dev_alloc(h, h->d_amp_dfac, (size_t)L * N_T * 8))) return rc;
+        if ((rc = dev_alloc(h, h->d_amp_new, (size_t)L * N_T * 8))) return rc;
+    }
+    if (h->dense) {
+        kr::AmpDev a;
+        if (h->amp_set) {
+            a.amp_old = (const double *)h->d_amp_old.p;
+            a.dfac = (const double *)h->d_amp_dfac.p;
+            a.poly = h->amp_poly.empty() ? nullptr : (const double *)h->d_amp_poly.p;
+            a.shape = h->amp_shape.empty() ? nullptr : (const double *)h->d_amp_shape.p;
+            a.amp_new = (double *)h->d_amp_new.p;
+        }
+        kr::dense_set_amp(h->dense, a);
+    }
     return KROTOV_OK;
 }
 

@@ -131,6 +131,17 @@ class KrotovCuda:
         self._check(self._lib.krotov_set_cheby(self._h, int(direction), ndtc, _ptr(dtc), _ptr(dts), _ptr(Emin),
                                                _ptr(Dl), _ptr(m), _ptr(tab), m_max))
 
+    def set_amplitudes(self, poly=None, shape=None):
+        """Non-linear amplitudes ``a_l(eps, n) = shape[l][n] * sum_p poly[l][p] eps^p`` (``krotov_set_amplitudes``);
+        ``poly``: (L, degree+1) or None, ``shape``: (L, N_T) or None."""
+        deg = 1
+        if poly is not None:
+            poly = np.ascontiguousarray(poly, np.float64).reshape(self.L, -1)
+            deg = poly.shape[1] - 1
+        if shape is not None:
+            shape = np.ascontiguousarray(shape, np.float64).reshape(self.L, self.N_T)
+        self._check(self._lib.krotov_set_amplitudes(self._h, int(deg), _ptr(poly), _ptr(shape)))
+
     # -- hot path -------------------------------------------------------------------------
     def forward(self, pulses):
         p = np.ascontiguousarray(pulses, np.float64).reshape(self.L, self.N_T)
@@ -227,6 +238,10 @@ class KrotovCudaGroup:
         m, tab = np.asarray(m), np.asarray(tab)
         for e, g in zip(self.engines, self.gens):
             e.set_cheby(direction, dt_class_of_step, dt_of_class, E_min[g], Delta[g], m[g], tab[g])
+
+    def set_amplitudes(self, poly=None, shape=None):
+        for e in self.engines:
+            e.set_amplitudes(poly, shape)
 
     def forward(self, pulses):
         for e in self.engines:  # no cross-rank dependency in a plain forward sweep

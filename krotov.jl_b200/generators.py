@@ -4,7 +4,39 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["Generator", "hamiltonian"]
+__all__ = ["Generator", "hamiltonian", "ShapedAmplitude", "PolynomialAmplitude"]
+
+
+class PolynomialAmplitude:
+    """A control amplitude that is a NON-LINEAR function of its control: the term enters the generator as
+    ``a(eps(t), t) * op`` with ``a(eps, t) = shape(t) * sum_p coeffs[p] * eps**p`` (``coeffs`` ascending, degree
+    1..4; ``shape`` a callable or a vector on the intervals of the time grid, default 1).
+
+    The reference handles such terms through ``get_control_derivs`` / ``evaluate`` (``src/optimize.jl:268-272``):
+    the derivative ``mu = a'(eps, t) op`` is evaluated at the GUESS pulse of every interval (``:337``).  Here the
+    amplitude is handed to the device as its polynomial (``krotov_set_amplitudes``)."""
+
+    def __init__(self, control, coeffs, shape=None):
+        coeffs = [float(c) for c in coeffs]
+        if not 2 <= len(coeffs) <= 5:
+            raise ValueError("PolynomialAmplitude: 2 to 5 coefficients (degree 1 to 4)")
+        self.control, self.coeffs, self.shape = control, coeffs, shape
+
+    def __call__(self, eps, t=None):
+        v = 0.0
+        for c in reversed(self.coeffs):
+            v = v * eps + c
+        if self.shape is not None and t is not None and callable(self.shape):
+            v = self.shape(t) * v
+        return v
+
+
+class ShapedAmplitude(PolynomialAmplitude):
+    """``a(t) = shape(t) * eps(t)``: QuantumPropagators' ``ShapedAmplitude`` -- linear in the control, but the
+    derivative ``mu = shape(t) op`` depends on time."""
+
+    def __init__(self, control, shape):
+        super().__init__(control, [0.0, 1.0], shape)
 
 
 def _is_sparse(op):
@@ -62,7 +94,8 @@ def hamiltonian(*terms):
     drift, cops, amps = [], [], []
     for term in terms:
         if isinstance(term, (tuple, list)) and len(term) == 2 and not np.isscalar(term[0]) and (
-                callable(term[1]) or np.ndim(term[1]) == 1) and (_is_sparse(term[0]) or np.ndim(term[0]) == 2):
+                callable(term[1]) or isinstance(term[1], PolynomialAmplitude) or np.ndim(term[1]) == 1) and (
+                _is_sparse(term[0]) or np.ndim(term[0]) == 2):
             cops.append(term[0])
             amps.append(term[1])
         else:

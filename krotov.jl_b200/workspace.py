@@ -20,7 +20,7 @@ import numpy as np
 
 from . import _lib as B
 from .cheby import ChebyDirection
-from .controls import discretize_on_midpoints, get_control_derivs, get_controls
+from .controls import discretize_on_midpoints, get_amplitudes, get_control_derivs, get_controls
 from .engine import KrotovCuda
 from .errors import ArgumentError, ErrorException
 from .functionals import make_chi
@@ -207,6 +207,7 @@ class KrotovWrk:
             raise ErrorException("no controls in trajectories: cannot optimize")
         self.control_derivs = [get_control_derivs(t.generator, self.controls) for t in self.trajectories]
         tlist = np.asarray(problem.tlist, np.float64)
+        self._amp_poly, self._amp_shape = self._collect_amplitudes(tlist)
         kwargs = dict(kwargs_in)  # shallow copy; ok to modify
         default_shape = kwargs_in.get("update_shape", lambda t: 1.0)
         default_lambda = float(kwargs_in.get("lambda_a", 1.0))
@@ -292,6 +293,59 @@ class KrotovWrk:
             self.result.states = self._states
 
     # -------------------------------------------------------------------------------------
+    def _collect_amplitudes(self, tlist):
+        """Non-linear / shaped amplitudes (``src/optimize.jl:268-272``): per control the polynomial and the per-interval
+        shape through which it enters the generators -- the same for every generator that depends on the control (the
+        batched device propagator evaluates one amplitude per control).  ``(None, None)`` for linear controls."""
+        L = len(self.controls)
+        chosen = [None] * L
+        seen = set()
+        for t in self.trajectories:
+            if id(t.generator) in seen:
+                continue
+            seen.add(id(t.generator))
+            amps = get_amplitudes(t.generator, self.controls)
+            derivs = get_control_derivs(t.generator, self.controls)
+            for l in range(L):
+                if derivs[l] is None:
+                    continue
+                a = amps[l]
+                key = None if a is None else (tuple(a.coeffs), id(a.shape) if a.shape is not None else None)
+                if chosen[l] is None:
+                    chosen[l] = (key, a)
+                elif chosen[l][0] != key:
+                    raise ArgumentError("a control must enter all generators through the same amplitude")
+        amps = [c[1] if c is not None else None for c in chosen]
+        if all(a is None for a in amps):
+            return None, None
+        deg = max(len(a.coeffs) - 1 for a in amps if a is not None)
+        poly = np.zeros((L, deg + 1))
+        shape = None
+        for l, a in enumerate(amps):
+            if a is None:
+                poly[l, 1] = 1.0
+                continue
+            poly[l, : len(a.coeffs)] = a.coeffs
+            if a.shape is not None:
+                if shape is None:
+                    shape = np.ones((L, len(tlist) - 1))
+                shape[l] = discretize_on_midpoints(a.shape, tlist)
+        if all(np.array_equal(poly[l], np.eye(deg + 1)[1]) for l in range(L)):
+            poly = None  # only shapes: a(eps, n) = shape[n] * eps
+        return poly, shape
+
+    def _amp_envelope(self, l, eps):
+        """Coefficient of H_l at a corner ``eps`` of the control range, for the spectral envelope: the polynomial at
+        the corner times the largest |shape| (unpinned convention, see oracle ``amplitude_envelope``)."""
+        v = eps
+        if self._amp_poly is not None:
+            v = 0.0
+            for c in self._amp_poly[l][::-1]:
+                v = v * eps + c
+        if self._amp_shape is not None:
+            v = float(np.max(np.abs(self._amp_shape[l]))) * v
+        return v
+
     def _build_device_side(self, tlist, comm):
         trajs = self.trajectories
         N, L = self.N, len(self.controls)
@@ -367,6 +421,9 @@ class KrotovWrk:
             self._Hc = [Hc[g] for g in local_gens]
         if comm is not None and world > 1:
             comm.connect(self.engine)
+        nonlinear = self._amp_poly is not None or self._amp_shape is not None
+        if nonlinear:
+            self.engine.set_amplitudes(self._amp_poly, self._amp_shape)
         # ---- Chebyshev settings of both directions (init_prop: un-widened ranges of the guess pulses)
         adj = lambda m: m.conj().T.tocsr() if hasattr(m, "tocsr") else m.conj().T  # noqa: E731
         same = lambda a, b: (abs(a - b).max() == 0) if hasattr(a, "tocsr") else np.array_equal(a, b)  # noqa: E731
@@ -382,7 +439,8 @@ class KrotovWrk:
                 H0s, Hcs, tlist, backward, self._init_pulses,
                 limit=pk.get("cheby_coeffs_limit", 1e-12), specrange_buffer=pk.get("specrange_buffer", 0.01),
                 specrange_method=pk.get("specrange_method", "auto"), E_min=pk.get("E_min"), E_max=pk.get("E_max"),
-                envelope_cache=shared if self._shared_envelope_ok(pk) else None)
+                envelope_cache=shared if self._shared_envelope_ok(pk) else None,
+                amplitude=self._amp_envelope if nonlinear else None)
 
         self.fw_settings = settings(self.fw_prop_kwargs[0], False)
         self.bw_settings = settings(self.bw_prop_kwargs[0], True)

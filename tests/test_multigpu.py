@@ -1,7 +1,9 @@
 """Two ranks on two GPUs: trajectories sharded, per-step overlap sums exchanged in-kernel over NVLink -- by the
-one-hop fixed-point sum (every CTA adds into every rank's accumulator) and by the mailbox protocol (rank sums pushed
-into the peers' mailboxes; `KROTOV_NO_XACC=1`, also the dense path's protocol).
-Needs >= 2 CUDA devices (skipped on the single-GPU box); run with `gpurun --gpus 2`."""
+hierarchical fixed-point sum (default: local accumulator, the completing add forwards one add per rank), by the one-hop
+sum (`KROTOV_XCHG=onehop`: every CTA adds into every rank's accumulator) and by the mailbox protocol
+(`KROTOV_XCHG=mbox`: rank sums pushed into the peers' mailboxes; also the dense path's protocol).
+Needs >= 2 CUDA devices (skipped on the single-GPU box); run with `gpurun --gpus 2`.  The same protocols run on ONE
+device in tests/test_parity_gpu.py (`emulate_ranks`, all ranks' CTAs in one cooperative launch)."""
 import os
 
 import numpy as np
@@ -70,9 +72,11 @@ def _worker(rank, world, port, kind, n_samples, n_grid, iters, q, env=None):
 
 
 @pytest.mark.parametrize("kind,n_samples,n_grid,env", [
-    ("c4", 8, 201, {}), ("c4", 64, 101, {}), ("c4", 64, 101, {"KROTOV_XACC_STRIDE": "16"}),
-    ("c4", 8, 201, {"KROTOV_NO_XACC": "1"}), ("c4", 64, 101, {"KROTOV_NO_XACC": "1"}),
-    ("c4", 8, 41, {"TEST_BIG_CHI": "1"}), ("sm", 20, 21, {}), ("ss", 9, 21, {})])
+    ("c4", 8, 201, {}), ("c4", 64, 101, {}), ("c4", 2, 101, {}), ("c4", 64, 101, {"KROTOV_XCHG": "onehop"}),
+    ("c4", 64, 101, {"KROTOV_XCHG": "onehop", "KROTOV_XACC_STRIDE": "16"}),
+    ("c4", 8, 201, {"KROTOV_XCHG": "mbox"}), ("c4", 64, 101, {"KROTOV_NO_XACC": "1"}),
+    ("c4", 8, 41, {"TEST_BIG_CHI": "1"}), ("c4", 8, 41, {"TEST_BIG_CHI": "1", "KROTOV_XCHG": "onehop"}),
+    ("sm", 20, 21, {}), ("ss", 9, 21, {})])
 def test_two_ranks_match_single_gpu(kind, n_samples, n_grid, env):
     """kind c4: warp path (in-kernel reducer exchange); kinds sm/ss: dense DMMA path (exchange in update_kernel)."""
     import torch

@@ -1067,3 +1067,81 @@ def test_emulated_ranks_fall_back_when_a_partial_does_not_fit(xchg, monkeypatch)
     assert min(fb) > 20  # most of the 40 steps carry sums beyond 2^28
     assert np.abs(np.array(got["J_T"]) - np.array(single["J_T"])).max() < 1e-12
     assert np.abs(got["pulses"] - single["pulses"]).max() < 1e-11
+
+
+# ---- non-linear control amplitudes (src/optimize.jl:268-272, 337-346) ---------------------------------------------------
+def _nonlinear(w, T):
+    """control 0 enters quadratically (eps + 2 eps^2), the last control through a time-dependent shape."""
+    L = len(w.controls)
+    w.amp_poly = [[0.0, 1.0, 2.0]] + [None] * (L - 1)
+    w.amp_shape = [None] * (L - 1) + [lambda t: 0.5 + 0.5 * W.flattop(t, T=T, t_rise=0.25 * T)]
+    if L == 1:
+        w.amp_poly = [[0.05, 1.0, 2.0, -0.5]]
+    return w
+
+
+def test_nonlinear_amplitude_tls_against_exact_50_digit_optimisation():
+    """H = -sz/2 + (eps + eps^2/2) sx: the derivative mu = (1 + eps) sx is evaluated at the guess pulse.  Against
+    the NumPy oracle at the BASELINE tolerances and against the oracle-independent 50-digit exact-propagator run."""
+    import mp_reference as M
+    from oracle import krotov_oracle as O
+
+    w = W.c1_tls()
+    w.amp_poly = [[0.0, 1.0, 0.5]]
+    got = run_product(w, 4)
+    assert got["info"]["block_threads"] > 32  # amplitudes are served by the warp kernel, not the one-thread kernel
+    ref = O.optimize_krotov(W.to_oracle(w), 4)
+    assert_parity(got, ref["J_T"], ref["pulses"], ref["g_a_int"])
+    exact = M.tls_krotov_exact(4, amp_poly=[0.0, 1.0, 0.5])
+    assert np.abs(np.array(got["J_T"]) - np.array(exact["J_T"])).max() < 1e-12
+    assert np.abs(got["pulses"][0] - np.array(exact["pulses"])).max() < 1e-12
+    assert got["J_T"][-1] < 0.01 < got["J_T"][0]
+
+
+def test_nonlinear_amplitudes_ensemble_multi_cta_and_emulated_ranks():
+    from oracle import c_oracle as C
+
+    w = _nonlinear(W.c4_ensemble(n_samples=8, n_grid=201), 400.0)
+    ref = C.optimize_krotov_c(W.to_oracle(w), 2)
+    got = run_product(w, 2)
+    assert got["info"]["grid_blocks"] > 1
+    assert_parity(got, ref["J_T"], ref["pulses"], rtol=1e-10, atol=5e-13)
+    assert np.abs(np.array(got["g_a_int"]) - np.array(ref["g_a_int"])).max() <= 1e-11
+    lin = run_product(W.c4_ensemble(n_samples=8, n_grid=201), 2)
+    assert np.abs(got["pulses"] - lin["pulses"]).max() > 1e-4  # the amplitudes do change the optimisation
+    two = run_product(w, 2, emulate_ranks=2)
+    assert np.abs(two["pulses"] - got["pulses"]).max() < 1e-12 and np.abs(np.array(two["J_T"]) - np.array(got["J_T"])).max() < 1e-12
+
+
+@pytest.mark.parametrize("kind", ["dense", "sparse_sweep", "sparse_stream", "reloaded_rows"])
+def test_nonlinear_amplitudes_block_paths(kind, monkeypatch):
+    from oracle import krotov_oracle as O
+
+    if kind == "dense":
+        w = _nonlinear(W.dummy_dense(d=40, n_traj=6, n_controls=2, n_grid=31, seed=3), 5.0)
+    elif kind == "reloaded_rows":
+        monkeypatch.setenv("KROTOV_NO_PREG", "1")
+        w = _nonlinear(W.dummy_dense(d=12, n_traj=5, n_controls=2, n_grid=31, seed=4), 5.0)
+    else:
+        if kind == "sparse_stream":
+            monkeypatch.setenv("KROTOV_NO_SWEEP", "1")
+        w = _nonlinear(W.spin_chain(n_spins=6, n_traj=8, n_grid=31), 4.0)
+    got = run_product(w, 2)
+    assert got["info"]["path"] == {"dense": 2, "reloaded_rows": 1}.get(kind, 3)
+    ref = O.optimize_krotov(W.to_oracle(w), 2)
+    assert_parity(got, ref["J_T"], ref["pulses"], ref["g_a_int"], rtol=1e-10, atol=5e-13)
+
+
+def test_amplitude_argument_errors():
+    w = W.c1_tls()
+    with pytest.raises(ValueError):
+        K.PolynomialAmplitude(w.controls[0], [1.0])
+    with pytest.raises(ValueError):
+        K.PolynomialAmplitude(w.controls[0], [0, 1, 2, 3, 4, 5])
+    eps = w.controls[0]
+    H_a = K.hamiltonian(w.H0[0], (w.Hc[0][0], K.PolynomialAmplitude(eps, [0, 1, 1])))
+    H_b = K.hamiltonian(w.H0[0], (w.Hc[0][0], K.PolynomialAmplitude(eps, [0, 1, 2])))
+    trajs = [K.Trajectory(w.psi0[0], H_a, target_state=w.target[0]), K.Trajectory(w.psi0[0], H_b, target_state=w.target[0])]
+    with pytest.raises(K.ArgumentError):
+        K.optimize(K.ControlProblem(trajs, w.tlist, prop_method=K.Cheby, J_T=K.J_T_sm, lambda_a=1.0, iter_stop=1,
+                                    print_iters=False, rethrow_exceptions=True), method=K.Krotov)

@@ -19,11 +19,19 @@ def to_problem(w, **kwargs):
     Ensemble members that share a generator share the Generator OBJECT and all trajectories share the
     control OBJECTS, as a user of the reference would write it."""
     gens = []
+    amps = list(w.controls)
+    for l, c in enumerate(w.controls):  # non-linear / shaped amplitudes: ONE amplitude object per control
+        poly = None if w.amp_poly is None else w.amp_poly[l]
+        shape = None if w.amp_shape is None else w.amp_shape[l]
+        if poly is not None:
+            amps[l] = K.PolynomialAmplitude(c, poly, shape)
+        elif shape is not None:
+            amps[l] = K.ShapedAmplitude(c, shape)
     for g in range(len(w.H0)):
         terms = [w.H0[g]]
         for l, c in enumerate(w.controls):
             if w.Hc[g][l] is not None:
-                terms.append((w.Hc[g][l], c))
+                terms.append((w.Hc[g][l], amps[l]))
         gens.append(K.hamiltonian(*terms))
     trajs = [K.Trajectory(w.psi0[k], gens[int(w.gen_of_traj[k])], target_state=w.target[k]) for k in range(w.N)]
     kw = dict(prop_method=K.Cheby, J_T=_JT[w.functional], lambda_a=w.lambda_a, update_shape=w.update_shape,

@@ -17,10 +17,11 @@ comm = Comm(device=local)
 ns = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 w = W.c4_ensemble(n_samples=ns)
 ghz = 1.965
-variants = [("xacc stride 1", {"KROTOV_XACC_STRIDE": "1"}), ("xacc stride 16", {"KROTOV_XACC_STRIDE": "16"}),
-            ("mailbox", {"KROTOV_NO_XACC": "1"})]
+variants = [("hierarchical", {"KROTOV_XCHG": "hier"}), ("one-hop", {"KROTOV_XCHG": "onehop"}), ("mailbox", {"KROTOV_XCHG": "mbox"})]
+if os.environ.get("MG_WPC"):
+    variants = [(n + " wpc=" + w, dict(e, KROTOV_WPC=w)) for w in os.environ["MG_WPC"].split(",") for n, e in variants[:2]]
 for name, env in variants:
-    for k in ("KROTOV_XACC_STRIDE", "KROTOV_NO_XACC"):
+    for k in ("KROTOV_XACC_STRIDE", "KROTOV_NO_XACC", "KROTOV_XCHG", "KROTOV_WPC"):
         os.environ.pop(k, None)
     os.environ.update(env)
     out = {"ms": []}
@@ -35,7 +36,11 @@ for name, env in variants:
     K.optimize(to_problem(w, iter_stop=4, callback=cb, device=local), method=K.Krotov, comm=comm)
     comm.barrier()
     f = lambda v: v / ghz / 1e3 / w.N_T
-    lines = [f"[rank {rank}] {name}: grid={out['info']['grid_blocks']}x{out['info']['block_threads']} ms={['%.2f' % m for m in out['ms']]} fallback={out['info'].get('fallback_steps')}"]
+    if rank != 0 and not os.environ.get("MG_ALL_RANKS"):
+        for r in range(world):
+            comm.barrier()
+        continue
+    lines = [f"[rank {rank}] {name}: exchange={out['info'].get('exchange')} grid={out['info']['grid_blocks']}x{out['info']['block_threads']} ms={['%.2f' % m for m in out['ms']]} fallback={out['info'].get('fallback_steps')}"]
     for key in ["backward", "forward", "overlap", "wait_pulse", "fw_step_total", "comm_wait_partials", "comm_reduce", "comm_gather"]:
         vals = np.array([f(a[key]) for a in out["all"]])
         lines.append(f"      {key:18s} cta0={vals[0]:.3f} all: min={vals.min():.3f} mean={vals.mean():.3f} max={vals.max():.3f} us/step")

@@ -33,6 +33,9 @@ class Workload:
     functional: str  # "sm" | "ss" | "re"
     specrange: Optional[tuple] = None
     meta: dict = field(default_factory=dict)
+    # non-linear control amplitudes: control l enters as shape_l(t) * sum_p amp_poly[l][p] eps^p (None = eps itself)
+    amp_poly: Optional[list] = None  # per control: coefficients (ascending) or None
+    amp_shape: Optional[list] = None  # per control: callable t -> factor, or None
 
     @property
     def N(self):
@@ -304,7 +307,13 @@ def to_oracle(w: Workload):
 
     pulses = np.array([midpoint_samples(c, w.tlist) for c in w.controls])
     S = np.array([midpoint_samples(w.update_shape, w.tlist) for _ in w.controls])
+    amp_poly, amp_shape = None, None
+    if w.amp_poly is not None and any(c is not None for c in w.amp_poly):
+        amp_poly = [None if c is None else [float(x) for x in c] for c in w.amp_poly]
+    if w.amp_shape is not None and any(f is not None for f in w.amp_shape):
+        amp_shape = np.array([np.ones(len(w.tlist) - 1) if f is None else midpoint_samples(f, w.tlist) for f in w.amp_shape])
     return ProblemArrays(
+        amp_poly=amp_poly, amp_shape=amp_shape,
         tlist=np.asarray(w.tlist, float),
         H0=w.H0,
         Hc=w.Hc,
