@@ -113,7 +113,8 @@ typedef struct {
     int32_t sm_count;
     int32_t exchange;        /* cross-rank protocol of the last launch: 0 none (one rank), 1 hierarchical sum (local
                                 accumulator, then one add per rank over NVLink), 2 one-hop sum (every CTA adds into every
-                                rank's accumulator), 3 rank sums through the peers' mailboxes */
+                                rank's accumulator), 3 rank sums through the peers' mailboxes, 4 hierarchical sum forwarded with plain
+                                stores into per-rank slots */
     int64_t launches_total;  /* kernels launched by this handle since creation       */
     int64_t launches_last;   /* kernels launched by the last forward/iterate call    */
     double ms_last;          /* device time of the last forward/iterate call (CUDA events on the launch stream) */

@@ -531,13 +531,13 @@ void fill_warp_params(krotov_handle h, int mode, kr::WarpParams &p) {
     std::string xchg = getenv("KROTOV_XCHG") ? getenv("KROTOV_XCHG") : "hier";
     if (getenv("KROTOV_NO_XACC")) xchg = "mbox";
     const bool hier_ok = h->max_ctas < 256 && h->total_ctas <= kr::kXMaxArrivals && !getenv("KROTOV_NO_ATOMIC_SUM");
-    if (xchg == "hier" && !hier_ok) xchg = "onehop";
+    if ((xchg == "hier" || xchg == "hierst") && !hier_ok) xchg = "onehop";
     if (xchg == "onehop" && h->total_ctas > xacc_max) xchg = "mbox";
     if (h->world > 1 && h->xacc_bytes && xchg != "mbox") {
         for (int r = 0; r < h->world; ++r) p.xacc[r] = (unsigned long long *)((char *)h->peer_mbox[par][r] + h->mail_bytes);
-        p.xchg_hier = (xchg == "hier") ? 1 : 0;
+        p.xchg_hier = (xchg == "hier") ? 1 : (xchg == "hierst") ? 2 : 0;
     }
-    h->xchg_last = h->world > 1 ? (p.xacc[0] ? (p.xchg_hier ? 1 : 2) : 3) : 0;
+    h->xchg_last = h->world > 1 ? (p.xacc[0] ? (p.xchg_hier == 1 ? 1 : p.xchg_hier == 2 ? 4 : 2) : 3) : 0;
     p.err_flag = (int *)h->d_err.p;
     p.prof = (long long *)h->d_prof.p;
     p.timeout_cycles = 20000000000ll;  // ~10 s

@@ -106,7 +106,8 @@ __global__ void __launch_bounds__(256, 1) krotov_warp2_kernel(const __grid_const
     const int nthr_all = (wpc + 1) * 32;
     const int N_T = p.N_T;
     if (warp == wpc) {
-        comm_warp_run(p, (int)blockIdx.x, L, lane, wpc, nthr_all, red, eps_s, gbuf);
+        __shared__ __align__(16) WarpParams p_sh;
+        comm_warp_run(p, (int)blockIdx.x, L, lane, wpc, nthr_all, red, eps_s, gbuf, &p_sh);
         return;
     }
     const int ka = (blockIdx.x * wpc + warp) * 2, kb = ka + 1;

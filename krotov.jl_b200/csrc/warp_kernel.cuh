@@ -94,6 +94,7 @@ struct WarpParams {
     int *err_flag;
     long long timeout_cycles;
     long long *prof;           // optional [nCTA][8] cycle counters (KROTOV_PROF=1), see krotov_get_profile
+    long long pad_;            // (keeps sizeof a multiple of 8 whatever follows)
     // several ranks emulated by ONE cooperative launch on one device (krotov_group_iterate: the multi-rank protocols
     // on a single-GPU box; ranks as separate launches on one GPU may never be co-resident): the launch parameter then
     // only carries `emul`, the per-rank parameter blocks in device memory, and CTA b serves the rank whose
@@ -578,8 +579,13 @@ __device__ __forceinline__ bool xrank_hier_sum(const WarpParams &p, const int n,
 #pragma unroll
     for (int l = 0; l < kMaxCtrl; ++l)
         if (l == myl) mine = tot[l];
-    // cross-rank words live in the xacc area with its layout [(n * L + l) * 4 + limb] (the fourth limb slot is unused)
-    const size_t off = (((size_t)n * L + (lane < nw ? myl : 0)) * kXLimbs + (lane < nw ? myj : 0)) * (size_t)p.xacc_stride;
+    // cross-rank words live in the xacc area with its layout [(n * L + l) * 4 + limb] (the fourth limb slot is unused).
+    // Store variant (xchg_hier == 2): every word has one 8-byte slot PER RANK, [((n * L + l) * 4 + limb) * 8 + rank], the
+    // completing lane writes its rank's slot of every rank with a plain store (no NVLink atomic) and the pollers add the
+    // `world` slots of a word themselves.
+    const bool by_store = p.xchg_hier == 2;
+    const size_t widx = ((size_t)n * L + (lane < nw ? myl : 0)) * kXLimbs + (lane < nw ? myj : 0);
+    const size_t off = by_store ? widx * kMaxRanks : widx * (size_t)p.xacc_stride;
     if (lane < nw) {
         unsigned __int128 v;
         const bool ok = fix_from_double(mine, v, kHLimExp);
@@ -599,7 +605,10 @@ __device__ __forceinline__ bool xrank_hier_sum(const WarpParams &p, const int n,
             for (int i = 1; i <= p.world; ++i) {  // peers first (the long way), own copy last
                 int r = p.rank + i;
                 if (r >= p.world) r -= p.world;
-                red_add_sys_u64(p.xacc[r] + off, fwd);
+                if (by_store)
+                    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p.xacc[r] + off + p.rank), "l"(fwd) : "memory");
+                else
+                    red_add_sys_u64(p.xacc[r] + off, fwd);
             }
         }
     }
@@ -608,8 +617,23 @@ __device__ __forceinline__ bool xrank_hier_sum(const WarpParams &p, const int n,
     unsigned long long w = 0;
     const double *mine_p = reinterpret_cast<const double *>(p.xacc[p.rank] + off);
     for (;;) {
-        if (lane < nw) w = ld_poll_u64<true>(mine_p);
-        const bool pending = lane < nw && (int)(w >> kHCntShift) != p.world;
+        bool pending = false;
+        if (lane < nw) {
+            if (by_store) {
+                unsigned long long u[kMaxRanks];
+#pragma unroll
+                for (int r = 0; r < kMaxRanks; ++r) u[r] = (r < p.world) ? ld_poll_u64<true>(mine_p + r) : 0ull;
+                w = 0;
+#pragma unroll
+                for (int r = 0; r < kMaxRanks; ++r) {
+                    pending |= (r < p.world) && u[r] == 0ull;
+                    w += u[r];
+                }
+            } else {
+                w = ld_poll_u64<true>(mine_p);
+                pending = (int)(w >> kHCntShift) != p.world;
+            }
+        }
         if (!__any_sync(0xffffffffu, pending)) break;
         if ((++spins & 63) == 0) {
             if (clock64() - t0 > p.timeout_cycles || *(volatile int *)p.err_flag) {
@@ -735,9 +759,19 @@ static __device__ __noinline__ void exchange_gather(const WarpParams *pp, const 
 // per-lane partial overlaps (named barrier 1), reduces them in a fixed order, runs the grid / rank exchange,
 // applies the pulse update (src/optimize.jl:351-358) and releases the trajectory warps (named barrier 2).
 __device__ __forceinline__ void comm_warp_run(const WarpParams &p, const int cta, const int L, const int lane, const int wpc,
-                                              const int nthr_all, double *red, double *eps_s, double *gbuf) {
+                                              const int nthr_all, double *red, double *eps_s, double *gbuf,
+                                              WarpParams *p_sh) {
     const int N_T = p.N_T;
     if (p.mode != 1) return;
+    // The out-of-line exchange functions read the parameter block through a pointer.  A pointer to the kernel
+    // parameter itself is a generic address into the constant bank: every field read is a slow, uncached-path load
+    // (measured: +0.35 us per time step on 2 GPUs).  They get a copy in shared memory instead.
+    {
+        const unsigned long long *src = reinterpret_cast<const unsigned long long *>(&p);
+        unsigned long long *dst = reinterpret_cast<unsigned long long *>(p_sh);
+        for (int i = lane; i < (int)(sizeof(WarpParams) / 8); i += 32) dst[i] = src[i];
+        __syncwarp();
+    }
     double ga = 0.0;  // lane l accumulates g_a_int[l]  (CTA 0 writes it)
     long long c_wait_a = 0, c_reduce = 0, c_gather = 0;
     for (int n = 0; n < N_T; ++n) {
@@ -772,7 +806,7 @@ __device__ __forceinline__ void comm_warp_run(const WarpParams &p, const int cta
             double tl[kMaxCtrl];
 #pragma unroll
             for (int l = 0; l < kMaxCtrl; ++l) tl[l] = tot[l];
-            exchange_ranks(&p, cta, n, L, lane, tl, gbuf);
+            exchange_ranks(p_sh, cta, n, L, lane, tl, gbuf);
 #pragma unroll
             for (int l = 0; l < kMaxCtrl; ++l) tot[l] = tl[l];
             summed = true;
@@ -784,7 +818,7 @@ __device__ __forceinline__ void comm_warp_run(const WarpParams &p, const int cta
             double tl[kMaxCtrl];
 #pragma unroll
             for (int l = 0; l < kMaxCtrl; ++l) tl[l] = tot[l];
-            exchange_gather(&p, cta, n, L, lane, tl, gbuf);
+            exchange_gather(p_sh, cta, n, L, lane, tl, gbuf);
 #pragma unroll
             for (int l = 0; l < kMaxCtrl; ++l) tot[l] = tl[l];
         }
@@ -850,7 +884,8 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
     const int N_T = p.N_T;
 
     if (is_comm) {
-        comm_warp_run(p, cta, L, lane, wpc * (LPT / 32), nthr_all, red, eps_s, gbuf);
+        __shared__ __align__(16) WarpParams p_sh;
+        comm_warp_run(p, cta, L, lane, wpc * (LPT / 32), nthr_all, red, eps_s, gbuf, &p_sh);
         return;
     }
 

@@ -1004,12 +1004,13 @@ def test_block_path_graph_replay_equals_direct_launches(monkeypatch):
 
 
 # ---- several ranks on ONE device: the multi-rank exchange protocols without a second GPU ------------------------------
-_EXCHANGE = {"hier": 1, "onehop": 2, "mbox": 3}
+_EXCHANGE = {"hier": 1, "onehop": 2, "mbox": 3, "hierst": 4}
 
 
 @pytest.mark.parametrize("ranks,n_samples,n_grid,xchg", [
     (2, 8, 201, "hier"), (2, 8, 201, "onehop"), (2, 8, 201, "mbox"), (2, 2, 101, "hier"), (2, 2, 101, "mbox"),
-    (4, 16, 101, "hier"), (3, 12, 101, "mbox"), (8, 32, 61, "hier"), (8, 32, 61, "onehop"), (8, 64, 41, "mbox")])
+    (4, 16, 101, "hier"), (3, 12, 101, "mbox"), (8, 32, 61, "hier"), (8, 32, 61, "onehop"), (8, 64, 41, "mbox"),
+    (2, 8, 201, "hierst"), (8, 32, 61, "hierst"), (3, 3, 61, "hierst")])
 def test_emulated_ranks_match_one_rank_and_oracle(ranks, n_samples, n_grid, xchg, monkeypatch):
     """The ensemble sharded over `ranks` handles on one device, all ranks' CTAs in ONE cooperative launch
     (`krotov_group_iterate`): the unchanged multi-rank kernel code with the hierarchical sum (local accumulator, one
@@ -1042,7 +1043,7 @@ def test_emulated_ranks_match_one_rank_and_oracle(ranks, n_samples, n_grid, xchg
     assert_parity(got, ref["J_T"], ref["pulses"], rtol=1e-10, atol=5e-13)
 
 
-@pytest.mark.parametrize("xchg", ["hier", "onehop"])
+@pytest.mark.parametrize("xchg", ["hier", "onehop", "hierst"])
 def test_emulated_ranks_fall_back_when_a_partial_does_not_fit(xchg, monkeypatch):
     """chi scaled by 1e13 (lambda_a alike, so the optimisation is unchanged): the overlap sums leave the fixed-point
     range, every CTA of every rank sees the same misfit mark and redoes the step with the mailbox protocol."""

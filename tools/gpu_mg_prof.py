@@ -17,9 +17,12 @@ comm = Comm(device=local)
 ns = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 w = W.c4_ensemble(n_samples=ns)
 ghz = 1.965
-variants = [("hierarchical", {"KROTOV_XCHG": "hier"}), ("one-hop", {"KROTOV_XCHG": "onehop"}), ("mailbox", {"KROTOV_XCHG": "mbox"})]
+variants = [("hierarchical", {"KROTOV_XCHG": "hier"}), ("hierarchical, stores", {"KROTOV_XCHG": "hierst"}),
+            ("one-hop", {"KROTOV_XCHG": "onehop"}), ("mailbox", {"KROTOV_XCHG": "mbox"})]
+if os.environ.get("MG_VARIANTS"):
+    variants = [v for v in variants if v[1]["KROTOV_XCHG"] in os.environ["MG_VARIANTS"].split(",")]
 if os.environ.get("MG_WPC"):
-    variants = [(n + " wpc=" + w, dict(e, KROTOV_WPC=w)) for w in os.environ["MG_WPC"].split(",") for n, e in variants[:2]]
+    variants = [(n + " wpc=" + w, dict(e, KROTOV_WPC=w)) for w in os.environ["MG_WPC"].split(",") for n, e in variants]
 for name, env in variants:
     for k in ("KROTOV_XACC_STRIDE", "KROTOV_NO_XACC", "KROTOV_XCHG", "KROTOV_WPC"):
         os.environ.pop(k, None)
