@@ -921,6 +921,12 @@ __global__ void __launch_bounds__(SP_WARPS * 32, 2) sparse_sweep_kernel(const __
     }
 }
 
+}  // namespace
+}  // namespace kr
+#include "dense_sweep.cuh"
+namespace kr {
+namespace {
+
 struct Block {  // one GEMM column block
     int g, col0, nt;
 };
@@ -991,6 +997,11 @@ struct DenseEngine {
            *sw_Delta[2] = {nullptr, nullptr};
     double2 *sw_phase[2] = {nullptr, nullptr};
     long long sweep_launches = 0;
+    // persistent cluster sweep for moderate dense generators (dense_sweep.cuh)
+    bool dsweep = false;
+    int ds_units = 0, ds_R = 0, ds_gpad = 0;
+    size_t ds_smem = 0;
+    int *ds_units_dev = nullptr;
 };
 
 namespace {
@@ -1113,12 +1124,91 @@ bool sweep_configure(DenseEngine *e) {
     return true;
 }
 
+inline const double *gen_coeffs_old(const DenseEngine *e, const double *d_eps);
+
+// Persistent cluster sweep for moderate dense generators: one cluster of 8 CTAs per group of <= 8 columns.
+bool dsweep_configure(DenseEngine *e) {
+    e->dsweep = false;
+    if (e->sparse || e->d > kDsMaxD || getenv("KROTOV_NO_DSWEEP")) return true;
+    std::vector<int> units;
+    for (const Block &b : e->blocks)
+        for (int c = 0; c < b.nt * 8; c += kDsCols) {
+            // columns of the block that hold a trajectory (a block is padded to a multiple of 8 columns)
+            int n = 0;
+            for (int q = c; q < std::min(c + kDsCols, b.nt * 8); ++q) n += (e->traj_of_col[b.col0 + q] >= 0) ? 1 : 0;
+            if (n == 0) continue;
+            units.insert(units.end(), {b.g, b.col0 + c, std::min(kDsCols, b.nt * 8 - c)});
+        }
+    const int n_units = (int)units.size() / 3;
+    if (n_units == 0 || n_units * kDsCluster > e->sm_count) return true;  // all clusters must be co-resident
+    e->ds_R = (e->d + kDsCluster - 1) / kDsCluster;
+    e->ds_gpad = e->d | 1;
+    e->ds_smem = ((size_t)e->ds_R * e->ds_gpad + (size_t)e->d * kDsCols) * 16;
+    if (e->ds_R * kDsCols > kDsMaxOut * kDsThreads || e->ds_smem > 220 * 1024) return true;
+    if (cudaFuncSetAttribute((const void *)dense_cluster_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)e->ds_smem) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    std::string err;
+    if (!dalloc(e->ds_units_dev, units.size(), err) || !dalloc(e->sw_partial, (size_t)kMaxL * n_units * kDsCluster, err) ||
+        !dalloc(e->sw_bar, 1, err))
+        return false;
+    cudaMemcpy(e->ds_units_dev, units.data(), units.size() * 4, cudaMemcpyHostToDevice);
+    e->ds_units = n_units;
+    e->dsweep = true;
+    return true;
+}
+
+bool launch_dsweep(DenseEngine *e, int mode, const double *d_eps_old, double *d_eps_new, const double *d_alpha,
+                   const double *d_dt, double *d_ga, std::string &err) {
+    DSweepParams p;
+    memset(&p, 0, sizeof(p));
+    p.d = e->d; p.dp = e->dp; p.ld = e->ld; p.L = e->L; p.N_T = e->N_T; p.mode = mode; p.store_fw = e->store_fw;
+    p.n_units = e->ds_units; p.R = e->ds_R; p.gpad = e->ds_gpad; p.units = e->ds_units_dev;
+    p.H[0] = e->Hf;
+    p.H[1] = e->hermitian ? e->Hf : e->Hb;
+    for (int dir = 0; dir < 2; ++dir) {
+        p.coef[dir] = e->sw_coef[dir]; p.m[dir] = e->sw_m[dir]; p.phase[dir] = e->sw_phase[dir]; p.dtc[dir] = e->sw_dtc[dir];
+        p.E_min[dir] = e->sw_Emin[dir]; p.Delta[dir] = e->sw_Delta[dir];
+        p.ndtc[dir] = e->ch[dir].ndtc; p.mmax[dir] = e->ch[dir].mmax;
+    }
+    p.PSI = e->PSI; p.X = e->X; p.PHI = e->PHI; p.VX[0] = e->V[0]; p.VX[1] = e->V[1];
+    p.PSI0 = e->PSI0; p.CHI = e->CHI; p.slab = e->slab;
+    p.eps_old = d_eps_old; p.eps_new = d_eps_new; p.alpha = d_alpha; p.dt = d_dt; p.ga = d_ga;
+    p.amp_old = gen_coeffs_old(e, d_eps_old); p.am = e->amp;
+    p.partial = e->sw_partial;
+    p.bar = e->sw_bar;
+    DK_CHECK(cudaMemsetAsync(e->sw_bar, 0, sizeof(unsigned), e->stream));
+    DK_CHECK(cudaFuncSetAttribute((const void *)dense_cluster_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)e->ds_smem));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(e->ds_units * kDsCluster);
+    cfg.blockDim = dim3(kDsThreads);
+    cfg.dynamicSmemBytes = e->ds_smem;
+    cfg.stream = e->stream;
+    cudaLaunchAttribute attrs[2];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = kDsCluster;
+    attrs[0].val.clusterDim.y = 1;
+    attrs[0].val.clusterDim.z = 1;
+    attrs[1].id = cudaLaunchAttributeCooperative;  // all clusters co-resident: they meet at a grid barrier per time step
+    attrs[1].val.cooperative = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = 2;
+    DK_CHECK(cudaLaunchKernelEx(&cfg, dense_cluster_sweep_kernel, p));
+    e->launches++;
+    e->sweep_launches++;
+    return true;
+}
+
 // generator coefficients of a sweep under known pulses / under the updated pulses
 inline const double *gen_coeffs_old(const DenseEngine *e, const double *d_eps) { return e->amp.amp_old ? e->amp.amp_old : d_eps; }
 inline const double *gen_coeffs_new(const DenseEngine *e, const double *d_eps_new) { return e->amp.amp_new ? e->amp.amp_new : d_eps_new; }
 
 bool sweep_usable(const DenseEngine *e, int mode) {
-    return e->sweep && e->comm.world <= 1 && e->ch[0].set && (mode == 0 || e->ch[1].set) && !getenv("KROTOV_NO_SWEEP");
+    return (e->sweep || e->dsweep) && e->comm.world <= 1 && e->ch[0].set && (mode == 0 || e->ch[1].set) && !getenv("KROTOV_NO_SWEEP");
 }
 
 template <typename T>
@@ -1132,6 +1222,7 @@ bool sweep_upload(T *&dst, const std::vector<T> &src, std::string &err) {
 
 bool launch_sweep(DenseEngine *e, int mode, const double *d_eps_old, double *d_eps_new, const double *d_alpha,
                   const double *d_dt, double *d_ga, std::string &err) {
+    if (e->dsweep) return launch_dsweep(e, mode, d_eps_old, d_eps_new, d_alpha, d_dt, d_ga, err);
     SweepParams p;
     memset(&p, 0, sizeof(p));
     p.dp = e->dp; p.ld = e->ld; p.W = e->W; p.L = e->L; p.N_T = e->N_T; p.n_blocks = (int)e->blocks.size();
@@ -1351,7 +1442,7 @@ DenseEngine *dense_create(int d, int N, int L, int N_T, int n_gen, const std::ve
             }
         }
     }
-    if (e->sparse && !sweep_configure(e)) {
+    if ((e->sparse && !sweep_configure(e)) || (!e->sparse && !dsweep_configure(e))) {
         err = "dense_create: allocation for the persistent sweep failed";
         dense_destroy(e);
         return nullptr;
@@ -1401,7 +1492,7 @@ void dense_destroy(DenseEngine *e) {
                     e->PHI, e->partial, e->d_col_of_traj, e->d_traj_of_col, e->ell_cols, e->Pvf, e->Pvb, e->Gv,
                     e->sk_ws, e->sk_flags, e->sw_blk, e->sw_partial, e->sw_bar, e->sw_m[0], e->sw_m[1], e->sw_dtc[0], e->sw_dtc[1],
                     e->sw_coef[0], e->sw_coef[1], e->sw_Emin[0], e->sw_Emin[1], e->sw_Delta[0], e->sw_Delta[1],
-                    e->sw_phase[0], e->sw_phase[1]};
+                    e->sw_phase[0], e->sw_phase[1], e->ds_units_dev};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
@@ -1414,6 +1505,10 @@ void dense_info(DenseEngine *e, krotov_info *out) {
     out->grid_blocks = e->sparse ? (e->sweep_launches ? e->sw_grid : e->dp / SP_ROWS) : (e->streamk ? e->sm_count : e->dp / BM);
     out->graph_replays = e->graph_replays;
     out->block_threads = e->sparse ? SP_WARPS * 32 : GEMM_THREADS;
+    if (e->dsweep && e->sweep_launches) {  // the cluster sweep served the last calls
+        out->grid_blocks = e->ds_units * kDsCluster;
+        out->block_threads = kDsThreads;
+    }
     out->nnz_union = e->sparse ? e->nnz_union : e->d * e->d;
     out->ell_width = e->sparse ? e->W : 0;
     out->hbm_bytes_state = (int64_t)(e->slab * (size_t)(e->N_T + 1) * 16);
@@ -1433,7 +1528,7 @@ bool dense_set_cheby(DenseEngine *e, int direction, int ndtc, const std::vector<
     c.ndtc = ndtc; c.mmax = m_max; c.dtc_of_step = dtc_of_step; c.E_min = E_min; c.Delta = Delta; c.m = m;
     c.coef = coef; c.phase = phase; c.set = true;
     if (!same) e->cheb_version++;  // coefficients travel by value in the launch parameters: a captured iteration is stale now
-    if (e->sweep && !same) {  // the persistent sweep reads the tables from device memory
+    if ((e->sweep || e->dsweep) && !same) {  // the persistent sweeps read the tables from device memory
         std::vector<double2> ph(phase.size());
         for (size_t i = 0; i < phase.size(); ++i) ph[i] = make_double2(phase[i].real(), phase[i].imag());
         cudaStreamSynchronize(e->stream);

@@ -1,0 +1,293 @@
+// Persistent sweep for MODERATE dense generators (32 < d <= kDsMaxD): the whole Krotov iteration in one cooperative
+// launch of thread-block clusters, no kernel boundary between Chebyshev terms or time steps.
+//
+// The launch-per-term stream of the DMMA path (dense_gemm_kernel + build_G_kernel + update_kernel, ~20 launches per
+// time step) costs 5-16 us per term on generators whose term is 0.1-1 us of arithmetic.  Here a CLUSTER of 8 CTAs owns
+// a group of <= 8 trajectories (columns of the state block) of one generator:
+//   * CTA r of the cluster owns rows [r R, (r+1) R) of the generator, R = ceil(d / 8); its slice of
+//     G = 2c (H_0 - beta + sum_l a_l H_l) is rebuilt in SHARED memory once per time step from the term slices in L2;
+//   * every CTA holds the full V_{j-1} of its column group in shared memory (d x 8 complex); thread (row, column)
+//     forms one element of V_j = G V_{j-1} + V_{j-2}: a dot product of a shared-memory row of G (broadcast to the 8
+//     column threads) with a column of V_{j-1}; V_{j-2}, the running sum and the own element stay in registers;
+//   * the new rows go to a ping-pong exchange block in L2, ONE cluster barrier (barrier.cluster, ~380 cycles) orders
+//     them, and every CTA of the cluster reloads the full column group -- the column groups never talk to each other
+//     inside a time step;
+//   * once per time step of the forward sweep the overlap sums Im<chi|H_l|psi> of all clusters meet: CTA partials,
+//     one grid barrier (the counter barrier of the sparse sweep), every CTA adds them in the same fixed order.
+// Same state blocks, storage slots, Chebyshev tables and per-element arithmetic as the launch stream
+// (build_G_kernel / dense_gemm_kernel epilogues / update_kernel): tested against it.
+// Reference: the time loop of src/optimize.jl:303-317 (backward) and :328-370 (update + forward).
+#pragma once
+
+namespace kr {
+namespace {
+
+constexpr int kDsCluster = 8;    // CTAs per cluster = row slices of the generator
+constexpr int kDsCols = 8;       // trajectories (columns) per cluster
+constexpr int kDsThreads = 256;
+constexpr int kDsMaxD = 288;     // R * (d|1) * 16 B (generator slice) + d * 8 * 16 B (column group) must fit 227 KB
+constexpr int kDsMaxOut = 2;     // outputs per thread: ceil(R * 8 / 256)
+
+struct DSweepParams {
+    int d, dp, ld, L, N_T, mode, store_fw;
+    int n_units;               // clusters that carry work; unit u = (generator, first column, columns)
+    int R;                     // rows per CTA
+    int gpad;                  // row stride of the generator slice in shared memory (odd: conflict-free across rows)
+    const int *units;          // [n_units][3]
+    const double2 *H[2];       // per direction: [g][1+L][dp][dp] row-major dense terms
+    const double *coef[2];
+    const int *m[2];
+    const double2 *phase[2];
+    const int *dtc[2];
+    const double *E_min[2], *Delta[2];
+    int ndtc[2], mmax[2];
+    double2 *PSI, *X, *PHI, *VX[2];
+    const double2 *PSI0, *CHI;
+    size_t slab;
+    const double *eps_old, *alpha, *dt, *amp_old;
+    double *eps_new, *ga;
+    double *partial;           // [L][gridDim.x]
+    unsigned *bar;
+    AmpDev am;
+};
+
+__device__ __forceinline__ unsigned ds_cluster_rank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void ds_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void ds_grid_barrier(unsigned *bar, unsigned &target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+        while ((int)(ld_acquire_u32(bar) - target) < 0) {
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// acc = row . column  (complex): `grow` a shared-memory row of the generator slice, `vcol` the column of the group
+__device__ __forceinline__ void ds_dot(const double2 *__restrict__ grow, const double2 *__restrict__ vcol, const int d,
+                                       double &cr, double &ci) {
+    double ar = 0.0, ai = 0.0, ar1 = 0.0, ai1 = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < d; ++k) {
+        const double2 g = grow[k], x = vcol[(size_t)k * kDsCols];
+        ar = fma(g.x, x.x, ar);
+        ar1 = fma(-g.y, x.y, ar1);
+        ai = fma(g.x, x.y, ai);
+        ai1 = fma(g.y, x.x, ai1);
+    }
+    cr = ar + ar1;
+    ci = ai + ai1;
+}
+
+// shared memory <- the column group of a state block in global memory (d x ncols; missing columns zero)
+__device__ __forceinline__ void ds_load_group(double2 *vs, const double2 *src, const int d, const int ld, const int col0,
+                                              const int ncols) {
+    for (int i = threadIdx.x; i < d * kDsCols; i += kDsThreads) {
+        const int k = i / kDsCols, c = i - k * kDsCols;
+        vs[i] = (c < ncols) ? __ldcg(src + (size_t)k * ld + col0 + c) : make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kDsThreads, 1) dense_cluster_sweep_kernel(const __grid_constant__ DSweepParams p) {
+    extern __shared__ __align__(16) unsigned char ds_smem[];
+    __shared__ double wsum[kMaxL][kDsThreads / 32];
+    __shared__ double eps_sh[kMaxL];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int crank = (int)ds_cluster_rank();
+    const int unit = blockIdx.x / kDsCluster;
+    const bool live = unit < p.n_units;
+    const int g = live ? p.units[unit * 3] : 0, col0 = live ? p.units[unit * 3 + 1] : 0, ncols = live ? p.units[unit * 3 + 2] : 0;
+    const int d = p.d, R = p.R, gpad = p.gpad;
+    const int row0 = crank * R, nrows = max(0, min(R, d - row0));
+    double2 *gs = reinterpret_cast<double2 *>(ds_smem);  // [R][gpad] generator slice (also stages the H_l slices)
+    double2 *vs = gs + (size_t)R * gpad;                 // [d][8] V_{j-1} of the column group
+    const size_t mat = (size_t)p.dp * p.dp;
+    // this thread's outputs: o = tid + q * 256 -> (row o / 8, column o % 8)
+    int orow[kDsMaxOut], ocol[kDsMaxOut];
+    bool oval[kDsMaxOut];
+#pragma unroll
+    for (int q = 0; q < kDsMaxOut; ++q) {
+        const int o = tid + q * kDsThreads;
+        orow[q] = o / kDsCols;
+        ocol[q] = o - orow[q] * kDsCols;
+        oval[q] = live && orow[q] < nrows && ocol[q] < ncols;
+    }
+    unsigned bar_target = 0;
+
+    // generator slice for interval n of direction dir with coefficients cf[]  (build_G_kernel's arithmetic)
+    auto build_G = [&](const int dir, const double (&cf)[kMaxL]) {
+        const double sc = 4.0 / p.Delta[dir][g], beta = p.Delta[dir][g] / 2 + p.E_min[dir][g];
+        const double2 f = (dir == KROTOV_FORWARD) ? make_double2(0.0, -sc) : make_double2(0.0, sc);
+        const double2 *H = p.H[dir] + (size_t)g * (1 + p.L) * mat;
+        for (int i = tid; i < nrows * d; i += kDsThreads) {
+            const int r = i / d, k = i - r * d;
+            const size_t src = (size_t)(row0 + r) * p.dp + k;
+            double2 h = H[src];
+            if (row0 + r == k) h.x -= beta;
+            for (int l = 0; l < p.L; ++l) {
+                const double2 hl = H[(size_t)(l + 1) * mat + src];
+                h.x = fma(cf[l], hl.x, h.x);
+                h.y = fma(cf[l], hl.y, h.y);
+            }
+            gs[(size_t)r * gpad + k] = make_double2(f.x * h.x - f.y * h.y, f.x * h.y + f.y * h.x);
+        }
+        __syncthreads();
+    };
+
+    // one propagation step of the cluster's column group: PSI <- exp(-/+ i H dt) PSI, result also into `store`
+    auto step = [&](const int dir, const int n, double2 *store) {
+        const int ci = g * p.ndtc[dir] + p.dtc[dir][n];
+        const int m = live ? p.m[dir][ci] : 0;
+        const double2 ph = p.phase[dir][ci];
+        const double *a = p.coef[dir] + (size_t)ci * p.mmax[dir];
+        const double a0 = a[0];
+        double2 vm1[kDsMaxOut], vm2[kDsMaxOut], out[kDsMaxOut];
+        if (live) ds_load_group(vs, p.PSI, d, p.ld, col0, ncols);
+#pragma unroll
+        for (int q = 0; q < kDsMaxOut; ++q) {
+            vm1[q] = oval[q] ? vs[(size_t)(row0 + orow[q]) * kDsCols + ocol[q]] : make_double2(0.0, 0.0);
+            vm2[q] = make_double2(0.0, 0.0);
+            out[q] = make_double2(a0 * vm1[q].x, a0 * vm1[q].y);
+        }
+        for (int j = 1; j < m; ++j) {
+            const double aj = a[j];
+            const bool last = (j == m - 1);
+            double2 *vx = p.VX[j & 1];
+#pragma unroll
+            for (int q = 0; q < kDsMaxOut; ++q) {
+                if (!oval[q]) continue;
+                double cr, ci_;
+                ds_dot(gs + (size_t)orow[q] * gpad, vs + ocol[q], d, cr, ci_);
+                double2 v;
+                if (j == 1)
+                    v = make_double2(0.5 * cr, 0.5 * ci_);
+                else
+                    v = make_double2(cr + vm2[q].x, ci_ + vm2[q].y);
+                out[q] = make_double2(fma(aj, v.x, out[q].x), fma(aj, v.y, out[q].y));
+                vm2[q] = vm1[q];
+                vm1[q] = v;
+                const size_t idx = (size_t)(row0 + orow[q]) * p.ld + col0 + ocol[q];
+                if (last) {
+                    const double2 r = make_double2(ph.x * out[q].x - ph.y * out[q].y, ph.x * out[q].y + ph.y * out[q].x);
+                    p.PSI[idx] = r;
+                    if (store) store[idx] = r;
+                } else {
+                    vx[idx] = v;
+                }
+            }
+            if (!last) {
+                ds_cluster_sync();  // every row slice of V_j is in L2
+                ds_load_group(vs, vx, d, p.ld, col0, ncols);
+            }
+        }
+        ds_cluster_sync();  // PSI of the column group is complete (the next step, or the overlaps, read all rows)
+    };
+
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + tid, gthreads = (size_t)gridDim.x * blockDim.x;
+    double cf[kMaxL];
+#pragma unroll
+    for (int l = 0; l < kMaxL; ++l) cf[l] = 0.0;
+
+    if (p.mode == 1) {
+        // ---- backward sweep: chi(t_n) for all n into X  (src/optimize.jl:303-317)
+        for (size_t i = gtid; i < p.slab; i += gthreads) {
+            const double2 v = p.CHI[i];
+            p.PSI[i] = v;
+            p.X[p.slab * (size_t)p.N_T + i] = v;
+        }
+        ds_grid_barrier(p.bar, bar_target);
+        for (int n = p.N_T - 1; n >= 0; --n) {
+            for (int l = 0; l < p.L; ++l) cf[l] = p.amp_old[(size_t)l * p.N_T + n];
+            if (live) build_G(KROTOV_BACKWARD, cf);
+            step(KROTOV_BACKWARD, n, p.X + p.slab * (size_t)n);
+        }
+        ds_grid_barrier(p.bar, bar_target);
+    }
+    // ---- forward sweep
+    for (size_t i = gtid; i < p.slab; i += gthreads) {
+        const double2 v = p.PSI0[i];
+        p.PSI[i] = v;
+        if (p.store_fw && p.mode == 0) p.PHI[i] = v;
+    }
+    ds_grid_barrier(p.bar, bar_target);
+    for (int n = 0; n < p.N_T; ++n) {
+        if (p.mode == 1) {
+            // overlaps Im <chi_k(t_n)| mu_l |psi_k(t_n)> of this CTA's rows and columns  (:339-349)
+            const double2 *CHI = p.X + p.slab * (size_t)n;
+            if (live) ds_load_group(vs, p.PSI, d, p.ld, col0, ncols);
+            for (int l = 0; l < p.L; ++l) {
+                double acc = 0.0;
+                if (live) {
+                    const double2 *Hl = p.H[0] + ((size_t)g * (1 + p.L) + 1 + l) * mat;
+                    for (int i = tid; i < nrows * d; i += kDsThreads) {  // stage the slice of H_l where G will be rebuilt
+                        const int r = i / d, k = i - r * d;
+                        gs[(size_t)r * gpad + k] = Hl[(size_t)(row0 + r) * p.dp + k];
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int q = 0; q < kDsMaxOut; ++q) {
+                        if (!oval[q]) continue;
+                        double cr, ci_;
+                        ds_dot(gs + (size_t)orow[q] * gpad, vs + ocol[q], d, cr, ci_);
+                        const double2 ch = CHI[(size_t)(row0 + orow[q]) * p.ld + col0 + ocol[q]];
+                        acc += ch.x * ci_ - ch.y * cr;
+                    }
+                    __syncthreads();
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0) wsum[l][warp] = acc;
+            }
+            __syncthreads();
+            if (tid < p.L) {
+                double t = 0.0;
+                for (int w = 0; w < kDsThreads / 32; ++w) t += wsum[tid][w];
+                p.partial[(size_t)tid * gridDim.x + blockIdx.x] = t;
+            }
+            ds_grid_barrier(p.bar, bar_target);
+            // every CTA adds the CTA partials in the same fixed order: the same bits everywhere, no broadcast
+            if (warp == 0) {
+                for (int l = 0; l < p.L; ++l) {
+                    double sacc = 0.0;
+                    for (int c = lane; c < (int)gridDim.x; c += 32) sacc += __ldcg(p.partial + (size_t)l * gridDim.x + c);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+                    if (lane == 0) {
+                        const double al = p.alpha[(size_t)l * p.N_T + n];
+                        if (p.am.dfac != nullptr) sacc = __dmul_rn(p.am.dfac[(size_t)l * p.N_T + n], sacc);
+                        const double e_new = __dadd_rn(p.eps_old[(size_t)l * p.N_T + n], __dmul_rn(al, sacc));  // :355-356
+                        eps_sh[l] = amp_apply(p.am, l, p.N_T, n, e_new);
+                        if (blockIdx.x == 0) {
+                            p.eps_new[(size_t)l * p.N_T + n] = e_new;
+                            const double prev = (n == 0) ? 0.0 : p.ga[l];
+                            p.ga[l] = __dadd_rn(prev, __dmul_rn(__dmul_rn(al, __dmul_rn(fabs(sacc), fabs(sacc))), p.dt[n]));  // :357
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            for (int l = 0; l < p.L; ++l) cf[l] = eps_sh[l];
+            __syncthreads();
+        } else {
+            for (int l = 0; l < p.L; ++l) cf[l] = p.amp_old[(size_t)l * p.N_T + n];
+        }
+        double2 *store = nullptr;
+        if (p.store_fw) store = p.PHI + p.slab * (size_t)(p.mode == 1 ? n : n + 1);  // slot n in an iteration (sic, :367)
+        if (live) build_G(KROTOV_FORWARD, cf);
+        step(KROTOV_FORWARD, n, store);
+    }
+}
+
+}  // namespace
+}  // namespace kr

@@ -755,6 +755,19 @@ static __device__ __noinline__ void exchange_gather(const WarpParams *pp, const 
     for (int l = 0; l < kMaxCtrl; ++l) tot_io[l] = tot[l];
 }
 
+// a_l(e, n) = shape * sum_p poly[l][p] e^p  (non-linear amplitudes only; kept out of the comm warp's loop body)
+static __device__ __noinline__ double amp_eval_cold(const WarpParams *pp, const int l, const double e, const double shp) {
+    double c = e;
+    if (pp->amp_poly != nullptr) {
+        const double *q = pp->amp_poly + l * (kAmpMaxDeg + 1);
+        c = q[kAmpMaxDeg];
+#pragma unroll
+        for (int d = kAmpMaxDeg - 1; d >= 0; --d) c = fma(c, e, q[d]);
+    }
+    if (pp->amp_shape != nullptr) c = __dmul_rn(shp, c);
+    return c;
+}
+
 // The communication warp of a CTA (shared by both kernel variants): per time step it waits for the CTA's
 // per-lane partial overlaps (named barrier 1), reduces them in a fixed order, runs the grid / rank exchange,
 // applies the pulse update (src/optimize.jl:351-358) and releases the trajectory warps (named barrier 2).
@@ -773,15 +786,20 @@ __device__ __forceinline__ void comm_warp_run(const WarpParams &p, const int cta
         __syncwarp();
     }
     double ga = 0.0;  // lane l accumulates g_a_int[l]  (CTA 0 writes it)
+    const bool nonlin = p.amp_dfac != nullptr;  // non-linear control amplitudes (rare): handled out of line
     long long c_wait_a = 0, c_reduce = 0, c_gather = 0;
     for (int n = 0; n < N_T; ++n) {
-        double a_ln = 0.0, e_old = 0.0, dtn = 0.0, dfac = 1.0, shp = 1.0;
+        double a_ln = 0.0, e_old = 0.0, dtn = 0.0, dfac = 1.0, shp = 1.0, a_eff = 0.0;
         if (lane < L) {
             a_ln = p.alpha[(size_t)lane * N_T + n];
             e_old = p.eps_old[(size_t)lane * N_T + n];
             dtn = p.dt[n];
-            if (p.amp_dfac != nullptr) dfac = p.amp_dfac[(size_t)lane * N_T + n];
-            if (p.amp_shape != nullptr) shp = p.amp_shape[(size_t)lane * N_T + n];
+            a_eff = a_ln;
+            if (nonlin) {  // fetched and folded BEFORE the barrier: nothing of it sits behind the exchange
+                dfac = p.amp_dfac[(size_t)lane * N_T + n];
+                if (p.amp_shape != nullptr) shp = p.amp_shape[(size_t)lane * N_T + n];
+                a_eff = __dmul_rn(a_ln, dfac);
+            }
         }
         const long long c0 = clock64();
         bar_sync(1, nthr_all);  // barrier A: partials are in `red`
@@ -830,25 +848,20 @@ __device__ __forceinline__ void comm_warp_run(const WarpParams &p, const int cta
 #pragma unroll
         for (int l = 0; l < kMaxCtrl; ++l)
             if (lane == l) mine = tot[l];
+        double e_new = 0.0;
         if (lane < L) {
-            if (p.amp_dfac != nullptr) mine = __dmul_rn(dfac, mine);  // mu_l = a_l'(eps^(i)_l[n]) H_l  (:337-346)
-            const double d_eps = __dmul_rn(a_ln, mine);      // src/optimize.jl:355
-            const double e_new = __dadd_rn(e_old, d_eps);    // :356
+            const double d_eps = __dmul_rn(a_eff, mine);     // src/optimize.jl:355 (a_eff = alpha, or alpha a_l' when non-linear)
+            e_new = __dadd_rn(e_old, d_eps);                 // :356
             double c_new = e_new;                            // coefficient of H_l in the forward step
-            if (p.amp_poly != nullptr) {
-                const double *q = p.amp_poly + lane * (kAmpMaxDeg + 1);
-                c_new = q[kAmpMaxDeg];
-#pragma unroll
-                for (int d = kAmpMaxDeg - 1; d >= 0; --d) c_new = fma(c_new, e_new, q[d]);
-            }
-            if (p.amp_shape != nullptr) c_new = __dmul_rn(shp, c_new);
+            if (nonlin) c_new = amp_eval_cold(p_sh, lane, e_new, shp);
             eps_s[lane] = c_new;
-            if (cta == 0) {
-                p.eps_new[(size_t)lane * N_T + n] = e_new;
-                ga = __dadd_rn(ga, __dmul_rn(__dmul_rn(a_ln, __dmul_rn(fabs(mine), fabs(mine))), dtn));  // :357
-            }
         }
         bar_arrive(2, nthr_all);  // barrier B: eps_s is valid
+        if (cta == 0 && lane < L) {  // bookkeeping, off the critical path
+            p.eps_new[(size_t)lane * N_T + n] = e_new;
+            const double du = nonlin ? __dmul_rn(dfac, mine) : mine;  // mu_l = a_l'(eps^(i)_l[n]) H_l  (:337-346)
+            ga = __dadd_rn(ga, __dmul_rn(__dmul_rn(a_ln, __dmul_rn(fabs(du), fabs(du))), dtn));  // :357
+        }
     }
     if (cta == 0 && lane < L) p.g_a_int[lane] = ga;
     if (p.prof != nullptr && lane == 0) {

@@ -1127,7 +1127,7 @@ def test_nonlinear_amplitudes_block_paths(kind, monkeypatch):
         if kind == "sparse_stream":
             monkeypatch.setenv("KROTOV_NO_SWEEP", "1")
         w = _nonlinear(W.spin_chain(n_spins=6, n_traj=8, n_grid=31), 4.0)
-    got = run_product(w, 2)
+    got = run_product(w, 2, **({"force_path": 3} if kind.startswith("sparse") else {}))
     assert got["info"]["path"] == {"dense": 2, "reloaded_rows": 1}.get(kind, 3)
     ref = O.optimize_krotov(W.to_oracle(w), 2)
     assert_parity(got, ref["J_T"], ref["pulses"], ref["g_a_int"], rtol=1e-10, atol=5e-13)
@@ -1146,3 +1146,40 @@ def test_amplitude_argument_errors():
     with pytest.raises(K.ArgumentError):
         K.optimize(K.ControlProblem(trajs, w.tlist, prop_method=K.Cheby, J_T=K.J_T_sm, lambda_a=1.0, iter_stop=1,
                                     print_iters=False, rethrow_exceptions=True), method=K.Krotov)
+
+
+# ---- persistent cluster sweep for moderate dense generators (dense_sweep.cuh) -------------------------------------------
+@pytest.mark.parametrize("d,n_traj,L,functional,hermitian,n_gen", [
+    (40, 6, 2, "ss", True, 1), (100, 20, 1, "sm", True, 1), (100, 64, 2, "re", True, 1), (200, 64, 2, "ss", True, 1),
+    (33, 9, 3, "sm", False, 1), (72, 13, 2, "ss", True, 3), (288, 8, 1, "ss", True, 1)])
+def test_dense_cluster_sweep_equals_launch_stream_and_oracle(d, n_traj, L, functional, hermitian, n_gen, monkeypatch):
+    """Dense generators with 32 < d <= 288: the whole iteration in ONE cooperative launch of 8-CTA clusters (generator
+    slices in shared memory, one cluster barrier per Chebyshev term) against the launch-per-term DMMA stream
+    (KROTOV_NO_DSWEEP=1) -- same state blocks and storage, agreement at rounding -- and against the oracle."""
+    from oracle import krotov_oracle as O
+
+    w = W.dummy_dense(d=d, n_traj=n_traj, n_controls=L, functional=functional, n_grid=21, seed=d + L, hermitian=hermitian)
+    if n_gen > 1:  # an ensemble: several generators with their own spectral radius (different coefficient counts)
+        w.H0 = [w.H0[0] * (1.0 + 0.3 * g) for g in range(n_gen)]
+        w.Hc = [w.Hc[0] for _ in range(n_gen)]
+        w.gen_of_traj = np.arange(n_traj) % n_gen
+    seen = {}
+
+    def cb(wrk, it, eps_new, eps_old):
+        if it == 1:
+            seen["X"] = wrk.bw_storage[n_traj - 1].copy()
+            seen["Phi"] = wrk.fw_storage[0].copy()
+
+    sweep = run_product(w, 2, store_fw_states=True, callback=cb)
+    assert sweep["info"]["path"] == 2 and sweep["info"]["launches_last"] <= 4 and sweep["info"]["block_threads"] == 256
+    Xs, Ps = seen["X"], seen["Phi"]
+    monkeypatch.setenv("KROTOV_NO_DSWEEP", "1")
+    stream = run_product(w, 2, store_fw_states=True, callback=cb)
+    assert stream["info"]["launches_last"] > 50
+    assert np.abs(np.array(sweep["J_T"]) - np.array(stream["J_T"])).max() < 1e-13
+    assert np.abs(sweep["pulses"] - stream["pulses"]).max() < 1e-13
+    assert np.abs(Xs - seen["X"]).max() < 1e-13 and np.abs(Ps - seen["Phi"]).max() < 1e-13
+    assert np.abs(np.array(sweep["result"].states) - np.array(stream["result"].states)).max() < 1e-13
+    if d <= 100:
+        ref = O.optimize_krotov(W.to_oracle(w), 2)
+        assert_parity(sweep, ref["J_T"], ref["pulses"], ref["g_a_int"], rtol=1e-10, atol=5e-13)
