@@ -1150,6 +1150,26 @@ bool dsweep_configure(DenseEngine *e) {
         cudaGetLastError();
         return true;
     }
+    {   // all clusters must be co-resident (they meet at a grid barrier): ask how many this device can hold
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(n_units * kDsCluster);
+        cfg.blockDim = dim3(kDsThreads);
+        cfg.dynamicSmemBytes = e->ds_smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = kDsCluster;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        int max_clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&max_clusters, dense_cluster_sweep_kernel, &cfg) != cudaSuccess ||
+            max_clusters < n_units) {
+            cudaGetLastError();
+            return true;
+        }
+    }
     std::string err;
     if (!dalloc(e->ds_units_dev, units.size(), err) || !dalloc(e->sw_partial, (size_t)kMaxL * n_units * kDsCluster, err) ||
         !dalloc(e->sw_bar, 1, err))
