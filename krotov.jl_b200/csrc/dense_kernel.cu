@@ -385,6 +385,35 @@ __device__ __forceinline__ double amp_apply(const AmpDev &am, const int l, const
     return c;
 }
 
+// The rank's sum `s` of control l at time step n -> the sum over all ranks, the same bits on every rank: the rank sum is
+// pushed into slot [rank] of every rank's mailbox (system-scope stores over NVLink, by the caller flagged `push` only)
+// and the `world` slots of the own mailbox are polled and added in rank order.  Called by ONE lane; every CTA of the
+// persistent sweeps calls it (they all need the total), the pushing is done by CTA 0.
+__device__ __forceinline__ double rank_sum_lane(const DenseComm &cm, const int L, const int n, const int l, const double s,
+                                                const bool push) {
+    if (cm.world <= 1) return s;
+    const size_t off = ((size_t)n * L + l) * cm.world;
+    if (push)
+        for (int r = 0; r < cm.world; ++r)
+            asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(cm.mbox[r] + off + cm.rank), "d"(s) : "memory");
+    double tot = 0.0;
+    const long long t0 = clock64();
+    for (int r = 0; r < cm.world; ++r) {
+        unsigned long long u;
+        int spins = 0;
+        for (;;) {
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(u) : "l"(cm.mbox[cm.rank] + off + r) : "memory");
+            if (u != 0xFFFFFFFFFFFFFFFFull) break;
+            if ((++spins & 63) == 0 && (clock64() - t0 > cm.timeout_cycles || *(volatile int *)cm.err_flag)) {
+                atomicExch(cm.err_flag, 1);
+                break;
+            }
+        }
+        tot += __longlong_as_double((long long)u);
+    }
+    return tot;
+}
+
 // fixed-order sum of the CTA partials of every control, rank exchange, pulse update (src/optimize.jl:351-358).
 // With several ranks the rank sum is pushed into every peer's mailbox (system-scope stores over NVLink) and
 // the `world` slots are summed in rank order -- the same protocol as the warp path's reducer.
@@ -629,6 +658,7 @@ struct SweepParams {
     double *partial;           // [L][gridDim.x]
     const double *amp_old;     // a(eps_old): coefficients of the generator under the known pulses (== eps_old when linear)
     AmpDev am;
+    DenseComm cm;              // several ranks: mailboxes of this iteration's parity
 };
 
 struct SweepItem {
@@ -898,6 +928,7 @@ __global__ void __launch_bounds__(SP_WARPS * 32, 2) sparse_sweep_kernel(const __
                     for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
                     if (lane == 0) {
                         const double a = p.alpha[(size_t)l * p.N_T + n];
+                        sacc = rank_sum_lane(p.cm, p.L, n, l, sacc, blockIdx.x == 0);
                         if (p.am.dfac != nullptr) sacc = __dmul_rn(p.am.dfac[(size_t)l * p.N_T + n], sacc);
                         const double e_new = __dadd_rn(p.eps_old[(size_t)l * p.N_T + n], __dmul_rn(a, sacc));  // :355-356
                         eps_sh[l] = amp_apply(p.am, l, p.N_T, n, e_new);
@@ -1142,9 +1173,9 @@ bool dsweep_configure(DenseEngine *e) {
     const int n_units = (int)units.size() / 3;
     if (n_units == 0 || n_units * kDsCluster > e->sm_count) return true;  // all clusters must be co-resident
     e->ds_R = (e->d + kDsCluster - 1) / kDsCluster;
-    e->ds_gpad = e->d | 1;
-    e->ds_smem = ((size_t)e->ds_R * e->ds_gpad + (size_t)e->d * kDsCols) * 16;
-    if (e->ds_R * kDsCols > kDsMaxOut * kDsThreads || e->ds_smem > 220 * 1024) return true;
+    e->ds_gpad = ds_stride(e->d);
+    e->ds_smem = ((size_t)((e->ds_R + 7) / 8 * 8) * e->ds_gpad + (size_t)kDsCols * e->ds_gpad) * 16;
+    if (e->ds_R > 8 * (kDsThreads / 32) || e->ds_smem > 220 * 1024) return true;
     if (cudaFuncSetAttribute((const void *)dense_cluster_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)e->ds_smem) != cudaSuccess) {
         cudaGetLastError();
@@ -1196,7 +1227,7 @@ bool launch_dsweep(DenseEngine *e, int mode, const double *d_eps_old, double *d_
     p.PSI = e->PSI; p.X = e->X; p.PHI = e->PHI; p.VX[0] = e->V[0]; p.VX[1] = e->V[1];
     p.PSI0 = e->PSI0; p.CHI = e->CHI; p.slab = e->slab;
     p.eps_old = d_eps_old; p.eps_new = d_eps_new; p.alpha = d_alpha; p.dt = d_dt; p.ga = d_ga;
-    p.amp_old = gen_coeffs_old(e, d_eps_old); p.am = e->amp;
+    p.amp_old = gen_coeffs_old(e, d_eps_old); p.am = e->amp; p.cm = e->comm;
     p.partial = e->sw_partial;
     p.bar = e->sw_bar;
     DK_CHECK(cudaMemsetAsync(e->sw_bar, 0, sizeof(unsigned), e->stream));
@@ -1228,7 +1259,10 @@ inline const double *gen_coeffs_old(const DenseEngine *e, const double *d_eps) {
 inline const double *gen_coeffs_new(const DenseEngine *e, const double *d_eps_new) { return e->amp.amp_new ? e->amp.amp_new : d_eps_new; }
 
 bool sweep_usable(const DenseEngine *e, int mode) {
-    return (e->sweep || e->dsweep) && e->comm.world <= 1 && e->ch[0].set && (mode == 0 || e->ch[1].set) && !getenv("KROTOV_NO_SWEEP");
+    // (several ranks: the per-step sums of the sweeps cross the ranks through the mailboxes, rank_sum_lane;
+    // KROTOV_NO_SWEEP_RANKS=1 keeps the launch-per-term stream there)
+    if (e->comm.world > 1 && getenv("KROTOV_NO_SWEEP_RANKS")) return false;
+    return (e->sweep || e->dsweep) && e->ch[0].set && (mode == 0 || e->ch[1].set) && !getenv("KROTOV_NO_SWEEP");
 }
 
 template <typename T>
@@ -1259,7 +1293,7 @@ bool launch_sweep(DenseEngine *e, int mode, const double *d_eps_old, double *d_e
     p.PSI = e->PSI; p.V[0] = e->V[0]; p.V[1] = e->V[1]; p.V[2] = e->V[2]; p.OUT = e->OUT; p.X = e->X; p.PHI = e->PHI;
     p.PSI0 = e->PSI0; p.CHI = e->CHI; p.slab = e->slab;
     p.eps_old = d_eps_old; p.eps_new = d_eps_new; p.alpha = d_alpha; p.dt = d_dt; p.ga = d_ga;
-    p.amp_old = gen_coeffs_old(e, d_eps_old); p.am = e->amp;
+    p.amp_old = gen_coeffs_old(e, d_eps_old); p.am = e->amp; p.cm = e->comm;
     p.partial = e->sw_partial;
     p.cg_sync = getenv("KROTOV_SWEEP_CGSYNC") ? 1 : 0;
     p.bar = e->sw_bar;

@@ -6,9 +6,12 @@
 // a group of <= 8 trajectories (columns of the state block) of one generator:
 //   * CTA r of the cluster owns rows [r R, (r+1) R) of the generator, R = ceil(d / 8); its slice of
 //     G = 2c (H_0 - beta + sum_l a_l H_l) is rebuilt in SHARED memory once per time step from the term slices in L2;
-//   * every CTA holds the full V_{j-1} of its column group in shared memory (d x 8 complex); thread (row, column)
-//     forms one element of V_j = G V_{j-1} + V_{j-2}: a dot product of a shared-memory row of G (broadcast to the 8
-//     column threads) with a column of V_{j-1}; V_{j-2}, the running sum and the own element stay in registers;
+//   * every CTA holds the full V_{j-1} of its column group in shared memory (8 x d complex, transposed); warp w forms
+//     the 8 rows x 8 columns tile w of V_j = G V_{j-1} + V_{j-2} on the FP64 tensor pipe: per 4 values of k one
+//     16-byte fragment load of G and one of V feed four `mma.sync.m8n8k4.f64` (DMMA: Gr Vr, -Gi Vi, Gr Vi, Gi Vr).
+//     (A first version formed one element per thread with DFMA: two 16-byte shared-memory loads per 4 FMA made it
+//     crossbar-bound at 45 / 95 us per step and direction for d = 100 / 200 -- the fragment form moves 1/8 of that.)
+//     V_{j-2}, the running sum and the own elements stay in registers;
 //   * the new rows go to a ping-pong exchange block in L2, ONE cluster barrier (barrier.cluster, ~380 cycles) orders
 //     them, and every CTA of the cluster reloads the full column group -- the column groups never talk to each other
 //     inside a time step;
@@ -25,14 +28,16 @@ namespace {
 constexpr int kDsCluster = 8;    // CTAs per cluster = row slices of the generator
 constexpr int kDsCols = 8;       // trajectories (columns) per cluster
 constexpr int kDsThreads = 256;
-constexpr int kDsMaxD = 288;     // R * (d|1) * 16 B (generator slice) + d * 8 * 16 B (column group) must fit 227 KB
-constexpr int kDsMaxOut = 2;     // outputs per thread: ceil(R * 8 / 256)
+constexpr int kDsMaxD = 256;     // 8 warps x 8 rows per CTA = 64 rows per slice; slice + column group must fit 227 KB
+// shared-memory row stride (in 16-byte words) for k-extent d: >= d rounded up to 4, and = 4 (mod 8) so that the 8 lanes
+// of a quarter-warp (2 rows x 4 consecutive k) of a fragment load hit 8 different 16-byte bank groups
+__host__ __device__ constexpr int ds_stride(int d) { return ((d + 3) / 4 * 4 + 7) / 8 * 8 + 4; }
 
 struct DSweepParams {
     int d, dp, ld, L, N_T, mode, store_fw;
     int n_units;               // clusters that carry work; unit u = (generator, first column, columns)
     int R;                     // rows per CTA
-    int gpad;                  // row stride of the generator slice in shared memory (odd: conflict-free across rows)
+    int gpad;                  // row stride of the generator slice and of the transposed column group in shared memory
     const int *units;          // [n_units][3]
     const double2 *H[2];       // per direction: [g][1+L][dp][dp] row-major dense terms
     const double *coef[2];
@@ -49,6 +54,7 @@ struct DSweepParams {
     double *partial;           // [L][gridDim.x]
     unsigned *bar;
     AmpDev am;
+    DenseComm cm;              // several ranks: mailboxes of this iteration's parity
 };
 
 __device__ __forceinline__ unsigned ds_cluster_rank() {
@@ -73,28 +79,28 @@ __device__ __forceinline__ void ds_grid_barrier(unsigned *bar, unsigned &target)
     __syncthreads();
 }
 
-// acc = row . column  (complex): `grow` a shared-memory row of the generator slice, `vcol` the column of the group
-__device__ __forceinline__ void ds_dot(const double2 *__restrict__ grow, const double2 *__restrict__ vcol, const int d,
-                                       double &cr, double &ci) {
-    double ar = 0.0, ai = 0.0, ar1 = 0.0, ai1 = 0.0;
+// C(8 x 8 tile) = A(8 rows of the slice) . V(column group), complex, on the FP64 tensor pipe.  `ga` -> this lane's row of the
+// A fragment (row gid of the tile, k offset tig), `vb` -> this lane's column of the transposed group (column gid, k offset
+// tig).  On return the lane holds C[gid][2 tig] = (cr0, ci0) and C[gid][2 tig + 1] = (cr1, ci1).
+__device__ __forceinline__ void ds_tile(const double2 *__restrict__ ga, const double2 *__restrict__ vb, const int d4,
+                                        double &cr0, double &cr1, double &ci0, double &ci1) {
+    cr0 = cr1 = ci0 = ci1 = 0.0;
 #pragma unroll 4
-    for (int k = 0; k < d; ++k) {
-        const double2 g = grow[k], x = vcol[(size_t)k * kDsCols];
-        ar = fma(g.x, x.x, ar);
-        ar1 = fma(-g.y, x.y, ar1);
-        ai = fma(g.x, x.y, ai);
-        ai1 = fma(g.y, x.x, ai1);
+    for (int k = 0; k < d4; k += 4) {
+        const double2 a = ga[k], b = vb[k];
+        dmma(cr0, cr1, a.x, b.x);
+        dmma(cr0, cr1, -a.y, b.y);
+        dmma(ci0, ci1, a.x, b.y);
+        dmma(ci0, ci1, a.y, b.x);
     }
-    cr = ar + ar1;
-    ci = ai + ai1;
 }
 
-// shared memory <- the column group of a state block in global memory (d x ncols; missing columns zero)
-__device__ __forceinline__ void ds_load_group(double2 *vs, const double2 *src, const int d, const int ld, const int col0,
-                                              const int ncols) {
-    for (int i = threadIdx.x; i < d * kDsCols; i += kDsThreads) {
+// shared memory (transposed, [column][k], zero padded) <- the column group of a state block in global memory
+__device__ __forceinline__ void ds_load_group(double2 *vt, const double2 *src, const int d, const int d4, const int vpad,
+                                              const int ld, const int col0, const int ncols) {
+    for (int i = threadIdx.x; i < d4 * kDsCols; i += kDsThreads) {
         const int k = i / kDsCols, c = i - k * kDsCols;
-        vs[i] = (c < ncols) ? __ldcg(src + (size_t)k * ld + col0 + c) : make_double2(0.0, 0.0);
+        vt[(size_t)c * vpad + k] = (c < ncols && k < d) ? __ldcg(src + (size_t)k * ld + col0 + c) : make_double2(0.0, 0.0);
     }
     __syncthreads();
 }
@@ -108,21 +114,26 @@ __global__ void __launch_bounds__(kDsThreads, 1) dense_cluster_sweep_kernel(cons
     const int unit = blockIdx.x / kDsCluster;
     const bool live = unit < p.n_units;
     const int g = live ? p.units[unit * 3] : 0, col0 = live ? p.units[unit * 3 + 1] : 0, ncols = live ? p.units[unit * 3 + 2] : 0;
-    const int d = p.d, R = p.R, gpad = p.gpad;
+    const int d = p.d, R = p.R, gpad = p.gpad, d4 = (d + 3) / 4 * 4, R8 = (R + 7) / 8 * 8;
     const int row0 = crank * R, nrows = max(0, min(R, d - row0));
-    double2 *gs = reinterpret_cast<double2 *>(ds_smem);  // [R][gpad] generator slice (also stages the H_l slices)
-    double2 *vs = gs + (size_t)R * gpad;                 // [d][8] V_{j-1} of the column group
+    double2 *gs = reinterpret_cast<double2 *>(ds_smem);  // [R8][gpad] generator slice (also stages the H_l slices)
+    double2 *vs = gs + (size_t)R8 * gpad;                // [8][gpad] V_{j-1} of the column group, transposed
     const size_t mat = (size_t)p.dp * p.dp;
-    // this thread's outputs: o = tid + q * 256 -> (row o / 8, column o % 8)
+    // warp w owns the 8 x 8 output tile of slice rows [8 w, 8 w + 8); DMMA accumulator layout: lane (gid, tig) holds
+    // row gid, columns 2 tig and 2 tig + 1
+    constexpr int kDsMaxOut = 2;
+    const int gid = lane >> 2, tig = lane & 3;
+    const bool tile_live = live && warp * 8 < nrows;
     int orow[kDsMaxOut], ocol[kDsMaxOut];
     bool oval[kDsMaxOut];
 #pragma unroll
     for (int q = 0; q < kDsMaxOut; ++q) {
-        const int o = tid + q * kDsThreads;
-        orow[q] = o / kDsCols;
-        ocol[q] = o - orow[q] * kDsCols;
+        orow[q] = warp * 8 + gid;
+        ocol[q] = 2 * tig + q;
         oval[q] = live && orow[q] < nrows && ocol[q] < ncols;
     }
+    const double2 *ga = gs + (size_t)(warp * 8 + gid) * gpad + tig;  // A fragment: row gid of the tile, k offset tig
+    const double2 *vb = vs + (size_t)gid * gpad + tig;               // B fragment: column gid, k offset tig
     unsigned bar_target = 0;
 
     // generator slice for interval n of direction dir with coefficients cf[]  (build_G_kernel's arithmetic)
@@ -130,17 +141,21 @@ __global__ void __launch_bounds__(kDsThreads, 1) dense_cluster_sweep_kernel(cons
         const double sc = 4.0 / p.Delta[dir][g], beta = p.Delta[dir][g] / 2 + p.E_min[dir][g];
         const double2 f = (dir == KROTOV_FORWARD) ? make_double2(0.0, -sc) : make_double2(0.0, sc);
         const double2 *H = p.H[dir] + (size_t)g * (1 + p.L) * mat;
-        for (int i = tid; i < nrows * d; i += kDsThreads) {
-            const int r = i / d, k = i - r * d;
-            const size_t src = (size_t)(row0 + r) * p.dp + k;
-            double2 h = H[src];
-            if (row0 + r == k) h.x -= beta;
-            for (int l = 0; l < p.L; ++l) {
-                const double2 hl = H[(size_t)(l + 1) * mat + src];
-                h.x = fma(cf[l], hl.x, h.x);
-                h.y = fma(cf[l], hl.y, h.y);
+        for (int i = tid; i < R8 * d4; i += kDsThreads) {
+            const int r = i / d4, k = i - r * d4;
+            double2 out = make_double2(0.0, 0.0);  // rows / columns beyond the slice: zero padding of the fragments
+            if (r < nrows && k < d) {
+                const size_t src = (size_t)(row0 + r) * p.dp + k;
+                double2 h = H[src];
+                if (row0 + r == k) h.x -= beta;
+                for (int l = 0; l < p.L; ++l) {
+                    const double2 hl = H[(size_t)(l + 1) * mat + src];
+                    h.x = fma(cf[l], hl.x, h.x);
+                    h.y = fma(cf[l], hl.y, h.y);
+                }
+                out = make_double2(f.x * h.x - f.y * h.y, f.x * h.y + f.y * h.x);
             }
-            gs[(size_t)r * gpad + k] = make_double2(f.x * h.x - f.y * h.y, f.x * h.y + f.y * h.x);
+            gs[(size_t)r * gpad + k] = out;
         }
         __syncthreads();
     };
@@ -153,10 +168,10 @@ __global__ void __launch_bounds__(kDsThreads, 1) dense_cluster_sweep_kernel(cons
         const double *a = p.coef[dir] + (size_t)ci * p.mmax[dir];
         const double a0 = a[0];
         double2 vm1[kDsMaxOut], vm2[kDsMaxOut], out[kDsMaxOut];
-        if (live) ds_load_group(vs, p.PSI, d, p.ld, col0, ncols);
+        if (live) ds_load_group(vs, p.PSI, d, d4, gpad, p.ld, col0, ncols);
 #pragma unroll
         for (int q = 0; q < kDsMaxOut; ++q) {
-            vm1[q] = oval[q] ? vs[(size_t)(row0 + orow[q]) * kDsCols + ocol[q]] : make_double2(0.0, 0.0);
+            vm1[q] = oval[q] ? vs[(size_t)ocol[q] * gpad + row0 + orow[q]] : make_double2(0.0, 0.0);
             vm2[q] = make_double2(0.0, 0.0);
             out[q] = make_double2(a0 * vm1[q].x, a0 * vm1[q].y);
         }
@@ -164,11 +179,12 @@ __global__ void __launch_bounds__(kDsThreads, 1) dense_cluster_sweep_kernel(cons
             const double aj = a[j];
             const bool last = (j == m - 1);
             double2 *vx = p.VX[j & 1];
+            double tr[kDsMaxOut] = {0.0, 0.0}, ti[kDsMaxOut] = {0.0, 0.0};
+            if (tile_live) ds_tile(ga, vb, d4, tr[0], tr[1], ti[0], ti[1]);  // warp-uniform: mma.sync needs the whole warp
 #pragma unroll
             for (int q = 0; q < kDsMaxOut; ++q) {
                 if (!oval[q]) continue;
-                double cr, ci_;
-                ds_dot(gs + (size_t)orow[q] * gpad, vs + ocol[q], d, cr, ci_);
+                const double cr = tr[q], ci_ = ti[q];
                 double2 v;
                 if (j == 1)
                     v = make_double2(0.5 * cr, 0.5 * ci_);
@@ -188,7 +204,7 @@ __global__ void __launch_bounds__(kDsThreads, 1) dense_cluster_sweep_kernel(cons
             }
             if (!last) {
                 ds_cluster_sync();  // every row slice of V_j is in L2
-                ds_load_group(vs, vx, d, p.ld, col0, ncols);
+                ds_load_group(vs, vx, d, d4, gpad, p.ld, col0, ncols);
             }
         }
         ds_cluster_sync();  // PSI of the column group is complete (the next step, or the overlaps, read all rows)
@@ -225,23 +241,23 @@ __global__ void __launch_bounds__(kDsThreads, 1) dense_cluster_sweep_kernel(cons
         if (p.mode == 1) {
             // overlaps Im <chi_k(t_n)| mu_l |psi_k(t_n)> of this CTA's rows and columns  (:339-349)
             const double2 *CHI = p.X + p.slab * (size_t)n;
-            if (live) ds_load_group(vs, p.PSI, d, p.ld, col0, ncols);
+            if (live) ds_load_group(vs, p.PSI, d, d4, gpad, p.ld, col0, ncols);
             for (int l = 0; l < p.L; ++l) {
                 double acc = 0.0;
                 if (live) {
                     const double2 *Hl = p.H[0] + ((size_t)g * (1 + p.L) + 1 + l) * mat;
-                    for (int i = tid; i < nrows * d; i += kDsThreads) {  // stage the slice of H_l where G will be rebuilt
-                        const int r = i / d, k = i - r * d;
-                        gs[(size_t)r * gpad + k] = Hl[(size_t)(row0 + r) * p.dp + k];
+                    for (int i = tid; i < R8 * d4; i += kDsThreads) {  // stage the slice of H_l where G will be rebuilt
+                        const int r = i / d4, k = i - r * d4;
+                        gs[(size_t)r * gpad + k] = (r < nrows && k < d) ? Hl[(size_t)(row0 + r) * p.dp + k] : make_double2(0.0, 0.0);
                     }
                     __syncthreads();
+                    double tr[kDsMaxOut] = {0.0, 0.0}, ti[kDsMaxOut] = {0.0, 0.0};
+                    if (tile_live) ds_tile(ga, vb, d4, tr[0], tr[1], ti[0], ti[1]);
 #pragma unroll
                     for (int q = 0; q < kDsMaxOut; ++q) {
                         if (!oval[q]) continue;
-                        double cr, ci_;
-                        ds_dot(gs + (size_t)orow[q] * gpad, vs + ocol[q], d, cr, ci_);
                         const double2 ch = CHI[(size_t)(row0 + orow[q]) * p.ld + col0 + ocol[q]];
-                        acc += ch.x * ci_ - ch.y * cr;
+                        acc += ch.x * ti[q] - ch.y * tr[q];
                     }
                     __syncthreads();
                 }
@@ -265,6 +281,7 @@ __global__ void __launch_bounds__(kDsThreads, 1) dense_cluster_sweep_kernel(cons
                     for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
                     if (lane == 0) {
                         const double al = p.alpha[(size_t)l * p.N_T + n];
+                        sacc = rank_sum_lane(p.cm, p.L, n, l, sacc, blockIdx.x == 0);
                         if (p.am.dfac != nullptr) sacc = __dmul_rn(p.am.dfac[(size_t)l * p.N_T + n], sacc);
                         const double e_new = __dadd_rn(p.eps_old[(size_t)l * p.N_T + n], __dmul_rn(al, sacc));  // :355-356
                         eps_sh[l] = amp_apply(p.am, l, p.N_T, n, e_new);

@@ -1151,14 +1151,19 @@ def test_amplitude_argument_errors():
 # ---- persistent cluster sweep for moderate dense generators (dense_sweep.cuh) -------------------------------------------
 @pytest.mark.parametrize("d,n_traj,L,functional,hermitian,n_gen", [
     (40, 6, 2, "ss", True, 1), (100, 20, 1, "sm", True, 1), (100, 64, 2, "re", True, 1), (200, 64, 2, "ss", True, 1),
-    (33, 9, 3, "sm", False, 1), (72, 13, 2, "ss", True, 3), (288, 8, 1, "ss", True, 1)])
+    (33, 9, 3, "sm", False, 1), (72, 13, 2, "ss", True, 3), (255, 8, 1, "ss", True, 1)])
 def test_dense_cluster_sweep_equals_launch_stream_and_oracle(d, n_traj, L, functional, hermitian, n_gen, monkeypatch):
     """Dense generators with 32 < d <= 288: the whole iteration in ONE cooperative launch of 8-CTA clusters (generator
     slices in shared memory, one cluster barrier per Chebyshev term) against the launch-per-term DMMA stream
     (KROTOV_NO_DSWEEP=1) -- same state blocks and storage, agreement at rounding -- and against the oracle."""
     from oracle import krotov_oracle as O
 
-    w = W.dummy_dense(d=d, n_traj=n_traj, n_controls=L, functional=functional, n_grid=21, seed=d + L, hermitian=hermitian)
+    w = W.dummy_dense(d=d, n_traj=n_traj, n_controls=L, functional=functional, n_grid=21, seed=d + L)
+    if not hermitian:  # weak decay on the drift and a non-Hermitian control term: backward = ADJOINT generator
+        rng = np.random.default_rng(3)
+        w.H0 = [w.H0[0] - 0.02j * np.diag(rng.uniform(0, 1, d))]
+        B = (rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d))) / np.sqrt(d)
+        w.Hc = [[h for h in w.Hc[0][:-1]] + [w.Hc[0][-1] + 0.05 * B]]
     if n_gen > 1:  # an ensemble: several generators with their own spectral radius (different coefficient counts)
         w.H0 = [w.H0[0] * (1.0 + 0.3 * g) for g in range(n_gen)]
         w.Hc = [w.Hc[0] for _ in range(n_gen)]
