@@ -1033,6 +1033,7 @@ struct DenseEngine {
     int ds_units = 0, ds_R = 0, ds_gpad = 0;
     size_t ds_smem = 0;
     int *ds_units_dev = nullptr;
+    long long *ds_prof = nullptr;
 };
 
 namespace {
@@ -1230,6 +1231,8 @@ bool launch_dsweep(DenseEngine *e, int mode, const double *d_eps_old, double *d_
     p.amp_old = gen_coeffs_old(e, d_eps_old); p.am = e->amp; p.cm = e->comm;
     p.partial = e->sw_partial;
     p.bar = e->sw_bar;
+    if (getenv("KROTOV_PROF") && !e->ds_prof) dalloc(e->ds_prof, 8, err);
+    p.prof = getenv("KROTOV_PROF") ? e->ds_prof : nullptr;
     DK_CHECK(cudaMemsetAsync(e->sw_bar, 0, sizeof(unsigned), e->stream));
     DK_CHECK(cudaFuncSetAttribute((const void *)dense_cluster_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)e->ds_smem));
@@ -1251,6 +1254,16 @@ bool launch_dsweep(DenseEngine *e, int mode, const double *d_eps_old, double *d_
     DK_CHECK(cudaLaunchKernelEx(&cfg, dense_cluster_sweep_kernel, p));
     e->launches++;
     e->sweep_launches++;
+    if (p.prof) {  // diagnostics: where CTA 0 spent its cycles (us per time step of the sweep)
+        long long h[6];
+        DK_CHECK(cudaStreamSynchronize(e->stream));
+        DK_CHECK(cudaMemcpy(h, e->ds_prof, sizeof(h), cudaMemcpyDeviceToHost));
+        const double f = 1.0 / 1965.0 / e->N_T;
+        fprintf(stderr, "[dense sweep, mode %d, d=%d, %d clusters] us per time step (both sweeps of an iteration summed): "
+                        "build G %.2f, tiles %.2f, exchange + cluster barrier %.2f, group reload %.2f, overlaps %.2f, "
+                        "grid barrier + update %.2f\n", mode, e->d, e->ds_units, h[0] * f, h[1] * f, h[2] * f, h[3] * f,
+                h[4] * f, h[5] * f);
+    }
     return true;
 }
 
@@ -1546,7 +1559,7 @@ void dense_destroy(DenseEngine *e) {
                     e->PHI, e->partial, e->d_col_of_traj, e->d_traj_of_col, e->ell_cols, e->Pvf, e->Pvb, e->Gv,
                     e->sk_ws, e->sk_flags, e->sw_blk, e->sw_partial, e->sw_bar, e->sw_m[0], e->sw_m[1], e->sw_dtc[0], e->sw_dtc[1],
                     e->sw_coef[0], e->sw_coef[1], e->sw_Emin[0], e->sw_Emin[1], e->sw_Delta[0], e->sw_Delta[1],
-                    e->sw_phase[0], e->sw_phase[1], e->ds_units_dev};
+                    e->sw_phase[0], e->sw_phase[1], e->ds_units_dev, e->ds_prof};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);

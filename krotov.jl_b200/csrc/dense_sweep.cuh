@@ -55,6 +55,8 @@ struct DSweepParams {
     unsigned *bar;
     AmpDev am;
     DenseComm cm;              // several ranks: mailboxes of this iteration's parity
+    long long *prof;           // optional [8] cycle counters of CTA 0 (KROTOV_PROF=1): build G, tiles, exchange store +
+                               // cluster barrier, group reload, overlaps, grid barrier + update
 };
 
 __device__ __forceinline__ unsigned ds_cluster_rank() {
@@ -135,6 +137,14 @@ __global__ void __launch_bounds__(kDsThreads, 1) dense_cluster_sweep_kernel(cons
     const double2 *ga = gs + (size_t)(warp * 8 + gid) * gpad + tig;  // A fragment: row gid of the tile, k offset tig
     const double2 *vb = vs + (size_t)gid * gpad + tig;               // B fragment: column gid, k offset tig
     unsigned bar_target = 0;
+    long long pc[6] = {0, 0, 0, 0, 0, 0};
+    const bool prof = p.prof != nullptr && blockIdx.x == 0 && tid == 0;
+#define DS_T(i, stmt)                          \
+    do {                                       \
+        const long long t_ = clock64();        \
+        stmt;                                  \
+        if (prof) pc[i] += clock64() - t_;     \
+    } while (0)
 
     // generator slice for interval n of direction dir with coefficients cf[]  (build_G_kernel's arithmetic)
     auto build_G = [&](const int dir, const double (&cf)[kMaxL]) {
@@ -180,7 +190,10 @@ __global__ void __launch_bounds__(kDsThreads, 1) dense_cluster_sweep_kernel(cons
             const bool last = (j == m - 1);
             double2 *vx = p.VX[j & 1];
             double tr[kDsMaxOut] = {0.0, 0.0}, ti[kDsMaxOut] = {0.0, 0.0};
+            const long long t_tile = clock64();
             if (tile_live) ds_tile(ga, vb, d4, tr[0], tr[1], ti[0], ti[1]);  // warp-uniform: mma.sync needs the whole warp
+            if (prof) pc[1] += clock64() - t_tile;
+            const long long t_x = clock64();
 #pragma unroll
             for (int q = 0; q < kDsMaxOut; ++q) {
                 if (!oval[q]) continue;
@@ -204,10 +217,11 @@ __global__ void __launch_bounds__(kDsThreads, 1) dense_cluster_sweep_kernel(cons
             }
             if (!last) {
                 ds_cluster_sync();  // every row slice of V_j is in L2
-                ds_load_group(vs, vx, d, d4, gpad, p.ld, col0, ncols);
+                if (prof) pc[2] += clock64() - t_x;
+                DS_T(3, ds_load_group(vs, vx, d, d4, gpad, p.ld, col0, ncols));
             }
         }
-        ds_cluster_sync();  // PSI of the column group is complete (the next step, or the overlaps, read all rows)
+        DS_T(2, ds_cluster_sync());  // PSI of the column group is complete (the next step, or the overlaps, read all rows)
     };
 
     const size_t gtid = (size_t)blockIdx.x * blockDim.x + tid, gthreads = (size_t)gridDim.x * blockDim.x;
@@ -225,7 +239,7 @@ __global__ void __launch_bounds__(kDsThreads, 1) dense_cluster_sweep_kernel(cons
         ds_grid_barrier(p.bar, bar_target);
         for (int n = p.N_T - 1; n >= 0; --n) {
             for (int l = 0; l < p.L; ++l) cf[l] = p.amp_old[(size_t)l * p.N_T + n];
-            if (live) build_G(KROTOV_BACKWARD, cf);
+            if (live) DS_T(0, build_G(KROTOV_BACKWARD, cf));
             step(KROTOV_BACKWARD, n, p.X + p.slab * (size_t)n);
         }
         ds_grid_barrier(p.bar, bar_target);
@@ -240,6 +254,7 @@ __global__ void __launch_bounds__(kDsThreads, 1) dense_cluster_sweep_kernel(cons
     for (int n = 0; n < p.N_T; ++n) {
         if (p.mode == 1) {
             // overlaps Im <chi_k(t_n)| mu_l |psi_k(t_n)> of this CTA's rows and columns  (:339-349)
+            const long long t_ov = clock64();
             const double2 *CHI = p.X + p.slab * (size_t)n;
             if (live) ds_load_group(vs, p.PSI, d, d4, gpad, p.ld, col0, ncols);
             for (int l = 0; l < p.L; ++l) {
@@ -271,6 +286,8 @@ __global__ void __launch_bounds__(kDsThreads, 1) dense_cluster_sweep_kernel(cons
                 for (int w = 0; w < kDsThreads / 32; ++w) t += wsum[tid][w];
                 p.partial[(size_t)tid * gridDim.x + blockIdx.x] = t;
             }
+            if (prof) pc[4] += clock64() - t_ov;
+            const long long t_gb = clock64();
             ds_grid_barrier(p.bar, bar_target);
             // every CTA adds the CTA partials in the same fixed order: the same bits everywhere, no broadcast
             if (warp == 0) {
@@ -296,14 +313,18 @@ __global__ void __launch_bounds__(kDsThreads, 1) dense_cluster_sweep_kernel(cons
             __syncthreads();
             for (int l = 0; l < p.L; ++l) cf[l] = eps_sh[l];
             __syncthreads();
+            if (prof) pc[5] += clock64() - t_gb;
         } else {
             for (int l = 0; l < p.L; ++l) cf[l] = p.amp_old[(size_t)l * p.N_T + n];
         }
         double2 *store = nullptr;
         if (p.store_fw) store = p.PHI + p.slab * (size_t)(p.mode == 1 ? n : n + 1);  // slot n in an iteration (sic, :367)
-        if (live) build_G(KROTOV_FORWARD, cf);
+        if (live) DS_T(0, build_G(KROTOV_FORWARD, cf));
         step(KROTOV_FORWARD, n, store);
     }
+    if (prof)
+        for (int i = 0; i < 6; ++i) p.prof[i] = pc[i];
+#undef DS_T
 }
 
 }  // namespace
