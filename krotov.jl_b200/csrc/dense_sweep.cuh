@@ -81,28 +81,48 @@ __device__ __forceinline__ void ds_grid_barrier(unsigned *bar, unsigned &target)
     __syncthreads();
 }
 
-// C(8 x 8 tile) = A(8 rows of the slice) . V(column group), complex, on the FP64 tensor pipe.  `ga` -> this lane's row of the
-// A fragment (row gid of the tile, k offset tig), `vb` -> this lane's column of the transposed group (column gid, k offset
-// tig).  On return the lane holds C[gid][2 tig] = (cr0, ci0) and C[gid][2 tig + 1] = (cr1, ci1).
-__device__ __forceinline__ void ds_tile(const double2 *__restrict__ ga, const double2 *__restrict__ vb, const int d4,
-                                        double &cr0, double &cr1, double &ci0, double &ci1) {
-    cr0 = cr1 = ci0 = ci1 = 0.0;
+// C(8 x 8 tile) = A(8 rows of the slice) . V(column group) over k in [k0, k1), complex, on the FP64 tensor pipe.
+// `ga` -> this lane's row of the A fragment (row gid of the tile, k offset tig), `vb` -> this lane's column of the
+// transposed group (column gid, k offset tig).  On return the lane holds C[gid][2 tig] = (cr0, ci0) and
+// C[gid][2 tig + 1] = (cr1, ci1).  Four independent accumulator pairs: back-to-back DMMAs into one pair wait for each
+// other (measured 88 cycles per k-step of 4 DMMAs against 64 of issue).
+__device__ __forceinline__ void ds_tile(const double2 *__restrict__ ga, const double2 *__restrict__ vb, const int k0,
+                                        const int k1, double &cr0, double &cr1, double &ci0, double &ci1) {
+    double pr0 = 0.0, pr1 = 0.0, qr0 = 0.0, qr1 = 0.0, pi0 = 0.0, pi1 = 0.0, qi0 = 0.0, qi1 = 0.0;
 #pragma unroll 4
-    for (int k = 0; k < d4; k += 4) {
+    for (int k = k0; k < k1; k += 4) {
         const double2 a = ga[k], b = vb[k];
-        dmma(cr0, cr1, a.x, b.x);
-        dmma(cr0, cr1, -a.y, b.y);
-        dmma(ci0, ci1, a.x, b.y);
-        dmma(ci0, ci1, a.y, b.x);
+        dmma(pr0, pr1, a.x, b.x);
+        dmma(pi0, pi1, a.x, b.y);
+        dmma(qr0, qr1, -a.y, b.y);
+        dmma(qi0, qi1, a.y, b.x);
     }
+    cr0 = pr0 + qr0;
+    cr1 = pr1 + qr1;
+    ci0 = pi0 + qi0;
+    ci1 = pi1 + qi1;
 }
 
-// shared memory (transposed, [column][k], zero padded) <- the column group of a state block in global memory
+// shared memory (transposed, [column][k], zero padded) <- the column group of a state block in global memory.  All loads
+// of a thread are in flight before the first store (a dependent loop cost 1.4 us per Chebyshev term at d = 200).
 __device__ __forceinline__ void ds_load_group(double2 *vt, const double2 *src, const int d, const int d4, const int vpad,
                                               const int ld, const int col0, const int ncols) {
-    for (int i = threadIdx.x; i < d4 * kDsCols; i += kDsThreads) {
-        const int k = i / kDsCols, c = i - k * kDsCols;
-        vt[(size_t)c * vpad + k] = (c < ncols && k < d) ? __ldcg(src + (size_t)k * ld + col0 + c) : make_double2(0.0, 0.0);
+    constexpr int U = 4;
+    const int total = d4 * kDsCols;
+    for (int base = threadIdx.x; base < total; base += U * kDsThreads) {
+        double2 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = base + u * kDsThreads;
+            const int k = i / kDsCols, c = i - k * kDsCols;
+            v[u] = (i < total && c < ncols && k < d) ? __ldcg(src + (size_t)k * ld + col0 + c) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = base + u * kDsThreads;
+            const int k = i / kDsCols, c = i - k * kDsCols;
+            if (i < total) vt[(size_t)c * vpad + k] = v[u];
+        }
     }
     __syncthreads();
 }
@@ -123,19 +143,49 @@ __global__ void __launch_bounds__(kDsThreads, 1) dense_cluster_sweep_kernel(cons
     const size_t mat = (size_t)p.dp * p.dp;
     // warp w owns the 8 x 8 output tile of slice rows [8 w, 8 w + 8); DMMA accumulator layout: lane (gid, tig) holds
     // row gid, columns 2 tig and 2 tig + 1
+    // With few tiles (R <= 32: 4 tiles or fewer) the k range of a tile is split over two warps, whose partial tiles
+    // meet in shared memory: all 8 warps (all four tensor pipes twice) work on every term.
     constexpr int kDsMaxOut = 2;
+    constexpr int kWarps = kDsThreads / 32;
     const int gid = lane >> 2, tig = lane & 3;
-    const bool tile_live = live && warp * 8 < nrows;
+    const int ntiles = R8 / 8;
+    const bool split = 2 * ntiles <= kWarps;
+    const int tile = split ? warp % ntiles : warp, khalf = split ? warp / ntiles : 0;
+    const bool tile_live = live && tile * 8 < nrows && (split ? khalf < 2 : true);
+    const int kmid = split ? (d4 / 8) * 4 : d4;  // multiple of 4
+    const int k_lo = khalf == 0 ? 0 : kmid, k_hi = (split && khalf == 0) ? kmid : d4;
+    const bool owner = tile_live && khalf == 0;  // the warp that finishes the tile (epilogue, stores)
     int orow[kDsMaxOut], ocol[kDsMaxOut];
     bool oval[kDsMaxOut];
 #pragma unroll
     for (int q = 0; q < kDsMaxOut; ++q) {
-        orow[q] = warp * 8 + gid;
+        orow[q] = tile * 8 + gid;
         ocol[q] = 2 * tig + q;
-        oval[q] = live && orow[q] < nrows && ocol[q] < ncols;
+        oval[q] = owner && orow[q] < nrows && ocol[q] < ncols;
     }
-    const double2 *ga = gs + (size_t)(warp * 8 + gid) * gpad + tig;  // A fragment: row gid of the tile, k offset tig
+    const double2 *ga = gs + (size_t)(tile * 8 + gid) * gpad + tig;  // A fragment: row gid of the tile, k offset tig
     const double2 *vb = vs + (size_t)gid * gpad + tig;               // B fragment: column gid, k offset tig
+    __shared__ double part_sm[kWarps / 2][32][4];                    // partial tiles of the second k half
+    // tile product of this warp's share; after it the owner lanes hold the complete (tr, ti)
+    auto tile_product = [&](double (&tr)[kDsMaxOut], double (&ti)[kDsMaxOut]) {
+        tr[0] = tr[1] = ti[0] = ti[1] = 0.0;
+        if (tile_live) ds_tile(ga, vb, k_lo, k_hi, tr[0], tr[1], ti[0], ti[1]);  // warp-uniform: mma.sync needs the whole warp
+        if (split) {
+            if (tile_live && khalf == 1) {
+                part_sm[tile][lane][0] = tr[0];
+                part_sm[tile][lane][1] = tr[1];
+                part_sm[tile][lane][2] = ti[0];
+                part_sm[tile][lane][3] = ti[1];
+            }
+            __syncthreads();
+            if (owner) {
+                tr[0] += part_sm[tile][lane][0];
+                tr[1] += part_sm[tile][lane][1];
+                ti[0] += part_sm[tile][lane][2];
+                ti[1] += part_sm[tile][lane][3];
+            }
+        }
+    };
     unsigned bar_target = 0;
     long long pc[6] = {0, 0, 0, 0, 0, 0};
     const bool prof = p.prof != nullptr && blockIdx.x == 0 && tid == 0;
@@ -151,21 +201,37 @@ __global__ void __launch_bounds__(kDsThreads, 1) dense_cluster_sweep_kernel(cons
         const double sc = 4.0 / p.Delta[dir][g], beta = p.Delta[dir][g] / 2 + p.E_min[dir][g];
         const double2 f = (dir == KROTOV_FORWARD) ? make_double2(0.0, -sc) : make_double2(0.0, sc);
         const double2 *H = p.H[dir] + (size_t)g * (1 + p.L) * mat;
-        for (int i = tid; i < R8 * d4; i += kDsThreads) {
-            const int r = i / d4, k = i - r * d4;
-            double2 out = make_double2(0.0, 0.0);  // rows / columns beyond the slice: zero padding of the fragments
-            if (r < nrows && k < d) {
-                const size_t src = (size_t)(row0 + r) * p.dp + k;
-                double2 h = H[src];
-                if (row0 + r == k) h.x -= beta;
-                for (int l = 0; l < p.L; ++l) {
-                    const double2 hl = H[(size_t)(l + 1) * mat + src];
-                    h.x = fma(cf[l], hl.x, h.x);
-                    h.y = fma(cf[l], hl.y, h.y);
-                }
-                out = make_double2(f.x * h.x - f.y * h.y, f.x * h.y + f.y * h.x);
+        constexpr int U = 4;  // U elements per thread with all their loads in flight (L2 latency, not bandwidth, bound this)
+        const int total = R8 * d4;
+        for (int base = tid; base < total; base += U * kDsThreads) {
+            double2 h[U];
+            bool ok[U];
+            size_t src[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = base + u * kDsThreads, r = i / d4, k = i - r * d4;
+                ok[u] = i < total && r < nrows && k < d;
+                src[u] = ok[u] ? (size_t)(row0 + r) * p.dp + k : 0;
+                h[u] = ok[u] ? H[src[u]] : make_double2(0.0, 0.0);
+                if (ok[u] && row0 + r == k) h[u].x -= beta;
             }
-            gs[(size_t)r * gpad + k] = out;
+            for (int l = 0; l < p.L; ++l) {
+                double2 hl[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) hl[u] = ok[u] ? H[(size_t)(l + 1) * mat + src[u]] : make_double2(0.0, 0.0);
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    h[u].x = fma(cf[l], hl[u].x, h[u].x);
+                    h[u].y = fma(cf[l], hl[u].y, h[u].y);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = base + u * kDsThreads, r = i / d4, k = i - r * d4;
+                // rows / columns beyond the slice: zero padding of the fragments
+                if (i < total) gs[(size_t)r * gpad + k] = ok[u] ? make_double2(f.x * h[u].x - f.y * h[u].y, f.x * h[u].y + f.y * h[u].x)
+                                                                 : make_double2(0.0, 0.0);
+            }
         }
         __syncthreads();
     };
@@ -191,7 +257,7 @@ __global__ void __launch_bounds__(kDsThreads, 1) dense_cluster_sweep_kernel(cons
             double2 *vx = p.VX[j & 1];
             double tr[kDsMaxOut] = {0.0, 0.0}, ti[kDsMaxOut] = {0.0, 0.0};
             const long long t_tile = clock64();
-            if (tile_live) ds_tile(ga, vb, d4, tr[0], tr[1], ti[0], ti[1]);  // warp-uniform: mma.sync needs the whole warp
+            tile_product(tr, ti);
             if (prof) pc[1] += clock64() - t_tile;
             const long long t_x = clock64();
 #pragma unroll
@@ -261,13 +327,26 @@ __global__ void __launch_bounds__(kDsThreads, 1) dense_cluster_sweep_kernel(cons
                 double acc = 0.0;
                 if (live) {
                     const double2 *Hl = p.H[0] + ((size_t)g * (1 + p.L) + 1 + l) * mat;
-                    for (int i = tid; i < R8 * d4; i += kDsThreads) {  // stage the slice of H_l where G will be rebuilt
-                        const int r = i / d4, k = i - r * d4;
-                        gs[(size_t)r * gpad + k] = (r < nrows && k < d) ? Hl[(size_t)(row0 + r) * p.dp + k] : make_double2(0.0, 0.0);
+                    {   // stage the slice of H_l where G will be rebuilt (loads of a thread in flight together)
+                        constexpr int U = 4;
+                        const int total = R8 * d4;
+                        for (int base = tid; base < total; base += U * kDsThreads) {
+                            double2 v[U];
+#pragma unroll
+                            for (int u = 0; u < U; ++u) {
+                                const int i = base + u * kDsThreads, r = i / d4, k = i - r * d4;
+                                v[u] = (i < total && r < nrows && k < d) ? Hl[(size_t)(row0 + r) * p.dp + k] : make_double2(0.0, 0.0);
+                            }
+#pragma unroll
+                            for (int u = 0; u < U; ++u) {
+                                const int i = base + u * kDsThreads, r = i / d4, k = i - r * d4;
+                                if (i < total) gs[(size_t)r * gpad + k] = v[u];
+                            }
+                        }
                     }
                     __syncthreads();
-                    double tr[kDsMaxOut] = {0.0, 0.0}, ti[kDsMaxOut] = {0.0, 0.0};
-                    if (tile_live) ds_tile(ga, vb, d4, tr[0], tr[1], ti[0], ti[1]);
+                    double tr[kDsMaxOut], ti[kDsMaxOut];
+                    tile_product(tr, ti);
 #pragma unroll
                     for (int q = 0; q < kDsMaxOut; ++q) {
                         if (!oval[q]) continue;

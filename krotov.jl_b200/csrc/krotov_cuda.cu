@@ -410,7 +410,8 @@ int choose_launch(krotov_handle h) {
     // trajectories.  KROTOV_WPC overrides the warps-per-CTA heuristic (experiments).
     const int N = h->N, sm = h->sm_count;
     const int lpt = h->lpt;
-    const int cap_preg = (256 - 32) / lpt, cap = std::min(13, (512 - 32) / lpt);  // groups per CTA (named barriers 3..15)
+    // groups per CTA (named barriers 3..15); the wide-row instances of one-warp groups are built for 256 threads
+    const int cap_preg = (256 - 32) / lpt, cap = (lpt == 32 && h->Wt >= 16) ? 7 : std::min(13, (512 - 32) / lpt);
     const bool preg_possible = kernel_table().count(KernelKey{h->Wt, h->L, lpt}) > 0;
     // Pair mode: when there are more trajectories than one-per-warp CTAs with register-resident rows can hold
     // (N > 7 per SM) and they come in generator-sharing pairs (ensembles over basis states), one warp runs two
@@ -528,7 +529,10 @@ void fill_warp_params(krotov_handle h, int mode, kr::WarpParams &p) {
     if (const char *e = getenv("KROTOV_XACC_STRIDE")) p.xacc_stride = std::max(1, std::min(kXaccMaxStride, atoi(e)));
     int xacc_max = 512;
     if (const char *e = getenv("KROTOV_XACC_MAX")) xacc_max = std::min(atoi(e), kr::kXMaxArrivals);
-    std::string xchg = getenv("KROTOV_XCHG") ? getenv("KROTOV_XCHG") : "hier";
+    // default: the one-hop sum while the ranks' CTAs are few (measured on C4, ms per iteration, one-hop / hier / hier
+    // with stores / mailboxes: 2 GPUs x 128 CTAs 12.85 / 13.4 / 13.7 / 15.6; 8 GPUs x 32 CTAs 13.9 / 14.2 / 14.5 / -),
+    // the hierarchical sum beyond (every rank then receives `world` adds per word instead of `total_ctas`)
+    std::string xchg = getenv("KROTOV_XCHG") ? getenv("KROTOV_XCHG") : (h->total_ctas <= xacc_max ? "onehop" : "hier");
     if (getenv("KROTOV_NO_XACC")) xchg = "mbox";
     const bool hier_ok = h->max_ctas < 256 && h->total_ctas <= kr::kXMaxArrivals && !getenv("KROTOV_NO_ATOMIC_SUM");
     if ((xchg == "hier" || xchg == "hierst") && !hier_ok) xchg = "onehop";
