@@ -381,8 +381,9 @@ def main():
                                            "rank over NVLink (hierarchical sum)",
                                         2: "per time step, in-kernel over NVLink: every CTA adds its fixed-point partial into "
                                            "every rank's accumulator (one hop)",
-                                        3: "per time step, in-kernel over NVLink: rank sums pushed into the peers' mailboxes"
-                                        }.get(info.get("exchange"), "?")} if world > 1 else {})},
+                                        3: "per time step, in-kernel over NVLink: rank sums pushed into the peers' mailboxes",
+                                        4: "per time step, in-kernel: hierarchical sum, rank sums forwarded with plain stores "
+                                           "into per-rank slots over NVLink"}.get(info.get("exchange"), "?")} if world > 1 else {})},
             "e2e": {"value": e2e, "unit": UNIT, "iterations_per_s": steps / wall_s,
                     "h2d_bytes_per_step": L * N_T * 8, "d2h_bytes_per_step": L * N_T * 8 + L * 8 + n_loc * 16,
                     "ms_per_step_each": [round(1e3 * (b - a), 2) for a, b in zip(marks["wall"][warmup:warmup + steps], marks["wall"][warmup + 1:warmup + steps + 1])]},
