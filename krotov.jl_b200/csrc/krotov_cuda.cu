@@ -768,7 +768,12 @@ int krotov_create(const krotov_problem *pb, krotov_handle *out) {
             W = std::max(W, (int)pat[i].size());
         }
         // sparse path when the generator is sparse enough for ELL rows to pay off against DMMA tiles
-        const bool sparse_ok = (double)nnz <= 0.25 * (double)d * d && W <= 512;
+        bool sparse_ok = (double)nnz <= 0.25 * (double)d * d && W <= 512;
+        // Dense generators just beyond the cluster sweep's reach (256 < d <= 448) with many trajectories: the one-launch
+        // ELL sweep with full-width rows beats the launch-per-term DMMA stream (measured, us per time step and direction,
+        // 64 trajectories: d = 288 202 / 336, d = 400 267 / 452; at d = 512 the stream wins again, and with 16
+        // trajectories it always does -- profiles/r2_dense_cluster_sweep.txt).  KROTOV_NO_DENSE_ELL=1 disables the rule.
+        if (!sparse_ok && d > 256 && d <= 448 && N >= 48 && W <= 512 && !getenv("KROTOV_NO_DENSE_ELL")) sparse_ok = true;
         if (path == 0) path = sparse_ok ? KROTOV_PATH_SPARSE : KROTOV_PATH_DENSE;
         if (path == KROTOV_PATH_SPARSE) {
             hs.W = W;

@@ -992,6 +992,7 @@ def test_seeded_shape_sweep_vs_oracle(d, n_traj, L, n_grid, functional, hermitia
 def test_block_path_graph_replay_equals_direct_launches(monkeypatch):
     """The block path captures a settled iteration into one CUDA graph (third identical iteration on) and replays
     it: same pulses and J_T, bit for bit, as launching every kernel directly."""
+    monkeypatch.setenv("KROTOV_NO_DSWEEP", "1")  # (d <= 256 would otherwise take the one-launch cluster sweep)
     w = W.dummy_dense(d=48, n_traj=12, n_controls=2, n_grid=41, seed=12)
     w.specrange = (-4.0, 4.0)  # fixed spectral range: the Chebyshev tables never change, so the graph is used
     a = run_product(w, 6)
@@ -1188,3 +1189,15 @@ def test_dense_cluster_sweep_equals_launch_stream_and_oracle(d, n_traj, L, funct
     if d <= 100:
         ref = O.optimize_krotov(W.to_oracle(w), 2)
         assert_parity(sweep, ref["J_T"], ref["pulses"], ref["g_a_int"], rtol=1e-10, atol=5e-13)
+
+
+def test_mid_size_dense_generator_with_many_trajectories_takes_the_ell_sweep():
+    """256 < d <= 448 with >= 48 trajectories: the one-launch sweep with full-width ELL rows (path 3) is chosen over the
+    launch-per-term DMMA stream; same numbers as the stream."""
+    w = W.dummy_dense(d=300, n_traj=48, n_controls=1, n_grid=6, seed=31)
+    a = run_product(w, 1)
+    assert a["info"]["path"] == 3 and a["info"]["launches_last"] <= 4
+    b = run_product(w, 1, force_path=2)
+    assert b["info"]["path"] == 2 and b["info"]["launches_last"] > 20
+    assert np.abs(np.array(a["J_T"]) - np.array(b["J_T"])).max() < 1e-12
+    assert np.abs(a["pulses"] - b["pulses"]).max() < 1e-12
