@@ -80,9 +80,31 @@ class Comm:
     def all_gather_rows(self, local, n_total):
         """Concatenate per-rank blocks of rows (tau or states) in rank order.  COLLECTIVE: every rank must call it
         (touching `wrk.result.states` in a callback on one rank only would leave that rank waiting)."""
-        parts = self.all_gather_object(np.ascontiguousarray(local))
-        out = np.concatenate(parts, axis=0)
-        assert out.shape[0] == n_total
+        import torch
+
+        local = np.ascontiguousarray(local)
+        if not hasattr(self, "_row_counts") or self._row_counts[0] != n_total:
+            counts = self.all_gather_object(int(local.shape[0]))  # once per problem: the shards never change
+            self._row_counts = (n_total, counts)
+        counts = self._row_counts[1]
+        assert sum(counts) == n_total
+        # array collective on the host group (no pickling: C5 moves 4 MB of states per call); shards are padded to the
+        # largest one because all_gather wants equal shapes
+        is_cplx = np.iscomplexobj(local)
+        flat = local.astype(np.complex128 if is_cplx else np.float64, copy=False).reshape(local.shape[0], -1)
+        width = flat.shape[1]
+        rows = max(counts)
+        buf = np.zeros((rows, width), flat.dtype)
+        buf[: flat.shape[0]] = flat
+        t = torch.from_numpy(buf.view(np.float64) if is_cplx else buf)
+        outs = [torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(outs, t, group=self.cpu_group)
+        parts = []
+        for r, o in enumerate(outs):
+            a = o.numpy()
+            a = a.view(np.complex128) if is_cplx else a
+            parts.append(a[: counts[r]])
+        out = np.concatenate(parts, axis=0).reshape((n_total,) + local.shape[1:])
         return out
 
     def barrier(self):

@@ -17,6 +17,8 @@ pytestmark = pytest.mark.gpu
 def _make(kind, n_samples, n_grid):
     if kind == "c4":
         return W.c4_ensemble(n_samples=n_samples, n_grid=n_grid)
+    if kind == "chain":  # sparse generator: the persistent ELL sweep (or its launch-per-term stream)
+        return W.spin_chain(n_spins=7, n_traj=n_samples, n_grid=n_grid, functional="sm")
     return W.dummy_dense(d=64, n_traj=n_samples, n_controls=2, n_grid=n_grid, functional=kind, seed=5)
 
 
@@ -64,6 +66,8 @@ def _worker(rank, world, port, kind, n_samples, n_grid, iters, q, env=None):
         extra = {}
         if (env or {}).get("TEST_BIG_CHI"):
             extra = dict(chi=_big_chi, lambda_a=_BIG * w.lambda_a)
+        if kind == "chain":
+            extra["force_path"] = 3
         res = K.optimize(to_problem(w, iter_stop=iters, callback=cb, device=rank, **extra), method=K.Krotov, comm=comm)
         q.put((rank, hist["J_T"], hist["pulses"], hist["shard"], res.message, np.array(res.states), hist["ga"],
                hist["fallback"]))
@@ -76,9 +80,12 @@ def _worker(rank, world, port, kind, n_samples, n_grid, iters, q, env=None):
     ("c4", 64, 101, {"KROTOV_XCHG": "onehop", "KROTOV_XACC_STRIDE": "16"}),
     ("c4", 8, 201, {"KROTOV_XCHG": "mbox"}), ("c4", 64, 101, {"KROTOV_NO_XACC": "1"}),
     ("c4", 8, 41, {"TEST_BIG_CHI": "1"}), ("c4", 8, 41, {"TEST_BIG_CHI": "1", "KROTOV_XCHG": "onehop"}),
-    ("sm", 20, 21, {}), ("ss", 9, 21, {})])
+    ("sm", 20, 21, {}), ("ss", 9, 21, {}), ("sm", 20, 21, {"KROTOV_NO_SWEEP_RANKS": "1"}),
+    ("chain", 40, 21, {}), ("chain", 40, 21, {"KROTOV_NO_SWEEP_RANKS": "1"})])
 def test_two_ranks_match_single_gpu(kind, n_samples, n_grid, env):
-    """kind c4: warp path (in-kernel reducer exchange); kinds sm/ss: dense DMMA path (exchange in update_kernel)."""
+    """kind c4: warp path (in-kernel exchange of the comm warps); kinds sm/ss: dense generators (d = 64: the cluster
+    sweep, rank sums through the mailboxes from inside the sweep; with KROTOV_NO_SWEEP_RANKS the DMMA stream with the
+    exchange in update_kernel); kind chain: sparse generator (the ELL sweep, or its stream)."""
     import torch
 
     if torch.cuda.device_count() < 2:
@@ -87,7 +94,7 @@ def test_two_ranks_match_single_gpu(kind, n_samples, n_grid, env):
     from util import run_product
 
     iters = 2
-    single = run_product(_make(kind, n_samples, n_grid), iters)
+    single = run_product(_make(kind, n_samples, n_grid), iters, **({"force_path": 3} if kind == "chain" else {}))
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29700 + os.getpid() % 1000
