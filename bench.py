@@ -362,10 +362,10 @@ def main():
         nnz = info["nnz_union"]
         flops = 2.0 * n_loc * N_T * (m - 1) * 8 * nnz + n_loc * N_T * L * 8 * (nnz + d)
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
         if world == 1 and args.samples == 256 and args.n_grid == 2001 and os.path.exists(tpath):
             with open(tpath) as fh:  # measured once under ncu for exactly this launch shape
-                traffic = json.load(fh).get("krotov_warp_kernel<6,2,256> on C4 (1024 trajectories, N_T=2000)")
+                traffic = json.load(fh).get("krotov_warp_kernel<6,2,256,32> on C4 (1024 trajectories, N_T=2000)")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": dev_total_ms / steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
@@ -391,8 +391,9 @@ def main():
             "clocks": marks["clocks"],
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": ach_gbs / peaks["hbm_gbs"], "traffic": traffic,
-                         "traffic_source": "profiles/r1_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of ONE "
-                                           "ncu --set full capture of this launch shape (round 1), NOT measured in this run; "
+                         "traffic_source": "profiles/r2_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of ONE "
+                                           "ncu --set full capture of this launch shape (profiles/r2_warp_kernel_ncu_full.txt), "
+                                           "NOT measured in this run; "
                                            "1.25x the algorithmic bytes because d = 25 states sit in 32-entry records",
                          "peak_source": peak_src,
                          "kernel": "krotov_warp_kernel", "algorithmic_bytes_per_launch": alg_bytes,
