@@ -263,6 +263,8 @@ def main():
                     "process may run on; never the OpenMP default, which torchrun pins to 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra-configs", action="store_true", help="skip the C1/C2/C3/C5 block of the JSON line")
+    ap.add_argument("--multi-gpu", choices=["auto", "shard", "replicate"], default="auto",
+                    help="several ranks: shard the trajectories (per-step exchange) or replicate the forward sweep")
     ap.add_argument("--scaling", choices=["strong", "weak"], default="strong",
                     help="strong: the BASELINE ensemble sharded over the ranks; weak: --samples per rank")
     args = ap.parse_args()
@@ -331,7 +333,7 @@ def main():
         marks["m_bw"] = int(wrk.bw_settings.coeff_count.max())
         marks["shard"] = wrk._shard
 
-    problem = to_problem(w, iter_stop=warmup + steps, callback=cb, device=local_rank)
+    problem = to_problem(w, iter_stop=warmup + steps, callback=cb, device=local_rank, multi_gpu=args.multi_gpu)
     res = K.optimize(problem, method=K.Krotov, comm=comm)
     if res.message.startswith("Exception"):
         raise SystemExit(f"optimisation failed: {res.message}")
@@ -383,7 +385,10 @@ def main():
                                            "every rank's accumulator (one hop)",
                                         3: "per time step, in-kernel over NVLink: rank sums pushed into the peers' mailboxes",
                                         4: "per time step, in-kernel: hierarchical sum, rank sums forwarded with plain stores "
-                                           "into per-rank slots over NVLink"}.get(info.get("exchange"), "?")} if world > 1 else {})},
+                                           "into per-rank slots over NVLink",
+                                        5: "none per time step: every rank holds all trajectories; the backward sweep is "
+                                           "sharded and writes chi to every rank over NVLink (one rank barrier per iteration), "
+                                           "the time-serial forward sweep runs on every rank (replicated forward sweep)"}.get(info.get("exchange"), "?")} if world > 1 else {})},
             "e2e": {"value": e2e, "unit": UNIT, "iterations_per_s": steps / wall_s,
                     "h2d_bytes_per_step": L * N_T * 8, "d2h_bytes_per_step": L * N_T * 8 + L * 8 + n_loc * 16,
                     "ms_per_step_each": [round(1e3 * (b - a), 2) for a, b in zip(marks["wall"][warmup:warmup + steps], marks["wall"][warmup + 1:warmup + steps + 1])]},

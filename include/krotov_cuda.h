@@ -98,7 +98,11 @@ typedef struct {
     int32_t store_fw;           /* keep the forward storage Phi (src/optimize.jl:367); 0 = skip */
     int32_t device;             /* CUDA device ordinal                    */
     int32_t force_path;         /* 0 = auto, else enum krotov_path        */
-    int32_t reserved[7];
+    int32_t replicated_forward; /* several ranks, every rank creates the handle with ALL trajectories: the backward sweep
+                                   is sharded and chi written to every rank over NVLink, the time-serial forward sweep
+                                   runs on every rank (no per-step exchange).  Chosen at krotov_comm_connect when every
+                                   rank asked for it and runs the persistent kernel with one trajectory per warp. */
+    int32_t reserved[6];
 } krotov_problem;
 
 typedef struct {
@@ -114,7 +118,8 @@ typedef struct {
     int32_t exchange;        /* cross-rank protocol of the last launch: 0 none (one rank), 1 hierarchical sum (local
                                 accumulator, then one add per rank over NVLink), 2 one-hop sum (every CTA adds into every
                                 rank's accumulator), 3 rank sums through the peers' mailboxes, 4 hierarchical sum forwarded with plain
-                                stores into per-rank slots */
+                                stores into per-rank slots, 5 replicated forward sweep (no per-step exchange: sharded backward sweep
+                                writes chi to every rank, one rank barrier per iteration) */
     int64_t launches_total;  /* kernels launched by this handle since creation       */
     int64_t launches_last;   /* kernels launched by the last forward/iterate call    */
     double ms_last;          /* device time of the last forward/iterate call (CUDA events on the launch stream) */
@@ -210,7 +215,7 @@ int krotov_get_profile(krotov_handle h, int cta, int64_t *out);
  * (src/optimize.jl:340-349).  Each rank exports an IPC descriptor of its mailbox; after the
  * descriptors of all ranks have been gathered (any transport), krotov_comm_connect maps the
  * peers' mailboxes and the forward sweep exchanges partial sums in-kernel over NVLink. */
-#define KROTOV_COMM_DESC_BYTES 192
+#define KROTOV_COMM_DESC_BYTES 256
 int krotov_comm_export(krotov_handle h, void *desc /* KROTOV_COMM_DESC_BYTES */);
 int krotov_comm_connect(krotov_handle h, int rank, int world, const void *descs /* [world][DESC_BYTES] */);
 

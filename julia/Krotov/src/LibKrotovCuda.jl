@@ -11,7 +11,7 @@ const KROTOV_GEN_DENSE_COLMAJOR, KROTOV_GEN_CSR = Cint(0), Cint(1)
 const KROTOV_FORWARD, KROTOV_BACKWARD = Cint(0), Cint(1)
 const KROTOV_CHI_HOST, KROTOV_CHI_SM, KROTOV_CHI_SS, KROTOV_CHI_RE = Cint(0), Cint(1), Cint(2), Cint(3)
 const KROTOV_PATH_WARP, KROTOV_PATH_DENSE, KROTOV_PATH_SPARSE = Cint(1), Cint(2), Cint(3)
-const COMM_DESC_BYTES = 192
+const COMM_DESC_BYTES = 256
 
 # mirrors `krotov_problem` field by field
 struct Problem
@@ -39,7 +39,8 @@ struct Problem
     store_fw::Int32
     device::Int32
     force_path::Int32
-    reserved::NTuple{7,Int32}
+    replicated_forward::Int32
+    reserved::NTuple{6,Int32}
 end
 
 # mirrors `krotov_info` field by field

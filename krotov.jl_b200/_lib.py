@@ -19,7 +19,7 @@ GEN_DENSE_COLMAJOR, GEN_CSR = 0, 1
 FORWARD, BACKWARD = 0, 1
 CHI_HOST, CHI_SM, CHI_SS, CHI_RE = 0, 1, 2, 3
 PATH_WARP, PATH_DENSE, PATH_SPARSE = 1, 2, 3
-COMM_DESC_BYTES = 192
+COMM_DESC_BYTES = 256
 
 # every symbol include/krotov_cuda.h declares (tests check the .so exports all of them)
 EXPORTS = [
@@ -46,7 +46,7 @@ class Problem(C.Structure):
         ("gen_values", C.c_void_p), ("term_present", C.c_void_p), ("psi0", C.c_void_p), ("target", C.c_void_p),
         ("weight", C.c_void_p), ("update_shape", C.c_void_p), ("lambda_a", C.c_void_p),
         ("functional", C.c_int32), ("n_traj_global", C.c_int32), ("store_fw", C.c_int32), ("device", C.c_int32),
-        ("force_path", C.c_int32), ("reserved", C.c_int32 * 7),
+        ("force_path", C.c_int32), ("replicated_forward", C.c_int32), ("reserved", C.c_int32 * 6),
     ]
 
 

@@ -113,6 +113,15 @@ struct krotov_handle_s {
     size_t mail_bytes = 0, xacc_bytes = 0;  // d_mbox[par] = mailboxes (sentinel-filled) followed by the cross-rank accumulators (zero-filled)
     int total_ctas = 0;  // CTAs of all ranks (krotov_comm_connect)
     int max_ctas = 0;    // largest CTA count of a rank
+    // replicated forward sweep (every rank holds all trajectories; backward sweep sharded, chi written to all ranks)
+    bool rf = false;
+    int bw_lo = 0, bw_hi = 0;
+    bool rf_wanted = false;                       // krotov_problem.replicated_forward: d_X holds TWO chi trajectories
+    size_t x_slab = 0;                            // elements of one chi trajectory
+    DevBuf d_rfcount;                             // arrival counter of the rank barrier
+    double2 *peer_Xbase[kr::kMaxRanks] = {};      // chi trajectories of every rank (parity p at + p * x_slab)
+    unsigned long long *peer_flag[kr::kMaxRanks] = {};
+    bool peer_x_opened[kr::kMaxRanks] = {};
     int xchg_last = 0;   // cross-rank protocol of the last launch: 0 none, 1 hier, 2 onehop, 3 mailboxes
     // non-linear control amplitudes (krotov_set_amplitudes)
     bool amp_set = false;
@@ -542,6 +551,28 @@ void fill_warp_params(krotov_handle h, int mode, kr::WarpParams &p) {
         p.xchg_hier = (xchg == "hier") ? 1 : (xchg == "hierst") ? 2 : 0;
     }
     h->xchg_last = h->world > 1 ? (p.xacc[0] ? (p.xchg_hier == 1 ? 1 : p.xchg_hier == 2 ? 4 : 2) : 3) : 0;
+    if (h->rf) {
+        // replicated forward sweep: no per-step exchange between the ranks at all
+        p.world = 1;
+        p.rank = 0;
+        for (int r = 0; r < kr::kMaxRanks; ++r) {
+            p.xacc[r] = nullptr;
+            p.mbox[r] = nullptr;
+        }
+        p.xchg_hier = 0;
+        p.rf_world = h->world;
+        p.rf_rank = h->rank;
+        p.bw_lo = h->bw_lo;
+        p.bw_hi = h->bw_hi;
+        for (int r = 0; r < h->world; ++r) {
+            p.Xr[r] = h->peer_Xbase[r] + (size_t)par * h->x_slab;
+            p.rf_flag[r] = h->peer_flag[r];
+        }
+        p.X = p.Xr[h->rank];
+        p.rf_count = (unsigned int *)h->d_rfcount.p;
+        p.rf_iter = (unsigned long long)(h->iter_count + 1);
+        h->xchg_last = 5;
+    }
     p.err_flag = (int *)h->d_err.p;
     p.prof = (long long *)h->d_prof.p;
     p.timeout_cycles = 20000000000ll;  // ~10 s
@@ -612,15 +643,17 @@ int krotov_destroy(krotov_handle h) {
     if (!h) return KROTOV_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (int r = 0; r < kr::kMaxRanks; ++r)
+    for (int r = 0; r < kr::kMaxRanks; ++r) {
         if (h->peer_opened[r])
             for (int par = 0; par < 2; ++par)
                 if (h->peer_mbox[par][r]) cudaIpcCloseMemHandle(h->peer_mbox[par][r]);
+        if (h->peer_x_opened[r] && h->peer_Xbase[r]) cudaIpcCloseMemHandle(h->peer_Xbase[r]);
+    }
     DevBuf *bufs[] = {&h->d_acc, &h->d_Tf, &h->d_Tb, &h->d_cols, &h->d_Pf, &h->d_Pb, &h->d_inv_s, &h->d_gen, &h->d_dt, &h->d_alpha,
                       &h->d_eps_old, &h->d_eps_new, &h->d_ga, &h->d_X, &h->d_Phi, &h->d_psi0, &h->d_target,
                       &h->d_chiT, &h->d_chicoef, &h->d_psif, &h->d_tau, &h->d_R, &h->d_err, &h->d_weight, &h->d_prof,
                       &h->d_mbox[0], &h->d_mbox[1], &h->d_emul,
-                      &h->d_amp_poly, &h->d_amp_shape, &h->d_amp_old, &h->d_amp_dfac, &h->d_amp_new};
+                      &h->d_amp_poly, &h->d_amp_shape, &h->d_amp_old, &h->d_amp_dfac, &h->d_amp_new, &h->d_rfcount};
     for (DevBuf *b : bufs) b->release();
     for (int dir = 0; dir < 2; ++dir) {
         h->cheb[dir].coef.release();
@@ -670,6 +703,7 @@ int krotov_create(const krotov_problem *pb, krotov_handle *out) {
     h->functional = pb->functional;
     h->N_global = pb->n_traj_global > 0 ? pb->n_traj_global : pb->n_traj;
     h->store_fw = pb->store_fw; h->device = pb->device;
+    h->rf_wanted = pb->replicated_forward != 0;
     const int d = h->d, N = h->N, L = h->L, N_T = h->N_T;
     if (cudaSetDevice(h->device) != cudaSuccess) return bail(fail(h, KROTOV_ERR_CUDA, "cudaSetDevice failed"));
     cudaDeviceProp prop;
@@ -829,7 +863,8 @@ int krotov_create(const krotov_problem *pb, krotov_handle *out) {
     h->mail_bytes = (size_t)N_T * kr::kMaxRanks * L * 8;
     h->xacc_bytes = (path == KROTOV_PATH_WARP && L * kr::kXLimbs <= 32) ? (size_t)N_T * L * kr::kXLimbs * kXaccMaxStride * 8 : 0;
     for (int par = 0; par < 2; ++par) {
-        if ((rc = dev_alloc(h, h->d_mbox[par], h->mail_bytes + h->xacc_bytes))) return bail(rc);
+        if ((rc = dev_alloc(h, h->d_mbox[par], h->mail_bytes + h->xacc_bytes + 256))) return bail(rc);
+        cudaMemset((char *)h->d_mbox[par].p + h->mail_bytes + h->xacc_bytes, 0, 256);  // rank-barrier flags (parity 0 only)
         cudaMemset(h->d_mbox[par].p, 0xFF, h->mail_bytes);
         if (h->xacc_bytes) cudaMemset((char *)h->d_mbox[par].p + h->mail_bytes, 0, h->xacc_bytes);
         h->peer_mbox[par][0] = (double *)h->d_mbox[par].p;
@@ -865,7 +900,10 @@ int krotov_create(const krotov_problem *pb, krotov_handle *out) {
             if ((rc = upload(h, h->d_target, tmp))) return bail(rc);
         }
         const size_t slab = (size_t)N * (N_T + 1) * h->lpt * 16;
-        if ((rc = dev_alloc(h, h->d_X, slab))) return bail(rc);
+        h->x_slab = slab / 16;
+        // (replicated forward sweep: two chi trajectories, by iteration parity -- a peer that is one iteration ahead
+        // writes the other one)
+        if ((rc = dev_alloc(h, h->d_X, slab * (h->rf_wanted ? 2 : 1)))) return bail(rc);
         if (h->store_fw && (rc = dev_alloc(h, h->d_Phi, slab))) return bail(rc);
         if ((rc = dev_alloc(h, h->d_chiT, (size_t)N * h->lpt * 16))) return bail(rc);
         if ((rc = dev_alloc(h, h->d_psif, (size_t)N * h->lpt * 16))) return bail(rc);
@@ -924,7 +962,7 @@ int krotov_get_info(krotov_handle h, krotov_info *out) {
     out->m_fw = h->cheb[0].m_max_used;
     out->m_bw = h->cheb[1].m_max_used;
     out->sm_count = h->sm_count;
-    out->exchange = h->xchg_last;
+    out->exchange = h->rf ? 5 : h->xchg_last;
     out->launches_total = h->launches_total;
     out->launches_last = h->launches_last;
     out->ms_last = h->ms_last;
@@ -1115,7 +1153,7 @@ static int iterate_prepare(krotov_handle h, const double *guess_pulses) {
         if (h->functional == KROTOV_CHI_HOST)
             return fail(h, KROTOV_ERR_STATE, "functional is KROTOV_CHI_HOST: call krotov_set_chi before krotov_iterate");
         if (!h->swept) return fail(h, KROTOV_ERR_STATE, "krotov_forward must run before the first krotov_iterate");
-        if (h->world > 1 && h->functional == KROTOV_CHI_SM)
+        if (h->world > 1 && !h->rf && h->functional == KROTOV_CHI_SM)
             return fail(h, KROTOV_ERR_STATE, "multi-rank J_T_sm needs krotov_set_chi_coeffs (global sum of tau)");
     }
     const size_t pbytes = (size_t)h->L * h->N_T * 8;
@@ -1128,7 +1166,8 @@ static int iterate_prepare(krotov_handle h, const double *guess_pulses) {
                                                  (const double *)h->d_weight.p, (double2 *)h->d_chicoef.p);
         h->launches_last += 1;
     }
-    if (h->world > 1) {
+    if (h->rf) KR_CUDA(h, cudaMemsetAsync(h->d_rfcount.p, 0, 16, h->stream));
+    if (h->world > 1 && !h->rf) {
         // the mailbox of the NEXT iteration's parity is cleared now (peers are at most one iteration ahead)
         const int nxt = (int)((h->iter_count + 1) & 1);
         KR_CUDA(h, cudaMemsetAsync(h->d_mbox[nxt].p, 0xFF, h->mail_bytes, h->stream));
@@ -1180,6 +1219,47 @@ int krotov_iterate(krotov_handle h, const double *guess_pulses, double *new_puls
     return iterate_finish(h, new_pulses, g_a_int);
 }
 
+// Replicated forward sweep: possible when this handle holds ALL trajectories of the problem and runs the persistent
+// kernel with one trajectory per warp (KROTOV_NO_RF=1 keeps the sharded forward sweep with its per-step exchange).
+static bool rf_eligible(krotov_handle h) {
+    return h->rf_wanted && h->path == KROTOV_PATH_WARP && h->N == h->N_global && h->tpw == 1 && !h->pair &&
+           !getenv("KROTOV_NO_RF");
+}
+
+// this rank's share of the backward sweep: a contiguous block cut at generator boundaries where that is possible
+static void rf_shard(krotov_handle h, int rank, int world, int *lo, int *hi) {
+    const int N = h->N;
+    std::vector<int> cuts{0};
+    for (int k = 1; k < N; ++k)
+        if (h->gen_of_traj[k] != h->gen_of_traj[k - 1]) cuts.push_back(k);
+    cuts.push_back(N);
+    std::vector<int> b(world + 1);
+    for (int r = 0; r <= world; ++r) {
+        const long long ideal = (long long)r * N / world;
+        int best = cuts[0];
+        for (int c : cuts)
+            if (std::llabs(c - ideal) < std::llabs(best - ideal)) best = c;
+        b[r] = best;
+    }
+    b[0] = 0;
+    b[world] = N;
+    bool ok = true;
+    for (int r = 0; r < world; ++r) ok = ok && b[r + 1] > b[r];
+    if (!ok)
+        for (int r = 0; r <= world; ++r) b[r] = (int)((long long)r * N / world);
+    *lo = b[rank];
+    *hi = b[rank + 1];
+}
+
+// arrival counter + backward shard of the replicated forward sweep (when the mode is chosen at connect time)
+static int rf_prepare(krotov_handle h, int rank, int world) {
+    int rc;
+    if ((rc = dev_alloc(h, h->d_rfcount, 16))) return rc;
+    rf_shard(h, rank, world, &h->bw_lo, &h->bw_hi);
+    h->rf = true;
+    return KROTOV_OK;
+}
+
 // ---- several ranks emulated on ONE device (diagnostics / tests) ---------------------------------------------------------
 // Ranks that wait for one another inside their persistent kernels cannot run as separate launches on one GPU (nothing
 // makes them co-resident).  A group of handles created on the same device is instead driven by ONE cooperative launch
@@ -1200,6 +1280,8 @@ int krotov_group_connect(krotov_handle *hs, int world) {
         mx = std::max(mx, h->nCTA);
     }
     if (total > hs[0]->sm_count) return fail(hs[0], KROTOV_ERR_UNSUPPORTED, "krotov_group_connect: more CTAs than SMs");
+    bool rf_all = world > 1;
+    for (int r = 0; r < world; ++r) rf_all = rf_all && rf_eligible(hs[r]) && hs[r]->N == hs[0]->N;
     for (int r = 0; r < world; ++r) {
         krotov_handle h = hs[r];
         h->rank = r;
@@ -1207,8 +1289,17 @@ int krotov_group_connect(krotov_handle *hs, int world) {
         h->total_ctas = total;
         h->max_ctas = mx;
         h->iter_count = 0;
+        h->rf = false;
         for (int q = 0; q < world; ++q)
             for (int par = 0; par < 2; ++par) h->peer_mbox[par][q] = (double *)hs[q]->d_mbox[par].p;
+        if (rf_all) {
+            int rc = rf_prepare(h, r, world);
+            if (rc) return rc;
+            for (int q = 0; q < world; ++q) {
+                h->peer_Xbase[q] = (double2 *)hs[q]->d_X.p;
+                h->peer_flag[q] = (unsigned long long *)((char *)hs[q]->d_mbox[0].p + hs[q]->mail_bytes + hs[q]->xacc_bytes);
+            }
+        }
     }
     return KROTOV_OK;
 }
@@ -1327,6 +1418,8 @@ int krotov_get_storage(krotov_handle h, int which, int k, int n0, int n1, double
         const DevBuf &b = which == KROTOV_FORWARD ? h->d_Phi : h->d_X;
         std::vector<cplx> tmp((size_t)(n1 - n0) * h->lpt);
         const char *src = (const char *)b.p + ((size_t)k * (h->N_T + 1) + n0) * h->lpt * 16;
+        if (h->rf && which == KROTOV_BACKWARD && h->iter_count > 0)  // the chi trajectory of the LAST iteration's parity
+            src += (size_t)((h->iter_count - 1) & 1) * h->x_slab * 16;
         KR_CUDA(h, cudaMemcpy(tmp.data(), src, tmp.size() * 16, cudaMemcpyDeviceToHost));
         cplx *o = reinterpret_cast<cplx *>(out);
         for (int n = 0; n < n1 - n0; ++n)
@@ -1355,9 +1448,12 @@ int krotov_get_profile(krotov_handle h, int cta, int64_t *out) {
 // ---- multi-GPU mailbox exchange over CUDA IPC -------------------------------------------------
 struct CommDesc {
     cudaIpcMemHandle_t mh[2];
+    cudaIpcMemHandle_t xh;  // the chi trajectory (replicated forward sweep: peers write it)
 };
 struct CommDescTail {  // behind the handles, in the descriptor's spare bytes
     int nCTA;
+    int n_traj, n_traj_global;
+    int rf_ok;  // this rank could run the replicated forward sweep (warp path, one trajectory per warp, all trajectories held)
 };
 static_assert(sizeof(CommDesc) + sizeof(CommDescTail) <= KROTOV_COMM_DESC_BYTES, "descriptor too large");
 
@@ -1367,9 +1463,10 @@ int krotov_comm_export(krotov_handle h, void *desc) {
     CommDesc cd;
     memset(&cd, 0, sizeof(cd));
     for (int par = 0; par < 2; ++par) KR_CUDA(h, cudaIpcGetMemHandle(&cd.mh[par], h->d_mbox[par].p));
+    if (h->path == KROTOV_PATH_WARP) KR_CUDA(h, cudaIpcGetMemHandle(&cd.xh, h->d_X.p));
     memset(desc, 0, KROTOV_COMM_DESC_BYTES);
     memcpy(desc, &cd, sizeof(cd));
-    CommDescTail tail{h->path == KROTOV_PATH_WARP ? h->nCTA : 0};
+    CommDescTail tail{h->path == KROTOV_PATH_WARP ? h->nCTA : 0, h->N, h->N_global, rf_eligible(h) ? 1 : 0};
     memcpy((char *)desc + sizeof(cd), &tail, sizeof(tail));
     return KROTOV_OK;
 }
@@ -1382,11 +1479,23 @@ int krotov_comm_connect(krotov_handle h, int rank, int world, const void *descs)
     h->world = world;
     h->total_ctas = 0;
     h->max_ctas = 0;
+    bool rf_all = world > 1;
     for (int r = 0; r < world; ++r) {
         CommDescTail tail;
         memcpy(&tail, (const char *)descs + (size_t)r * KROTOV_COMM_DESC_BYTES + sizeof(CommDesc), sizeof(tail));
         h->total_ctas += tail.nCTA;
         h->max_ctas = std::max(h->max_ctas, tail.nCTA);
+        rf_all = rf_all && tail.rf_ok && tail.n_traj == h->N && tail.n_traj_global == h->N_global;
+    }
+    h->rf = false;
+    if (rf_all) {  // every rank holds the whole problem: replicated forward sweep (same decision on every rank)
+        int rc = rf_prepare(h, rank, world);
+        if (rc) return rc;
+    } else if (world > 1 && h->rf_wanted) {
+        // a handle that holds ALL trajectories must never run the sharded exchange (every trajectory would count
+        // `world` times): fail loudly instead
+        return fail(h, KROTOV_ERR_UNSUPPORTED, "replicated_forward was requested but cannot be used (needs the persistent "
+                                               "kernel with one trajectory per warp and the same full problem on every rank)");
     }
     for (int r = 0; r < world; ++r) {
         if (r == rank) {
@@ -1403,6 +1512,21 @@ int krotov_comm_connect(krotov_handle h, int rank, int world, const void *descs)
         h->peer_opened[r] = true;
     }
     h->iter_count = 0;
+    if (h->rf) {  // the peers' chi trajectories (both parities in one allocation) and their rank-barrier flags
+        for (int r = 0; r < world; ++r) {
+            if (r == rank) {
+                h->peer_Xbase[r] = (double2 *)h->d_X.p;
+            } else {
+                CommDesc cd;
+                memcpy(&cd, (const char *)descs + (size_t)r * KROTOV_COMM_DESC_BYTES, sizeof(cd));
+                void *ptr = nullptr;
+                KR_CUDA(h, cudaIpcOpenMemHandle(&ptr, cd.xh, cudaIpcMemLazyEnablePeerAccess));
+                h->peer_Xbase[r] = (double2 *)ptr;
+                h->peer_x_opened[r] = true;
+            }
+            h->peer_flag[r] = (unsigned long long *)((char *)h->peer_mbox[0][r] + h->mail_bytes + h->xacc_bytes);
+        }
+    }
     return KROTOV_OK;
 }
 

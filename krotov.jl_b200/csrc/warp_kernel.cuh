@@ -101,6 +101,15 @@ struct WarpParams {
     // [cta_base, cta_base + nCTA) holds b
     const WarpParams *emul;
     int emul_ranks, cta_base;
+    // Replicated forward sweep (several ranks, every rank holds ALL trajectories): the backward sweep is sharded -- this
+    // rank propagates trajectories [bw_lo, bw_hi) and writes every chi_k(t_n) into the chi trajectory of EVERY rank
+    // (peer stores over NVLink) -- one rank barrier follows, and the time-serial forward sweep runs on every rank over all
+    // trajectories with the one-rank exchange: no NVLink hop per time step, bit-identical replicas by construction.
+    int rf_world, rf_rank, bw_lo, bw_hi;
+    double2 *Xr[kMaxRanks];                 // chi trajectory of every rank (this iteration's parity); Xr[rf_rank] == X
+    unsigned long long *rf_flag[kMaxRanks]; // [world] per rank: "rank r has finished its backward sweep of iteration i"
+    unsigned int *rf_count;                 // arrivals of this rank's trajectory warps (zeroed per launch)
+    unsigned long long rf_iter;
 };
 
 template <bool EMUL>
@@ -920,9 +929,14 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
     const long long t_begin = clock64();
     long long t_wait_b = 0, t_overlap = 0, t_step = 0;
     // ================================================================ backward sweep
+    const bool rf = p.rf_world > 1;
     if (p.mode == 1) {
         for (int t = 0; t < tpw; ++t) {
-            const int k = kbase + t;
+            int k = kbase + t;
+            if (rf) {  // (tpw == 1) this rank's backward shard, spread over the CTAs: one trajectory per SM first
+                const int tl = warp * p.nCTA + cta;
+                k = (tl < p.bw_hi - p.bw_lo) ? p.bw_lo + tl : p.N;
+            }
             if (k >= p.N) break;
             const int gi = p.gen_of_traj[k];
             const double2 *Pg = p.Pb + (size_t)gi * (1 + L) * rowstride;
@@ -938,8 +952,15 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
                 const double2 tg = p.target[(size_t)k * LPT + lane];
                 chi = make_double2(c.x * tg.x - c.y * tg.y, c.x * tg.y + c.y * tg.x);
             }
-            double2 *Xk = p.X + (size_t)k * (N_T + 1) * LPT;
-            Xk[(size_t)N_T * LPT + lane] = chi;
+            const size_t xoff = (size_t)k * (N_T + 1) * LPT + lane;
+            auto store_chi = [&](const int slot, const double2 v) {
+                if (!rf) {
+                    p.X[xoff + (size_t)slot * LPT] = v;
+                } else {
+                    for (int r = 0; r < p.rf_world; ++r) p.Xr[r][xoff + (size_t)slot * LPT] = v;  // peers over NVLink
+                }
+            };
+            store_chi(N_T, chi);
             mypsi[t * LPT + lane] = chi;
             grp_sync<LPT>(gbar);
             StepMeta meta = load_meta(p.dtc_b, p.m_b, p.phase_b, p.coef_b, p.ndtc_b, p.mmax_b, gi, N_T - 1);
@@ -983,8 +1004,41 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
                 for (int l = 0; l < kMaxCtrl; ++l) e_cur[l] = e_next[l];
                 mypsi[t * LPT + lane] = chi;
                 grp_sync<LPT>(gbar);
-                Xk[(size_t)n * LPT + lane] = chi;
+                store_chi(n, chi);
             }
+        }
+        if (rf) {
+            // ---- rank barrier: every rank's chi trajectory is complete on every rank before anybody reads it.
+            // writers: fence -> arrival (gpu-scope release); warp 0 of CTA 0 collects the arrivals of this rank, fences at
+            // system scope and raises this rank's flag on every rank; everybody waits for all flags in its own memory.
+            __threadfence_system();
+            grp_sync<LPT>(gbar);
+            if (lane == 0 && (LPT == 32 || (threadIdx.x % LPT) == 0)) {
+                asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.rf_count) : "memory");
+                const long long t0 = clock64();
+                if (cta == 0 && warp == 0) {
+                    const unsigned total = (unsigned)(p.nCTA * p.wpc);
+                    unsigned seen;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.rf_count) : "memory");
+                    } while (seen < total && clock64() - t0 < p.timeout_cycles);
+                    __threadfence_system();
+                    for (int r = 0; r < p.rf_world; ++r)
+                        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p.rf_flag[r] + p.rf_rank), "l"(p.rf_iter) : "memory");
+                }
+                for (int r = 0; r < p.rf_world; ++r) {
+                    unsigned long long f;
+                    do {
+                        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(p.rf_flag[p.rf_rank] + r) : "memory");
+                        if (clock64() - t0 > p.timeout_cycles || *(volatile int *)p.err_flag) {
+                            atomicExch(p.err_flag, 1);
+                            break;
+                        }
+                    } while (f < p.rf_iter);
+                }
+                __threadfence_system();
+            }
+            grp_sync<LPT>(gbar);
         }
     }
 
@@ -1012,7 +1066,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
     const double inv_s0 = (k0 < p.N) ? p.inv_s_f[g0] : 0.0;
     StepMeta fmeta = load_meta(p.dtc_f, p.m_f, p.phase_f, p.coef_f, p.ndtc_f, p.mmax_f, g0, 0);
     double2 chi_next = make_double2(0.0, 0.0);
-    if (p.mode == 1 && k0 < p.N) chi_next = p.X[(size_t)k0 * (N_T + 1) * LPT + lane];
+    if (p.mode == 1 && k0 < p.N) chi_next = __ldcg(&p.X[(size_t)k0 * (N_T + 1) * LPT + lane]);
     // FAST: register-resident rows, one trajectory per warp, Hermitian control terms.  Then
     //   Im<chi|mu_l|psi> = -(1/s) Re <P_l chi|psi>   (P_l = -i s mu_l is anti-Hermitian)
     // so xi_l = P_l chi(t_n) can be formed BEFORE psi(t_n) exists, and the overlap on the critical path is a
@@ -1055,7 +1109,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
                 const int gi = (t == 0) ? g0 : p.gen_of_traj[k];
                 const double inv_s = (t == 0) ? inv_s0 : p.inv_s_f[gi];
                 const double2 psi = (tpw == 1) ? psi_reg : mypsi[t * LPT + lane];
-                const double2 chi = (t == 0) ? chi_next : p.X[((size_t)k * (N_T + 1) + n) * LPT + lane];
+                const double2 chi = (t == 0) ? chi_next : __ldcg(&p.X[((size_t)k * (N_T + 1) + n) * LPT + lane]);
                 if (PREG) {
 #pragma unroll
                     for (int l = 0; l < NT - 1; ++l) {
@@ -1079,7 +1133,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
             bar_arrive(1, nthr_all);  // barrier A
             const long long w0 = clock64();
             t_overlap += w0 - ts0;
-            if (n + 1 < N_T && k0 < p.N) chi_next = p.X[((size_t)k0 * (N_T + 1) + n + 1) * LPT + lane];
+            if (n + 1 < N_T && k0 < p.N) chi_next = __ldcg(&p.X[((size_t)k0 * (N_T + 1) + n + 1) * LPT + lane]);
             if (PREG && FAST && k0 < p.N) {
                 // ---- idle window: everything for this and the next step that does not depend on eps_n
 #pragma unroll

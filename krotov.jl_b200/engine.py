@@ -17,7 +17,8 @@ def _ptr(a):
 
 class KrotovCuda:
     def __init__(self, *, tlist, H0, Hc, gen_of_traj, psi0, target=None, weight=None, update_shape, lambda_a,
-                 functional=B.CHI_HOST, n_traj_global=0, store_fw=False, device=0, force_path=0, csr=False):
+                 functional=B.CHI_HOST, n_traj_global=0, store_fw=False, device=0, force_path=0, csr=False,
+                 replicated_forward=False):
         """H0: (n_gen, d, d) complex, Hc: (n_gen, L, d, d) complex with ``None`` entries allowed
         (as zeros + term_present=0); psi0/target: (N, d); update_shape: (L, N_T); lambda_a: (L,)."""
         lib = B.lib()
@@ -90,6 +91,7 @@ class KrotovCuda:
         p.update_shape, p.lambda_a = _ptr(S), _ptr(lam)
         p.functional, p.n_traj_global = int(functional), int(n_traj_global)
         p.store_fw, p.device, p.force_path = int(bool(store_fw)), int(device), int(force_path)
+        p.replicated_forward = int(bool(replicated_forward))
         rc = lib.krotov_create(C.byref(p), C.byref(self._h))
         if rc != B.KROTOV_OK:
             msg = lib.krotov_last_error(None).decode()
@@ -207,13 +209,16 @@ class KrotovCudaGroup:
     with a one-rank run) on a single-GPU box.  ``bounds[r] = (lo, hi)``: trajectories of rank r; ``gens[r]``: indices
     (into the caller's generator list) of the generators rank r holds, in the rank's local order."""
 
-    def __init__(self, engines, bounds, gens):
+    def __init__(self, engines, bounds, gens, replicated=False):
+        """replicated: every engine holds ALL trajectories (replicated forward sweep, sharded backward sweep): arrays are
+        passed whole to every rank and read back from rank 0."""
         self.engines, self.bounds, self.gens = list(engines), list(bounds), [np.asarray(g, int) for g in gens]
+        self.replicated = bool(replicated)
         e0 = self.engines[0]
         self._lib = e0._lib
-        self.N = sum(e.N for e in self.engines)
+        self.N = e0.N if replicated else sum(e.N for e in self.engines)
         self.d, self.L, self.N_T = e0.d, e0.L, e0.N_T
-        self.n_gen = sum(len(g) for g in self.gens)
+        self.n_gen = len(self.gens[0]) if replicated else sum(len(g) for g in self.gens)
         self.world = len(self.engines)
         self.pulses_all = None  # every rank's copy of the last new pulses: (world, L, N_T)
         arr = (C.c_void_p * self.world)(*[e._h for e in self.engines])
@@ -237,7 +242,7 @@ class KrotovCudaGroup:
         E_min, Delta = np.asarray(E_min), np.asarray(Delta)
         m, tab = np.asarray(m), np.asarray(tab)
         for e, g in zip(self.engines, self.gens):
-            e.set_cheby(direction, dt_class_of_step, dt_of_class, E_min[g], Delta[g], m[g], tab[g])
+            e.set_cheby(direction, dt_class_of_step, dt_of_class, E_min[g], Delta[g], m[g], tab[g])  # (replicated: g = all)
 
     def set_amplitudes(self, poly=None, shape=None):
         for e in self.engines:
@@ -271,10 +276,18 @@ class KrotovCudaGroup:
         return allp[0].copy(), ga[0].copy()
 
     def states(self):
+        if self.replicated:
+            return self.engines[0].states()
         return np.concatenate([e.states() for e in self.engines], axis=0)
 
     def tau(self):
+        if self.replicated:
+            return self.engines[0].tau()
         return np.concatenate([e.tau() for e in self.engines], axis=0)
+
+    def states_all(self):
+        """Final states of EVERY rank (replicated mode: they must be identical)."""
+        return [e.states() for e in self.engines]
 
     def storage(self, which, k, n0=0, n1=None):
         for e, (lo, hi) in zip(self.engines, self.bounds):

@@ -387,6 +387,20 @@ class KrotovWrk:
         pk = self.fw_prop_kwargs[0]
         device = int(self.kwargs.get("device", comm.device if comm is not None else 0))
 
+        # several ranks: "shard" = every rank holds its block of trajectories, the overlap sums cross the ranks at every
+        # time step; "replicate" = every rank holds ALL trajectories, the backward sweep is sharded and writes chi to
+        # every rank, the time-serial forward sweep runs everywhere (no per-step exchange; replicas identical by
+        # construction).  "auto": replicate where the persistent one-warp-per-trajectory kernel serves the problem.
+        mode = str(self.kwargs.get("multi_gpu", "auto"))
+        n_ranks_wanted = max(world, int(self.kwargs.get("emulate_ranks", 0) or 0))
+        any_sparse = any(hasattr(m, "tocsr") for m in H0)
+        if mode == "auto":
+            mode = "replicate" if (n_ranks_wanted > 1 and d <= 32 and N <= 7 * 148 and not any_sparse and
+                                   int(self.kwargs.get("force_path", 0)) in (0, 1)) else "shard"
+        if mode not in ("shard", "replicate"):
+            raise ArgumentError(f"multi_gpu={mode!r}: expected 'auto', 'shard' or 'replicate'")
+        self._replicated = mode == "replicate" and n_ranks_wanted > 1
+
         def make_engine(lo, hi):
             local_gens = sorted(set(int(g) for g in gen_of_traj[lo:hi]))
             remap = {g: i for i, g in enumerate(local_gens)}
@@ -396,7 +410,7 @@ class KrotovWrk:
                 psi0=psi0[lo:hi], target=None if target is None else target[lo:hi], weight=weight[lo:hi],
                 update_shape=S, lambda_a=self.lambda_vals, functional=functional, n_traj_global=N,
                 store_fw=self.store_fw, device=device, force_path=int(self.kwargs.get("force_path", 0)),
-                csr=bool(self.kwargs.get("csr_generators", False)))
+                csr=bool(self.kwargs.get("csr_generators", False)), replicated_forward=self._replicated)
             return eng, local_gens
 
         emulate = int(self.kwargs.get("emulate_ranks", 0) or 0)
@@ -406,16 +420,16 @@ class KrotovWrk:
                 raise ArgumentError("`emulate_ranks` and a multi-rank `comm` exclude each other")
             from .engine import KrotovCudaGroup
 
-            bounds = [shard_bounds(gen_of_traj, r, emulate) for r in range(emulate)]
+            bounds = [(0, N)] * emulate if self._replicated else [shard_bounds(gen_of_traj, r, emulate) for r in range(emulate)]
             made = [make_engine(lo, hi) for lo, hi in bounds]
-            self.engine = KrotovCudaGroup([m[0] for m in made], bounds, [m[1] for m in made])
+            self.engine = KrotovCudaGroup([m[0] for m in made], bounds, [m[1] for m in made], replicated=self._replicated)
             self._shard = (0, N)
-            self._n_ranks = emulate
+            self._n_ranks = 1 if self._replicated else emulate
             self._H0, self._Hc = H0, Hc
         else:
-            lo, hi = shard_bounds(gen_of_traj, rank, world)
+            lo, hi = (0, N) if self._replicated else shard_bounds(gen_of_traj, rank, world)
             self._shard = (lo, hi)
-            self._n_ranks = world
+            self._n_ranks = 1 if self._replicated else world
             self.engine, local_gens = make_engine(lo, hi)
             self._H0 = [H0[g] for g in local_gens]
             self._Hc = [Hc[g] for g in local_gens]
@@ -457,13 +471,13 @@ class KrotovWrk:
 
     def _fetch_states(self):
         local = self.engine.states()
-        if self.comm is not None and self.comm.world > 1:
+        if self.comm is not None and self.comm.world > 1 and not self._replicated:
             return self.comm.all_gather_rows(local, self.N)
         return local
 
     def _fetch_tau(self):
         local = self.engine.tau()
-        if self.comm is not None and self.comm.world > 1:
+        if self.comm is not None and self.comm.world > 1 and not self._replicated:
             return self.comm.all_gather_rows(local, self.N)
         return local
 

@@ -230,7 +230,7 @@ def _gloo_worker(rank, world, port, out):
         lo, hi = shard_bounds(gen, rank, world)
         local_tau = (np.arange(lo, hi) + 1j * rank).astype(complex)
         tau = comm.all_gather_rows(local_tau, len(gen))
-        descs = comm.all_gather_object(bytes([rank]) * 192)
+        descs = comm.all_gather_object(bytes([rank]) * 256)
         # J_T_sm chi coefficients from the gathered tau: identical on all ranks
         coef = (1.0 / len(gen) ** 2) * np.sum(tau)
         out.put((rank, lo, hi, tau.real.tolist(), [d[0] for d in descs], complex(coef)))

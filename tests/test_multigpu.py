@@ -68,6 +68,7 @@ def _worker(rank, world, port, kind, n_samples, n_grid, iters, q, env=None):
             extra = dict(chi=_big_chi, lambda_a=_BIG * w.lambda_a)
         if kind == "chain":
             extra["force_path"] = 3
+        extra["multi_gpu"] = (env or {}).get("TEST_MULTI_GPU", "shard")
         res = K.optimize(to_problem(w, iter_stop=iters, callback=cb, device=rank, **extra), method=K.Krotov, comm=comm)
         q.put((rank, hist["J_T"], hist["pulses"], hist["shard"], res.message, np.array(res.states), hist["ga"],
                hist["fallback"]))
@@ -81,7 +82,9 @@ def _worker(rank, world, port, kind, n_samples, n_grid, iters, q, env=None):
     ("c4", 8, 201, {"KROTOV_XCHG": "mbox"}), ("c4", 64, 101, {"KROTOV_NO_XACC": "1"}),
     ("c4", 8, 41, {"TEST_BIG_CHI": "1"}), ("c4", 8, 41, {"TEST_BIG_CHI": "1", "KROTOV_XCHG": "onehop"}),
     ("sm", 20, 21, {}), ("ss", 9, 21, {}), ("sm", 20, 21, {"KROTOV_NO_SWEEP_RANKS": "1"}),
-    ("chain", 40, 21, {}), ("chain", 40, 21, {"KROTOV_NO_SWEEP_RANKS": "1"})])
+    ("chain", 40, 21, {}), ("chain", 40, 21, {"KROTOV_NO_SWEEP_RANKS": "1"}),
+    ("c4", 8, 201, {"TEST_MULTI_GPU": "replicate"}), ("c4", 64, 101, {"TEST_MULTI_GPU": "replicate"}),
+    ("c4", 3, 101, {"TEST_MULTI_GPU": "auto"})])
 def test_two_ranks_match_single_gpu(kind, n_samples, n_grid, env):
     """kind c4: warp path (in-kernel exchange of the comm warps); kinds sm/ss: dense generators (d = 64: the cluster
     sweep, rank sums through the mailboxes from inside the sweep; with KROTOV_NO_SWEEP_RANKS the DMMA stream with the
@@ -108,7 +111,14 @@ def test_two_ranks_match_single_gpu(kind, n_samples, n_grid, env):
     (r0, J0, P0, s0, m0, st0, ga0, fb0), (r1, J1, P1, s1, m1, st1, ga1, fb1) = out
     assert m0 == m1 == "Reached maximum number of iterations"
     n_traj = 4 * n_samples if kind == "c4" else n_samples
-    assert s0 == (0, n_traj // 2) and s1 == (n_traj // 2, n_traj)
+    replicated = env.get("TEST_MULTI_GPU") in ("replicate", "auto")
+    if replicated:
+        # replicated forward sweep: every rank holds everything and must reproduce the one-GPU run bit for bit
+        assert s0 == s1 == (0, n_traj)
+        assert np.array_equal(P0, single["pulses"]) and J0 == list(single["J_T"]) and np.array_equal(st0, st1)
+        assert np.array_equal(st0, np.array(single["result"].states))
+    else:
+        assert s0 == (0, n_traj // 2) and s1 == (n_traj // 2, n_traj)
     # replicas must hold bit-identical pulses (every rank applies the same rank-ordered sum)
     assert np.array_equal(P0, P1) and J0 == J1 and np.array_equal(ga0, ga1)
     # and agree with the single-GPU run up to the summation order of the overlap sums

@@ -1030,7 +1030,7 @@ def test_emulated_ranks_match_one_rank_and_oracle(ranks, n_samples, n_grid, xchg
             seen.setdefault("ga", []).append(wrk.engine.g_a_all.copy())
             seen["info"] = wrk.engine.info()
 
-    got = run_product(w, 2, emulate_ranks=ranks, callback=cb)
+    got = run_product(w, 2, emulate_ranks=ranks, callback=cb, multi_gpu="shard")
     for allp, ga in zip(seen["all"], seen["ga"]):
         assert allp.shape[0] == ranks
         for r in range(1, ranks):  # replicas hold the same bits: same exact sum rounded once, same update
@@ -1065,7 +1065,7 @@ def test_emulated_ranks_fall_back_when_a_partial_does_not_fit(xchg, monkeypatch)
             fb.append(wrk.engine.info()["fallback_steps"])
             assert all(np.array_equal(p, wrk.engine.pulses_all[0]) for p in wrk.engine.pulses_all)
 
-    got = run_product(w, 2, emulate_ranks=2, callback=cb, chi=big_chi, lambda_a=big * w.lambda_a)
+    got = run_product(w, 2, emulate_ranks=2, callback=cb, chi=big_chi, lambda_a=big * w.lambda_a, multi_gpu="shard")
     assert min(fb) > 20  # most of the 40 steps carry sums beyond 2^28
     assert np.abs(np.array(got["J_T"]) - np.array(single["J_T"])).max() < 1e-12
     assert np.abs(got["pulses"] - single["pulses"]).max() < 1e-11
@@ -1111,8 +1111,10 @@ def test_nonlinear_amplitudes_ensemble_multi_cta_and_emulated_ranks():
     assert np.abs(np.array(got["g_a_int"]) - np.array(ref["g_a_int"])).max() <= 1e-11
     lin = run_product(W.c4_ensemble(n_samples=8, n_grid=201), 2)
     assert np.abs(got["pulses"] - lin["pulses"]).max() > 1e-4  # the amplitudes do change the optimisation
-    two = run_product(w, 2, emulate_ranks=2)
-    assert np.abs(two["pulses"] - got["pulses"]).max() < 1e-12 and np.abs(np.array(two["J_T"]) - np.array(got["J_T"])).max() < 1e-12
+    for mode in ("shard", "replicate"):
+        two = run_product(w, 2, emulate_ranks=2, multi_gpu=mode)
+        assert np.abs(two["pulses"] - got["pulses"]).max() < 1e-12
+        assert np.abs(np.array(two["J_T"]) - np.array(got["J_T"])).max() < 1e-12
 
 
 @pytest.mark.parametrize("kind", ["dense", "sparse_sweep", "sparse_stream", "reloaded_rows"])
@@ -1201,3 +1203,42 @@ def test_mid_size_dense_generator_with_many_trajectories_takes_the_ell_sweep():
     assert b["info"]["path"] == 2 and b["info"]["launches_last"] > 20
     assert np.abs(np.array(a["J_T"]) - np.array(b["J_T"])).max() < 1e-12
     assert np.abs(a["pulses"] - b["pulses"]).max() < 1e-12
+
+
+@pytest.mark.parametrize("ranks,n_samples,n_grid,functional", [(2, 8, 201, "sm"), (3, 7, 101, "ss"), (8, 32, 61, "sm"),
+                                                               (4, 2, 101, "re")])
+def test_emulated_ranks_replicated_forward_sweep_is_bit_identical(ranks, n_samples, n_grid, functional):
+    """Several ranks, every rank holding ALL trajectories (`multi_gpu="replicate"`, the default where the persistent
+    one-warp-per-trajectory kernel serves the problem): the backward sweep is sharded and every chi_k(t_n) written into
+    the chi trajectory of EVERY rank, one rank barrier, then the time-serial forward sweep on every rank -- no
+    exchange between the ranks per time step.  Every rank must reproduce the one-rank run BIT FOR BIT (same
+    per-trajectory arithmetic, same exact grid sum), including the stored chi trajectory."""
+    w = W.c4_ensemble(n_samples=n_samples, n_grid=n_grid)
+    w.functional = functional
+    seen = {}
+
+    def cb_single(wrk, it, eps_new, eps_old):
+        if it == 2:
+            seen["X1"] = wrk.bw_storage[w.N - 1].copy()
+
+    single = run_product(w, 2, callback=cb_single)
+
+    def cb(wrk, it, eps_new, eps_old):
+        if it >= 1:
+            seen.setdefault("all", []).append(wrk.engine.pulses_all.copy())
+            seen["info"] = wrk.engine.info()
+            seen["states_all"] = wrk.engine.states_all()
+        if it == 2:
+            seen["X"] = [e.storage(1, w.N - 1).T.copy() for e in wrk.engine.engines]
+
+    got = run_product(w, 2, emulate_ranks=ranks, callback=cb)  # auto -> replicate
+    assert seen["info"]["exchange"] == 5 and seen["info"]["ranks"] == ranks
+    for allp in seen["all"]:
+        for r in range(1, ranks):
+            assert np.array_equal(allp[r], allp[0])
+    assert np.array_equal(got["pulses"], single["pulses"]) and got["J_T"] == single["J_T"]
+    assert np.array_equal(np.array(got["g_a_int"]), np.array(single["g_a_int"]))
+    for st in seen["states_all"]:
+        assert np.array_equal(st, np.array(single["result"].states))
+    for X in seen["X"]:  # the last trajectory's chi was propagated by the LAST rank and written to every rank
+        assert np.array_equal(X, seen["X1"])
