@@ -375,7 +375,8 @@ def main():
             "iterations_per_s": steps / (dev_total_ms * 1e-3),
             "config": {"workload": f"C4 robust two-transmon CNOT ensemble: {n_samples} samples x 4 basis states = "
                                    f"{N} trajectories, d={d}, L={L}, N_T={N_T}, Chebyshev m={m}",
-                       "parallelism": f"trajectories sharded over {world} GPU(s)",
+                       "parallelism": (f"backward sweep sharded over {world} GPUs, forward sweep replicated on each"
+                                       if info.get("exchange") == 5 else f"trajectories sharded over {world} GPU(s)"),
                        "l2": "chi trajectory (%.0f MB per GPU) is larger than L2; no flush needed" % (info["hbm_bytes_state"] / 1e6),
                        "grid": [info["grid_blocks"], info["block_threads"]], "J_T_last": marks["J_T"],
                        **({"exchange": {1: "per time step, in-kernel: every CTA adds its fixed-point partial into its rank's "

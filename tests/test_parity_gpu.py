@@ -1205,8 +1205,8 @@ def test_mid_size_dense_generator_with_many_trajectories_takes_the_ell_sweep():
     assert np.abs(a["pulses"] - b["pulses"]).max() < 1e-12
 
 
-@pytest.mark.parametrize("ranks,n_samples,n_grid,functional", [(2, 8, 201, "sm"), (3, 7, 101, "ss"), (8, 32, 61, "sm"),
-                                                               (4, 2, 101, "re")])
+@pytest.mark.parametrize("ranks,n_samples,n_grid,functional", [(2, 8, 201, "sm"), (3, 7, 101, "ss"), (8, 4, 61, "sm"),
+                                                               (4, 2, 101, "re"), (2, 64, 41, "sm")])
 def test_emulated_ranks_replicated_forward_sweep_is_bit_identical(ranks, n_samples, n_grid, functional):
     """Several ranks, every rank holding ALL trajectories (`multi_gpu="replicate"`, the default where the persistent
     one-warp-per-trajectory kernel serves the problem): the backward sweep is sharded and every chi_k(t_n) written into
