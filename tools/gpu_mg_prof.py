@@ -17,9 +17,12 @@ comm = Comm(device=local)
 ns = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 w = W.c4_ensemble(n_samples=ns)
 ghz = 1.965
+mode = os.environ.get("MG_MODE", "shard")  # shard (per-step exchange) | replicate (replicated forward sweep)
 variants = [("hierarchical", {"KROTOV_XCHG": "hier"}), ("hierarchical, stores", {"KROTOV_XCHG": "hierst"}),
             ("one-hop", {"KROTOV_XCHG": "onehop"}), ("mailbox", {"KROTOV_XCHG": "mbox"})]
-if os.environ.get("MG_VARIANTS"):
+if mode == "replicate":
+    variants = [("replicated forward sweep", {})]
+if os.environ.get("MG_VARIANTS") and mode != "replicate":
     variants = [v for v in variants if v[1]["KROTOV_XCHG"] in os.environ["MG_VARIANTS"].split(",")]
 if os.environ.get("MG_WPC"):
     variants = [(n + " wpc=" + w, dict(e, KROTOV_WPC=w)) for w in os.environ["MG_WPC"].split(",") for n, e in variants]
@@ -36,7 +39,7 @@ for name, env in variants:
             out["info"] = info
             out["all"] = [wrk.engine.profile(c) for c in range(info["grid_blocks"])]
 
-    K.optimize(to_problem(w, iter_stop=4, callback=cb, device=local), method=K.Krotov, comm=comm)
+    K.optimize(to_problem(w, iter_stop=4, callback=cb, device=local, multi_gpu=mode), method=K.Krotov, comm=comm)
     comm.barrier()
     f = lambda v: v / ghz / 1e3 / w.N_T
     if rank != 0 and not os.environ.get("MG_ALL_RANKS"):
