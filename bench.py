@@ -317,6 +317,7 @@ def main():
         if it >= 1:
             info = wrk.engine.info()
             dev_ms.append(info["ms_last"])
+            marks.setdefault("rank_wait", []).append(round(info.get("ms_rank_wait", 0.0), 3))
             launches.append(info["launches_last"])
             marks["info"] = info
         if it == warmup:
@@ -341,7 +342,14 @@ def main():
     timed_ms = np.array(dev_ms[warmup:warmup + steps])
     dev_total_ms = float(timed_ms.sum())
     wall_s = marks["t1"] - marks["t0"]
+    per_rank = None
     if world > 1:
+        # per-rank record (device ms and host wall ms of every timed iteration, time spent at the rank barrier): the line
+        # reports the MAX over ranks, this shows where it comes from
+        mine = {"rank": rank, "dev_ms": [round(float(x), 2) for x in timed_ms],
+                "wall_ms": [round(1e3 * (b - a), 2) for a, b in zip(marks["wall"][warmup:warmup + steps], marks["wall"][warmup + 1:warmup + steps + 1])],
+                "timed_region_ms": round(1e3 * wall_s, 2), "J_T_last": marks["J_T"], "rank_wait_ms": marks.get("rank_wait", [])[warmup:warmup + steps]}
+        per_rank = comm.all_gather_object(mine)
         t = torch.tensor([dev_total_ms, wall_s], dtype=torch.float64, device="cuda")
         import torch.distributed as dist
 
@@ -379,6 +387,7 @@ def main():
                                        if info.get("exchange") == 5 else f"trajectories sharded over {world} GPU(s)"),
                        "l2": "chi trajectory (%.0f MB per GPU) is larger than L2; no flush needed" % (info["hbm_bytes_state"] / 1e6),
                        "grid": [info["grid_blocks"], info["block_threads"]], "J_T_last": marks["J_T"],
+                       **({"rank_barrier_wait_ms_last": round(info.get("ms_rank_wait", 0.0), 3)} if info.get("exchange") == 5 else {}),
                        **({"exchange": {1: "per time step, in-kernel: every CTA adds its fixed-point partial into its rank's "
                                            "accumulator; the add that completes a word forwards the rank sum with one add per "
                                            "rank over NVLink (hierarchical sum)",
@@ -415,6 +424,8 @@ def main():
                               "bound": "not the FP64 pipe: shared-memory crossbar (roofline_smem) in the sweeps, exchange "
                                        "latency between the time steps of the forward sweep"},
         }
+        if per_rank is not None:
+            line["per_rank"] = per_rank
         if world == 1 and not args.no_extra_configs and args.samples == 256:
             line["extra_configs"] = extra_configs(K, to_problem, peaks)
         if world == 1 and not args.no_cpu_baseline:

@@ -128,7 +128,9 @@ typedef struct {
     int64_t fallback_steps;  /* WARP path: time steps of the last krotov_iterate whose grid sum left the fixed-point
                                 range of the one-hop all-reduce and was redone with the gather protocol */
     int64_t graph_replays;   /* block paths: iterations served by replaying the captured CUDA graph since creation */
-    int64_t reserved[4];
+    double ms_rank_wait;     /* replicated forward sweep: time CTA 0 of this rank spent at the rank barrier behind the backward
+                                sweep in the last krotov_iterate (launch skew between the ranks + the slowest backward shard) */
+    int64_t reserved[3];
 } krotov_info;
 
 /* ---- lifetime ------------------------------------------------------------------------ */

@@ -62,7 +62,8 @@ struct Info
     hbm_bytes_state::Int64
     fallback_steps::Int64
     graph_replays::Int64
-    reserved::NTuple{4,Int64}
+    ms_rank_wait::Float64
+    reserved::NTuple{3,Int64}
 end
 
 mutable struct Handle

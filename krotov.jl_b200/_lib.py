@@ -57,7 +57,7 @@ class Info(C.Structure):
         ("sm_count", C.c_int32), ("exchange", C.c_int32),
         ("launches_total", C.c_int64), ("launches_last", C.c_int64), ("ms_last", C.c_double),
         ("ms_last_backward", C.c_double), ("hbm_bytes_state", C.c_int64), ("fallback_steps", C.c_int64),
-        ("graph_replays", C.c_int64), ("reserved", C.c_int64 * 4),
+        ("graph_replays", C.c_int64), ("ms_rank_wait", C.c_double), ("reserved", C.c_int64 * 3),
     ]
 
 

@@ -23,10 +23,15 @@ void add_warp_instances_wide64(KernelMap &t);   // 64 threads (rows) per traject
 void add_warp_instances_wide128(KernelMap &t);  // 128 threads per trajectory, 64 < d <= 128
 void add_warp_instances_emul(KernelMap &t);     // several ranks emulated by one launch (krotov_group_iterate)
 void add_warp2_instances(KernelMap &t);         // pair kernel: two trajectories of one generator per warp
+void add_warp_instances_rf(KernelMap &t);       // replicated forward sweep of several ranks (one trajectory per warp, d <= 32)
+void add_warp_instances_rf2(KernelMap &t);      // ... one / three controls, runtime L
+void add_warp_instances_rf_emul(KernelMap &t);  // the same with the ranks emulated by one launch
 
 #define KR_INST(W, LT, MT) t[KernelKey{W, LT, 32}] = (WarpKernel)krotov_warp_kernel<W, LT, MT>
 #define KR_INSTW(W, LT, MT, LPT) t[KernelKey{W, LT, LPT}] = (WarpKernel)krotov_warp_kernel<W, LT, MT, LPT>
 #define KR_INSTE(W, LT, MT) t[KernelKey{W, LT, 32}] = (WarpKernel)krotov_warp_kernel<W, LT, MT, 32, true>
+#define KR_INSTR(W, LT, MT) t[KernelKey{W, LT, 32}] = (WarpKernel)krotov_warp_kernel<W, LT, MT, 32, false, true>
+#define KR_INSTRE(W, LT, MT) t[KernelKey{W, LT, 32}] = (WarpKernel)krotov_warp_kernel<W, LT, MT, 32, true, true>
 #define KR_INST2(W, LT) t[KernelKey{W, LT, 32}] = (WarpKernel)krotov_warp2_kernel<W, LT>
 
 }  // namespace kr

@@ -115,6 +115,8 @@ struct krotov_handle_s {
     int max_ctas = 0;    // largest CTA count of a rank
     // replicated forward sweep (every rank holds all trajectories; backward sweep sharded, chi written to all ranks)
     bool rf = false;
+    double ms_rank_wait = 0.0;
+    int sm_clock_khz = 1965000;
     int bw_lo = 0, bw_hi = 0;
     bool rf_wanted = false;                       // krotov_problem.replicated_forward: d_X holds TWO chi trajectories
     size_t x_slab = 0;                            // elements of one chi trajectory
@@ -210,6 +212,25 @@ const std::map<KernelKey, WarpKernel> &kernel_emul_table() {
     static const std::map<KernelKey, WarpKernel> tab = [] {
         std::map<KernelKey, WarpKernel> t;
         kr::add_warp_instances_emul(t);
+        return t;
+    }();
+    return tab;
+}
+
+// instances with the replicated forward sweep of several ranks compiled in (regular / emulated ranks)
+const std::map<KernelKey, WarpKernel> &kernel_rf_table() {
+    static const std::map<KernelKey, WarpKernel> tab = [] {
+        std::map<KernelKey, WarpKernel> t;
+        kr::add_warp_instances_rf(t);
+        kr::add_warp_instances_rf2(t);
+        return t;
+    }();
+    return tab;
+}
+const std::map<KernelKey, WarpKernel> &kernel_rf_emul_table() {
+    static const std::map<KernelKey, WarpKernel> tab = [] {
+        std::map<KernelKey, WarpKernel> t;
+        kr::add_warp_instances_rf_emul(t);
         return t;
     }();
     return tab;
@@ -484,7 +505,8 @@ size_t warp_smem_bytes(const krotov_handle h) {
         return (size_t)h->wpc * (128 + 64) * 16 + (size_t)h->L * h->wpc * 32 * 8 + kr::kMaxCtrl * 8 +
                (size_t)kr::kMaxCtrl * 160 * 8;
     return (size_t)h->wpc * 2 * h->lpt * 16 + (size_t)h->wpc * h->tpw * h->lpt * 16 + (size_t)h->L * h->wpc * h->lpt * 8 +
-           kr::kMaxCtrl * 8 + (size_t)kr::kMaxCtrl * 160 * 8 + (size_t)h->wpc * h->lpt * 16;
+           kr::kMaxCtrl * 8 + (size_t)kr::kMaxCtrl * 160 * 8 + (size_t)h->wpc * h->lpt * 16 +
+           (h->rf_wanted ? (size_t)h->wpc * kr::kRfRing * 32 * 16 + (size_t)h->wpc * 2 * 4 + 16 : 0);  // forwarder rings
 }
 
 void fill_warp_params(krotov_handle h, int mode, kr::WarpParams &p) {
@@ -571,6 +593,9 @@ void fill_warp_params(krotov_handle h, int mode, kr::WarpParams &p) {
         p.X = p.Xr[h->rank];
         p.rf_count = (unsigned int *)h->d_rfcount.p;
         p.rf_iter = (unsigned long long)(h->iter_count + 1);
+        p.rf_pack = getenv("KROTOV_RF_PACK") ? (h->bw_hi - h->bw_lo + h->nCTA - 1) / h->nCTA : 0;
+        // forwarder warps (the value is their polling interval in ns); KROTOV_RF_DIRECT=1: producers store to all ranks
+        p.rf_fwd = (h->lpt == 32 && !getenv("KROTOV_RF_DIRECT")) ? (getenv("KROTOV_RF_SLEEP") ? std::max(1, atoi(getenv("KROTOV_RF_SLEEP"))) : 64) : 0;
         h->xchg_last = 5;
     }
     p.err_flag = (int *)h->d_err.p;
@@ -600,7 +625,7 @@ int launch_warp(krotov_handle h, int mode) {
         return KROTOV_OK;
     }
     KernelKey key{h->Wt, h->preg ? h->L : 0, h->pair ? 32 : h->lpt};
-    const auto &table = h->pair ? kernel2_table() : kernel_table();
+    const auto &table = h->pair ? kernel2_table() : h->rf ? kernel_rf_table() : kernel_table();
     auto it = table.find(key);
     if (it == table.end()) return fail(h, KROTOV_ERR_UNSUPPORTED, "no kernel instance for this (W, L)");
     WarpKernel fn = it->second;
@@ -618,10 +643,14 @@ int launch_warp(krotov_handle h, int mode) {
 }
 
 int check_err_flag(krotov_handle h) {
-    int flags[2] = {0, 0};  // [0] exchange timed out, [1] time steps redone with the gather protocol
+    int flags[4] = {0, 0, 0, 0};  // [0] exchange timed out, [1] time steps redone with the gather protocol,
+                                  // [2..3] SM cycles CTA 0 waited at the rank barrier (replicated forward sweep)
     KR_CUDA(h, cudaMemcpy(flags, h->d_err.p, sizeof(flags), cudaMemcpyDeviceToHost));
     const int flag = flags[0];
     h->fallback_steps = flags[1];
+    long long wait_cycles;
+    memcpy(&wait_cycles, flags + 2, 8);
+    h->ms_rank_wait = h->rf ? (double)wait_cycles / (double)h->sm_clock_khz : 0.0;
     if (flags[1]) cudaMemset((int *)h->d_err.p + 1, 0, sizeof(int));
     if (flag) {
         cudaMemset(h->d_err.p, 0, sizeof(int));
@@ -709,6 +738,10 @@ int krotov_create(const krotov_problem *pb, krotov_handle *out) {
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, h->device);
     h->sm_count = prop.multiProcessorCount;
+    {
+        int khz = 0;
+        if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device) == cudaSuccess && khz > 0) h->sm_clock_khz = khz;
+    }
     if (prop.major < 10) return bail(fail(h, KROTOV_ERR_UNSUPPORTED, "libkrotov_cuda is built for sm_100a only"));
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess)
@@ -969,6 +1002,7 @@ int krotov_get_info(krotov_handle h, krotov_info *out) {
     out->ms_last_backward = h->ms_last_bw;
     out->hbm_bytes_state = (int64_t)h->d_X.bytes;
     out->fallback_steps = h->fallback_steps;
+    out->ms_rank_wait = h->ms_rank_wait;
     if (h->dense) kr::dense_info(h->dense, out);
     return KROTOV_OK;
 }
@@ -1222,8 +1256,8 @@ int krotov_iterate(krotov_handle h, const double *guess_pulses, double *new_puls
 // Replicated forward sweep: possible when this handle holds ALL trajectories of the problem and runs the persistent
 // kernel with one trajectory per warp (KROTOV_NO_RF=1 keeps the sharded forward sweep with its per-step exchange).
 static bool rf_eligible(krotov_handle h) {
-    return h->rf_wanted && h->path == KROTOV_PATH_WARP && h->N == h->N_global && h->tpw == 1 && !h->pair &&
-           !getenv("KROTOV_NO_RF");
+    return h->rf_wanted && h->path == KROTOV_PATH_WARP && h->N == h->N_global && h->tpw == 1 && !h->pair && h->lpt == 32 &&
+           kernel_rf_table().count(KernelKey{h->Wt, h->preg ? h->L : 0, 32}) && !getenv("KROTOV_NO_RF");
 }
 
 // this rank's share of the backward sweep: a contiguous block cut at generator boundaries where that is possible
@@ -1282,6 +1316,11 @@ int krotov_group_connect(krotov_handle *hs, int world) {
     if (total > hs[0]->sm_count) return fail(hs[0], KROTOV_ERR_UNSUPPORTED, "krotov_group_connect: more CTAs than SMs");
     bool rf_all = world > 1;
     for (int r = 0; r < world; ++r) rf_all = rf_all && rf_eligible(hs[r]) && hs[r]->N == hs[0]->N;
+    rf_all = rf_all && kernel_rf_emul_table().count(KernelKey{hs[0]->Wt, hs[0]->preg ? hs[0]->L : 0, hs[0]->lpt});
+    if (!rf_all && world > 1)
+        for (int r = 0; r < world; ++r)
+            if (hs[r]->rf_wanted)  // handles that hold ALL trajectories must never run the sharded exchange
+                return fail(hs[r], KROTOV_ERR_UNSUPPORTED, "replicated_forward was requested but cannot be used by this group");
     for (int r = 0; r < world; ++r) {
         krotov_handle h = hs[r];
         h->rank = r;
@@ -1327,8 +1366,9 @@ int krotov_group_iterate(krotov_handle *hs, int world, const double *guess_pulse
     p0.emul = (const kr::WarpParams *)h0->d_emul.p;
     p0.emul_ranks = world;
     p0.wpc = h0->wpc;
-    auto it = kernel_emul_table().find(KernelKey{h0->Wt, h0->preg ? h0->L : 0, h0->lpt});
-    if (it == kernel_emul_table().end())
+    const auto &etab = h0->rf ? kernel_rf_emul_table() : kernel_emul_table();
+    auto it = etab.find(KernelKey{h0->Wt, h0->preg ? h0->L : 0, h0->lpt});
+    if (it == etab.end())
         return fail(h0, KROTOV_ERR_UNSUPPORTED, "no emulated-ranks instance of this kernel (W, L)");
     size_t smem = 0;
     for (int r = 0; r < world; ++r) smem = std::max(smem, warp_smem_bytes(hs[r]));

@@ -110,7 +110,23 @@ struct WarpParams {
     unsigned long long *rf_flag[kMaxRanks]; // [world] per rank: "rank r has finished its backward sweep of iteration i"
     unsigned int *rf_count;                 // arrivals of this rank's trajectory warps (zeroed per launch)
     unsigned long long rf_iter;
+    // forwarder warps: the trajectory warps of a CTA that have no trajectory in the backward shard take the chi values of
+    // the producing warps out of a shared-memory ring and store them to every rank, so the producers' serial chain carries
+    // no peer store at all (0 = every producer stores to all ranks itself)
+    int rf_fwd;
+    int rf_pack;  // producers per CTA when the backward shard is packed (warps of a CTA take CONSECUTIVE trajectories); 0 = spread
 };
+
+constexpr int kRfRing = 8;  // ring slots per producing warp (one chi record of 32 entries each)
+
+__device__ __forceinline__ int ld_acquire_cta_shared(const int *a) {
+    int v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(a)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_cta_shared(int *a, const int v) {
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(a)), "r"(v) : "memory");
+}
 
 template <bool EMUL>
 __device__ __forceinline__ const WarpParams &select_params(const WarpParams &p0) {
@@ -880,7 +896,127 @@ __device__ __forceinline__ void comm_warp_run(const WarpParams &p, const int cta
     }
 }
 
-template <int W, int LT /*0 = runtime L, rows reloaded from L1/L2 per use*/, int MAXTHREADS, int LPT = 32, bool EMUL = false>
+// ---- replicated forward sweep: the cold parts, out of line so that the sweeps of the RF instances keep the code of the
+// regular ones (the parameter block is read through a generic pointer here: slow loads, off every critical path)
+// Forwarder warp: takes the chi records of its producing warps out of their rings and stores them to every rank.
+static __device__ __noinline__ void rf_forward_records(const WarpParams *pp, const double2 *rf_ring, int *rf_prog, const int cta,
+                                                       const int warp, const int lane, const int n_prod, const int n_fwd) {
+    const WarpParams &p = *pp;
+    const int N_T = p.N_T, wpc = p.wpc, world = p.rf_world, nCTA = p.nCTA, bw_lo = p.bw_lo;
+    const unsigned sleep_ns = (unsigned)p.rf_fwd;
+    const long long timeout = p.timeout_cycles;
+    double2 *Xr[kMaxRanks];
+#pragma unroll
+    for (int r = 0; r < kMaxRanks; ++r) Xr[r] = p.Xr[r];
+    const long long t0 = clock64();
+    bool dead = false;
+    for (int i = 0; i <= N_T && !dead; ++i) {
+        for (int w = warp - n_prod; w < n_prod; w += n_fwd) {
+            if (lane == 0) {
+                int spins = 0;
+                while (ld_acquire_cta_shared(rf_prog + w) <= i) {
+                    __nanosleep(sleep_ns);
+                    if ((++spins & 1023) == 0 && (clock64() - t0 > timeout || *(volatile int *)p.err_flag)) {
+                        atomicExch(p.err_flag, 1);
+                        dead = true;
+                        break;
+                    }
+                }
+            }
+            dead = __shfl_sync(0xffffffffu, dead, 0);
+            if (dead) break;
+            const double2 v = rf_ring[((size_t)w * kRfRing + (i % kRfRing)) * 32 + lane];
+            __syncwarp();
+            if (lane == 0) st_release_cta_shared(rf_prog + wpc + w, i + 1);
+            const size_t off = ((size_t)(bw_lo + (p.rf_pack ? cta * p.rf_pack + w : w * nCTA + cta)) * (N_T + 1) + (N_T - i)) * 32 + lane;
+#pragma unroll
+            for (int r = 0; r < kMaxRanks; ++r)
+                if (r < world) Xr[r][off] = v;  // peers over NVLink
+        }
+    }
+}
+
+// Rank barrier behind the backward sweep: every rank's chi trajectory is complete on every rank before anybody reads it.
+// Writers: fence -> arrival (gpu-scope release); warp 0 of CTA 0 collects the arrivals of this rank, fences at system
+// scope and raises this rank's flag on every rank; everybody waits for all flags in its own memory.
+template <int LPT>
+static __device__ __noinline__ void rf_rank_barrier(const WarpParams *pp, const int cta, const int warp, const int lane,
+                                                    const int gbar) {
+    const WarpParams &p = *pp;
+    const int nthr = p.wpc * LPT;  // the trajectory threads of the CTA; warps without work sleep in this hardware barrier
+    __threadfence_system();
+    bar_sync(15, nthr);
+    if (warp == 0 && lane == 0) {
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.rf_count) : "memory");
+        const long long t0 = clock64();
+        if (cta == 0) {
+            const unsigned total = (unsigned)p.nCTA;
+            unsigned seen;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.rf_count) : "memory");
+            } while (seen < total && clock64() - t0 < p.timeout_cycles);
+            __threadfence_system();
+            for (int r = 0; r < p.rf_world; ++r)
+                asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p.rf_flag[r] + p.rf_rank), "l"(p.rf_iter) : "memory");
+        }
+        for (int r = 0; r < p.rf_world; ++r) {
+            unsigned long long f;
+            do {
+                asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(p.rf_flag[p.rf_rank] + r) : "memory");
+                if (clock64() - t0 > p.timeout_cycles || *(volatile int *)p.err_flag) {
+                    atomicExch(p.err_flag, 1);
+                    break;
+                }
+            } while (f < p.rf_iter);
+        }
+        __threadfence_system();
+        if (cta == 0) *reinterpret_cast<long long *>(p.err_flag + 2) = clock64() - t0;  // krotov_info.ms_rank_wait
+    }
+    bar_sync(15, nthr);
+}
+
+// Producer side of the replicated forward sweep's backward shard (RF instances only; empty otherwise).
+template <bool RF>
+struct RfProducer {};
+template <>
+struct RfProducer<true> {
+    double2 *v0, *ring;
+    int *prog, *cons;
+    size_t xoff;
+    int item, consumed;
+    bool use_fwd, rf;
+    __device__ __forceinline__ void init(double2 *plain, double2 *ring_, int *prog_, int *cons_, size_t xoff_, bool use_fwd_,
+                                         bool rf_) {
+        v0 = plain; ring = ring_; prog = prog_; cons = cons_; xoff = xoff_; item = 0; consumed = 0; use_fwd = use_fwd_; rf = rf_;
+    }
+    __device__ __forceinline__ void peek() {
+        if (use_fwd) consumed = ld_acquire_cta_shared(cons);
+    }
+    template <int LPT>
+    __device__ __forceinline__ void put(const WarpParams &p, const int slot, const double2 v, const int lane, const int gbar) {
+        if (use_fwd) {
+            while (item - consumed >= kRfRing && *(volatile int *)p.err_flag == 0) consumed = ld_acquire_cta_shared(cons);
+            v0 = ring + (item % kRfRing) * 32;
+            v0[lane] = v;
+            __syncwarp();
+            ++item;
+            if (lane == 0) st_release_cta_shared(prog, item);
+        } else {
+            v0[lane] = v;
+            grp_sync<LPT>(gbar);
+            if (rf) {
+                for (int r = 0; r < p.rf_world; ++r) p.Xr[r][xoff + (size_t)slot * LPT] = v;  // peers over NVLink
+            } else {
+                p.X[xoff + (size_t)slot * LPT] = v;
+            }
+        }
+    }
+};
+
+// RF: instance with the replicated forward sweep of several ranks compiled in (sharded backward sweep, forwarder warps, rank
+// barrier); the regular instances carry none of it (at 254 registers per thread every extra live value costs the sweeps).
+template <int W, int LT /*0 = runtime L, rows reloaded from L1/L2 per use*/, int MAXTHREADS, int LPT = 32, bool EMUL = false,
+          bool RF = false>
 __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid_constant__ WarpParams p0) {
     const WarpParams &p = select_params<EMUL>(p0);
     const int cta = EMUL ? (int)blockIdx.x - p.cta_base : (int)blockIdx.x;
@@ -902,8 +1038,15 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
     double *eps_s = red + (size_t)L * wpc * LPT;                  // [kMaxCtrl]
     double *gbuf = eps_s + kMaxCtrl;                              // [kMaxCtrl * 160] reducer scratch (CTA 0)
     double2 *chibufs = reinterpret_cast<double2 *>(gbuf + kMaxCtrl * 160);  // [wpc][LPT] chi(t_{n+1}) for the precompute
+    double2 *rf_ring = chibufs + (size_t)wpc * LPT;               // [wpc][kRfRing][32]  (only with p.rf_fwd)
+    int *rf_prog = reinterpret_cast<int *>(rf_ring + (size_t)wpc * kRfRing * 32);  // [wpc] items produced, [wpc] consumed
     const int nthr_all = wpc * LPT + 32;
     const int N_T = p.N_T;
+    const bool rf_fwd = RF && LPT == 32 && p.rf_world > 1 && p.rf_fwd != 0 && p.mode == 1;
+    if (rf_fwd) {  // (uniform over the CTA)
+        if ((int)threadIdx.x < 2 * wpc) rf_prog[threadIdx.x] = 0;
+        __syncthreads();
+    }
 
     if (is_comm) {
         __shared__ __align__(16) WarpParams p_sh;
@@ -929,12 +1072,21 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
     const long long t_begin = clock64();
     long long t_wait_b = 0, t_overlap = 0, t_step = 0;
     // ================================================================ backward sweep
-    const bool rf = p.rf_world > 1;
+    const bool rf = RF && p.rf_world > 1;
+    // replicated forward sweep: warps [0, n_prod) of this CTA propagate a trajectory of the backward shard, the others
+    // forward the chi records to all ranks
+    const int n_prod = !rf ? 0
+                       : p.rf_pack ? min(p.rf_pack, max(0, p.bw_hi - p.bw_lo - cta * p.rf_pack))
+                                   : min(wpc, max(0, (p.bw_hi - p.bw_lo - cta + p.nCTA - 1) / p.nCTA));
+    const int n_fwd = wpc - n_prod;
+    const bool use_fwd = rf_fwd && n_prod > 0 && n_fwd > 0;
+    if constexpr (RF)
+        if (p.mode == 1 && use_fwd && warp >= n_prod) rf_forward_records(&p, rf_ring, rf_prog, cta, warp, lane, n_prod, n_fwd);
     if (p.mode == 1) {
         for (int t = 0; t < tpw; ++t) {
             int k = kbase + t;
-            if (rf) {  // (tpw == 1) this rank's backward shard, spread over the CTAs: one trajectory per SM first
-                const int tl = warp * p.nCTA + cta;
+            if constexpr (RF) if (rf) {  // (tpw == 1) this rank's backward shard, spread over the CTAs: one trajectory per SM first
+                const int tl = p.rf_pack ? (warp < p.rf_pack ? cta * p.rf_pack + warp : p.N) : warp * p.nCTA + cta;
                 k = (tl < p.bw_hi - p.bw_lo) ? p.bw_lo + tl : p.N;
             }
             if (k >= p.N) break;
@@ -952,17 +1104,21 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
                 const double2 tg = p.target[(size_t)k * LPT + lane];
                 chi = make_double2(c.x * tg.x - c.y * tg.y, c.x * tg.y + c.y * tg.x);
             }
-            const size_t xoff = (size_t)k * (N_T + 1) * LPT + lane;
-            auto store_chi = [&](const int slot, const double2 v) {
-                if (!rf) {
-                    p.X[xoff + (size_t)slot * LPT] = v;
-                } else {
-                    for (int r = 0; r < p.rf_world; ++r) p.Xr[r][xoff + (size_t)slot * LPT] = v;  // peers over NVLink
-                }
-            };
-            store_chi(N_T, chi);
-            mypsi[t * LPT + lane] = chi;
-            grp_sync<LPT>(gbar);
+            double2 *Xk = p.X + (size_t)k * (N_T + 1) * LPT;
+            // RF instances: the record goes to every rank (peer stores over NVLink) -- or, with forwarder warps, into this
+            // warp's ring slot (which doubles as the next step's v_0 buffer), published with one release store; a
+            // forwarder warp then stores it to every rank.  (Kept in a type that is EMPTY in the regular instances: a mere
+            // unused lambda here changed their register allocation and cost the forward sweep 2 %.)
+            RfProducer<RF> rfp;
+            if constexpr (RF) rfp.init(mypsi + t * LPT, rf_ring + (size_t)warp * kRfRing * 32, rf_prog + warp, rf_prog + wpc + warp,
+                                       (size_t)k * (N_T + 1) * LPT + lane, use_fwd, rf);
+            if constexpr (RF) {
+                rfp.template put<LPT>(p, N_T, chi, lane, gbar);
+            } else {
+                Xk[(size_t)N_T * LPT + lane] = chi;
+                mypsi[t * LPT + lane] = chi;
+                grp_sync<LPT>(gbar);
+            }
             StepMeta meta = load_meta(p.dtc_b, p.m_b, p.phase_b, p.coef_b, p.ndtc_b, p.mmax_b, gi, N_T - 1);
             double e_cur[kMaxCtrl];
 #pragma unroll
@@ -998,48 +1154,26 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
                         }
                     }
                 }
-                chi = cheby_step<W, LPT>(chi, g, col, mypsi + t * LPT, bufA, bufB, meta.a, meta.m, meta.phase, lane, gbar);
+                if constexpr (RF) {
+                    rfp.peek();  // (consumer's progress: used when the next record is put)
+                    chi = cheby_step<W, LPT>(chi, g, col, rfp.v0, bufA, bufB, meta.a, meta.m, meta.phase, lane, gbar);
+                } else {
+                    chi = cheby_step<W, LPT>(chi, g, col, mypsi + t * LPT, bufA, bufB, meta.a, meta.m, meta.phase, lane, gbar);
+                }
                 meta = meta_next;
 #pragma unroll
                 for (int l = 0; l < kMaxCtrl; ++l) e_cur[l] = e_next[l];
-                mypsi[t * LPT + lane] = chi;
-                grp_sync<LPT>(gbar);
-                store_chi(n, chi);
+                if constexpr (RF) {
+                    rfp.template put<LPT>(p, n, chi, lane, gbar);
+                } else {
+                    mypsi[t * LPT + lane] = chi;
+                    grp_sync<LPT>(gbar);
+                    Xk[(size_t)n * LPT + lane] = chi;
+                }
             }
         }
-        if (rf) {
-            // ---- rank barrier: every rank's chi trajectory is complete on every rank before anybody reads it.
-            // writers: fence -> arrival (gpu-scope release); warp 0 of CTA 0 collects the arrivals of this rank, fences at
-            // system scope and raises this rank's flag on every rank; everybody waits for all flags in its own memory.
-            __threadfence_system();
-            grp_sync<LPT>(gbar);
-            if (lane == 0 && (LPT == 32 || (threadIdx.x % LPT) == 0)) {
-                asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.rf_count) : "memory");
-                const long long t0 = clock64();
-                if (cta == 0 && warp == 0) {
-                    const unsigned total = (unsigned)(p.nCTA * p.wpc);
-                    unsigned seen;
-                    do {
-                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.rf_count) : "memory");
-                    } while (seen < total && clock64() - t0 < p.timeout_cycles);
-                    __threadfence_system();
-                    for (int r = 0; r < p.rf_world; ++r)
-                        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p.rf_flag[r] + p.rf_rank), "l"(p.rf_iter) : "memory");
-                }
-                for (int r = 0; r < p.rf_world; ++r) {
-                    unsigned long long f;
-                    do {
-                        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(p.rf_flag[p.rf_rank] + r) : "memory");
-                        if (clock64() - t0 > p.timeout_cycles || *(volatile int *)p.err_flag) {
-                            atomicExch(p.err_flag, 1);
-                            break;
-                        }
-                    } while (f < p.rf_iter);
-                }
-                __threadfence_system();
-            }
-            grp_sync<LPT>(gbar);
-        }
+        if constexpr (RF)
+            if (rf) rf_rank_barrier<LPT>(&p, cta, warp, lane, gbar);
     }
 
     const long long t_bw_end = clock64();
@@ -1066,7 +1200,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
     const double inv_s0 = (k0 < p.N) ? p.inv_s_f[g0] : 0.0;
     StepMeta fmeta = load_meta(p.dtc_f, p.m_f, p.phase_f, p.coef_f, p.ndtc_f, p.mmax_f, g0, 0);
     double2 chi_next = make_double2(0.0, 0.0);
-    if (p.mode == 1 && k0 < p.N) chi_next = __ldcg(&p.X[(size_t)k0 * (N_T + 1) * LPT + lane]);
+    if (p.mode == 1 && k0 < p.N) chi_next = p.X[(size_t)k0 * (N_T + 1) * LPT + lane];
     // FAST: register-resident rows, one trajectory per warp, Hermitian control terms.  Then
     //   Im<chi|mu_l|psi> = -(1/s) Re <P_l chi|psi>   (P_l = -i s mu_l is anti-Hermitian)
     // so xi_l = P_l chi(t_n) can be formed BEFORE psi(t_n) exists, and the overlap on the critical path is a
@@ -1109,7 +1243,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
                 const int gi = (t == 0) ? g0 : p.gen_of_traj[k];
                 const double inv_s = (t == 0) ? inv_s0 : p.inv_s_f[gi];
                 const double2 psi = (tpw == 1) ? psi_reg : mypsi[t * LPT + lane];
-                const double2 chi = (t == 0) ? chi_next : __ldcg(&p.X[((size_t)k * (N_T + 1) + n) * LPT + lane]);
+                const double2 chi = (t == 0) ? chi_next : p.X[((size_t)k * (N_T + 1) + n) * LPT + lane];
                 if (PREG) {
 #pragma unroll
                     for (int l = 0; l < NT - 1; ++l) {
@@ -1133,7 +1267,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
             bar_arrive(1, nthr_all);  // barrier A
             const long long w0 = clock64();
             t_overlap += w0 - ts0;
-            if (n + 1 < N_T && k0 < p.N) chi_next = __ldcg(&p.X[((size_t)k0 * (N_T + 1) + n + 1) * LPT + lane]);
+            if (n + 1 < N_T && k0 < p.N) chi_next = p.X[((size_t)k0 * (N_T + 1) + n + 1) * LPT + lane];
             if (PREG && FAST && k0 < p.N) {
                 // ---- idle window: everything for this and the next step that does not depend on eps_n
 #pragma unroll

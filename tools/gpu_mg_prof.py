@@ -46,7 +46,7 @@ for name, env in variants:
         for r in range(world):
             comm.barrier()
         continue
-    lines = [f"[rank {rank}] {name}: exchange={out['info'].get('exchange')} grid={out['info']['grid_blocks']}x{out['info']['block_threads']} ms={['%.2f' % m for m in out['ms']]} fallback={out['info'].get('fallback_steps')}"]
+    lines = [f"[rank {rank}] {name}: exchange={out['info'].get('exchange')} grid={out['info']['grid_blocks']}x{out['info']['block_threads']} ms={['%.2f' % m for m in out['ms']]} fallback={out['info'].get('fallback_steps')} rank_barrier_wait_ms={out['info'].get('ms_rank_wait', 0.0):.3f}"]
     for key in ["backward", "forward", "overlap", "wait_pulse", "fw_step_total", "comm_wait_partials", "comm_reduce", "comm_gather"]:
         vals = np.array([f(a[key]) for a in out["all"]])
         lines.append(f"      {key:18s} cta0={vals[0]:.3f} all: min={vals.min():.3f} mean={vals.mean():.3f} max={vals.max():.3f} us/step")
