@@ -103,7 +103,8 @@ struct krotov_handle_s {
     std::vector<char> slot_valid;  // [Wt][32] slot holds a real matrix entry (i, cols[s][i])
     int wpc = 1, tpw = 1, nCTA = 1;
     DevBuf d_cols, d_Pf, d_Pb, d_inv_s, d_gen, d_dt, d_alpha, d_eps_old, d_eps_new, d_ga, d_X, d_Phi, d_psi0,
-        d_target, d_chiT, d_chicoef, d_psif, d_tau, d_R, d_err, d_weight, d_prof, d_Tf, d_Tb, d_acc;
+        d_target, d_chiT, d_chicoef, d_psif, d_tau, d_R, d_err, d_weight, d_prof, d_Tf, d_Tb, d_acc,
+        d_rawf, d_rawb, d_rowscale;  // unscaled generator rows of both directions + per-generator (fy, beta): rows are scaled on the device
     DevBuf d_mbox[2];
     ChebyTables cheb[2];
     bool chiT_valid = false, chicoef_valid = false, swept = false;
@@ -374,6 +375,55 @@ void build_rows(krotov_handle h, int dir, std::vector<cplx> &out) {
         for (int t = 0; t < nt; ++t) pool.emplace_back(work, (h->n_gen * t) / nt, (h->n_gen * (t + 1)) / nt);
         for (auto &th : pool) th.join();
     }
+}
+
+// The same rows WITHOUT the Chebyshev scaling (entry values as build_rows picks them; diagonal in the last slot), uploaded
+// once per direction at krotov_create.  krotov_set_cheby then forms P_t = f (H_t - beta delta_t0) on the device from the
+// per-generator numbers (fy, beta) -- 2 n_gen doubles instead of building and uploading all rows on the host (C4: 2.75 MB
+// and 1.0-1.5 ms per direction and spectral-range event).  Same arithmetic as build_rows: one product per component.
+void build_raw_rows(krotov_handle h, int dir, std::vector<cplx> &out) {
+    const int d = h->d, L = h->L, Wt = h->Wt, lpt = h->lpt;
+    out.assign((size_t)h->n_gen * (1 + L) * (Wt + 1) * lpt, cplx(0, 0));
+    const bool fw = (dir == KROTOV_FORWARD);
+    for (int g = 0; g < h->n_gen; ++g)
+        for (int t = 0; t <= L; ++t) {
+            cplx *row = &out[((size_t)g * (1 + L) + t) * (Wt + 1) * lpt];
+            const cplx *H = &h->Hdense[(((size_t)g * (1 + L) + t) * d) * d];
+            for (int sl = 0; sl < Wt; ++sl)
+                for (int i = 0; i < d; ++i) {
+                    if (!h->slot_valid[(size_t)sl * lpt + i]) continue;
+                    const int j = h->cols[(size_t)sl * lpt + i];
+                    row[(size_t)sl * lpt + i] = fw ? H[(size_t)i * d + j] : std::conj(H[(size_t)j * d + i]);
+                }
+            for (int i = 0; i < d; ++i) {
+                const cplx hv = H[(size_t)i * d + i];
+                row[(size_t)Wt * lpt + i] = cplx(hv.real(), fw ? hv.imag() : -hv.imag());
+            }
+        }
+}
+
+// P[g][t][slot][lane] = (0, fy_g) * (raw - beta_g on the diagonal of term 0); rows beyond d stay zero
+__global__ void scale_rows_kernel(const double2 *__restrict__ raw, const double2 *__restrict__ fy_beta, double2 *__restrict__ out,
+                                  const int n_terms, const int Wt, const int lpt, const int d, const size_t total) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int lane = (int)(idx % lpt);
+    const int sl = (int)((idx / lpt) % (Wt + 1));
+    const size_t gt = idx / ((size_t)lpt * (Wt + 1));
+    const int t = (int)(gt % n_terms);
+    const int g = (int)(gt / n_terms);
+    const double2 v = raw[idx];
+    const double2 fb = fy_beta[g];
+    double2 o = make_double2(0.0, 0.0);
+    if (sl == Wt) {
+        if (lane < d) {
+            const double re = v.x - (t == 0 ? fb.y : 0.0);
+            o = make_double2(__dmul_rn(-fb.x, v.y), __dmul_rn(fb.x, re));
+        }
+    } else if (v.x != 0.0 || v.y != 0.0) {
+        o = make_double2(__dmul_rn(-fb.x, v.y), __dmul_rn(fb.x, v.x));
+    }
+    out[idx] = o;
 }
 
 // dense prepared terms of one direction for the tiny kernel: [g][1+L][d*d] row-major, same numbers as build_rows
@@ -682,7 +732,8 @@ int krotov_destroy(krotov_handle h) {
                       &h->d_eps_old, &h->d_eps_new, &h->d_ga, &h->d_X, &h->d_Phi, &h->d_psi0, &h->d_target,
                       &h->d_chiT, &h->d_chicoef, &h->d_psif, &h->d_tau, &h->d_R, &h->d_err, &h->d_weight, &h->d_prof,
                       &h->d_mbox[0], &h->d_mbox[1], &h->d_emul,
-                      &h->d_amp_poly, &h->d_amp_shape, &h->d_amp_old, &h->d_amp_dfac, &h->d_amp_new, &h->d_rfcount};
+                      &h->d_amp_poly, &h->d_amp_shape, &h->d_amp_old, &h->d_amp_dfac, &h->d_amp_new, &h->d_rfcount,
+                      &h->d_rawf, &h->d_rawb, &h->d_rowscale};
     for (DevBuf *b : bufs) b->release();
     for (int dir = 0; dir < 2; ++dir) {
         h->cheb[dir].coef.release();
@@ -916,6 +967,13 @@ int krotov_create(const krotov_problem *pb, krotov_handle *out) {
     if (path == KROTOV_PATH_WARP) {
         if (!pattern_built && (rc = build_pattern(h))) return bail(rc);
         if ((rc = upload(h, h->d_cols, h->cols))) return bail(rc);
+        {
+            std::vector<cplx> raw;
+            build_raw_rows(h, KROTOV_FORWARD, raw);
+            if ((rc = upload(h, h->d_rawf, raw))) return bail(rc);
+            build_raw_rows(h, KROTOV_BACKWARD, raw);
+            if ((rc = upload(h, h->d_rawb, raw))) return bail(rc);
+        }
         choose_launch(h);
         h->tiny = d >= 2 && d <= 4 && N <= 32 && tiny_kernel_for(d, L) != nullptr && !getenv("KROTOV_NO_TINY");
         // padded state arrays [N][32]
@@ -1055,9 +1113,30 @@ int krotov_set_cheby(krotov_handle h, int direction, int n_dt_class, const int32
     tr.lap("tables uploaded");
     if (h->path == KROTOV_PATH_WARP) {
         std::vector<cplx> rows;
-        build_rows(h, direction, rows);
-        tr.lap("rows built");
-        if ((rc = upload(h, direction == KROTOV_FORWARD ? h->d_Pf : h->d_Pb, rows))) return rc;
+        DevBuf &dP = direction == KROTOV_FORWARD ? h->d_Pf : h->d_Pb;
+        const DevBuf &raw = direction == KROTOV_FORWARD ? h->d_rawf : h->d_rawb;
+        if (raw.p && !getenv("KROTOV_HOST_ROWS")) {
+            // rows scaled on the device from the unscaled rows uploaded at krotov_create
+            std::vector<double> fb((size_t)2 * h->n_gen);
+            for (int g = 0; g < h->n_gen; ++g) {
+                const double sc = 4.0 / Delta[g];
+                fb[2 * g] = direction == KROTOV_FORWARD ? -sc : sc;
+                fb[2 * g + 1] = Delta[g] / 2 + E_min[g];
+            }
+            if ((rc = dev_alloc(h, h->d_rowscale, fb.size() * 8))) return rc;
+            KR_CUDA(h, cudaMemcpyAsync(h->d_rowscale.p, fb.data(), fb.size() * 8, cudaMemcpyHostToDevice, h->stream));
+            const size_t total = (size_t)h->n_gen * (1 + h->L) * (h->Wt + 1) * h->lpt;
+            if ((rc = dev_alloc(h, dP, total * 16))) return rc;
+            scale_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(
+                (const double2 *)raw.p, (const double2 *)h->d_rowscale.p, (double2 *)dP.p, 1 + h->L, h->Wt, h->lpt, h->d, total);
+            KR_CUDA(h, cudaStreamSynchronize(h->stream));  // fb is a local; the next call may rewrite d_rowscale
+            h->launches_total += 1;
+            tr.lap("rows scaled on the device");
+        } else {
+            build_rows(h, direction, rows);
+            tr.lap("rows built");
+            if ((rc = upload(h, dP, rows))) return rc;
+        }
         if (direction == KROTOV_FORWARD) {
             std::vector<double> inv_s(h->n_gen);
             for (int g = 0; g < h->n_gen; ++g) inv_s[g] = Delta[g] / 4.0;

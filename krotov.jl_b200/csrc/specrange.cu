@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <complex>
+#include <cstdlib>
 #include <thread>
 #include <vector>
 
@@ -170,7 +171,19 @@ static void extremes_of(int d, std::vector<double> &ar, std::vector<double> &ai,
 
 template <typename F>
 static void run_threads(int n_items, int n_threads, F &&work) {
-    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    // default: all hardware threads -- shared fairly when several ranks of one job run on this host (torchrun exports
+    // LOCAL_WORLD_SIZE; with the replicated forward sweep every rank solves the same envelopes at the same moment, and
+    // 8 x 32 threads on 32 cores cost more than 8 x 4).  KROTOV_HOST_THREADS overrides.
+    int nt = n_threads;
+    if (nt <= 0) {
+        const char *e = getenv("KROTOV_HOST_THREADS");
+        if (e && atoi(e) > 0) {
+            nt = atoi(e);
+        } else {
+            const char *lw = getenv("LOCAL_WORLD_SIZE");
+            nt = (int)std::thread::hardware_concurrency() / std::max(1, lw ? atoi(lw) : 1);
+        }
+    }
     nt = std::max(1, std::min(nt, std::min(n_items, 64)));
     if (nt == 1) {
         work(0, 1);

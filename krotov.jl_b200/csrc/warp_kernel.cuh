@@ -989,13 +989,17 @@ struct RfProducer<true> {
                                          bool rf_) {
         v0 = plain; ring = ring_; prog = prog_; cons = cons_; xoff = xoff_; item = 0; consumed = 0; use_fwd = use_fwd_; rf = rf_;
     }
+    // the consumer's progress, read a step ahead of its use.  A relaxed load: an acquire load puts a MEMBAR behind it that
+    // waits for the metadata prefetches of the next step (their latency is otherwise hidden behind the Chebyshev terms);
+    // the ring slot is only rewritten after this value has been tested (control dependency), and the forwarder
+    // publishes it behind a release once its own read of the slot has been performed
     __device__ __forceinline__ void peek() {
-        if (use_fwd) consumed = ld_acquire_cta_shared(cons);
+        if (use_fwd) consumed = *reinterpret_cast<volatile int *>(cons);
     }
     template <int LPT>
     __device__ __forceinline__ void put(const WarpParams &p, const int slot, const double2 v, const int lane, const int gbar) {
         if (use_fwd) {
-            while (item - consumed >= kRfRing && *(volatile int *)p.err_flag == 0) consumed = ld_acquire_cta_shared(cons);
+            while (item - consumed >= kRfRing && *(volatile int *)p.err_flag == 0) consumed = *reinterpret_cast<volatile int *>(cons);
             v0 = ring + (item % kRfRing) * 32;
             v0[lane] = v;
             __syncwarp();
