@@ -243,6 +243,13 @@ int krotov_hermitian_extremes(int n_mat, int d, const double *mats, double *e_mi
 int krotov_envelope_extremes(int n_gen, int d, int n_ctrl, const double *H0, const double *Hc, int n_corner,
                              const double *amps, double *e_min, double *e_max, int n_threads);
 
+/* The same envelope on the DEVICE, from the generator terms the handle already holds (persistent kernel path, d <= 32,
+ * Hermitian generators -- the caller's duty, as for krotov_envelope_extremes): one warp per (generator, corner) forms
+ * H0[g] + sum_l amps[corner][l] Hc[l][g] in shared memory and diagonalises it with cyclic Jacobi rotations.  Agrees
+ * with LAPACK to a few ulp of the matrix norm.  Returns KROTOV_ERR_UNSUPPORTED on the other paths (use the host solver).
+ * amps: [n_corner][L], e_min/e_max: [n_gen]. */
+int krotov_envelope_extremes_device(krotov_handle h, int n_corner, const double *amps, double *e_min, double *e_max);
+
 #ifdef __cplusplus
 }
 #endif

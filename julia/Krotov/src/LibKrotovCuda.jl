@@ -186,6 +186,14 @@ function hermitian_extremes(mats::Array{ComplexF64,3}; threads = 0)
     e_min, e_max
 end
 
+# The envelope solved on the device from the terms the handle holds (persistent kernel path); amps: [L, n_corner]
+function envelope_extremes_device(h::Handle, amps::Matrix{Float64}, n_gen::Integer)
+    e_min, e_max = Vector{Float64}(undef, n_gen), Vector{Float64}(undef, n_gen)
+    check(h, ccall((:krotov_envelope_extremes_device, lib), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                   h.ptr, size(amps, 2), amps, e_min, e_max))
+    e_min, e_max
+end
+
 # H0: [d, d, n_gen], Hc: [d, d, n_gen, L], amps: [L, n_corner]
 function envelope_extremes(H0::Array{ComplexF64,3}, Hc::Array{ComplexF64,4}, amps::Matrix{Float64}; threads = 0)
     d, n_gen, L = size(H0, 1), size(H0, 3), size(Hc, 4)

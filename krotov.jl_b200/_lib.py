@@ -27,7 +27,7 @@ EXPORTS = [
     "krotov_set_cheby", "krotov_set_amplitudes", "krotov_forward", "krotov_set_chi", "krotov_set_chi_coeffs", "krotov_iterate",
     "krotov_get_states", "krotov_get_tau", "krotov_get_storage", "krotov_get_profile", "krotov_comm_export", "krotov_comm_connect",
     "krotov_group_connect", "krotov_group_iterate",
-    "krotov_hermitian_extremes", "krotov_envelope_extremes",
+    "krotov_hermitian_extremes", "krotov_envelope_extremes", "krotov_envelope_extremes_device",
 ]
 
 
@@ -98,6 +98,7 @@ def lib():
     L.krotov_group_iterate.argtypes = [vp, i32, vp, vp, vp]
     L.krotov_hermitian_extremes.argtypes = [i32, i32, vp, vp, vp, i32]
     L.krotov_envelope_extremes.argtypes = [i32, i32, i32, vp, vp, i32, vp, vp, vp, i32]
+    L.krotov_envelope_extremes_device.argtypes = [vp, i32, vp, vp, vp]
     for name in EXPORTS:
         if name not in ("krotov_last_error",):
             getattr(L, name).restype = i32

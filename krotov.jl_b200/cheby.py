@@ -27,13 +27,16 @@ def cheby_coeffs(Delta, dt, limit=1e-12):
     return np.asarray(out, np.float64)
 
 
-def cheby_coeffs_table(Deltas, dt, limit=1e-12):
+def cheby_coeffs_table(Deltas, dt, limit=1e-12, m_hint=0):
     """`cheby_coeffs` for many spectral radii at once (one vectorised Bessel call) as a zero-padded table
     ``(a[n_gen, m_max], m[n_gen])``; every number is what the scalar function returns (same ufunc, evaluated
-    elementwise)."""
+    elementwise).  ``m_hint``: the largest coefficient count of the previous table of this step size -- a re-derived
+    envelope moves it by a term or two, so the Bessel call covers ``m_hint + 4`` orders first."""
     Deltas = np.asarray(Deltas, np.float64)
     alpha = np.abs(0.5 * Deltas * dt)
     nmax = int(np.max(alpha)) + 24  # enough for limit = 1e-12 at small alpha; doubled below when it is not
+    if m_hint > 0:
+        nmax = min(nmax, int(m_hint) + 4)
     while True:
         n = np.arange(nmax)
         a = jv(n[None, :], alpha[:, None])
@@ -123,8 +126,11 @@ class ChebyDirection:
     generator forward, the ADJOINT generator backward (``src/workspace.jl:69,150-160``)."""
 
     def __init__(self, H0, Hc, tlist, backward, pulses, *, limit=1e-12, specrange_buffer=0.01,
-                 specrange_method="auto", E_min=None, E_max=None, envelope_cache=None, amplitude=None):
+                 specrange_method="auto", E_min=None, E_max=None, envelope_cache=None, amplitude=None,
+                 device_envelope=None):
         self.H0, self.Hc = H0, Hc
+        # `device_envelope(corners) -> (e_min, e_max)`: the engine's solver for the generators it holds (ensembles)
+        self._device_envelope = device_envelope
         # non-linear amplitudes: `amplitude(l, eps)` = coefficient of H_l for the control value eps (range corners)
         self._amplitude = amplitude
         # spectral envelopes by control ranges.  The two directions of a Hermitian problem propagate with the
@@ -181,9 +187,13 @@ class ChebyDirection:
                 # ensembles: the library's threaded host solver (forms the corner generators and finds their extreme
                 # eigenvalues only); agrees with LAPACK to a few ulp of the matrix norm, far below what the
                 # Chebyshev expansion resolves
-                from ._lib import envelope_extremes
+                if self._device_envelope is not None:
+                    # ... or, on the persistent-kernel path, the device (one warp per corner generator, Jacobi rotations)
+                    e_min, e_max = self._device_envelope(np.array([hi, lo], np.float64))
+                else:
+                    from ._lib import envelope_extremes
 
-                e_min, e_max = envelope_extremes(self._H0s, self._Hcs_stack, np.array([hi, lo], np.float64))
+                    e_min, e_max = envelope_extremes(self._H0s, self._Hcs_stack, np.array([hi, lo], np.float64))
             else:
                 G_hi, G_lo = self._H0s.copy(), self._H0s.copy()  # same elementwise sums as `_evaluate`, for all g at once
                 for l in range(len(hi)):
@@ -243,7 +253,9 @@ class ChebyDirection:
         for (_, rep) in classes:
             if rep not in reps:
                 reps.append(rep)
-        per_rep = {rep: cheby_coeffs_table(self.Delta, rep, self.limit) for rep in reps}
+        hints = getattr(self, "_m_hint", {})
+        per_rep = {rep: cheby_coeffs_table(self.Delta, rep, self.limit, hints.get(rep, 0)) for rep in reps}
+        self._m_hint = {rep: int(per_rep[rep][1].max()) for rep in reps}
         n_gen = len(self.H0)
         m_max = max(int(a.shape[1]) for a, _ in per_rep.values())
         self.coeff_table = np.zeros((n_gen, len(classes), m_max), np.float64)  # [g][class][j], zero-padded

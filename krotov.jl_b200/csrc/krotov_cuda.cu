@@ -104,7 +104,7 @@ struct krotov_handle_s {
     int wpc = 1, tpw = 1, nCTA = 1;
     DevBuf d_cols, d_Pf, d_Pb, d_inv_s, d_gen, d_dt, d_alpha, d_eps_old, d_eps_new, d_ga, d_X, d_Phi, d_psi0,
         d_target, d_chiT, d_chicoef, d_psif, d_tau, d_R, d_err, d_weight, d_prof, d_Tf, d_Tb, d_acc,
-        d_rawf, d_rawb, d_rowscale;  // unscaled generator rows of both directions + per-generator (fy, beta): rows are scaled on the device
+        d_rawf, d_rawb, d_rowscale, d_envamps, d_envout;  // unscaled generator rows of both directions + per-generator (fy, beta): rows are scaled on the device
     DevBuf d_mbox[2];
     ChebyTables cheb[2];
     bool chiT_valid = false, chicoef_valid = false, swept = false;
@@ -426,6 +426,87 @@ __global__ void scale_rows_kernel(const double2 *__restrict__ raw, const double2
     out[idx] = o;
 }
 
+// Spectral envelope on the device (krotov_envelope_extremes_device): one warp per (generator, corner).  The warp forms
+// A = H_0 + sum_l amp_l H_l from the unscaled forward rows in shared memory (lane i owns row i) and runs cyclic Jacobi
+// rotations on the complex Hermitian matrix until the off-diagonal norm is below 1e-30 ||A||_F^2 (eigenvalues to a few
+// ulp of the norm); the extreme diagonal entries are the extreme eigenvalues.  out[(g * n_corner + c)] = (lo, hi).
+__global__ void __launch_bounds__(32) jacobi_extremes_kernel(const double2 *__restrict__ raw, const int *__restrict__ cols,
+                                                             const double *__restrict__ amps, double2 *__restrict__ out,
+                                                             const int L, const int Wt, const int d, const int n_corner) {
+    constexpr int LD = 33;
+    __shared__ double2 A[32 * LD];
+    const int lane = threadIdx.x;
+    const int g = blockIdx.x / n_corner, c = blockIdx.x % n_corner;
+    for (int j = 0; j < 32; ++j) A[lane * LD + j] = make_double2(0.0, 0.0);
+    __syncwarp();
+    const size_t rowstride = (size_t)(Wt + 1) * 32;
+    for (int sl = 0; sl <= Wt; ++sl) {
+        double2 v = raw[((size_t)g * (1 + L)) * rowstride + (size_t)sl * 32 + lane];
+        for (int l = 0; l < L; ++l) {
+            const double a = amps[c * L + l];
+            const double2 w = raw[((size_t)g * (1 + L) + l + 1) * rowstride + (size_t)sl * 32 + lane];
+            v.x = fma(a, w.x, v.x);
+            v.y = fma(a, w.y, v.y);
+        }
+        const int j = (sl == Wt) ? lane : cols[sl * 32 + lane];
+        if (lane < d && j < d) {  // (each lane owns its row: no two lanes touch the same element)
+            A[lane * LD + j].x += v.x;
+            A[lane * LD + j].y += v.y;
+        }
+    }
+    __syncwarp();
+    // Frobenius norm (for the stopping rule)
+    double nrm = 0.0;
+    if (lane < d)
+        for (int j = 0; j < d; ++j) nrm += A[lane * LD + j].x * A[lane * LD + j].x + A[lane * LD + j].y * A[lane * LD + j].y;
+    for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0;
+        if (lane < d)
+            for (int j = 0; j < d; ++j)
+                if (j != lane) off += A[lane * LD + j].x * A[lane * LD + j].x + A[lane * LD + j].y * A[lane * LD + j].y;
+        for (int o = 16; o > 0; o >>= 1) off += __shfl_xor_sync(0xffffffffu, off, o);
+        if (off <= 1e-30 * nrm) break;
+        for (int p = 0; p < d - 1; ++p)
+            for (int q = p + 1; q < d; ++q) {
+                const double2 cpq = A[p * LD + q];
+                const double ac = sqrt(cpq.x * cpq.x + cpq.y * cpq.y);
+                if (ac < 1e-300) continue;  // (warp-uniform: every lane reads the same element)
+                const double app = A[p * LD + p].x, aqq = A[q * LD + q].x;
+                const double tau = (aqq - app) / (2.0 * ac);
+                const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                const double cs = 1.0 / sqrt(1.0 + t * t), sn = t * cs;
+                const double wr = cpq.x / ac, wi = cpq.y / ac;  // w = e^{i phi}
+                __syncwarp();
+                if (lane < d && lane != p && lane != q) {
+                    const double2 akp = A[lane * LD + p], akq = A[lane * LD + q];
+                    // A'_kp = cs A_kp - sn conj(w) A_kq ;  A'_kq = sn w A_kp + cs A_kq
+                    const double2 nkp = make_double2(cs * akp.x - sn * (wr * akq.x + wi * akq.y),
+                                                     cs * akp.y - sn * (wr * akq.y - wi * akq.x));
+                    const double2 nkq = make_double2(sn * (wr * akp.x - wi * akp.y) + cs * akq.x,
+                                                     sn * (wr * akp.y + wi * akp.x) + cs * akq.y);
+                    A[lane * LD + p] = nkp;
+                    A[lane * LD + q] = nkq;
+                    A[p * LD + lane] = make_double2(nkp.x, -nkp.y);
+                    A[q * LD + lane] = make_double2(nkq.x, -nkq.y);
+                } else if (lane == p) {
+                    A[p * LD + p] = make_double2(app - t * ac, 0.0);
+                    A[p * LD + q] = make_double2(0.0, 0.0);
+                } else if (lane == q) {
+                    A[q * LD + q] = make_double2(aqq + t * ac, 0.0);
+                    A[q * LD + p] = make_double2(0.0, 0.0);
+                }
+                __syncwarp();
+            }
+    }
+    double lo = (lane < d) ? A[lane * LD + lane].x : INFINITY, hi = (lane < d) ? A[lane * LD + lane].x : -INFINITY;
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0) out[blockIdx.x] = make_double2(lo, hi);
+}
+
 // dense prepared terms of one direction for the tiny kernel: [g][1+L][d*d] row-major, same numbers as build_rows
 void build_dense_terms(krotov_handle h, int dir, std::vector<cplx> &out) {
     const int d = h->d, L = h->L;
@@ -733,7 +814,7 @@ int krotov_destroy(krotov_handle h) {
                       &h->d_chiT, &h->d_chicoef, &h->d_psif, &h->d_tau, &h->d_R, &h->d_err, &h->d_weight, &h->d_prof,
                       &h->d_mbox[0], &h->d_mbox[1], &h->d_emul,
                       &h->d_amp_poly, &h->d_amp_shape, &h->d_amp_old, &h->d_amp_dfac, &h->d_amp_new, &h->d_rfcount,
-                      &h->d_rawf, &h->d_rawb, &h->d_rowscale};
+                      &h->d_rawf, &h->d_rawb, &h->d_rowscale, &h->d_envamps, &h->d_envout};
     for (DevBuf *b : bufs) b->release();
     for (int dir = 0; dir < 2; ++dir) {
         h->cheb[dir].coef.release();
@@ -1546,6 +1627,36 @@ int krotov_get_storage(krotov_handle h, int which, int k, int n0, int n1, double
     } else {
         std::string e;
         if (!kr::dense_get_storage(h->dense, which, k, n0, n1, out, e)) return fail(h, KROTOV_ERR_CUDA, e);
+    }
+    return KROTOV_OK;
+}
+
+int krotov_envelope_extremes_device(krotov_handle h, int n_corner, const double *amps, double *e_min, double *e_max) {
+    if (!h) return KROTOV_ERR_ARG;
+    if (n_corner < 1 || !amps || !e_min || !e_max) return fail(h, KROTOV_ERR_ARG, "bad argument to krotov_envelope_extremes_device");
+    if (h->path != KROTOV_PATH_WARP || h->lpt != 32 || !h->d_rawf.p)
+        return fail(h, KROTOV_ERR_UNSUPPORTED, "krotov_envelope_extremes_device: persistent kernel path with d <= 32 only");
+    cudaSetDevice(h->device);
+    int rc;
+    const size_t n_out = (size_t)h->n_gen * n_corner;
+    if ((rc = dev_alloc(h, h->d_envamps, (size_t)n_corner * h->L * 8 + 16))) return rc;
+    if ((rc = dev_alloc(h, h->d_envout, n_out * 16))) return rc;
+    KR_CUDA(h, cudaMemcpyAsync(h->d_envamps.p, amps, (size_t)n_corner * h->L * 8, cudaMemcpyHostToDevice, h->stream));
+    jacobi_extremes_kernel<<<(unsigned)n_out, 32, 0, h->stream>>>((const double2 *)h->d_rawf.p, (const int *)h->d_cols.p,
+                                                                  (const double *)h->d_envamps.p, (double2 *)h->d_envout.p,
+                                                                  h->L, h->Wt, h->d, n_corner);
+    std::vector<double> out(2 * n_out);
+    KR_CUDA(h, cudaMemcpyAsync(out.data(), h->d_envout.p, n_out * 16, cudaMemcpyDeviceToHost, h->stream));
+    KR_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->launches_total += 1;
+    for (int g = 0; g < h->n_gen; ++g) {
+        double lo = out[2 * ((size_t)g * n_corner)], hi = out[2 * ((size_t)g * n_corner) + 1];
+        for (int c = 1; c < n_corner; ++c) {
+            lo = std::min(lo, out[2 * ((size_t)g * n_corner + c)]);
+            hi = std::max(hi, out[2 * ((size_t)g * n_corner + c) + 1]);
+        }
+        e_min[g] = lo;
+        e_max[g] = hi;
     }
     return KROTOV_OK;
 }

@@ -181,6 +181,15 @@ class KrotovCuda:
         self._check(self._lib.krotov_get_storage(self._h, int(which), int(k), int(n0), int(n1), _ptr(out)))
         return out
 
+    def envelope_extremes(self, corners):
+        """``(e_min, e_max)`` per generator over the amplitude corners ``(n_corner, L)``, solved on the device from the
+        generator terms the handle holds (``krotov_envelope_extremes_device``); raises where the path has no device
+        solver."""
+        amps = np.ascontiguousarray(corners, np.float64).reshape(-1, self.L)
+        lo, hi = np.empty(self.n_gen, np.float64), np.empty(self.n_gen, np.float64)
+        self._check(self._lib.krotov_envelope_extremes_device(self._h, amps.shape[0], _ptr(amps), _ptr(lo), _ptr(hi)))
+        return lo, hi
+
     def profile(self, cta=-1):
         out = np.zeros(8, np.int64)
         self._check(self._lib.krotov_get_profile(self._h, int(cta), _ptr(out)))

@@ -446,6 +446,15 @@ class KrotovWrk:
         # spectral envelopes (see ChebyDirection)
         shared = {} if all(same(m, adj(m)) for m in terms) else None
 
+        # ensembles on the persistent-kernel path: the spectral envelopes behind `reinit_prop!` are solved on the device
+        # from the generator terms the handle holds (ChebyDirection uses it for Hermitian generators only, where both
+        # directions propagate with the same matrices); KROTOV_HOST_ENVELOPE=1 keeps the threaded host solver
+        device_envelope = None
+        import os as _os
+        if (hasattr(self.engine, "envelope_extremes") and d <= 32 and not _os.environ.get("KROTOV_HOST_ENVELOPE")
+                and self.engine.info()["path"] == 1):
+            device_envelope = self.engine.envelope_extremes
+
         def settings(pk, backward):
             H0s = [adj(h) for h in self._H0] if backward else self._H0
             Hcs = [[None if h is None else adj(h) for h in row] for row in self._Hc] if backward else self._Hc
@@ -454,7 +463,7 @@ class KrotovWrk:
                 limit=pk.get("cheby_coeffs_limit", 1e-12), specrange_buffer=pk.get("specrange_buffer", 0.01),
                 specrange_method=pk.get("specrange_method", "auto"), E_min=pk.get("E_min"), E_max=pk.get("E_max"),
                 envelope_cache=shared if self._shared_envelope_ok(pk) else None,
-                amplitude=self._amp_envelope if nonlinear else None)
+                amplitude=self._amp_envelope if nonlinear else None, device_envelope=device_envelope)
 
         self.fw_settings = settings(self.fw_prop_kwargs[0], False)
         self.bw_settings = settings(self.bw_prop_kwargs[0], True)

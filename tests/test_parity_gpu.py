@@ -1242,3 +1242,34 @@ def test_emulated_ranks_replicated_forward_sweep_is_bit_identical(ranks, n_sampl
         assert np.array_equal(st, np.array(single["result"].states))
     for X in seen["X"]:  # the last trajectory's chi was propagated by the LAST rank and written to every rank
         assert np.array_equal(X, seen["X1"])
+
+
+def test_device_envelope_solver_matches_lapack_and_the_optimisation_is_unchanged(monkeypatch):
+    """krotov_envelope_extremes_device (one warp per corner generator, cyclic Jacobi) against numpy's eigvalsh for the
+    generators of an ensemble at several amplitude corners, and an optimisation whose spectral envelopes were solved on
+    the device against one that used the threaded host solver (BASELINE tolerances; range events included)."""
+    w = W.c4_ensemble(n_samples=24, n_grid=101)
+    seen = {}
+
+    def cb(wrk, it, eps_new, eps_old):
+        if it == 0:
+            eng = wrk.engine
+            corners = np.array([[0.3, -0.2], [-0.25, 0.4], [0.0, 0.0], [1.7, 1.1]])
+            lo, hi = eng.envelope_extremes(corners)
+            H0 = np.stack([np.asarray(h) for h in w.H0])
+            ref_lo, ref_hi = np.full(len(H0), np.inf), np.full(len(H0), -np.inf)
+            for c in corners:
+                G = H0 + sum(c[l] * np.stack([np.asarray(row[l]) for row in w.Hc]) for l in range(w.L))
+                ev = np.linalg.eigvalsh(G)
+                ref_lo, ref_hi = np.minimum(ref_lo, ev[:, 0]), np.maximum(ref_hi, ev[:, -1])
+            scale = np.abs(np.stack([ref_lo, ref_hi])).max()
+            seen["err"] = max(np.abs(lo - ref_lo).max(), np.abs(hi - ref_hi).max()) / scale
+        seen["updates"] = wrk.bw_settings.n_updates
+
+    dev = run_product(w, 4, callback=cb)
+    assert seen["err"] < 1e-14, seen["err"]
+    assert seen["updates"] >= 1  # the far-off guess widens the pulse range: at least one envelope was re-derived
+    monkeypatch.setenv("KROTOV_HOST_ENVELOPE", "1")
+    monkeypatch.setenv("KROTOV_HOST_ROWS", "1")
+    host = run_product(w, 4)
+    assert_parity(dev, host["J_T"], host["pulses"])
