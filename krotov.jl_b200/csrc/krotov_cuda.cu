@@ -724,9 +724,10 @@ void fill_warp_params(krotov_handle h, int mode, kr::WarpParams &p) {
         p.X = p.Xr[h->rank];
         p.rf_count = (unsigned int *)h->d_rfcount.p;
         p.rf_iter = (unsigned long long)(h->iter_count + 1);
+        p.rf_stride = getenv("KROTOV_RF_STRIDE") ? std::max(1, atoi(getenv("KROTOV_RF_STRIDE"))) : 1;
         p.rf_pack = getenv("KROTOV_RF_PACK") ? (h->bw_hi - h->bw_lo + h->nCTA - 1) / h->nCTA : 0;
         // forwarder warps (the value is their polling interval in ns); KROTOV_RF_DIRECT=1: producers store to all ranks
-        p.rf_fwd = (h->lpt == 32 && !getenv("KROTOV_RF_DIRECT")) ? (getenv("KROTOV_RF_SLEEP") ? std::max(1, atoi(getenv("KROTOV_RF_SLEEP"))) : 64) : 0;
+        p.rf_fwd = (h->lpt == 32 && !getenv("KROTOV_RF_DIRECT")) ? (getenv("KROTOV_RF_SLEEP") ? std::max(1, atoi(getenv("KROTOV_RF_SLEEP"))) : 1000) : 0;
         h->xchg_last = 5;
     }
     p.err_flag = (int *)h->d_err.p;
@@ -756,13 +757,25 @@ int launch_warp(krotov_handle h, int mode) {
         return KROTOV_OK;
     }
     KernelKey key{h->Wt, h->preg ? h->L : 0, h->pair ? 32 : h->lpt};
-    const auto &table = h->pair ? kernel2_table() : h->rf ? kernel_rf_table() : kernel_table();
+    const auto &table = h->pair ? kernel2_table() : kernel_table();
     auto it = table.find(key);
     if (it == table.end()) return fail(h, KROTOV_ERR_UNSUPPORTED, "no kernel instance for this (W, L)");
     WarpKernel fn = it->second;
     const size_t smem = warp_smem_bytes(h);
     KR_CUDA(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(h->nCTA), block(h->wpc * h->lpt + 32);
+    if (h->rf && mode == 1) {
+        // replicated forward sweep, stage 1: the RF instance runs this rank's shard of the backward sweep, writes chi to
+        // every rank and ends behind the rank barrier; stage 2 below: the regular instance runs the forward sweep
+        auto itr = kernel_rf_table().find(key);
+        if (itr == kernel_rf_table().end()) return fail(h, KROTOV_ERR_UNSUPPORTED, "no RF kernel instance for this (W, L)");
+        KR_CUDA(h, cudaFuncSetAttribute((const void *)itr->second, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        void *args1[] = {(void *)&p};
+        KR_CUDA(h, cudaLaunchCooperativeKernel((const void *)itr->second, grid, block, args1, smem, h->stream));
+        h->launches_last += 1;
+        p.skip_bw = 1;
+    }
+    p.rf_world = 0;  // (the regular instances carry no RF code; the field is theirs to ignore)
     void *args[] = {(void *)&p};
     if (h->nCTA > 1 && mode == 1) {
         KR_CUDA(h, cudaLaunchCooperativeKernel((const void *)fn, grid, block, args, smem, h->stream));
@@ -1520,20 +1533,41 @@ int krotov_group_iterate(krotov_handle *hs, int world, const double *guess_pulse
         base += hs[r]->nCTA;
         KR_CUDA(hs[r], cudaStreamSynchronize(hs[r]->stream));  // the ranks' preparation ran on their own streams
     }
+    // (replicated forward sweep: two stages -- the RF instance for the backward shards, the regular one for the forward sweeps;
+    // the parameter blocks of stage 2 sit behind those of stage 1)
+    const bool rf = h0->rf;
+    if (rf) {
+        pv.resize(2 * world);
+        for (int r = 0; r < world; ++r) {
+            pv[world + r] = pv[r];
+            pv[world + r].skip_bw = 1;
+            pv[world + r].rf_world = 0;
+        }
+    }
     if ((rc = upload(h0, h0->d_emul, pv))) return rc;
     kr::WarpParams p0;
     memset(&p0, 0, sizeof(p0));
     p0.emul = (const kr::WarpParams *)h0->d_emul.p;
     p0.emul_ranks = world;
     p0.wpc = h0->wpc;
-    const auto &etab = h0->rf ? kernel_rf_emul_table() : kernel_emul_table();
-    auto it = etab.find(KernelKey{h0->Wt, h0->preg ? h0->L : 0, h0->lpt});
-    if (it == etab.end())
+    const KernelKey key{h0->Wt, h0->preg ? h0->L : 0, h0->lpt};
+    auto it = kernel_emul_table().find(key);
+    if (it == kernel_emul_table().end())
         return fail(h0, KROTOV_ERR_UNSUPPORTED, "no emulated-ranks instance of this kernel (W, L)");
     size_t smem = 0;
     for (int r = 0; r < world; ++r) smem = std::max(smem, warp_smem_bytes(hs[r]));
-    KR_CUDA(h0, cudaFuncSetAttribute((const void *)it->second, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(base), block(h0->wpc * h0->lpt + 32);
+    if (rf) {
+        auto itr = kernel_rf_emul_table().find(key);
+        if (itr == kernel_rf_emul_table().end())
+            return fail(h0, KROTOV_ERR_UNSUPPORTED, "no emulated-ranks RF instance of this kernel (W, L)");
+        KR_CUDA(h0, cudaFuncSetAttribute((const void *)itr->second, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        void *args1[] = {(void *)&p0};
+        KR_CUDA(h0, cudaLaunchCooperativeKernel((const void *)itr->second, grid, block, args1, smem, h0->stream));
+        h0->launches_last += 1;
+        p0.emul = (const kr::WarpParams *)h0->d_emul.p + world;
+    }
+    KR_CUDA(h0, cudaFuncSetAttribute((const void *)it->second, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void *args[] = {(void *)&p0};
     KR_CUDA(h0, cudaLaunchCooperativeKernel((const void *)it->second, grid, block, args, smem, h0->stream));
     KR_CUDA(h0, cudaStreamSynchronize(h0->stream));

@@ -114,6 +114,9 @@ struct WarpParams {
     // the producing warps out of a shared-memory ring and store them to every rank, so the producers' serial chain carries
     // no peer store at all (0 = every producer stores to all ranks itself)
     int rf_fwd;
+    int skip_bw;  // mode 1 in the REGULAR instances: the backward sweep was done by an RF instance (stage 1 of the replicated
+                  // forward sweep); run the sequential update / forward sweep of the iteration only
+    int rf_stride;  // RF instances: warp w plays slot (w * rf_stride) % wpc of the producer / forwarder roles (1 = identity)
     int rf_pack;  // producers per CTA when the backward shard is packed (warps of a CTA take CONSECUTIVE trajectories); 0 = spread
 };
 
@@ -1052,6 +1055,9 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
         __syncthreads();
     }
 
+    if constexpr (RF) {
+        if (is_comm) return;  // (the RF instances run the backward sweep only: nothing to exchange)
+    }
     if (is_comm) {
         __shared__ __align__(16) WarpParams p_sh;
         comm_warp_run(p, cta, L, lane, wpc * (LPT / 32), nthr_all, red, eps_s, gbuf, &p_sh);
@@ -1084,13 +1090,14 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
                                    : min(wpc, max(0, (p.bw_hi - p.bw_lo - cta + p.nCTA - 1) / p.nCTA));
     const int n_fwd = wpc - n_prod;
     const bool use_fwd = rf_fwd && n_prod > 0 && n_fwd > 0;
+    const int vw = RF ? (warp * max(1, p.rf_stride)) % wpc : warp;  // role slot of this warp
     if constexpr (RF)
-        if (p.mode == 1 && use_fwd && warp >= n_prod) rf_forward_records(&p, rf_ring, rf_prog, cta, warp, lane, n_prod, n_fwd);
-    if (p.mode == 1) {
+        if (p.mode == 1 && use_fwd && vw >= n_prod) rf_forward_records(&p, rf_ring, rf_prog, cta, vw, lane, n_prod, n_fwd);
+    if (p.mode == 1 && (RF || !p.skip_bw)) {
         for (int t = 0; t < tpw; ++t) {
             int k = kbase + t;
             if constexpr (RF) if (rf) {  // (tpw == 1) this rank's backward shard, spread over the CTAs: one trajectory per SM first
-                const int tl = p.rf_pack ? (warp < p.rf_pack ? cta * p.rf_pack + warp : p.N) : warp * p.nCTA + cta;
+                const int tl = p.rf_pack ? (vw < p.rf_pack ? cta * p.rf_pack + vw : p.N) : vw * p.nCTA + cta;
                 k = (tl < p.bw_hi - p.bw_lo) ? p.bw_lo + tl : p.N;
             }
             if (k >= p.N) break;
@@ -1114,7 +1121,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
             // forwarder warp then stores it to every rank.  (Kept in a type that is EMPTY in the regular instances: a mere
             // unused lambda here changed their register allocation and cost the forward sweep 2 %.)
             RfProducer<RF> rfp;
-            if constexpr (RF) rfp.init(mypsi + t * LPT, rf_ring + (size_t)warp * kRfRing * 32, rf_prog + warp, rf_prog + wpc + warp,
+            if constexpr (RF) rfp.init(mypsi + t * LPT, rf_ring + (size_t)vw * kRfRing * 32, rf_prog + vw, rf_prog + wpc + vw,
                                        (size_t)k * (N_T + 1) * LPT + lane, use_fwd, rf);
             if constexpr (RF) {
                 rfp.template put<LPT>(p, N_T, chi, lane, gbar);
@@ -1178,6 +1185,13 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
         }
         if constexpr (RF)
             if (rf) rf_rank_barrier<LPT>(&p, cta, warp, lane, gbar);
+    }
+    if constexpr (RF) {
+        // Stage 1 of the replicated forward sweep ends here; the forward sweep is a launch of the REGULAR instance
+        // (skip_bw = 1).  Compiled together with the forward sweep, this backward sweep ran 0.15-0.3 us per time step
+        // behind the regular one (register allocation of the bigger function).
+        if (p.prof != nullptr && warp == 0 && lane == 0) p.prof[cta * 8 + 0] = clock64() - t_begin;
+        return;
     }
 
     const long long t_bw_end = clock64();
@@ -1367,7 +1381,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
 
     if (p.prof != nullptr && warp == 0 && lane == 0) {
         const long long t_end = clock64();
-        p.prof[cta * 8 + 0] = t_bw_end - t_begin;
+        if (!p.skip_bw) p.prof[cta * 8 + 0] = t_bw_end - t_begin;
         p.prof[cta * 8 + 1] = t_end - t_bw_end;
         p.prof[cta * 8 + 2] = t_wait_b;
         p.prof[cta * 8 + 6] = t_overlap;

@@ -294,6 +294,15 @@ class KrotovCudaGroup:
             return self.engines[0].tau()
         return np.concatenate([e.tau() for e in self.engines], axis=0)
 
+    def envelope_extremes(self, corners):
+        """Device-side spectral envelopes of all generators of the group (every rank solves the ones it holds)."""
+        if self.replicated:
+            return self.engines[0].envelope_extremes(corners)
+        lo, hi = np.empty(self.n_gen, np.float64), np.empty(self.n_gen, np.float64)
+        for e, g in zip(self.engines, self.gens):
+            lo[g], hi[g] = e.envelope_extremes(corners)
+        return lo, hi
+
     def states_all(self):
         """Final states of EVERY rank (replicated mode: they must be identical)."""
         return [e.states() for e in self.engines]
