@@ -58,7 +58,10 @@ class ClockSampler:
         self._stop = threading.Event()
         self.thread = None
 
-    def start(self):
+    def prepare(self):
+        """NVML initialisation (tens of ms, and not the same on every rank): done before the run, never between the
+        barrier that opens the timed region and the first timed launch -- with several ranks the ranks that are ready
+        first launch and wait IN the kernel for the last one, which counts as device time."""
         try:
             import pynvml
 
@@ -68,6 +71,9 @@ class ClockSampler:
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
         except Exception:
             self.nv = None
+
+    def start(self):
+        if getattr(self, "nv", None) is None:
             return
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
@@ -311,6 +317,7 @@ def main():
     # ---- timed run through the public API; device time is read from the handle after every iteration
     dev_ms, launches, marks = [], [], {}
     sampler = ClockSampler(local_rank)
+    sampler.prepare()
 
     def cb(wrk, it, eps_new, eps_old):
         marks.setdefault("wall", []).append(time.perf_counter())
@@ -321,8 +328,8 @@ def main():
             launches.append(info["launches_last"])
             marks["info"] = info
         if it == warmup:
-            barrier()
             sampler.start()
+            barrier()
             marks["t0"] = time.perf_counter()
             marks["wall"][-1] = marks["t0"]  # per-iteration list starts where the timed region starts
         if it == warmup + steps:

@@ -470,13 +470,16 @@ __global__ void __launch_bounds__(32) jacobi_extremes_kernel(const double2 *__re
         for (int p = 0; p < d - 1; ++p)
             for (int q = p + 1; q < d; ++q) {
                 const double2 cpq = A[p * LD + q];
-                const double ac = sqrt(cpq.x * cpq.x + cpq.y * cpq.y);
-                if (ac < 1e-300) continue;  // (warp-uniform: every lane reads the same element)
+                const double ac2 = cpq.x * cpq.x + cpq.y * cpq.y;
+                // (warp-uniform: every lane reads the same element.)  Elements below 1e-17 ||A||_F are left alone: all 300
+                // of them together stay under the stopping rule, and the last sweeps consist of little else
+                if (ac2 <= 1e-34 * nrm || ac2 < 1e-300) continue;
+                const double ac = sqrt(ac2), iac = 1.0 / ac;
                 const double app = A[p * LD + p].x, aqq = A[q * LD + q].x;
-                const double tau = (aqq - app) / (2.0 * ac);
+                const double tau = 0.5 * (aqq - app) * iac;
                 const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
                 const double cs = 1.0 / sqrt(1.0 + t * t), sn = t * cs;
-                const double wr = cpq.x / ac, wi = cpq.y / ac;  // w = e^{i phi}
+                const double wr = cpq.x * iac, wi = cpq.y * iac;  // w = e^{i phi}
                 __syncwarp();
                 if (lane < d && lane != p && lane != q) {
                     const double2 akp = A[lane * LD + p], akq = A[lane * LD + q];
