@@ -138,6 +138,9 @@ class ChebyDirection:
         # buffer the backward check saw in the previous iteration, src/optimize.jl:305-306 vs :321-325),
         # so the workspace hands both the same dictionary and every envelope is derived once.
         self._envelopes = envelope_cache if envelope_cache is not None else {}
+        # coefficient tables by (spectral radii, |dt|, limit): the two directions of a Hermitian problem meet the same
+        # radii one iteration apart and a_n depends on |Delta dt| only, so the second one finds its table made
+        self._tables = self._envelopes.setdefault("__tables__", {})
         self.tlist = np.asarray(tlist, np.float64)
         self.backward = bool(backward)
         self.limit = float(limit)
@@ -213,8 +216,9 @@ class ChebyDirection:
                 a1, b1 = specrange(self._evaluate(g, lo), self.method)
                 e_min[g], e_max[g] = min(a0, a1), max(b0, b1)
         if self.manual is None:
-            if len(self._envelopes) >= 8:
-                self._envelopes.pop(next(iter(self._envelopes)))
+            env_keys = [k for k in self._envelopes if k != "__tables__"]
+            if len(env_keys) >= 8:
+                self._envelopes.pop(env_keys[0])
             self._envelopes[key] = (e_min, e_max)
         Delta = e_max - e_min
         delta = self.buffer * Delta
@@ -254,7 +258,16 @@ class ChebyDirection:
             if rep not in reps:
                 reps.append(rep)
         hints = getattr(self, "_m_hint", {})
-        per_rep = {rep: cheby_coeffs_table(self.Delta, rep, self.limit, hints.get(rep, 0)) for rep in reps}
+        per_rep = {}
+        for rep in reps:
+            key = (np.ascontiguousarray(self.Delta, np.float64).tobytes(), abs(float(rep)), self.limit)
+            hit = self._tables.get(key)
+            if hit is None:
+                hit = cheby_coeffs_table(self.Delta, rep, self.limit, hints.get(rep, 0))
+                while len(self._tables) >= 8:
+                    self._tables.pop(next(iter(self._tables)))
+                self._tables[key] = hit
+            per_rep[rep] = hit
         self._m_hint = {rep: int(per_rep[rep][1].max()) for rep in reps}
         n_gen = len(self.H0)
         m_max = max(int(a.shape[1]) for a, _ in per_rep.values())

@@ -140,6 +140,27 @@ def test_cheby_settings_match_oracle_bits():
     assert K.transform_control_ranges(None, -1.0, 2.0, True) == (-2.0, 4.0)
 
 
+def test_coefficient_tables_with_hint_and_shared_between_directions():
+    """The Bessel table sized from the previous coefficient count holds the numbers of the scalar function (and grows when
+    the hint is too small); the two directions of a Hermitian problem share one table per (radii, |dt|)."""
+    Deltas = np.array([3.1, 7.7, 12.9, 0.4])
+    full, m_full = K.cheby.cheby_coeffs_table(Deltas, 0.37)
+    for hint in (1, 3, int(m_full.max()), 40):
+        a, m = K.cheby.cheby_coeffs_table(Deltas, 0.37, m_hint=hint)
+        assert np.array_equal(m, m_full) and np.array_equal(a, full)
+    for g, D in enumerate(Deltas):
+        assert np.array_equal(full[g, : m_full[g]], K.cheby.cheby_coeffs(D, 0.37))
+    w = W.c3_two_transmon(n_grid=41)
+    p = W.to_oracle(w)
+    shared = {}
+    fw = K.cheby.ChebyDirection(p.H0, p.Hc, p.tlist, False, p.pulses, envelope_cache=shared)
+    bw = K.cheby.ChebyDirection(p.H0, p.Hc, p.tlist, True, p.pulses, envelope_cache=shared)
+    assert fw._tables is bw._tables and len(fw._tables) == 1  # the backward direction found the forward one's table
+    assert np.array_equal(fw.coeff_table, bw.coeff_table)
+    alone = K.cheby.ChebyDirection(p.H0, p.Hc, p.tlist, True, p.pulses)
+    assert np.array_equal(alone.coeff_table, bw.coeff_table) and np.array_equal(alone.coeff_count, bw.coeff_count)
+
+
 def test_result_layout():
     names = [f.name for f in K.KrotovResult.__dataclass_fields__.values()]
     assert names == ["tlist", "iter_start", "iter_stop", "iter", "secs", "tau_vals", "J_T", "J_T_prev",
