@@ -640,7 +640,7 @@ size_t warp_smem_bytes(const krotov_handle h) {
                (size_t)kr::kMaxCtrl * 160 * 8;
     return (size_t)h->wpc * 2 * h->lpt * 16 + (size_t)h->wpc * h->tpw * h->lpt * 16 + (size_t)h->L * h->wpc * h->lpt * 8 +
            kr::kMaxCtrl * 8 + (size_t)kr::kMaxCtrl * 160 * 8 + (size_t)h->wpc * h->lpt * 16 +
-           (h->rf_wanted ? (size_t)h->wpc * kr::kRfRing * 32 * 16 + (size_t)h->wpc * 2 * 4 + 16 : 0);  // forwarder rings
+           (h->rf_wanted ? (size_t)h->wpc * kr::kRfRing * (32 * 16 + 8) + (size_t)h->wpc * 2 * 4 + 16 : 0);  // forwarder rings + barriers
 }
 
 void fill_warp_params(krotov_handle h, int mode, kr::WarpParams &p) {

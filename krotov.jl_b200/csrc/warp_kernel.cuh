@@ -130,6 +130,26 @@ __device__ __forceinline__ int ld_acquire_cta_shared(const int *a) {
 __device__ __forceinline__ void st_release_cta_shared(int *a, const int v) {
     asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(a)), "r"(v) : "memory");
 }
+// shared-memory barrier objects: the "record ready" signal of the replicated forward sweep's rings.  A forwarder waiting in
+// mbarrier.try_wait is suspended by the hardware; a polling loop with nanosleep was measured to come back every ~33 cycles
+// (ncu: 38 M polls in one backward sweep, 30 % of the issue slots of the sub-partition it shares with a producing warp)
+__device__ __forceinline__ void rf_mbar_init(unsigned long long *bar, const int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void rf_mbar_arrive(unsigned long long *bar) {  // (release at CTA scope)
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ bool rf_mbar_try_wait(unsigned long long *bar, const unsigned parity) {  // (acquire at CTA scope)
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 
 template <bool EMUL>
 __device__ __forceinline__ const WarpParams &select_params(const WarpParams &p0) {
@@ -902,11 +922,11 @@ __device__ __forceinline__ void comm_warp_run(const WarpParams &p, const int cta
 // ---- replicated forward sweep: the cold parts, out of line so that the sweeps of the RF instances keep the code of the
 // regular ones (the parameter block is read through a generic pointer here: slow loads, off every critical path)
 // Forwarder warp: takes the chi records of its producing warps out of their rings and stores them to every rank.
-static __device__ __noinline__ void rf_forward_records(const WarpParams *pp, const double2 *rf_ring, int *rf_prog, const int cta,
-                                                       const int warp, const int lane, const int n_prod, const int n_fwd) {
+static __device__ __noinline__ void rf_forward_records(const WarpParams *pp, const double2 *rf_ring, unsigned long long *rf_bar,
+                                                       int *rf_prog, const int cta, const int warp, const int lane,
+                                                       const int n_prod, const int n_fwd) {
     const WarpParams &p = *pp;
     const int N_T = p.N_T, wpc = p.wpc, world = p.rf_world, nCTA = p.nCTA, bw_lo = p.bw_lo;
-    const unsigned sleep_ns = (unsigned)p.rf_fwd;
     const long long timeout = p.timeout_cycles;
     double2 *Xr[kMaxRanks];
 #pragma unroll
@@ -915,18 +935,20 @@ static __device__ __noinline__ void rf_forward_records(const WarpParams *pp, con
     bool dead = false;
     for (int i = 0; i <= N_T && !dead; ++i) {
         for (int w = warp - n_prod; w < n_prod; w += n_fwd) {
-            if (lane == 0) {
-                int spins = 0;
-                while (ld_acquire_cta_shared(rf_prog + w) <= i) {
-                    __nanosleep(sleep_ns);
-                    if ((++spins & 1023) == 0 && (clock64() - t0 > timeout || *(volatile int *)p.err_flag)) {
+            {   // record i of producer w is ready when phase i / kRfRing of its slot's barrier has completed; every lane
+                // waits for itself (acquire), suspended by the hardware between the time-limited tries
+                unsigned long long *bar = rf_bar + (size_t)w * kRfRing + (i % kRfRing);
+                const unsigned parity = (unsigned)(i / kRfRing) & 1u;
+                int tries = 0;
+                while (!rf_mbar_try_wait(bar, parity)) {
+                    if ((++tries & 63) == 0 && (clock64() - t0 > timeout || *(volatile int *)p.err_flag)) {
                         atomicExch(p.err_flag, 1);
                         dead = true;
                         break;
                     }
                 }
             }
-            dead = __shfl_sync(0xffffffffu, dead, 0);
+            dead = __any_sync(0xffffffffu, dead);
             if (dead) break;
             const double2 v = rf_ring[((size_t)w * kRfRing + (i % kRfRing)) * 32 + lane];
             __syncwarp();
@@ -984,13 +1006,14 @@ struct RfProducer {};
 template <>
 struct RfProducer<true> {
     double2 *v0, *ring;
-    int *prog, *cons;
+    unsigned long long *bar;  // [kRfRing] "record ready" barriers of this producer's slots
+    int *cons;
     size_t xoff;
     int item, consumed;
     bool use_fwd, rf;
-    __device__ __forceinline__ void init(double2 *plain, double2 *ring_, int *prog_, int *cons_, size_t xoff_, bool use_fwd_,
-                                         bool rf_) {
-        v0 = plain; ring = ring_; prog = prog_; cons = cons_; xoff = xoff_; item = 0; consumed = 0; use_fwd = use_fwd_; rf = rf_;
+    __device__ __forceinline__ void init(double2 *plain, double2 *ring_, unsigned long long *bar_, int *cons_, size_t xoff_,
+                                         bool use_fwd_, bool rf_) {
+        v0 = plain; ring = ring_; bar = bar_; cons = cons_; xoff = xoff_; item = 0; consumed = 0; use_fwd = use_fwd_; rf = rf_;
     }
     // the consumer's progress, read a step ahead of its use.  A relaxed load: an acquire load puts a MEMBAR behind it that
     // waits for the metadata prefetches of the next step (their latency is otherwise hidden behind the Chebyshev terms);
@@ -1006,8 +1029,8 @@ struct RfProducer<true> {
             v0 = ring + (item % kRfRing) * 32;
             v0[lane] = v;
             __syncwarp();
+            if (lane == 0) rf_mbar_arrive(bar + (item % kRfRing));  // "record `item` is in its slot" (release)
             ++item;
-            if (lane == 0) st_release_cta_shared(prog, item);
         } else {
             v0[lane] = v;
             grp_sync<LPT>(gbar);
@@ -1046,12 +1069,14 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
     double *gbuf = eps_s + kMaxCtrl;                              // [kMaxCtrl * 160] reducer scratch (CTA 0)
     double2 *chibufs = reinterpret_cast<double2 *>(gbuf + kMaxCtrl * 160);  // [wpc][LPT] chi(t_{n+1}) for the precompute
     double2 *rf_ring = chibufs + (size_t)wpc * LPT;               // [wpc][kRfRing][32]  (only with p.rf_fwd)
-    int *rf_prog = reinterpret_cast<int *>(rf_ring + (size_t)wpc * kRfRing * 32);  // [wpc] items produced, [wpc] consumed
+    unsigned long long *rf_bar = reinterpret_cast<unsigned long long *>(rf_ring + (size_t)wpc * kRfRing * 32);  // [wpc][kRfRing]
+    int *rf_prog = reinterpret_cast<int *>(rf_bar + (size_t)wpc * kRfRing);  // [wpc] (unused), [wpc] records consumed
     const int nthr_all = wpc * LPT + 32;
     const int N_T = p.N_T;
     const bool rf_fwd = RF && LPT == 32 && p.rf_world > 1 && p.rf_fwd != 0 && p.mode == 1;
     if (rf_fwd) {  // (uniform over the CTA)
         if ((int)threadIdx.x < 2 * wpc) rf_prog[threadIdx.x] = 0;
+        if ((int)threadIdx.x < wpc * kRfRing) rf_mbar_init(rf_bar + threadIdx.x, 1);
         __syncthreads();
     }
 
@@ -1092,7 +1117,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
     const bool use_fwd = rf_fwd && n_prod > 0 && n_fwd > 0;
     const int vw = RF ? (warp * max(1, p.rf_stride)) % wpc : warp;  // role slot of this warp
     if constexpr (RF)
-        if (p.mode == 1 && use_fwd && vw >= n_prod) rf_forward_records(&p, rf_ring, rf_prog, cta, vw, lane, n_prod, n_fwd);
+        if (p.mode == 1 && use_fwd && vw >= n_prod) rf_forward_records(&p, rf_ring, rf_bar, rf_prog, cta, vw, lane, n_prod, n_fwd);
     if (p.mode == 1 && (RF || !p.skip_bw)) {
         for (int t = 0; t < tpw; ++t) {
             int k = kbase + t;
@@ -1121,7 +1146,7 @@ __global__ void __launch_bounds__(MAXTHREADS, 1) krotov_warp_kernel(const __grid
             // forwarder warp then stores it to every rank.  (Kept in a type that is EMPTY in the regular instances: a mere
             // unused lambda here changed their register allocation and cost the forward sweep 2 %.)
             RfProducer<RF> rfp;
-            if constexpr (RF) rfp.init(mypsi + t * LPT, rf_ring + (size_t)vw * kRfRing * 32, rf_prog + vw, rf_prog + wpc + vw,
+            if constexpr (RF) rfp.init(mypsi + t * LPT, rf_ring + (size_t)vw * kRfRing * 32, rf_bar + (size_t)vw * kRfRing, rf_prog + wpc + vw,
                                        (size_t)k * (N_T + 1) * LPT + lane, use_fwd, rf);
             if constexpr (RF) {
                 rfp.template put<LPT>(p, N_T, chi, lane, gbar);
