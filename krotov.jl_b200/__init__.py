@@ -14,9 +14,11 @@ from .errors import ArgumentError, ErrorException
 from .functionals import J_T_re, J_T_sm, J_T_ss, chi_re, chi_sm, chi_ss, make_chi, taus
 from .generators import Generator, PolynomialAmplitude, ShapedAmplitude, hamiltonian
 from .optimize import (Cheby, Krotov, finalize_result, krotov_initial_fw_prop, krotov_iteration,
-                       make_krotov_print_iters, make_print_iters, optimize, optimize_krotov, update_result)
+                       make_krotov_print_iters, make_print_iters, optimize, optimize_krotov, update_result,
+                       update_sigma)
 from .problem import ControlProblem, Trajectory
 from .result import KrotovResult
+from .second_order import NumericalSigma, Sigma, numerical_estimate_A
 from .shapes import blackman, box, flattop
 from .cheby import cheby_coeffs, specrange, transform_control_ranges
 from .workspace import IdDict, KrotovWrk

@@ -21,11 +21,12 @@ from . import _lib as B
 from .cheby import transform_control_ranges
 from .controls import discretize
 from .errors import ArgumentError
+from .second_order import sigma_value
 from .workspace import KrotovWrk
 
 log = logging.getLogger("krotov_jl_b200")
 
-__all__ = ["optimize", "optimize_krotov", "krotov_initial_fw_prop", "krotov_iteration", "update_result",
+__all__ = ["optimize", "optimize_krotov", "krotov_initial_fw_prop", "krotov_iteration", "update_result", "update_sigma",
            "finalize_result", "detached_result", "make_krotov_print_iters", "make_print_iters", "Krotov", "Cheby"]
 
 
@@ -63,7 +64,7 @@ def krotov_iteration(wrk, eps_i, eps_ip1):
     """One Krotov iteration (``src/optimize.jl:279-371``): chi boundary condition, then
     ``krotov_iterate`` = backward sweep + sequential update + forward sweep on the device."""
     # chi_k(T)  (:297-302)
-    if wrk.functional == B.CHI_HOST:
+    if wrk.functional == B.CHI_HOST or wrk.sigma is not None:
         chi_fn = wrk.kwargs["chi"]
         Psi = wrk.result.states
         if wrk.chi_takes_tau:
@@ -71,7 +72,16 @@ def krotov_iteration(wrk, eps_i, eps_ip1):
         else:
             chi = chi_fn(Psi, wrk.trajectories)
         lo, hi = wrk._shard
-        wrk.engine.set_chi(np.array(chi[lo:hi], np.complex128))
+        chi_T = np.array(chi[lo:hi], np.complex128)
+        if wrk.sigma is not None:
+            # second order (the TODO at :350): for Hermitian generators and a sigma that is constant over the time
+            # grid, chi(t_n) + sigma/2 (Psi^(i+1)(t_n) - Psi^(i)(t_n)) acts in the update like the backward-propagated
+            # chi(T) - sigma/2 Psi^(i)(T)  (second_order.py)
+            sig = sigma_value(wrk.sigma, wrk.result.tlist)
+            psi_T = np.array([np.asarray(s) for s in Psi], np.complex128)
+            wrk._sigma_info = dict(forward_states0=list(psi_T), chi_states=[np.array(c, np.complex128) for c in chi])
+            chi_T = chi_T - (0.5 * sig) * psi_T[lo:hi]
+        wrk.engine.set_chi(chi_T)
     elif wrk._n_ranks > 1 and wrk.functional == B.CHI_SM:
         # the only functional whose chi needs a sum over ALL ranks' tau: done here from the gathered tau
         tau, w, n = wrk.result.tau_vals, wrk._weight, wrk.N
@@ -118,6 +128,18 @@ def update_result(wrk, i):
     prev = res.end_local_time
     res.end_local_time = _dt.datetime.now()
     res.secs = (res.end_local_time - prev).total_seconds()
+
+
+def update_sigma(wrk, eps_ip1, eps_i):
+    """The "update sigma" step (TODO at ``src/optimize.jl:369``), run once the iteration's J_T is known:
+    ``sigma.refresh(**info)`` with the final-time states of this and of the previous iteration, chi(T), J_T."""
+    refresh = getattr(wrk.sigma, "refresh", None)
+    if refresh is None:
+        return
+    res = wrk.result
+    refresh(forward_states=[np.array(s) for s in res.states], J_T=res.J_T, J_T_prev=res.J_T_prev,
+            optimized_pulses=eps_ip1, guess_pulses=eps_i, trajectories=wrk.trajectories, result=res,
+            **wrk._sigma_info)
 
 
 def detached_result(res):
@@ -269,6 +291,8 @@ def optimize_krotov(problem, comm=None):
                 i += 1
                 krotov_iteration(wrk, eps_i, eps_ip1)
                 update_result(wrk, i)
+                if wrk.sigma is not None:
+                    update_sigma(wrk, eps_ip1, eps_i)
                 info = callback(wrk, i, eps_ip1, eps_i)
                 if info:
                     wrk.result.records.append(tuple(info))

@@ -26,6 +26,7 @@ from .errors import ArgumentError, ErrorException
 from .functionals import make_chi
 from .generators import Generator
 from .result import KrotovResult, convert_result
+from .second_order import sigma_value
 
 log = logging.getLogger("krotov_jl_b200")
 
@@ -283,7 +284,17 @@ class KrotovWrk:
         self.verbose = verbose
         self.store_fw = bool(kwargs.get("store_fw_states", False))
         self.fw_storage2 = None  # never read or written by the reference (src/workspace.jl:129-130)
+        # second order (`sigma`, src/optimize.jl:104-105; TODOs :187, :350, :369): see second_order.py
+        self.sigma = kwargs.get("sigma", None)
         self._build_device_side(tlist, comm)
+        if self.sigma is not None:
+            if not self._hermitian:
+                raise ArgumentError("`sigma` (second-order Krotov) needs Hermitian generators and control operators: "
+                                    "the device path folds the second-order term into the boundary condition chi(T)")
+            if kwargs.get("skip_initial_forward_propagation", False):
+                raise ArgumentError("`sigma` needs the forward states of the guess pulses: it cannot be combined with "
+                                    "`skip_initial_forward_propagation`")
+            sigma_value(self.sigma, tlist)  # (raises for a sigma that varies over the time grid)
         self.fw_storage = _Storage(self, B.FORWARD)
         self.bw_storage = _Storage(self, B.BACKWARD)
         self.fw_propagators = [_PropagatorView(self, k, False) for k in range(N)]
@@ -445,6 +456,7 @@ class KrotovWrk:
         # Hermitian generators: both directions propagate with the same matrices, so they share their
         # spectral envelopes (see ChebyDirection)
         shared = {} if all(same(m, adj(m)) for m in terms) else None
+        self._hermitian = shared is not None
 
         # ensembles on the persistent-kernel path: the spectral envelopes behind `reinit_prop!` are solved on the device
         # from the generator terms the handle holds (ChebyDirection uses it for Hermitian generators only, where both

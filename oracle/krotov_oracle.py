@@ -58,6 +58,8 @@ __all__ = [
     "ExpPropagator",
     "transform_control_ranges",
     "krotov_initial_fw_prop",
+    "sigma_on_intervals",
+    "numerical_estimate_A",
     "krotov_iteration",
     "optimize_krotov",
     "optimize_krotov_blocked",
@@ -525,6 +527,16 @@ class OracleWrk:
         self.tau_vals = np.zeros(N, complex)
         self.J_T = 0.0
         self.J_T_prev = 0.0
+        # second order only (`sigma`; TODO at src/optimize.jl:187 "if sigma, fw_storage0 = fw_storage"): the forward
+        # trajectory of the PREVIOUS iteration, column n = Psi^(i)(t_n) -- a separate pair of arrays because the
+        # iteration writes `fw_storage` shifted by one slot (sic, :367)
+        self.fw_storage0 = None
+        self.fw_storage1 = None
+
+    def enable_second_order(self):
+        N, d, N_T = self.p.N, self.p.d, self.p.N_T
+        self.fw_storage0 = [np.zeros((d, N_T + 1), complex) for _ in range(N)]
+        self.fw_storage1 = [np.zeros((d, N_T + 1), complex) for _ in range(N)]
 
 
 def krotov_initial_fw_prop(eps0, phi_k, k, wrk: OracleWrk):
@@ -535,15 +547,29 @@ def krotov_initial_fw_prop(eps0, phi_k, k, wrk: OracleWrk):
     Phi0 = wrk.fw_storage[k]
     if Phi0 is not None:
         Phi0[:, 0] = phi_k
+    prev = None if wrk.fw_storage0 is None else wrk.fw_storage0[k]
+    if prev is not None:
+        prev[:, 0] = phi_k
     N_T = len(wrk.tlist) - 1
     for n in range(N_T):
         psi = wrk.fw_propagators[k].prop_step()
         if Phi0 is not None:
             Phi0[:, n + 1] = psi
+        if prev is not None:
+            prev[:, n + 1] = psi
 
 
-def krotov_iteration(wrk: OracleWrk, eps_i, eps_ip1, chi=None):
-    """``src/optimize.jl:279-371``, same loop order, same storage slots."""
+def krotov_iteration(wrk: OracleWrk, eps_i, eps_ip1, chi=None, sigma_vals=None):
+    """``src/optimize.jl:279-371``, same loop order, same storage slots.
+
+    ``sigma_vals`` (one value per time interval) switches on the second-order update the reference documents
+    (``src/optimize.jl:104-105``) but leaves as TODOs (``:187, :350, :369``).  It is restated from the published
+    algorithm -- Reich, Ndong, Koch, J. Chem. Phys. 136, 104103 (2012), Eq. (33), as implemented by the `krotov`
+    Python package's ``optimize_pulses`` (``second_order`` branch): the overlap of interval n becomes
+
+        <chi_k(t_n)| mu |Psi_k(t_n)>  +  (sigma_n / 2) <Psi_k^(i+1)(t_n) - Psi_k^(i)(t_n)| mu |Psi_k^(i+1)(t_n)> ,
+
+    with Psi^(i) the forward trajectory of the previous iteration (``wrk.fw_storage0``)."""
     p = wrk.p
     tlist = wrk.tlist
     N_T = len(tlist) - 1
@@ -587,19 +613,28 @@ def krotov_iteration(wrk: OracleWrk, eps_i, eps_ip1, chi=None):
                 psi_k = wrk.fw_propagators[k].state
                 mu = wrk.control_derivs[k][l]
                 if mu is not None:
+                    ov = np.vdot(chi_k[k], mu @ psi_k)
+                    if sigma_vals is not None:  # second-order contribution (TODO at src/optimize.jl:350)
+                        ov = ov + 0.5 * sigma_vals[n] * np.vdot(psi_k - wrk.fw_storage0[k][:, n], mu @ psi_k)
                     if fac is None:
-                        du[l] += np.vdot(chi_k[k], mu @ psi_k).imag
+                        du[l] += ov.imag
                     else:
-                        du[l] += (fac * np.vdot(chi_k[k], mu @ psi_k)).imag
+                        du[l] += (fac * ov).imag
         for l in range(L):
             alpha = wrk.update_shapes[l][n] / wrk.lambda_vals[l]
             d_eps = alpha * du[l]
             eps_ip1[l][n] = eps_i[l][n] + d_eps
             wrk.g_a_int[l] += alpha * abs(du[l]) ** 2 * dt
         for k in range(N):
+            if sigma_vals is not None and n == 0:
+                wrk.fw_storage1[k][:, 0] = wrk.fw_propagators[k].state
             psi_k = wrk.fw_propagators[k].prop_step()
             if Phi[k] is not None:
                 Phi[k][:, n] = psi_k  # sic: slot n (src/optimize.jl:367)
+            if sigma_vals is not None:
+                wrk.fw_storage1[k][:, n + 1] = psi_k
+    if sigma_vals is not None:  # this iteration's trajectory is the next one's Psi^(i)
+        wrk.fw_storage0, wrk.fw_storage1 = wrk.fw_storage1, wrk.fw_storage0
 
 
 def update_result(wrk: OracleWrk):
@@ -612,21 +647,57 @@ def update_result(wrk: OracleWrk):
     return states
 
 
+def sigma_on_intervals(sigma, tlist):
+    """sigma(t) sampled like the pulses (``discretize_on_midpoints``): one value per time interval.  A number is a
+    time-independent sigma."""
+    if sigma is None:
+        return None
+    if callable(sigma):
+        return np.asarray(discretize_on_midpoints(lambda t: float(sigma(t)), tlist), float)
+    return np.full(len(tlist) - 1, float(sigma))
+
+
+def numerical_estimate_A(psi_new, psi_old, chi, delta_J_T):
+    """The estimate of the second-order constant A of Reich et al. (2012), Eq. (36), from one iteration, as the `krotov`
+    Python package's ``second_order.numerical_estimate_A`` forms it:
+        A = [ sum_k 2 Re<chi_k(T)|dPsi_k(T)> + dJ_T ] / sum_k |dPsi_k(T)|^2 ,   dPsi = Psi^(i+1)(T) - Psi^(i)(T)."""
+    dpsi = [np.asarray(a) - np.asarray(b) for a, b in zip(psi_new, psi_old)]
+    den = float(sum(np.vdot(x, x).real for x in dpsi))
+    if den <= 1e-30:
+        return 0.0
+    return (sum(2.0 * np.vdot(c, x).real for c, x in zip(chi, dpsi)) + delta_J_T) / den
+
+
 def optimize_krotov(p: ProblemArrays, iter_stop=5, prop_method="cheby",
-                    callback: Optional[Callable] = None, store_fw=False):
+                    callback: Optional[Callable] = None, store_fw=False, sigma=None):
     """The loop of ``src/optimize.jl:161-235`` with the bookkeeping the parity tests
-    compare: per-iteration J_T, ∫g_a dt, τ, and the final pulses."""
+    compare: per-iteration J_T, ∫g_a dt, τ, and the final pulses.
+
+    ``sigma``: None (first order), a number, a callable ``sigma(t)``, optionally with a method
+    ``refresh(forward_states=, forward_states0=, chi_states=, J_T=, J_T_prev=)`` called at the end of every iteration
+    (the "update sigma" TODO at ``src/optimize.jl:369``) with the final-time states of this and the previous
+    iteration and the chi(T) the iteration started from."""
     wrk = OracleWrk(p, prop_method=prop_method, store_fw=store_fw)
+    if sigma is not None:
+        wrk.enable_second_order()
     eps_i, eps_ip1 = wrk.pulses0, wrk.pulses1
     for k in range(p.N):
         krotov_initial_fw_prop(eps_i, p.psi0[k], k, wrk)
     states = update_result(wrk)
-    hist = dict(J_T=[wrk.J_T], g_a_int=[], tau=[wrk.tau_vals.copy()], m_fw=[], m_bw=[])
+    hist = dict(J_T=[wrk.J_T], g_a_int=[], tau=[wrk.tau_vals.copy()], m_fw=[], m_bw=[], sigma=[])
     if callback is not None:
         callback(wrk, 0, eps_ip1, eps_i)
     for i in range(1, iter_stop + 1):
-        krotov_iteration(wrk, eps_i, eps_ip1)
+        sv = sigma_on_intervals(sigma, wrk.tlist)
+        if sigma is not None:
+            hist["sigma"].append(sv.copy())
+            psi_old = [np.array(s) for s in states]
+            chi_T = [np.array(c, complex) for c in chi_states(p.functional, wrk.tau_vals, p.weights(), p.target)]
+        krotov_iteration(wrk, eps_i, eps_ip1, sigma_vals=sv)
         states = update_result(wrk)
+        if sigma is not None and hasattr(sigma, "refresh"):
+            sigma.refresh(forward_states=[np.array(s) for s in states], forward_states0=psi_old, chi_states=chi_T,
+                          J_T=wrk.J_T, J_T_prev=wrk.J_T_prev)
         hist["J_T"].append(wrk.J_T)
         hist["g_a_int"].append(wrk.g_a_int.copy())
         hist["tau"].append(wrk.tau_vals.copy())

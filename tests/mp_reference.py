@@ -41,11 +41,14 @@ def _step(psi, eps, dt):
     return (c * a - 1j * s * (-a / 2 + eps * b), c * b - 1j * s * (eps * a + b / 2))
 
 
-def tls_krotov_exact(iters=5, n_grid=501, dps=50, float_grid=True, amp_poly=None, amp_shape=None, lam=1):
+def tls_krotov_exact(iters=5, n_grid=501, dps=50, float_grid=True, amp_poly=None, amp_shape=None, lam=1, sigma=None):
     """J_T history, running costs and final pulses of the TLS optimisation in `dps`-digit arithmetic.
 
     float_grid: take the time grid and the guess pulse samples from their Float64 values (what both the reference
-    and the oracles start from) so that the comparison isolates the arithmetic of the loop."""
+    and the oracles start from) so that the comparison isolates the arithmetic of the loop.
+
+    sigma: None (first order) | a number | one number per time interval -- the second-order update of Reich, Ndong, Koch,
+    J. Chem. Phys. 136, 104103 (2012): the overlap gains (sigma_n / 2) <psi_new(t_n) - psi_old(t_n)| mu |psi_new(t_n)>."""
     mp.mp.dps = dps
     T, t_rise, lam = mp.mpf(5), mp.mpf("0.3"), mp.mpf(lam)
     # non-linear amplitude: H = -sz/2 + a(eps, n) sx,  a = shape[n] * sum_p c_p eps^p;  mu = dH/d eps = a'(eps, n) sx is
@@ -86,10 +89,16 @@ def tls_krotov_exact(iters=5, n_grid=501, dps=50, float_grid=True, amp_poly=None
     psi0 = (mp.mpc(1), mp.mpc(0))
     dts = [tl[n + 1] - tl[n] for n in range(N_T)]
 
+    if sigma is not None:
+        sig = [mp.mpf(float(x)) for x in sigma] if hasattr(sigma, "__len__") else [mp.mpf(float(sigma))] * N_T
+    old_traj = []
+
     def forward(e):
         psi = psi0
         for n in range(N_T):
+            old_traj.append(psi)
             psi = _step(psi, amp(e[n], n), dts[n])
+        old_traj.append(psi)
         return psi
 
     psi = forward(eps)
@@ -109,12 +118,18 @@ def tls_krotov_exact(iters=5, n_grid=501, dps=50, float_grid=True, amp_poly=None
         for n in range(N_T):
             c0, c1 = X[n]
             # <chi| sx |psi> = conj(c0) psi1 + conj(c1) psi0
-            du = damp(eps[n], n) * mp.im(mp.conj(c0) * psi[1] + mp.conj(c1) * psi[0])
+            ov = mp.conj(c0) * psi[1] + mp.conj(c1) * psi[0]
+            if sigma is not None:
+                d0, d1 = psi[0] - old_traj[n][0], psi[1] - old_traj[n][1]
+                ov += sig[n] / 2 * (mp.conj(d0) * psi[1] + mp.conj(d1) * psi[0])
+                old_traj[n] = psi  # (slot n is not read again in this iteration)
+            du = damp(eps[n], n) * mp.im(ov)
             alpha = mp.mpf(1) / lam  # S = 1
             new[n] = eps[n] + alpha * du
             ga += alpha * du * du * dts[n]
             psi = _step(psi, amp(new[n], n), dts[n])
         eps = new
+        old_traj[N_T] = psi
         tau = psi[1]
         J.append(1 - abs(tau) ** 2)
         ga_hist.append(ga)

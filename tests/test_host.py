@@ -424,3 +424,90 @@ def test_julia_bindings_match_the_header():
     defined = set(re.findall(r"^(?:function\s+)?(\w+!?)\(", src, flags=re.M))
     for fn in set(re.findall(r"LibKrotovCuda\.(\w+!?)\(", drv)):
         assert fn in defined or fn in ("Problem", "Handle"), fn
+
+
+# ---- the host driver on an oracle-backed engine (tests/oracle_engine.py) ---------------------------------------------
+@pytest.fixture
+def oracle_engine(monkeypatch):
+    """`KrotovCuda` replaced by the oracle-backed stand-in: the product's host driver runs on CPU (test-only)."""
+    import importlib
+
+    import oracle_engine as E
+
+    monkeypatch.setattr(importlib.import_module("krotov_jl_b200.workspace"), "KrotovCuda", E.OracleEngine)
+    before = E.OracleEngine.created
+    yield E
+    assert E.OracleEngine.created > before
+
+
+def test_host_driver_reproduces_the_oracle_loop_bit_for_bit(oracle_engine):
+    """optimize() -> KrotovWrk -> krotov_initial_fw_prop / krotov_iteration -> engine calls -> update_result, with the
+    engine's arithmetic done by the oracle: the pulse buffers, their swap, tau / J_T and the records must come out
+    exactly as the oracle's own loop of src/optimize.jl:161-235 produces them (built-in chi, user chi, continue_from)."""
+    from oracle import krotov_oracle as O
+    from util import run_product
+
+    for w in (W.c1_tls(), W.dummy_dense(d=10, n_traj=3, n_controls=2, n_grid=51, functional="ss")):
+        ref = O.optimize_krotov(W.to_oracle(w), 4)
+        got = run_product(w, 4)
+        assert np.array_equal(got["pulses"], ref["pulses"])
+        assert np.abs(np.array(got["J_T"]) - np.array(ref["J_T"])).max() < 5e-16  # (J_T is evaluated by the product's functional)
+        assert np.array_equal(np.array(got["g_a_int"]), np.array(ref["g_a_int"]))
+        # a user-supplied chi (KROTOV_CHI_HOST: chi(T) formed on the host and pushed with set_chi)
+        user = run_product(w, 4, chi=lambda Psi, trajs, tau=None: K.chi_ss(Psi, trajs, tau=tau) if w.functional == "ss"
+                           else K.chi_sm(Psi, trajs, tau=tau))
+        assert np.abs(user["pulses"] - ref["pulses"]).max() < 1e-14
+        # two iterations, then two more from the result (the pulses make the round trip midpoints -> grid -> midpoints)
+        a = run_product(w, 2)
+        b = run_product(w, 4, continue_from=a["result"])
+        assert b["result"].iter == 4 and np.abs(b["pulses"] - ref["pulses"]).max() < 1e-11
+
+
+def test_second_order_host_path_matches_general_formula(oracle_engine):
+    """`sigma` through the product's host path (chi(T) - sigma/2 Psi(T) pushed with set_chi, sigma.refresh after
+    update_result) against the oracle's general second-order update with a stored previous trajectory."""
+    from oracle import krotov_oracle as O
+    from util import run_product
+
+    for w, a0 in ((W.c1_tls(), 1.0), (W.dummy_dense(d=10, n_traj=3, n_controls=2, n_grid=51, functional="sm"), 0.2)):
+        for make in (lambda: -1.3 * a0, lambda: (lambda t: -0.8 * a0), lambda: K.NumericalSigma(a0, 0.1 * a0)):
+            ref = O.optimize_krotov(W.to_oracle(w), 4, sigma=make())
+            got = run_product(w, 4, sigma=make())
+            assert np.abs(np.array(got["J_T"]) - np.array(ref["J_T"])).max() < 1e-12
+            assert np.abs(got["pulses"] - ref["pulses"]).max() < 1e-12
+        first = O.optimize_krotov(W.to_oracle(w), 4)
+        assert np.abs(first["pulses"] - ref["pulses"]).max() > 1e-3
+    # refresh receives what it needs to re-estimate A
+    seen = []
+
+    class S(K.Sigma):
+        def __call__(self, t):
+            return -0.5
+
+        def refresh(self, **info):
+            seen.append(info)
+
+    w = W.c1_tls()
+    got = run_product(w, 2, sigma=S())
+    assert len(seen) == 2
+    i = seen[-1]
+    assert set(i) >= {"forward_states", "forward_states0", "chi_states", "J_T", "J_T_prev", "optimized_pulses", "guess_pulses",
+                      "trajectories", "result"}
+    assert i["J_T"] == got["J_T"][2] and i["J_T_prev"] == got["J_T"][1]
+    assert np.array_equal(i["forward_states"][0], got["result"].states[0])
+    tau_prev = got["tau"][1]
+    assert np.allclose(i["chi_states"][0], tau_prev[0] * w.target[0], atol=1e-15)  # chi_sm, N = 1, BEFORE the fold
+    A = K.numerical_estimate_A(i["forward_states"], i["forward_states0"], i["chi_states"], i["J_T"] - i["J_T_prev"])
+    assert np.isfinite(A)
+
+
+def test_sigma_argument_errors(oracle_engine):
+    w = W.c1_tls()
+    with pytest.raises(K.ArgumentError, match="varies over the time grid"):
+        K.optimize(to_problem(w, sigma=lambda t: -1.0 - t, iter_stop=1), method=K.Krotov)
+    with pytest.raises(K.ArgumentError, match="skip_initial_forward_propagation"):
+        K.optimize(to_problem(w, sigma=-1.0, skip_initial_forward_propagation=True, iter_stop=1), method=K.Krotov)
+    wn = W.dummy_dense(d=6, n_traj=2, n_controls=1, n_grid=11)
+    wn.H0 = [wn.H0[0] - 0.1j * np.eye(6)]
+    with pytest.raises(K.ArgumentError, match="Hermitian"):
+        K.optimize(to_problem(wn, sigma=-1.0, iter_stop=1), method=K.Krotov)

@@ -178,3 +178,80 @@ def test_c_oracle_reports_divergence_instead_of_crashing():
     w.functional, w.lambda_a = "ss", 1e-4
     with pytest.raises(RuntimeError):
         C.optimize_krotov_c(W.to_oracle(w), 4, n_threads=2)
+
+
+def test_second_order_oracle_against_50_digit_exact_propagator_optimisation():
+    """Second-order update (`sigma`; documented at src/optimize.jl:104-105, TODOs at :187, :350, :369; restated from
+    Reich, Ndong, Koch, J. Chem. Phys. 136, 104103 (2012) and the `krotov` Python package): the oracle's general formula
+    <chi + sigma_n/2 (Psi_new(t_n) - Psi_old(t_n))| mu |Psi_new(t_n)>  against the same update written independently in
+    50-digit arithmetic with the closed-form propagator -- for a constant sigma and for one that varies over the grid."""
+    import mp_reference as M
+
+    p = W.to_oracle(W.c1_tls())
+    for sigma in (-2.0, lambda t: -1.0 - 0.2 * t):
+        sv = O.sigma_on_intervals(sigma, p.tlist)
+        assert sv.shape == (p.N_T,) and (callable(sigma) or np.ptp(sv) == 0.0)
+        exact = M.tls_krotov_exact(3, sigma=list(sv))
+        for method, tol in (("expm", 5e-14), ("cheby", 1e-12)):
+            h = O.optimize_krotov(p, 3, method, sigma=sigma)
+            assert np.abs(np.array(h["J_T"]) - np.array(exact["J_T"])).max() < tol
+            assert np.abs(h["pulses"][0] - np.array(exact["pulses"])).max() < tol
+            assert np.abs(np.array([g[0] for g in h["g_a_int"]]) - np.array(exact["g_a_int"])).max() < tol
+    first = M.tls_krotov_exact(3)
+    assert abs(first["J_T"][-1] - exact["J_T"][-1]) > 1e-2  # (the second-order term is not a no-op here)
+
+
+def test_second_order_boundary_fold_identity():
+    """What the device path relies on (krotov.jl_b200/second_order.py): for Hermitian generators and a sigma that is
+    constant over the grid, the general second-order update equals the FIRST-order update started from the boundary
+    condition chi(T) - sigma/2 Psi_old(T).  Checked inside the oracle (no product code), to the propagator's accuracy."""
+    def folded(p, iters, sigma):
+        wrk = O.OracleWrk(p)
+        e0, e1 = wrk.pulses0, wrk.pulses1
+        for k in range(p.N):
+            O.krotov_initial_fw_prop(e0, p.psi0[k], k, wrk)
+        O.update_result(wrk)
+        J = [wrk.J_T]
+        for _ in range(iters):
+            def chi(Psi):
+                c = O.chi_states(p.functional, wrk.tau_vals, p.weights(), p.target)
+                return [np.array(ck) - 0.5 * sigma * np.array(ps) for ck, ps in zip(c, Psi)]
+            O.krotov_iteration(wrk, e0, e1, chi=chi)
+            O.update_result(wrk)
+            J.append(wrk.J_T)
+            e0, e1 = e1, e0
+        return np.array(J), np.array(e0)
+
+    for w, sigma in ((W.c1_tls(), -2.0), (W.c1_tls(), 0.7),
+                     (W.dummy_dense(d=10, n_traj=3, n_controls=2, n_grid=51, functional="ss"), -2.0),
+                     (W.dummy_dense(d=12, n_traj=4, n_controls=1, n_grid=31, functional="sm", seed=3), -0.4)):
+        a = O.optimize_krotov(W.to_oracle(w), 3, sigma=sigma)
+        J, e = folded(W.to_oracle(w), 3, sigma)
+        assert np.abs(J - np.array(a["J_T"])).max() < 1e-12 and np.abs(e - a["pulses"]).max() < 1e-12
+    # and it is an identity of UNITARY dynamics only: with a non-Hermitian drift the fold is wrong at first order in the loss
+    w = W.dummy_dense(d=10, n_traj=3, n_controls=2, n_grid=51, functional="ss")
+    w.H0 = [w.H0[0] - 0.05j * np.diag(np.arange(10.0))]
+    a = O.optimize_krotov(W.to_oracle(w), 2, sigma=-2.0)
+    J, e = folded(W.to_oracle(w), 2, -2.0)
+    assert np.abs(e - a["pulses"]).max() > 1e-6
+
+
+def test_numerical_estimate_of_A_vanishes_for_the_linear_functional():
+    """A = [sum_k 2 Re<chi_k|dPsi_k> + dJ_T] / sum_k |dPsi_k|^2 is the curvature of J_T along the step: exactly zero for
+    J_T_re (linear in the states), negative for the concave J_T_ss."""
+    class Rec:
+        def __init__(self):
+            self.A = []
+
+        def __call__(self, t):
+            return -0.1
+
+        def refresh(self, *, forward_states, forward_states0, chi_states, J_T, J_T_prev):
+            self.A.append(O.numerical_estimate_A(forward_states, forward_states0, chi_states, J_T - J_T_prev))
+
+    for functional, check in (("re", lambda A: abs(A) < 1e-12), ("ss", lambda A: A < -1e-3)):
+        w = W.dummy_dense(d=10, n_traj=3, n_controls=2, n_grid=51, functional=functional)
+        w.lambda_a = 0.05
+        s = Rec()
+        O.optimize_krotov(W.to_oracle(w), 3, sigma=s)
+        assert len(s.A) == 3 and all(check(A) for A in s.A), s.A

@@ -1273,3 +1273,35 @@ def test_device_envelope_solver_matches_lapack_and_the_optimisation_is_unchanged
     monkeypatch.setenv("KROTOV_HOST_ROWS", "1")
     host = run_product(w, 4)
     assert_parity(dev, host["J_T"], host["pulses"])
+
+
+# ---- second-order Krotov (sigma) -----------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["tls", "c4", "dense40", "c4-emulated-ranks", "spin-chain"])
+def test_second_order_sigma_matches_general_formula_oracle(case):
+    """The device path folds a time-independent sigma into the boundary condition of the backward sweep
+    (second_order.py); the oracle evaluates the general update  <chi + sigma/2 (Psi_new - Psi_old)| mu |Psi_new>  from a
+    stored previous trajectory (pinned by the 50-digit exact optimisation in tests/test_oracle.py).  One case per kernel
+    family: tiny, persistent warp kernel (several CTAs; ranks emulated with the replicated forward sweep), dense GEMM
+    stream / cluster sweep, sparse sweep.  sigma is re-estimated every iteration (NumericalSigma.refresh)."""
+    from oracle import krotov_oracle as O
+
+    kw = {}
+    if case == "tls":
+        w, a0 = W.c1_tls(), 1.0
+    elif case.startswith("c4"):
+        w, a0 = W.c4_ensemble(n_samples=2, n_grid=101), 0.004
+        w.lambda_a = 10.0
+        if case.endswith("ranks"):
+            kw = dict(emulate_ranks=2)
+    elif case == "dense40":
+        w, a0 = W.dummy_dense(d=40, n_traj=6, n_controls=2, n_grid=41, functional="ss", seed=11), 0.05
+    else:
+        w, a0 = W.spin_chain(n_spins=6, n_traj=8, n_grid=41), 0.05
+        kw = dict(force_path=3)
+    iters = 3
+    got = run_product(w, iters, sigma=K.NumericalSigma(a0, 0.1 * a0), **kw)
+    ref = O.optimize_krotov(W.to_oracle(w), iters, sigma=K.NumericalSigma(a0, 0.1 * a0))
+    assert abs(ref["sigma"][0][0] + 2.1 * a0) < 1e-15 and ref["sigma"][1][0] != ref["sigma"][0][0]  # (refresh changed it)
+    first = run_product(w, iters, **kw)
+    assert np.abs(got["pulses"] - first["pulses"]).max() > 1e-4  # the second-order term matters in this case
+    assert_parity(got, ref["J_T"], ref["pulses"], ref["g_a_int"])
