@@ -9,6 +9,7 @@
 using QuantumControl.QuantumPropagators.Controls: discretize
 using QuantumControl: set_atexit_save_optimization
 using Dates: now, value
+using LinearAlgebra: ⋅, ishermitian
 using Printf
 
 import QuantumControl: optimize, make_print_iters
@@ -44,7 +45,17 @@ function krotov_iteration(wrk, ϵ⁽ⁱ⁾, ϵ⁽ⁱ⁺¹⁾)
         chi = wrk.kwargs[:chi]
         Ψ = final_states(wrk)
         χ = wrk.chi_takes_tau ? chi(Ψ, wrk.trajectories; tau = wrk.result.tau_vals) : chi(Ψ, wrk.trajectories)
-        LibKrotovCuda.set_chi(wrk.handle, reduce(hcat, [Vector{ComplexF64}(x) for x in χ]))
+        χT = reduce(hcat, [Vector{ComplexF64}(x) for x in χ])
+        if wrk.sigma !== nothing
+            # second order (the TODO at src/optimize.jl:350 of the reference).  For Hermitian generators and a sigma that is
+            # constant over the time grid, chi(t_n) + sigma/2 (Psi^(i+1)(t_n) - Psi^(i)(t_n)) acts in the update like the
+            # backward-propagated chi(T) - sigma/2 Psi^(i)(T): Im<Psi|mu|Psi> = 0 and the backward propagator under the
+            # guess pulses inverts the forward propagator that produced Psi^(i).  No second forward storage is needed.
+            σ = sigma_value(wrk.sigma, wrk.result.tlist)
+            wrk.sigma_info = (forward_states0 = map(copy, Ψ), chi_states = [Vector{ComplexF64}(x) for x in χ])
+            χT = χT .- (σ / 2) .* reduce(hcat, Ψ)
+        end
+        LibKrotovCuda.set_chi(wrk.handle, χT)
     end
     # `reinit_prop!` of the backward propagators under the guess pulses, then of the forward propagators, whose check
     # sees the update buffers as they are NOW (the reference's aliased arrays)
@@ -81,6 +92,37 @@ function update_result!(wrk::KrotovWrk, i::Int64)
     before = res.end_local_time
     res.end_local_time = now()
     res.secs = value(res.end_local_time - before) / 1000.0
+end
+
+# The "update sigma" step (TODO at src/optimize.jl:369 of the reference), once the iteration's J_T is known: a sigma that
+# defines `refresh!` is handed the final-time states of this and of the previous iteration, chi(T), J_T.
+function update_sigma!(wrk::KrotovWrk, ϵ⁽ⁱ⁺¹⁾, ϵ⁽ⁱ⁾)
+    applicable(refresh!, wrk.sigma) || return
+    res = wrk.result
+    refresh!(wrk.sigma; forward_states = map(copy, res.states), J_T = res.J_T, J_T_prev = res.J_T_prev,
+             optimized_pulses = ϵ⁽ⁱ⁺¹⁾, guess_pulses = ϵ⁽ⁱ⁾, trajectories = wrk.trajectories, result = res, wrk.sigma_info...)
+end
+
+"""Hook for second-order functions: `refresh!(sigma; forward_states, forward_states0, chi_states, J_T, J_T_prev, ...)`."""
+function refresh! end
+
+# Estimate of the second-order constant A from one iteration (Reich, Ndong, Koch, J. Chem. Phys. 136, 104103 (2012)):
+#   A = [ sum_k 2 Re<chi_k(T)|dPsi_k(T)> + dJ_T ] / sum_k |dPsi_k(T)|^2 ,   dPsi = Psi^(i+1)(T) - Psi^(i)(T)
+function numerical_estimate_A(forward_states, forward_states0, chi_states, ΔJ_T)
+    ΔΨ = [a - b for (a, b) in zip(forward_states, forward_states0)]
+    den = sum(real(x ⋅ x) for x in ΔΨ)
+    den <= 1e-30 && return 0.0
+    (sum(2 * real(c ⋅ x) for (c, x) in zip(chi_states, ΔΨ)) + ΔJ_T) / den
+end
+
+# sigma(t) = -max(eps_A, 2A + eps_A), A re-estimated after every iteration
+mutable struct NumericalSigma
+    A::Float64
+    eps_A::Float64
+end
+(s::NumericalSigma)(t) = -max(s.eps_A, 2 * s.A + s.eps_A)
+function refresh!(s::NumericalSigma; forward_states, forward_states0, chi_states, J_T, J_T_prev, kwargs...)
+    s.A = numerical_estimate_A(forward_states, forward_states0, chi_states, J_T - J_T_prev)
 end
 
 function finalize_result!(ϵ_opt, wrk::KrotovWrk)
@@ -122,6 +164,7 @@ function optimize_krotov(problem)
             i += 1
             krotov_iteration(wrk, ϵ⁽ⁱ⁾, ϵ⁽ⁱ⁺¹⁾)   # a non-zero status of the library is an ErrorException raised here
             update_result!(wrk, i)
+            wrk.sigma === nothing || update_sigma!(wrk, ϵ⁽ⁱ⁺¹⁾, ϵ⁽ⁱ⁾)
             record!(callback(wrk, i, ϵ⁽ⁱ⁺¹⁾, ϵ⁽ⁱ⁾))
             check_convergence!(wrk.result)
             ϵ⁽ⁱ⁾, ϵ⁽ⁱ⁺¹⁾ = ϵ⁽ⁱ⁺¹⁾, ϵ⁽ⁱ⁾

@@ -155,6 +155,20 @@ mutable struct KrotovWrk
     fw_cheby::ChebySettings
     bw_cheby::ChebySettings
     states_cache::Union{Nothing,Matrix{ComplexF64}}
+    # ---- second order (`sigma`, documented at src/optimize.jl:104-105 of the reference, TODOs at :187, :350, :369)
+    sigma            # nothing | a number | a callable sigma(t), optionally with a method `refresh!(sigma; info...)`
+    sigma_info       # what `update_sigma!` hands to `refresh!`: Psi^(i)(T) and the chi(T) the iteration started from
+end
+
+# The one value a sigma takes over the time grid (sampled like the pulses).  The device path folds a time-independent
+# sigma into the boundary condition of the backward sweep (see `krotov_iteration`); anything else is refused.
+function sigma_value(sigma, tlist)
+    vals = sigma isa Number ? fill(Float64(sigma), length(tlist) - 1) : discretize_on_midpoints(t -> Float64(sigma(t)), tlist)
+    all(isfinite, vals) || throw(ArgumentError("sigma(t) is not finite on the time grid"))
+    all(==(vals[1]), vals) || throw(ArgumentError(
+        "sigma(t) varies over the time grid: the device path folds a time-independent sigma into the boundary " *
+        "condition of the backward sweep; re-estimate it per iteration in `refresh!` instead"))
+    vals[1]
 end
 
 function final_states(wrk::KrotovWrk)
@@ -260,6 +274,16 @@ function KrotovWrk(problem::QuantumControl.ControlProblem; verbose = false)
             end
         end
     end
+    sigma = get(kwargs, :sigma, nothing)
+    if sigma !== nothing
+        all(ishermitian(@view vals[:, :, t, g]) for t in 1:(1+L), g in eachindex(gens)) || throw(ArgumentError(
+            "`sigma` (second-order Krotov) needs Hermitian generators and control operators: the device path folds the " *
+            "second-order term into the boundary condition chi(T)"))
+        get(kwargs, :skip_initial_forward_propagation, false) && throw(ArgumentError(
+            "`sigma` needs the forward states of the guess pulses: it cannot be combined with `skip_initial_forward_propagation`"))
+        sigma_value(sigma, tlist)
+        chi_kind = LibKrotovCuda.KROTOV_CHI_HOST   # chi(T) - sigma/2 Psi(T) is formed on the host and pushed with set_chi
+    end
     psi0 = reduce(hcat, [Vector{ComplexF64}(t.initial_state) for t in trajectories])
     targets = have_targets ? reduce(hcat, [Vector{ComplexF64}(t.target_state) for t in trajectories]) : Matrix{ComplexF64}(undef, 0, 0)
     weights = Float64[hasproperty(t, :weight) ? t.weight : 1.0 for t in trajectories]
@@ -287,7 +311,7 @@ function KrotovWrk(problem::QuantumControl.ControlProblem; verbose = false)
         trajectories, adjoint_trajectories, kwargs, controls, pulses0, pulses1, zeros(L), update_shapes, lambda_vals,
         J_T_takes_tau, chi_takes_tau, result, control_derivs, fw_prop_kwargs, bw_prop_kwargs,
         nothing, nothing, nothing, nothing, nothing, get(kwargs, :use_threads, false),
-        handle, chi_kind, fw_cheby, bw_cheby, nothing,
+        handle, chi_kind, fw_cheby, bw_cheby, nothing, sigma, nothing,
     )
     wrk.fw_storage = StorageView(wrk, LibKrotovCuda.KROTOV_FORWARD)
     wrk.bw_storage = StorageView(wrk, LibKrotovCuda.KROTOV_BACKWARD)
