@@ -96,9 +96,13 @@ class OracleEngine:
 
     # -- results --------------------------------------------------------------------------
     def states(self):
+        if self.wrk is None:  # no sweep yet (skip_initial_forward_propagation): the handle holds Psi(0) and its tau
+            return np.array(self.p.psi0)
         return np.array([prop.state for prop in self.wrk.fw_propagators])
 
     def tau(self):
+        if self.wrk is None:
+            return O.taus(list(self.p.psi0), self.p.target)
         return np.array(self.wrk.tau_vals)
 
     def storage(self, which, k, n0=0, n1=None):
