@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["taus", "J_T_sm", "J_T_ss", "J_T_re", "chi_sm", "chi_ss", "chi_re", "make_chi"]
+__all__ = ["taus", "J_T_sm", "J_T_ss", "J_T_re", "chi_sm", "chi_ss", "chi_re", "chi_coefficients", "make_chi"]
 
 
 def taus(states, trajectories, ignore_missing_target_state=False):
@@ -65,6 +65,20 @@ def chi_re(states, trajectories, tau=None):
     tau, w = _tau_w(states, trajectories, tau)
     n = len(tau)
     return [(w[k] / (2 * n)) * trajectories[k].target_state for k in range(n)]
+
+
+def chi_coefficients(kind, tau, w):
+    """c_k with chi_k = c_k |target_k> for the three analytic functionals, all trajectories at once (what the device
+    forms in ``chi_coef_kernel``; used on the host where chi(T) is needed as an array, e.g. second_order.py)."""
+    tau, w = np.asarray(tau, np.complex128), np.asarray(w, np.float64)
+    n = len(tau)
+    if kind == "sm":
+        return (w / n**2) * np.sum(w * tau)
+    if kind == "ss":
+        return (w / n) * tau
+    if kind == "re":
+        return (w / (2 * n)).astype(np.complex128)
+    raise ValueError(kind)
 
 
 chi_sm.krotov_builtin = "sm"

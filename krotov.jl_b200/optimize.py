@@ -21,6 +21,7 @@ from . import _lib as B
 from .cheby import transform_control_ranges
 from .controls import discretize
 from .errors import ArgumentError
+from .functionals import chi_coefficients
 from .second_order import sigma_value
 from .workspace import KrotovWrk
 
@@ -65,23 +66,28 @@ def krotov_iteration(wrk, eps_i, eps_ip1):
     ``krotov_iterate`` = backward sweep + sequential update + forward sweep on the device."""
     # chi_k(T)  (:297-302)
     if wrk.functional == B.CHI_HOST or wrk.sigma is not None:
-        chi_fn = wrk.kwargs["chi"]
-        Psi = wrk.result.states
-        if wrk.chi_takes_tau:
-            chi = chi_fn(Psi, wrk.trajectories, tau=wrk.result.tau_vals)
-        else:
-            chi = chi_fn(Psi, wrk.trajectories)
         lo, hi = wrk._shard
-        chi_T = np.array(chi[lo:hi], np.complex128)
+        Psi = wrk.result.states
+        if wrk.functional == B.CHI_HOST:
+            chi_fn = wrk.kwargs["chi"]
+            if wrk.chi_takes_tau:
+                chi = chi_fn(Psi, wrk.trajectories, tau=wrk.result.tau_vals)
+            else:
+                chi = chi_fn(Psi, wrk.trajectories)
+            chi = np.array([np.asarray(c) for c in chi], np.complex128)
+        else:  # (second order with a built-in functional: chi = c_k |target_k>, all trajectories at once)
+            kind = {B.CHI_SM: "sm", B.CHI_SS: "ss", B.CHI_RE: "re"}[wrk.functional]
+            chi = chi_coefficients(kind, wrk.result.tau_vals, wrk._weight)[:, None] * wrk._target
+        chi_T = chi[lo:hi]
         if wrk.sigma is not None:
             # second order (the TODO at :350): for Hermitian generators and a sigma that is constant over the time
             # grid, chi(t_n) + sigma/2 (Psi^(i+1)(t_n) - Psi^(i)(t_n)) acts in the update like the backward-propagated
             # chi(T) - sigma/2 Psi^(i)(T)  (second_order.py)
             sig = sigma_value(wrk.sigma, wrk.result.tlist)
-            psi_T = np.array([np.asarray(s) for s in Psi], np.complex128)
-            wrk._sigma_info = dict(forward_states0=list(psi_T), chi_states=[np.array(c, np.complex128) for c in chi])
+            psi_T = np.array(Psi._get() if hasattr(Psi, "_get") else [np.asarray(s) for s in Psi], np.complex128)
+            wrk._sigma_info = dict(forward_states0=list(psi_T), chi_states=list(chi))
             chi_T = chi_T - (0.5 * sig) * psi_T[lo:hi]
-        wrk.engine.set_chi(chi_T)
+        wrk.engine.set_chi(np.ascontiguousarray(chi_T))
     elif wrk._n_ranks > 1 and wrk.functional == B.CHI_SM:
         # the only functional whose chi needs a sum over ALL ranks' tau: done here from the gathered tau
         tau, w, n = wrk.result.tau_vals, wrk._weight, wrk.N
