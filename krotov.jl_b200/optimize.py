@@ -83,9 +83,9 @@ def krotov_iteration(wrk, eps_i, eps_ip1):
             # second order (the TODO at :350): for Hermitian generators and a sigma that is constant over the time
             # grid, chi(t_n) + sigma/2 (Psi^(i+1)(t_n) - Psi^(i)(t_n)) acts in the update like the backward-propagated
             # chi(T) - sigma/2 Psi^(i)(T)  (second_order.py)
-            sig = sigma_value(wrk.sigma, wrk.result.tlist)
+            sig = sigma_value(wrk.sigma, wrk.result.tlist, full=False)
             psi_T = np.array(Psi._get() if hasattr(Psi, "_get") else [np.asarray(s) for s in Psi], np.complex128)
-            wrk._sigma_info = dict(forward_states0=list(psi_T), chi_states=list(chi))
+            wrk._sigma_info = dict(forward_states0=psi_T, chi_states=chi)
             chi_T = chi_T - (0.5 * sig) * psi_T[lo:hi]
         wrk.engine.set_chi(np.ascontiguousarray(chi_T))
     elif wrk._n_ranks > 1 and wrk.functional == B.CHI_SM:
@@ -143,7 +143,9 @@ def update_sigma(wrk, eps_ip1, eps_i):
     if refresh is None:
         return
     res = wrk.result
-    refresh(forward_states=[np.array(s) for s in res.states], J_T=res.J_T, J_T_prev=res.J_T_prev,
+    Psi = res.states
+    new = np.array(Psi._get() if hasattr(Psi, "_get") else [np.asarray(s) for s in Psi], np.complex128)
+    refresh(forward_states=new, J_T=res.J_T, J_T_prev=res.J_T_prev,
             optimized_pulses=eps_ip1, guess_pulses=eps_i, trajectories=wrk.trajectories, result=res,
             **wrk._sigma_info)
 

@@ -37,7 +37,8 @@ __all__ = ["Sigma", "NumericalSigma", "numerical_estimate_A", "sigma_value"]
 class Sigma:
     """Base class of a second-order function: callable ``sigma(t)``, optionally ``refresh(**info)`` once per iteration
     (the "update sigma" TODO at ``src/optimize.jl:369``).  ``info`` holds ``forward_states`` / ``forward_states0`` (the
-    final-time states of this and of the previous iteration), ``chi_states`` (chi(T) the iteration started from),
+    final-time states of this and of the previous iteration, row k = trajectory k), ``chi_states`` (chi(T) the iteration
+    started from, before the fold),
     ``J_T``, ``J_T_prev``, ``optimized_pulses``, ``guess_pulses``, ``trajectories``, ``result``."""
 
     def __call__(self, t):
@@ -50,12 +51,12 @@ class Sigma:
 def numerical_estimate_A(forward_states, forward_states0, chi_states, delta_J_T):
     """Estimate of the constant A of the second-order construction from one iteration (Reich et al. 2012, Eq. (36)):
     ``A = [sum_k 2 Re<chi_k(T)|dPsi_k(T)> + dJ_T] / sum_k |dPsi_k(T)|^2`` with ``dPsi = Psi^(i+1)(T) - Psi^(i)(T)``."""
-    dpsi = [np.asarray(a) - np.asarray(b) for a, b in zip(forward_states, forward_states0)]
-    den = float(sum(np.vdot(x, x).real for x in dpsi))
+    dpsi = np.asarray(forward_states, np.complex128) - np.asarray(forward_states0, np.complex128)  # (N, d)
+    den = float(np.vdot(dpsi, dpsi).real)
     if den <= 1e-30:
         return 0.0
-    num = sum(2.0 * np.vdot(np.asarray(c), x).real for c, x in zip(chi_states, dpsi)) + delta_J_T
-    return float(num) / den
+    num = 2.0 * float(np.vdot(np.asarray(chi_states, np.complex128), dpsi).real) + delta_J_T
+    return num / den
 
 
 class NumericalSigma(Sigma):
@@ -72,12 +73,18 @@ class NumericalSigma(Sigma):
         self.A = numerical_estimate_A(forward_states, forward_states0, chi_states, J_T - J_T_prev)
 
 
-def sigma_value(sigma, tlist):
-    """The one value a sigma takes over the time grid (sampled like the pulses, on the interval midpoints)."""
-    if callable(sigma):
+def sigma_value(sigma, tlist, full=True):
+    """The one value a sigma takes over the time grid (sampled like the pulses, on the interval midpoints).
+    ``full=False`` samples the first, a middle and the last interval only: the per-iteration re-check after
+    ``sigma.refresh`` (the full grid was checked when the workspace was built)."""
+    if not callable(sigma):
+        vals = np.array([float(sigma)])
+    elif full:
         vals = np.asarray(discretize_on_midpoints(lambda t: float(sigma(t)), tlist), np.float64)
     else:
-        vals = np.full(len(tlist) - 1, float(sigma))
+        n = len(tlist) - 1
+        vals = np.array([float(sigma(tlist[0])), float(sigma(0.5 * (tlist[n // 2] + tlist[n // 2 + 1]))) if n > 2
+                         else float(sigma(tlist[0])), float(sigma(tlist[-1]))])
     if not np.all(np.isfinite(vals)):
         raise ArgumentError("sigma(t) is not finite on the time grid")
     if np.ptp(vals) != 0.0:
