@@ -1276,13 +1276,13 @@ def test_device_envelope_solver_matches_lapack_and_the_optimisation_is_unchanged
 
 
 # ---- second-order Krotov (sigma) -----------------------------------------------------------------------
-@pytest.mark.parametrize("case", ["tls", "c4", "dense40", "c4-emulated-ranks", "spin-chain"])
+@pytest.mark.parametrize("case", ["tls", "c4", "dense40", "c4-emulated-ranks", "c4-emulated-ranks-shard", "spin-chain"])
 def test_second_order_sigma_matches_general_formula_oracle(case):
     """The device path folds a time-independent sigma into the boundary condition of the backward sweep
     (second_order.py); the oracle evaluates the general update  <chi + sigma/2 (Psi_new - Psi_old)| mu |Psi_new>  from a
     stored previous trajectory (pinned by the 50-digit exact optimisation in tests/test_oracle.py).  One case per kernel
-    family: tiny, persistent warp kernel (several CTAs; ranks emulated with the replicated forward sweep), dense GEMM
-    stream / cluster sweep, sparse sweep.  sigma is re-estimated every iteration (NumericalSigma.refresh)."""
+    family: tiny, persistent warp kernel (several CTAs; ranks emulated with the replicated forward sweep and with sharded
+    trajectories), dense GEMM stream / cluster sweep, sparse sweep.  sigma is re-estimated every iteration (NumericalSigma.refresh)."""
     from oracle import krotov_oracle as O
 
     kw = {}
@@ -1293,6 +1293,8 @@ def test_second_order_sigma_matches_general_formula_oracle(case):
         w.lambda_a = 10.0
         if case.endswith("ranks"):
             kw = dict(emulate_ranks=2)
+        elif case.endswith("shard"):  # every rank holds its block of trajectories: set_chi per shard, per-step exchange
+            kw = dict(emulate_ranks=2, multi_gpu="shard")
     elif case == "dense40":
         w, a0 = W.dummy_dense(d=40, n_traj=6, n_controls=2, n_grid=41, functional="ss", seed=11), 0.05
     else:
