@@ -511,3 +511,25 @@ def test_sigma_argument_errors(oracle_engine):
     wn.H0 = [wn.H0[0] - 0.1j * np.eye(6)]
     with pytest.raises(K.ArgumentError, match="Hermitian"):
         K.optimize(to_problem(wn, sigma=-1.0, iter_stop=1), method=K.Krotov)
+
+
+def test_product_never_touches_the_oracle_or_a_cpu_fallback():
+    """The oracle (and the oracle-backed engine the CPU tests inject) is test infrastructure: nothing under
+    krotov.jl_b200/, include/ or julia/ may import, link or name it, and the product's engine has exactly one way to
+    compute -- the handle of libkrotov_cuda (`krotov_create` fails without a GPU, see test_create_without_gpu_fails_loudly)."""
+    bad = []
+    for top in ("krotov.jl_b200", "include", "julia"):
+        for folder, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if not f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):
+                    continue
+                with open(os.path.join(folder, f), encoding="utf-8") as fh:
+                    for n, line in enumerate(fh, 1):
+                        if re.search(r"\b(import|from|include|dlopen|CDLL)\b.*\boracle", line) or "oracle_engine" in line or "libkrotov_oracle" in line:
+                            bad.append(f"{os.path.relpath(os.path.join(folder, f), ROOT)}:{n}: {line.strip()}")
+    assert not bad, bad
+    import importlib
+
+    eng = importlib.import_module("krotov_jl_b200.engine")
+    ws = importlib.import_module("krotov_jl_b200.workspace")
+    assert ws.KrotovCuda is eng.KrotovCuda  # (outside the tests that patch it, the workspace builds the CUDA engine)
