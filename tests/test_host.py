@@ -426,6 +426,75 @@ def test_julia_bindings_match_the_header():
         assert fn in defined or fn in ("Problem", "Handle"), fn
 
 
+def _jl_strip(src):
+    """Julia source without comments, strings (incl. interpolations) and character literals."""
+    out, i, n = [], 0, len(src)
+    while i < n:
+        if src.startswith('"""', i):
+            i = src.find('"""', i + 3) + 3
+            out.append('""')
+            continue
+        c = src[i]
+        if c == '"':
+            j = i + 1
+            while j < n and src[j] != '"':
+                if src[j] == "\\":
+                    j += 1
+                elif src[j] == "$" and j + 1 < n and src[j + 1] == "(":
+                    depth, k = 0, j + 1
+                    while k < n:
+                        depth += (src[k] == "(") - (src[k] == ")")
+                        if depth == 0:
+                            break
+                        k += 1
+                    j = k
+                j += 1
+            i = j + 1
+            out.append('""')
+            continue
+        if c == "#":
+            j = src.find("\n", i)
+            i = n if j < 0 else j
+            continue
+        if c == "'" and i + 2 < n and (src[i + 2] == "'" or (src[i + 1] == "\\" and i + 3 < n and src[i + 3] == "'")):
+            i += 3 if src[i + 2] == "'" else 4
+            out.append("' '")
+            continue
+        out.append(c)
+        i += 1
+    return "".join(out)
+
+
+def test_julia_sources_have_balanced_blocks():
+    """Julia cannot run here, so the module cannot even be parsed by its own compiler; this catches the crudest class of
+    slip in an edit: every block opener (function / if / for / while / begin / let / try / struct / module / do) outside
+    brackets has its `end`, brackets balance, and `end` inside an index expression is not counted."""
+    openers = {"function", "if", "for", "while", "begin", "let", "try", "struct", "module", "do", "quote", "macro"}
+    folder = os.path.join(ROOT, "julia", "Krotov", "src")
+    for name in sorted(os.listdir(folder)):
+        s = _jl_strip(open(os.path.join(folder, name), encoding="utf-8").read())
+        stack, par, sq, line = [], 0, 0, 1
+        for m in re.finditer(r"\n|[\[\]\(\)]|:?[^\W\d]\w*!?", s):
+            t = m.group(0)
+            if t == "\n":
+                line += 1
+            elif t in "()":
+                par += 1 if t == "(" else -1
+            elif t in "[]":
+                sq += 1 if t == "[" else -1
+            elif t.startswith(":") or sq > 0:
+                continue
+            elif t in openers:
+                if not (t in ("for", "if") and par > 0):  # (generators inside parentheses need no `end`)
+                    stack.append((t, line))
+            elif t == "end":
+                assert stack, f"{name}:{line}: `end` without an opener"
+                stack.pop()
+            assert par >= 0 and sq >= 0, f"{name}:{line}: closing bracket without an opener"
+        assert not stack, f"{name}: unclosed {stack[-3:]}"
+        assert par == 0 and sq == 0, f"{name}: unbalanced brackets"
+
+
 # ---- the host driver on an oracle-backed engine (tests/oracle_engine.py) ---------------------------------------------
 @pytest.fixture
 def oracle_engine(monkeypatch):
