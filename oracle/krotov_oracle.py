@@ -559,7 +559,7 @@ def krotov_initial_fw_prop(eps0, phi_k, k, wrk: OracleWrk):
             prev[:, n + 1] = psi
 
 
-def krotov_iteration(wrk: OracleWrk, eps_i, eps_ip1, chi=None, sigma_vals=None):
+def krotov_iteration(wrk: OracleWrk, eps_i, eps_ip1, chi=None, sigma_vals=None, reduce_du=None):
     """``src/optimize.jl:279-371``, same loop order, same storage slots.
 
     ``sigma_vals`` (one value per time interval) switches on the second-order update the reference documents
@@ -569,7 +569,11 @@ def krotov_iteration(wrk: OracleWrk, eps_i, eps_ip1, chi=None, sigma_vals=None):
 
         <chi_k(t_n)| mu |Psi_k(t_n)>  +  (sigma_n / 2) <Psi_k^(i+1)(t_n) - Psi_k^(i)(t_n)| mu |Psi_k^(i+1)(t_n)> ,
 
-    with Psi^(i) the forward trajectory of the previous iteration (``wrk.fw_storage0``)."""
+    with Psi^(i) the forward trajectory of the previous iteration (``wrk.fw_storage0``).
+
+    ``reduce_du`` (tests of the multi-rank host logic): when this workspace holds only a shard of the trajectories, the
+    callable sums the per-step overlap vector over all shards -- the one cross-rank dependency of a time step
+    (``src/optimize.jl:340-349`` sums over ALL k)."""
     p = wrk.p
     tlist = wrk.tlist
     N_T = len(tlist) - 1
@@ -620,6 +624,8 @@ def krotov_iteration(wrk: OracleWrk, eps_i, eps_ip1, chi=None, sigma_vals=None):
                         du[l] += ov.imag
                     else:
                         du[l] += (fac * ov).imag
+        if reduce_du is not None:
+            du = np.asarray(reduce_du(du), float)
         for l in range(L):
             alpha = wrk.update_shapes[l][n] / wrk.lambda_vals[l]
             d_eps = alpha * du[l]

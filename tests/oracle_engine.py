@@ -18,7 +18,7 @@ class OracleEngine:
     created = 0  # how many engines the tests made (to prove the patch was in effect)
 
     def __init__(self, *, tlist, H0, Hc, gen_of_traj, psi0, target=None, weight=None, update_shape, lambda_a,
-                 functional=0, n_traj_global=0, store_fw=False, **_):
+                 functional=0, n_traj_global=0, store_fw=False, replicated_forward=False, **_):
         OracleEngine.created += 1
         dense = lambda m: None if m is None else np.asarray(m.toarray() if hasattr(m, "toarray") else m, complex)  # noqa: E731
         psi0 = np.asarray(psi0, complex)
@@ -33,6 +33,9 @@ class OracleEngine:
             lam=np.asarray(lambda_a, float).reshape(self.L), weight=None if weight is None else np.asarray(weight, float),
             functional=self.functional if self.functional != "host" else "sm")
         self.store_fw = bool(store_fw)
+        self.n_global = int(n_traj_global) or self.N  # > N: this engine holds one rank's shard of the trajectories
+        self._reduce = None
+        self.replicated = bool(replicated_forward)  # every rank holds all trajectories: no per-step exchange
         self.wrk = None
         self.cheby_pushed = []
         self._chi = None
@@ -84,7 +87,14 @@ class OracleEngine:
             chi = lambda Psi, c=self._chi_coef: [c[k] * self.p.target[k] for k in range(self.N)]  # noqa: E731
         elif self.functional == "host":
             raise RuntimeError("functional is KROTOV_CHI_HOST: call set_chi before iterate")
-        O.krotov_iteration(self.wrk, eps_i, eps_ip1, chi=chi)
+        elif self.n_global != self.N:
+            # a shard forms its boundary condition with the GLOBAL trajectory count (krotov_problem.n_traj_global)
+            if self.functional == "sm":
+                raise RuntimeError("multi-rank J_T_sm needs krotov_set_chi_coeffs (global sum of tau)")
+            w, n = self.p.weights(), self.n_global
+            c = (w / n) * self.wrk.tau_vals if self.functional == "ss" else (w / (2 * n)).astype(complex)
+            chi = lambda Psi, c=c: [c[k] * self.p.target[k] for k in range(self.N)]  # noqa: E731
+        O.krotov_iteration(self.wrk, eps_i, eps_ip1, chi=chi, reduce_du=self._reduce)
         O.update_result(self.wrk)
         self._chi = self._chi_coef = None
         self._bufs = [eps_ip1, eps_i]
@@ -109,6 +119,25 @@ class OracleEngine:
         n1 = self.N_T + 1 if n1 is None else n1
         src = self.wrk.bw_storage if which == 1 else self.wrk.fw_storage
         return np.array(src[k][:, n0:n1].T)
+
+    # -- multi-rank (gloo tests): the per-step overlap sums cross the ranks through torch.distributed -----------------
+    def comm_export(self):
+        return bytes(256)
+
+    def comm_connect(self, rank, world, descs):
+        import torch
+        import torch.distributed as dist
+
+        assert len(descs) == world
+        if self.replicated:
+            return
+
+        def reduce(du):
+            t = torch.from_numpy(np.array(du, float))
+            dist.all_reduce(t)
+            return t.numpy()
+
+        self._reduce = reduce
 
     def close(self):
         pass

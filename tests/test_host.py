@@ -602,3 +602,74 @@ def test_product_never_touches_the_oracle_or_a_cpu_fallback():
     eng = importlib.import_module("krotov_jl_b200.engine")
     ws = importlib.import_module("krotov_jl_b200.workspace")
     assert ws.KrotovCuda is eng.KrotovCuda  # (outside the tests that patch it, the workspace builds the CUDA engine)
+
+
+# ---- two ranks over gloo: the product's multi-rank HOST path on the oracle-backed engine -----------------------------------
+def _gloo_driver_worker(rank, world, port, out, functional, mode, use_sigma):
+    import importlib
+
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import oracle_engine as E
+        from krotov_jl_b200.distributed import Comm
+
+        importlib.import_module("krotov_jl_b200.workspace").KrotovCuda = E.OracleEngine
+        comm = Comm(device=rank)
+        w = _two_rank_workload(functional)
+        hist = {"J_T": []}
+
+        def cb(wrk, it, eps_new, eps_old):
+            hist["J_T"].append(wrk.result.J_T)
+            hist["pulses"] = np.array([np.array(e) for e in eps_new])
+            hist["shard"] = wrk._shard
+            hist["tau"] = np.array(wrk.result.tau_vals)
+
+        kw = dict(sigma=K.NumericalSigma(0.3, 0.05)) if use_sigma else {}
+        res = K.optimize(to_problem(w, iter_stop=3, callback=cb, multi_gpu=mode, **kw), method=K.Krotov, comm=comm)
+        out.put((rank, hist["J_T"], hist["pulses"], hist["shard"], res.message, np.array(res.states), hist["tau"],
+                 E.OracleEngine.created))
+    finally:
+        dist.destroy_process_group()
+
+
+def _two_rank_workload(functional):
+    w = W.dummy_dense(d=8, n_traj=6, n_controls=2, n_grid=31, functional=functional, seed=21)
+    w.H0 = [w.H0[0], w.H0[0] * 1.2]  # two generators, three trajectories each: the shards are cut between them
+    w.Hc = [w.Hc[0], [w.Hc[0][0] * 0.8, w.Hc[0][1]]]
+    w.gen_of_traj = np.array([0, 0, 0, 1, 1, 1])
+    return w
+
+
+@pytest.mark.parametrize("functional,mode,use_sigma", [("sm", "shard", False), ("ss", "shard", True), ("re", "shard", False),
+                                                       ("sm", "replicate", True)])
+def test_gloo_world2_host_driver_matches_one_rank(functional, mode, use_sigma):
+    """optimize(problem, comm=Comm) on two CPU processes (gloo): sharding of the trajectories (`shard_bounds`, generator
+    runs stay together), the per-iteration gathers of tau and states, the global J_T_sm coefficient through
+    `set_chi_coeffs`, the second-order boundary condition per shard, replicas with identical pulses -- everything the
+    host does for several ranks, with the engines' arithmetic (and the per-step cross-rank sum of the overlaps, which the
+    CUDA kernels exchange over NVLink) done by the oracle-backed engine.  Against the one-process oracle run."""
+    import torch.multiprocessing as mp
+    from oracle import krotov_oracle as O
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_driver_worker, args=(r, 2, port, q, functional, mode, use_sigma)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=300) for _ in procs), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, J0, P0, s0, m0, st0, tau0, made0), (r1, J1, P1, s1, m1, st1, tau1, made1) = res
+    assert m0 == m1 == "Reached maximum number of iterations" and made0 == made1 == 1
+    assert (s0, s1) == (((0, 3), (3, 6)) if mode == "shard" else ((0, 6), (0, 6)))
+    assert J0 == J1 and np.array_equal(P0, P1) and np.array_equal(st0, st1) and np.array_equal(tau0, tau1)
+    ref = O.optimize_krotov(W.to_oracle(_two_rank_workload(functional)), 3,
+                            sigma=K.NumericalSigma(0.3, 0.05) if use_sigma else None)
+    assert np.abs(np.array(J0) - np.array(ref["J_T"])).max() < 1e-12
+    assert np.abs(P0 - ref["pulses"]).max() < 1e-12
+    assert np.abs(st0 - ref["states"]).max() < 1e-12 and np.abs(tau0 - ref["tau"][-1]).max() < 1e-12
