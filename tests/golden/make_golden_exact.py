@@ -1,0 +1,27 @@
+"""Golden vectors that do NOT come from the oracle: the two-level system of test/test_tls_optimization.jl:12-63 optimised
+in 50-digit arithmetic with the closed-form propagator of every interval (tests/mp_reference.py), first order and
+second order (sigma = -2).  30 significant digits are stored; Float64 readers round them.
+
+    python tests/golden/make_golden_exact.py"""
+import json
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+import mpmath as mp  # noqa: E402
+
+import mp_reference as M  # noqa: E402
+
+CASES = {"c1_tls_exact50": dict(iters=5), "c1_tls_sigma_exact50": dict(iters=3, sigma=-2.0)}
+
+for name, kw in CASES.items():
+    h = M.tls_krotov_exact(**kw)
+    out = {"source": "tests/mp_reference.py tls_krotov_exact(%s), mpmath dps=50" % ", ".join(f"{k}={v}" for k, v in kw.items()),
+           "J_T": [float(x) for x in h["J_T"]], "J_T_30_digits": [mp.nstr(x, 30) for x in h["J_T_mp"]],
+           "g_a_int": h["g_a_int"], "pulses": h["pulses"], **({"sigma": kw["sigma"]} if "sigma" in kw else {})}
+    with open(os.path.join(HERE, name + ".json"), "w") as fh:
+        json.dump(out, fh)
+    print(name, out["J_T_30_digits"])

@@ -36,3 +36,4 @@ test_c1_tls_parity_and_reference_inequalities = G.test_c1_tls_parity_and_referen
 test_dense_dummy_problems = G.test_dense_dummy_problems
 test_amplitude_argument_errors = G.test_amplitude_argument_errors
 test_edge_shapes = G.test_edge_shapes
+test_tls_against_the_committed_exact_vectors = G.test_tls_against_the_committed_exact_vectors

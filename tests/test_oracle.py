@@ -255,3 +255,19 @@ def test_numerical_estimate_of_A_vanishes_for_the_linear_functional():
         s = Rec()
         O.optimize_krotov(W.to_oracle(w), 3, sigma=s)
         assert len(s.A) == 3 and all(check(A) for A in s.A), s.A
+
+
+@pytest.mark.parametrize("name,iters,sigma", [("c1_tls_exact50", 5, None), ("c1_tls_sigma_exact50", 3, -2.0)])
+def test_oracles_reproduce_the_committed_exact_vectors(name, iters, sigma):
+    """tests/golden/*_exact50.json are NOT oracle output: they come from the 50-digit exact-propagator optimisation
+    (tests/golden/make_golden_exact.py).  The committed copy must equal a fresh run, and the oracles must meet it."""
+    import mp_reference as M
+
+    g = gold(name)
+    fresh = M.tls_krotov_exact(iters, **({} if sigma is None else {"sigma": sigma}))
+    assert fresh["J_T"] == g["J_T"] and fresh["pulses"] == g["pulses"]
+    p = W.to_oracle(W.c1_tls())
+    for method, tol in (("expm", 5e-14), ("cheby", 1e-12)):
+        h = O.optimize_krotov(p, iters, method, sigma=sigma)
+        assert np.abs(np.array(h["J_T"]) - np.array(g["J_T"])).max() < tol
+        assert np.abs(h["pulses"][0] - np.array(g["pulses"])).max() < tol

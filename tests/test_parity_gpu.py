@@ -1307,3 +1307,15 @@ def test_second_order_sigma_matches_general_formula_oracle(case):
     first = run_product(w, iters, **kw)
     assert np.abs(got["pulses"] - first["pulses"]).max() > 1e-4  # the second-order term matters in this case
     assert_parity(got, ref["J_T"], ref["pulses"], ref["g_a_int"])
+
+
+@pytest.mark.parametrize("name,iters,sigma", [("c1_tls_exact50", 5, None), ("c1_tls_sigma_exact50", 3, -2.0)])
+def test_tls_against_the_committed_exact_vectors(name, iters, sigma):
+    """The CUDA path against vectors that are NOT oracle output (50-digit exact-propagator optimisation,
+    tests/golden/make_golden_exact.py): first order and second order.  Two exact propagators differ by the truncation
+    level of the Chebyshev expansion (|a_m| <= 1e-12 per step): absolute 1e-12 in J_T and in the pulses."""
+    g = gold(name)
+    got = run_product(W.c1_tls(), iters, **({} if sigma is None else {"sigma": sigma}))
+    assert np.abs(np.array(got["J_T"]) - np.array(g["J_T"])).max() < 1e-12
+    assert np.abs(got["pulses"][0] - np.array(g["pulses"])).max() < 1e-12
+    assert np.abs(np.array([x[0] for x in got["g_a_int"]]) - np.array(g["g_a_int"])).max() < 1e-12
