@@ -1,6 +1,8 @@
 """Golden vectors that do NOT come from the oracle: the two-level system of test/test_tls_optimization.jl:12-63 optimised
 in 50-digit arithmetic with the closed-form propagator of every interval (tests/mp_reference.py), first order and
-second order (sigma = -2).  30 significant digits are stored; Float64 readers round them.
+second order (sigma = -2), 30 significant digits stored next to the Float64 values; and the general exact-propagator
+loop (mpmath.expm, 40 digits) on the small problems of mp_reference.exact_cases(): several trajectories / generators /
+controls, a missing control term, complex operators, the three functionals, a non-Hermitian generator.
 
     python tests/golden/make_golden_exact.py"""
 import json
@@ -25,3 +27,14 @@ for name, kw in CASES.items():
     with open(os.path.join(HERE, name + ".json"), "w") as fh:
         json.dump(out, fh)
     print(name, out["J_T_30_digits"])
+
+import workloads as W  # noqa: E402
+
+for name, (make, iters) in M.exact_cases().items():
+    h = M.krotov_exact_general(W.to_oracle(make()), iters)
+    out = {"source": f"tests/mp_reference.py krotov_exact_general(exact_cases()[{name!r}]), mpmath dps=40, mpmath.expm per interval",
+           "iters": iters, "J_T": h["J_T"], "g_a_int": h["g_a_int"], "pulses": h["pulses"],
+           "tau_re": [t.real for t in h["tau"]], "tau_im": [t.imag for t in h["tau"]]}
+    with open(os.path.join(HERE, name + "_exact40.json"), "w") as fh:
+        json.dump(out, fh)
+    print(name, out["J_T"])

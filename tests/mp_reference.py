@@ -134,3 +134,123 @@ def tls_krotov_exact(iters=5, n_grid=501, dps=50, float_grid=True, amp_poly=None
         J.append(1 - abs(tau) ** 2)
         ga_hist.append(ga)
     return dict(J_T=[float(x) for x in J], J_T_mp=J, g_a_int=[float(x) for x in ga_hist], pulses=[float(x) for x in eps])
+
+
+def krotov_exact_general(p, iters=2, dps=40):
+    """The Krotov loop of ``src/optimize.jl:279-371`` for ANY small problem in `dps`-digit arithmetic with the exact
+    propagator of every interval (``mpmath.expm``): several trajectories and generators, several controls, complex /
+    missing control operators, weights, non-uniform grids, non-Hermitian generators (the backward sweep uses the adjoint
+    generator), all three built-in functionals.  `p` is only the CONTAINER of the Float64 inputs (``W.to_oracle(w)``:
+    time grid, midpoint pulses, update shapes, lambda_a, matrices, states); none of its methods or of the oracle's code is
+    used.  Returns J_T per iteration, the running costs and the final pulses as floats."""
+    mp.mp.dps = dps
+    N, d, L, N_T = p.psi0.shape[0], p.psi0.shape[1], len(p.pulses), len(p.tlist) - 1
+    c = lambda z: mp.mpc(float(z.real), float(z.imag))  # noqa: E731
+    mat = lambda M: mp.matrix([[c(M[i, j]) for j in range(d)] for i in range(d)])  # noqa: E731
+    H0 = [mat(h) for h in p.H0]
+    Hc = [[None if h is None else mat(h) for h in row] for row in p.Hc]
+    gen = [int(g) for g in p.gen_of_traj]
+    psi0 = [mp.matrix([c(x) for x in p.psi0[k]]) for k in range(N)]
+    tgt = [mp.matrix([c(x) for x in p.target[k]]) for k in range(N)]
+    w = [mp.mpf(1)] * N if p.weight is None else [mp.mpf(float(x)) for x in p.weight]
+    dts = [mp.mpf(float(p.tlist[n + 1])) - mp.mpf(float(p.tlist[n])) for n in range(N_T)]
+    eps = [[mp.mpf(float(x)) for x in row] for row in p.pulses]
+    S = [[mp.mpf(float(x)) for x in row] for row in p.S]
+    lam = [mp.mpf(float(x)) for x in p.lam]
+    j = mp.mpc(0, 1)
+
+    def H(g, vals):
+        out = H0[g].copy()
+        for l in range(L):
+            if Hc[g][l] is not None:
+                out += vals[l] * Hc[g][l]
+        return out
+
+    def vdot(a, b):
+        return sum(mp.conj(a[i]) * b[i] for i in range(d))
+
+    def taus(states):
+        return [vdot(tgt[k], states[k]) for k in range(N)]
+
+    def J_of(tau):
+        if p.functional == "sm":
+            return 1 - abs(sum(w[k] * tau[k] for k in range(N)) / N) ** 2
+        if p.functional == "ss":
+            return 1 - sum(w[k] * abs(tau[k]) ** 2 for k in range(N)) / N
+        return 1 - mp.re(sum(w[k] * tau[k] for k in range(N))) / N
+
+    def chi_of(tau):  # chi_k = -dJ_T/d<psi_k|
+        if p.functional == "sm":
+            s = sum(w[k] * tau[k] for k in range(N))
+            return [(w[k] / N**2) * s * tgt[k] for k in range(N)]
+        if p.functional == "ss":
+            return [(w[k] / N) * tau[k] * tgt[k] for k in range(N)]
+        return [(w[k] / (2 * N)) * tgt[k] for k in range(N)]
+
+    gens = sorted(set(gen))
+    states = list(psi0)
+    for n in range(N_T):
+        U = {g: mp.expm(-j * dts[n] * H(g, [e[n] for e in eps])) for g in gens}
+        states = [U[gen[k]] * states[k] for k in range(N)]
+    tau = taus(states)
+    J, ga_hist = [J_of(tau)], []
+    for _ in range(iters):
+        chi = chi_of(tau)
+        X = [[None] * (N_T + 1) for _ in range(N)]
+        for k in range(N):
+            X[k][N_T] = chi[k]
+        for n in range(N_T - 1, -1, -1):  # backward with the adjoint generator under the GUESS pulses
+            Ub = {g: mp.expm(j * dts[n] * H(g, [e[n] for e in eps]).H) for g in gens}
+            for k in range(N):
+                X[k][n] = Ub[gen[k]] * X[k][n + 1]
+        new = [list(row) for row in eps]
+        ga = [mp.mpf(0)] * L
+        states = list(psi0)
+        for n in range(N_T):
+            for l in range(L):
+                du = mp.mpf(0)
+                for k in range(N):
+                    mu = Hc[gen[k]][l]
+                    if mu is not None:
+                        du += mp.im(vdot(X[k][n], mu * states[k]))
+                alpha = S[l][n] / lam[l]
+                new[l][n] = eps[l][n] + alpha * du
+                ga[l] += alpha * du * du * dts[n]
+            U = {g: mp.expm(-j * dts[n] * H(g, [e[n] for e in new])) for g in gens}
+            states = [U[gen[k]] * states[k] for k in range(N)]
+        eps = new
+        tau = taus(states)
+        J.append(J_of(tau))
+        ga_hist.append(ga)
+    return dict(J_T=[float(x) for x in J], g_a_int=[[float(x) for x in g] for g in ga_hist],
+                pulses=[[float(x) for x in row] for row in eps],
+                tau=[complex(float(mp.re(t)), float(mp.im(t))) for t in tau])
+
+
+def exact_cases():
+    """Small problems for ``krotov_exact_general``: name -> (workload factory, iterations).  Between them: several
+    trajectories, two generators, a control one generator does not depend on, complex control operators, two controls,
+    the three functionals, a non-Hermitian generator."""
+    import numpy as np
+
+    import workloads as W
+
+    def two_generators():
+        w = W.dummy_dense(d=5, n_traj=4, n_controls=2, n_grid=41, functional="ss", seed=31)
+        rng = np.random.default_rng(32)
+        A = rng.standard_normal((5, 5)) + 1j * rng.standard_normal((5, 5))
+        w.H0 = [w.H0[0], 0.4 * (A + A.conj().T)]
+        w.Hc = [w.Hc[0], [w.Hc[0][0] * 0.7, None]]
+        w.gen_of_traj = np.array([0, 1, 0, 1])
+        w.lambda_a = 0.2
+        return w
+
+    def non_hermitian():
+        w = W.dummy_dense(d=4, n_traj=3, n_controls=1, n_grid=41, functional="re", seed=33)
+        w.H0 = [w.H0[0] - 0.05j * np.diag(np.arange(4.0))]
+        w.lambda_a = 0.3
+        return w
+
+    return {"c2_transmon_x_g101": (lambda: W.c2_transmon_x(n_grid=101), 3),
+            "two_generators_d5": (two_generators, 2),
+            "non_hermitian_d4": (non_hermitian, 2)}

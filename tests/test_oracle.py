@@ -271,3 +271,27 @@ def test_oracles_reproduce_the_committed_exact_vectors(name, iters, sigma):
         h = O.optimize_krotov(p, iters, method, sigma=sigma)
         assert np.abs(np.array(h["J_T"]) - np.array(g["J_T"])).max() < tol
         assert np.abs(h["pulses"][0] - np.array(g["pulses"])).max() < tol
+
+
+@pytest.mark.parametrize("name", ["c2_transmon_x_g101", "two_generators_d5", "non_hermitian_d4"])
+def test_oracles_against_exact_propagator_vectors_of_general_problems(name):
+    """tests/golden/*_exact40.json: the Krotov loop in 40-digit arithmetic with `mpmath.expm` per interval
+    (tests/mp_reference.py `krotov_exact_general`, written independently of the oracles; made by make_golden_exact.py).
+    Pins, beyond the two-level system: the sum over several trajectories and the J_T_sm / J_T_ss / J_T_re boundary
+    conditions for N > 1, two generators, a control one generator does not depend on, complex control operators, two
+    controls updated in one time step -- and that the backward sweep of a NON-Hermitian generator runs with its
+    adjoint.  ExpProp oracle: rounding; Chebyshev oracles: the truncation level of the expansion."""
+    import mp_reference as M
+
+    make, iters = M.exact_cases()[name]
+    g = gold(name + "_exact40")
+    p = W.to_oracle(make())
+    runs = [(O.optimize_krotov(p, iters, "expm"), 5e-14), (O.optimize_krotov(p, iters, "cheby"), 1e-12),
+            (C.optimize_krotov_c(p, iters), 1e-12)]
+    for h, tol in runs:
+        assert np.abs(np.array(h["J_T"]) - np.array(g["J_T"])).max() < tol
+        assert np.abs(np.asarray(h["pulses"]) - np.array(g["pulses"])).max() < tol
+        assert np.abs(np.array(h["g_a_int"]) - np.array(g["g_a_int"])).max() < tol
+    if name == "non_hermitian_d4":  # the committed vector is what a fresh 40-digit run gives (the cheapest case: ~4 s)
+        fresh = M.krotov_exact_general(p, iters)
+        assert fresh["J_T"] == g["J_T"] and fresh["pulses"] == g["pulses"]

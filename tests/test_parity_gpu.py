@@ -1319,3 +1319,19 @@ def test_tls_against_the_committed_exact_vectors(name, iters, sigma):
     assert np.abs(np.array(got["J_T"]) - np.array(g["J_T"])).max() < 1e-12
     assert np.abs(got["pulses"][0] - np.array(g["pulses"])).max() < 1e-12
     assert np.abs(np.array([x[0] for x in got["g_a_int"]]) - np.array(g["g_a_int"])).max() < 1e-12
+
+
+@pytest.mark.parametrize("name", ["c2_transmon_x_g101", "two_generators_d5", "non_hermitian_d4"])
+def test_against_exact_propagator_vectors_of_general_problems(name):
+    """The CUDA path against the 40-digit exact-propagator vectors (NOT oracle output; see tests/test_oracle.py
+    test_oracles_against_exact_propagator_vectors_of_general_problems): several trajectories and generators, a missing
+    control term, complex operators, two controls, all three functionals, a non-Hermitian generator."""
+    import mp_reference as M
+
+    make, iters = M.exact_cases()[name]
+    g = gold(name + "_exact40")
+    got = run_product(make(), iters)
+    assert np.abs(np.array(got["J_T"]) - np.array(g["J_T"])).max() < 1e-12
+    assert np.abs(got["pulses"] - np.array(g["pulses"])).max() < 1e-12
+    assert np.abs(np.array(got["g_a_int"]) - np.array(g["g_a_int"])).max() < 1e-12
+    assert np.abs(got["tau"][-1] - (np.array(g["tau_re"]) + 1j * np.array(g["tau_im"]))).max() < 1e-12
