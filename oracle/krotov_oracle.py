@@ -12,6 +12,9 @@ numeric golden vector for this path (only the inequalities of
 arithmetic the reference delegates to QuantumPropagators.jl / QuantumControl.jl
 (un-vendored, compat ``QuantumControl >= 0.11.1``, ``Project.toml:19``; no
 Manifest) is restated from its published algorithm.
+What does pin the LOOP restated here independently of this file: ``tests/mp_reference.py`` (the same loop in 40-50
+digit arithmetic with exact interval propagators, on the reference's two-level test problem and on small general
+problems incl. several trajectories / generators / controls and a non-Hermitian generator); see DESIGN.md section 2.
 
 What is restated, with the reference lines each function follows:
 
