@@ -1335,3 +1335,82 @@ def test_against_exact_propagator_vectors_of_general_problems(name):
     assert np.abs(got["pulses"] - np.array(g["pulses"])).max() < 1e-12
     assert np.abs(np.array(got["g_a_int"]) - np.array(g["g_a_int"])).max() < 1e-12
     assert np.abs(got["tau"][-1] - (np.array(g["tau_re"]) + 1j * np.array(g["tau_im"]))).max() < 1e-12
+
+
+# ---- seeded sweep over the WAYS a problem can be written (the host translation layer) ------------------------------------------
+@pytest.mark.parametrize("seed", range(10))
+def test_seeded_api_variants_vs_oracle(seed):
+    """The same numbers handed to the oracle as plain arrays and to `optimize` through randomly chosen API forms:
+    controls as functions / midpoint vectors / on-grid vectors, global `lambda_a` + `update_shape` or a per-control
+    `pulse_options` dict (``src/workspace.jl:77-106``), trajectory weights, equal generators given as ONE shared
+    object or as separate objects, keyword arguments on the problem or overriding at `optimize`
+    (``src/optimize.jl:60-62``), uniform or two-step time grids, a user `chi` instead of the analytic one."""
+    from oracle import krotov_oracle as O
+
+    rng = np.random.default_rng(7000 + seed)
+    d, N, L = int(rng.integers(2, 9)), int(rng.integers(1, 6)), int(rng.integers(1, 4))
+    n_grid = int(rng.integers(6, 30))
+    functional = str(rng.choice(["sm", "ss", "re"]))
+    w = W.dummy_dense(d=d, n_traj=N, n_controls=L, n_grid=n_grid, functional=functional, seed=int(rng.integers(1, 10**6)))
+    if rng.random() < 0.5:  # two dt classes
+        k = n_grid // 2
+        w.tlist = np.concatenate([np.linspace(0.0, 1.0, k + 1)[:-1], np.linspace(1.0, 2.7, n_grid - k)])
+    t = np.asarray(w.tlist, float)
+    T = float(t[-1])
+    # ---- the oracle's side: plain arrays
+    mids = np.array([W.midpoint_samples(c, t) for c in w.controls])
+    lam = rng.uniform(0.3, 3.0, L)
+    shapes = [(lambda x, r=float(rng.uniform(0.1, 0.4) * T): W.flattop(x, T=T, t_rise=r)) if rng.random() < 0.6 else (lambda x: 1.0)
+              for _ in range(L)]
+    per_control = bool(rng.random() < 0.5) or L == 1
+    if not per_control:  # one global setting
+        lam[:] = lam[0]
+        shapes = [shapes[0]] * L
+    weights = rng.uniform(0.5, 2.0, N) if rng.random() < 0.5 else np.ones(N)
+    p = W.to_oracle(w)
+    p.pulses, p.lam, p.weight = mids.copy(), lam.copy(), weights.copy()
+    p.S = np.array([W.midpoint_samples(s, t) for s in shapes])
+    ref = O.optimize_krotov(p, 2)
+    # ---- the product's side: API forms
+    forms = [str(rng.choice(["function", "midpoints", "grid"])) for _ in range(L)]
+    controls = []
+    for l, form in enumerate(forms):
+        if form == "function":
+            controls.append(w.controls[l])
+        elif form == "midpoints":
+            controls.append(mids[l].copy())
+        else:  # on the grid points: `discretize_on_midpoints` must invert `discretize` exactly
+            controls.append(O.discretize(mids[l], t))
+    shared = bool(rng.random() < 0.5)
+    gens = [K.hamiltonian(w.H0[0], *[(w.Hc[0][l], controls[l]) for l in range(L)]) for _ in range(1 if shared else N)]
+    trajs = [K.Trajectory(w.psi0[k], gens[0 if shared else k], target_state=w.target[k], weight=float(weights[k]))
+             for k in range(N)]
+    hist = dict(J_T=[], g=[])
+
+    def cb(wrk, it, eps_new, eps_old):
+        hist["J_T"].append(wrk.result.J_T)
+        hist["pulses"] = np.array([np.array(e) for e in eps_new])
+        if it > 0:
+            hist["g"].append(np.array(wrk.g_a_int))
+
+    JT = {"sm": K.J_T_sm, "ss": K.J_T_ss, "re": K.J_T_re}[functional]
+    kw = dict(prop_method=K.Cheby, J_T=JT, print_iters=False, callback=cb, iter_stop=2)
+    if per_control:
+        ctr = K.get_controls(trajs)
+        assert len(ctr) == L
+        kw["pulse_options"] = K.IdDict([(ctr[l], {"lambda_a": float(lam[l]), "update_shape": shapes[l]}) for l in range(L)])
+    else:
+        kw.update(lambda_a=float(lam[0]), update_shape=shapes[0])
+    if rng.random() < 0.4:
+        kw["chi"] = {"sm": K.chi_sm, "ss": K.chi_ss, "re": K.chi_re}[functional]  # (explicit: the analytic one, tagged)
+    elif rng.random() < 0.4:
+        base = {"sm": K.chi_sm, "ss": K.chi_ss, "re": K.chi_re}[functional]
+        kw["chi"] = lambda Psi, trajectories, tau=None: base(Psi, trajectories, tau=tau)  # (a user function: host path)
+    override = {}
+    if rng.random() < 0.5:  # a keyword given to `optimize` wins over the problem's
+        override = dict(iter_stop=kw.pop("iter_stop"))
+        kw["iter_stop"] = 7
+    K.optimize(K.ControlProblem(trajs, t, **kw), method=K.Krotov, **override)
+    assert len(hist["J_T"]) == 3
+    got = dict(J_T=hist["J_T"], pulses=hist["pulses"], g_a_int=hist["g"])
+    assert_parity(got, ref["J_T"], ref["pulses"], ref["g_a_int"])
