@@ -673,3 +673,41 @@ def test_gloo_world2_host_driver_matches_one_rank(functional, mode, use_sigma):
     assert np.abs(np.array(J0) - np.array(ref["J_T"])).max() < 1e-12
     assert np.abs(P0 - ref["pulses"]).max() < 1e-12
     assert np.abs(st0 - ref["states"]).max() < 1e-12 and np.abs(tau0 - ref["tau"][-1]).max() < 1e-12
+
+
+def test_committed_bench_lines_follow_the_contract():
+    """The JSON lines bench.py printed on the B200 boxes (committed under profiles/) carry every key of the bench
+    contract, and their derived numbers are consistent with one another."""
+    import json
+
+    for name, n in (("r2_bench_c4_1gpu_final.json", 1), ("r2_bench_c4_2gpu_replicate.json", 2),
+                    ("r2_bench_c4_8gpu_replicate.json", 8)):
+        with open(os.path.join(ROOT, "profiles", name)) as fh:
+            d = json.load(fh)
+        for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                    "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline"):
+            assert key in d, (name, key)
+        assert d["n_gpus"] == n and d["warmup"] >= 3 and d["dtype"] == "f64" and d["data"] == "synthetic"
+        assert d["vs_baseline"] is None  # BASELINE.md holds no published number for this metric
+        assert "workload" in d["config"] and "model" not in d["config"]
+        for key in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+            assert key in d["e2e"]
+        assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+        assert 0 < d["e2e"]["value"] < d["value"]  # end to end includes what the device-timed value does not
+        assert d["gpu_launches"] >= d["steps"]
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        r = d["roofline"]
+        for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+            assert key in r
+        assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and 0 < r["frac"] < 1
+        # value = whole-job state-timesteps over the device time of the timed iterations
+        st = 2 * 1024 * 2000
+        assert abs(d["value"] - st / (d["ms_per_step"] * 1e-3)) / d["value"] < 1e-9
+        if n == 1:
+            c = d["cpu_baseline"]
+            for key in ("value", "unit", "cores", "kind", "sample"):
+                assert key in c
+            assert c["kind"] == "port" and c["cores"] > 1
+            assert abs(r["achieved"] - r["algorithmic_bytes_per_launch"] / (d["ms_per_step"] * 1e-3) / 1e9) / r["achieved"] < 1e-9
+            t5 = d["extra_configs"]["C5 dense d=4096 N=64, N_T=20 of 10000 (every step costs the same)"]["roofline_fp64_tensor"]
+            assert abs(t5["frac"] - t5["achieved"] / t5["peak"]) < 1e-12 and t5["frac"] < 1
