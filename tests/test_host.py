@@ -470,9 +470,12 @@ def test_julia_sources_have_balanced_blocks():
     slip in an edit: every block opener (function / if / for / while / begin / let / try / struct / module / do) outside
     brackets has its `end`, brackets balance, and `end` inside an index expression is not counted."""
     openers = {"function", "if", "for", "while", "begin", "let", "try", "struct", "module", "do", "quote", "macro"}
-    folder = os.path.join(ROOT, "julia", "Krotov", "src")
-    for name in sorted(os.listdir(folder)):
-        s = _jl_strip(open(os.path.join(folder, name), encoding="utf-8").read())
+    files = [os.path.join(ROOT, "julia", "Krotov", sub, f) for sub in ("src", "test")
+             for f in sorted(os.listdir(os.path.join(ROOT, "julia", "Krotov", sub)))]
+    assert len(files) >= 6
+    for path in files:
+        name = os.path.relpath(path, ROOT)
+        s = _jl_strip(open(path, encoding="utf-8").read())
         stack, par, sq, line = [], 0, 0, 1
         for m in re.finditer(r"\n|[\[\]\(\)]|:?[^\W\d]\w*!?", s):
             t = m.group(0)
