@@ -38,3 +38,17 @@ for name, (make, iters) in M.exact_cases().items():
     with open(os.path.join(HERE, name + "_exact40.json"), "w") as fh:
         json.dump(out, fh)
     print(name, out["J_T"])
+
+# second order with a sigma that varies over the grid, on a non-Hermitian generator and on two generators: the GENERAL
+# update (previous trajectory stored), which the oracle implements and the device path refuses
+for name in ("non_hermitian_d4", "two_generators_d5"):
+    make, iters = M.exact_cases()[name]
+    p = W.to_oracle(make())
+    mids = [float(p.tlist[0])] + [float(p.tlist[i] + 0.5 * (p.tlist[i + 1] - p.tlist[i])) for i in range(1, len(p.tlist) - 2)] + [float(p.tlist[-1])]
+    sigma = [-0.6 - 0.3 * t for t in mids]
+    h = M.krotov_exact_general(p, iters, sigma=sigma)
+    out = {"source": f"krotov_exact_general(exact_cases()[{name!r}], sigma(t) = -0.6 - 0.3 t on the midpoints), mpmath dps=40",
+           "iters": iters, "sigma": sigma, "J_T": h["J_T"], "g_a_int": h["g_a_int"], "pulses": h["pulses"]}
+    with open(os.path.join(HERE, name + "_sigma_exact40.json"), "w") as fh:
+        json.dump(out, fh)
+    print(name, "sigma(t)", out["J_T"])

@@ -136,13 +136,16 @@ def tls_krotov_exact(iters=5, n_grid=501, dps=50, float_grid=True, amp_poly=None
     return dict(J_T=[float(x) for x in J], J_T_mp=J, g_a_int=[float(x) for x in ga_hist], pulses=[float(x) for x in eps])
 
 
-def krotov_exact_general(p, iters=2, dps=40):
+def krotov_exact_general(p, iters=2, dps=40, sigma=None):
     """The Krotov loop of ``src/optimize.jl:279-371`` for ANY small problem in `dps`-digit arithmetic with the exact
     propagator of every interval (``mpmath.expm``): several trajectories and generators, several controls, complex /
     missing control operators, weights, non-uniform grids, non-Hermitian generators (the backward sweep uses the adjoint
     generator), all three built-in functionals.  `p` is only the CONTAINER of the Float64 inputs (``W.to_oracle(w)``:
     time grid, midpoint pulses, update shapes, lambda_a, matrices, states); none of its methods or of the oracle's code is
-    used.  Returns J_T per iteration, the running costs and the final pulses as floats."""
+    used.  Returns J_T per iteration, the running costs and the final pulses as floats.
+
+    sigma: None | one number per time interval -- second-order update, the overlap of interval n gains
+    (sigma_n / 2) <psi_new(t_n) - psi_old(t_n)| mu |psi_new(t_n)> (any generator, any sigma(t): the general formula)."""
     mp.mp.dps = dps
     N, d, L, N_T = p.psi0.shape[0], p.psi0.shape[1], len(p.pulses), len(p.tlist) - 1
     c = lambda z: mp.mpc(float(z.real), float(z.imag))  # noqa: E731
@@ -188,10 +191,16 @@ def krotov_exact_general(p, iters=2, dps=40):
         return [(w[k] / (2 * N)) * tgt[k] for k in range(N)]
 
     gens = sorted(set(gen))
+    sig = None if sigma is None else [mp.mpf(float(x)) for x in sigma]
     states = list(psi0)
+    old = [[None] * (N_T + 1) for _ in range(N)]  # psi_k^(i)(t_n): the previous iteration's forward trajectory
     for n in range(N_T):
+        for k in range(N):
+            old[k][n] = states[k]
         U = {g: mp.expm(-j * dts[n] * H(g, [e[n] for e in eps])) for g in gens}
         states = [U[gen[k]] * states[k] for k in range(N)]
+    for k in range(N):
+        old[k][N_T] = states[k]
     tau = taus(states)
     J, ga_hist = [J_of(tau)], []
     for _ in range(iters):
@@ -212,12 +221,19 @@ def krotov_exact_general(p, iters=2, dps=40):
                 for k in range(N):
                     mu = Hc[gen[k]][l]
                     if mu is not None:
-                        du += mp.im(vdot(X[k][n], mu * states[k]))
+                        ov = vdot(X[k][n], mu * states[k])
+                        if sig is not None:
+                            ov += sig[n] / 2 * vdot(states[k] - old[k][n], mu * states[k])
+                        du += mp.im(ov)
                 alpha = S[l][n] / lam[l]
                 new[l][n] = eps[l][n] + alpha * du
                 ga[l] += alpha * du * du * dts[n]
+            for k in range(N):
+                old[k][n] = states[k]  # (slot n is not read again in this iteration)
             U = {g: mp.expm(-j * dts[n] * H(g, [e[n] for e in new])) for g in gens}
             states = [U[gen[k]] * states[k] for k in range(N)]
+        for k in range(N):
+            old[k][N_T] = states[k]
         eps = new
         tau = taus(states)
         J.append(J_of(tau))

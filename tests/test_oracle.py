@@ -295,3 +295,25 @@ def test_oracles_against_exact_propagator_vectors_of_general_problems(name):
     if name == "non_hermitian_d4":  # the committed vector is what a fresh 40-digit run gives (the cheapest case: ~4 s)
         fresh = M.krotov_exact_general(p, iters)
         assert fresh["J_T"] == g["J_T"] and fresh["pulses"] == g["pulses"]
+
+
+@pytest.mark.parametrize("name", ["non_hermitian_d4", "two_generators_d5"])
+def test_general_second_order_oracle_against_exact_propagator_vectors(name):
+    """The oracle's GENERAL second-order update (sigma varying over the grid, a non-Hermitian generator, several
+    trajectories and controls; previous trajectory stored) against the 40-digit exact-propagator loop with the same
+    term written independently (tests/golden/*_sigma_exact40.json).  This is the formula the device path's boundary-
+    condition fold is tested against in its domain of validity (Hermitian generators, constant sigma)."""
+    import mp_reference as M
+
+    make, iters = M.exact_cases()[name]
+    g = gold(name + "_sigma_exact40")
+    p = W.to_oracle(make())
+    sv = O.sigma_on_intervals(lambda t: -0.6 - 0.3 * t, p.tlist)
+    assert np.abs(sv - np.array(g["sigma"])).max() < 1e-15
+    for method, tol in (("expm", 5e-14), ("cheby", 1e-12)):
+        h = O.optimize_krotov(W.to_oracle(make()), iters, method, sigma=lambda t: -0.6 - 0.3 * t)
+        assert np.abs(np.array(h["J_T"]) - np.array(g["J_T"])).max() < tol
+        assert np.abs(h["pulses"] - np.array(g["pulses"])).max() < tol
+        assert np.abs(np.array(h["g_a_int"]) - np.array(g["g_a_int"])).max() < tol
+    first = gold(name + "_exact40")
+    assert abs(first["J_T"][-1] - g["J_T"][-1]) > 1e-3
