@@ -659,7 +659,7 @@ def test_gloo_world2_host_driver_matches_one_rank(functional, mode, use_sigma):
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 31500 + os.getpid() % 2000
+    port = 31500 + (os.getpid() + 37 * ["sm", "ss", "re"].index(functional) + 211 * use_sigma + 503 * (mode == "replicate")) % 2000
     procs = [ctx.Process(target=_gloo_driver_worker, args=(r, 2, port, q, functional, mode, use_sigma)) for r in range(2)]
     for p in procs:
         p.start()
