@@ -52,3 +52,13 @@ for name in ("non_hermitian_d4", "two_generators_d5"):
     with open(os.path.join(HERE, name + "_sigma_exact40.json"), "w") as fh:
         json.dump(out, fh)
     print(name, "sigma(t)", out["J_T"])
+
+if "--c3" in sys.argv:  # 4.5 minutes: mpmath.expm on 25 x 25 matrices, 30 digits
+    w = W.c3_two_transmon(n_grid=41, T=8.0)
+    h = M.krotov_exact_general(W.to_oracle(w), 2, dps=30)
+    out = {"source": "tests/mp_reference.py krotov_exact_general(W.c3_two_transmon(n_grid=41, T=8.0)), mpmath dps=30, mpmath.expm per interval",
+           "iters": 2, "J_T": h["J_T"], "g_a_int": h["g_a_int"], "pulses": h["pulses"],
+           "tau_re": [t.real for t in h["tau"]], "tau_im": [t.imag for t in h["tau"]]}
+    with open(os.path.join(HERE, "c3_two_transmon_g41_exact30.json"), "w") as fh:
+        json.dump(out, fh)
+    print("c3_two_transmon_g41", out["J_T"])

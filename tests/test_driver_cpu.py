@@ -39,3 +39,4 @@ test_edge_shapes = G.test_edge_shapes
 test_tls_against_the_committed_exact_vectors = G.test_tls_against_the_committed_exact_vectors
 test_against_exact_propagator_vectors_of_general_problems = G.test_against_exact_propagator_vectors_of_general_problems
 test_seeded_api_variants_vs_oracle = G.test_seeded_api_variants_vs_oracle
+test_two_transmon_problem_against_exact_propagator_vector = G.test_two_transmon_problem_against_exact_propagator_vector

@@ -371,3 +371,17 @@ def test_oracles_against_reference_run_vectors(name):
         ref = np.array(g["J_T"])
         assert np.all(np.abs(np.array(h["J_T"]) - ref) <= 1e-10 * np.abs(ref) + 5e-13)
         assert np.abs(np.asarray(h["pulses"]) - np.array(g["pulses"])).max() <= 1e-9
+
+
+def test_oracles_against_exact_propagator_vector_of_the_two_transmon_problem():
+    """C3's generator (two 5-level transmons, d = 25, two controls of which one starts at zero, 4 logical-basis
+    trajectories, J_T_sm) on a 40-step grid with C3's time step: tests/golden/c3_two_transmon_g41_exact30.json from the
+    30-digit exact-propagator loop (mpmath.expm on 25 x 25 matrices; 4.5 minutes to make, tests/golden/make_golden_exact.py
+    --c3)."""
+    g = gold("c3_two_transmon_g41_exact30")
+    make = lambda: W.to_oracle(W.c3_two_transmon(n_grid=41, T=8.0))  # noqa: E731
+    for h, tol in ((O.optimize_krotov(make(), 2, "expm"), 5e-14), (O.optimize_krotov(make(), 2, "cheby"), 1e-12),
+                   (C.optimize_krotov_c(make(), 2), 1e-12)):
+        assert np.abs(np.array(h["J_T"]) - np.array(g["J_T"])).max() < tol
+        assert np.abs(np.asarray(h["pulses"]) - np.array(g["pulses"])).max() < tol
+        assert np.abs(np.array(h["g_a_int"]) - np.array(g["g_a_int"])).max() < tol

@@ -1437,3 +1437,14 @@ def test_cuda_path_against_reference_run_vectors(name):
     make, iters = X.CASES[name]
     got = run_product(make(), iters)
     assert_parity(got, g["J_T"], g["pulses"], g.get("g_a_int"), atol=5e-13)  # (floor of two Chebyshev implementations)
+
+
+def test_two_transmon_problem_against_exact_propagator_vector():
+    """The warp kernel on C3's generator (d = 25, two controls, 4 trajectories; 40 steps of C3's time step) against the
+    30-digit exact-propagator loop (NOT oracle output; the oracles agree with it to 2.4e-14)."""
+    g = gold("c3_two_transmon_g41_exact30")
+    got = run_product(W.c3_two_transmon(n_grid=41, T=8.0), 2)
+    assert np.abs(np.array(got["J_T"]) - np.array(g["J_T"])).max() < 1e-12
+    assert np.abs(got["pulses"] - np.array(g["pulses"])).max() < 1e-12
+    assert np.abs(np.array(got["g_a_int"]) - np.array(g["g_a_int"])).max() < 1e-12
+    assert np.abs(got["tau"][-1] - (np.array(g["tau_re"]) + 1j * np.array(g["tau_im"]))).max() < 1e-12
