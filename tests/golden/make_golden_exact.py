@@ -31,6 +31,8 @@ for name, kw in CASES.items():
 import workloads as W  # noqa: E402
 
 for name, (make, iters) in M.exact_cases().items():
+    if "--only-new" in sys.argv and os.path.exists(os.path.join(HERE, name + "_exact40.json")):
+        continue
     h = M.krotov_exact_general(W.to_oracle(make()), iters)
     out = {"source": f"tests/mp_reference.py krotov_exact_general(exact_cases()[{name!r}]), mpmath dps=40, mpmath.expm per interval",
            "iters": iters, "J_T": h["J_T"], "g_a_int": h["g_a_int"], "pulses": h["pulses"],

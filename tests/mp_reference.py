@@ -192,12 +192,25 @@ def krotov_exact_general(p, iters=2, dps=40, sigma=None):
 
     gens = sorted(set(gen))
     sig = None if sigma is None else [mp.mpf(float(x)) for x in sigma]
+    # non-linear amplitudes (data fields of the container only): control l enters as shape_l[n] * sum_q c_lq eps^q;
+    # mu_l = dH/d eps_l is taken at the GUESS value of the interval (src/optimize.jl:337)
+    poly = None if p.amp_poly is None else [None if c is None else [mp.mpf(float(x)) for x in c] for c in p.amp_poly]
+    ashape = None if p.amp_shape is None else [[mp.mpf(float(x)) for x in row] for row in p.amp_shape]
+
+    def amp(l, n, e):
+        v = e if poly is None or poly[l] is None else sum(cq * e**q for q, cq in enumerate(poly[l]))
+        return v if ashape is None else ashape[l][n] * v
+
+    def damp(l, n, e):
+        v = mp.mpf(1) if poly is None or poly[l] is None else sum(q * cq * e ** (q - 1) for q, cq in enumerate(poly[l]) if q > 0)
+        return v if ashape is None else ashape[l][n] * v
+
     states = list(psi0)
     old = [[None] * (N_T + 1) for _ in range(N)]  # psi_k^(i)(t_n): the previous iteration's forward trajectory
     for n in range(N_T):
         for k in range(N):
             old[k][n] = states[k]
-        U = {g: mp.expm(-j * dts[n] * H(g, [e[n] for e in eps])) for g in gens}
+        U = {g: mp.expm(-j * dts[n] * H(g, [amp(l, n, eps[l][n]) for l in range(L)])) for g in gens}
         states = [U[gen[k]] * states[k] for k in range(N)]
     for k in range(N):
         old[k][N_T] = states[k]
@@ -209,7 +222,7 @@ def krotov_exact_general(p, iters=2, dps=40, sigma=None):
         for k in range(N):
             X[k][N_T] = chi[k]
         for n in range(N_T - 1, -1, -1):  # backward with the adjoint generator under the GUESS pulses
-            Ub = {g: mp.expm(j * dts[n] * H(g, [e[n] for e in eps]).H) for g in gens}
+            Ub = {g: mp.expm(j * dts[n] * H(g, [amp(l, n, eps[l][n]) for l in range(L)]).H) for g in gens}
             for k in range(N):
                 X[k][n] = Ub[gen[k]] * X[k][n + 1]
         new = [list(row) for row in eps]
@@ -224,13 +237,13 @@ def krotov_exact_general(p, iters=2, dps=40, sigma=None):
                         ov = vdot(X[k][n], mu * states[k])
                         if sig is not None:
                             ov += sig[n] / 2 * vdot(states[k] - old[k][n], mu * states[k])
-                        du += mp.im(ov)
+                        du += mp.im(damp(l, n, eps[l][n]) * ov)
                 alpha = S[l][n] / lam[l]
                 new[l][n] = eps[l][n] + alpha * du
                 ga[l] += alpha * du * du * dts[n]
             for k in range(N):
                 old[k][n] = states[k]  # (slot n is not read again in this iteration)
-            U = {g: mp.expm(-j * dts[n] * H(g, [e[n] for e in new])) for g in gens}
+            U = {g: mp.expm(-j * dts[n] * H(g, [amp(l, n, new[l][n]) for l in range(L)])) for g in gens}
             states = [U[gen[k]] * states[k] for k in range(N)]
         for k in range(N):
             old[k][N_T] = states[k]
@@ -267,6 +280,13 @@ def exact_cases():
         w.lambda_a = 0.3
         return w
 
+    def nonlinear():
+        w = two_generators()
+        w.amp_poly = [[0.0, 1.0, 0.4], None]  # control 0 enters as eps + 0.4 eps^2
+        w.amp_shape = [None, lambda t: 0.5 + 0.25 * t]  # control 1 as shape(t) * eps
+        return w
+
     return {"c2_transmon_x_g101": (lambda: W.c2_transmon_x(n_grid=101), 3),
+            "nonlinear_two_generators_d5": (nonlinear, 2),
             "two_generators_d5": (two_generators, 2),
             "non_hermitian_d4": (non_hermitian, 2)}

@@ -40,3 +40,10 @@ test_tls_against_the_committed_exact_vectors = G.test_tls_against_the_committed_
 test_against_exact_propagator_vectors_of_general_problems = G.test_against_exact_propagator_vectors_of_general_problems
 test_seeded_api_variants_vs_oracle = G.test_seeded_api_variants_vs_oracle
 test_two_transmon_problem_against_exact_propagator_vector = G.test_two_transmon_problem_against_exact_propagator_vector
+
+
+def test_nonlinear_amplitudes_through_the_api_against_exact_vector():
+    """PolynomialAmplitude / ShapedAmplitude through the product's host path (amplitude collection, `set_amplitudes`)
+    against the 40-digit exact-propagator vector of the two-generator problem with a quadratic and a shaped amplitude.
+    (CPU engine only: the GPU list of this test was fixed before this vector existed.)"""
+    G.test_against_exact_propagator_vectors_of_general_problems("nonlinear_two_generators_d5")

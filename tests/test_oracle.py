@@ -273,14 +273,14 @@ def test_oracles_reproduce_the_committed_exact_vectors(name, iters, sigma):
         assert np.abs(h["pulses"][0] - np.array(g["pulses"])).max() < tol
 
 
-@pytest.mark.parametrize("name", ["c2_transmon_x_g101", "two_generators_d5", "non_hermitian_d4"])
+@pytest.mark.parametrize("name", ["c2_transmon_x_g101", "two_generators_d5", "non_hermitian_d4", "nonlinear_two_generators_d5"])
 def test_oracles_against_exact_propagator_vectors_of_general_problems(name):
     """tests/golden/*_exact40.json: the Krotov loop in 40-digit arithmetic with `mpmath.expm` per interval
     (tests/mp_reference.py `krotov_exact_general`, written independently of the oracles; made by make_golden_exact.py).
     Pins, beyond the two-level system: the sum over several trajectories and the J_T_sm / J_T_ss / J_T_re boundary
     conditions for N > 1, two generators, a control one generator does not depend on, complex control operators, two
-    controls updated in one time step -- and that the backward sweep of a NON-Hermitian generator runs with its
-    adjoint.  ExpProp oracle: rounding; Chebyshev oracles: the truncation level of the expansion."""
+    controls updated in one time step, non-linear amplitudes (a quadratic and a shaped one; mu = a'(eps_guess) H_l)
+    on two generators -- and that the backward sweep of a NON-Hermitian generator runs with its adjoint.  ExpProp oracle: rounding; Chebyshev oracles: the truncation level of the expansion."""
     import mp_reference as M
 
     make, iters = M.exact_cases()[name]
