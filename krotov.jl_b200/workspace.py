@@ -286,15 +286,16 @@ class KrotovWrk:
         self.fw_storage2 = None  # never read or written by the reference (src/workspace.jl:129-130)
         # second order (`sigma`, src/optimize.jl:104-105; TODOs :187, :350, :369): see second_order.py
         self.sigma = kwargs.get("sigma", None)
-        self._build_device_side(tlist, comm)
         if self.sigma is not None:
-            if not self._hermitian:
-                raise ArgumentError("`sigma` (second-order Krotov) needs Hermitian generators and control operators: "
-                                    "the device path folds the second-order term into the boundary condition chi(T)")
             if kwargs.get("skip_initial_forward_propagation", False):
                 raise ArgumentError("`sigma` needs the forward states of the guess pulses: it cannot be combined with "
                                     "`skip_initial_forward_propagation`")
             sigma_value(self.sigma, tlist)  # (raises for a sigma that varies over the time grid)
+        self._build_device_side(tlist, comm)
+        if self.sigma is not None and not self._hermitian:
+            self.engine.close()
+            raise ArgumentError("`sigma` (second-order Krotov) needs Hermitian generators and control operators: "
+                                "the device path folds the second-order term into the boundary condition chi(T)")
         self.fw_storage = _Storage(self, B.FORWARD)
         self.bw_storage = _Storage(self, B.BACKWARD)
         self.fw_propagators = [_PropagatorView(self, k, False) for k in range(N)]
